@@ -1,0 +1,151 @@
+"""TEST INFRASTRUCTURE (oracle) -- CPU restatement of the reference's hot path.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this package. It is the checker, never the product: the product path is
+``performance-test_b200`` (CUDA, no CPU fallback).
+
+parity unpinned: FEniCS/performance-test has no golden vectors / KATs for this path and cannot be
+built or imported here; see oracle.c's header for what is restated from where.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import tables as _tables
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_libs = {}
+_tab_cache = {}
+
+
+def build():
+    r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+
+
+def _lib(fast=False):
+    key = "fast" if fast else "strict"
+    if key not in _libs:
+        path = os.path.join(_HERE, "_build", "liboracle_fast.so" if fast else "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_max_threads.restype = C.c_int
+        L.orc_cg.restype = C.c_int
+        _libs[key] = L
+    return _libs[key]
+
+
+def max_threads():
+    return _lib().orc_max_threads()
+
+
+def element_tables(order):
+    if order not in _tab_cache:
+        _tab_cache[order] = _tables.element_tables(order)
+    return _tab_cache[order]
+
+
+def _p(a, dtype):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=dtype)
+    return a, a.ctypes.data_as(C.c_void_p)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+PROBLEMS = {"poisson": 0, "cgpoisson": 0, "elasticity": 1}
+
+
+def bc_marker(P):
+    m = np.zeros(P.n_owned + P.n_ghost, dtype=np.int8)
+    m[P["bc_dofs"]] = 1
+    return m
+
+
+def assemble_matrix(P, slot=None, nthreads=1, fast=False, set_diagonal=True):
+    """ZZZ Assemble matrix (src/poisson_problem.cpp:125-139). Returns block-CSR values
+    [nnz*bs*bs] on the pattern P['rowptr'], P['cols'] (owned rows)."""
+    T = element_tables(P.order)
+    bs = P.bs
+    x = _arr(P["x"], np.float64)
+    xd = _arr(P["x_dofmap"], np.int32)
+    dm = _arr(P["dofmap"], np.int32)
+    rp = _arr(P["rowptr"], np.int64)
+    cl = _arr(P["cols"], np.int32)
+    bcd = _arr(P["bc_dofs"], np.int32)
+    mk = bc_marker(P)
+    vals = np.zeros(len(cl) * bs * bs, dtype=np.float64)
+    sl = None if slot is None else _arr(slot, np.int64)
+    L = _lib(fast)
+    rc = L.orc_assemble_matrix(
+        C.c_int(PROBLEMS[P.problem_type]), C.c_int(T["nd"]), C.c_int(bs), C.c_int(T["nq_a"]),
+        _ptr(T["w_a"]), _ptr(T["dphi_a"]), _ptr(T["dgeo"]), C.c_int64(P.n_cells), _ptr(x),
+        _ptr(xd), _ptr(dm), C.c_int32(P.n_owned), _ptr(rp), _ptr(cl), _ptr(mk),
+        None if sl is None else _ptr(sl), _ptr(vals), C.c_int(nthreads))
+    if rc != 0:
+        raise RuntimeError("oracle: (row, col) missing from the sparsity pattern")
+    if set_diagonal:
+        rc = L.orc_set_diagonal(C.c_int(bs), C.c_int32(P.n_owned), _ptr(rp), _ptr(cl),
+                                C.c_int32(len(bcd)), _ptr(bcd), _ptr(vals))
+        if rc != 0:
+            raise RuntimeError("oracle: diagonal missing from the sparsity pattern")
+    return vals
+
+
+def assemble_vector(P, fast=False):
+    """ZZZ Assemble vector (src/poisson_problem.cpp:146-157), owned rows. apply_lifting is
+    omitted: g = u0 = 0 makes it a numerical no-op."""
+    T = element_tables(P.order)
+    bs = P.bs
+    x = _arr(P["x"], np.float64)
+    xd = _arr(P["x_dofmap"], np.int32)
+    dm = _arr(P["dofmap"], np.int32)
+    f = _arr(P["f"], np.float64)
+    g = _arr(P["g"], np.float64) if len(P["g"]) else None
+    fc = _arr(P["facet_cells"], np.int32)
+    fl = _arr(P["facet_local"], np.int32)
+    bcd = _arr(P["bc_dofs"], np.int32)
+    b = np.zeros(P.n_owned * bs, dtype=np.float64)
+    _lib(fast).orc_assemble_vector(
+        C.c_int(T["nd"]), C.c_int(bs), C.c_int(T["nq_l"]), _ptr(T["w_l"]), _ptr(T["phi_l"]),
+        C.c_int(T["nq_f"]), _ptr(T["w_f"]), _ptr(T["phi_f"]), _ptr(T["dgeo"]),
+        _ptr(T["facet_t"]), C.c_int64(P.n_cells), _ptr(x), _ptr(xd), _ptr(dm),
+        C.c_int32(P.n_owned), _ptr(f), None if g is None else _ptr(g), C.c_int64(len(fc)),
+        _ptr(fc), _ptr(fl), C.c_int32(len(bcd)), _ptr(bcd), _ptr(b))
+    return b
+
+
+def spmv(bs, n_rows, rowptr, cols, vals, p, nthreads=1, fast=False):
+    y = np.zeros(n_rows * bs, dtype=np.float64)
+    p = _arr(p, np.float64)
+    _lib(fast).orc_spmv(C.c_int(bs), C.c_int32(n_rows), _ptr(_arr(rowptr, np.int64)),
+                        _ptr(_arr(cols, np.int32)), _ptr(_arr(vals, np.float64)), _ptr(p),
+                        _ptr(y), C.c_int(nthreads))
+    return y
+
+
+def cg(bs, n_rows, rowptr, cols, vals, b, x0=None, kmax=50, rtol=1e-8, precond="none",
+       nthreads=1, fast=False):
+    """linalg::cg (src/cg.h:38-86) [+ Jacobi]; single partition. Returns (x, iterations, rel_res)."""
+    x = np.zeros(n_rows * bs) if x0 is None else np.array(x0, dtype=np.float64)
+    rel = C.c_double()
+    rp, cl, vl, bb = (_arr(rowptr, np.int64), _arr(cols, np.int32), _arr(vals, np.float64),
+                      _arr(b, np.float64))
+    k = _lib(fast).orc_cg(C.c_int(bs), C.c_int32(n_rows), _ptr(rp), _ptr(cl), _ptr(vl), _ptr(bb),
+                          _ptr(x), C.c_int(kmax), C.c_double(rtol),
+                          C.c_int({"none": 0, "jacobi": 1}[precond]), C.byref(rel),
+                          C.c_int(nthreads))
+    return x, k, rel.value

@@ -1,0 +1,240 @@
+"""ctypes binding of libptb200.so (include/ptb200.h): the drop-in C-ABI over the sm_100a kernels.
+
+No CPU fallback: ``Context()`` raises when the library or a CUDA device is missing.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_lib = None
+
+POISSON, ELASTICITY = 0, 1
+PC_NONE, PC_JACOBI = 0, 1
+STAGE_ASSEMBLE_MATRIX, STAGE_ASSEMBLE_VECTOR, STAGE_SOLVE, STAGE_SPMV = 0, 1, 2, 3
+PROBLEMS = {"poisson": POISSON, "cgpoisson": POISSON, "elasticity": ELASTICITY}
+PRECOND = {"none": PC_NONE, "jacobi": PC_JACOBI}
+
+
+def declared_symbols():
+    """Every function include/ptb200.h declares (used by the CPU-side export test)."""
+    from . import INCLUDE_DIR
+    src = open(os.path.join(INCLUDE_DIR, "ptb200.h")).read()
+    return sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        from . import ABI_LIB
+        if not os.path.exists(ABI_LIB):
+            raise RuntimeError(f"{ABI_LIB} is missing: run __graft_entry__.build() / make "
+                               "(there is no CPU fallback)")
+        L = C.CDLL(ABI_LIB)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        L.ptb_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.ptb_destroy.argtypes = [vp]
+        L.ptb_destroy.restype = None
+        L.ptb_last_error.argtypes = [vp]
+        L.ptb_last_error.restype = C.c_char_p
+        L.ptb_set_stream.argtypes = [vp, vp]
+        L.ptb_set_mesh.argtypes = [vp, i64, vp, i64, vp]
+        L.ptb_update_geometry.argtypes = [vp, vp]
+        L.ptb_set_space.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32, i32, vp]
+        L.ptb_set_pattern.argtypes = [vp, vp, vp]
+        L.ptb_set_bc.argtypes = [vp, i32, vp]
+        L.ptb_set_exterior_facets.argtypes = [vp, i64, vp, vp]
+        L.ptb_set_source.argtypes = [vp, vp, vp]
+        L.ptb_set_halo.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
+        L.ptb_nccl_unique_id.argtypes = [vp]
+        L.ptb_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ptb_assemble_matrix.argtypes = [vp]
+        L.ptb_assemble_vector.argtypes = [vp]
+        L.ptb_cg_solve.argtypes = [vp, C.c_int, dbl, C.c_int, C.POINTER(C.c_int), C.POINTER(dbl)]
+        L.ptb_apply_operator.argtypes = [vp, vp, vp]
+        L.ptb_set_rhs.argtypes = [vp, vp]
+        L.ptb_set_initial_guess.argtypes = [vp, vp]
+        L.ptb_get_matrix_values.argtypes = [vp, vp]
+        L.ptb_get_diagonal_inverse.argtypes = [vp, vp]
+        L.ptb_get_rhs.argtypes = [vp, vp]
+        L.ptb_get_solution.argtypes = [vp, vp]
+        L.ptb_solution_norm.argtypes = [vp, C.POINTER(dbl)]
+        L.ptb_build_cell_slot_map.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp]
+        L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
+        L.ptb_stage_ms.argtypes = [vp, C.c_int]
+        L.ptb_stage_ms.restype = dbl
+        L.ptb_launch_count.argtypes = [vp]
+        L.ptb_launch_count.restype = i64
+        L.ptb_device_bytes.argtypes = [vp]
+        L.ptb_device_bytes.restype = i64
+        _lib = L
+    return _lib
+
+
+def _a(x, dtype):
+    return np.ascontiguousarray(x, dtype=dtype)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def build_cell_slot_map(dofmap, nd, n_owned, rowptr, cols):
+    """Host-only (no GPU): the uncompressed cell -> CSR-slot map."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    n_cells = len(dm) // nd
+    out = np.empty(n_cells * nd * nd, dtype=np.int64)
+    rc = lib().ptb_build_cell_slot_map(n_cells, nd, _ptr(dm), n_owned, _ptr(rp), _ptr(cl),
+                                       _ptr(out))
+    if rc != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return out
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    if lib().ptb_nccl_unique_id(buf) != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return buf.raw
+
+
+class Context:
+    """One GPU / one rank. Mirrors the C-ABI one to one."""
+
+    def __init__(self, device: int = 0, stream=None):
+        self._h = C.c_void_p()
+        if lib().ptb_create(device, C.byref(self._h)) != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+        if stream is not None:
+            self._check(lib().ptb_set_stream(self._h, C.c_void_p(stream)))
+        self.P = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(self._h).decode())
+
+    def close(self):
+        if self._h:
+            lib().ptb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- setup ---------------------------------------------------------------------------
+    def set_problem(self, P, source=True):
+        """Upload everything a host problem (host.Problem or the oracle's RefProblem) holds."""
+        self.P = P
+        self.bs, self.nd = P.bs, P.nd
+        self.n_owned, self.n_ghost, self.nnz = P.n_owned, P.n_ghost, P.nnz
+        x, xd = _a(P["x"], np.float64), _a(P["x_dofmap"], np.int32)
+        self._check(lib().ptb_set_mesh(self._h, len(x) // 3, _ptr(x), len(xd) // 4, _ptr(xd)))
+        dm = _a(P["dofmap"], np.int32)
+        self._check(lib().ptb_set_space(self._h, PROBLEMS[P.problem_type], P.order, P.bs,
+                                        P.n_owned, P.n_ghost, _ptr(dm)))
+        rp, cl = _a(P["rowptr"], np.int64), _a(P["cols"], np.int32)
+        self._check(lib().ptb_set_pattern(self._h, _ptr(rp), _ptr(cl)))
+        bc = _a(P["bc_dofs"], np.int32)
+        self._check(lib().ptb_set_bc(self._h, len(bc), _ptr(bc)))
+        fc, fl = _a(P["facet_cells"], np.int32), _a(P["facet_local"], np.int32)
+        self._check(lib().ptb_set_exterior_facets(self._h, len(fc), _ptr(fc), _ptr(fl)))
+        if source:
+            self.set_source(P["f"], P["g"] if len(P["g"]) else None)
+        if P.n_nbr > 0:
+            self._check(lib().ptb_set_halo(
+                self._h, P.n_nbr, _ptr(_a(P["nbr_ranks"], np.int32)),
+                _ptr(_a(P["send_displ"], np.int32)), _ptr(_a(P["local_indices"], np.int32)),
+                _ptr(_a(P["recv_displ"], np.int32)), _ptr(_a(P["remote_indices"], np.int32))))
+
+    def set_source(self, f, g=None):
+        f = _a(f, np.float64)
+        g = None if g is None else _a(g, np.float64)
+        self._check(lib().ptb_set_source(self._h, _ptr(f), _ptr(g)))
+
+    def update_geometry(self, x):
+        x = _a(x, np.float64)
+        self._check(lib().ptb_update_geometry(self._h, _ptr(x)))
+
+    def comm_init(self, rank, nranks, unique_id: bytes):
+        self._check(lib().ptb_comm_init(self._h, rank, nranks, C.c_char_p(unique_id)))
+
+    # ---- hot calls -----------------------------------------------------------------------
+    def assemble_matrix(self):
+        self._check(lib().ptb_assemble_matrix(self._h))
+
+    def assemble_vector(self):
+        self._check(lib().ptb_assemble_vector(self._h))
+
+    def cg_solve(self, kmax=10000, rtol=1e-8, precond="jacobi"):
+        it, rel = C.c_int(), C.c_double()
+        self._check(lib().ptb_cg_solve(self._h, kmax, rtol, PRECOND[precond], C.byref(it),
+                                       C.byref(rel)))
+        return it.value, rel.value
+
+    def apply_operator(self, p):
+        p = _a(p, np.float64)
+        assert len(p) == (self.n_owned + self.n_ghost) * self.bs
+        y = np.empty(self.n_owned * self.bs)
+        self._check(lib().ptb_apply_operator(self._h, _ptr(p), _ptr(y)))
+        return y
+
+    # ---- data ----------------------------------------------------------------------------
+    def set_rhs(self, b):
+        b = _a(b, np.float64)
+        assert len(b) == self.n_owned * self.bs
+        self._check(lib().ptb_set_rhs(self._h, _ptr(b)))
+
+    def set_initial_guess(self, x):
+        x = None if x is None else _a(x, np.float64)
+        self._check(lib().ptb_set_initial_guess(self._h, _ptr(x)))
+
+    def matrix_values(self, out=None):
+        v = np.empty(self.nnz * self.bs * self.bs) if out is None else out
+        self._check(lib().ptb_get_matrix_values(self._h, _ptr(v)))
+        return v
+
+    def diagonal_inverse(self):
+        v = np.empty(self.n_owned * self.bs)
+        self._check(lib().ptb_get_diagonal_inverse(self._h, _ptr(v)))
+        return v
+
+    def rhs(self, out=None):
+        v = np.empty(self.n_owned * self.bs) if out is None else out
+        self._check(lib().ptb_get_rhs(self._h, _ptr(v)))
+        return v
+
+    def solution(self, out=None):
+        v = np.empty((self.n_owned + self.n_ghost) * self.bs) if out is None else out
+        self._check(lib().ptb_get_solution(self._h, _ptr(v)))
+        return v
+
+    def solution_norm(self):
+        n = C.c_double()
+        self._check(lib().ptb_solution_norm(self._h, C.byref(n)))
+        return n.value
+
+    def slot_offsets(self):
+        n = C.c_int64()
+        self._check(lib().ptb_get_slot_offsets(self._h, C.byref(n), None, None, None))
+        ptr = np.empty(self.n_owned + 1, dtype=np.int64)
+        pairs = np.empty(n.value, dtype=np.uint32)
+        off = np.empty(n.value * self.nd, dtype=np.uint16)
+        self._check(lib().ptb_get_slot_offsets(self._h, C.byref(n), _ptr(ptr), _ptr(pairs),
+                                               _ptr(off)))
+        return ptr, pairs, off
+
+    # ---- instrumentation -------------------------------------------------------------------
+    def stage_ms(self, stage):
+        return lib().ptb_stage_ms(self._h, stage)
+
+    def launch_count(self):
+        return lib().ptb_launch_count(self._h)
+
+    def device_bytes(self):
+        return lib().ptb_device_bytes(self._h)

@@ -1,0 +1,576 @@
+// extern "C" entry points of libptb200.so (include/ptb200.h).
+#include "comm.h"
+#include "kernels.h"
+#include "layout.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+using namespace ptb;
+
+namespace
+{
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(ptb_ctx* c, F&& fn)
+{
+  try
+  {
+    fn();
+    return 0;
+  }
+  catch (const std::exception& e)
+  {
+    (c ? c->err : g_err) = e.what();
+    return 1;
+  }
+}
+
+void need(bool ok, const char* msg)
+{
+  if (!ok)
+    throw std::runtime_error(msg);
+}
+
+void use_device(ptb_ctx* c) { PTB_CUDA(cudaSetDevice(c->device)); }
+
+struct StageTimer
+{
+  ptb_ctx* c;
+  int stage;
+  StageTimer(ptb_ctx* c_, int s) : c(c_), stage(s) { PTB_CUDA(cudaEventRecord(c->ev0, c->stream)); }
+  void stop()
+  {
+    PTB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PTB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    PTB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stage_ms[stage] = ms;
+  }
+};
+
+std::int64_t n_local_entries(const ptb_ctx* c)
+{
+  return (static_cast<std::int64_t>(c->n_owned) + c->n_ghost) * c->bs;
+}
+std::int64_t n_owned_entries(const ptb_ctx* c) { return static_cast<std::int64_t>(c->n_owned) * c->bs; }
+
+void alloc_vectors(ptb_ctx* c)
+{
+  const std::int64_t nl = n_local_entries(c), no = n_owned_entries(c);
+  c->b.alloc(no), c->dinv.alloc(no), c->ones.alloc(no), c->r.alloc(no), c->y.alloc(no);
+  c->x.alloc(nl), c->p.alloc(nl);
+  c->x.zero(c->stream), c->p.zero(c->stream), c->b.zero(c->stream);
+  launch_fill(c, c->ones.p, no, 1.0);
+  launch_fill(c, c->dinv.p, no, 1.0);
+}
+} // namespace
+
+std::int64_t ptb_ctx::device_bytes() const
+{
+  return xyz.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
+         + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
+         + adjso.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
+         + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
+         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes();
+}
+
+extern "C" {
+
+int ptb_create(int device, ptb_ctx** out)
+{
+  return guarded(nullptr, [&] {
+    need(out != nullptr, "ptb_create: out is NULL");
+    int ndev = 0;
+    const cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+      throw std::runtime_error(
+          std::string("ptb_create: no CUDA device (there is no CPU fallback): ")
+          + cudaGetErrorString(e));
+    need(device >= 0 && device < ndev, "ptb_create: device index out of range");
+    auto c = std::make_unique<ptb_ctx>();
+    c->device = device;
+    PTB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PTB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+      throw std::runtime_error("ptb_create: kernels are built for sm_100a only; found "
+                               + std::string(prop.name));
+    c->num_sms = prop.multiProcessorCount;
+    PTB_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    PTB_CUDA(cudaEventCreate(&c->ev0));
+    PTB_CUDA(cudaEventCreate(&c->ev1));
+    c->cg.alloc(2);
+    c->partials.alloc(static_cast<std::size_t>(3) * c->num_sms * 8);
+    c->tickets.alloc(4);
+    c->tickets.zero(c->stream);
+    PTB_CUDA(cudaMallocHost(&c->h_cg, 2 * sizeof(CgState)));
+    PTB_CUDA(cudaMallocHost(&c->h_scalar, 4 * sizeof(double)));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    *out = c.release();
+  });
+}
+
+void ptb_destroy(ptb_ctx* c)
+{
+  if (!c)
+    return;
+  cudaSetDevice(c->device);
+  try
+  {
+    comm_destroy(c);
+  }
+  catch (...)
+  {
+  }
+  if (c->h_cg)
+    cudaFreeHost(c->h_cg);
+  if (c->h_scalar)
+    cudaFreeHost(c->h_scalar);
+  if (c->ev0)
+    cudaEventDestroy(c->ev0);
+  if (c->ev1)
+    cudaEventDestroy(c->ev1);
+  if (c->own_stream)
+    cudaStreamDestroy(c->own_stream);
+  delete c;
+}
+
+const char* ptb_last_error(const ptb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int ptb_set_stream(ptb_ctx* c, void* s)
+{
+  return guarded(c, [&] { c->stream = s ? static_cast<cudaStream_t>(s) : c->own_stream; });
+}
+
+int ptb_set_mesh(ptb_ctx* c, int64_t n_vertices, const double* x, int64_t n_cells,
+                 const int32_t* x_dofmap)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(n_vertices > 0 && n_cells > 0 && x && x_dofmap, "ptb_set_mesh: empty mesh");
+    need(n_vertices <= INT32_MAX, "ptb_set_mesh: too many vertices for int32 indices");
+    c->n_vertices = n_vertices, c->n_cells = n_cells;
+    c->x_dofmap.upload(x_dofmap, static_cast<std::size_t>(n_cells) * 4, c->stream);
+    c->xyz.alloc(static_cast<std::size_t>(n_vertices) * 4);
+    PTB_CUDA(cudaMemcpy2DAsync(c->xyz.p, 4 * sizeof(double), x, 3 * sizeof(double),
+                               3 * sizeof(double), n_vertices, cudaMemcpyHostToDevice, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_mesh = true;
+    c->matrix_assembled = c->vector_assembled = false;
+  });
+}
+
+int ptb_update_geometry(ptb_ctx* c, const double* x)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_mesh && x, "ptb_update_geometry: call ptb_set_mesh first");
+    PTB_CUDA(cudaMemcpy2DAsync(c->xyz.p, 4 * sizeof(double), x, 3 * sizeof(double),
+                               3 * sizeof(double), c->n_vertices, cudaMemcpyHostToDevice,
+                               c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, int32_t n_ghost,
+                  const int32_t* dofmap)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_mesh, "ptb_set_space: call ptb_set_mesh first");
+    need(problem == PTB_POISSON || problem == PTB_ELASTICITY, "ptb_set_space: unknown problem");
+    need(order >= 1 && order <= 3, "Order not supported");
+    need((problem == PTB_POISSON && bs == 1) || (problem == PTB_ELASTICITY && bs == 3),
+         "ptb_set_space: bs must be 1 for Poisson and 3 for elasticity");
+    need(n_owned > 0 && n_ghost >= 0 && dofmap, "ptb_set_space: empty space");
+    c->problem = problem, c->order = order, c->bs = bs;
+    c->nd = (order + 1) * (order + 2) * (order + 3) / 6;
+    c->n_owned = n_owned, c->n_ghost = n_ghost;
+    need(static_cast<std::uint64_t>(c->n_cells) * c->nd <= 0xFFFFFFFEull,
+         "ptb_set_space: n_cells * nd exceeds the 32-bit pair index");
+    c->h_dofmap.assign(dofmap, dofmap + static_cast<std::size_t>(c->n_cells) * c->nd);
+    c->dofmap.upload(c->h_dofmap, c->stream);
+    c->bc.alloc(static_cast<std::size_t>(n_owned) + n_ghost);
+    c->bc.zero(c->stream);
+    c->h_bc_dofs.clear();
+    alloc_vectors(c);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_space = true, c->have_pattern = false, c->have_source = false;
+    c->matrix_assembled = c->vector_assembled = false;
+  });
+}
+
+int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_set_pattern: call ptb_set_space first");
+    need(rowptr && cols, "ptb_set_pattern: NULL pattern");
+    const std::int32_t N = c->n_owned;
+    c->nnz = rowptr[N];
+    const std::vector<std::int32_t>& dm = c->h_dofmap;
+    build_row_adjacency(dm.data(), c->n_cells, c->nd, N, c->h_adj);
+    const std::int64_t max_so
+        = build_slot_offsets(dm.data(), c->nd, N, c->h_adj, rowptr, cols, c->h_so);
+    need(max_so >= 0, "ptb_set_pattern: a cell's (row, col) pair is missing from the pattern");
+    SellLayout L;
+    build_sell_layout(N, c->nd, rowptr, cols, c->h_adj, c->h_so, max_so, L);
+    c->n_slices = L.n_slices, c->max_w = L.max_w, c->max_wa = L.max_wa;
+    c->so_bits = L.so_bits, c->so_words = L.so_words;
+    c->h_rowptr.assign(rowptr, rowptr + N + 1);
+    c->rowptr.upload(c->h_rowptr, c->stream);
+    c->mat_off.upload(L.mat_off, c->stream);
+    c->adj_off.upload(L.adj_off, c->stream);
+    c->cols.upload(L.cols, c->stream);
+    c->adj.upload(L.adj, c->stream);
+    c->adjso.upload(L.adjso, c->stream);
+    c->vals.alloc(L.cols.size() * c->bs * c->bs);
+    c->vals.zero(c->stream);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_pattern = true;
+    c->matrix_assembled = false;
+  });
+}
+
+int ptb_set_bc(ptb_ctx* c, int32_t n_bc, const int32_t* bc_dofs)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_set_bc: call ptb_set_space first");
+    const std::int64_t nl = static_cast<std::int64_t>(c->n_owned) + c->n_ghost;
+    std::vector<std::uint8_t> m(nl, 0);
+    for (std::int32_t k = 0; k < n_bc; ++k)
+    {
+      need(bc_dofs[k] >= 0 && bc_dofs[k] < nl, "ptb_set_bc: dof index out of range");
+      m[bc_dofs[k]] = 1;
+    }
+    c->h_bc_dofs.assign(bc_dofs, bc_dofs + n_bc);
+    c->bc.upload(m, c->stream);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->matrix_assembled = c->vector_assembled = false;
+  });
+}
+
+int ptb_set_exterior_facets(ptb_ctx* c, int64_t n_facets, const int32_t* cells,
+                            const int32_t* local_facets)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_set_exterior_facets: call ptb_set_space first");
+    const std::vector<std::int32_t>& dm = c->h_dofmap;
+    for (std::int64_t k = 0; k < n_facets; ++k)
+      need(cells[k] >= 0 && cells[k] < c->n_cells, "exterior facet: cell index out of range");
+    std::vector<std::int32_t> ids, ptr, ent;
+    build_facet_rows(n_facets, cells, local_facets, dm.data(), c->nd, c->order, c->n_owned, ids,
+                     ptr, ent);
+    c->n_frows = static_cast<std::int32_t>(ids.size());
+    c->frow_ids.upload(ids, c->stream);
+    c->frow_ptr.upload(ptr, c->stream);
+    c->fent.upload(ent, c->stream);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->vector_assembled = false;
+  });
+}
+
+int ptb_set_source(ptb_ctx* c, const double* f, const double* g)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && f, "ptb_set_source: call ptb_set_space first / f is NULL");
+    c->f.upload(f, n_local_entries(c), c->stream);
+    if (g)
+      c->g.upload(g, static_cast<std::size_t>(c->n_owned) + c->n_ghost, c->stream);
+    else
+      c->g.release();
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_source = true;
+    c->vector_assembled = false;
+  });
+}
+
+int ptb_set_halo(ptb_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_t* send_displ,
+                 const int32_t* local_indices, const int32_t* recv_displ,
+                 const int32_t* remote_indices)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_set_halo: call ptb_set_space first");
+    c->nbr_ranks.assign(nbr_ranks, nbr_ranks + n_nbr);
+    c->send_displ.assign(send_displ, send_displ + n_nbr + 1);
+    c->recv_displ.assign(recv_displ, recv_displ + n_nbr + 1);
+    const std::int64_t ns = c->send_displ.back(), nr = c->recv_displ.back();
+    for (std::int64_t i = 0; i < ns; ++i)
+      need(local_indices[i] >= 0 && local_indices[i] < c->n_owned,
+           "ptb_set_halo: send index is not an owned dof");
+    for (std::int64_t i = 0; i < nr; ++i)
+      need(remote_indices[i] >= c->n_owned && remote_indices[i] < c->n_owned + c->n_ghost,
+           "ptb_set_halo: receive index is not a ghost dof");
+    c->send_idx.upload(local_indices, ns, c->stream);
+    c->recv_idx.upload(remote_indices, nr, c->stream);
+    c->send_buf.alloc(ns * c->bs);
+    c->recv_buf.alloc(nr * c->bs);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_nccl_unique_id(void* out128)
+{
+  return guarded(nullptr, [&] { nccl_unique_id(out128); });
+}
+
+int ptb_comm_init(ptb_ctx* c, int rank, int nranks, const void* id)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    comm_init(c, rank, nranks, id);
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot calls
+// ---------------------------------------------------------------------------------------------
+
+int ptb_assemble_matrix(ptb_ctx* c)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_pattern, "ptb_assemble_matrix: pattern not set");
+    StageTimer t(c, PTB_STAGE_ASSEMBLE_MATRIX);
+    MatrixArgs A{c->n_owned, c->n_slices, c->so_bits, c->so_words, c->xyz.p, c->x_dofmap.p,
+                 c->dofmap.p, c->bc.p, c->rowptr.p, c->mat_off.p, c->adj_off.p, c->cols.p,
+                 c->adj.p, c->adjso.p, c->vals.p, c->dinv.p};
+    launch_assemble_matrix(c, A);
+    t.stop();
+    c->matrix_assembled = true;
+  });
+}
+
+int ptb_assemble_vector(ptb_ctx* c)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_pattern && c->have_source, "ptb_assemble_vector: pattern / source not set");
+    StageTimer t(c, PTB_STAGE_ASSEMBLE_VECTOR);
+    VectorArgs A{c->n_owned, c->n_slices, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p,
+                 c->adj_off.p, c->adj.p, c->f.p, c->b.p};
+    FacetArgs F{c->n_frows, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p, c->frow_ids.p,
+                c->frow_ptr.p, c->fent.p, c->g.p, c->b.p};
+    launch_assemble_vector(c, A, F);
+    t.stop();
+    c->vector_assembled = true;
+  });
+}
+
+int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations,
+                 double* rel_residual)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->matrix_assembled, "ptb_cg_solve: matrix not assembled");
+    need(precond == PTB_PC_NONE || precond == PTB_PC_JACOBI, "ptb_cg_solve: unknown preconditioner");
+    need(kmax >= 0, "ptb_cg_solve: kmax < 0");
+    StageTimer t(c, PTB_STAGE_SOLVE);
+    const double* dinv = precond == PTB_PC_JACOBI ? c->dinv.p : c->ones.p;
+    CgState* st = c->cg.p;
+    if (!c->have_x0)
+      c->x.zero(c->stream);
+    // r0 = b - A x0 (cg.h:46-47): the action is evaluated even for x0 = 0, like the reference.
+    halo_forward(c, c->x.p);
+    launch_spmv(c, c->x.p, c->y.p, nullptr);
+    launch_cg_init(c, dinv, &st[1]);
+    allreduce_sum(c, &st[1].rr, 2);
+    launch_cg_finish_init(c, &st[1], rtol);
+
+    // Iterations are queued in batches; the stopping flag of batch j is read back while batch
+    // j + 1 is already running, so the device never waits for the host. Kernels of iterations
+    // after convergence return immediately.
+    const int batch = 8;
+    int it = 0;
+    int pending = -1;
+    bool done = false;
+    cudaEvent_t evs[2];
+    PTB_CUDA(cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming));
+    PTB_CUDA(cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming));
+    int slot = 0;
+    while (it < kmax && !done)
+    {
+      const int n = std::min(batch, kmax - it);
+      for (int j = 0; j < n; ++j)
+      {
+        ++it;
+        CgState* cur = &st[it & 1];
+        CgState* nxt = &st[(it + 1) & 1];
+        halo_forward(c, c->p.p);
+        launch_spmv(c, c->p.p, c->y.p, cur);
+        allreduce_sum(c, &cur->py, 1);
+        launch_cg_update(c, dinv, cur);
+        allreduce_sum(c, &cur->rr, 2);
+        launch_cg_direction(c, dinv, cur, nxt);
+      }
+      PTB_CUDA(cudaMemcpyAsync(&c->h_cg[slot], &st[(it + 1) & 1], sizeof(CgState),
+                               cudaMemcpyDeviceToHost, c->stream));
+      PTB_CUDA(cudaEventRecord(evs[slot], c->stream));
+      if (pending >= 0)
+      {
+        PTB_CUDA(cudaEventSynchronize(evs[pending]));
+        done = c->h_cg[pending].conv != 0;
+      }
+      pending = slot;
+      slot ^= 1;
+    }
+    PTB_CUDA(cudaMemcpyAsync(&c->h_cg[0], &st[(it + 1) & 1], sizeof(CgState),
+                             cudaMemcpyDeviceToHost, c->stream));
+    halo_forward(c, c->x.p); // leave the ghosts of the solution current (cg.h:36-37)
+    t.stop();
+    cudaEventDestroy(evs[0]);
+    cudaEventDestroy(evs[1]);
+    const CgState fin = c->h_cg[0];
+    if (iterations)
+      *iterations = kmax == 0 ? 0 : fin.k;
+    if (rel_residual)
+      *rel_residual = std::sqrt(fin.rnorm / fin.rnorm0);
+  });
+}
+
+int ptb_apply_operator(ptb_ctx* c, const double* p_host, double* y_host)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->matrix_assembled, "ptb_apply_operator: matrix not assembled");
+    PTB_CUDA(cudaMemcpyAsync(c->p.p, p_host, n_local_entries(c) * sizeof(double),
+                             cudaMemcpyHostToDevice, c->stream));
+    StageTimer t(c, PTB_STAGE_SPMV);
+    halo_forward(c, c->p.p);
+    launch_spmv(c, c->p.p, c->y.p, nullptr);
+    t.stop();
+    PTB_CUDA(cudaMemcpyAsync(y_host, c->y.p, n_owned_entries(c) * sizeof(double),
+                             cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+// ---------------------------------------------------------------------------------------------
+// data in / out
+// ---------------------------------------------------------------------------------------------
+
+int ptb_set_rhs(ptb_ctx* c, const double* b)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && b, "ptb_set_rhs: space not set / NULL");
+    PTB_CUDA(cudaMemcpyAsync(c->b.p, b, n_owned_entries(c) * sizeof(double),
+                             cudaMemcpyHostToDevice, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_set_initial_guess(ptb_ctx* c, const double* x)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_set_initial_guess: space not set");
+    c->have_x0 = x != nullptr;
+    if (x)
+      PTB_CUDA(cudaMemcpyAsync(c->x.p, x, n_local_entries(c) * sizeof(double),
+                               cudaMemcpyHostToDevice, c->stream));
+    else
+      c->x.zero(c->stream);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_get_matrix_values(ptb_ctx* c, double* vals)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->matrix_assembled && vals, "ptb_get_matrix_values: matrix not assembled");
+    DevBuf<double> csr;
+    csr.alloc(static_cast<std::size_t>(c->nnz) * c->bs * c->bs);
+    launch_sell_to_csr(c, csr.p);
+    PTB_CUDA(cudaMemcpyAsync(vals, csr.p, csr.bytes(), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_get_diagonal_inverse(ptb_ctx* c, double* dinv)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->matrix_assembled && dinv, "ptb_get_diagonal_inverse: matrix not assembled");
+    PTB_CUDA(cudaMemcpyAsync(dinv, c->dinv.p, c->dinv.bytes(), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_get_rhs(ptb_ctx* c, double* b)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && b, "ptb_get_rhs: space not set");
+    PTB_CUDA(cudaMemcpyAsync(b, c->b.p, c->b.bytes(), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_get_solution(ptb_ctx* c, double* x)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && x, "ptb_get_solution: space not set");
+    PTB_CUDA(cudaMemcpyAsync(x, c->x.p, c->x.bytes(), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int ptb_solution_norm(ptb_ctx* c, double* norm)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && norm, "ptb_solution_norm: space not set");
+    double* d = &c->cg.p[0].py; // scratch: not live outside a solve
+    launch_sqnorm(c, c->x.p, n_owned_entries(c), d);
+    allreduce_sum(c, d, 1);
+    PTB_CUDA(cudaMemcpyAsync(c->h_scalar, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    *norm = std::sqrt(c->h_scalar[0]);
+  });
+}
+
+int ptb_build_cell_slot_map(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_owned,
+                            const int64_t* rowptr, const int32_t* cols, int64_t* slot)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && slot, "ptb_build_cell_slot_map: NULL argument");
+    build_cell_slot_map(dofmap, n_cells, nd, n_owned, rowptr, cols, slot);
+  });
+}
+
+int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
+                         uint16_t* offsets)
+{
+  return guarded(c, [&] {
+    need(c->have_pattern, "ptb_get_slot_offsets: pattern not set");
+    if (n_pairs)
+      *n_pairs = static_cast<std::int64_t>(c->h_adj.pairs.size());
+    if (pair_ptr)
+      std::copy(c->h_adj.ptr.begin(), c->h_adj.ptr.end(), pair_ptr);
+    if (pairs)
+      std::copy(c->h_adj.pairs.begin(), c->h_adj.pairs.end(), pairs);
+    if (offsets)
+      std::copy(c->h_so.begin(), c->h_so.end(), offsets);
+  });
+}
+
+double ptb_stage_ms(const ptb_ctx* c, int stage)
+{
+  return (c && stage >= 0 && stage < PTB_STAGE_COUNT) ? c->stage_ms[stage] : -1.0;
+}
+int64_t ptb_launch_count(const ptb_ctx* c) { return c ? c->launches : 0; }
+int64_t ptb_device_bytes(const ptb_ctx* c) { return c ? c->device_bytes() : 0; }
+
+} // extern "C"

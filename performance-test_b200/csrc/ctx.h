@@ -1,0 +1,151 @@
+// Internal context of libptb200.so. Device data layout (DESIGN.md "Data layout in HBM"):
+//
+//   rows are the owned block dofs; 32 consecutive rows form a *slice* (one warp);
+//   every per-row list is stored slice-major, column-major inside the slice (SELL-32), so a warp
+//   reading "entry k of my row" touches 32 consecutive words:
+//     matrix   cols[mat_off[s] + k*32 + lane]           vals[(mat_off[s] + k*32)*bs2 + e*32 + lane]
+//     cells    adj [adj_off[s] + k*32 + lane]           (pair = cell*nd + local index)
+//     slots    adjso[(adj_off[s] + k*32)*nw + w*32 + lane]   (4 x uint8 or 2 x uint16 per word)
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ptb200.h"
+#include "../common/intmaps.h"
+
+namespace ptb
+{
+
+struct CudaError : std::runtime_error
+{
+  using std::runtime_error::runtime_error;
+};
+
+#define PTB_CUDA(call)                                                                            \
+  do                                                                                              \
+  {                                                                                               \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      throw ::ptb::CudaError(std::string(#call) + ": " + cudaGetErrorString(e__));                \
+  } while (0)
+
+/// Owning device buffer.
+template <typename T>
+struct DevBuf
+{
+  T* p = nullptr;
+  std::size_t n = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p)
+      cudaFree(p);
+    p = nullptr, n = 0;
+  }
+  void alloc(std::size_t count)
+  {
+    if (count == n && p)
+      return;
+    release();
+    if (count)
+      PTB_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    n = count;
+  }
+  void upload(const T* h, std::size_t count, cudaStream_t s)
+  {
+    alloc(count);
+    if (count)
+      PTB_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& h, cudaStream_t s) { upload(h.data(), h.size(), s); }
+  void zero(cudaStream_t s)
+  {
+    if (n)
+      PTB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+  }
+  std::size_t bytes() const { return n * sizeof(T); }
+};
+
+/// Scalars of the CG loop, double-buffered by iteration parity (DESIGN.md "CG").
+struct CgState
+{
+  double py;     // p.y                 (written by spmv's last block, then allreduced)
+  double rr;     // r.r   after update  (written by update's last block, allreduced with rz)
+  double rz;     // r.z   after update
+  double rz_old; // r.z entering this iteration
+  double rnorm0; // |r0|^2
+  double rtol2;
+  double rnorm;  // |r|^2 entering this iteration
+  int k;         // iterations completed
+  int conv;      // 1 once the stopping rule fired
+};
+
+} // namespace ptb
+
+struct ptb_ctx
+{
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  double stage_ms[PTB_STAGE_COUNT] = {0, 0, 0, 0};
+  std::int64_t launches = 0;
+  int num_sms = 148;
+
+  // problem description
+  int problem = PTB_POISSON, order = 1, bs = 1, nd = 4;
+  std::int64_t n_vertices = 0, n_cells = 0;
+  std::int32_t n_owned = 0, n_ghost = 0;
+  std::int64_t nnz = 0; // block nonzeros
+  bool have_mesh = false, have_space = false, have_pattern = false, have_source = false,
+       matrix_assembled = false, vector_assembled = false;
+
+  // geometry + dofmaps
+  ptb::DevBuf<double> xyz;        // [n_vertices][4] padded
+  ptb::DevBuf<std::int32_t> x_dofmap, dofmap;
+  ptb::DevBuf<std::uint8_t> bc;   // marker per local block dof
+  std::vector<std::int32_t> h_bc_dofs, h_dofmap; // host copy of the dofmap for the integer maps
+
+  // pattern (CSR, kept for inspection) + SELL layouts
+  std::vector<std::int64_t> h_rowptr;
+  std::int32_t n_slices = 0;
+  int max_w = 0, max_wa = 0, so_bits = 8, so_words = 1;
+  ptb::DevBuf<std::int64_t> rowptr, mat_off, adj_off;
+  ptb::DevBuf<std::int32_t> cols;      // SELL
+  ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry
+  ptb::DevBuf<std::uint32_t> adj, adjso;
+  // host copies of the compressed slot map (parity inspection)
+  ptb::RowAdjacency h_adj;
+  std::vector<std::uint16_t> h_so;
+
+  // exterior facets: CSR over boundary rows
+  std::int32_t n_frows = 0;
+  ptb::DevBuf<std::int32_t> frow_ids, frow_ptr, fent; // fent = {cell, local_facet*nd + li} pairs
+
+  // vectors
+  ptb::DevBuf<double> f, g, b, dinv, ones, x, p, r, y;
+  bool have_x0 = false;
+
+  // CG scalars + reductions
+  ptb::DevBuf<ptb::CgState> cg;          // [2]
+  ptb::DevBuf<double> partials;          // [3 * max_grid]
+  ptb::DevBuf<unsigned int> tickets;     // [4]
+  ptb::CgState* h_cg = nullptr;          // pinned [2]
+  double* h_scalar = nullptr;            // pinned [4]
+
+  // halo / comm
+  int rank = 0, nranks = 1;
+  void* nccl_comm = nullptr;
+  std::vector<std::int32_t> nbr_ranks, send_displ, recv_displ;
+  ptb::DevBuf<std::int32_t> send_idx, recv_idx;
+  ptb::DevBuf<double> send_buf, recv_buf;
+
+  std::int64_t device_bytes() const;
+};

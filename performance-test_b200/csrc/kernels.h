@@ -1,0 +1,86 @@
+// Kernel argument blocks and launchers shared by the .cu files.
+#pragma once
+#include "ctx.h"
+
+namespace ptb
+{
+
+#define ADJ_INVALID_DEV 0xFFFFFFFFu
+
+struct MatrixArgs
+{
+  std::int32_t n_rows, n_slices;
+  int so_bits, so_words;
+  const double* xyz;
+  const std::int32_t* x_dofmap;
+  const std::int32_t* dofmap;
+  const std::uint8_t* bc;
+  const std::int64_t* rowptr;
+  const std::int64_t* mat_off;
+  const std::int64_t* adj_off;
+  const std::int32_t* cols;
+  const std::uint32_t* adj;
+  const std::uint32_t* adjso;
+  double* vals;
+  double* dinv;
+};
+
+struct VectorArgs
+{
+  std::int32_t n_rows, n_slices;
+  const double* xyz;
+  const std::int32_t* x_dofmap;
+  const std::int32_t* dofmap;
+  const std::uint8_t* bc;
+  const std::int64_t* adj_off;
+  const std::uint32_t* adj;
+  const double* f;
+  double* b;
+};
+
+struct FacetArgs
+{
+  std::int32_t n_frows;
+  const double* xyz;
+  const std::int32_t* x_dofmap;
+  const std::int32_t* dofmap;
+  const std::uint8_t* bc;
+  const std::int32_t* frow_ids;
+  const std::int32_t* frow_ptr;
+  const std::int32_t* fent;
+  const double* g;
+  double* b;
+};
+
+/// SELL-32 matrix view for the SpMV.
+struct SpmvArgs
+{
+  std::int32_t n_rows, n_slices;
+  const std::int64_t* mat_off;
+  const std::int32_t* cols;
+  const double* vals;
+};
+
+void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
+void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
+void launch_sell_to_csr(ptb_ctx* c, double* out);
+
+// cg.cu
+int cg_grid(const ptb_ctx* c);
+/// y = A p on owned rows; if st != nullptr also st->py = p.y (local sum) and honours st->conv.
+void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st);
+/// r = b - y; p = dinv*r (owned); st: rnorm0 = rnorm = rr, rz_old = rz (local sums into rr, rz).
+void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st);
+void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol);
+/// x += alpha p; r -= alpha y; local sums r.r, r.z into cur->rr, cur->rz.
+void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur);
+/// beta, convergence test, bookkeeping into nxt; p = beta p + dinv r unless converged.
+void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt);
+void launch_fill(ptb_ctx* c, double* v, std::int64_t n, double value);
+void launch_pack(ptb_ctx* c, const double* v, const std::int32_t* idx, std::int64_t n, int bs,
+                 double* out);
+void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::int64_t n, int bs,
+                   double* v);
+void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev);
+
+} // namespace ptb

@@ -1,0 +1,129 @@
+#include "layout.h"
+#include <algorithm>
+#include <map>
+#include <stdexcept>
+
+namespace ptb
+{
+
+void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
+                       const std::int32_t* cols, const RowAdjacency& adj,
+                       const std::vector<std::uint16_t>& so, std::int64_t max_so, SellLayout& L)
+{
+  const std::int32_t S = (n_rows + 31) / 32;
+  L.n_slices = S;
+  L.so_bits = max_so < 256 ? 8 : 16;
+  const int per_word = 32 / L.so_bits;
+  L.so_words = (nd + per_word - 1) / per_word;
+  L.mat_off.assign(S + 1, 0);
+  L.adj_off.assign(S + 1, 0);
+  int max_w = 0, max_wa = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_w, max_wa)
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    std::int64_t w = 0, wa = 0;
+    for (std::int32_t r = 32 * s; r < std::min(n_rows, 32 * s + 32); ++r)
+    {
+      w = std::max(w, rowptr[r + 1] - rowptr[r]);
+      wa = std::max(wa, adj.ptr[r + 1] - adj.ptr[r]);
+    }
+    L.mat_off[s + 1] = 32 * w;
+    L.adj_off[s + 1] = 32 * wa;
+    max_w = std::max<int>(max_w, w);
+    max_wa = std::max<int>(max_wa, wa);
+  }
+  L.max_w = max_w, L.max_wa = max_wa;
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    L.mat_off[s + 1] += L.mat_off[s];
+    L.adj_off[s + 1] += L.adj_off[s];
+  }
+  L.cols.resize(static_cast<std::size_t>(L.mat_off[S]));
+  L.adj.resize(static_cast<std::size_t>(L.adj_off[S]));
+  L.adjso.resize(static_cast<std::size_t>(L.adj_off[S]) * L.so_words);
+  const std::uint32_t* pairs = adj.pairs.data();
+#pragma omp parallel for schedule(static)
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    const std::int64_t mo = L.mat_off[s], w = (L.mat_off[s + 1] - mo) / 32;
+    const std::int64_t ao = L.adj_off[s], wa = (L.adj_off[s + 1] - ao) / 32;
+    for (int lane = 0; lane < 32; ++lane)
+    {
+      const std::int32_t r = 32 * s + lane;
+      const bool live = r < n_rows;
+      const std::int64_t len = live ? rowptr[r + 1] - rowptr[r] : 0;
+      const std::int32_t pad = len > 0 ? cols[rowptr[r]] : 0;
+      for (std::int64_t k = 0; k < w; ++k)
+        L.cols[mo + k * 32 + lane] = k < len ? cols[rowptr[r] + k] : pad;
+      const std::int64_t alen = live ? adj.ptr[r + 1] - adj.ptr[r] : 0;
+      for (std::int64_t k = 0; k < wa; ++k)
+      {
+        const bool on = k < alen;
+        L.adj[ao + k * 32 + lane] = on ? pairs[adj.ptr[r] + k] : ADJ_INVALID;
+        for (int wd = 0; wd < L.so_words; ++wd)
+        {
+          std::uint32_t word = 0;
+          if (on)
+            for (int t = 0; t < per_word; ++t)
+            {
+              const int j = wd * per_word + t;
+              if (j < nd)
+                word |= static_cast<std::uint32_t>(so[(adj.ptr[r] + k) * nd + j])
+                        << (t * L.so_bits);
+            }
+          L.adjso[(ao + k * 32) * L.so_words + wd * 32 + lane] = word;
+        }
+      }
+    }
+  }
+}
+
+namespace
+{
+const int tet_edges[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};
+}
+
+void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
+                      const std::int32_t* local_facets, const std::int32_t* dofmap, int nd,
+                      int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
+                      std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent)
+{
+  // local dofs on local facet lf (Basix layout: vertices, edges, faces)
+  std::vector<int> on[4];
+  const int ne = order - 1, nf = (order - 1) * (order - 2) / 2;
+  for (int lf = 0; lf < 4; ++lf)
+  {
+    for (int v = 0; v < 4; ++v)
+      if (v != lf)
+        on[lf].push_back(v);
+    for (int e = 0; e < 6; ++e)
+      if (tet_edges[e][0] != lf && tet_edges[e][1] != lf)
+        for (int s = 0; s < ne; ++s)
+          on[lf].push_back(4 + e * ne + s);
+    for (int s = 0; s < nf; ++s)
+      on[lf].push_back(4 + 6 * ne + lf * nf + s);
+  }
+  std::map<std::int32_t, std::vector<std::int32_t>> rows; // ordered by row; entries ascending in k
+  for (std::int64_t k = 0; k < n_facets; ++k)
+  {
+    const std::int32_t c = cells[k], lf = local_facets[k];
+    if (lf < 0 || lf > 3)
+      throw std::runtime_error("exterior facet: local facet index out of range");
+    for (int li : on[lf])
+    {
+      const std::int32_t r = dofmap[static_cast<std::int64_t>(c) * nd + li];
+      if (r < n_rows)
+        rows[r].push_back(c), rows[r].push_back(lf * nd + li);
+    }
+  }
+  row_ids.clear(), ent.clear();
+  row_ptr.assign(1, 0);
+  for (auto& [r, v] : rows)
+  {
+    row_ids.push_back(r);
+    ent.insert(ent.end(), v.begin(), v.end());
+    row_ptr.push_back(static_cast<std::int32_t>(ent.size() / 2));
+  }
+}
+
+} // namespace ptb

@@ -1,0 +1,36 @@
+// Host-side construction of the SELL-32 device layouts from the CSR pattern and the compressed
+// cell -> slot map (see ctx.h for the layout).
+#pragma once
+#include "../common/intmaps.h"
+#include <cstdint>
+#include <vector>
+
+namespace ptb
+{
+
+constexpr std::uint32_t ADJ_INVALID = 0xFFFFFFFFu;
+
+struct SellLayout
+{
+  std::int32_t n_slices = 0;
+  int max_w = 0, max_wa = 0;
+  int so_bits = 8, so_words = 1; // slot-offset packing
+  std::vector<std::int64_t> mat_off, adj_off; // [n_slices + 1], in entries
+  std::vector<std::int32_t> cols;             // padded with the row's first column (0 past n_rows)
+  std::vector<std::uint32_t> adj, adjso;
+};
+
+void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
+                       const std::int32_t* cols, const RowAdjacency& adj,
+                       const std::vector<std::uint16_t>& so, std::int64_t max_so,
+                       SellLayout& L);
+
+/// Boundary-facet gather lists: for every owned row touched by an exterior facet, the entries
+/// (facet k, local dof li) with dofmap[cell_k][li] == row and li on the facet, ascending in k.
+/// ent holds two ints per entry: cell, local_facet*nd + li.
+void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
+                      const std::int32_t* local_facets, const std::int32_t* dofmap, int nd,
+                      int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
+                      std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent);
+
+} // namespace ptb

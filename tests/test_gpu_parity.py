@@ -1,0 +1,208 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on the same inputs.
+
+Tolerances (the reference pins nothing):
+  * integer side: bit-identical;
+  * A: |dA| <= 1e-12 * (diagonal magnitude of the row) -- 8 of the 15 stored P1-Poisson entries
+    per interior row are analytic zeros, so a per-entry relative tolerance is meaningless;
+  * b: |db| <= 1e-12 * |b|_inf;
+  * CG: iteration count within +-1, final relative residual within 1e-10 relative... of the
+    oracle's when the counts agree (same stopping rule |r|^2/|r0|^2 < rtol^2, cg.h:78).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx(pt):
+    c = pt.abi.Context(0)
+    yield c
+    c.close()
+
+
+def _row_scale(P, vals):
+    """Per-entry tolerance scale: |diagonal| of the entry's row (max over the 3x3 block)."""
+    bs2 = P.bs * P.bs
+    rp, cl = P["rowptr"], P["cols"]
+    rows = np.repeat(np.arange(P.n_owned), np.diff(rp))
+    diag = np.zeros(P.n_owned)
+    d = cl == rows
+    blk = np.abs(vals.reshape(-1, bs2))
+    diag[rows[d]] = blk[d].max(axis=1)
+    return np.repeat(diag[rows], bs2)
+
+
+def _check_matrix(P, got, ref):
+    scale = _row_scale(P, ref)
+    assert scale.min() > 0
+    err = np.abs(got - ref) / scale
+    assert err.max() <= 1e-12, f"max scaled matrix error {err.max():.3e}"
+
+
+SMALL = [("poisson", 1, (5, 4, 6)), ("poisson", 1, (1, 1, 1)), ("poisson", 1, (9, 2, 3)),
+         ("poisson", 1, (16, 15, 17)), ("elasticity", 1, (4, 5, 3)), ("elasticity", 1, (1, 1, 2)),
+         ("elasticity", 1, (12, 11, 13))]
+
+
+@pytest.mark.parametrize("ptype,order,dims", SMALL)
+def test_assembly_matches_oracle(pt, oracle, ctx, ptype, order, dims):
+    P = pt.host.Problem(ptype, order, *dims)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref = oracle.assemble_matrix(P)
+    b_ref = oracle.assemble_vector(P)
+    A = ctx.matrix_values()
+    _check_matrix(P, A, A_ref)
+    b = ctx.rhs()
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    # BC rows: identity, exact
+    bs = P.bs
+    rp, cl = P["rowptr"], P["cols"]
+    for d in P["bc_dofs"][: 50]:
+        blk = A.reshape(-1, bs, bs)[rp[d]:rp[d + 1]]
+        for k, c in enumerate(cl[rp[d]:rp[d + 1]]):
+            assert np.array_equal(blk[k], np.eye(bs) if c == d else np.zeros((bs, bs)))
+        assert np.all(b.reshape(-1, bs)[d] == 0.0)
+    # Jacobi diagonal
+    rows = np.repeat(np.arange(P.n_owned), np.diff(rp))
+    diag = np.einsum("kii->ki", A.reshape(-1, bs, bs)[cl == rows]).reshape(-1)
+    np.testing.assert_allclose(ctx.diagonal_inverse(), 1.0 / diag, rtol=1e-15)
+
+
+@pytest.mark.parametrize("ptype,order,dims", SMALL[:1] + SMALL[4:5])
+def test_slot_offsets_bit_identical(pt, ctx, ptype, order, dims):
+    """Compressed cell -> CSR-slot map held by the context == rowptr + oracle's slot map."""
+    from oracle import intmaps_ref as R
+    P = pt.host.Problem(ptype, order, *dims)
+    ctx.set_problem(P)
+    ptr, pairs, off = ctx.slot_offsets()
+    slot = R.cell_slot_map(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"]).reshape(-1, P.nd)
+    dm = P["dofmap"]
+    assert ptr[-1] == len(pairs) == np.count_nonzero(dm < P.n_owned)
+    for r in range(P.n_owned):
+        pr = pairs[ptr[r]:ptr[r + 1]]
+        assert np.all(np.diff(pr.astype(np.int64)) > 0)
+        assert np.all(dm[pr] == r)
+        got = P["rowptr"][r] + off.reshape(-1, P.nd)[ptr[r]:ptr[r + 1]].astype(np.int64)
+        assert np.array_equal(got, slot[pr])
+
+
+@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6]])
+def test_operator_matches_oracle(pt, oracle, ctx, ptype, order, dims):
+    P = pt.host.Problem(ptype, order, *dims)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    A = ctx.matrix_values()
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal((P.n_owned + P.n_ghost) * P.bs)
+    y = ctx.apply_operator(p)
+    y_ref = oracle.spmv(P.bs, P.n_owned, P["rowptr"], P["cols"], A, p)
+    assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+
+
+@pytest.mark.parametrize("precond", ["jacobi", "none"])
+@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6]])
+def test_cg_matches_oracle(pt, oracle, ctx, ptype, order, dims, precond):
+    P = pt.host.Problem(ptype, order, *dims)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    x_ref, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref,
+                                      kmax=5000, rtol=1e-8, precond=precond)
+    k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond=precond)
+    assert abs(k - k_ref) <= 1, (k, k_ref)
+    assert rel < 1e-8
+    if k == k_ref:
+        assert abs(rel - rel_ref) <= 1e-10 * max(1.0, rel_ref) + 1e-3 * rel_ref
+    x = ctx.solution()[: P.n_owned * P.bs]
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+    assert ctx.solution_norm() == pytest.approx(np.linalg.norm(x), rel=1e-12)
+    # true residual through the operator seam
+    xl = ctx.solution()
+    r = b_ref - ctx.apply_operator(xl)
+    assert np.linalg.norm(r) / np.linalg.norm(b_ref) < 5e-8
+
+
+def test_cg_kmax_and_minimum_iterations(pt, ctx):
+    """cg.h:57-59,78-79,85: at most kmax, at least one iteration, returns k."""
+    P = pt.host.Problem("poisson", 1, 8, 8, 8)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    k, rel = ctx.cg_solve(kmax=7, rtol=1e-30)
+    assert k == 7
+    k, rel = ctx.cg_solve(kmax=50, rtol=1e3)
+    assert k == 1
+    k, rel = ctx.cg_solve(kmax=50, rtol=1e-8)  # cg.h default kmax: may or may not converge
+    assert 1 <= k <= 50
+
+
+def test_bitwise_deterministic(pt, ctx):
+    """No floating-point atomics anywhere: two runs give identical bits."""
+    P = pt.host.Problem("elasticity", 1, 10, 9, 11)
+    out = []
+    for _ in range(2):
+        ctx.set_problem(P)
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        k, rel = ctx.cg_solve(kmax=2000, rtol=1e-8)
+        out.append((ctx.matrix_values().copy(), ctx.rhs().copy(), ctx.solution().copy(), k, rel))
+    for a, b in zip(out[0], out[1]):
+        assert np.array_equal(a, b)
+
+
+def test_errors_are_reported_not_thrown(pt, ctx):
+    P = pt.host.Problem("poisson", 1, 3, 3, 3)
+    ctx.set_problem(P)
+    with pytest.raises(RuntimeError, match="matrix not assembled"):
+        ctx.cg_solve()
+    with pytest.raises(RuntimeError, match="out of range"):
+        ctx._check(pt.abi.lib().ptb_set_bc(ctx._h, 1, np.array([10**6], np.int32).ctypes.data))
+
+
+def test_config1_full_size_against_oracle(pt, oracle, ctx):
+    """BASELINE config[0]: Poisson P1, 500k DOFs (78x78x79), CG + Jacobi rtol 1e-8."""
+    Nx, Ny, Nz, r = pt.host.cube_sizing(500000, False, 1, 1, 1)
+    P = pt.host.Problem("poisson", 1, Nx << r, Ny << r, Nz << r)
+    assert (P.n_owned, P.n_cells, P.nnz) == (499280, 2883816, 7339102)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    _check_matrix(P, ctx.matrix_values(), A_ref)
+    assert np.abs(ctx.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    x_ref, k_ref, rel_ref = oracle.cg(1, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref,
+                                      kmax=10000, rtol=1e-8, precond="jacobi", nthreads=1)
+    k, rel = ctx.cg_solve(kmax=10000, rtol=1e-8, precond="jacobi")
+    assert abs(k - k_ref) <= 1 and rel < 1e-8
+    x = ctx.solution()
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
+def test_large_properties_elasticity(pt, ctx):
+    """Size-independent properties at a size the oracle would not finish quickly (3.2M DOFs):
+    symmetry via <Au, v> = <u, Av>, rigid-body modes in the kernel away from the BC, and the CG
+    solution's true residual."""
+    P = pt.host.Problem("elasticity", 1, 101, 102, 103)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    rng = np.random.default_rng(5)
+    n = P.n_owned * 3
+    u, v = rng.standard_normal(n), rng.standard_normal(n)
+    Au, Av = ctx.apply_operator(u), ctx.apply_operator(v)
+    assert abs(Au @ v - u @ Av) <= 1e-12 * np.linalg.norm(Au) * np.linalg.norm(v)
+    X = P["dof_x"].reshape(-1, 3)
+    m = np.zeros_like(X); m[:, 0] = -X[:, 1]; m[:, 1] = X[:, 0]
+    y = ctx.apply_operator(m.reshape(-1)).reshape(-1, 3)
+    far = X[:, 1] > 2.5 / 102  # rows whose cells do not touch the clamped y = 0 plane
+    assert np.abs(y[far]).max() <= 1e-10 * 1e6
+    b = ctx.rhs()
+    k, rel = ctx.cg_solve(kmax=20000, rtol=1e-8)
+    assert rel < 1e-8
+    r = b - ctx.apply_operator(ctx.solution())
+    assert np.linalg.norm(r) / np.linalg.norm(b) < 1e-7

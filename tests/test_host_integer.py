@@ -1,0 +1,115 @@
+"""Integer side: sizing replay, mesh/dofmap/sparsity/slot map -- product C++ vs the independent
+numpy restatement in oracle/intmaps_ref.py (bit-identical), plus closed-form counts."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sizing.json")))
+
+
+@pytest.mark.parametrize("case", GOLD, ids=[c["name"] for c in GOLD])
+def test_sizing_matches_golden(pt, case):
+    """create_cube_mesh sizing, src/mesh.cpp:78-151, against tests/golden/sizing.json."""
+    got = pt.host.cube_sizing(case["target"], case["total"], case["dofs_per_node"], case["order"],
+                              case["nproc"])
+    assert list(got) == case["sizing"]
+    Nx, Ny, Nz, r = got
+    assert list(pt.host.num_entities(Nx, Ny, Nz, r)) == case["entities"]
+    assert pt.host.num_pdofs(Nx, Ny, Nz, r, case["order"]) == case["pdofs"]
+
+
+def test_order_not_supported(pt):
+    with pytest.raises(RuntimeError, match="Order not supported"):
+        pt.host.num_pdofs(2, 2, 2, 0, 5)
+    with pytest.raises(RuntimeError, match="Unknown problem type"):
+        pt.host.Problem("stokes", 1, 2, 2, 2)
+
+
+CASES = [("poisson", 1, (2, 3, 4), 1), ("poisson", 2, (3, 2, 3), 1), ("poisson", 3, (2, 2, 3), 1),
+         ("elasticity", 1, (3, 2, 5), 2), ("poisson", 1, (2, 2, 7), 3), ("poisson", 2, (2, 3, 4), 2),
+         ("elasticity", 3, (2, 2, 4), 2), ("poisson", 3, (1, 1, 1), 1)]
+
+
+@pytest.mark.parametrize("ptype,order,dims,nranks", CASES)
+def test_host_arrays_bit_identical_to_numpy_restatement(pt, ptype, order, dims, nranks):
+    from oracle import intmaps_ref as R
+    for rank in range(nranks):
+        P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+        Q = R.RefProblem(ptype, order, *dims, rank, nranks)
+        for s in pt.host.SCALARS:
+            assert getattr(P, s) == getattr(Q, s), s
+        for a in pt.host.ARRAYS:
+            x, y = P[a], Q[a]
+            assert x.shape == y.shape, a
+            if x.dtype.kind == "f":
+                np.testing.assert_allclose(x, y, rtol=1e-14, atol=1e-15, err_msg=a)
+            else:
+                assert np.array_equal(x, y), a
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("dims", [(4, 3, 5), (2, 6, 3)])
+def test_counts_match_closed_forms(pt, order, dims):
+    """DOFs = mesh.cpp:56-74; nnz = SURVEY 8d closed forms; facets = 4(ij+ik+jk)."""
+    i, j, k = dims
+    P = pt.host.Problem("poisson", order, i, j, k)
+    s, t = i * j + i * k + j * k, i + j + k
+    assert P.n_global == pt.host.num_pdofs(i, j, k, 0, order) == P.n_owned
+    nnz = {1: 15 * i * j * k + 7 * s + 3 * t + 1, 2: 230 * i * j * k + 46 * s + 8 * t + 1,
+           3: 1311 * i * j * k + 153 * s + 15 * t + 1}[order]
+    assert P.nnz == nnz
+    assert P.n_facets == 4 * s
+    assert P.n_cells == 6 * i * j * k
+
+
+@pytest.mark.parametrize("ptype,order,dims,nranks", CASES[:6])
+def test_cell_slot_map_bit_identical(pt, ptype, order, dims, nranks):
+    """The cell -> CSR-slot map (host-only entry point of the C-ABI) vs the numpy restatement."""
+    from oracle import intmaps_ref as R
+    for rank in range(nranks):
+        P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+        got = pt.abi.build_cell_slot_map(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+        ref = R.cell_slot_map(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+        assert np.array_equal(got, ref)
+
+
+def test_partition_covers_global_problem(pt):
+    """Owned ranges tile the global numbering; every rank's owned rows equal the serial rows."""
+    dims, order = (3, 2, 7), 2
+    S = pt.host.Problem("poisson", order, *dims)
+    cols_g = [None] * S.n_owned
+    tot = 0
+    for rank in range(3):
+        P = pt.host.Problem("poisson", order, *dims, rank, 3)
+        assert P.global_offset == tot
+        tot += P.n_owned
+        l2g = np.concatenate([np.arange(P.global_offset, P.global_offset + P.n_owned),
+                              P["ghost_global"]])
+        rp, cl = P["rowptr"], P["cols"]
+        for r in range(P.n_owned):
+            got = np.sort(l2g[cl[rp[r]:rp[r + 1]]])
+            ref = S["cols"][S["rowptr"][P.global_offset + r]:S["rowptr"][P.global_offset + r + 1]]
+            assert np.array_equal(got, ref)
+        np.testing.assert_array_equal(P["dof_x"].reshape(-1, 3)[:P.n_owned],
+                                      S["dof_x"].reshape(-1, 3)[P.global_offset:tot])
+    assert tot == S.n_global
+
+
+def test_abi_library_exports_every_declared_symbol(pt):
+    """-m "not gpu": the C-ABI library loads and exports all of include/ptb200.h; no compute."""
+    L = pt.abi.lib()
+    names = pt.abi.declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), n
+
+
+def test_no_cpu_fallback(pt):
+    """Without a CUDA device the product must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CUDA device"):
+        pt.abi.Context(0)
