@@ -1,0 +1,398 @@
+#!/usr/bin/env python
+"""bench.py -- the hot path of FEniCS/performance-test on B200: ZZZ Assemble matrix +
+ZZZ Assemble vector + ZZZ Solve (cg.h CG + Jacobi, rtol 1e-8) on the unit-cube tet mesh.
+
+    python bench.py --gpus N --steps K --warmup W                 (N = 1)
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        CPU restatement of the reference on the host cores
+
+One "step" = one pass of the hot path on device-resident mesh/dofmap/pattern data: assemble A,
+assemble b, solve to rtol 1e-8. Prints ONE JSON line (rank 0):
+
+  metric/value   CG DOF-iterations/s of the ZZZ Solve stage, whole job (the reference's own formula,
+                 src/cgpoisson_problem.cpp:236-241: num_it * ndofs_global / t_solve)
+  assembled_nnz_per_s   stored CSR nnz / ZZZ Assemble matrix time (second half of BASELINE metric)
+  ms_per_step    whole step (assemble matrix + vector + solve), max over ranks
+  e2e            same metric through the C-ABI with HOST buffers: per step, coordinates and source
+                 terms are copied host->device from pinned memory and b, u are copied back
+  roofline       dominant kernel (SpMV inside CG): algorithmic bytes / measured launch time vs the
+                 measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline   the CPU oracle ("port": restatement, not DOLFINx/PETSc) on a bounded sample
+
+Workloads (BASELINE.json configs): default = configs[1] "Poisson P1 weak scaling 20M DOFs/GPU";
+--workload elasticity = configs[2] "Elasticity P1 strong scaling 10M DOFs"; --workload small =
+configs[0] "Poisson P1 500k".
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (problem_type, scaling, ndofs, order, description)
+    "poisson": ("poisson", "weak", 20_000_000, 1, "Poisson P1 weak scaling 20M DOFs/GPU, CG+Jacobi rtol 1e-8"),
+    "elasticity": ("elasticity", "strong", 10_000_000, 1, "Elasticity P1 strong scaling 10M DOFs total, CG+Jacobi rtol 1e-8"),
+    "small": ("poisson", "weak", 500_000, 1, "Poisson P1 unit cube 500k DOFs/GPU, CG+Jacobi rtol 1e-8"),
+}
+KMAX = 10000  # PETSc's default -ksp_max_it; cg.h's own default of 50 never converges at these sizes
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="poisson", choices=sorted(WORKLOADS))
+    ap.add_argument("--ndofs", type=int, default=None, help="override the workload's --ndofs")
+    ap.add_argument("--cpu-sample-ndofs", type=int, default=2_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.rows, self.proc = device, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "200", "-i", str(self.device)], stdout=subprocess.PIPE,
+                stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])), mx.append(float(r[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def sizing(pt, wl, nranks, ndofs_override=None):
+    ptype, scaling, ndofs, order, desc = WORKLOADS[wl]
+    if ndofs_override:
+        ndofs = ndofs_override
+    dpn = 3 if ptype == "elasticity" else 1
+    Nx, Ny, Nz, r = pt.host.cube_sizing(ndofs, scaling == "strong", dpn, order, nranks)
+    return ptype, order, (Nx << r, Ny << r, Nz << r), (Nx, Ny, Nz, r), scaling, ndofs
+
+
+def algorithmic_bytes(P):
+    """SpMV 12*nnz + 20*n (scalar CSR) / 76*nnzb + 52*nb (3x3 BCSR); CG vectors
+    96 B/DOF (Jacobi); assembly: values written once + dofmaps + coordinates + markers."""
+    n, nnz, bs = P.n_owned, P.nnz, P.bs
+    spmv = 12 * nnz + 20 * n if bs == 1 else 76 * nnz + 52 * n
+    cg_iter = spmv + 96 * n * bs
+    asm = 8 * nnz * bs * bs + P.n_cells * (16 + 4 * P.nd) + 24 * (n + P.n_ghost) + (n + P.n_ghost)
+    return spmv, cg_iter, asm
+
+
+def run_reference(args):
+    """--impl reference: the CPU restatement (oracle, -Ofast like src/CMakeLists.txt:19-20) with
+    all host threads, on a bounded sample of the same workload. DOLFINx/PETSc/MPI are not
+    installable here, so this is kind='port' (BASELINE.md section 2)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pt = importlib.import_module("performance-test_b200")
+    import oracle
+    oracle.build()
+    nthreads = oracle.max_threads()
+    ptype, order, dims, base, scaling, ndofs = sizing(pt, args.workload, 1, args.cpu_sample_ndofs)
+    P = pt.host.Problem(ptype, order, *dims)
+    ndof = P.n_owned * P.bs
+
+    def step():
+        t0 = time.perf_counter()
+        A = oracle.assemble_matrix(P, nthreads=nthreads, fast=True)
+        t1 = time.perf_counter()
+        b = oracle.assemble_vector(P, fast=True)
+        t2 = time.perf_counter()
+        x, k, rel = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=KMAX, rtol=1e-8,
+                              precond="jacobi", nthreads=nthreads, fast=True)
+        t3 = time.perf_counter()
+        return t1 - t0, t2 - t1, t3 - t2, k
+
+    for _ in range(min(args.warmup, 1)):
+        step()
+    ts = [step() for _ in range(args.steps)]
+    t_am = sum(t[0] for t in ts)
+    t_solve = sum(t[2] for t in ts)
+    iters = sum(t[3] for t in ts)
+    total = sum(t[0] + t[1] + t[2] for t in ts)
+    value = iters * ndof / t_solve
+    wl = WORKLOADS[args.workload]
+    sample = (f"{ptype} P{order} at --ndofs {args.cpu_sample_ndofs} ({ndof} DOFs, {P.n_cells} cells), "
+              f"full hot path to rtol 1e-8, {nthreads} OpenMP threads")
+    line = {
+        "impl": "reference", "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "scaling": wl[1], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "assembled_nnz_per_s": P.nnz * P.bs * P.bs * args.steps / t_am,
+        "cg_iterations": iters // args.steps,
+        "config": {"workload": wl[4], "cpu_sample": sample},
+        "cpu_baseline": {"value": value, "unit": "DOF-iters/s", "cores": nthreads, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "DOF-iters/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(pt, args):
+    """Oracle on 1 core on a bounded sample (rank 0, N = 1 only)."""
+    import oracle
+    oracle.build()
+    ptype, order, dims, base, scaling, ndofs = sizing(pt, args.workload, 1, args.cpu_sample_ndofs)
+    P = pt.host.Problem(ptype, order, *dims)
+    t0 = time.perf_counter()
+    A = oracle.assemble_matrix(P, nthreads=1, fast=True)
+    t1 = time.perf_counter()
+    b = oracle.assemble_vector(P, fast=True)
+    kcap = 60  # bounded: 60 CG iterations are enough for a stable per-iteration rate
+    t2 = time.perf_counter()
+    x, k, rel = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=kcap, rtol=1e-8,
+                          precond="jacobi", nthreads=1, fast=True)
+    t3 = time.perf_counter()
+    ndof = P.n_owned * P.bs
+    return {"value": k * ndof / (t3 - t2), "unit": "DOF-iters/s", "cores": 1, "kind": "port",
+            "assembled_nnz_per_s": P.nnz * P.bs * P.bs / (t1 - t0),
+            "sample": (f"CPU restatement (oracle, gcc -Ofast, 1 core; not DOLFINx/PETSc): {ptype} "
+                       f"P{order} at --ndofs {args.cpu_sample_ndofs} ({ndof} DOFs): matrix assembly "
+                       f"{t1 - t0:.2f} s, vector {t2 - t1:.2f} s, first {k} CG+Jacobi iterations "
+                       f"{t3 - t2:.2f} s")}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    pt = importlib.import_module("performance-test_b200")
+    abi = pt.abi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allmax(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- setup (untimed): host mesh/dofmap/pattern, upload, NCCL bootstrap -------------------
+    ptype, order, dims, base, scaling, ndofs_arg = sizing(pt, args.workload, world, args.ndofs)
+    t_setup0 = time.perf_counter()
+    P = pt.host.Problem(ptype, order, *dims, rank, world)
+    t_host = time.perf_counter() - t_setup0
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = abi.Context(local_rank, stream=stream)
+    if world > 1:
+        uid = [abi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.comm_init(rank, world, uid[0])
+    t0 = time.perf_counter()
+    ctx.set_problem(P)
+    t_upload = time.perf_counter() - t0
+    ndofs_global = P.n_global * P.bs
+    nnz_global = allsum(float(P.nnz * P.bs * P.bs))
+
+    # pinned host buffers for the e2e leg
+    nl = (P.n_owned + P.n_ghost) * P.bs
+    x_pin = torch.from_numpy(np.array(P["x"])).pin_memory()
+    f_pin = torch.from_numpy(np.array(P["f"])).pin_memory()
+    g_pin = torch.from_numpy(np.array(P["g"])).pin_memory() if len(P["g"]) else None
+    b_pin = torch.empty(P.n_owned * P.bs, dtype=torch.float64).pin_memory()
+    u_pin = torch.empty(nl, dtype=torch.float64).pin_memory()
+    h2d = x_pin.numel() * 8 + f_pin.numel() * 8 + (g_pin.numel() * 8 if g_pin is not None else 0)
+    d2h = b_pin.numel() * 8 + u_pin.numel() * 8
+
+    state = {}
+
+    def step(e2e=False):
+        if e2e:
+            ctx.update_geometry(x_pin.numpy())
+            ctx.set_source(f_pin.numpy(), None if g_pin is None else g_pin.numpy())
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        k, rel = ctx.cg_solve(kmax=KMAX, rtol=1e-8, precond="jacobi")
+        if e2e:
+            ctx.rhs(out=b_pin.numpy())
+            ctx.solution(out=u_pin.numpy())
+        state.update(k=k, rel=rel, am=ctx.stage_ms(abi.STAGE_ASSEMBLE_MATRIX),
+                     av=ctx.stage_ms(abi.STAGE_ASSEMBLE_VECTOR), sv=ctx.stage_ms(abi.STAGE_SOLVE))
+        return k
+
+    for _ in range(args.warmup):
+        step()
+
+    def timed(nsteps, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        am = sv = 0.0
+        iters = 0
+        barrier()
+        ev0.record()
+        for _ in range(nsteps):
+            iters += step(e2e)
+            am += state["am"]
+            sv += state["sv"]
+        ev1.record()
+        barrier()
+        ms = allmax(ev0.elapsed_time(ev1))
+        return ms, allmax(am), allmax(sv), iters
+
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, am_ms, sv_ms, iters = timed(args.steps, e2e=False)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, am_e2e, sv_e2e, iters_e2e = timed(args.steps, e2e=True)
+
+    value = iters * ndofs_global / (sv_ms * 1e-3)
+    nnz_per_s = nnz_global * args.steps / (am_ms * 1e-3)
+    # e2e: the same metric with the whole host-buffer step as the denominator share of the solve:
+    # (iterations * DOFs) / (time of the e2e steps minus nothing) -- copies and assembly included.
+    e2e_value = iters_e2e * ndofs_global / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMV inside CG), timed live with CUDA events -------
+    step()  # leaves p, r, x in their end-of-solve state
+    t_spmv = ctx.time_kernel(abi.KERNEL_SPMV, 30)
+    t_upd = ctx.time_kernel(abi.KERNEL_CG_UPDATE, 30)
+    t_dir = ctx.time_kernel(abi.KERNEL_CG_DIRECTION, 30)
+    t_am = ctx.time_kernel(abi.KERNEL_ASSEMBLE_MATRIX, 5)
+    t_av = ctx.time_kernel(abi.KERNEL_ASSEMBLE_VECTOR, 5)
+    spmv_b, cg_b, asm_b = algorithmic_bytes(P)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = spmv_b / (t_spmv * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    roofline = {"bound": "hbm", "kernel": "spmv_sell (y = A p + p.y inside CG)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": spmv_b, "ms_per_launch": t_spmv,
+                "other_kernels": {
+                    "cg_update": {"ms": t_upd, "GBps": 56.0 * P.n_owned * P.bs / t_upd / 1e6},
+                    "cg_direction": {"ms": t_dir, "GBps": 32.0 * P.n_owned * P.bs / t_dir / 1e6},
+                    "assemble_matrix": {"ms": t_am, "GBps": asm_b / t_am / 1e6,
+                                        "nnz_per_s": P.nnz * P.bs * P.bs / (t_am * 1e-3)},
+                    "assemble_vector": {"ms": t_av}},
+                "cg_iteration_frac_of_hbm_roofline":
+                    cg_b / ((t_spmv + t_upd + t_dir) * 1e-3) / 1e9 / peak}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(pt, args)
+
+    if rank == 0:
+        wl = WORKLOADS[args.workload]
+        line = {
+            "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl[1],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "assembled_nnz_per_s": nnz_per_s,
+            "stage_ms": {"assemble_matrix": am_ms / args.steps, "assemble_vector": state["av"],
+                         "solve": sv_ms / args.steps},
+            "cg_iterations": iters // args.steps, "rel_residual": state["rel"],
+            "ndofs_global": ndofs_global, "nnz_global": nnz_global,
+            "config": {"workload": wl[4], "problem_type": ptype, "order": order,
+                       "ndofs_arg": ndofs_arg, "scaling_type": scaling,
+                       "base_box": list(base[:3]), "refinements": base[3],
+                       "fine_box": list(dims), "partition": f"z-slabs x{world}",
+                       "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"
+                             if P.nnz * 12 * P.bs > 3e8 else "working set near L2 size: small config",
+                       "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "
+                                            "Plaza refinement (same entity counts)" if base[3] else None},
+            "e2e": {"value": e2e_value, "unit": "DOF-iters/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                    "note": "per step: x, f, g host->device from pinned memory, assemble A and b, "
+                            "solve, b and u device->host; value = iterations*DOFs / whole e2e time"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "setup_s": {"host_mesh_dofmap_pattern": t_host, "slot_map_and_upload": t_upload},
+            "device_bytes": ctx.device_bytes(),
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

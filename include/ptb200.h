@@ -117,6 +117,12 @@ int ptb_get_slot_offsets(ptb_ctx* ctx, int64_t* n_pairs, int64_t* pair_ptr, uint
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);
+/* Average device time in ms (CUDA events on the launching stream, after one warm-up launch) of
+ * `reps` back-to-back launches of one hot kernel on the resident data. Scratches the solver
+ * state (the next ptb_cg_solve re-initialises it); used by bench.py for the roofline numbers. */
+enum { PTB_KERNEL_SPMV = 0, PTB_KERNEL_CG_UPDATE = 1, PTB_KERNEL_CG_DIRECTION = 2,
+       PTB_KERNEL_ASSEMBLE_MATRIX = 3, PTB_KERNEL_ASSEMBLE_VECTOR = 4 };
+int ptb_time_kernel(ptb_ctx* ctx, int which, int reps, double* ms_avg);
 /* Kernels launched by this context so far. */
 int64_t ptb_launch_count(const ptb_ctx* ctx);
 /* Bytes of device memory held by the context. */

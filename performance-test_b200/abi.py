@@ -15,6 +15,8 @@ _lib = None
 POISSON, ELASTICITY = 0, 1
 PC_NONE, PC_JACOBI = 0, 1
 STAGE_ASSEMBLE_MATRIX, STAGE_ASSEMBLE_VECTOR, STAGE_SOLVE, STAGE_SPMV = 0, 1, 2, 3
+KERNEL_SPMV, KERNEL_CG_UPDATE, KERNEL_CG_DIRECTION, KERNEL_ASSEMBLE_MATRIX, \
+    KERNEL_ASSEMBLE_VECTOR = range(5)
 PROBLEMS = {"poisson": POISSON, "cgpoisson": POISSON, "elasticity": ELASTICITY}
 PRECOND = {"none": PC_NONE, "jacobi": PC_JACOBI}
 
@@ -64,6 +66,7 @@ def lib():
         L.ptb_solution_norm.argtypes = [vp, C.POINTER(dbl)]
         L.ptb_build_cell_slot_map.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
+        L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
         L.ptb_stage_ms.restype = dbl
         L.ptb_launch_count.argtypes = [vp]
@@ -232,6 +235,12 @@ class Context:
     # ---- instrumentation -------------------------------------------------------------------
     def stage_ms(self, stage):
         return lib().ptb_stage_ms(self._h, stage)
+
+    def time_kernel(self, which, reps=20):
+        """Average ms per launch of one hot kernel (KERNEL_* constants) on the resident data."""
+        ms = C.c_double()
+        self._check(lib().ptb_time_kernel(self._h, which, reps, C.byref(ms)))
+        return ms.value
 
     def launch_count(self):
         return lib().ptb_launch_count(self._h)

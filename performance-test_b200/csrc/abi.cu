@@ -566,6 +566,51 @@ int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32
   });
 }
 
+int ptb_time_kernel(ptb_ctx* c, int which, int reps, double* ms_avg)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->matrix_assembled && c->have_source, "ptb_time_kernel: assemble first");
+    need(reps > 0 && ms_avg, "ptb_time_kernel: reps must be positive");
+    // benign scalars: alpha = 0, beta = 1, never converged
+    CgState s{};
+    s.py = 1.0, s.rr = 1.0, s.rz = 1.0, s.rz_old = 0.0, s.rnorm0 = 1.0, s.rtol2 = 0.0, s.rnorm = 1.0;
+    CgState sd = s;
+    sd.rz_old = 1.0;
+    PTB_CUDA(cudaMemcpyAsync(&c->cg.p[0], &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));
+    PTB_CUDA(cudaMemcpyAsync(&c->cg.p[1], &sd, sizeof(s), cudaMemcpyHostToDevice, c->stream));
+    MatrixArgs MA{c->n_owned, c->n_slices, c->so_bits, c->so_words, c->xyz.p, c->x_dofmap.p,
+                  c->dofmap.p, c->bc.p, c->rowptr.p, c->mat_off.p, c->adj_off.p, c->cols.p,
+                  c->adj.p, c->adjso.p, c->vals.p, c->dinv.p};
+    VectorArgs VA{c->n_owned, c->n_slices, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p,
+                  c->adj_off.p, c->adj.p, c->f.p, c->b.p};
+    FacetArgs FA{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto one = [&] {
+      switch (which)
+      {
+      case PTB_KERNEL_SPMV: launch_spmv(c, c->p.p, c->y.p, &c->cg.p[0]); break;
+      case PTB_KERNEL_CG_UPDATE: launch_cg_update(c, c->dinv.p, &c->cg.p[0]); break;
+      case PTB_KERNEL_CG_DIRECTION:
+        launch_cg_direction(c, c->dinv.p, &c->cg.p[1], reinterpret_cast<CgState*>(c->partials.p));
+        break;
+      case PTB_KERNEL_ASSEMBLE_MATRIX: launch_assemble_matrix(c, MA); break;
+      case PTB_KERNEL_ASSEMBLE_VECTOR: launch_assemble_vector(c, VA, FA); break;
+      default: throw std::runtime_error("ptb_time_kernel: unknown kernel");
+      }
+    };
+    one();
+    PTB_CUDA(cudaEventRecord(c->ev0, c->stream));
+    for (int i = 0; i < reps; ++i)
+      one();
+    PTB_CUDA(cudaEventRecord(c->ev1, c->stream));
+    PTB_CUDA(cudaEventSynchronize(c->ev1));
+    float ms = 0.f;
+    PTB_CUDA(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    *ms_avg = ms / reps;
+    c->vector_assembled = c->vector_assembled && which != PTB_KERNEL_ASSEMBLE_VECTOR;
+  });
+}
+
 double ptb_stage_ms(const ptb_ctx* c, int stage)
 {
   return (c && stage >= 0 && stage < PTB_STAGE_COUNT) ? c->stage_ms[stage] : -1.0;
