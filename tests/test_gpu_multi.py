@@ -1,0 +1,114 @@
+"""Partitioned (multi-rank) CUDA path.
+
+* test_partitioned_assembly_...: every rank's slab is assembled on ONE GPU (no communication is
+  needed for assembly: ghost-cell layer) and must reproduce the serial rows bit for bit.
+* test_two_rank_solve_...: needs >= 2 GPUs (skipped otherwise): one process per GPU, NCCL halo +
+  all-reduce inside ptb_cg_solve, compared with the single-partition oracle.
+"""
+import importlib
+import os
+import sys
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("ptype,dims,world", [("poisson", (9, 8, 10), 3), ("elasticity", (6, 5, 8), 2)])
+def test_partitioned_assembly_is_partition_independent(pt, ptype, dims, world):
+    S = pt.host.Problem(ptype, 1, *dims)
+    ctx = pt.abi.Context(0)
+    ctx.set_problem(S)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_s, b_s = ctx.matrix_values().copy(), ctx.rhs().copy()
+    bs = S.bs
+    for rank in range(world):
+        P = pt.host.Problem(ptype, 1, *dims, rank, world)
+        ctx.set_problem(P)
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        A, b = ctx.matrix_values(), ctx.rhs()
+        off, n = P.global_offset, P.n_owned
+        assert np.array_equal(b, b_s[off * bs:(off + n) * bs])
+        l2g = np.concatenate([np.arange(off, off + n), P["ghost_global"]])
+        rp, cl = P["rowptr"], P["cols"]
+        for r in range(n):
+            g = l2g[cl[rp[r]:rp[r + 1]]]
+            o = np.argsort(g)
+            srow = slice(S["rowptr"][off + r], S["rowptr"][off + r + 1])
+            assert np.array_equal(g[o], S["cols"][srow])
+            assert np.array_equal(A.reshape(-1, bs * bs)[rp[r]:rp[r + 1]][o],
+                                  A_s.reshape(-1, bs * bs)[srow])
+    ctx.close()
+
+
+def _worker(rank, world, port, ptype, dims, out):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pt = importlib.import_module("performance-test_b200")
+        uid = [pt.abi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx = pt.abi.Context(rank)
+        ctx.comm_init(rank, world, uid[0])
+        P = pt.host.Problem(ptype, 1, *dims, rank, world)
+        ctx.set_problem(P)
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        x = ctx.solution()
+        nrm = ctx.solution_norm()
+        rng = np.random.default_rng(7)
+        pg = rng.standard_normal(P.n_global * P.bs)  # same on every rank
+        pl = np.zeros((P.n_owned + P.n_ghost) * P.bs)
+        pl[: P.n_owned * P.bs] = pg[P.global_offset * P.bs:(P.global_offset + P.n_owned) * P.bs]
+        y = ctx.apply_operator(pl)  # ghosts of p are filled by the halo exchange
+        out.put((rank, k, rel, P.global_offset, P.n_owned, x, nrm, y, np.array(P["ghost_global"])))
+        ctx.close()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ptype,dims", [("poisson", (12, 11, 14)), ("elasticity", (7, 8, 9))])
+def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    world = 2
+    ctxm = mp.get_context("spawn")
+    out = ctxm.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, ptype, dims, out))
+             for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([out.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    S = pt.host.Problem(ptype, 1, *dims)
+    bs = S.bs
+    A_s, b_s = oracle.assemble_matrix(S), oracle.assemble_vector(S)
+    x_s, k_s, rel_s = oracle.cg(bs, S.n_owned, S["rowptr"], S["cols"], A_s, b_s, kmax=5000,
+                                rtol=1e-8, precond="jacobi")
+    rng = np.random.default_rng(7)
+    pg = rng.standard_normal(S.n_global * bs)
+    y_s = oracle.spmv(bs, S.n_owned, S["rowptr"], S["cols"], A_s, pg)
+    xg = np.zeros(S.n_owned * bs)
+    for rank, k, rel, off, n, x, nrm, y, gg in res:
+        assert abs(k - k_s) <= 1 and rel < 1e-8
+        xg[off * bs:(off + n) * bs] = x[: n * bs]
+        assert np.abs(y - y_s[off * bs:(off + n) * bs]).max() <= 1e-12 * np.abs(y_s).max()
+    for rank, k, rel, off, n, x, nrm, y, gg in res:
+        assert np.array_equal(x.reshape(-1, bs)[n:], xg.reshape(-1, bs)[gg])  # ghosts current
+        assert nrm == pytest.approx(np.linalg.norm(xg), rel=1e-12)
+    assert np.linalg.norm(xg - x_s) <= 1e-6 * np.linalg.norm(x_s)
