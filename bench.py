@@ -37,6 +37,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1; the (untimed) host setup is OpenMP code, so give each rank
+# its share of the host cores before any OpenMP runtime starts.
+_world = int(os.environ.get("WORLD_SIZE", "1"))
+if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+    os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // _world))
+
 WORKLOADS = {
     # name: (problem_type, scaling, ndofs, order, description)
     "poisson": ("poisson", "weak", 20_000_000, 1, "Poisson P1 weak scaling 20M DOFs/GPU, CG+Jacobi rtol 1e-8"),

@@ -72,7 +72,7 @@ std::int64_t ptb_ctx::device_bytes() const
 {
   return xyz.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
-         + adjso.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
          + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes();
@@ -173,6 +173,8 @@ int ptb_update_geometry(ptb_ctx* c, const double* x)
     PTB_CUDA(cudaMemcpy2DAsync(c->xyz.p, 4 * sizeof(double), x, 3 * sizeof(double),
                                3 * sizeof(double), c->n_vertices, cudaMemcpyHostToDevice,
                                c->stream));
+    if (c->have_space)
+      launch_gather_xdof(c);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
   });
 }
@@ -198,6 +200,30 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
     c->bc.alloc(static_cast<std::size_t>(n_owned) + n_ghost);
     c->bc.zero(c->stream);
     c->h_bc_dofs.clear();
+    // Geometry by dof index: local dofs 0..3 of a Lagrange cell sit on its vertices.
+    {
+      const std::int64_t nl = static_cast<std::int64_t>(n_owned) + n_ghost;
+      std::vector<std::int32_t> dv(nl, -1);
+      std::vector<std::int32_t> xd(static_cast<std::size_t>(c->n_cells) * 4);
+      PTB_CUDA(cudaMemcpy(xd.data(), c->x_dofmap.p, xd.size() * sizeof(std::int32_t),
+                          cudaMemcpyDeviceToHost));
+      const int nd = c->nd;
+      bool bad = false;
+#pragma omp parallel for schedule(static) reduction(|| : bad)
+      for (std::int64_t cell = 0; cell < c->n_cells; ++cell)
+        for (int i = 0; i < 4; ++i)
+        {
+          const std::int32_t d = dofmap[cell * nd + i];
+          if (d < 0 || d >= nl)
+            bad = true;
+          else
+            dv[d] = xd[cell * 4 + i]; // every writer of dv[d] stores the same vertex
+        }
+      need(!bad, "ptb_set_space: dofmap entry out of range");
+      c->dof_vertex.upload(dv, c->stream);
+      c->xdof.alloc(static_cast<std::size_t>(nl) * 4);
+      launch_gather_xdof(c);
+    }
     alloc_vectors(c);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_space = true, c->have_pattern = false, c->have_source = false;
@@ -227,8 +253,18 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     c->mat_off.upload(L.mat_off, c->stream);
     c->adj_off.upload(L.adj_off, c->stream);
     c->cols.upload(L.cols, c->stream);
-    c->adj.upload(L.adj, c->stream);
-    c->adjso.upload(L.adjso, c->stream);
+    if (!L.adjrot.empty())
+    {
+      // P1: the rotated one-word slot map is all the kernels need
+      c->adjrot.upload(L.adjrot, c->stream);
+      c->adj.release(), c->adjso.release();
+    }
+    else
+    {
+      c->adjrot.release();
+      c->adj.upload(L.adj, c->stream);
+      c->adjso.upload(L.adjso, c->stream);
+    }
     c->vals.alloc(L.cols.size() * c->bs * c->bs);
     c->vals.zero(c->stream);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -343,7 +379,7 @@ int ptb_assemble_matrix(ptb_ctx* c)
     StageTimer t(c, PTB_STAGE_ASSEMBLE_MATRIX);
     MatrixArgs A{c->n_owned, c->n_slices, c->so_bits, c->so_words, c->xyz.p, c->x_dofmap.p,
                  c->dofmap.p, c->bc.p, c->rowptr.p, c->mat_off.p, c->adj_off.p, c->cols.p,
-                 c->adj.p, c->adjso.p, c->vals.p, c->dinv.p};
+                 c->adj.p, c->adjso.p, c->adjrot.p, c->xdof.p, c->max_w, c->vals.p, c->dinv.p};
     launch_assemble_matrix(c, A);
     t.stop();
     c->matrix_assembled = true;
@@ -357,7 +393,8 @@ int ptb_assemble_vector(ptb_ctx* c)
     need(c->have_pattern && c->have_source, "ptb_assemble_vector: pattern / source not set");
     StageTimer t(c, PTB_STAGE_ASSEMBLE_VECTOR);
     VectorArgs A{c->n_owned, c->n_slices, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p,
-                 c->adj_off.p, c->adj.p, c->f.p, c->b.p};
+                 c->adj_off.p, c->adj.p, c->adjrot.p, c->xdof.p, c->mat_off.p, c->cols.p, c->max_w, c->f.p,
+                 c->b.p};
     FacetArgs F{c->n_frows, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p, c->frow_ids.p,
                 c->frow_ptr.p, c->fent.p, c->g.p, c->b.p};
     launch_assemble_vector(c, A, F);
@@ -581,9 +618,10 @@ int ptb_time_kernel(ptb_ctx* c, int which, int reps, double* ms_avg)
     PTB_CUDA(cudaMemcpyAsync(&c->cg.p[1], &sd, sizeof(s), cudaMemcpyHostToDevice, c->stream));
     MatrixArgs MA{c->n_owned, c->n_slices, c->so_bits, c->so_words, c->xyz.p, c->x_dofmap.p,
                   c->dofmap.p, c->bc.p, c->rowptr.p, c->mat_off.p, c->adj_off.p, c->cols.p,
-                  c->adj.p, c->adjso.p, c->vals.p, c->dinv.p};
+                  c->adj.p, c->adjso.p, c->adjrot.p, c->xdof.p, c->max_w, c->vals.p, c->dinv.p};
     VectorArgs VA{c->n_owned, c->n_slices, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p,
-                  c->adj_off.p, c->adj.p, c->f.p, c->b.p};
+                  c->adj_off.p, c->adj.p, c->adjrot.p, c->xdof.p, c->mat_off.p, c->cols.p, c->max_w, c->f.p,
+                 c->b.p};
     FacetArgs FA{0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     auto one = [&] {
       switch (which)

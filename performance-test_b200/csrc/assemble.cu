@@ -3,14 +3,20 @@
 //   fem::assemble_vector + DirichletBC::set                        poisson_problem.cpp:150-155
 // and of the FFCx tabulate_tensor kernels generated from Poisson.py:31-32 / Elasticity.py:39-40.
 //
-// Scheme ("row-owner gather"): one thread owns one scalar matrix row. It walks the
-// row's cells in ascending cell order (the precomputed dof -> (cell, local index) list), evaluates
-// only *its* row of each element matrix in registers, and adds the entries into per-thread
-// accumulators in shared memory at the precomputed in-row slot offsets. Each CSR value is written
-// exactly once, by its owner, in a fixed summation order: deterministic, no atomics, no zero-fill
-// pass, and the BC row/column zeroing, the unit BC diagonal and the Jacobi diagonal are fused into
-// the epilogue. All per-row streams (cell lists, slot offsets, column indices, values) are stored
-// SELL-32 so every warp access is a full 128/256-byte line.
+// Scheme ("row-owner gather"): one thread owns one scalar matrix row.
+//   prologue  the row's column list *is* its vertex star (P1): the thread stages the edge vectors
+//             E[k] = X(col_k) - X(row) of its <= w neighbours in shared memory, once;
+//   loop      it walks the row's cells in ascending cell order. A cell is one 32-bit word holding
+//             the in-row slot offsets of its four vertices, rotated so the owner comes first (the
+//             compressed cell -> CSR-slot map). Three edge vectors come from shared memory, the
+//             owner's row of the element matrix is evaluated in registers (cofactor form) and
+//             added into per-thread accumulators in shared memory at those offsets;
+//   epilogue  BC row/column zeroing, unit BC diagonal (set_diagonal), one coalesced write of every
+//             stored value, and 1/diag for Jacobi.
+// Each CSR value is written exactly once, by its owner, in a fixed summation order: deterministic,
+// no atomics, no zero-fill pass, independent of the partition. All per-row streams are SELL-32 so
+// every warp access is a full 128/256-byte line; the cell loop touches global memory once per
+// cell (4 bytes per thread).
 #include "kernels.h"
 
 namespace ptb
@@ -30,10 +36,10 @@ __device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
 __device__ __forceinline__ double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ double comp(Vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 
-__device__ __forceinline__ Vec3 load_vertex(const double* __restrict__ xyz, int v)
+__device__ __forceinline__ Vec3 load_point(const double* __restrict__ xyz4, std::int64_t v)
 {
   // padded [n][4]: two 16-byte loads
-  const double2* p = reinterpret_cast<const double2*>(xyz + 4 * static_cast<std::int64_t>(v));
+  const double2* p = reinterpret_cast<const double2*>(xyz4 + 4 * v);
   const double2 a = __ldg(p), b = __ldg(p + 1);
   return {a.x, a.y, b.x};
 }
@@ -43,22 +49,15 @@ __device__ __forceinline__ int sel4(int4 v, int i)
   return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
 }
 
-// P1 geometry seen from local vertex li: vertices are taken in the rotated order
-// (li, li+1, li+2, li+3) mod 4, so "my" basis function is always number 0. Returns the scaled
-// gradients c_t = det * grad(phi_t) (cofactor vectors) and det. Ae[0][t] = c_0.c_t / (6 |det|).
+// P1 geometry seen from the owner (local vertex 0 after rotation): scaled gradients
+// c_t = det * grad(phi_t) (cofactor vectors) from the three edge vectors. Ae[0][t] = c_0.c_t/(6|det|).
 struct P1Geom
 {
   Vec3 c0, c1, c2, c3;
   double det;
 };
-
-__device__ __forceinline__ P1Geom p1_geometry(const double* __restrict__ xyz, int4 v, int li)
+__device__ __forceinline__ P1Geom p1_geometry(Vec3 e1, Vec3 e2, Vec3 e3)
 {
-  const Vec3 X0 = load_vertex(xyz, sel4(v, li));
-  const Vec3 X1 = load_vertex(xyz, sel4(v, (li + 1) & 3));
-  const Vec3 X2 = load_vertex(xyz, sel4(v, (li + 2) & 3));
-  const Vec3 X3 = load_vertex(xyz, sel4(v, (li + 3) & 3));
-  const Vec3 e1 = X1 - X0, e2 = X2 - X0, e3 = X3 - X0;
   P1Geom G;
   G.c1 = cross(e2, e3);
   G.c2 = cross(e3, e1);
@@ -68,81 +67,108 @@ __device__ __forceinline__ P1Geom p1_geometry(const double* __restrict__ xyz, in
   return G;
 }
 
-// In-row slot offset of rotated local column t (nd = 4, one packed word per pair).
-__device__ __forceinline__ int slot4(std::uint32_t word, int li, int t, int so_bits)
+constexpr int MAT_THREADS_1 = 128; // 4 slices of scalar rows
+constexpr int MAT_THREADS_3 = 192; // 2 slices x 3 components
+
+// Shared-memory staging of the row star. E is [w][3] per row, column-major over the 32 lanes of
+// the slice: E[(k*3 + d)*32 + lane].
+__device__ __forceinline__ Vec3 star_edge(const double* E, int k, int lane)
 {
-  const int j = (li + t) & 3;
-  return so_bits == 8 ? (word >> (8 * j)) & 0xffu : 0; // 16-bit packing handled by slot4w
+  return {E[(k * 3 + 0) * 32 + lane], E[(k * 3 + 1) * 32 + lane], E[(k * 3 + 2) * 32 + lane]};
 }
 
 // ------------------------------------------------------------------------------------------
-// Matrix, P1. BS = 1: Poisson, thread = row. BS = 3: elasticity, thread = (node row, component a);
-// the three warps of a slice hold a = 0, 1, 2.
+// Matrix, P1. BS = 1: Poisson, one warp per slice. BS = 3: elasticity, three warps per slice hold
+// the components a = 0, 1, 2 of the 32 block rows and share the staged star.
+// Shared memory per slice: E [w*3][32] doubles, then per warp acc [w*BS][32] doubles.
 // ------------------------------------------------------------------------------------------
 template <int BS>
-__global__ void __launch_bounds__(BS == 1 ? 128 : 192)
+__global__ void __launch_bounds__(BS == 1 ? MAT_THREADS_1 : MAT_THREADS_3)
 assemble_matrix_p1(MatrixArgs A)
 {
-  extern __shared__ double acc[]; // [w * BS][blockDim.x]
+  extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slices_per_cta = (blockDim.x >> 5) / BS;
-  const int a = BS == 1 ? 0 : warp % BS;
-  const std::int32_t slice = blockIdx.x * slices_per_cta + warp / BS;
-  if (slice >= A.n_slices)
-    return;
+  const int sl = warp / BS;                // slice within the CTA
+  const int a = BS == 1 ? 0 : warp % BS;   // component handled by this warp
+  const std::int32_t slice = blockIdx.x * slices_per_cta + sl;
+  const bool slice_ok = slice < A.n_slices;
   const std::int32_t row = slice * 32 + lane;
-  const bool live = row < A.n_rows;
-  const std::int64_t mo = A.mat_off[slice];
-  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
-  const std::int64_t ao = A.adj_off[slice];
-  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
-  const int nt = blockDim.x;
+  const bool live = slice_ok && row < A.n_rows;
+  const std::int64_t mo = slice_ok ? A.mat_off[slice] : 0;
+  const int w = slice_ok ? static_cast<int>((A.mat_off[slice + 1] - mo) >> 5) : 0;
+  const std::int64_t ao = slice_ok ? A.adj_off[slice] : 0;
+  const int wa = slice_ok ? static_cast<int>((A.adj_off[slice + 1] - ao) >> 5) : 0;
 
+  const int per_slice = A.max_w * (3 + BS * BS) * 32; // doubles
+  double* E = smem + sl * per_slice;
+  double* acc = E + A.max_w * 3 * 32 + a * (A.max_w * BS * 32);
+
+  // ---- prologue: stage the star (the BS warps of a slice split the columns) -----------------
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  for (int k = a; k < w; k += BS)
+  {
+    const std::int32_t col = A.cols[mo + k * 32 + lane];
+    const Vec3 e = load_point(A.xdof, col) - X0;
+    E[(k * 3 + 0) * 32 + lane] = e.x;
+    E[(k * 3 + 1) * 32 + lane] = e.y;
+    E[(k * 3 + 2) * 32 + lane] = e.z;
+  }
   for (int k = 0; k < w * BS; ++k)
-    acc[k * nt + tid] = 0.0;
+    acc[k * 32 + lane] = 0.0;
+  if constexpr (BS == 1)
+    __syncwarp();
+  else
+    __syncthreads();
 
   constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
   constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
 
+  // ---- cell loop --------------------------------------------------------------------------
+  double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0; // owner's own (diagonal) block row, kept in registers
   for (int k = 0; k < wa; ++k)
   {
-    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
-    if (pair == ADJ_INVALID_DEV)
+    const std::uint32_t word = A.adjrot[ao + k * 32 + lane];
+    if (word == ADJ_INVALID_DEV)
       continue;
-    const std::uint32_t sow = A.adjso[(ao + k * 32) * A.so_words + lane];
-    const std::uint32_t sow1 = A.so_bits == 16 ? A.adjso[(ao + k * 32) * A.so_words + 32 + lane] : 0u;
-    const std::uint32_t cell = pair >> 2;
-    const int li = pair & 3;
-    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
-    const P1Geom G = p1_geometry(A.xyz, v, li);
+    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+    const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
+                                 star_edge(E, o3, lane));
     const double s = 1.0 / (6.0 * fabs(G.det));
-    const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
+    if constexpr (BS == 1)
     {
-      const int j = (li + t) & 3;
-      const int o = A.so_bits == 8 ? (sow >> (8 * j)) & 0xffu
-                                   : ((j < 2 ? sow : sow1) >> (16 * (j & 1))) & 0xffffu;
-      if constexpr (BS == 1)
-      {
-        acc[o * nt + tid] += s * dot(G.c0, ct[t]);
-      }
-      else
-      {
-        // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
-        const double d = dot(G.c0, ct[t]);
-        const double c0a = comp(G.c0, a), cta = comp(ct[t], a);
-        const double vb[3] = {s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x),
-                              s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y),
-                              s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z)};
+      dg0 += s * dot(G.c0, G.c0);
+      acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
+      acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
+      acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
+    }
+    else
+    {
+      // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
+      const double c0a = comp(G.c0, a);
+      const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
+      const int ot[4] = {0, o1, o2, o3};
 #pragma unroll
-        for (int b = 0; b < 3; ++b)
-          acc[(o * 3 + b) * nt + tid] += vb[b];
+      for (int t = 0; t < 4; ++t)
+      {
+        const double d = dot(G.c0, ct[t]);
+        const double cta = comp(ct[t], a);
+        const double v0 = s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x);
+        const double v1 = s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y);
+        const double v2 = s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z);
+        if (t == 0)
+          dg0 += v0, dg1 += v1, dg2 += v2;
+        else
+        {
+          acc[(ot[t] * 3 + 0) * 32 + lane] += v0;
+          acc[(ot[t] * 3 + 1) * 32 + lane] += v1;
+          acc[(ot[t] * 3 + 2) * 32 + lane] += v2;
+        }
       }
     }
   }
 
-  // Epilogue: BC rows/cols -> 0, BC diagonal -> 1 (set_diagonal), write values once, coalesced.
+  // ---- epilogue: BC rows/cols -> 0, BC diagonal -> 1, write values once, coalesced ----------
   const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
   const bool bc_row = live && A.bc[row];
   double diag = 1.0;
@@ -150,30 +176,32 @@ assemble_matrix_p1(MatrixArgs A)
   {
     const std::int32_t col = A.cols[mo + k * 32 + lane];
     const bool real = k < len;
+    const bool own = real && col == row;
     const bool bc_any = bc_row || (real && A.bc[col]);
     if constexpr (BS == 1)
     {
-      double val = acc[k * nt + tid];
+      double val = own ? dg0 : acc[k * 32 + lane];
       if (bc_any)
-        val = (col == row) ? 1.0 : 0.0;
+        val = own ? 1.0 : 0.0;
       if (!real)
         val = 0.0;
       A.vals[mo + k * 32 + lane] = val;
-      if (real && col == row)
+      if (own)
         diag = val;
     }
     else
     {
+      const double dg[3] = {dg0, dg1, dg2};
 #pragma unroll
       for (int b = 0; b < 3; ++b)
       {
-        double val = acc[(k * 3 + b) * nt + tid];
+        double val = own ? dg[b] : acc[(k * 3 + b) * 32 + lane];
         if (bc_any)
-          val = (col == row && a == b) ? 1.0 : 0.0;
+          val = (own && a == b) ? 1.0 : 0.0;
         if (!real)
           val = 0.0;
         A.vals[(mo + k * 32) * 9 + (a * 3 + b) * 32 + lane] = val;
-        if (real && col == row && a == b)
+        if (own && a == b)
           diag = val;
       }
     }
@@ -184,40 +212,63 @@ assemble_matrix_p1(MatrixArgs A)
 
 // ------------------------------------------------------------------------------------------
 // Vector, P1: b[row] = sum_cells |det|/120 (sum_j f_j + f_row); thread = (row, component).
+// Shared memory per slice: E [w*3][32], F [w*BS][32] (source term at the star's vertices).
 // ------------------------------------------------------------------------------------------
 template <int BS>
-__global__ void __launch_bounds__(BS == 1 ? 128 : 192)
+__global__ void __launch_bounds__(BS == 1 ? MAT_THREADS_1 : MAT_THREADS_3)
 assemble_vector_p1(VectorArgs A)
 {
+  extern __shared__ double smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int slices_per_cta = (blockDim.x >> 5) / BS;
+  const int sl = warp / BS;
   const int a = BS == 1 ? 0 : warp % BS;
-  const std::int32_t slice = blockIdx.x * slices_per_cta + warp / BS;
-  if (slice >= A.n_slices)
-    return;
+  const std::int32_t slice = blockIdx.x * slices_per_cta + sl;
+  const bool slice_ok = slice < A.n_slices;
   const std::int32_t row = slice * 32 + lane;
-  if (row >= A.n_rows)
-    return;
-  const std::int64_t ao = A.adj_off[slice];
-  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  const bool live = slice_ok && row < A.n_rows;
+  const std::int64_t mo = slice_ok ? A.mat_off[slice] : 0;
+  const int w = slice_ok ? static_cast<int>((A.mat_off[slice + 1] - mo) >> 5) : 0;
+  const std::int64_t ao = slice_ok ? A.adj_off[slice] : 0;
+  const int wa = slice_ok ? static_cast<int>((A.adj_off[slice + 1] - ao) >> 5) : 0;
+
+  const int per_slice = A.max_w * (3 + BS) * 32;
+  double* E = smem + sl * per_slice;
+  double* F = E + A.max_w * 3 * 32;
+
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  for (int k = a; k < w; k += BS)
+  {
+    const std::int64_t col = A.cols[mo + k * 32 + lane];
+    const Vec3 e = load_point(A.xdof, col) - X0;
+    E[(k * 3 + 0) * 32 + lane] = e.x;
+    E[(k * 3 + 1) * 32 + lane] = e.y;
+    E[(k * 3 + 2) * 32 + lane] = e.z;
+#pragma unroll
+    for (int b = 0; b < BS; ++b)
+      F[(k * BS + b) * 32 + lane] = __ldg(A.f + col * BS + b);
+  }
+  if constexpr (BS == 1)
+    __syncwarp();
+  else
+    __syncthreads();
+
+  const double f0 = live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
   double sum = 0.0;
   for (int k = 0; k < wa; ++k)
   {
-    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
-    if (pair == ADJ_INVALID_DEV)
-      break; // lists are front-packed
-    const std::uint32_t cell = pair >> 2;
-    const int li = pair & 3;
-    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
-    const int4 d = __ldg(reinterpret_cast<const int4*>(A.dofmap) + cell);
-    const P1Geom G = p1_geometry(A.xyz, v, li);
-    const double f0 = __ldg(A.f + static_cast<std::int64_t>(sel4(d, li)) * BS + a);
-    const double f1 = __ldg(A.f + static_cast<std::int64_t>(sel4(d, (li + 1) & 3)) * BS + a);
-    const double f2 = __ldg(A.f + static_cast<std::int64_t>(sel4(d, (li + 2) & 3)) * BS + a);
-    const double f3 = __ldg(A.f + static_cast<std::int64_t>(sel4(d, (li + 3) & 3)) * BS + a);
-    sum += fabs(G.det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
+    const std::uint32_t word = A.adjrot[ao + k * 32 + lane];
+    if (word == ADJ_INVALID_DEV)
+      continue;
+    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+    const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane), e3 = star_edge(E, o3, lane);
+    const double det = dot(e1, cross(e2, e3));
+    const double f1 = F[(o1 * BS + a) * 32 + lane], f2 = F[(o2 * BS + a) * 32 + lane],
+                 f3 = F[(o3 * BS + a) * 32 + lane];
+    sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
   }
-  A.b[static_cast<std::int64_t>(row) * BS + a] = A.bc[row] ? 0.0 : sum;
+  if (live)
+    A.b[static_cast<std::int64_t>(row) * BS + a] = A.bc[row] ? 0.0 : sum;
 }
 
 // Exterior facets, P1 (Poisson.py:32 g*v*ds): thread = boundary row; facet mass = area/12 (1+delta).
@@ -237,16 +288,21 @@ __global__ void assemble_facets_p1(FacetArgs A)
     const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
     const int4 d = __ldg(reinterpret_cast<const int4*>(A.dofmap) + cell);
     // the two other facet vertices: the locals != lf, != li
-    int o[2], n = 0;
+    int o0 = -1, o1 = -1;
 #pragma unroll
     for (int t = 0; t < 4; ++t)
-      if (t != lf && t != li && n < 2)
-        o[n++] = t;
-    const Vec3 X0 = load_vertex(A.xyz, sel4(v, li)), X1 = load_vertex(A.xyz, sel4(v, o[0])),
-               X2 = load_vertex(A.xyz, sel4(v, o[1]));
+      if (t != lf && t != li)
+      {
+        if (o0 < 0)
+          o0 = t;
+        else
+          o1 = t;
+      }
+    const Vec3 X0 = load_point(A.xyz, sel4(v, li)), X1 = load_point(A.xyz, sel4(v, o0)),
+               X2 = load_point(A.xyz, sel4(v, o1));
     const Vec3 cr = cross(X1 - X0, X2 - X0);
     const double area2 = sqrt(dot(cr, cr)); // 2 * area
-    const double g0 = A.g[sel4(d, li)], g1 = A.g[sel4(d, o[0])], g2 = A.g[sel4(d, o[1])];
+    const double g0 = A.g[sel4(d, li)], g1 = A.g[sel4(d, o0)], g2 = A.g[sel4(d, o1)];
     sum += area2 * (1.0 / 24.0) * ((g0 + g1 + g2) + g0);
   }
   A.b[row] += sum;
@@ -268,29 +324,54 @@ __global__ void sell_to_csr(std::int32_t n_rows, int bs2, const std::int64_t* __
       out[(r0 + k) * bs2 + e] = vals[(mo + k * 32) * bs2 + e * 32 + lane];
 }
 
+// Coordinates by dof index (vertex dofs): xdof[d] = xyz[dof_vertex[d]].
+__global__ void gather_xdof(std::int64_t n, const std::int32_t* __restrict__ dof_vertex,
+                            const double* __restrict__ xyz, double* __restrict__ xdof)
+{
+  const std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  const std::int32_t v = dof_vertex[i];
+  double2 a = {0.0, 0.0}, b = {0.0, 0.0};
+  if (v >= 0)
+  {
+    const double2* p = reinterpret_cast<const double2*>(xyz + 4 * static_cast<std::int64_t>(v));
+    a = p[0], b = p[1];
+  }
+  double2* q = reinterpret_cast<double2*>(xdof + 4 * i);
+  q[0] = a, q[1] = b;
+}
+
+template <typename K>
+void set_smem(K kernel, std::size_t smem)
+{
+  if (smem > 227 * 1024)
+    throw std::runtime_error("assembly: row too long for the shared-memory star/accumulators");
+  PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+}
+
 } // namespace
 
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
 {
   if (c->order != 1)
     throw std::runtime_error("assemble_matrix: only order 1 kernels are built in this round");
+  if (A.adjrot == nullptr)
+    throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
   if (c->bs == 1)
   {
-    const int threads = 128, spc = 4;
-    const std::size_t smem = static_cast<std::size_t>(c->max_w) * threads * sizeof(double);
-    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_p1<1>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assemble_matrix_p1<1><<<(A.n_slices + spc - 1) / spc, threads, smem, c->stream>>>(A);
+    const int spc = MAT_THREADS_1 / 32;
+    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);
+    set_smem(assemble_matrix_p1<1>, smem);
+    assemble_matrix_p1<1><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_1, smem, c->stream>>>(A);
   }
   else
   {
-    const int threads = 192, spc = 2;
-    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 3 * threads * sizeof(double);
-    if (smem > 227 * 1024)
-      throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
-    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_p1<3>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assemble_matrix_p1<3><<<(A.n_slices + spc - 1) / spc, threads, smem, c->stream>>>(A);
+    const int spc = MAT_THREADS_3 / 96;
+    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 12 * 32 * spc * sizeof(double);
+    set_smem(assemble_matrix_p1<3>, smem);
+    assemble_matrix_p1<3><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_3, smem, c->stream>>>(A);
   }
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
@@ -300,10 +381,22 @@ void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
 {
   if (c->order != 1)
     throw std::runtime_error("assemble_vector: only order 1 kernels are built in this round");
+  if (A.adjrot == nullptr)
+    throw std::runtime_error("assemble_vector: a P1 row has more than 254 columns");
   if (c->bs == 1)
-    assemble_vector_p1<1><<<(A.n_slices + 3) / 4, 128, 0, c->stream>>>(A);
+  {
+    const int spc = MAT_THREADS_1 / 32;
+    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);
+    set_smem(assemble_vector_p1<1>, smem);
+    assemble_vector_p1<1><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_1, smem, c->stream>>>(A);
+  }
   else
-    assemble_vector_p1<3><<<(A.n_slices + 1) / 2, 192, 0, c->stream>>>(A);
+  {
+    const int spc = MAT_THREADS_3 / 96;
+    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 6 * 32 * spc * sizeof(double);
+    set_smem(assemble_vector_p1<3>, smem);
+    assemble_vector_p1<3><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_3, smem, c->stream>>>(A);
+  }
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
   if (F.n_frows > 0 && F.g != nullptr)
@@ -319,6 +412,15 @@ void launch_sell_to_csr(ptb_ctx* c, double* out)
   const int bs2 = c->bs * c->bs;
   sell_to_csr<<<(c->n_owned + 127) / 128, 128, 0, c->stream>>>(c->n_owned, bs2, c->rowptr.p,
                                                                c->mat_off.p, c->vals.p, out);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+}
+
+void launch_gather_xdof(ptb_ctx* c)
+{
+  const std::int64_t n = static_cast<std::int64_t>(c->n_owned) + c->n_ghost;
+  gather_xdof<<<static_cast<int>((n + 255) / 256), 256, 0, c->stream>>>(n, c->dof_vertex.p,
+                                                                        c->xyz.p, c->xdof.p);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }

@@ -109,6 +109,8 @@ struct ptb_ctx
 
   // geometry + dofmaps
   ptb::DevBuf<double> xyz;        // [n_vertices][4] padded
+  ptb::DevBuf<double> xdof;       // [n_local dofs][4]: coordinates of vertex dofs, by dof index
+  ptb::DevBuf<std::int32_t> dof_vertex; // [n_local dofs] geometry vertex of a vertex dof, else -1
   ptb::DevBuf<std::int32_t> x_dofmap, dofmap;
   ptb::DevBuf<std::uint8_t> bc;   // marker per local block dof
   std::vector<std::int32_t> h_bc_dofs, h_dofmap; // host copy of the dofmap for the integer maps
@@ -120,7 +122,7 @@ struct ptb_ctx
   ptb::DevBuf<std::int64_t> rowptr, mat_off, adj_off;
   ptb::DevBuf<std::int32_t> cols;      // SELL
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry
-  ptb::DevBuf<std::uint32_t> adj, adjso;
+  ptb::DevBuf<std::uint32_t> adj, adjso, adjrot;
   // host copies of the compressed slot map (parity inspection)
   ptb::RowAdjacency h_adj;
   std::vector<std::uint16_t> h_so;

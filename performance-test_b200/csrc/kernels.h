@@ -21,6 +21,9 @@ struct MatrixArgs
   const std::int32_t* cols;
   const std::uint32_t* adj;
   const std::uint32_t* adjso;
+  const std::uint32_t* adjrot;
+  const double* xdof;
+  int max_w;
   double* vals;
   double* dinv;
 };
@@ -34,6 +37,11 @@ struct VectorArgs
   const std::uint8_t* bc;
   const std::int64_t* adj_off;
   const std::uint32_t* adj;
+  const std::uint32_t* adjrot;
+  const double* xdof;
+  const std::int64_t* mat_off;
+  const std::int32_t* cols;
+  int max_w;
   const double* f;
   double* b;
 };
@@ -64,6 +72,8 @@ struct SpmvArgs
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 void launch_sell_to_csr(ptb_ctx* c, double* out);
+/// xdof[d] = xyz[dof_vertex[d]] for vertex dofs.
+void launch_gather_xdof(ptb_ctx* c);
 
 // cg.cu
 int cg_grid(const ptb_ctx* c);

@@ -41,6 +41,9 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
   L.cols.resize(static_cast<std::size_t>(L.mat_off[S]));
   L.adj.resize(static_cast<std::size_t>(L.adj_off[S]));
   L.adjso.resize(static_cast<std::size_t>(L.adj_off[S]) * L.so_words);
+  const bool rot = nd == 4 && max_so < 255;
+  if (rot)
+    L.adjrot.resize(static_cast<std::size_t>(L.adj_off[S]));
   const std::uint32_t* pairs = adj.pairs.data();
 #pragma omp parallel for schedule(static)
   for (std::int32_t s = 0; s < S; ++s)
@@ -60,6 +63,19 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
       {
         const bool on = k < alen;
         L.adj[ao + k * 32 + lane] = on ? pairs[adj.ptr[r] + k] : ADJ_INVALID;
+        if (rot)
+        {
+          std::uint32_t word = ADJ_INVALID;
+          if (on)
+          {
+            const std::int64_t q = adj.ptr[r] + k;
+            const int li = pairs[q] & 3;
+            word = 0;
+            for (int t = 0; t < 4; ++t)
+              word |= static_cast<std::uint32_t>(so[q * 4 + ((li + t) & 3)]) << (8 * t);
+          }
+          L.adjrot[ao + k * 32 + lane] = word;
+        }
         for (int wd = 0; wd < L.so_words; ++wd)
         {
           std::uint32_t word = 0;

@@ -18,6 +18,9 @@ struct SellLayout
   std::vector<std::int64_t> mat_off, adj_off; // [n_slices + 1], in entries
   std::vector<std::int32_t> cols;             // padded with the row's first column (0 past n_rows)
   std::vector<std::uint32_t> adj, adjso;
+  // P1 only (nd == 4, offsets < 255): the four in-row offsets of a pair rotated so that the
+  // owner's own column comes first: byte t = offset of local vertex (li + t) & 3.
+  std::vector<std::uint32_t> adjrot;
 };
 
 void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
