@@ -80,8 +80,85 @@ __device__ __forceinline__ Vec3 star_edge(const double* E, int k, int lane)
 // ------------------------------------------------------------------------------------------
 // Matrix, P1. BS = 1: Poisson, one warp per slice. BS = 3: elasticity, three warps per slice hold
 // the components a = 0, 1, 2 of the 32 block rows and share the staged star.
-// Shared memory per slice: E [w*3][32] doubles, then per warp acc [w*BS][32] doubles.
+// Shared memory per slice: E [w*3][32] doubles, C [w][32] int32 columns, then per warp
+// acc [w*BS][32] doubles. Global loads are issued in chunks (LD_CHUNK independent loads in flight
+// per thread) because the occupancy is bounded by the shared-memory footprint.
 // ------------------------------------------------------------------------------------------
+constexpr int LD_CHUNK = 8;
+
+struct SliceView
+{
+  std::int32_t row;
+  bool live;
+  std::int64_t mo, ao;
+  int w, wa;
+};
+
+template <typename Args>
+__device__ __forceinline__ SliceView slice_view(const Args& A, std::int32_t slice, int lane)
+{
+  SliceView S;
+  const bool ok = slice < A.n_slices;
+  S.row = slice * 32 + lane;
+  S.live = ok && S.row < A.n_rows;
+  S.mo = ok ? A.mat_off[slice] : 0;
+  S.w = ok ? static_cast<int>((A.mat_off[slice + 1] - S.mo) >> 5) : 0;
+  S.ao = ok ? A.adj_off[slice] : 0;
+  S.wa = ok ? static_cast<int>((A.adj_off[slice + 1] - S.ao) >> 5) : 0;
+  return S;
+}
+
+// Stage the star of the slice: columns k = a, a + BS, ... are handled by this warp.
+template <int BS, bool WITH_F>
+__device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
+                                           const std::int32_t* __restrict__ cols,
+                                           const double* __restrict__ xdof, Vec3 X0, double* E,
+                                           std::int32_t* C, const double* __restrict__ f, double* F)
+{
+  for (int k0 = a; k0 < S.w; k0 += BS * LD_CHUNK)
+  {
+    std::int32_t c[LD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+    {
+      const int k = k0 + BS * j;
+      c[j] = k < S.w ? __ldg(cols + S.mo + k * 32 + lane) : -1;
+    }
+    Vec3 e[LD_CHUNK];
+    double fv[LD_CHUNK][WITH_F ? BS : 1];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        e[j] = load_point(xdof, c[j]);
+        if constexpr (WITH_F)
+        {
+#pragma unroll
+          for (int b = 0; b < BS; ++b)
+            fv[j][b] = __ldg(f + static_cast<std::int64_t>(c[j]) * BS + b);
+        }
+      }
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        const int k = k0 + BS * j;
+        const Vec3 d = e[j] - X0;
+        E[(k * 3 + 0) * 32 + lane] = d.x;
+        E[(k * 3 + 1) * 32 + lane] = d.y;
+        E[(k * 3 + 2) * 32 + lane] = d.z;
+        if (C != nullptr)
+          C[k * 32 + lane] = c[j];
+        if constexpr (WITH_F)
+        {
+#pragma unroll
+          for (int b = 0; b < BS; ++b)
+            F[(k * BS + b) * 32 + lane] = fv[j][b];
+        }
+      }
+  }
+}
+
 template <int BS>
 __global__ void __launch_bounds__(BS == 1 ? MAT_THREADS_1 : MAT_THREADS_3)
 assemble_matrix_p1(MatrixArgs A)
@@ -91,30 +168,19 @@ assemble_matrix_p1(MatrixArgs A)
   const int slices_per_cta = (blockDim.x >> 5) / BS;
   const int sl = warp / BS;                // slice within the CTA
   const int a = BS == 1 ? 0 : warp % BS;   // component handled by this warp
-  const std::int32_t slice = blockIdx.x * slices_per_cta + sl;
-  const bool slice_ok = slice < A.n_slices;
-  const std::int32_t row = slice * 32 + lane;
-  const bool live = slice_ok && row < A.n_rows;
-  const std::int64_t mo = slice_ok ? A.mat_off[slice] : 0;
-  const int w = slice_ok ? static_cast<int>((A.mat_off[slice + 1] - mo) >> 5) : 0;
-  const std::int64_t ao = slice_ok ? A.adj_off[slice] : 0;
-  const int wa = slice_ok ? static_cast<int>((A.adj_off[slice + 1] - ao) >> 5) : 0;
+  const SliceView S = slice_view(A, blockIdx.x * slices_per_cta + sl, lane);
+  const std::int32_t row = S.row;
 
-  const int per_slice = A.max_w * (3 + BS * BS) * 32; // doubles
+  // per slice: E (3w) + acc (BS*BS*w) doubles + C (w int32 = w/2 doubles)
+  const int per_slice = A.max_w * (3 + BS * BS) * 32 + (A.max_w * 32 + 1) / 2;
   double* E = smem + sl * per_slice;
   double* acc = E + A.max_w * 3 * 32 + a * (A.max_w * BS * 32);
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(E + A.max_w * (3 + BS * BS) * 32);
 
   // ---- prologue: stage the star (the BS warps of a slice split the columns) -----------------
-  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  for (int k = a; k < w; k += BS)
-  {
-    const std::int32_t col = A.cols[mo + k * 32 + lane];
-    const Vec3 e = load_point(A.xdof, col) - X0;
-    E[(k * 3 + 0) * 32 + lane] = e.x;
-    E[(k * 3 + 1) * 32 + lane] = e.y;
-    E[(k * 3 + 2) * 32 + lane] = e.z;
-  }
-  for (int k = 0; k < w * BS; ++k)
+  const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  stage_star<BS, false>(S, a, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr);
+  for (int k = 0; k < S.w * BS; ++k)
     acc[k * 32 + lane] = 0.0;
   if constexpr (BS == 1)
     __syncwarp();
@@ -126,87 +192,110 @@ assemble_matrix_p1(MatrixArgs A)
 
   // ---- cell loop --------------------------------------------------------------------------
   double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0; // owner's own (diagonal) block row, kept in registers
-  for (int k = 0; k < wa; ++k)
+  for (int k0 = 0; k0 < S.wa; k0 += LD_CHUNK)
   {
-    const std::uint32_t word = A.adjrot[ao + k * 32 + lane];
-    if (word == ADJ_INVALID_DEV)
-      continue;
-    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-    const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
-                                 star_edge(E, o3, lane));
-    const double s = 1.0 / (6.0 * fabs(G.det));
-    if constexpr (BS == 1)
-    {
-      dg0 += s * dot(G.c0, G.c0);
-      acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
-      acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
-      acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
-    }
-    else
-    {
-      // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
-      const double c0a = comp(G.c0, a);
-      const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
-      const int ot[4] = {0, o1, o2, o3};
+    std::uint32_t wd[LD_CHUNK];
 #pragma unroll
-      for (int t = 0; t < 4; ++t)
+    for (int j = 0; j < LD_CHUNK; ++j)
+      wd[j] = k0 + j < S.wa ? __ldg(A.adjrot + S.ao + (k0 + j) * 32 + lane) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+    {
+      const std::uint32_t word = wd[j];
+      if (word == ADJ_INVALID_DEV)
+        continue;
+      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+      const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
+                                   star_edge(E, o3, lane));
+      const double s = 1.0 / (6.0 * fabs(G.det));
+      if constexpr (BS == 1)
       {
-        const double d = dot(G.c0, ct[t]);
-        const double cta = comp(ct[t], a);
-        const double v0 = s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x);
-        const double v1 = s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y);
-        const double v2 = s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z);
-        if (t == 0)
-          dg0 += v0, dg1 += v1, dg2 += v2;
-        else
+        dg0 += s * dot(G.c0, G.c0);
+        acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
+        acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
+        acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
+      }
+      else
+      {
+        // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
+        const double c0a = comp(G.c0, a);
+        const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
+        const int ot[4] = {0, o1, o2, o3};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
         {
-          acc[(ot[t] * 3 + 0) * 32 + lane] += v0;
-          acc[(ot[t] * 3 + 1) * 32 + lane] += v1;
-          acc[(ot[t] * 3 + 2) * 32 + lane] += v2;
+          const double d = dot(G.c0, ct[t]);
+          const double cta = comp(ct[t], a);
+          const double v0 = s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x);
+          const double v1 = s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y);
+          const double v2 = s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z);
+          if (t == 0)
+            dg0 += v0, dg1 += v1, dg2 += v2;
+          else
+          {
+            acc[(ot[t] * 3 + 0) * 32 + lane] += v0;
+            acc[(ot[t] * 3 + 1) * 32 + lane] += v1;
+            acc[(ot[t] * 3 + 2) * 32 + lane] += v2;
+          }
         }
       }
     }
   }
 
   // ---- epilogue: BC rows/cols -> 0, BC diagonal -> 1, write values once, coalesced ----------
-  const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
-  const bool bc_row = live && A.bc[row];
+  const std::int64_t len = S.live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
+  const bool bc_row = S.live && A.bc[row];
   double diag = 1.0;
-  for (int k = 0; k < w; ++k)
+  for (int k0 = 0; k0 < S.w; k0 += LD_CHUNK)
   {
-    const std::int32_t col = A.cols[mo + k * 32 + lane];
-    const bool real = k < len;
-    const bool own = real && col == row;
-    const bool bc_any = bc_row || (real && A.bc[col]);
-    if constexpr (BS == 1)
-    {
-      double val = own ? dg0 : acc[k * 32 + lane];
-      if (bc_any)
-        val = own ? 1.0 : 0.0;
-      if (!real)
-        val = 0.0;
-      A.vals[mo + k * 32 + lane] = val;
-      if (own)
-        diag = val;
-    }
-    else
-    {
-      const double dg[3] = {dg0, dg1, dg2};
+    std::int32_t col[LD_CHUNK];
+    bool bcc[LD_CHUNK];
 #pragma unroll
-      for (int b = 0; b < 3; ++b)
+    for (int j = 0; j < LD_CHUNK; ++j)
+    {
+      const int k = k0 + j;
+      col[j] = k < S.w ? C[k * 32 + lane] : 0;
+      bcc[j] = k < len ? A.bc[col[j]] != 0 : false;
+    }
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+    {
+      const int k = k0 + j;
+      if (k >= S.w)
+        break;
+      const bool real = k < len;
+      const bool own = real && col[j] == row;
+      const bool bc_any = bc_row || bcc[j];
+      if constexpr (BS == 1)
       {
-        double val = own ? dg[b] : acc[(k * 3 + b) * 32 + lane];
+        double val = own ? dg0 : acc[k * 32 + lane];
         if (bc_any)
-          val = (own && a == b) ? 1.0 : 0.0;
+          val = own ? 1.0 : 0.0;
         if (!real)
           val = 0.0;
-        A.vals[(mo + k * 32) * 9 + (a * 3 + b) * 32 + lane] = val;
-        if (own && a == b)
+        A.vals[S.mo + k * 32 + lane] = val;
+        if (own)
           diag = val;
+      }
+      else
+      {
+        const double dg[3] = {dg0, dg1, dg2};
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+        {
+          double val = own ? dg[b] : acc[(k * 3 + b) * 32 + lane];
+          if (bc_any)
+            val = (own && a == b) ? 1.0 : 0.0;
+          if (!real)
+            val = 0.0;
+          A.vals[(S.mo + k * 32) * 9 + (a * 3 + b) * 32 + lane] = val;
+          if (own && a == b)
+            diag = val;
+        }
       }
     }
   }
-  if (live)
+  if (S.live)
     A.dinv[static_cast<std::int64_t>(row) * BS + a] = 1.0 / diag;
 }
 
@@ -223,51 +312,44 @@ assemble_vector_p1(VectorArgs A)
   const int slices_per_cta = (blockDim.x >> 5) / BS;
   const int sl = warp / BS;
   const int a = BS == 1 ? 0 : warp % BS;
-  const std::int32_t slice = blockIdx.x * slices_per_cta + sl;
-  const bool slice_ok = slice < A.n_slices;
-  const std::int32_t row = slice * 32 + lane;
-  const bool live = slice_ok && row < A.n_rows;
-  const std::int64_t mo = slice_ok ? A.mat_off[slice] : 0;
-  const int w = slice_ok ? static_cast<int>((A.mat_off[slice + 1] - mo) >> 5) : 0;
-  const std::int64_t ao = slice_ok ? A.adj_off[slice] : 0;
-  const int wa = slice_ok ? static_cast<int>((A.adj_off[slice + 1] - ao) >> 5) : 0;
+  const SliceView S = slice_view(A, blockIdx.x * slices_per_cta + sl, lane);
+  const std::int32_t row = S.row;
 
   const int per_slice = A.max_w * (3 + BS) * 32;
   double* E = smem + sl * per_slice;
   double* F = E + A.max_w * 3 * 32;
 
-  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  for (int k = a; k < w; k += BS)
-  {
-    const std::int64_t col = A.cols[mo + k * 32 + lane];
-    const Vec3 e = load_point(A.xdof, col) - X0;
-    E[(k * 3 + 0) * 32 + lane] = e.x;
-    E[(k * 3 + 1) * 32 + lane] = e.y;
-    E[(k * 3 + 2) * 32 + lane] = e.z;
-#pragma unroll
-    for (int b = 0; b < BS; ++b)
-      F[(k * BS + b) * 32 + lane] = __ldg(A.f + col * BS + b);
-  }
+  const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  stage_star<BS, true>(S, a, lane, A.cols, A.xdof, X0, E, nullptr, A.f, F);
   if constexpr (BS == 1)
     __syncwarp();
   else
     __syncthreads();
 
-  const double f0 = live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
+  const double f0 = S.live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
   double sum = 0.0;
-  for (int k = 0; k < wa; ++k)
+  for (int k0 = 0; k0 < S.wa; k0 += LD_CHUNK)
   {
-    const std::uint32_t word = A.adjrot[ao + k * 32 + lane];
-    if (word == ADJ_INVALID_DEV)
-      continue;
-    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-    const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane), e3 = star_edge(E, o3, lane);
-    const double det = dot(e1, cross(e2, e3));
-    const double f1 = F[(o1 * BS + a) * 32 + lane], f2 = F[(o2 * BS + a) * 32 + lane],
-                 f3 = F[(o3 * BS + a) * 32 + lane];
-    sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
+    std::uint32_t wd[LD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      wd[j] = k0 + j < S.wa ? __ldg(A.adjrot + S.ao + (k0 + j) * 32 + lane) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+    {
+      const std::uint32_t word = wd[j];
+      if (word == ADJ_INVALID_DEV)
+        continue;
+      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+      const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane),
+                 e3 = star_edge(E, o3, lane);
+      const double det = dot(e1, cross(e2, e3));
+      const double f1 = F[(o1 * BS + a) * 32 + lane], f2 = F[(o2 * BS + a) * 32 + lane],
+                   f3 = F[(o3 * BS + a) * 32 + lane];
+      sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
+    }
   }
-  if (live)
+  if (S.live)
     A.b[static_cast<std::int64_t>(row) * BS + a] = A.bc[row] ? 0.0 : sum;
 }
 
@@ -342,6 +424,11 @@ __global__ void gather_xdof(std::int64_t n, const std::int32_t* __restrict__ dof
   q[0] = a, q[1] = b;
 }
 
+std::size_t mat_smem_doubles(int max_w, int bs)
+{
+  return static_cast<std::size_t>(max_w) * (3 + bs * bs) * 32 + (static_cast<std::size_t>(max_w) * 32 + 1) / 2;
+}
+
 template <typename K>
 void set_smem(K kernel, std::size_t smem)
 {
@@ -362,14 +449,14 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
   if (c->bs == 1)
   {
     const int spc = MAT_THREADS_1 / 32;
-    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);
+    const std::size_t smem = mat_smem_doubles(c->max_w, 1) * spc * sizeof(double);
     set_smem(assemble_matrix_p1<1>, smem);
     assemble_matrix_p1<1><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_1, smem, c->stream>>>(A);
   }
   else
   {
     const int spc = MAT_THREADS_3 / 96;
-    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 12 * 32 * spc * sizeof(double);
+    const std::size_t smem = mat_smem_doubles(c->max_w, 3) * spc * sizeof(double);
     set_smem(assemble_matrix_p1<3>, smem);
     assemble_matrix_p1<3><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_3, smem, c->stream>>>(A);
   }
