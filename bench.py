@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--ndofs", type=int, default=None, help="override the workload's --ndofs")
     ap.add_argument("--cpu-sample-ndofs", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
+                    help="N>1: NVLink peer-memory kernels (default) or NCCL send/recv + all-reduce")
     return ap.parse_args()
 
 
@@ -255,13 +257,14 @@ def main():
     t_host = time.perf_counter() - t_setup0
     stream = torch.cuda.current_stream().cuda_stream
     ctx = abi.Context(local_rank, stream=stream)
-    if world > 1:
-        uid = [abi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
-        ctx.comm_init(rank, world, uid[0])
     t0 = time.perf_counter()
     ctx.set_problem(P)
     t_upload = time.perf_counter() - t0
+    if world > 1:
+        if args.comm == "nccl":
+            pt.dist.init_nccl(ctx, abi, dist, rank, world)
+        else:
+            pt.dist.connect_peers(ctx, P, dist, rank, world)
     ndofs_global = P.n_global * P.bs
     nnz_global = allsum(float(P.nnz * P.bs * P.bs))
 
@@ -379,6 +382,9 @@ def main():
                        "ndofs_arg": ndofs_arg, "scaling_type": scaling,
                        "base_box": list(base[:3]), "refinements": base[3],
                        "fine_box": list(dims), "partition": f"z-slabs x{world}",
+                       "comm": ("none" if world == 1 else
+                                "nvlink peer memory (halo pull + window all-reduce in the CG kernels)"
+                                if args.comm == "peer" else "nccl send/recv + allreduce"),
                        "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"
                              if P.nnz * 12 * P.bs > 3e8 else "working set near L2 size: small config",
                        "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "
@@ -395,6 +401,7 @@ def main():
             "device_bytes": ctx.device_bytes(),
         }
         print(json.dumps(line), flush=True)
+    barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -78,6 +78,16 @@ int ptb_set_halo(ptb_ctx* ctx, int n_nbr, const int32_t* nbr_ranks, const int32_
 int ptb_nccl_unique_id(void* out128);
 int ptb_comm_init(ptb_ctx* ctx, int rank, int nranks, const void* unique_id128);
 
+/* NCCL-free alternative over NVLink peer memory (CUDA IPC): the CG kernels pull ghost values
+ * straight out of the neighbours' vectors and all-reduce their dot products through per-rank
+ * windows -- no collective launches inside the solve. Call after ptb_set_space + ptb_set_halo:
+ * every rank exports 192 bytes (3 IPC handles), the host all-gathers them, every rank connects.
+ * src_index[j] = index, in the OWNER's local numbering, of the dof received as remote_indices[j]
+ * (i.e. the owner's local_indices entry that feeds it). Re-connect if the space is set again. */
+int ptb_peer_export(ptb_ctx* ctx, void* handles192);
+int ptb_peer_connect(ptb_ctx* ctx, int rank, int nranks, const void* all_handles,
+                     const int32_t* src_index);
+
 /* ---- hot calls -------------------------------------------------------------------------- */
 /* ZZZ Assemble matrix: element kernels + BC row/col zeroing + unit BC diagonal, deterministic
  * (no atomics). Also extracts the Jacobi diagonal. */

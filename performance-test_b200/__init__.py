@@ -36,5 +36,6 @@ def build(verbose: bool = False) -> None:
 
 from . import host  # noqa: E402
 from . import abi  # noqa: E402
+from . import dist  # noqa: E402
 
-__all__ = ["build", "host", "abi", "HOST_LIB", "ABI_LIB", "INCLUDE_DIR"]
+__all__ = ["build", "host", "abi", "dist", "HOST_LIB", "ABI_LIB", "INCLUDE_DIR"]

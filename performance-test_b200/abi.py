@@ -53,6 +53,8 @@ def lib():
         L.ptb_set_halo.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp]
         L.ptb_nccl_unique_id.argtypes = [vp]
         L.ptb_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+        L.ptb_peer_export.argtypes = [vp, vp]
+        L.ptb_peer_connect.argtypes = [vp, C.c_int, C.c_int, vp, vp]
         L.ptb_assemble_matrix.argtypes = [vp]
         L.ptb_assemble_vector.argtypes = [vp]
         L.ptb_cg_solve.argtypes = [vp, C.c_int, dbl, C.c_int, C.POINTER(C.c_int), C.POINTER(dbl)]
@@ -166,6 +168,17 @@ class Context:
 
     def comm_init(self, rank, nranks, unique_id: bytes):
         self._check(lib().ptb_comm_init(self._h, rank, nranks, C.c_char_p(unique_id)))
+
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(192)
+        self._check(lib().ptb_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank, nranks, all_handles: bytes, src_index):
+        assert len(all_handles) == 192 * nranks
+        si = _a(src_index, np.int32)
+        self._check(lib().ptb_peer_connect(self._h, rank, nranks, C.c_char_p(all_handles),
+                                           _ptr(si)))
 
     # ---- hot calls -----------------------------------------------------------------------
     def assemble_matrix(self):

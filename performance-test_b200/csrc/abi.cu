@@ -75,7 +75,8 @@ std::int64_t ptb_ctx::device_bytes() const
          + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
-         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes();
+         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes()
+         + peer.src_index.bytes();
 }
 
 extern "C" {
@@ -122,6 +123,7 @@ void ptb_destroy(ptb_ctx* c)
   cudaSetDevice(c->device);
   try
   {
+    peer_disconnect(c);
     comm_destroy(c);
   }
   catch (...)
@@ -367,6 +369,25 @@ int ptb_comm_init(ptb_ctx* c, int rank, int nranks, const void* id)
   });
 }
 
+int ptb_peer_export(ptb_ctx* c, void* handles192)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(handles192 != nullptr, "ptb_peer_export: NULL buffer");
+    peer_export(c, handles192);
+  });
+}
+
+int ptb_peer_connect(ptb_ctx* c, int rank, int nranks, const void* all_handles,
+                     const int32_t* src_index)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(all_handles != nullptr, "ptb_peer_connect: NULL handles");
+    peer_connect(c, rank, nranks, all_handles, src_index);
+  });
+}
+
 // ---------------------------------------------------------------------------------------------
 // hot calls
 // ---------------------------------------------------------------------------------------------
@@ -419,9 +440,10 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     // r0 = b - A x0 (cg.h:46-47): the action is evaluated even for x0 = 0, like the reference.
     halo_forward(c, c->x.p);
     launch_spmv(c, c->x.p, c->y.p, nullptr);
-    launch_cg_init(c, dinv, &st[1]);
+    const unsigned int e0 = next_red_epoch(c);
+    launch_cg_init(c, dinv, &st[1], e0);
     allreduce_sum(c, &st[1].rr, 2);
-    launch_cg_finish_init(c, &st[1], rtol);
+    launch_cg_finish_init(c, &st[1], rtol, e0);
 
     // Iterations are queued in batches; the stopping flag of batch j is read back while batch
     // j + 1 is already running, so the device never waits for the host. Kernels of iterations
@@ -443,11 +465,12 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
         CgState* cur = &st[it & 1];
         CgState* nxt = &st[(it + 1) & 1];
         halo_forward(c, c->p.p);
-        launch_spmv(c, c->p.p, c->y.p, cur);
+        const unsigned int ea = next_red_epoch(c), eb = next_red_epoch(c);
+        launch_spmv(c, c->p.p, c->y.p, cur, ea);
         allreduce_sum(c, &cur->py, 1);
-        launch_cg_update(c, dinv, cur);
+        launch_cg_update(c, dinv, cur, ea, eb);
         allreduce_sum(c, &cur->rr, 2);
-        launch_cg_direction(c, dinv, cur, nxt);
+        launch_cg_direction(c, dinv, cur, nxt, eb);
       }
       PTB_CUDA(cudaMemcpyAsync(&c->h_cg[slot], &st[(it + 1) & 1], sizeof(CgState),
                                cudaMemcpyDeviceToHost, c->stream));
@@ -463,6 +486,7 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     PTB_CUDA(cudaMemcpyAsync(&c->h_cg[0], &st[(it + 1) & 1], sizeof(CgState),
                              cudaMemcpyDeviceToHost, c->stream));
     halo_forward(c, c->x.p); // leave the ghosts of the solution current (cg.h:36-37)
+    peer_neighbour_barrier(c); // peers may still be reading x
     t.stop();
     cudaEventDestroy(evs[0]);
     cudaEventDestroy(evs[1]);
@@ -484,6 +508,7 @@ int ptb_apply_operator(ptb_ctx* c, const double* p_host, double* y_host)
     StageTimer t(c, PTB_STAGE_SPMV);
     halo_forward(c, c->p.p);
     launch_spmv(c, c->p.p, c->y.p, nullptr);
+    peer_neighbour_barrier(c); // peers may still be reading p
     t.stop();
     PTB_CUDA(cudaMemcpyAsync(y_host, c->y.p, n_owned_entries(c) * sizeof(double),
                              cudaMemcpyDeviceToHost, c->stream));
@@ -626,10 +651,10 @@ int ptb_time_kernel(ptb_ctx* c, int which, int reps, double* ms_avg)
     auto one = [&] {
       switch (which)
       {
-      case PTB_KERNEL_SPMV: launch_spmv(c, c->p.p, c->y.p, &c->cg.p[0]); break;
-      case PTB_KERNEL_CG_UPDATE: launch_cg_update(c, c->dinv.p, &c->cg.p[0]); break;
+      case PTB_KERNEL_SPMV: launch_spmv(c, c->p.p, c->y.p, &c->cg.p[0], 0); break;
+      case PTB_KERNEL_CG_UPDATE: launch_cg_update(c, c->dinv.p, &c->cg.p[0], 0, 0); break;
       case PTB_KERNEL_CG_DIRECTION:
-        launch_cg_direction(c, c->dinv.p, &c->cg.p[1], reinterpret_cast<CgState*>(c->partials.p));
+        launch_cg_direction(c, c->dinv.p, &c->cg.p[1], reinterpret_cast<CgState*>(c->partials.p), 0);
         break;
       case PTB_KERNEL_ASSEMBLE_MATRIX: launch_assemble_matrix(c, MA); break;
       case PTB_KERNEL_ASSEMBLE_VECTOR: launch_assemble_vector(c, VA, FA); break;

@@ -10,6 +10,7 @@
 // Dot products use the deterministic last-block reduction of reduce.cuh (la::inner_product /
 // squared_norm sum owned entries only: cg.h:53,65,74).
 #include "kernels.h"
+#include "peer.cuh"
 #include "reduce.cuh"
 
 namespace ptb
@@ -23,7 +24,7 @@ constexpr int VEC_THREADS = 256;
 template <int BS>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
-          double* partials, unsigned int* ticket)
+          double* partials, unsigned int* ticket, PeerView P, unsigned int epoch)
 {
   __shared__ double red[32];
   if (st != nullptr && st->conv)
@@ -89,15 +90,36 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   {
     double v[1] = {dotv}, out[1];
     if (grid_sum_last_block<1>(v, partials, ticket, red, out) && threadIdx.x == 0)
-      st->py = out[0];
+    {
+      if (P.nranks > 1)
+        peer_publish(P, epoch, out[0], 0.0); // all-reduce of p.y: every rank gets every partial
+      else
+        st->py = out[0];
+    }
   }
+}
+
+// Global sums for the consumer kernels: one thread per CTA collects the nranks partials from the
+// local window (peer mode) or reads the locally reduced / NCCL-reduced values.
+__device__ __forceinline__ void global_sums(const PeerView& P, unsigned int epoch, double l0,
+                                            double l1, double* sh, double& s0, double& s1)
+{
+  if (P.nranks > 1)
+  {
+    if (threadIdx.x == 0)
+      peer_collect(P, epoch, sh[0], sh[1]);
+    __syncthreads();
+    s0 = sh[0], s1 = sh[1];
+  }
+  else
+    s0 = l0, s1 = l1;
 }
 
 // r = b - y (cg.h:47), p = z = D^-1 r (cg.h:50), local r.r and r.z.
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_init(std::int64_t n, const double* __restrict__ b, const double* __restrict__ y,
         const double* __restrict__ dinv, double* __restrict__ r, double* __restrict__ p,
-        CgState* st, double* partials, unsigned int* ticket)
+        CgState* st, double* partials, unsigned int* ticket, PeerView P, unsigned int epoch)
 {
   __shared__ double red[64];
   double v[2] = {0.0, 0.0};
@@ -113,12 +135,19 @@ cg_init(std::int64_t n, const double* __restrict__ b, const double* __restrict__
   }
   double out[2];
   if (grid_sum_last_block<2>(v, partials, ticket, red, out) && threadIdx.x == 0)
-    st->rr = out[0], st->rz = out[1];
+  {
+    if (P.nranks > 1)
+      peer_publish(P, epoch, out[0], out[1]);
+    else
+      st->rr = out[0], st->rz = out[1];
+  }
 }
 
-__global__ void cg_finish_init(CgState* st, double rtol)
+__global__ void cg_finish_init(CgState* st, double rtol, PeerView P, unsigned int epoch)
 {
   // st->rr, st->rz hold the (all-reduced) initial sums (cg.h:53-55)
+  if (P.nranks > 1)
+    peer_collect(P, epoch, st->rr, st->rz);
   st->rnorm0 = st->rr;
   st->rnorm = st->rr;
   st->rz_old = st->rz;
@@ -131,12 +160,16 @@ __global__ void cg_finish_init(CgState* st, double rtol)
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_update(std::int64_t n, const double* __restrict__ p, const double* __restrict__ y,
           const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-          CgState* cur, double* partials, unsigned int* ticket)
+          CgState* cur, double* partials, unsigned int* ticket, PeerView P, unsigned int epoch_in,
+          unsigned int epoch_out)
 {
   __shared__ double red[64];
+  __shared__ double sh[2];
   if (cur->conv)
     return;
-  const double alpha = cur->rz_old / cur->py; // cg.h:65
+  double py, unused;
+  global_sums(P, epoch_in, cur->py, 0.0, sh, py, unused);
+  const double alpha = cur->rz_old / py; // cg.h:65
   double v[2] = {0.0, 0.0};
   for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<std::int64_t>(gridDim.x) * blockDim.x)
@@ -149,13 +182,20 @@ cg_update(std::int64_t n, const double* __restrict__ p, const double* __restrict
   }
   double out[2];
   if (grid_sum_last_block<2>(v, partials, ticket, red, out) && threadIdx.x == 0)
-    cur->rr = out[0], cur->rz = out[1];
+  {
+    if (P.nranks > 1)
+      peer_publish(P, epoch_out, out[0], out[1]);
+    else
+      cur->rr = out[0], cur->rz = out[1];
+  }
 }
 
 __global__ void __launch_bounds__(VEC_THREADS)
 cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
-             double* __restrict__ p, const CgState* cur, CgState* nxt)
+             double* __restrict__ p, const CgState* cur, CgState* nxt, PeerView P,
+             unsigned int epoch)
 {
+  __shared__ double sh[2];
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   if (cur->conv)
   {
@@ -163,7 +203,8 @@ cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restr
       *nxt = *cur;
     return;
   }
-  const double rr = cur->rr, rz = cur->rz;
+  double rr, rz;
+  global_sums(P, epoch, cur->rr, cur->rz, sh, rr, rz);
   const double beta = rz / cur->rz_old;                 // cg.h:75
   const bool converged = rr / cur->rnorm0 < cur->rtol2; // cg.h:78
   if (first)
@@ -207,7 +248,7 @@ __global__ void unpack_kernel(const double* __restrict__ in, const std::int32_t*
 
 __global__ void __launch_bounds__(VEC_THREADS)
 sqnorm_kernel(std::int64_t n, const double* __restrict__ v, double* out, double* partials,
-              unsigned int* ticket)
+              unsigned int* ticket, PeerView P, unsigned int epoch)
 {
   __shared__ double red[32];
   double s[1] = {0.0};
@@ -216,7 +257,16 @@ sqnorm_kernel(std::int64_t n, const double* __restrict__ v, double* out, double*
     s[0] += v[i] * v[i];
   double o[1];
   if (grid_sum_last_block<1>(s, partials, ticket, red, o) && threadIdx.x == 0)
+  {
+    if (P.nranks > 1)
+    {
+      double t0, t1;
+      peer_publish(P, epoch, o[0], 0.0);
+      peer_collect(P, epoch, t0, t1);
+      o[0] = t0;
+    }
     *out = o[0];
+  }
 }
 
 int vec_grid(const ptb_ctx* c, std::int64_t n)
@@ -235,47 +285,55 @@ int cg_grid(const ptb_ctx* c)
   return static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
 }
 
-void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st)
+void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch)
 {
   SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p};
   const int grid = cg_grid(c);
+  const PeerView P = peer_view(c);
   if (c->bs == 1)
-    spmv_sell<1><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p);
+    spmv_sell<1><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p,
+                                                       P, epoch);
   else
-    spmv_sell<3><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p);
+    spmv_sell<3><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p,
+                                                       P, epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
 
-void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st)
+void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
   cg_init<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->b.p, c->y.p, dinv, c->r.p, c->p.p,
-                                                         st, c->partials.p, c->tickets.p + 1);
+                                                         st, c->partials.p, c->tickets.p + 1,
+                                                         peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
 
-void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol)
+void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol, unsigned int epoch)
 {
-  cg_finish_init<<<1, 1, 0, c->stream>>>(st, rtol);
+  cg_finish_init<<<1, 1, 0, c->stream>>>(st, rtol, peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
 
-void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur)
+void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int epoch_in,
+                      unsigned int epoch_out)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
   cg_update<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->p.p, c->y.p, dinv, c->x.p, c->r.p,
-                                                           cur, c->partials.p, c->tickets.p + 1);
+                                                           cur, c->partials.p, c->tickets.p + 1,
+                                                           peer_view(c), epoch_in, epoch_out);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
 
-void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt)
+void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt,
+                         unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_direction<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, cur, nxt);
+  cg_direction<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, cur, nxt,
+                                                              peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -312,7 +370,8 @@ void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::i
 void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev)
 {
   sqnorm_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, v, out_dev, c->partials.p,
-                                                               c->tickets.p + 2);
+                                                               c->tickets.p + 2, peer_view(c),
+                                                               next_red_epoch(c));
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }

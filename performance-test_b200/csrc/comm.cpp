@@ -97,7 +97,7 @@ void comm_destroy(ptb_ctx* c)
 
 void allreduce_sum(ptb_ctx* c, double* dev, int n)
 {
-  if (c->nranks == 1)
+  if (c->nranks == 1 || c->peer.enabled) // peer mode: the kernels reduce through the windows
     return;
   if (!c->nccl_comm)
     throw std::runtime_error("allreduce: communicator not initialised (ptb_comm_init)");
@@ -109,6 +109,8 @@ void halo_forward(ptb_ctx* c, double* v)
 {
   if (c->nranks == 1 || c->nbr_ranks.empty())
     return;
+  if (c->peer.enabled)
+    return peer_halo_forward(c, v);
   if (!c->nccl_comm)
     throw std::runtime_error("halo: communicator not initialised (ptb_comm_init)");
   Nccl& N = nccl();

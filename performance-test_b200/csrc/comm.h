@@ -15,4 +15,12 @@ void comm_destroy(ptb_ctx* c);
 void allreduce_sum(ptb_ctx* c, double* dev, int n);
 /// Forward scatter: owned values of v -> ghost entries of v on the neighbours (stream-ordered).
 void halo_forward(ptb_ctx* c, double* v);
+
+// peer.cu: NCCL-free path over NVLink peer memory
+void peer_export(ptb_ctx* c, void* handles192);
+void peer_connect(ptb_ctx* c, int rank, int nranks, const void* all_handles,
+                  const std::int32_t* src_index);
+void peer_disconnect(ptb_ctx* c);
+void peer_halo_forward(ptb_ctx* c, double* v);
+void peer_neighbour_barrier(ptb_ctx* c);
 } // namespace ptb

@@ -149,5 +149,19 @@ struct ptb_ctx
   ptb::DevBuf<std::int32_t> send_idx, recv_idx;
   ptb::DevBuf<double> send_buf, recv_buf;
 
+  // peer-memory (NVLink P2P) communication state, see peer.cuh
+  struct Peer
+  {
+    bool enabled = false;
+    ptb::DevBuf<unsigned char> window;    // this rank's PeerWindow
+    void* win[16] = {};                   // every rank's window (device pointers)
+    void* nbr_x[8] = {};                  // neighbours' x and p vectors
+    void* nbr_p[8] = {};
+    ptb::DevBuf<std::int32_t> src_index;  // owner-local index per receive entry
+    std::vector<void*> opened;            // IPC mappings to close
+    unsigned long long halo_epoch = 0;
+    unsigned int red_epoch = 0;
+  } peer;
+
   std::int64_t device_bytes() const;
 };

@@ -1,6 +1,7 @@
 // Kernel argument blocks and launchers shared by the .cu files.
 #pragma once
 #include "ctx.h"
+#include "peer.h"
 
 namespace ptb
 {
@@ -78,19 +79,31 @@ void launch_gather_xdof(ptb_ctx* c);
 // cg.cu
 int cg_grid(const ptb_ctx* c);
 /// y = A p on owned rows; if st != nullptr also st->py = p.y (local sum) and honours st->conv.
-void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st);
+void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch = 0);
 /// r = b - y; p = dinv*r (owned); st: rnorm0 = rnorm = rr, rz_old = rz (local sums into rr, rz).
-void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st);
-void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol);
+void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch);
+void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol, unsigned int epoch);
 /// x += alpha p; r -= alpha y; local sums r.r, r.z into cur->rr, cur->rz.
-void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur);
+void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int epoch_in,
+                      unsigned int epoch_out);
 /// beta, convergence test, bookkeeping into nxt; p = beta p + dinv r unless converged.
-void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt);
+void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt,
+                         unsigned int epoch);
+/// Reduction epochs of the peer-memory all-reduce (never 0; see peer.cuh).
+inline unsigned int next_red_epoch(ptb_ctx* c)
+{
+  if (++c->peer.red_epoch == 0)
+    ++c->peer.red_epoch;
+  return c->peer.red_epoch;
+}
 void launch_fill(ptb_ctx* c, double* v, std::int64_t n, double value);
 void launch_pack(ptb_ctx* c, const double* v, const std::int32_t* idx, std::int64_t n, int bs,
                  double* out);
 void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::int64_t n, int bs,
                    double* v);
 void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev);
+
+// peer.cu
+PeerView peer_view(const ptb_ctx* c);
 
 } // namespace ptb

@@ -1,0 +1,74 @@
+// Device-side primitives of the peer-memory path (structures and protocol: peer.h).
+#pragma once
+#include "peer.h"
+#include <cuda_runtime.h>
+
+namespace ptb
+{
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+
+/// Publish this rank's two partial sums for reduction `epoch` to every rank (one thread).
+__device__ __forceinline__ void peer_publish(const PeerView& P, unsigned int epoch, double v0,
+                                             double v1)
+{
+  const unsigned long long b0 = static_cast<unsigned long long>(__double_as_longlong(v0));
+  const unsigned long long b1 = static_cast<unsigned long long>(__double_as_longlong(v1));
+  const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
+  const unsigned long long w[4] = {(b0 & 0xffffffffull) | tag, (b0 >> 32) | tag,
+                                   (b1 & 0xffffffffull) | tag, (b1 >> 32) | tag};
+  for (int r = 0; r < P.nranks; ++r)
+  {
+    unsigned long long* dst = P.win[r]->red[epoch & 3u][P.rank];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      st_relaxed_sys(dst + i, w[i]);
+  }
+}
+
+/// Wait for all ranks' partials of reduction `epoch` and add them in rank order (one thread).
+__device__ __forceinline__ void peer_collect(const PeerView& P, unsigned int epoch, double& s0,
+                                             double& s1)
+{
+  s0 = 0.0, s1 = 0.0;
+  const PeerWindow* W = P.win[P.rank];
+  for (int r = 0; r < P.nranks; ++r)
+  {
+    const unsigned long long* src = W->red[epoch & 3u][r];
+    unsigned long long w[4];
+    bool ok;
+    do
+    {
+      ok = true;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+      {
+        w[i] = ld_relaxed_sys(src + i);
+        ok = ok && static_cast<unsigned int>(w[i] >> 32) == epoch;
+      }
+    } while (!ok);
+    s0 += __longlong_as_double(static_cast<long long>((w[0] & 0xffffffffull) | (w[1] << 32)));
+    s1 += __longlong_as_double(static_cast<long long>((w[2] & 0xffffffffull) | (w[3] << 32)));
+  }
+}
+
+} // namespace ptb

@@ -45,7 +45,7 @@ def test_partitioned_assembly_is_partition_independent(pt, ptype, dims, world):
     ctx.close()
 
 
-def _worker(rank, world, port, ptype, dims, out):
+def _worker(rank, world, port, ptype, dims, comm, out):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -55,12 +55,13 @@ def _worker(rank, world, port, ptype, dims, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         pt = importlib.import_module("performance-test_b200")
-        uid = [pt.abi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(uid, src=0)
         ctx = pt.abi.Context(rank)
-        ctx.comm_init(rank, world, uid[0])
         P = pt.host.Problem(ptype, 1, *dims, rank, world)
         ctx.set_problem(P)
+        if comm == "nccl":
+            pt.dist.init_nccl(ctx, pt.abi, dist, rank, world)
+        else:
+            pt.dist.connect_peers(ctx, P, dist, rank, world)
         ctx.assemble_matrix()
         ctx.assemble_vector()
         k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
@@ -72,13 +73,15 @@ def _worker(rank, world, port, ptype, dims, out):
         pl[: P.n_owned * P.bs] = pg[P.global_offset * P.bs:(P.global_offset + P.n_owned) * P.bs]
         y = ctx.apply_operator(pl)  # ghosts of p are filled by the halo exchange
         out.put((rank, k, rel, P.global_offset, P.n_owned, x, nrm, y, np.array(P["ghost_global"])))
+        dist.barrier()  # nobody frees device memory a peer may still map
         ctx.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("comm", ["nccl", "peer"])
 @pytest.mark.parametrize("ptype,dims", [("poisson", (12, 11, 14)), ("elasticity", (7, 8, 9))])
-def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims):
+def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims, comm):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -87,7 +90,7 @@ def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims):
     ctxm = mp.get_context("spawn")
     out = ctxm.Queue()
     port = 29500 + (os.getpid() % 2000)
-    procs = [ctxm.Process(target=_worker, args=(r, world, port, ptype, dims, out))
+    procs = [ctxm.Process(target=_worker, args=(r, world, port, ptype, dims, comm, out))
              for r in range(world)]
     for p in procs:
         p.start()
