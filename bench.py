@@ -48,6 +48,8 @@ WORKLOADS = {
     "poisson": ("poisson", "weak", 20_000_000, 1, "Poisson P1 weak scaling 20M DOFs/GPU, CG+Jacobi rtol 1e-8"),
     "elasticity": ("elasticity", "strong", 10_000_000, 1, "Elasticity P1 strong scaling 10M DOFs total, CG+Jacobi rtol 1e-8"),
     "small": ("poisson", "weak", 500_000, 1, "Poisson P1 unit cube 500k DOFs/GPU, CG+Jacobi rtol 1e-8"),
+    "poisson_p2": ("poisson", "strong", 50_000_000, 2, "Poisson P2 50M DOFs total (strong), CG+Jacobi rtol 1e-8"),
+    "poisson_p3": ("poisson", "strong", 50_000_000, 3, "Poisson P3 50M DOFs total (strong), CG+Jacobi rtol 1e-8"),
 }
 KMAX = 10000  # PETSc's default -ksp_max_it; cg.h's own default of 50 never converges at these sizes
 

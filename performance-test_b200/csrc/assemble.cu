@@ -443,7 +443,7 @@ void set_smem(K kernel, std::size_t smem)
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
 {
   if (c->order != 1)
-    throw std::runtime_error("assemble_matrix: only order 1 kernels are built in this round");
+    return launch_assemble_matrix_pk(c, A);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
   if (c->bs == 1)
@@ -467,7 +467,7 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
 {
   if (c->order != 1)
-    throw std::runtime_error("assemble_vector: only order 1 kernels are built in this round");
+    return launch_assemble_vector_pk(c, A, F);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_vector: a P1 row has more than 254 columns");
   if (c->bs == 1)

@@ -1,0 +1,273 @@
+// Assembly kernels for the higher-order Lagrange spaces (P2: nd = 10, P3: nd = 20; scalar Poisson,
+// BASELINE config 4). Same row-owner gather as the P1 kernels (assemble.cu): one thread owns one
+// matrix row, walks the row's cells in ascending order and evaluates only its own row of each
+// element tensor, here in FFCx-free "tensor representation" (SURVEY B4):
+//
+//     Ae[li][j] = sum_{b<=c} G_bc S[bc][li][j],   G = K K^T |detJ|   (6 geometry factors per cell)
+//     be[li]    = |detJ| sum_j M[li][j] f_j
+//     facet     = |J t1 x J t2| sum_j MF[lf][li][j] g_j
+//
+// with the exactly integrated reference tensors of element_tables.h staged in shared memory.
+// Replaces the generated tabulate_tensor kernels of Poisson.py:31-32 for degree 2 and 3 and the
+// DOLFINx insertion loop (poisson_problem.cpp:129-137,150-155).
+#include "element_tables.h"
+#include "kernels.h"
+
+namespace ptb
+{
+namespace
+{
+
+struct Vec3
+{
+  double x, y, z;
+};
+__device__ __forceinline__ Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
+{
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ Vec3 load_point(const double* __restrict__ xyz4, std::int64_t v)
+{
+  const double2* p = reinterpret_cast<const double2*>(xyz4 + 4 * v);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  return {a.x, a.y, b.x};
+}
+
+constexpr int PK_THREADS = 128;
+
+// In-row slot offset of local column j from the packed words of a pair.
+template <int ND, bool WIDE>
+__device__ __forceinline__ int slot_of(const std::uint32_t* w, int j)
+{
+  if constexpr (WIDE)
+    return (w[j >> 1] >> (16 * (j & 1))) & 0xffffu;
+  else
+    return (w[j >> 2] >> (8 * (j & 3))) & 0xffu;
+}
+
+template <int ND, bool WIDE>
+__global__ void __launch_bounds__(PK_THREADS)
+assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
+{
+  constexpr int NW = WIDE ? (ND + 1) / 2 : (ND + 3) / 4;
+  extern __shared__ double smem[];
+  double* St = smem; // [6][ND][ND]
+  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
+    St[i] = Sg[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const std::int64_t mo = A.mat_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const std::int64_t ao = A.adj_off[slice];
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  double* acc = smem + 6 * ND * ND + warp * (A.max_w * 32);
+  for (int k = 0; k < w; ++k)
+    acc[k * 32 + lane] = 0.0;
+  __syncwarp();
+
+  for (int k = 0; k < wa; ++k)
+  {
+    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+    if (pair == ADJ_INVALID_DEV)
+      continue;
+    std::uint32_t words[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+      words[q] = A.adjso[(ao + k * 32) * NW + q * 32 + lane];
+    const std::uint32_t cell = pair / ND;
+    const int li = pair - cell * ND;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    const Vec3 X0 = load_point(A.xyz, v.x);
+    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+               e3 = load_point(A.xyz, v.w) - X0;
+    // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
+    const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+    const double inv = 1.0 / fabs(dot(e1, c1));
+    const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
+                 G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+    const double* S = St + li * ND;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
+                         + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
+                         + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+      acc[slot_of<ND, WIDE>(words, j) * 32 + lane] += val;
+    }
+  }
+
+  const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
+  const bool bc_row = live && A.bc[row];
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const std::int32_t col = A.cols[mo + k * 32 + lane];
+    const bool real = k < len;
+    const bool own = real && col == row;
+    double val = acc[k * 32 + lane];
+    if (bc_row || (real && A.bc[col]))
+      val = own ? 1.0 : 0.0;
+    if (!real)
+      val = 0.0;
+    A.vals[mo + k * 32 + lane] = val;
+    if (own)
+      diag = val;
+  }
+  if (live)
+    A.dinv[row] = 1.0 / diag;
+}
+
+template <int ND>
+__global__ void __launch_bounds__(PK_THREADS)
+assemble_vector_pk(VectorArgs A, const double* __restrict__ Mg)
+{
+  __shared__ double Mt[ND * ND];
+  for (int i = threadIdx.x; i < ND * ND; i += blockDim.x)
+    Mt[i] = Mg[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int32_t row = slice * 32 + lane;
+  if (row >= A.n_rows)
+    return;
+  const std::int64_t ao = A.adj_off[slice];
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  double sum = 0.0;
+  for (int k = 0; k < wa; ++k)
+  {
+    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+    if (pair == ADJ_INVALID_DEV)
+      break; // lists are front-packed
+    const std::uint32_t cell = pair / ND;
+    const int li = pair - cell * ND;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    const Vec3 X0 = load_point(A.xyz, v.x);
+    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+               e3 = load_point(A.xyz, v.w) - X0;
+    const double det = fabs(dot(e1, cross(e2, e3)));
+    const std::int32_t* dofs = A.dofmap + static_cast<std::int64_t>(cell) * ND;
+    double s = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+      s += Mt[li * ND + j] * __ldg(A.f + __ldg(dofs + j));
+    sum += det * s;
+  }
+  A.b[row] = A.bc[row] ? 0.0 : sum;
+}
+
+template <int ND>
+__global__ void assemble_facets_pk(FacetArgs A, const double* __restrict__ MFg)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= A.n_frows)
+    return;
+  const std::int32_t row = A.frow_ids[i];
+  if (A.bc[row])
+    return;
+  double sum = 0.0;
+  for (int e = A.frow_ptr[i]; e < A.frow_ptr[i + 1]; ++e)
+  {
+    const std::int32_t cell = A.fent[2 * e], code = A.fent[2 * e + 1];
+    const int lf = code / ND, li = code - lf * ND;
+    const std::int32_t* xv = A.x_dofmap + 4 * static_cast<std::int64_t>(cell);
+    // facet lf = face opposite local vertex lf, vertices in ascending local order
+    const int a0 = lf == 0 ? 1 : 0, a1 = lf <= 1 ? 2 : 1, a2 = lf <= 2 ? 3 : 2;
+    const Vec3 P0 = load_point(A.xyz, xv[a0]), P1 = load_point(A.xyz, xv[a1]),
+               P2 = load_point(A.xyz, xv[a2]);
+    const Vec3 cr = cross(P1 - P0, P2 - P0);
+    const double scale = sqrt(dot(cr, cr)); // |J t1 x J t2| = 2 * area
+    const std::int32_t* dofs = A.dofmap + static_cast<std::int64_t>(cell) * ND;
+    const double* Mrow = MFg + (lf * ND + li) * ND;
+    double s = 0.0;
+    for (int j = 0; j < ND; ++j)
+      s += Mrow[j] * A.g[dofs[j]];
+    sum += scale * s;
+  }
+  A.b[row] += sum;
+}
+
+void ensure_tables(ptb_ctx* c)
+{
+  if (c->tab_order == c->order)
+    return;
+  const bool p2 = c->order == 2;
+  const int nd = c->nd;
+  c->tab_S.upload(p2 ? tables::S_P2 : tables::S_P3, 6 * nd * nd, c->stream);
+  c->tab_M.upload(p2 ? tables::M_P2 : tables::M_P3, nd * nd, c->stream);
+  c->tab_MF.upload(p2 ? tables::MF_P2 : tables::MF_P3, 4 * nd * nd, c->stream);
+  c->tab_order = c->order;
+}
+
+template <int ND>
+void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
+{
+  const std::size_t smem
+      = (static_cast<std::size_t>(6) * ND * ND + static_cast<std::size_t>(c->max_w) * 32 * (PK_THREADS / 32))
+        * sizeof(double);
+  if (smem > 227 * 1024)
+    throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
+  const int grid = (A.n_slices + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
+  if (c->so_bits == 8)
+  {
+    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk<ND, false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_matrix_pk<ND, false><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p);
+  }
+  else
+  {
+    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk<ND, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    assemble_matrix_pk<ND, true><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p);
+  }
+}
+
+} // namespace
+
+void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A)
+{
+  if (c->bs != 1)
+    throw std::runtime_error("assemble_matrix: order > 1 is built for the scalar Poisson space only");
+  ensure_tables(c);
+  if (c->order == 2)
+    launch_matrix<10>(c, A);
+  else
+    launch_matrix<20>(c, A);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+}
+
+void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
+{
+  if (c->bs != 1)
+    throw std::runtime_error("assemble_vector: order > 1 is built for the scalar Poisson space only");
+  ensure_tables(c);
+  const int grid = (A.n_slices + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
+  if (c->order == 2)
+    assemble_vector_pk<10><<<grid, PK_THREADS, 0, c->stream>>>(A, c->tab_M.p);
+  else
+    assemble_vector_pk<20><<<grid, PK_THREADS, 0, c->stream>>>(A, c->tab_M.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  if (F.n_frows > 0 && F.g != nullptr)
+  {
+    const int fg = (F.n_frows + 127) / 128;
+    if (c->order == 2)
+      assemble_facets_pk<10><<<fg, 128, 0, c->stream>>>(F, c->tab_MF.p);
+    else
+      assemble_facets_pk<20><<<fg, 128, 0, c->stream>>>(F, c->tab_MF.p);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+  }
+}
+
+} // namespace ptb

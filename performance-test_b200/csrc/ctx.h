@@ -131,6 +131,10 @@ struct ptb_ctx
   std::int32_t n_frows = 0;
   ptb::DevBuf<std::int32_t> frow_ids, frow_ptr, fent; // fent = {cell, local_facet*nd + li} pairs
 
+  // reference tensors of the P2/P3 element (element_tables.h), uploaded on first use
+  ptb::DevBuf<double> tab_S, tab_M, tab_MF;
+  int tab_order = 0;
+
   // vectors
   ptb::DevBuf<double> f, g, b, dinv, ones, x, p, r, y;
   bool have_x0 = false;

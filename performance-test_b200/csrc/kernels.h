@@ -72,6 +72,8 @@ struct SpmvArgs
 
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
+void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A);
+void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 void launch_sell_to_csr(ptb_ctx* c, double* out);
 /// xdof[d] = xyz[dof_vertex[d]] for vertex dofs.
 void launch_gather_xdof(ptb_ctx* c);

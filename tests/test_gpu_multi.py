@@ -16,9 +16,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("ptype,dims,world", [("poisson", (9, 8, 10), 3), ("elasticity", (6, 5, 8), 2)])
-def test_partitioned_assembly_is_partition_independent(pt, ptype, dims, world):
-    S = pt.host.Problem(ptype, 1, *dims)
+@pytest.mark.parametrize("ptype,order,dims,world",
+                         [("poisson", 1, (9, 8, 10), 3), ("elasticity", 1, (6, 5, 8), 2),
+                          ("poisson", 2, (4, 5, 6), 2), ("poisson", 3, (3, 3, 5), 2)])
+def test_partitioned_assembly_is_partition_independent(pt, ptype, order, dims, world):
+    S = pt.host.Problem(ptype, order, *dims)
     ctx = pt.abi.Context(0)
     ctx.set_problem(S)
     ctx.assemble_matrix()
@@ -26,7 +28,7 @@ def test_partitioned_assembly_is_partition_independent(pt, ptype, dims, world):
     A_s, b_s = ctx.matrix_values().copy(), ctx.rhs().copy()
     bs = S.bs
     for rank in range(world):
-        P = pt.host.Problem(ptype, 1, *dims, rank, world)
+        P = pt.host.Problem(ptype, order, *dims, rank, world)
         ctx.set_problem(P)
         ctx.assemble_matrix()
         ctx.assemble_vector()

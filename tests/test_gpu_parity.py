@@ -43,7 +43,9 @@ def _check_matrix(P, got, ref):
 
 SMALL = [("poisson", 1, (5, 4, 6)), ("poisson", 1, (1, 1, 1)), ("poisson", 1, (9, 2, 3)),
          ("poisson", 1, (16, 15, 17)), ("elasticity", 1, (4, 5, 3)), ("elasticity", 1, (1, 1, 2)),
-         ("elasticity", 1, (12, 11, 13))]
+         ("elasticity", 1, (12, 11, 13)),
+         ("poisson", 2, (4, 3, 5)), ("poisson", 2, (1, 1, 1)), ("poisson", 2, (9, 8, 10)),
+         ("poisson", 3, (3, 4, 2)), ("poisson", 3, (1, 1, 1)), ("poisson", 3, (6, 5, 7))]
 
 
 @pytest.mark.parametrize("ptype,order,dims", SMALL)
@@ -72,7 +74,7 @@ def test_assembly_matches_oracle(pt, oracle, ctx, ptype, order, dims):
     np.testing.assert_allclose(ctx.diagonal_inverse(), 1.0 / diag, rtol=1e-15)
 
 
-@pytest.mark.parametrize("ptype,order,dims", SMALL[:1] + SMALL[4:5])
+@pytest.mark.parametrize("ptype,order,dims", SMALL[:1] + SMALL[4:5] + SMALL[7:8] + SMALL[10:11])
 def test_slot_offsets_bit_identical(pt, ctx, ptype, order, dims):
     """Compressed cell -> CSR-slot map held by the context == rowptr + oracle's slot map."""
     from oracle import intmaps_ref as R
@@ -90,7 +92,7 @@ def test_slot_offsets_bit_identical(pt, ctx, ptype, order, dims):
         assert np.array_equal(got, slot[pr])
 
 
-@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6]])
+@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6], SMALL[9], SMALL[12]])
 def test_operator_matches_oracle(pt, oracle, ctx, ptype, order, dims):
     P = pt.host.Problem(ptype, order, *dims)
     ctx.set_problem(P)
@@ -104,7 +106,7 @@ def test_operator_matches_oracle(pt, oracle, ctx, ptype, order, dims):
 
 
 @pytest.mark.parametrize("precond", ["jacobi", "none"])
-@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6]])
+@pytest.mark.parametrize("ptype,order,dims", [SMALL[3], SMALL[6], SMALL[9], SMALL[12]])
 def test_cg_matches_oracle(pt, oracle, ctx, ptype, order, dims, precond):
     P = pt.host.Problem(ptype, order, *dims)
     ctx.set_problem(P)
