@@ -356,8 +356,8 @@ def main():
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmv_b, "ms_per_launch": t_spmv,
                 "other_kernels": {
-                    "cg_update": {"ms": t_upd, "GBps": 56.0 * P.n_owned * P.bs / t_upd / 1e6},
-                    "cg_direction": {"ms": t_dir, "GBps": 32.0 * P.n_owned * P.bs / t_dir / 1e6},
+                    "cg_update": {"ms": t_upd, "GBps": 32.0 * P.n_owned * P.bs / t_upd / 1e6},
+                    "cg_direction": {"ms": t_dir, "GBps": 48.0 * P.n_owned * P.bs / t_dir / 1e6},
                     "assemble_matrix": {"ms": t_am, "GBps": asm_b / t_am / 1e6,
                                         "nnz_per_s": P.nnz * P.bs * P.bs / (t_am * 1e-3)},
                     "assemble_vector": {"ms": t_av}},

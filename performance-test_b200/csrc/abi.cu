@@ -75,7 +75,7 @@ std::int64_t ptb_ctx::device_bytes() const
          + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
-         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes()
+         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes()
          + peer.src_index.bytes();
 }
 
@@ -266,6 +266,20 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->adjrot.release();
       c->adj.upload(L.adj, c->stream);
       c->adjso.upload(L.adjso, c->stream);
+    }
+    {
+      // visiting order for the fused-halo operator: slices that read ghost columns go last
+      std::vector<std::int32_t> inner, outer;
+      for (std::int32_t s = 0; s < L.n_slices; ++s)
+      {
+        bool ghost = false;
+        for (std::int64_t q = L.mat_off[s]; q < L.mat_off[s + 1] && !ghost; ++q)
+          ghost = L.cols[q] >= N;
+        (ghost ? outer : inner).push_back(s);
+      }
+      c->n_interior_slices = static_cast<std::int32_t>(inner.size());
+      inner.insert(inner.end(), outer.begin(), outer.end());
+      c->slice_order.upload(inner, c->stream);
     }
     c->vals.alloc(L.cols.size() * c->bs * c->bs);
     c->vals.zero(c->stream);
@@ -464,9 +478,11 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
         ++it;
         CgState* cur = &st[it & 1];
         CgState* nxt = &st[(it + 1) & 1];
-        halo_forward(c, c->p.p);
+        const bool fused = c->peer.enabled && !c->nbr_ranks.empty();
+        if (!fused)
+          halo_forward(c, c->p.p);
         const unsigned int ea = next_red_epoch(c), eb = next_red_epoch(c);
-        launch_spmv(c, c->p.p, c->y.p, cur, ea);
+        launch_spmv(c, c->p.p, c->y.p, cur, ea, fused);
         allreduce_sum(c, &cur->py, 1);
         launch_cg_update(c, dinv, cur, ea, eb);
         allreduce_sum(c, &cur->rr, 2);
@@ -637,6 +653,7 @@ int ptb_time_kernel(ptb_ctx* c, int which, int reps, double* ms_avg)
     // benign scalars: alpha = 0, beta = 1, never converged
     CgState s{};
     s.py = 1.0, s.rr = 1.0, s.rz = 1.0, s.rz_old = 0.0, s.rnorm0 = 1.0, s.rtol2 = 0.0, s.rnorm = 1.0;
+    s.alpha = 0.0;
     CgState sd = s;
     sd.rz_old = 1.0;
     PTB_CUDA(cudaMemcpyAsync(&c->cg.p[0], &s, sizeof(s), cudaMemcpyHostToDevice, c->stream));

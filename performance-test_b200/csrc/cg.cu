@@ -2,8 +2,8 @@
 // extension, fused into three kernels per iteration:
 //
 //   spmv_sell        y = A p  (the `action` of cg.h:62) + local p.y                 cg.h:62,65
-//   cg_update        alpha = rz/py; x += alpha p; r -= alpha y; local r.r, r.z      cg.h:65-74
-//   cg_direction     beta = rz'/rz; stopping rule; p = beta p + D^-1 r              cg.h:75-82
+//   cg_update        alpha = rz/py; r -= alpha y; local r.r, r.z                    cg.h:65,71,74
+//   cg_direction     x += alpha p; beta = rz'/rz; stopping rule; p = beta p + D^-1 r cg.h:68,75-82
 //
 // Scalars never visit the host: they live in two CgState records indexed by iteration parity, so
 // the kernel that writes the next iteration's record never races with readers of the current one.
@@ -21,10 +21,46 @@ namespace
 constexpr int SPMV_THREADS = 256;
 constexpr int VEC_THREADS = 256;
 
-template <int BS>
+// Gather of the input vector. In the fused-halo kernel the ghost part of p is written by the same
+// launch, so the non-coherent (read-only) path must not be used there.
+template <bool FUSED>
+__device__ __forceinline__ double ldp(const double* q)
+{
+  if constexpr (FUSED)
+    return *q;
+  else
+    return __ldg(q);
+}
+
+// Halo exchange fused into the operator (peer mode): the first FH.npull CTAs pull the ghost values
+// of p out of the neighbours' vectors over NVLink while every other warp already works on the
+// interior slices; slices that read ghost columns come last in FH.order and wait for the pull.
+struct FusedHalo
+{
+  PeerHalo H;
+  const std::int32_t* order;      // slice visiting order: interior first, ghost-reading last
+  std::int32_t n_interior;        // number of leading slices of `order` without ghost columns
+  int npull;                      // CTAs that copy (<= 32)
+  unsigned long long epoch;       // halo epoch of this launch
+  unsigned long long* ready;      // [32] per-puller completion epochs (local memory)
+  double* pw;                     // writable alias of p (ghost part)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+template <int BS, bool FUSED>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
-          double* partials, unsigned int* ticket, PeerView P, unsigned int epoch)
+          double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH)
 {
   __shared__ double red[32];
   if (st != nullptr && st->conv)
@@ -33,9 +69,61 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   const int warps_per_cta = SPMV_THREADS / 32;
   const std::int32_t warp0 = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
   const std::int32_t stride = gridDim.x * warps_per_cta;
-  double dotv = 0.0;
-  for (std::int32_t slice = warp0; slice < A.n_slices; slice += stride)
+  if constexpr (FUSED)
   {
+    const PeerHalo& H = FH.H;
+    if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
+    {
+      __threadfence_system(); // p was completed by the previous kernel: publish "ready"
+      st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
+    }
+    if (blockIdx.x < FH.npull)
+    {
+      if (threadIdx.x < H.n_nbr)
+      {
+        const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
+        while (ld_acquire_sys(flag) < FH.epoch)
+        {
+        }
+      }
+      __syncthreads();
+      const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
+      for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+           i < n; i += static_cast<std::int64_t>(FH.npull) * blockDim.x)
+      {
+        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+        int nb = 0;
+        while (j >= H.recv_displ[nb + 1])
+          ++nb;
+        FH.pw[static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c]
+            = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        __threadfence();
+        st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
+      }
+    }
+  }
+  bool ghosts_ready = !FUSED;
+  double dotv = 0.0;
+  for (std::int32_t it = warp0; it < A.n_slices; it += stride)
+  {
+    std::int32_t slice = it;
+    if constexpr (FUSED)
+    {
+      slice = FH.order[it];
+      if (!ghosts_ready && it >= FH.n_interior)
+      {
+        unsigned long long f;
+        do
+          f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
+        while (!__all_sync(0xffffffffu, f >= FH.epoch));
+        ghosts_ready = true;
+      }
+    }
     const std::int64_t mo = A.mat_off[slice];
     const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
     const std::int32_t row = slice * 32 + lane;
@@ -51,17 +139,17 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
                            c3 = cp[(k + 3) * 32];
         const double v0 = vp[(k + 0) * 32], v1 = vp[(k + 1) * 32], v2 = vp[(k + 2) * 32],
                      v3 = vp[(k + 3) * 32];
-        sum += v0 * __ldg(p + c0);
-        sum += v1 * __ldg(p + c1);
-        sum += v2 * __ldg(p + c2);
-        sum += v3 * __ldg(p + c3);
+        sum += v0 * ldp<FUSED>(p + c0);
+        sum += v1 * ldp<FUSED>(p + c1);
+        sum += v2 * ldp<FUSED>(p + c2);
+        sum += v3 * ldp<FUSED>(p + c3);
       }
       for (; k < w; ++k)
-        sum += vp[k * 32] * __ldg(p + cp[k * 32]);
+        sum += vp[k * 32] * ldp<FUSED>(p + cp[k * 32]);
       if (row < A.n_rows)
       {
         y[row] = sum;
-        dotv += sum * __ldg(p + row);
+        dotv += sum * ldp<FUSED>(p + row);
       }
     }
     else
@@ -73,7 +161,8 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
       {
         const std::int64_t c = cp[k * 32];
         const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
-        const double p0 = __ldg(p + 3 * c), p1 = __ldg(p + 3 * c + 1), p2 = __ldg(p + 3 * c + 2);
+        const double p0 = ldp<FUSED>(p + 3 * c), p1 = ldp<FUSED>(p + 3 * c + 1),
+                     p2 = ldp<FUSED>(p + 3 * c + 2);
         s0 += v[0 * 32] * p0 + v[1 * 32] * p1 + v[2 * 32] * p2;
         s1 += v[3 * 32] * p0 + v[4 * 32] * p1 + v[5 * 32] * p2;
         s2 += v[6 * 32] * p0 + v[7 * 32] * p1 + v[8 * 32] * p2;
@@ -82,7 +171,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
       {
         const std::int64_t r3 = 3 * static_cast<std::int64_t>(row);
         y[r3] = s0, y[r3 + 1] = s1, y[r3 + 2] = s2;
-        dotv += s0 * __ldg(p + r3) + s1 * __ldg(p + r3 + 1) + s2 * __ldg(p + r3 + 2);
+        dotv += s0 * ldp<FUSED>(p + r3) + s1 * ldp<FUSED>(p + r3 + 1) + s2 * ldp<FUSED>(p + r3 + 2);
       }
     }
   }
@@ -157,11 +246,12 @@ __global__ void cg_finish_init(CgState* st, double rtol, PeerView P, unsigned in
   st->conv = 0;
 }
 
+// r -= alpha y (cg.h:71) with the local r.r and r.z (cg.h:74). The x update of cg.h:68 is deferred
+// to cg_direction, which streams p anyway: 32 B/DOF here instead of 56.
 __global__ void __launch_bounds__(VEC_THREADS)
-cg_update(std::int64_t n, const double* __restrict__ p, const double* __restrict__ y,
-          const double* __restrict__ dinv, double* __restrict__ x, double* __restrict__ r,
-          CgState* cur, double* partials, unsigned int* ticket, PeerView P, unsigned int epoch_in,
-          unsigned int epoch_out)
+cg_update(std::int64_t n, const double* __restrict__ y, const double* __restrict__ dinv,
+          double* __restrict__ r, CgState* cur, double* partials, unsigned int* ticket, PeerView P,
+          unsigned int epoch_in, unsigned int epoch_out)
 {
   __shared__ double red[64];
   __shared__ double sh[2];
@@ -170,15 +260,32 @@ cg_update(std::int64_t n, const double* __restrict__ p, const double* __restrict
   double py, unused;
   global_sums(P, epoch_in, cur->py, 0.0, sh, py, unused);
   const double alpha = cur->rz_old / py; // cg.h:65
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    cur->alpha = alpha; // for cg_direction; no CTA of this kernel reads it
   double v[2] = {0.0, 0.0};
-  for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n;
+  const std::int64_t n2 = n >> 1;
+  const double2* __restrict__ y2 = reinterpret_cast<const double2*>(y);
+  const double2* __restrict__ d2 = reinterpret_cast<const double2*>(dinv);
+  double2* __restrict__ r2 = reinterpret_cast<double2*>(r);
+  for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<std::int64_t>(gridDim.x) * blockDim.x)
   {
-    x[i] = alpha * p[i] + x[i];             // cg.h:68
-    const double ri = -alpha * y[i] + r[i]; // cg.h:71
-    r[i] = ri;
-    v[0] += ri * ri;                        // cg.h:74
-    v[1] += ri * (dinv[i] * ri);
+    const double2 yy = y2[i], dd = d2[i];
+    double2 rr = r2[i];
+    rr.x = -alpha * yy.x + rr.x;
+    rr.y = -alpha * yy.y + rr.y;
+    r2[i] = rr;
+    v[0] += rr.x * rr.x;
+    v[1] += rr.x * (dd.x * rr.x);
+    v[0] += rr.y * rr.y;
+    v[1] += rr.y * (dd.y * rr.y);
+  }
+  if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    const double ri = -alpha * y[n - 1] + r[n - 1];
+    r[n - 1] = ri;
+    v[0] += ri * ri;
+    v[1] += ri * (dinv[n - 1] * ri);
   }
   double out[2];
   if (grid_sum_last_block<2>(v, partials, ticket, red, out) && threadIdx.x == 0)
@@ -190,10 +297,12 @@ cg_update(std::int64_t n, const double* __restrict__ p, const double* __restrict
   }
 }
 
-__global__ void __launch_bounds__(VEC_THREADS)
+// x += alpha p (cg.h:68, deferred), beta and the stopping rule (cg.h:75-79), p = beta p + D^-1 r
+// (cg.h:82) unless converged. 48 B/DOF.
+__global__ void __launch_bounds__(VEC_THREADS, 5)
 cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restrict__ dinv,
-             double* __restrict__ p, const CgState* cur, CgState* nxt, PeerView P,
-             unsigned int epoch)
+             double* __restrict__ p, double* __restrict__ x, const CgState* cur, CgState* nxt,
+             PeerView P, unsigned int epoch)
 {
   __shared__ double sh[2];
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -205,6 +314,7 @@ cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restr
   }
   double rr, rz;
   global_sums(P, epoch, cur->rr, cur->rz, sh, rr, rz);
+  const double alpha = cur->alpha;
   const double beta = rz / cur->rz_old;                 // cg.h:75
   const bool converged = rr / cur->rnorm0 < cur->rtol2; // cg.h:78
   if (first)
@@ -216,11 +326,33 @@ cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restr
     s.conv = converged ? 1 : 0;
     *nxt = s;
   }
-  if (converged)
-    return;
-  for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n;
+  const std::int64_t n2 = n >> 1;
+  const double2* __restrict__ r2 = reinterpret_cast<const double2*>(r);
+  const double2* __restrict__ d2 = reinterpret_cast<const double2*>(dinv);
+  double2* __restrict__ p2 = reinterpret_cast<double2*>(p);
+  double2* __restrict__ x2 = reinterpret_cast<double2*>(x);
+  for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<std::int64_t>(gridDim.x) * blockDim.x)
-    p[i] = beta * p[i] + dinv[i] * r[i]; // cg.h:82
+  {
+    double2 pp = p2[i], xx = x2[i];
+    xx.x = alpha * pp.x + xx.x;
+    xx.y = alpha * pp.y + xx.y;
+    x2[i] = xx;
+    if (!converged)
+    {
+      const double2 rv = r2[i], dd = d2[i];
+      pp.x = beta * pp.x + dd.x * rv.x;
+      pp.y = beta * pp.y + dd.y * rv.y;
+      p2[i] = pp;
+    }
+  }
+  if ((n & 1) && first)
+  {
+    const double pv = p[n - 1];
+    x[n - 1] = alpha * pv + x[n - 1];
+    if (!converged)
+      p[n - 1] = beta * pv + dinv[n - 1] * r[n - 1];
+  }
 }
 
 __global__ void fill_kernel(double* v, std::int64_t n, double value)
@@ -285,17 +417,37 @@ int cg_grid(const ptb_ctx* c)
   return static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
 }
 
-void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch)
+void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
+                 bool fused_halo)
 {
   SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p};
   const int grid = cg_grid(c);
   const PeerView P = peer_view(c);
-  if (c->bs == 1)
-    spmv_sell<1><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p,
-                                                       P, epoch);
+  FusedHalo FH{};
+  if (fused_halo)
+  {
+    if (!c->peer.enabled || p != c->p.p)
+      throw std::runtime_error("fused halo: peer mode and the search direction vector only");
+    FH.H = peer_halo(c);
+    FH.order = c->slice_order.p;
+    FH.n_interior = c->n_interior_slices;
+    FH.npull = std::min(32, grid);
+    FH.epoch = ++c->peer.halo_epoch;
+    FH.ready = c->peer.ready.p;
+    FH.pw = c->p.p;
+    if (c->bs == 1)
+      spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                               c->tickets.p, P, epoch, FH);
+    else
+      spmv_sell<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                               c->tickets.p, P, epoch, FH);
+  }
+  else if (c->bs == 1)
+    spmv_sell<1, false><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                              c->tickets.p, P, epoch, FH);
   else
-    spmv_sell<3><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p,
-                                                       P, epoch);
+    spmv_sell<3, false><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                              c->tickets.p, P, epoch, FH);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -321,8 +473,8 @@ void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int
                       unsigned int epoch_out)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_update<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->p.p, c->y.p, dinv, c->x.p, c->r.p,
-                                                           cur, c->partials.p, c->tickets.p + 1,
+  cg_update<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->y.p, dinv, c->r.p, cur,
+                                                           c->partials.p, c->tickets.p + 1,
                                                            peer_view(c), epoch_in, epoch_out);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
@@ -332,8 +484,8 @@ void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgS
                          unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_direction<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, cur, nxt,
-                                                              peer_view(c), epoch);
+  cg_direction<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
+                                                              nxt, peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }

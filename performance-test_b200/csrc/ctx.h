@@ -83,6 +83,7 @@ struct CgState
   double rnorm0; // |r0|^2
   double rtol2;
   double rnorm;  // |r|^2 entering this iteration
+  double alpha;  // step length of this iteration (written by cg_update for cg_direction)
   int k;         // iterations completed
   int conv;      // 1 once the stopping rule fired
 };
@@ -121,6 +122,8 @@ struct ptb_ctx
   int max_w = 0, max_wa = 0, so_bits = 8, so_words = 1;
   ptb::DevBuf<std::int64_t> rowptr, mat_off, adj_off;
   ptb::DevBuf<std::int32_t> cols;      // SELL
+  ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)
+  std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry
   ptb::DevBuf<std::uint32_t> adj, adjso, adjrot;
   // host copies of the compressed slot map (parity inspection)
@@ -162,6 +165,7 @@ struct ptb_ctx
     void* nbr_x[8] = {};                  // neighbours' x and p vectors
     void* nbr_p[8] = {};
     ptb::DevBuf<std::int32_t> src_index;  // owner-local index per receive entry
+    ptb::DevBuf<unsigned long long> ready; // [32] completion epochs of the fused halo pull
     std::vector<void*> opened;            // IPC mappings to close
     unsigned long long halo_epoch = 0;
     unsigned int red_epoch = 0;

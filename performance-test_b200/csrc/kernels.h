@@ -81,7 +81,8 @@ void launch_gather_xdof(ptb_ctx* c);
 // cg.cu
 int cg_grid(const ptb_ctx* c);
 /// y = A p on owned rows; if st != nullptr also st->py = p.y (local sum) and honours st->conv.
-void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch = 0);
+void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch = 0,
+                 bool fused_halo = false);
 /// r = b - y; p = dinv*r (owned); st: rnorm0 = rnorm = rr, rz_old = rz (local sums into rr, rz).
 void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch);
 void launch_cg_finish_init(ptb_ctx* c, CgState* st, double rtol, unsigned int epoch);
@@ -107,5 +108,6 @@ void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev)
 
 // peer.cu
 PeerView peer_view(const ptb_ctx* c);
+PeerHalo peer_halo(const ptb_ctx* c);
 
 } // namespace ptb

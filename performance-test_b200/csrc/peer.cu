@@ -67,7 +67,7 @@ PeerView peer_view(const ptb_ctx* c)
   return V;
 }
 
-static PeerHalo peer_halo(const ptb_ctx* c)
+PeerHalo peer_halo(const ptb_ctx* c)
 {
   PeerHalo H{};
   H.n_nbr = static_cast<int>(c->nbr_ranks.size());
@@ -143,6 +143,8 @@ void peer_connect(ptb_ctx* c, int rank, int nranks, const void* all_handles,
   if (n_recv > 0 && !src_index)
     throw std::runtime_error("ptb_peer_connect: src_index is NULL");
   c->peer.src_index.upload(src_index, n_recv, c->stream);
+  c->peer.ready.alloc(32);
+  c->peer.ready.zero(c->stream);
   PTB_CUDA(cudaStreamSynchronize(c->stream));
   c->peer.enabled = nranks > 1;
 }
