@@ -73,6 +73,8 @@ def lib():
         L.ptb_stage_ms.restype = dbl
         L.ptb_launch_count.argtypes = [vp]
         L.ptb_launch_count.restype = i64
+        L.ptb_cols_explicit_fraction.argtypes = [vp]
+        L.ptb_cols_explicit_fraction.restype = dbl
         L.ptb_device_bytes.argtypes = [vp]
         L.ptb_device_bytes.restype = i64
         _lib = L
@@ -257,6 +259,9 @@ class Context:
 
     def launch_count(self):
         return lib().ptb_launch_count(self._h)
+
+    def cols_explicit_fraction(self):
+        return lib().ptb_cols_explicit_fraction(self._h)
 
     def device_bytes(self):
         return lib().ptb_device_bytes(self._h)

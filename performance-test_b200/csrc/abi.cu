@@ -75,7 +75,7 @@ std::int64_t ptb_ctx::device_bytes() const
          + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
-         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes()
+         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes()
          + peer.src_index.bytes();
 }
 
@@ -255,6 +255,15 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     c->mat_off.upload(L.mat_off, c->stream);
     c->adj_off.upload(L.adj_off, c->stream);
     c->cols.upload(L.cols, c->stream);
+    if (c->bs == 1)
+    {
+      compress_columns(N, static_cast<std::int64_t>(N) + c->n_ghost, rowptr, L);
+      c->cdelta.upload(L.cdelta, c->stream);
+      c->colsx.upload(L.colsx, c->stream);
+      c->xoff.upload(L.xoff, c->stream);
+      c->cols_explicit_frac
+          = L.cols.empty() ? 0.0 : static_cast<double>(L.colsx.size()) / L.cols.size();
+    }
     if (!L.adjrot.empty())
     {
       // P1: the rotated one-word slot map is all the kernels need
@@ -697,5 +706,6 @@ double ptb_stage_ms(const ptb_ctx* c, int stage)
 }
 int64_t ptb_launch_count(const ptb_ctx* c) { return c ? c->launches : 0; }
 int64_t ptb_device_bytes(const ptb_ctx* c) { return c ? c->device_bytes() : 0; }
+double ptb_cols_explicit_fraction(const ptb_ctx* c) { return c ? c->cols_explicit_frac : 1.0; }
 
 } // extern "C"

@@ -12,6 +12,7 @@
 #include "kernels.h"
 #include "peer.cuh"
 #include "reduce.cuh"
+#include <climits>
 
 namespace ptb
 {
@@ -21,15 +22,88 @@ namespace
 constexpr int SPMV_THREADS = 256;
 constexpr int VEC_THREADS = 256;
 
-// Gather of the input vector. In the fused-halo kernel the ghost part of p is written by the same
-// launch, so the non-coherent (read-only) path must not be used there.
-template <bool FUSED>
+// Gather of the input vector: read-only (non-coherent) path, except for slices that read ghost
+// entries in the fused-halo kernel -- those were written by this very launch, so they bypass L1.
+enum class Ld
+{
+  NC,
+  CG
+};
+template <Ld L>
 __device__ __forceinline__ double ldp(const double* q)
 {
-  if constexpr (FUSED)
-    return *q;
-  else
+  if constexpr (L == Ld::NC)
     return __ldg(q);
+  else
+    return __ldcg(q);
+}
+
+// One SELL-32 slice: y[row] = sum_k vals * p[col]; returns this row's p.y contribution.
+template <int BS, Ld L>
+__device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __restrict__ p,
+                                             double* __restrict__ y, std::int32_t slice, int lane)
+{
+  const std::int64_t mo = A.mat_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  if constexpr (BS == 1)
+  {
+    const double* __restrict__ vp = A.vals + mo + lane;
+    // compressed columns: one warp-uniform delta per (slice, k) when the stencil is translation
+    // invariant over the slice, explicit indices otherwise (layout.h)
+    const std::int32_t* __restrict__ dp = A.cdelta + (mo >> 5);
+    const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
+    auto column = [&](int kk) -> std::int32_t {
+      const std::int32_t d = __ldg(dp + kk);
+      if (d != INT32_MIN)
+        return row + d;
+      const std::int32_t c = xp[0];
+      xp += 32;
+      return c;
+    };
+    double sum = 0.0;
+    int k = 0;
+    for (; k + 4 <= w; k += 4)
+    {
+      const std::int32_t c0 = column(k), c1 = column(k + 1), c2 = column(k + 2), c3 = column(k + 3);
+      const double v0 = vp[(k + 0) * 32], v1 = vp[(k + 1) * 32], v2 = vp[(k + 2) * 32],
+                   v3 = vp[(k + 3) * 32];
+      sum += v0 * ldp<L>(p + c0);
+      sum += v1 * ldp<L>(p + c1);
+      sum += v2 * ldp<L>(p + c2);
+      sum += v3 * ldp<L>(p + c3);
+    }
+    for (; k < w; ++k)
+      sum += vp[k * 32] * ldp<L>(p + column(k));
+    if (row < A.n_rows)
+    {
+      y[row] = sum;
+      return sum * ldp<L>(p + row);
+    }
+    return 0.0;
+  }
+  else
+  {
+    const std::int32_t* __restrict__ cp = A.cols + mo + lane;
+    const double* __restrict__ vp = A.vals + mo * 9 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = 0; k < w; ++k)
+    {
+      const std::int64_t c = cp[k * 32];
+      const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
+      const double p0 = ldp<L>(p + 3 * c), p1 = ldp<L>(p + 3 * c + 1), p2 = ldp<L>(p + 3 * c + 2);
+      s0 += v[0 * 32] * p0 + v[1 * 32] * p1 + v[2 * 32] * p2;
+      s1 += v[3 * 32] * p0 + v[4 * 32] * p1 + v[5 * 32] * p2;
+      s2 += v[6 * 32] * p0 + v[7 * 32] * p1 + v[8 * 32] * p2;
+    }
+    if (row < A.n_rows)
+    {
+      const std::int64_t r3 = 3 * static_cast<std::int64_t>(row);
+      y[r3] = s0, y[r3 + 1] = s1, y[r3 + 2] = s2;
+      return s0 * ldp<L>(p + r3) + s1 * ldp<L>(p + r3 + 1) + s2 * ldp<L>(p + r3 + 2);
+    }
+    return 0.0;
+  }
 }
 
 // Halo exchange fused into the operator (peer mode): the first FH.npull CTAs pull the ghost values
@@ -58,7 +132,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 }
 
 template <int BS, bool FUSED>
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? (FUSED ? 6 : 8) : 5)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
           double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH)
 {
@@ -87,17 +161,35 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
         }
       }
       __syncthreads();
+      // pull: PULL_ILP independent remote loads in flight per thread (NVLink latency ~2 us)
+      constexpr int PULL_ILP = 4;
       const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
-      for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
-           i < n; i += static_cast<std::int64_t>(FH.npull) * blockDim.x)
+      const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
+      for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+           i0 < n; i0 += step * PULL_ILP)
       {
-        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
-        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
-        int nb = 0;
-        while (j >= H.recv_displ[nb + 1])
-          ++nb;
-        FH.pw[static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c]
-            = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+        double val[PULL_ILP];
+        std::int64_t dst[PULL_ILP];
+#pragma unroll
+        for (int u = 0; u < PULL_ILP; ++u)
+        {
+          const std::int64_t i = i0 + u * step;
+          dst[u] = -1;
+          if (i < n)
+          {
+            const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+            const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+            int nb = 0;
+            while (j >= H.recv_displ[nb + 1])
+              ++nb;
+            dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
+            val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PULL_ILP; ++u)
+          if (dst[u] >= 0)
+            FH.pw[dst[u]] = val[u];
       }
       __syncthreads();
       if (threadIdx.x == 0)
@@ -111,69 +203,26 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   double dotv = 0.0;
   for (std::int32_t it = warp0; it < A.n_slices; it += stride)
   {
-    std::int32_t slice = it;
     if constexpr (FUSED)
     {
-      slice = FH.order[it];
-      if (!ghosts_ready && it >= FH.n_interior)
+      const std::int32_t slice = FH.order[it];
+      if (it >= FH.n_interior)
       {
-        unsigned long long f;
-        do
-          f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
-        while (!__all_sync(0xffffffffu, f >= FH.epoch));
-        ghosts_ready = true;
+        if (!ghosts_ready)
+        {
+          unsigned long long f;
+          do
+            f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
+          while (!__all_sync(0xffffffffu, f >= FH.epoch));
+          ghosts_ready = true;
+        }
+        dotv += spmv_slice<BS, Ld::CG>(A, p, y, slice, lane);
       }
-    }
-    const std::int64_t mo = A.mat_off[slice];
-    const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
-    const std::int32_t row = slice * 32 + lane;
-    if constexpr (BS == 1)
-    {
-      const std::int32_t* __restrict__ cp = A.cols + mo + lane;
-      const double* __restrict__ vp = A.vals + mo + lane;
-      double sum = 0.0;
-      int k = 0;
-      for (; k + 4 <= w; k += 4)
-      {
-        const std::int32_t c0 = cp[(k + 0) * 32], c1 = cp[(k + 1) * 32], c2 = cp[(k + 2) * 32],
-                           c3 = cp[(k + 3) * 32];
-        const double v0 = vp[(k + 0) * 32], v1 = vp[(k + 1) * 32], v2 = vp[(k + 2) * 32],
-                     v3 = vp[(k + 3) * 32];
-        sum += v0 * ldp<FUSED>(p + c0);
-        sum += v1 * ldp<FUSED>(p + c1);
-        sum += v2 * ldp<FUSED>(p + c2);
-        sum += v3 * ldp<FUSED>(p + c3);
-      }
-      for (; k < w; ++k)
-        sum += vp[k * 32] * ldp<FUSED>(p + cp[k * 32]);
-      if (row < A.n_rows)
-      {
-        y[row] = sum;
-        dotv += sum * ldp<FUSED>(p + row);
-      }
+      else
+        dotv += spmv_slice<BS, Ld::NC>(A, p, y, slice, lane);
     }
     else
-    {
-      const std::int32_t* __restrict__ cp = A.cols + mo + lane;
-      const double* __restrict__ vp = A.vals + mo * 9 + lane;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-      for (int k = 0; k < w; ++k)
-      {
-        const std::int64_t c = cp[k * 32];
-        const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
-        const double p0 = ldp<FUSED>(p + 3 * c), p1 = ldp<FUSED>(p + 3 * c + 1),
-                     p2 = ldp<FUSED>(p + 3 * c + 2);
-        s0 += v[0 * 32] * p0 + v[1 * 32] * p1 + v[2 * 32] * p2;
-        s1 += v[3 * 32] * p0 + v[4 * 32] * p1 + v[5 * 32] * p2;
-        s2 += v[6 * 32] * p0 + v[7 * 32] * p1 + v[8 * 32] * p2;
-      }
-      if (row < A.n_rows)
-      {
-        const std::int64_t r3 = 3 * static_cast<std::int64_t>(row);
-        y[r3] = s0, y[r3 + 1] = s1, y[r3 + 2] = s2;
-        dotv += s0 * ldp<FUSED>(p + r3) + s1 * ldp<FUSED>(p + r3 + 1) + s2 * ldp<FUSED>(p + r3 + 2);
-      }
-    }
+      dotv += spmv_slice<BS, Ld::NC>(A, p, y, it, lane);
   }
   if (st != nullptr)
   {
@@ -420,7 +469,8 @@ int cg_grid(const ptb_ctx* c)
 void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
                  bool fused_halo)
 {
-  SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p};
+  SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
+             c->cdelta.p, c->colsx.p, c->xoff.p};
   const int grid = cg_grid(c);
   const PeerView P = peer_view(c);
   FusedHalo FH{};

@@ -122,6 +122,9 @@ struct ptb_ctx
   int max_w = 0, max_wa = 0, so_bits = 8, so_words = 1;
   ptb::DevBuf<std::int64_t> rowptr, mat_off, adj_off;
   ptb::DevBuf<std::int32_t> cols;      // SELL
+  ptb::DevBuf<std::int32_t> cdelta, colsx; // compressed column indices for the scalar SpMV
+  ptb::DevBuf<std::int64_t> xoff;
+  double cols_explicit_frac = 1.0;
   ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)
   std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry

@@ -68,6 +68,9 @@ struct SpmvArgs
   const std::int64_t* mat_off;
   const std::int32_t* cols;
   const double* vals;
+  const std::int32_t* cdelta; // scalar matrices: compressed columns (nullptr: use cols)
+  const std::int32_t* colsx;
+  const std::int64_t* xoff;
 };
 
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);

@@ -94,6 +94,69 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
   }
 }
 
+void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64_t* rowptr,
+                      SellLayout& L)
+{
+  const std::int32_t S = L.n_slices;
+  L.cdelta.assign(static_cast<std::size_t>(L.mat_off[S] / 32), CDELTA_EXPLICIT);
+  L.xoff.assign(S + 1, 0);
+#pragma omp parallel for schedule(static)
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    const std::int64_t mo = L.mat_off[s], w = (L.mat_off[s + 1] - mo) / 32;
+    const std::int32_t r0 = 32 * s;
+    const bool full = r0 + 32 <= n_rows; // a partial last slice stays explicit (r + d may overrun)
+    std::int64_t nx = 0;
+    for (std::int64_t k = 0; k < w; ++k)
+    {
+      bool uniform = full;
+      std::int64_t d = 0;
+      bool have = false;
+      for (int lane = 0; lane < 32 && uniform; ++lane)
+      {
+        const std::int32_t r = r0 + lane;
+        if (k >= rowptr[r + 1] - rowptr[r])
+          continue; // padding: free to choose
+        const std::int64_t dl = static_cast<std::int64_t>(L.cols[mo + k * 32 + lane]) - r;
+        if (!have)
+          d = dl, have = true;
+        else if (dl != d)
+          uniform = false;
+      }
+      if (uniform && !have)
+        d = 0; // all padding: point at the row itself
+      if (uniform)
+        for (int lane = 0; lane < 32; ++lane)
+        {
+          const std::int64_t cidx = static_cast<std::int64_t>(r0) + lane + d;
+          if (cidx < 0 || cidx >= n_cols)
+            uniform = false;
+        }
+      if (uniform)
+        L.cdelta[mo / 32 + k] = static_cast<std::int32_t>(d);
+      else
+        ++nx;
+    }
+    L.xoff[s + 1] = nx * 32;
+  }
+  for (std::int32_t s = 0; s < S; ++s)
+    L.xoff[s + 1] += L.xoff[s];
+  L.colsx.resize(static_cast<std::size_t>(L.xoff[S]));
+#pragma omp parallel for schedule(static)
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    const std::int64_t mo = L.mat_off[s], w = (L.mat_off[s + 1] - mo) / 32;
+    std::int64_t j = 0;
+    for (std::int64_t k = 0; k < w; ++k)
+      if (L.cdelta[mo / 32 + k] == CDELTA_EXPLICIT)
+      {
+        for (int lane = 0; lane < 32; ++lane)
+          L.colsx[L.xoff[s] + j * 32 + lane] = L.cols[mo + k * 32 + lane];
+        ++j;
+      }
+  }
+}
+
 namespace
 {
 const int tet_edges[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};

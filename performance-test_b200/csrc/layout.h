@@ -2,6 +2,7 @@
 // cell -> slot map (see ctx.h for the layout).
 #pragma once
 #include "../common/intmaps.h"
+#include <climits>
 #include <cstdint>
 #include <vector>
 
@@ -21,7 +22,18 @@ struct SellLayout
   // P1 only (nd == 4, offsets < 255): the four in-row offsets of a pair rotated so that the
   // owner's own column comes first: byte t = offset of local vertex (li + t) & 3.
   std::vector<std::uint32_t> adjrot;
+  // Column-index compression for the SpMV (scalar matrices): cdelta[mat_off[s]/32 + k] = d when
+  // every row r of slice s has col_k = r + d (translation-invariant stencil), else CDELTA_EXPLICIT
+  // and the 32 indices are stored in colsx at xoff[s] + j*32 + lane (j-th explicit k of the slice).
+  std::vector<std::int32_t> cdelta, colsx;
+  std::vector<std::int64_t> xoff; // [n_slices + 1]
 };
+constexpr std::int32_t CDELTA_EXPLICIT = INT32_MIN;
+
+/// Build cdelta / colsx / xoff from the padded SELL columns. Padding entries (value 0) may take
+/// any valid column, so they never break uniformity unless r + d leaves [0, n_cols).
+void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64_t* rowptr,
+                      SellLayout& L);
 
 void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
                        const std::int32_t* cols, const RowAdjacency& adj,

@@ -5,8 +5,10 @@ Tolerances (the reference pins nothing):
   * A: |dA| <= 1e-12 * (diagonal magnitude of the row) -- 8 of the 15 stored P1-Poisson entries
     per interior row are analytic zeros, so a per-entry relative tolerance is meaningless;
   * b: |db| <= 1e-12 * |b|_inf;
-  * CG: iteration count within +-1, final relative residual within 1e-10 relative... of the
-    oracle's when the counts agree (same stopping rule |r|^2/|r0|^2 < rtol^2, cg.h:78).
+  * CG: iteration count within +-1; both final relative residuals below rtol and, when the
+    counts agree, within 1e-10 + 5% of each other (same stopping rule |r|^2/|r0|^2 < rtol^2,
+    cg.h:78; the two sides sum in different orders, so bitwise-equal residual histories are not
+    expected).
 """
 import numpy as np
 import pytest
@@ -119,7 +121,9 @@ def test_cg_matches_oracle(pt, oracle, ctx, ptype, order, dims, precond):
     assert abs(k - k_ref) <= 1, (k, k_ref)
     assert rel < 1e-8
     if k == k_ref:
-        assert abs(rel - rel_ref) <= 1e-10 * max(1.0, rel_ref) + 1e-3 * rel_ref
+        # same stopping rule, different (deterministic) summation order: after hundreds of
+        # iterations the last residuals agree to a few percent of rtol, not to the last digit
+        assert abs(rel - rel_ref) <= 1e-10 + 0.05 * rel_ref
     x = ctx.solution()[: P.n_owned * P.bs]
     assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
     assert ctx.solution_norm() == pytest.approx(np.linalg.norm(x), rel=1e-12)
