@@ -450,28 +450,33 @@ sqnorm_kernel(std::int64_t n, const double* __restrict__ v, double* out, double*
   }
 }
 
-int vec_grid(const ptb_ctx* c, std::int64_t n)
+// Grids are sized to exactly one resident wave: SMs x (CTAs of this kernel that fit on an SM),
+// capped by the work. A second partial wave would run at low occupancy and stretch the tail.
+template <typename K>
+int resident_grid(const ptb_ctx* c, K kernel, int threads, std::int64_t need)
 {
-  const std::int64_t need = (n + VEC_THREADS - 1) / VEC_THREADS;
-  const std::int64_t cap = static_cast<std::int64_t>(c->num_sms) * 8;
+  int per_sm = 0;
+  PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0));
+  const std::int64_t cap = static_cast<std::int64_t>(c->num_sms) * std::max(1, std::min(per_sm, 8));
   return static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
+}
+
+template <typename K>
+int vec_grid(const ptb_ctx* c, K kernel, std::int64_t n)
+{
+  return resident_grid(c, kernel, VEC_THREADS, (n / 2 + VEC_THREADS - 1) / VEC_THREADS);
 }
 
 } // namespace
 
-int cg_grid(const ptb_ctx* c)
-{
-  const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
-  const std::int64_t cap = static_cast<std::int64_t>(c->num_sms) * 8;
-  return static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
-}
+int cg_grid(const ptb_ctx* c) { return c->num_sms * 8; }
 
 void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
                  bool fused_halo)
 {
   SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
              c->cdelta.p, c->colsx.p, c->xoff.p};
-  const int grid = cg_grid(c);
+  const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const PeerView P = peer_view(c);
   FusedHalo FH{};
   if (fused_halo)
@@ -481,23 +486,30 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
     FH.H = peer_halo(c);
     FH.order = c->slice_order.p;
     FH.n_interior = c->n_interior_slices;
-    FH.npull = std::min(32, grid);
     FH.epoch = ++c->peer.halo_epoch;
     FH.ready = c->peer.ready.p;
     FH.pw = c->p.p;
     if (c->bs == 1)
+    {
+      const int grid = resident_grid(c, spmv_sell<1, true>, SPMV_THREADS, need);
+      FH.npull = std::min(32, grid);
       spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                c->tickets.p, P, epoch, FH);
+    }
     else
+    {
+      const int grid = resident_grid(c, spmv_sell<3, true>, SPMV_THREADS, need);
+      FH.npull = std::min(32, grid);
       spmv_sell<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                c->tickets.p, P, epoch, FH);
+    }
   }
   else if (c->bs == 1)
-    spmv_sell<1, false><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
-                                                              c->tickets.p, P, epoch, FH);
+    spmv_sell<1, false><<<resident_grid(c, spmv_sell<1, false>, SPMV_THREADS, need), SPMV_THREADS,
+                          0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
   else
-    spmv_sell<3, false><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
-                                                              c->tickets.p, P, epoch, FH);
+    spmv_sell<3, false><<<resident_grid(c, spmv_sell<3, false>, SPMV_THREADS, need), SPMV_THREADS,
+                          0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -505,7 +517,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
 void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_init<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->b.p, c->y.p, dinv, c->r.p, c->p.p,
+  cg_init<<<vec_grid(c, cg_init, 2 * n), VEC_THREADS, 0, c->stream>>>(n, c->b.p, c->y.p, dinv, c->r.p, c->p.p,
                                                          st, c->partials.p, c->tickets.p + 1,
                                                          peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
@@ -523,7 +535,7 @@ void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int
                       unsigned int epoch_out)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_update<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->y.p, dinv, c->r.p, cur,
+  cg_update<<<vec_grid(c, cg_update, n), VEC_THREADS, 0, c->stream>>>(n, c->y.p, dinv, c->r.p, cur,
                                                            c->partials.p, c->tickets.p + 1,
                                                            peer_view(c), epoch_in, epoch_out);
   PTB_CUDA(cudaGetLastError());
@@ -534,7 +546,7 @@ void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgS
                          unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_direction<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
+  cg_direction<<<vec_grid(c, cg_direction, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
                                                               nxt, peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
@@ -544,7 +556,7 @@ void launch_fill(ptb_ctx* c, double* v, std::int64_t n, double value)
 {
   if (n == 0)
     return;
-  fill_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(v, n, value);
+  fill_kernel<<<vec_grid(c, fill_kernel, 2 * n), VEC_THREADS, 0, c->stream>>>(v, n, value);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -571,7 +583,7 @@ void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::i
 
 void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev)
 {
-  sqnorm_kernel<<<vec_grid(c, n), VEC_THREADS, 0, c->stream>>>(n, v, out_dev, c->partials.p,
+  sqnorm_kernel<<<vec_grid(c, sqnorm_kernel, 2 * n), VEC_THREADS, 0, c->stream>>>(n, v, out_dev, c->partials.p,
                                                                c->tickets.p + 2, peer_view(c),
                                                                next_red_epoch(c));
   PTB_CUDA(cudaGetLastError());
