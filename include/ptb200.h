@@ -124,6 +124,12 @@ int ptb_build_cell_slot_map(int64_t n_cells, int nd, const int32_t* dofmap, int3
 int ptb_get_slot_offsets(ptb_ctx* ctx, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets);
 
+/* Round trip of the device matrix layout on the host (no GPU): builds the SELL-32 layout and the
+ * compressed column indices from a CSR pattern, decodes them again into cols_out (CSR order) and
+ * reports the fraction of indices that stayed explicit. Used by the CPU tests. */
+int ptb_debug_layout_roundtrip(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
+                               const int32_t* cols, int32_t* cols_out, double* explicit_fraction);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

@@ -67,6 +67,7 @@ def lib():
         L.ptb_get_solution.argtypes = [vp, vp]
         L.ptb_solution_norm.argtypes = [vp, C.POINTER(dbl)]
         L.ptb_build_cell_slot_map.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp]
+        L.ptb_debug_layout_roundtrip.argtypes = [i32, i64, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
@@ -99,6 +100,18 @@ def build_cell_slot_map(dofmap, nd, n_owned, rowptr, cols):
     if rc != 0:
         raise RuntimeError(lib().ptb_last_error(None).decode())
     return out
+
+
+def layout_roundtrip(n_rows, n_cols, rowptr, cols):
+    """Host-only: SELL-32 + column compression encode/decode; returns (cols decoded, explicit fraction)."""
+    rp, cl = _a(rowptr, np.int64), _a(cols, np.int32)
+    out = np.full(len(cl), -1, dtype=np.int32)
+    frac = C.c_double()
+    rc = lib().ptb_debug_layout_roundtrip(n_rows, n_cols, _ptr(rp), _ptr(cl), _ptr(out),
+                                          C.byref(frac))
+    if rc != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return out, frac.value
 
 
 def nccl_unique_id() -> bytes:

@@ -70,7 +70,7 @@ void alloc_vectors(ptb_ctx* c)
 
 std::int64_t ptb_ctx::device_bytes() const
 {
-  return xyz.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
+  return xyz.bytes() + xyz3.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
          + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
@@ -159,8 +159,8 @@ int ptb_set_mesh(ptb_ctx* c, int64_t n_vertices, const double* x, int64_t n_cell
     c->n_vertices = n_vertices, c->n_cells = n_cells;
     c->x_dofmap.upload(x_dofmap, static_cast<std::size_t>(n_cells) * 4, c->stream);
     c->xyz.alloc(static_cast<std::size_t>(n_vertices) * 4);
-    PTB_CUDA(cudaMemcpy2DAsync(c->xyz.p, 4 * sizeof(double), x, 3 * sizeof(double),
-                               3 * sizeof(double), n_vertices, cudaMemcpyHostToDevice, c->stream));
+    c->xyz3.upload(x, static_cast<std::size_t>(n_vertices) * 3, c->stream); // one contiguous DMA
+    launch_pad_xyz(c);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_mesh = true;
     c->matrix_assembled = c->vector_assembled = false;
@@ -172,9 +172,8 @@ int ptb_update_geometry(ptb_ctx* c, const double* x)
   return guarded(c, [&] {
     use_device(c);
     need(c->have_mesh && x, "ptb_update_geometry: call ptb_set_mesh first");
-    PTB_CUDA(cudaMemcpy2DAsync(c->xyz.p, 4 * sizeof(double), x, 3 * sizeof(double),
-                               3 * sizeof(double), c->n_vertices, cudaMemcpyHostToDevice,
-                               c->stream));
+    c->xyz3.upload(x, static_cast<std::size_t>(c->n_vertices) * 3, c->stream);
+    launch_pad_xyz(c);
     if (c->have_space)
       launch_gather_xdof(c);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -634,6 +633,42 @@ int ptb_build_cell_slot_map(int64_t n_cells, int nd, const int32_t* dofmap, int3
   return guarded(nullptr, [&] {
     need(dofmap && rowptr && cols && slot, "ptb_build_cell_slot_map: NULL argument");
     build_cell_slot_map(dofmap, n_cells, nd, n_owned, rowptr, cols, slot);
+  });
+}
+
+int ptb_debug_layout_roundtrip(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
+                               const int32_t* cols, int32_t* cols_out, double* explicit_fraction)
+{
+  return guarded(nullptr, [&] {
+    need(rowptr && cols && cols_out, "ptb_debug_layout_roundtrip: NULL argument");
+    RowAdjacency adj;
+    adj.ptr.assign(static_cast<std::size_t>(n_rows) + 1, 0);
+    std::vector<std::uint16_t> so;
+    SellLayout L;
+    build_sell_layout(n_rows, 4, rowptr, cols, adj, so, 0, L);
+    compress_columns(n_rows, n_cols, rowptr, L);
+    for (std::int32_t s = 0; s < L.n_slices; ++s)
+    {
+      const std::int64_t mo = L.mat_off[s], w = (L.mat_off[s + 1] - mo) / 32;
+      for (int lane = 0; lane < 32; ++lane)
+      {
+        const std::int32_t r = 32 * s + lane;
+        if (r >= n_rows)
+          continue;
+        std::int64_t j = 0;
+        for (std::int64_t k = 0; k < w; ++k)
+        {
+          const std::int32_t d = L.cdelta[mo / 32 + k];
+          const std::int32_t cidx = d != CDELTA_EXPLICIT ? r + d : L.colsx[L.xoff[s] + (j++) * 32 + lane];
+          if (k < rowptr[r + 1] - rowptr[r])
+            cols_out[rowptr[r] + k] = cidx;
+          else
+            need(cidx >= 0 && cidx < n_cols, "layout: padding column out of range");
+        }
+      }
+    }
+    if (explicit_fraction)
+      *explicit_fraction = L.cols.empty() ? 0.0 : static_cast<double>(L.colsx.size()) / L.cols.size();
   });
 }
 

@@ -207,7 +207,7 @@ assemble_matrix_p1(MatrixArgs A)
       const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
       const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
                                    star_edge(E, o3, lane));
-      const double s = 1.0 / (6.0 * fabs(G.det));
+      const double s = __drcp_rn(6.0 * fabs(G.det));
       if constexpr (BS == 1)
       {
         dg0 += s * dot(G.c0, G.c0);
@@ -429,6 +429,16 @@ std::size_t mat_smem_doubles(int max_w, int bs)
   return static_cast<std::size_t>(max_w) * (3 + bs * bs) * 32 + (static_cast<std::size_t>(max_w) * 32 + 1) / 2;
 }
 
+__global__ void pad_xyz(std::int64_t n, const double* __restrict__ x3, double* __restrict__ x4)
+{
+  const std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n)
+    return;
+  double2* q = reinterpret_cast<double2*>(x4 + 4 * i);
+  q[0] = make_double2(x3[3 * i], x3[3 * i + 1]);
+  q[1] = make_double2(x3[3 * i + 2], 0.0);
+}
+
 template <typename K>
 void set_smem(K kernel, std::size_t smem)
 {
@@ -499,6 +509,14 @@ void launch_sell_to_csr(ptb_ctx* c, double* out)
   const int bs2 = c->bs * c->bs;
   sell_to_csr<<<(c->n_owned + 127) / 128, 128, 0, c->stream>>>(c->n_owned, bs2, c->rowptr.p,
                                                                c->mat_off.p, c->vals.p, out);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+}
+
+void launch_pad_xyz(ptb_ctx* c)
+{
+  const std::int64_t n = c->n_vertices;
+  pad_xyz<<<static_cast<int>((n + 255) / 256), 256, 0, c->stream>>>(n, c->xyz3.p, c->xyz.p);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }

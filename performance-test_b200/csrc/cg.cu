@@ -49,32 +49,54 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
   if constexpr (BS == 1)
   {
     const double* __restrict__ vp = A.vals + mo + lane;
-    // compressed columns: one warp-uniform delta per (slice, k) when the stencil is translation
-    // invariant over the slice, explicit indices otherwise (layout.h)
+    // Compressed columns (layout.h): one delta per (slice, k) when the stencil is translation
+    // invariant over the slice, explicit indices otherwise. The deltas of up to 32 entries are
+    // fetched with ONE coalesced load and broadcast by shuffle, so neither the value loads nor
+    // the gathers of p wait on index loads.
     const std::int32_t* __restrict__ dp = A.cdelta + (mo >> 5);
     const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
-    auto column = [&](int kk) -> std::int32_t {
-      const std::int32_t d = __ldg(dp + kk);
-      if (d != INT32_MIN)
-        return row + d;
-      const std::int32_t c = xp[0];
-      xp += 32;
-      return c;
-    };
     double sum = 0.0;
-    int k = 0;
-    for (; k + 4 <= w; k += 4)
+    for (int k0 = 0; k0 < w; k0 += 32)
     {
-      const std::int32_t c0 = column(k), c1 = column(k + 1), c2 = column(k + 2), c3 = column(k + 3);
-      const double v0 = vp[(k + 0) * 32], v1 = vp[(k + 1) * 32], v2 = vp[(k + 2) * 32],
-                   v3 = vp[(k + 3) * 32];
-      sum += v0 * ldp<L>(p + c0);
-      sum += v1 * ldp<L>(p + c1);
-      sum += v2 * ldp<L>(p + c2);
-      sum += v3 * ldp<L>(p + c3);
+      const int kn = min(32, w - k0);
+      const std::int32_t dl = lane < kn ? __ldg(dp + k0 + lane) : 0;
+      const unsigned int em = __ballot_sync(0xffffffffu, lane < kn && dl == INT32_MIN);
+      const double* __restrict__ v = vp + static_cast<std::int64_t>(k0) * 32;
+      if (em == 0u)
+      {
+        int kk = 0;
+        constexpr int U = 5; // 15 entries per interior P1 row = 3 batches of 5
+        for (; kk + U <= kn; kk += U)
+        {
+          double vv[U], pp[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+          {
+            vv[u] = v[(kk + u) * 32];
+            pp[u] = ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk + u)));
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            sum += vv[u] * pp[u];
+        }
+        for (; kk < kn; ++kk)
+          sum += v[kk * 32] * ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk)));
+      }
+      else
+      {
+        for (int kk = 0; kk < kn; ++kk)
+        {
+          const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
+          std::int32_t c = row + d;
+          if ((em >> kk) & 1u)
+          {
+            c = xp[0];
+            xp += 32;
+          }
+          sum += v[kk * 32] * ldp<L>(p + c);
+        }
+      }
     }
-    for (; k < w; ++k)
-      sum += vp[k * 32] * ldp<L>(p + column(k));
     if (row < A.n_rows)
     {
       y[row] = sum;
@@ -132,7 +154,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 }
 
 template <int BS, bool FUSED>
-__global__ void __launch_bounds__(SPMV_THREADS, BS == 1 ? (FUSED ? 6 : 8) : 5)
+__global__ void __launch_bounds__(SPMV_THREADS, 5)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
           double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH)
 {

@@ -80,6 +80,8 @@ void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs&
 void launch_sell_to_csr(ptb_ctx* c, double* out);
 /// xdof[d] = xyz[dof_vertex[d]] for vertex dofs.
 void launch_gather_xdof(ptb_ctx* c);
+/// xyz[v][0..2] = xyz3[v][0..2] (pad the caller's 3-column geometry to 32-byte points).
+void launch_pad_xyz(ptb_ctx* c);
 
 // cg.cu
 int cg_grid(const ptb_ctx* c);
