@@ -259,6 +259,244 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TMA-staged variant of the scalar operator (rows with <= 32 stored entries, i.e. P1).
+// With the column indices compressed away the kernel streams almost nothing but matrix values,
+// and a thread-per-row loop cannot keep enough of them in flight from registers. Here every warp
+// owns a ring of TMA_STAGES shared-memory buffers; lane 0 fetches whole slices (w x 256 B of
+// values, one contiguous block in SELL-32) with cp.async.bulk (TMA, SASS UBLKCP) completing on an
+// mbarrier, TMA_STAGES slices ahead, while the warp gathers p for the current slice from
+// registers. Bytes in flight per SM are set by the ring depth, not by the register file.
+// ------------------------------------------------------------------------------------------
+constexpr int TMA_STAGES = 3;
+constexpr int TMA_THREADS = 256;
+
+__device__ __forceinline__ std::uint32_t smem_u32(const void* p)
+{
+  return static_cast<std::uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(std::uint64_t* bar, std::uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(std::uint64_t* bar, std::uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, std::uint32_t bytes,
+                                            std::uint64_t* bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(std::uint64_t* bar, std::uint32_t parity)
+{
+  std::uint32_t ok = 0;
+  const std::uint32_t a = smem_u32(bar);
+  do
+  {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok)
+                 : "r"(a), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+template <bool FUSED>
+__global__ void __launch_bounds__(TMA_THREADS, 3)
+spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
+              double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH,
+              int stage_doubles)
+{
+  extern __shared__ __align__(128) unsigned char dsm[];
+  __shared__ double red[32];
+  if (st != nullptr && st->conv)
+    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int warps_per_cta = TMA_THREADS / 32;
+  const std::int32_t warp0 = blockIdx.x * warps_per_cta + warp;
+  const std::int32_t stride = gridDim.x * warps_per_cta;
+  double* ring = reinterpret_cast<double*>(dsm) + static_cast<std::size_t>(warp) * TMA_STAGES * stage_doubles;
+  std::uint64_t* bars = reinterpret_cast<std::uint64_t*>(
+                            dsm + static_cast<std::size_t>(warps_per_cta) * TMA_STAGES * stage_doubles * sizeof(double))
+                        + warp * TMA_STAGES;
+  if (lane == 0)
+  {
+#pragma unroll
+    for (int s = 0; s < TMA_STAGES; ++s)
+      mbar_init(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+
+  if constexpr (FUSED)
+  {
+    const PeerHalo& H = FH.H;
+    if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
+    {
+      __threadfence_system();
+      st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
+    }
+    if (blockIdx.x < FH.npull)
+    {
+      if (threadIdx.x < H.n_nbr)
+      {
+        const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
+        while (ld_acquire_sys(flag) < FH.epoch)
+        {
+        }
+      }
+      __syncthreads();
+      constexpr int PULL_ILP = 4;
+      const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
+      const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
+      for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+           i0 < n; i0 += step * PULL_ILP)
+      {
+        double val[PULL_ILP];
+        std::int64_t dst[PULL_ILP];
+#pragma unroll
+        for (int u = 0; u < PULL_ILP; ++u)
+        {
+          const std::int64_t i = i0 + u * step;
+          dst[u] = -1;
+          if (i < n)
+          {
+            const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+            const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+            int nb = 0;
+            while (j >= H.recv_displ[nb + 1])
+              ++nb;
+            dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
+            val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < PULL_ILP; ++u)
+          if (dst[u] >= 0)
+            FH.pw[dst[u]] = val[u];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0)
+      {
+        __threadfence();
+        st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
+      }
+    }
+  }
+
+  // slices of this warp: it = warp0 + j*stride, j = 0 .. n_my-1
+  const std::int32_t n_my = warp0 < A.n_slices ? (A.n_slices - warp0 + stride - 1) / stride : 0;
+  auto slice_of = [&](std::int32_t j) -> std::int32_t {
+    const std::int32_t it = warp0 + j * stride;
+    if constexpr (FUSED)
+      return FH.order[it];
+    else
+      return it;
+  };
+  auto issue = [&](std::int32_t j) {
+    if (lane == 0)
+    {
+      const std::int32_t sl = slice_of(j);
+      const std::int64_t mo = A.mat_off[sl];
+      const std::uint32_t bytes = static_cast<std::uint32_t>((A.mat_off[sl + 1] - mo) * sizeof(double));
+      std::uint64_t* bar = &bars[j % TMA_STAGES];
+      mbar_expect_tx(bar, bytes);
+      if (bytes > 0)
+        tma_load_1d(ring + (j % TMA_STAGES) * stage_doubles, A.vals + mo, bytes, bar);
+    }
+  };
+  for (std::int32_t j = 0; j < min(n_my, TMA_STAGES); ++j)
+    issue(j);
+
+  bool ghosts_ready = !FUSED;
+  double dotv = 0.0;
+  for (std::int32_t j = 0; j < n_my; ++j)
+  {
+    const std::int32_t slice = slice_of(j);
+    const std::int64_t mo = A.mat_off[slice];
+    const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5); // <= 32 by construction
+    const std::int32_t row = slice * 32 + lane;
+    bool ghost_slice = false;
+    if constexpr (FUSED)
+    {
+      ghost_slice = warp0 + j * stride >= FH.n_interior;
+      if (ghost_slice && !ghosts_ready)
+      {
+        unsigned long long f;
+        do
+          f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
+        while (!__all_sync(0xffffffffu, f >= FH.epoch));
+        ghosts_ready = true;
+      }
+    }
+    // columns: one coalesced load of the slice's deltas, broadcast by shuffle
+    const std::int32_t dl = lane < w ? __ldg(A.cdelta + (mo >> 5) + lane) : 0;
+    const unsigned int em = __ballot_sync(0xffffffffu, lane < w && dl == INT32_MIN);
+    const double* __restrict__ v = ring + (j % TMA_STAGES) * stage_doubles + lane;
+    std::uint64_t* bar = &bars[j % TMA_STAGES];
+    const std::uint32_t parity = (j / TMA_STAGES) & 1;
+    double sum = 0.0;
+    if (em == 0u && w <= 16)
+    {
+      // gathers of p are issued before waiting for the values
+      double pp[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+      {
+        const std::int32_t d = __shfl_sync(0xffffffffu, dl, u);
+        pp[u] = u < w ? (ghost_slice ? __ldcg(p + (row + d)) : __ldg(p + (row + d))) : 0.0;
+      }
+      mbar_wait(bar, parity);
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (u < w)
+          sum += v[u * 32] * pp[u];
+    }
+    else
+    {
+      const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
+      mbar_wait(bar, parity);
+      for (int kk = 0; kk < w; ++kk)
+      {
+        std::int32_t c = row + __shfl_sync(0xffffffffu, dl, kk);
+        if ((em >> kk) & 1u)
+        {
+          c = xp[0];
+          xp += 32;
+        }
+        sum += v[kk * 32] * (ghost_slice ? __ldcg(p + c) : __ldg(p + c));
+      }
+    }
+    __syncwarp(); // every lane is done with this stage's buffer
+    if (j + TMA_STAGES < n_my)
+    {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      issue(j + TMA_STAGES);
+    }
+    if (row < A.n_rows)
+    {
+      y[row] = sum;
+      dotv += sum * (ghost_slice ? __ldcg(p + row) : __ldg(p + row));
+    }
+  }
+  if (st != nullptr)
+  {
+    double vsum[1] = {dotv}, out[1];
+    if (grid_sum_last_block<1>(vsum, partials, ticket, red, out) && threadIdx.x == 0)
+    {
+      if (P.nranks > 1)
+        peer_publish(P, epoch, out[0], 0.0);
+      else
+        st->py = out[0];
+    }
+  }
+}
+
 // Global sums for the consumer kernels: one thread per CTA collects the nranks partials from the
 // local window (peer mode) or reads the locally reduced / NCCL-reduced values.
 __device__ __forceinline__ void global_sums(const PeerView& P, unsigned int epoch, double l0,
@@ -501,7 +739,40 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const PeerView P = peer_view(c);
   FusedHalo FH{};
-  if (fused_halo)
+  if (c->bs == 1 && c->max_w <= 32)
+  {
+    // TMA-staged scalar kernel
+    if (fused_halo)
+    {
+      if (!c->peer.enabled || p != c->p.p)
+        throw std::runtime_error("fused halo: peer mode and the search direction vector only");
+      FH.H = peer_halo(c);
+      FH.order = c->slice_order.p;
+      FH.n_interior = c->n_interior_slices;
+      FH.epoch = ++c->peer.halo_epoch;
+      FH.ready = c->peer.ready.p;
+      FH.pw = c->p.p;
+    }
+    const int stage_doubles = std::max(1, c->max_w) * 32;
+    const std::size_t smem = static_cast<std::size_t>(TMA_THREADS / 32) * TMA_STAGES
+                             * (stage_doubles * sizeof(double) + sizeof(std::uint64_t));
+    auto launch = [&](auto kernel) {
+      PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+      int per_sm = 0;
+      PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TMA_THREADS, smem));
+      const std::int64_t cap = static_cast<std::int64_t>(c->num_sms) * std::max(1, std::min(per_sm, 8));
+      const int grid = static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
+      FH.npull = std::min(32, grid);
+      kernel<<<grid, TMA_THREADS, smem, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
+                                                     epoch, FH, stage_doubles);
+    };
+    if (fused_halo)
+      launch(spmv_sell_tma<true>);
+    else
+      launch(spmv_sell_tma<false>);
+  }
+  else if (fused_halo)
   {
     if (!c->peer.enabled || p != c->p.p)
       throw std::runtime_error("fused halo: peer mode and the search direction vector only");
