@@ -307,7 +307,7 @@ __device__ __forceinline__ void mbar_wait(std::uint64_t* bar, std::uint32_t pari
 }
 
 template <bool FUSED>
-__global__ void __launch_bounds__(TMA_THREADS, 3)
+__global__ void __launch_bounds__(TMA_THREADS, 2)
 spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
               double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH,
               int stage_doubles)
@@ -413,64 +413,102 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
   for (std::int32_t j = 0; j < min(n_my, TMA_STAGES); ++j)
     issue(j);
 
+  // Software pipeline over this warp's slices: the column deltas are loaded two slices ahead and
+  // the gathers of p one slice ahead, so in steady state nothing an iteration consumes was
+  // requested in that iteration (values: TMA ring; p: registers; deltas: registers).
+  struct Meta
+  {
+    std::int32_t slice, dl;
+    int w;
+    bool ghost;
+  };
+  auto load_meta = [&](std::int32_t j) -> Meta {
+    Meta m{0, 0, 0, false};
+    if (j < n_my)
+    {
+      m.slice = slice_of(j);
+      const std::int64_t mo = A.mat_off[m.slice];
+      m.w = static_cast<int>((A.mat_off[m.slice + 1] - mo) >> 5); // <= 32 by construction
+      m.dl = lane < m.w ? __ldg(A.cdelta + (mo >> 5) + lane) : 0;
+      if constexpr (FUSED)
+        m.ghost = warp0 + j * stride >= FH.n_interior;
+    }
+    return m;
+  };
+  // fast slices: all columns are row + delta, at most 16 entries, no ghost columns
+  auto is_fast = [&](const Meta& m) -> bool {
+    const unsigned int em = __ballot_sync(0xffffffffu, lane < m.w && m.dl == INT32_MIN);
+    return em == 0u && m.w <= 16 && !m.ghost;
+  };
+  auto gather = [&](const Meta& m, double (&pp)[16]) {
+    const std::int32_t row = m.slice * 32 + lane;
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+    {
+      const std::int32_t d = __shfl_sync(0xffffffffu, m.dl, u);
+      pp[u] = u < m.w ? __ldg(p + (row + d)) : 0.0;
+    }
+  };
+
   bool ghosts_ready = !FUSED;
   double dotv = 0.0;
+  Meta cur = load_meta(0), nxt = load_meta(1);
+  double pp_cur[16], pp_nxt[16];
+  bool fast_cur = n_my > 0 && is_fast(cur);
+  if (fast_cur)
+    gather(cur, pp_cur);
   for (std::int32_t j = 0; j < n_my; ++j)
   {
-    const std::int32_t slice = slice_of(j);
-    const std::int64_t mo = A.mat_off[slice];
-    const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5); // <= 32 by construction
+    // prefetch: gathers of the next slice, deltas of the one after
+    const bool fast_nxt = j + 1 < n_my && is_fast(nxt);
+    if (fast_nxt)
+      gather(nxt, pp_nxt);
+    const Meta nn = load_meta(j + 2);
+
+    const std::int32_t slice = cur.slice;
+    const int w = cur.w;
     const std::int32_t row = slice * 32 + lane;
-    bool ghost_slice = false;
-    if constexpr (FUSED)
-    {
-      ghost_slice = warp0 + j * stride >= FH.n_interior;
-      if (ghost_slice && !ghosts_ready)
-      {
-        unsigned long long f;
-        do
-          f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
-        while (!__all_sync(0xffffffffu, f >= FH.epoch));
-        ghosts_ready = true;
-      }
-    }
-    // columns: one coalesced load of the slice's deltas, broadcast by shuffle
-    const std::int32_t dl = lane < w ? __ldg(A.cdelta + (mo >> 5) + lane) : 0;
-    const unsigned int em = __ballot_sync(0xffffffffu, lane < w && dl == INT32_MIN);
     const double* __restrict__ v = ring + (j % TMA_STAGES) * stage_doubles + lane;
     std::uint64_t* bar = &bars[j % TMA_STAGES];
     const std::uint32_t parity = (j / TMA_STAGES) & 1;
     double sum = 0.0;
-    if (em == 0u && w <= 16)
+    double prow;
+    if (fast_cur)
     {
-      // gathers of p are issued before waiting for the values
-      double pp[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u)
-      {
-        const std::int32_t d = __shfl_sync(0xffffffffu, dl, u);
-        pp[u] = u < w ? (ghost_slice ? __ldcg(p + (row + d)) : __ldg(p + (row + d))) : 0.0;
-      }
       mbar_wait(bar, parity);
 #pragma unroll
       for (int u = 0; u < 16; ++u)
         if (u < w)
-          sum += v[u * 32] * pp[u];
+          sum += v[u * 32] * pp_cur[u];
+      prow = __ldg(p + row);
     }
     else
     {
+      if constexpr (FUSED)
+      {
+        if (cur.ghost && !ghosts_ready)
+        {
+          unsigned long long f;
+          do
+            f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
+          while (!__all_sync(0xffffffffu, f >= FH.epoch));
+          ghosts_ready = true;
+        }
+      }
+      const unsigned int em = __ballot_sync(0xffffffffu, lane < w && cur.dl == INT32_MIN);
       const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
       mbar_wait(bar, parity);
       for (int kk = 0; kk < w; ++kk)
       {
-        std::int32_t c = row + __shfl_sync(0xffffffffu, dl, kk);
+        std::int32_t c = row + __shfl_sync(0xffffffffu, cur.dl, kk);
         if ((em >> kk) & 1u)
         {
           c = xp[0];
           xp += 32;
         }
-        sum += v[kk * 32] * (ghost_slice ? __ldcg(p + c) : __ldg(p + c));
+        sum += v[kk * 32] * (cur.ghost ? __ldcg(p + c) : __ldg(p + c));
       }
+      prow = row < A.n_rows ? (cur.ghost ? __ldcg(p + row) : __ldg(p + row)) : 0.0;
     }
     __syncwarp(); // every lane is done with this stage's buffer
     if (j + TMA_STAGES < n_my)
@@ -481,8 +519,14 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     if (row < A.n_rows)
     {
       y[row] = sum;
-      dotv += sum * (ghost_slice ? __ldcg(p + row) : __ldg(p + row));
+      dotv += sum * prow;
     }
+    cur = nxt;
+    nxt = nn;
+    fast_cur = fast_nxt;
+#pragma unroll
+    for (int u = 0; u < 16; ++u)
+      pp_cur[u] = pp_nxt[u];
   }
   if (st != nullptr)
   {
