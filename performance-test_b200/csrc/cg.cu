@@ -13,6 +13,7 @@
 #include "peer.cuh"
 #include "reduce.cuh"
 #include <climits>
+#include <type_traits>
 
 namespace ptb
 {
@@ -452,19 +453,29 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
 
   bool ghosts_ready = !FUSED;
   double dotv = 0.0;
-  Meta cur = load_meta(0), nxt = load_meta(1);
-  double pp_cur[16], pp_nxt[16];
-  bool fast_cur = n_my > 0 && is_fast(cur);
-  if (fast_cur)
-    gather(cur, pp_cur);
-  for (std::int32_t j = 0; j < n_my; ++j)
-  {
-    // prefetch: gathers of the next slice, deltas of the one after
-    const bool fast_nxt = j + 1 < n_my && is_fast(nxt);
-    if (fast_nxt)
-      gather(nxt, pp_nxt);
-    const Meta nn = load_meta(j + 2);
+  // Ring of 4 slice descriptors and 2 gather buffers, indexed statically (the loop is unrolled by
+  // 4): a register that a load is still filling is never moved, so nothing stalls on a copy.
+  Meta M[4];
+  double PP[2][16];
+  bool fast[4] = {false, false, false, false};
+  M[0] = load_meta(0);
+  M[1] = load_meta(1);
+  fast[0] = n_my > 0 && is_fast(M[0]);
+  if (fast[0])
+    gather(M[0], PP[0]);
 
+  auto step = [&](std::int32_t j, auto S_) {
+    constexpr int S = decltype(S_)::value;
+    constexpr int S1 = (S + 1) & 3, S2 = (S + 2) & 3;
+    if (j >= n_my)
+      return;
+    // prefetch: gathers of slice j+1, descriptor of slice j+2
+    fast[S1] = j + 1 < n_my && is_fast(M[S1]);
+    if (fast[S1])
+      gather(M[S1], PP[(S + 1) & 1]);
+    M[S2] = load_meta(j + 2);
+
+    const Meta& cur = M[S];
     const std::int32_t slice = cur.slice;
     const int w = cur.w;
     const std::int32_t row = slice * 32 + lane;
@@ -473,13 +484,14 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     const std::uint32_t parity = (j / TMA_STAGES) & 1;
     double sum = 0.0;
     double prow;
-    if (fast_cur)
+    if (fast[S])
     {
+      const double(&pp)[16] = PP[S & 1];
       mbar_wait(bar, parity);
 #pragma unroll
       for (int u = 0; u < 16; ++u)
         if (u < w)
-          sum += v[u * 32] * pp_cur[u];
+          sum += v[u * 32] * pp[u];
       prow = __ldg(p + row);
     }
     else
@@ -521,12 +533,13 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
       y[row] = sum;
       dotv += sum * prow;
     }
-    cur = nxt;
-    nxt = nn;
-    fast_cur = fast_nxt;
-#pragma unroll
-    for (int u = 0; u < 16; ++u)
-      pp_cur[u] = pp_nxt[u];
+  };
+  for (std::int32_t j = 0; j < n_my; j += 4)
+  {
+    step(j, std::integral_constant<int, 0>{});
+    step(j + 1, std::integral_constant<int, 1>{});
+    step(j + 2, std::integral_constant<int, 2>{});
+    step(j + 3, std::integral_constant<int, 3>{});
   }
   if (st != nullptr)
   {
