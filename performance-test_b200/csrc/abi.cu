@@ -4,6 +4,7 @@
 #include "layout.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -276,17 +277,10 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->adjso.upload(L.adjso, c->stream);
     }
     {
-      // visiting order for the fused-halo operator: slices that read ghost columns go last
-      std::vector<std::int32_t> inner, outer;
-      for (std::int32_t s = 0; s < L.n_slices; ++s)
-      {
-        bool ghost = false;
-        for (std::int64_t q = L.mat_off[s]; q < L.mat_off[s + 1] && !ghost; ++q)
-          ghost = L.cols[q] >= N;
-        (ghost ? outer : inner).push_back(s);
-      }
-      c->n_interior_slices = static_cast<std::int32_t>(inner.size());
-      inner.insert(inner.end(), outer.begin(), outer.end());
+      // visiting order of the operator kernels (ghost-reading slices last, clustered groups)
+      std::vector<std::int32_t> inner;
+      const char* env = std::getenv("PTB_SLICE_CLUSTER");
+      build_slice_order(L, N, 8, !(env && env[0] == '0'), inner, c->n_interior_slices);
       c->slice_order.upload(inner, c->stream);
     }
     c->vals.alloc(L.cols.size() * c->bs * c->bs);

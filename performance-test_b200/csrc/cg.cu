@@ -13,6 +13,7 @@
 #include "peer.cuh"
 #include "reduce.cuh"
 #include <climits>
+#include <cstdlib>
 #include <type_traits>
 
 namespace ptb
@@ -226,9 +227,9 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   double dotv = 0.0;
   for (std::int32_t it = warp0; it < A.n_slices; it += stride)
   {
+    const std::int32_t slice = FH.order[it];
     if constexpr (FUSED)
     {
-      const std::int32_t slice = FH.order[it];
       if (it >= FH.n_interior)
       {
         if (!ghosts_ready)
@@ -245,7 +246,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
         dotv += spmv_slice<BS, Ld::NC>(A, p, y, slice, lane);
     }
     else
-      dotv += spmv_slice<BS, Ld::NC>(A, p, y, it, lane);
+      dotv += spmv_slice<BS, Ld::NC>(A, p, y, slice, lane);
   }
   if (st != nullptr)
   {
@@ -393,11 +394,7 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
   // slices of this warp: it = warp0 + j*stride, j = 0 .. n_my-1
   const std::int32_t n_my = warp0 < A.n_slices ? (A.n_slices - warp0 + stride - 1) / stride : 0;
   auto slice_of = [&](std::int32_t j) -> std::int32_t {
-    const std::int32_t it = warp0 + j * stride;
-    if constexpr (FUSED)
-      return FH.order[it];
-    else
-      return it;
+    return FH.order[warp0 + j * stride];
   };
   auto issue = [&](std::int32_t j) {
     if (lane == 0)
@@ -796,7 +793,13 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const PeerView P = peer_view(c);
   FusedHalo FH{};
-  if (c->bs == 1 && c->max_w <= 32)
+  FH.order = c->slice_order.p;
+  FH.n_interior = c->n_interior_slices;
+  static const bool use_tma = [] {
+    const char* e = std::getenv("PTB_SPMV_TMA");
+    return !(e && e[0] == '0');
+  }();
+  if (c->bs == 1 && c->max_w <= 32 && use_tma)
   {
     // TMA-staged scalar kernel
     if (fused_halo)

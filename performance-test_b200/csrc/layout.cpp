@@ -157,6 +157,58 @@ void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64
   }
 }
 
+void build_slice_order(const SellLayout& L, std::int32_t n_rows, int group, bool cluster,
+                       std::vector<std::int32_t>& order, std::int32_t& n_interior)
+{
+  const std::int32_t S = L.n_slices;
+  std::vector<char> ghost(S, 0), seen(S, 0);
+#pragma omp parallel for schedule(static)
+  for (std::int32_t s = 0; s < S; ++s)
+    for (std::int64_t q = L.mat_off[s]; q < L.mat_off[s + 1]; ++q)
+      if (L.cols[q] >= n_rows)
+      {
+        ghost[s] = 1;
+        break;
+      }
+  order.clear();
+  order.reserve(S);
+  std::vector<std::int32_t> grp, nb;
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    for (std::int32_t seed = 0; seed < S; ++seed)
+    {
+      if (seen[seed] || ghost[seed] != pass)
+        continue;
+      grp.assign(1, seed);
+      seen[seed] = 1;
+      for (std::size_t head = 0; cluster && head < grp.size() && grp.size() < static_cast<std::size_t>(group); ++head)
+      {
+        // neighbours of grp[head]: the slices its columns point into (first and last lane suffice
+        // to see every stencil direction; all lanes are scanned to stay general)
+        const std::int32_t s = grp[head];
+        nb.clear();
+        for (std::int64_t q = L.mat_off[s]; q < L.mat_off[s + 1]; ++q)
+        {
+          const std::int32_t c = L.cols[q];
+          if (c < n_rows)
+            nb.push_back(c >> 5);
+        }
+        std::sort(nb.begin(), nb.end());
+        nb.erase(std::unique(nb.begin(), nb.end()), nb.end());
+        for (std::int32_t t : nb)
+          if (!seen[t] && ghost[t] == pass && grp.size() < static_cast<std::size_t>(group))
+          {
+            seen[t] = 1;
+            grp.push_back(t);
+          }
+      }
+      order.insert(order.end(), grp.begin(), grp.end());
+    }
+    if (pass == 0)
+      n_interior = static_cast<std::int32_t>(order.size());
+  }
+}
+
 namespace
 {
 const int tet_edges[6][2] = {{2, 3}, {1, 3}, {1, 2}, {0, 3}, {0, 2}, {0, 1}};

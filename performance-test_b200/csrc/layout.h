@@ -40,6 +40,14 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
                        const std::vector<std::uint16_t>& so, std::int64_t max_so,
                        SellLayout& L);
 
+/// Visiting order of the slices for the operator kernels. Slices without ghost columns come first
+/// (n_interior of them), so the fused halo pull overlaps with them. Inside each class the order is
+/// built from groups of `group` slices that reference each other's rows (breadth-first over the
+/// slice graph from the lowest unvisited slice): the warps of one CTA work on one group at a time,
+/// so the entries of p they gather overlap and are served by L1 instead of L2.
+void build_slice_order(const SellLayout& L, std::int32_t n_rows, int group, bool cluster,
+                       std::vector<std::int32_t>& order, std::int32_t& n_interior);
+
 /// Boundary-facet gather lists: for every owned row touched by an exterior facet, the entries
 /// (facet k, local dof li) with dofmap[cell_k][li] == row and li on the facet, ascending in k.
 /// ent holds two ints per entry: cell, local_facet*nd + li.
