@@ -280,7 +280,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       // visiting order of the operator kernels (ghost-reading slices last, clustered groups)
       std::vector<std::int32_t> inner;
       const char* env = std::getenv("PTB_SLICE_CLUSTER");
-      build_slice_order(L, N, 8, !(env && env[0] == '0'), inner, c->n_interior_slices);
+      build_slice_order(L, N, 8, env && env[0] == '1', inner, c->n_interior_slices);
       c->slice_order.upload(inner, c->stream);
     }
     c->vals.alloc(L.cols.size() * c->bs * c->bs);
@@ -480,7 +480,11 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
         ++it;
         CgState* cur = &st[it & 1];
         CgState* nxt = &st[(it + 1) & 1];
-        const bool fused = c->peer.enabled && !c->nbr_ranks.empty();
+        static const bool allow_fused = [] {
+          const char* e = std::getenv("PTB_FUSED_HALO");
+          return !(e && e[0] == '0');
+        }();
+        const bool fused = allow_fused && c->peer.enabled && !c->nbr_ranks.empty();
         if (!fused)
           halo_forward(c, c->p.p);
         const unsigned int ea = next_red_epoch(c), eb = next_red_epoch(c);

@@ -797,7 +797,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   FH.n_interior = c->n_interior_slices;
   static const bool use_tma = [] {
     const char* e = std::getenv("PTB_SPMV_TMA");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   if (c->bs == 1 && c->max_w <= 32 && use_tma)
   {
