@@ -13,6 +13,7 @@
 #include "peer.cuh"
 #include "reduce.cuh"
 #include <climits>
+#include <cmath>
 #include <cstdlib>
 #include <type_traits>
 
@@ -130,17 +131,23 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
   }
 }
 
-// Halo exchange fused into the operator (peer mode): the first FH.npull CTAs pull the ghost values
-// of p out of the neighbours' vectors over NVLink while every other warp already works on the
-// interior slices; slices that read ghost columns come last in FH.order and wait for the pull.
+// Halo exchange fused into the operator (peer mode). The CTAs split into two roles:
+//   pullers (blockIdx < npull)  publish "my p is complete", wait for the neighbours, pull the ghost
+//                               values of p straight out of the owners' vectors over NVLink, then
+//                               process ALL slices that read ghost columns (they are the only ones
+//                               that must wait for the pull);
+//   the others                  process the slices without ghost columns and never wait.
+// npull is chosen on the host in proportion to the ghost-reading share of the work, so neither
+// role is the tail of the kernel.
+constexpr int MAX_PULL = 256;
 struct FusedHalo
 {
   PeerHalo H;
   const std::int32_t* order;      // slice visiting order: interior first, ghost-reading last
   std::int32_t n_interior;        // number of leading slices of `order` without ghost columns
-  int npull;                      // CTAs that copy (<= 32)
+  int npull;                      // puller CTAs (<= MAX_PULL, < gridDim.x)
   unsigned long long epoch;       // halo epoch of this launch
-  unsigned long long* ready;      // [32] per-puller completion epochs (local memory)
+  unsigned long long* ready;      // [MAX_PULL] per-puller completion epochs (local memory)
   double* pw;                     // writable alias of p (ghost part)
 };
 
@@ -155,6 +162,60 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
   asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// The pull of one CTA's share of the receive list (generic Scatterer index lists).
+__device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHalo& FH)
+{
+  const PeerHalo& H = FH.H;
+  if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
+  {
+    __threadfence_system(); // p was completed by the previous kernel: publish "ready"
+    st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
+  }
+  if (threadIdx.x < H.n_nbr)
+  {
+    const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
+    while (ld_acquire_sys(flag) < FH.epoch)
+    {
+    }
+  }
+  __syncthreads();
+  constexpr int PULL_ILP = 4; // independent remote loads in flight per thread (NVLink ~2 us)
+  const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
+  const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
+  for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i0 < n;
+       i0 += step * PULL_ILP)
+  {
+    double val[PULL_ILP];
+    std::int64_t dst[PULL_ILP];
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
+    {
+      const std::int64_t i = i0 + u * step;
+      dst[u] = -1;
+      if (i < n)
+      {
+        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+        int nb = 0;
+        while (j >= H.recv_displ[nb + 1])
+          ++nb;
+        dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
+        val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
+      if (dst[u] >= 0)
+        FH.pw[dst[u]] = val[u];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
+  }
+}
+
 template <int BS, bool FUSED>
 __global__ void __launch_bounds__(SPMV_THREADS, 5)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
@@ -163,90 +224,39 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   __shared__ double red[32];
   if (st != nullptr && st->conv)
     return;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_cta = SPMV_THREADS / 32;
-  const std::int32_t warp0 = blockIdx.x * warps_per_cta + (threadIdx.x >> 5);
-  const std::int32_t stride = gridDim.x * warps_per_cta;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int warps_per_cta = SPMV_THREADS / 32;
+  double dotv = 0.0;
   if constexpr (FUSED)
   {
-    const PeerHalo& H = FH.H;
-    if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
-    {
-      __threadfence_system(); // p was completed by the previous kernel: publish "ready"
-      st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
-    }
     if (blockIdx.x < FH.npull)
     {
-      if (threadIdx.x < H.n_nbr)
+      halo_pull_share(P, FH);
+      // all shares must have landed before any ghost column is read
+      for (int base = 0; base < FH.npull; base += 32)
       {
-        const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
-        while (ld_acquire_sys(flag) < FH.epoch)
-        {
-        }
+        unsigned long long f;
+        do
+          f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
+        while (!__all_sync(0xffffffffu, f >= FH.epoch));
       }
-      __syncthreads();
-      // pull: PULL_ILP independent remote loads in flight per thread (NVLink latency ~2 us)
-      constexpr int PULL_ILP = 4;
-      const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
-      const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
-      for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
-           i0 < n; i0 += step * PULL_ILP)
-      {
-        double val[PULL_ILP];
-        std::int64_t dst[PULL_ILP];
-#pragma unroll
-        for (int u = 0; u < PULL_ILP; ++u)
-        {
-          const std::int64_t i = i0 + u * step;
-          dst[u] = -1;
-          if (i < n)
-          {
-            const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
-            const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
-            int nb = 0;
-            while (j >= H.recv_displ[nb + 1])
-              ++nb;
-            dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
-            val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PULL_ILP; ++u)
-          if (dst[u] >= 0)
-            FH.pw[dst[u]] = val[u];
-      }
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-        __threadfence();
-        st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
-      }
-    }
-  }
-  bool ghosts_ready = !FUSED;
-  double dotv = 0.0;
-  for (std::int32_t it = warp0; it < A.n_slices; it += stride)
-  {
-    const std::int32_t slice = FH.order[it];
-    if constexpr (FUSED)
-    {
-      if (it >= FH.n_interior)
-      {
-        if (!ghosts_ready)
-        {
-          unsigned long long f;
-          do
-            f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
-          while (!__all_sync(0xffffffffu, f >= FH.epoch));
-          ghosts_ready = true;
-        }
-        dotv += spmv_slice<BS, Ld::CG>(A, p, y, slice, lane);
-      }
-      else
-        dotv += spmv_slice<BS, Ld::NC>(A, p, y, slice, lane);
+      for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
+           it += FH.npull * warps_per_cta)
+        dotv += spmv_slice<BS, Ld::CG>(A, p, y, FH.order[it], lane);
     }
     else
-      dotv += spmv_slice<BS, Ld::NC>(A, p, y, slice, lane);
+    {
+      const std::int32_t stride = (gridDim.x - FH.npull) * warps_per_cta;
+      for (std::int32_t it = (blockIdx.x - FH.npull) * warps_per_cta + warp; it < FH.n_interior;
+           it += stride)
+        dotv += spmv_slice<BS, Ld::NC>(A, p, y, FH.order[it], lane);
+    }
+  }
+  else
+  {
+    const std::int32_t stride = gridDim.x * warps_per_cta;
+    for (std::int32_t it = blockIdx.x * warps_per_cta + warp; it < A.n_slices; it += stride)
+      dotv += spmv_slice<BS, Ld::NC>(A, p, y, FH.order[it], lane);
   }
   if (st != nullptr)
   {
@@ -308,7 +318,6 @@ __device__ __forceinline__ void mbar_wait(std::uint64_t* bar, std::uint32_t pari
   } while (!ok);
 }
 
-template <bool FUSED>
 __global__ void __launch_bounds__(TMA_THREADS, 2)
 spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
               double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH,
@@ -334,62 +343,6 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-
-  if constexpr (FUSED)
-  {
-    const PeerHalo& H = FH.H;
-    if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
-    {
-      __threadfence_system();
-      st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
-    }
-    if (blockIdx.x < FH.npull)
-    {
-      if (threadIdx.x < H.n_nbr)
-      {
-        const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
-        while (ld_acquire_sys(flag) < FH.epoch)
-        {
-        }
-      }
-      __syncthreads();
-      constexpr int PULL_ILP = 4;
-      const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
-      const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
-      for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
-           i0 < n; i0 += step * PULL_ILP)
-      {
-        double val[PULL_ILP];
-        std::int64_t dst[PULL_ILP];
-#pragma unroll
-        for (int u = 0; u < PULL_ILP; ++u)
-        {
-          const std::int64_t i = i0 + u * step;
-          dst[u] = -1;
-          if (i < n)
-          {
-            const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
-            const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
-            int nb = 0;
-            while (j >= H.recv_displ[nb + 1])
-              ++nb;
-            dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
-            val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
-          }
-        }
-#pragma unroll
-        for (int u = 0; u < PULL_ILP; ++u)
-          if (dst[u] >= 0)
-            FH.pw[dst[u]] = val[u];
-      }
-      __syncthreads();
-      if (threadIdx.x == 0)
-      {
-        __threadfence();
-        st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
-      }
-    }
-  }
 
   // slices of this warp: it = warp0 + j*stride, j = 0 .. n_my-1
   const std::int32_t n_my = warp0 < A.n_slices ? (A.n_slices - warp0 + stride - 1) / stride : 0;
@@ -428,8 +381,6 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
       const std::int64_t mo = A.mat_off[m.slice];
       m.w = static_cast<int>((A.mat_off[m.slice + 1] - mo) >> 5); // <= 32 by construction
       m.dl = lane < m.w ? __ldg(A.cdelta + (mo >> 5) + lane) : 0;
-      if constexpr (FUSED)
-        m.ghost = warp0 + j * stride >= FH.n_interior;
     }
     return m;
   };
@@ -448,7 +399,6 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     }
   };
 
-  bool ghosts_ready = !FUSED;
   double dotv = 0.0;
   // Ring of 4 slice descriptors and 2 gather buffers, indexed statically (the loop is unrolled by
   // 4): a register that a load is still filling is never moved, so nothing stalls on a copy.
@@ -493,17 +443,6 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     }
     else
     {
-      if constexpr (FUSED)
-      {
-        if (cur.ghost && !ghosts_ready)
-        {
-          unsigned long long f;
-          do
-            f = lane < FH.npull ? ld_acquire_gpu(&FH.ready[lane]) : ~0ull;
-          while (!__all_sync(0xffffffffu, f >= FH.epoch));
-          ghosts_ready = true;
-        }
-      }
       const unsigned int em = __ballot_sync(0xffffffffu, lane < w && cur.dl == INT32_MIN);
       const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
       mbar_wait(bar, parity);
@@ -776,14 +715,30 @@ int resident_grid(const ptb_ctx* c, K kernel, int threads, std::int64_t need)
 }
 
 template <typename K>
-int vec_grid(const ptb_ctx* c, K kernel, std::int64_t n)
+int vec_grid(ptb_ctx* c, K kernel, std::int64_t n, int slot)
 {
-  return resident_grid(c, kernel, VEC_THREADS, (n / 2 + VEC_THREADS - 1) / VEC_THREADS);
+  const std::int64_t need = (n / 2 + VEC_THREADS - 1) / VEC_THREADS;
+  if (c->grid_cache[slot] == 0)
+    c->grid_cache[slot] = resident_grid(c, kernel, VEC_THREADS, INT32_MAX);
+  return static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
 }
 
 } // namespace
 
 int cg_grid(const ptb_ctx* c) { return c->num_sms * 8; }
+
+// One-wave grid of a kernel, cached per context (the occupancy query is a host API call).
+template <typename K>
+int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, std::int64_t need)
+{
+  if (c->grid_cache[slot] == 0)
+  {
+    int per_sm = 0;
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
+  }
+  return static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
+}
 
 void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
                  bool fused_halo)
@@ -799,70 +754,54 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
     const char* e = std::getenv("PTB_SPMV_TMA");
     return e && e[0] == '1';
   }();
-  if (c->bs == 1 && c->max_w <= 32 && use_tma)
-  {
-    // TMA-staged scalar kernel
-    if (fused_halo)
-    {
-      if (!c->peer.enabled || p != c->p.p)
-        throw std::runtime_error("fused halo: peer mode and the search direction vector only");
-      FH.H = peer_halo(c);
-      FH.order = c->slice_order.p;
-      FH.n_interior = c->n_interior_slices;
-      FH.epoch = ++c->peer.halo_epoch;
-      FH.ready = c->peer.ready.p;
-      FH.pw = c->p.p;
-    }
-    const int stage_doubles = std::max(1, c->max_w) * 32;
-    const std::size_t smem = static_cast<std::size_t>(TMA_THREADS / 32) * TMA_STAGES
-                             * (stage_doubles * sizeof(double) + sizeof(std::uint64_t));
-    auto launch = [&](auto kernel) {
-      PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    static_cast<int>(smem)));
-      int per_sm = 0;
-      PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TMA_THREADS, smem));
-      const std::int64_t cap = static_cast<std::int64_t>(c->num_sms) * std::max(1, std::min(per_sm, 8));
-      const int grid = static_cast<int>(std::max<std::int64_t>(1, std::min(need, cap)));
-      FH.npull = std::min(32, grid);
-      kernel<<<grid, TMA_THREADS, smem, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
-                                                     epoch, FH, stage_doubles);
-    };
-    if (fused_halo)
-      launch(spmv_sell_tma<true>);
-    else
-      launch(spmv_sell_tma<false>);
-  }
-  else if (fused_halo)
+  if (fused_halo)
   {
     if (!c->peer.enabled || p != c->p.p)
       throw std::runtime_error("fused halo: peer mode and the search direction vector only");
     FH.H = peer_halo(c);
-    FH.order = c->slice_order.p;
-    FH.n_interior = c->n_interior_slices;
     FH.epoch = ++c->peer.halo_epoch;
     FH.ready = c->peer.ready.p;
     FH.pw = c->p.p;
+    const int grid = c->bs == 1
+                         ? cached_grid(c, 0, spmv_sell<1, true>, SPMV_THREADS, 0, need)
+                         : cached_grid(c, 1, spmv_sell<3, true>, SPMV_THREADS, 0, need);
+    // pullers get the ghost-reading slices: size their number to that share of the work (+25 %
+    // for the pull itself), at least 8 so the remote loads have enough parallelism
+    const double share = c->n_slices > 0
+                             ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
+                             : 0.0;
+    int npull = static_cast<int>(std::ceil(1.25 * share * grid)) + 4;
+    npull = std::max(8, std::min(std::min(npull, MAX_PULL), grid / 2));
+    FH.npull = std::max(1, npull);
+    if (grid < 2) // degenerate: one CTA does everything in order
+      throw std::runtime_error("fused halo: grid too small");
     if (c->bs == 1)
-    {
-      const int grid = resident_grid(c, spmv_sell<1, true>, SPMV_THREADS, need);
-      FH.npull = std::min(32, grid);
       spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                c->tickets.p, P, epoch, FH);
-    }
     else
-    {
-      const int grid = resident_grid(c, spmv_sell<3, true>, SPMV_THREADS, need);
-      FH.npull = std::min(32, grid);
       spmv_sell<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                c->tickets.p, P, epoch, FH);
-    }
+  }
+  else if (c->bs == 1 && c->max_w <= 32 && use_tma)
+  {
+    // opt-in TMA-staged scalar kernel (profiles/r01_spmv_ab_*.txt: measured slower than registers)
+    const int stage_doubles = std::max(1, c->max_w) * 32;
+    const std::size_t smem = static_cast<std::size_t>(TMA_THREADS / 32) * TMA_STAGES
+                             * (stage_doubles * sizeof(double) + sizeof(std::uint64_t));
+    PTB_CUDA(cudaFuncSetAttribute(spmv_sell_tma, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    const int grid = cached_grid(c, 2, spmv_sell_tma, TMA_THREADS, smem, need);
+    spmv_sell_tma<<<grid, TMA_THREADS, smem, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p,
+                                                          P, epoch, FH, stage_doubles);
   }
   else if (c->bs == 1)
-    spmv_sell<1, false><<<resident_grid(c, spmv_sell<1, false>, SPMV_THREADS, need), SPMV_THREADS,
-                          0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
+    spmv_sell<1, false><<<cached_grid(c, 3, spmv_sell<1, false>, SPMV_THREADS, 0, need),
+                          SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
+                                                        epoch, FH);
   else
-    spmv_sell<3, false><<<resident_grid(c, spmv_sell<3, false>, SPMV_THREADS, need), SPMV_THREADS,
-                          0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
+    spmv_sell<3, false><<<cached_grid(c, 4, spmv_sell<3, false>, SPMV_THREADS, 0, need),
+                          SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
+                                                        epoch, FH);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -870,7 +809,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
 void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_init<<<vec_grid(c, cg_init, 2 * n), VEC_THREADS, 0, c->stream>>>(n, c->b.p, c->y.p, dinv, c->r.p, c->p.p,
+  cg_init<<<vec_grid(c, cg_init, 2 * n, 5), VEC_THREADS, 0, c->stream>>>(n, c->b.p, c->y.p, dinv, c->r.p, c->p.p,
                                                          st, c->partials.p, c->tickets.p + 1,
                                                          peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
@@ -888,7 +827,7 @@ void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int
                       unsigned int epoch_out)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_update<<<vec_grid(c, cg_update, n), VEC_THREADS, 0, c->stream>>>(n, c->y.p, dinv, c->r.p, cur,
+  cg_update<<<vec_grid(c, cg_update, n, 6), VEC_THREADS, 0, c->stream>>>(n, c->y.p, dinv, c->r.p, cur,
                                                            c->partials.p, c->tickets.p + 1,
                                                            peer_view(c), epoch_in, epoch_out);
   PTB_CUDA(cudaGetLastError());
@@ -899,7 +838,7 @@ void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgS
                          unsigned int epoch)
 {
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
-  cg_direction<<<vec_grid(c, cg_direction, n), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
+  cg_direction<<<vec_grid(c, cg_direction, n, 7), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
                                                               nxt, peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
@@ -909,7 +848,7 @@ void launch_fill(ptb_ctx* c, double* v, std::int64_t n, double value)
 {
   if (n == 0)
     return;
-  fill_kernel<<<vec_grid(c, fill_kernel, 2 * n), VEC_THREADS, 0, c->stream>>>(v, n, value);
+  fill_kernel<<<vec_grid(c, fill_kernel, 2 * n, 8), VEC_THREADS, 0, c->stream>>>(v, n, value);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -936,7 +875,7 @@ void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::i
 
 void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev)
 {
-  sqnorm_kernel<<<vec_grid(c, sqnorm_kernel, 2 * n), VEC_THREADS, 0, c->stream>>>(n, v, out_dev, c->partials.p,
+  sqnorm_kernel<<<vec_grid(c, sqnorm_kernel, 2 * n, 9), VEC_THREADS, 0, c->stream>>>(n, v, out_dev, c->partials.p,
                                                                c->tickets.p + 2, peer_view(c),
                                                                next_red_epoch(c));
   PTB_CUDA(cudaGetLastError());

@@ -98,6 +98,7 @@ struct ptb_ctx
   std::string err;
   double stage_ms[PTB_STAGE_COUNT] = {0, 0, 0, 0};
   std::int64_t launches = 0;
+  int grid_cache[16] = {}; // one-wave grid sizes per kernel (0 = not queried yet)
   int num_sms = 148;
 
   // problem description
@@ -169,7 +170,7 @@ struct ptb_ctx
     void* nbr_x[8] = {};                  // neighbours' x and p vectors
     void* nbr_p[8] = {};
     ptb::DevBuf<std::int32_t> src_index;  // owner-local index per receive entry
-    ptb::DevBuf<unsigned long long> ready; // [32] completion epochs of the fused halo pull
+    ptb::DevBuf<unsigned long long> ready; // [256] completion epochs of the fused halo pullers
     std::vector<void*> opened;            // IPC mappings to close
     unsigned long long halo_epoch = 0;
     unsigned int red_epoch = 0;

@@ -143,7 +143,7 @@ void peer_connect(ptb_ctx* c, int rank, int nranks, const void* all_handles,
   if (n_recv > 0 && !src_index)
     throw std::runtime_error("ptb_peer_connect: src_index is NULL");
   c->peer.src_index.upload(src_index, n_recv, c->stream);
-  c->peer.ready.alloc(32);
+  c->peer.ready.alloc(256);
   c->peer.ready.zero(c->stream);
   PTB_CUDA(cudaStreamSynchronize(c->stream));
   c->peer.enabled = nranks > 1;
