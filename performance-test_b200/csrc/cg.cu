@@ -9,6 +9,7 @@
 // the kernel that writes the next iteration's record never races with readers of the current one.
 // Dot products use the deterministic last-block reduction of reduce.cuh (la::inner_product /
 // squared_norm sum owned entries only: cg.h:53,65,74).
+#include "comm.h"
 #include "kernels.h"
 #include "peer.cuh"
 #include "reduce.cuh"
@@ -754,27 +755,35 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
     const char* e = std::getenv("PTB_SPMV_TMA");
     return e && e[0] == '1';
   }();
+  int fused_grid = 0;
   if (fused_halo)
   {
     if (!c->peer.enabled || p != c->p.p)
       throw std::runtime_error("fused halo: peer mode and the search direction vector only");
+    fused_grid = c->bs == 1 ? cached_grid(c, 0, spmv_sell<1, true>, SPMV_THREADS, 0, need)
+                            : cached_grid(c, 1, spmv_sell<3, true>, SPMV_THREADS, 0, need);
+    if (fused_grid < 4)
+    {
+      // too little work to split into roles: separate pull kernel, then the plain operator
+      halo_forward(c, c->p.p);
+      fused_halo = false;
+    }
+  }
+  if (fused_halo)
+  {
+    const int grid = fused_grid;
     FH.H = peer_halo(c);
     FH.epoch = ++c->peer.halo_epoch;
     FH.ready = c->peer.ready.p;
     FH.pw = c->p.p;
-    const int grid = c->bs == 1
-                         ? cached_grid(c, 0, spmv_sell<1, true>, SPMV_THREADS, 0, need)
-                         : cached_grid(c, 1, spmv_sell<3, true>, SPMV_THREADS, 0, need);
     // pullers get the ghost-reading slices: size their number to that share of the work (+25 %
-    // for the pull itself), at least 8 so the remote loads have enough parallelism
+    // for the pull itself), at least 8 when the grid allows so the remote loads have parallelism
     const double share = c->n_slices > 0
                              ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
                              : 0.0;
-    int npull = static_cast<int>(std::ceil(1.25 * share * grid)) + 4;
-    npull = std::max(8, std::min(std::min(npull, MAX_PULL), grid / 2));
-    FH.npull = std::max(1, npull);
-    if (grid < 2) // degenerate: one CTA does everything in order
-      throw std::runtime_error("fused halo: grid too small");
+    int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
+    npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
+    FH.npull = npull;
     if (c->bs == 1)
       spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                c->tickets.p, P, epoch, FH);

@@ -82,7 +82,8 @@ def _worker(rank, world, port, ptype, dims, comm, out):
 
 
 @pytest.mark.parametrize("comm", ["nccl", "peer"])
-@pytest.mark.parametrize("ptype,dims", [("poisson", (12, 11, 14)), ("elasticity", (7, 8, 9))])
+@pytest.mark.parametrize("ptype,dims", [("poisson", (12, 11, 14)), ("elasticity", (7, 8, 9)),
+                                        ("poisson", (24, 23, 30))])
 def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims, comm):
     import torch
     if torch.cuda.device_count() < 2:
@@ -96,10 +97,15 @@ def test_two_rank_solve_matches_oracle(pt, oracle, ptype, dims, comm):
              for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted([out.get(timeout=600) for _ in range(world)], key=lambda t: t[0])
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = sorted([out.get(timeout=150) for _ in range(world)], key=lambda t: t[0])
+        for p in procs:
+            p.join(timeout=60)
+            assert p.exitcode == 0
+    finally:
+        for p in procs:  # never leave a spinning rank behind (a hung peer kernel would block the box)
+            if p.is_alive():
+                p.kill()
     S = pt.host.Problem(ptype, 1, *dims)
     bs = S.bs
     A_s, b_s = oracle.assemble_matrix(S), oracle.assemble_vector(S)
