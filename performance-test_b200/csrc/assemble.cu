@@ -108,42 +108,41 @@ __device__ __forceinline__ SliceView slice_view(const Args& A, std::int32_t slic
   return S;
 }
 
-// Stage the star of the slice: columns k = a, a + STRIDE, ... are handled by this warp (STRIDE
-// warps share a slice); NF source-term components per dof when WITH_F.
-template <int STRIDE, int NF, bool WITH_F, int CH = LD_CHUNK>
+// Stage the star of the slice: columns k = a, a + BS, ... are handled by this warp.
+template <int BS, bool WITH_F>
 __device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
                                            const std::int32_t* __restrict__ cols,
                                            const double* __restrict__ xdof, Vec3 X0, double* E,
                                            std::int32_t* C, const double* __restrict__ f, double* F)
 {
-  for (int k0 = a; k0 < S.w; k0 += STRIDE * CH)
+  for (int k0 = a; k0 < S.w; k0 += BS * LD_CHUNK)
   {
-    std::int32_t c[CH];
+    std::int32_t c[LD_CHUNK];
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
+    for (int j = 0; j < LD_CHUNK; ++j)
     {
-      const int k = k0 + STRIDE * j;
+      const int k = k0 + BS * j;
       c[j] = k < S.w ? __ldg(cols + S.mo + k * 32 + lane) : -1;
     }
-    Vec3 e[CH];
-    double fv[CH][WITH_F ? NF : 1];
+    Vec3 e[LD_CHUNK];
+    double fv[LD_CHUNK][WITH_F ? BS : 1];
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
+    for (int j = 0; j < LD_CHUNK; ++j)
       if (c[j] >= 0)
       {
         e[j] = load_point(xdof, c[j]);
         if constexpr (WITH_F)
         {
 #pragma unroll
-          for (int b = 0; b < NF; ++b)
-            fv[j][b] = __ldg(f + static_cast<std::int64_t>(c[j]) * NF + b);
+          for (int b = 0; b < BS; ++b)
+            fv[j][b] = __ldg(f + static_cast<std::int64_t>(c[j]) * BS + b);
         }
       }
 #pragma unroll
-    for (int j = 0; j < CH; ++j)
+    for (int j = 0; j < LD_CHUNK; ++j)
       if (c[j] >= 0)
       {
-        const int k = k0 + STRIDE * j;
+        const int k = k0 + BS * j;
         const Vec3 d = e[j] - X0;
         E[(k * 3 + 0) * 32 + lane] = d.x;
         E[(k * 3 + 1) * 32 + lane] = d.y;
@@ -153,8 +152,8 @@ __device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
         if constexpr (WITH_F)
         {
 #pragma unroll
-          for (int b = 0; b < NF; ++b)
-            F[(k * NF + b) * 32 + lane] = fv[j][b];
+          for (int b = 0; b < BS; ++b)
+            F[(k * BS + b) * 32 + lane] = fv[j][b];
         }
       }
   }
@@ -180,7 +179,7 @@ assemble_matrix_p1(MatrixArgs A)
 
   // ---- prologue: stage the star (the BS warps of a slice split the columns) -----------------
   const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  stage_star<BS, BS, false>(S, a, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr);
+  stage_star<BS, false>(S, a, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr);
   for (int k = 0; k < S.w * BS; ++k)
     acc[k * 32 + lane] = 0.0;
   if constexpr (BS == 1)
@@ -321,7 +320,7 @@ assemble_vector_p1(VectorArgs A)
   double* F = E + A.max_w * 3 * 32;
 
   const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  stage_star<BS, BS, true>(S, a, lane, A.cols, A.xdof, X0, E, nullptr, A.f, F);
+  stage_star<BS, true>(S, a, lane, A.cols, A.xdof, X0, E, nullptr, A.f, F);
   if constexpr (BS == 1)
     __syncwarp();
   else
@@ -352,147 +351,6 @@ assemble_vector_p1(VectorArgs A)
   }
   if (S.live)
     A.b[static_cast<std::int64_t>(row) * BS + a] = A.bc[row] ? 0.0 : sum;
-}
-
-// ------------------------------------------------------------------------------------------
-// Poisson P1, cell-split variants: the SPLIT warps of a slice share the staged star and each
-// takes every SPLIT-th cell of the rows' cell lists into its own accumulators; the partial sums
-// are added in warp order in the epilogue (fixed order: still bit-reproducible and independent
-// of the partition). The shared-memory footprint per thread drops from 4w to (3 + SPLIT)w/SPLIT
-// doubles, which raises the resident warps per SM from 12 to 32.
-// ------------------------------------------------------------------------------------------
-constexpr int SPLIT = 4;
-constexpr int SPLIT_THREADS = 256; // 2 slices x 4 warps
-constexpr int SPLIT_CHUNK = 3;     // cells per warp per row ~ 24 / SPLIT = 6 = 2 chunks
-
-__global__ void __launch_bounds__(SPLIT_THREADS, 4)
-assemble_matrix_p1_split(MatrixArgs A)
-{
-  extern __shared__ double smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sl = warp / SPLIT, t = warp % SPLIT;
-  const SliceView S = slice_view(A, blockIdx.x * (SPLIT_THREADS / 32 / SPLIT) + sl, lane);
-  const std::int32_t row = S.row;
-
-  // per slice: E (3w) + acc (SPLIT*w) + dg (SPLIT) doubles + C (w int32)
-  const int per_slice = A.max_w * (3 + SPLIT) * 32 + SPLIT * 32 + (A.max_w * 32 + 1) / 2;
-  double* E = smem + sl * per_slice;
-  double* acc0 = E + A.max_w * 3 * 32;
-  double* acc = acc0 + t * (A.max_w * 32);
-  double* dgs = acc0 + SPLIT * A.max_w * 32;
-  std::int32_t* C = reinterpret_cast<std::int32_t*>(dgs + SPLIT * 32);
-
-  const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  stage_star<SPLIT, 1, false, 4>(S, t, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr);
-  for (int k = 0; k < S.w; ++k)
-    acc[k * 32 + lane] = 0.0;
-  __syncthreads();
-
-  double dg = 0.0;
-  for (int k0 = t; k0 < S.wa; k0 += SPLIT * SPLIT_CHUNK)
-  {
-    std::uint32_t wd[SPLIT_CHUNK];
-#pragma unroll
-    for (int j = 0; j < SPLIT_CHUNK; ++j)
-    {
-      const int k = k0 + SPLIT * j;
-      wd[j] = k < S.wa ? __ldg(A.adjrot + S.ao + k * 32 + lane) : ADJ_INVALID_DEV;
-    }
-#pragma unroll
-    for (int j = 0; j < SPLIT_CHUNK; ++j)
-    {
-      const std::uint32_t word = wd[j];
-      if (word == ADJ_INVALID_DEV)
-        continue;
-      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-      const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
-                                   star_edge(E, o3, lane));
-      const double s = __drcp_rn(6.0 * fabs(G.det));
-      dg += s * dot(G.c0, G.c0);
-      acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
-      acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
-      acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
-    }
-  }
-  dgs[t * 32 + lane] = dg;
-  __syncthreads();
-
-  // epilogue: warp t finishes the columns k = t, t + SPLIT, ...
-  const std::int64_t len = S.live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
-  const bool bc_row = S.live && A.bc[row];
-  for (int k = t; k < S.w; k += SPLIT)
-  {
-    const std::int32_t col = C[k * 32 + lane];
-    const bool real = k < len;
-    const bool own = real && col == row;
-    const bool bc_any = bc_row || (real && A.bc[col] != 0);
-    double val;
-    if (own)
-      val = ((dgs[lane] + dgs[32 + lane]) + dgs[64 + lane]) + dgs[96 + lane];
-    else
-      val = ((acc0[k * 32 + lane] + acc0[(A.max_w + k) * 32 + lane])
-             + acc0[(2 * A.max_w + k) * 32 + lane])
-            + acc0[(3 * A.max_w + k) * 32 + lane];
-    if (bc_any)
-      val = own ? 1.0 : 0.0;
-    if (!real)
-      val = 0.0;
-    A.vals[S.mo + k * 32 + lane] = val;
-    if (own)
-      A.dinv[row] = 1.0 / val;
-  }
-}
-
-__global__ void __launch_bounds__(SPLIT_THREADS, 4)
-assemble_vector_p1_split(VectorArgs A)
-{
-  extern __shared__ double smem[];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int sl = warp / SPLIT, t = warp % SPLIT;
-  const SliceView S = slice_view(A, blockIdx.x * (SPLIT_THREADS / 32 / SPLIT) + sl, lane);
-  const std::int32_t row = S.row;
-
-  const int per_slice = A.max_w * 4 * 32 + SPLIT * 32; // E (3w) + F (w) + partial sums
-  double* E = smem + sl * per_slice;
-  double* F = E + A.max_w * 3 * 32;
-  double* part = F + A.max_w * 32;
-
-  const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  stage_star<SPLIT, 1, true, 4>(S, t, lane, A.cols, A.xdof, X0, E, nullptr, A.f, F);
-  __syncthreads();
-
-  const double f0 = S.live ? __ldg(A.f + row) : 0.0;
-  double sum = 0.0;
-  for (int k0 = t; k0 < S.wa; k0 += SPLIT * SPLIT_CHUNK)
-  {
-    std::uint32_t wd[SPLIT_CHUNK];
-#pragma unroll
-    for (int j = 0; j < SPLIT_CHUNK; ++j)
-    {
-      const int k = k0 + SPLIT * j;
-      wd[j] = k < S.wa ? __ldg(A.adjrot + S.ao + k * 32 + lane) : ADJ_INVALID_DEV;
-    }
-#pragma unroll
-    for (int j = 0; j < SPLIT_CHUNK; ++j)
-    {
-      const std::uint32_t word = wd[j];
-      if (word == ADJ_INVALID_DEV)
-        continue;
-      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-      const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane),
-                 e3 = star_edge(E, o3, lane);
-      const double det = dot(e1, cross(e2, e3));
-      const double f1 = F[o1 * 32 + lane], f2 = F[o2 * 32 + lane], f3 = F[o3 * 32 + lane];
-      sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
-    }
-  }
-  part[t * 32 + lane] = sum;
-  __syncthreads();
-  if (t == 0 && S.live)
-  {
-    const double tot = ((part[lane] + part[32 + lane]) + part[64 + lane]) + part[96 + lane];
-    A.b[row] = A.bc[row] ? 0.0 : tot;
-  }
 }
 
 // Exterior facets, P1 (Poisson.py:32 g*v*ds): thread = boundary row; facet mass = area/12 (1+delta).
@@ -600,13 +458,10 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
     throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
   if (c->bs == 1)
   {
-    const int spc = SPLIT_THREADS / 32 / SPLIT;
-    const std::size_t smem
-        = (static_cast<std::size_t>(c->max_w) * (3 + SPLIT) * 32 + SPLIT * 32
-           + (static_cast<std::size_t>(c->max_w) * 32 + 1) / 2)
-          * spc * sizeof(double);
-    set_smem(assemble_matrix_p1_split, smem);
-    assemble_matrix_p1_split<<<(A.n_slices + spc - 1) / spc, SPLIT_THREADS, smem, c->stream>>>(A);
+    const int spc = MAT_THREADS_1 / 32;
+    const std::size_t smem = mat_smem_doubles(c->max_w, 1) * spc * sizeof(double);
+    set_smem(assemble_matrix_p1<1>, smem);
+    assemble_matrix_p1<1><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_1, smem, c->stream>>>(A);
   }
   else
   {
@@ -627,11 +482,10 @@ void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
     throw std::runtime_error("assemble_vector: a P1 row has more than 254 columns");
   if (c->bs == 1)
   {
-    const int spc = SPLIT_THREADS / 32 / SPLIT;
-    const std::size_t smem
-        = (static_cast<std::size_t>(c->max_w) * 4 * 32 + SPLIT * 32) * spc * sizeof(double);
-    set_smem(assemble_vector_p1_split, smem);
-    assemble_vector_p1_split<<<(A.n_slices + spc - 1) / spc, SPLIT_THREADS, smem, c->stream>>>(A);
+    const int spc = MAT_THREADS_1 / 32;
+    const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);
+    set_smem(assemble_vector_p1<1>, smem);
+    assemble_vector_p1<1><<<(A.n_slices + spc - 1) / spc, MAT_THREADS_1, smem, c->stream>>>(A);
   }
   else
   {
