@@ -18,6 +18,7 @@
 // every warp access is a full 128/256-byte line; the cell loop touches global memory once per
 // cell (4 bytes per thread).
 #include "kernels.h"
+#include <climits>
 
 namespace ptb
 {
@@ -113,7 +114,8 @@ template <int BS, bool WITH_F>
 __device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
                                            const std::int32_t* __restrict__ cols,
                                            const double* __restrict__ xdof, Vec3 X0, double* E,
-                                           std::int32_t* C, const double* __restrict__ f, double* F)
+                                           std::int32_t* C, const double* __restrict__ f, double* F,
+                                           const std::uint8_t* __restrict__ bc = nullptr)
 {
   for (int k0 = a; k0 < S.w; k0 += BS * LD_CHUNK)
   {
@@ -126,11 +128,13 @@ __device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
     }
     Vec3 e[LD_CHUNK];
     double fv[LD_CHUNK][WITH_F ? BS : 1];
+    std::uint8_t bcv[LD_CHUNK];
 #pragma unroll
     for (int j = 0; j < LD_CHUNK; ++j)
       if (c[j] >= 0)
       {
         e[j] = load_point(xdof, c[j]);
+        bcv[j] = bc != nullptr ? __ldg(bc + c[j]) : 0;
         if constexpr (WITH_F)
         {
 #pragma unroll
@@ -147,8 +151,8 @@ __device__ __forceinline__ void stage_star(const SliceView& S, int a, int lane,
         E[(k * 3 + 0) * 32 + lane] = d.x;
         E[(k * 3 + 1) * 32 + lane] = d.y;
         E[(k * 3 + 2) * 32 + lane] = d.z;
-        if (C != nullptr)
-          C[k * 32 + lane] = c[j];
+        if (C != nullptr) // column index, Dirichlet flag of the column in the top bit
+          C[k * 32 + lane] = c[j] | (bcv[j] ? INT32_MIN : 0);
         if constexpr (WITH_F)
         {
 #pragma unroll
@@ -177,9 +181,17 @@ assemble_matrix_p1(MatrixArgs A)
   double* acc = E + A.max_w * 3 * 32 + a * (A.max_w * BS * 32);
   std::int32_t* C = reinterpret_cast<std::int32_t*>(E + A.max_w * (3 + BS * BS) * 32);
 
-  // ---- prologue: stage the star (the BS warps of a slice split the columns) -----------------
+  // ---- every global load of the row is issued up front: the cell words (first W0 cells), the
+  // row length and BC flag, then the star staging; nothing later in the kernel waits on DRAM ----
+  constexpr int W0 = 24;
+  std::uint32_t wd0[W0];
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    wd0[j] = j < S.wa ? __ldg(A.adjrot + S.ao + j * 32 + lane) : ADJ_INVALID_DEV;
+  const std::int64_t len = S.live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
+  const bool bc_row = S.live && A.bc[row];
   const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  stage_star<BS, false>(S, a, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr);
+  stage_star<BS, false>(S, a, lane, A.cols, A.xdof, X0, E, C, nullptr, nullptr, A.bc);
   for (int k = 0; k < S.w * BS; ++k)
     acc[k * 32 + lane] = 0.0;
   if constexpr (BS == 1)
@@ -192,7 +204,49 @@ assemble_matrix_p1(MatrixArgs A)
 
   // ---- cell loop --------------------------------------------------------------------------
   double dg0 = 0.0, dg1 = 0.0, dg2 = 0.0; // owner's own (diagonal) block row, kept in registers
-  for (int k0 = 0; k0 < S.wa; k0 += LD_CHUNK)
+  auto cell = [&](std::uint32_t word) {
+    if (word == ADJ_INVALID_DEV)
+      return;
+    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+    const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
+                                 star_edge(E, o3, lane));
+    const double s = __drcp_rn(6.0 * fabs(G.det));
+    if constexpr (BS == 1)
+    {
+      dg0 += s * dot(G.c0, G.c0);
+      acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
+      acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
+      acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
+    }
+    else
+    {
+      // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
+      const double c0a = comp(G.c0, a);
+      const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
+      const int ot[4] = {0, o1, o2, o3};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+      {
+        const double d = dot(G.c0, ct[t]);
+        const double cta = comp(ct[t], a);
+        const double v0 = s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x);
+        const double v1 = s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y);
+        const double v2 = s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z);
+        if (t == 0)
+          dg0 += v0, dg1 += v1, dg2 += v2;
+        else
+        {
+          acc[(ot[t] * 3 + 0) * 32 + lane] += v0;
+          acc[(ot[t] * 3 + 1) * 32 + lane] += v1;
+          acc[(ot[t] * 3 + 2) * 32 + lane] += v2;
+        }
+      }
+    }
+  };
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    cell(wd0[j]);
+  for (int k0 = W0; k0 < S.wa; k0 += LD_CHUNK) // rows with more than W0 cells (unstructured meshes)
   {
     std::uint32_t wd[LD_CHUNK];
 #pragma unroll
@@ -200,72 +254,19 @@ assemble_matrix_p1(MatrixArgs A)
       wd[j] = k0 + j < S.wa ? __ldg(A.adjrot + S.ao + (k0 + j) * 32 + lane) : ADJ_INVALID_DEV;
 #pragma unroll
     for (int j = 0; j < LD_CHUNK; ++j)
-    {
-      const std::uint32_t word = wd[j];
-      if (word == ADJ_INVALID_DEV)
-        continue;
-      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-      const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
-                                   star_edge(E, o3, lane));
-      const double s = __drcp_rn(6.0 * fabs(G.det));
-      if constexpr (BS == 1)
-      {
-        dg0 += s * dot(G.c0, G.c0);
-        acc[o1 * 32 + lane] += s * dot(G.c0, G.c1);
-        acc[o2 * 32 + lane] += s * dot(G.c0, G.c2);
-        acc[o3 * 32 + lane] += s * dot(G.c0, G.c3);
-      }
-      else
-      {
-        // Ae[(0,a),(t,b)] = s [ mu (delta_ab c0.ct + c0[b] ct[a]) + lambda c0[a] ct[b] ]
-        const double c0a = comp(G.c0, a);
-        const Vec3 ct[4] = {G.c0, G.c1, G.c2, G.c3};
-        const int ot[4] = {0, o1, o2, o3};
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-        {
-          const double d = dot(G.c0, ct[t]);
-          const double cta = comp(ct[t], a);
-          const double v0 = s * (mu * ((a == 0 ? d : 0.0) + G.c0.x * cta) + lmbda * c0a * ct[t].x);
-          const double v1 = s * (mu * ((a == 1 ? d : 0.0) + G.c0.y * cta) + lmbda * c0a * ct[t].y);
-          const double v2 = s * (mu * ((a == 2 ? d : 0.0) + G.c0.z * cta) + lmbda * c0a * ct[t].z);
-          if (t == 0)
-            dg0 += v0, dg1 += v1, dg2 += v2;
-          else
-          {
-            acc[(ot[t] * 3 + 0) * 32 + lane] += v0;
-            acc[(ot[t] * 3 + 1) * 32 + lane] += v1;
-            acc[(ot[t] * 3 + 2) * 32 + lane] += v2;
-          }
-        }
-      }
-    }
+      cell(wd[j]);
   }
 
   // ---- epilogue: BC rows/cols -> 0, BC diagonal -> 1, write values once, coalesced ----------
-  const std::int64_t len = S.live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
-  const bool bc_row = S.live && A.bc[row];
   double diag = 1.0;
-  for (int k0 = 0; k0 < S.w; k0 += LD_CHUNK)
   {
-    std::int32_t col[LD_CHUNK];
-    bool bcc[LD_CHUNK];
-#pragma unroll
-    for (int j = 0; j < LD_CHUNK; ++j)
+    for (int k = 0; k < S.w; ++k)
     {
-      const int k = k0 + j;
-      col[j] = k < S.w ? C[k * 32 + lane] : 0;
-      bcc[j] = k < len ? A.bc[col[j]] != 0 : false;
-    }
-#pragma unroll
-    for (int j = 0; j < LD_CHUNK; ++j)
-    {
-      const int k = k0 + j;
-      if (k >= S.w)
-        break;
+      const std::int32_t cw = C[k * 32 + lane];
+      const std::int32_t colk = cw & INT32_MAX;
       const bool real = k < len;
-      const bool own = real && col[j] == row;
-      const bool bc_any = bc_row || bcc[j];
+      const bool own = real && colk == row;
+      const bool bc_any = bc_row || (real && cw < 0);
       if constexpr (BS == 1)
       {
         double val = own ? dg0 : acc[k * 32 + lane];
@@ -319,6 +320,13 @@ assemble_vector_p1(VectorArgs A)
   double* E = smem + sl * per_slice;
   double* F = E + A.max_w * 3 * 32;
 
+  constexpr int W0 = 24; // all cell words of the row are requested before the star is staged
+  std::uint32_t wd0[W0];
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    wd0[j] = j < S.wa ? __ldg(A.adjrot + S.ao + j * 32 + lane) : ADJ_INVALID_DEV;
+  const bool bc_row = S.live && A.bc[row];
+  const double f0 = S.live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
   const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
   stage_star<BS, true>(S, a, lane, A.cols, A.xdof, X0, E, nullptr, A.f, F);
   if constexpr (BS == 1)
@@ -326,9 +334,21 @@ assemble_vector_p1(VectorArgs A)
   else
     __syncthreads();
 
-  const double f0 = S.live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
   double sum = 0.0;
-  for (int k0 = 0; k0 < S.wa; k0 += LD_CHUNK)
+  auto cell = [&](std::uint32_t word) {
+    if (word == ADJ_INVALID_DEV)
+      return;
+    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+    const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane), e3 = star_edge(E, o3, lane);
+    const double det = dot(e1, cross(e2, e3));
+    const double f1 = F[(o1 * BS + a) * 32 + lane], f2 = F[(o2 * BS + a) * 32 + lane],
+                 f3 = F[(o3 * BS + a) * 32 + lane];
+    sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
+  };
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    cell(wd0[j]);
+  for (int k0 = W0; k0 < S.wa; k0 += LD_CHUNK)
   {
     std::uint32_t wd[LD_CHUNK];
 #pragma unroll
@@ -336,21 +356,10 @@ assemble_vector_p1(VectorArgs A)
       wd[j] = k0 + j < S.wa ? __ldg(A.adjrot + S.ao + (k0 + j) * 32 + lane) : ADJ_INVALID_DEV;
 #pragma unroll
     for (int j = 0; j < LD_CHUNK; ++j)
-    {
-      const std::uint32_t word = wd[j];
-      if (word == ADJ_INVALID_DEV)
-        continue;
-      const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
-      const Vec3 e1 = star_edge(E, o1, lane), e2 = star_edge(E, o2, lane),
-                 e3 = star_edge(E, o3, lane);
-      const double det = dot(e1, cross(e2, e3));
-      const double f1 = F[(o1 * BS + a) * 32 + lane], f2 = F[(o2 * BS + a) * 32 + lane],
-                   f3 = F[(o3 * BS + a) * 32 + lane];
-      sum += fabs(det) * (1.0 / 120.0) * (((f0 + f1) + (f2 + f3)) + f0);
-    }
+      cell(wd[j]);
   }
   if (S.live)
-    A.b[static_cast<std::int64_t>(row) * BS + a] = A.bc[row] ? 0.0 : sum;
+    A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
 }
 
 // Exterior facets, P1 (Poisson.py:32 g*v*ds): thread = boundary row; facet mass = area/12 (1+delta).
