@@ -262,11 +262,25 @@ def main():
     t0 = time.perf_counter()
     ctx.set_problem(P)
     t_upload = time.perf_counter() - t0
+    comm_used = "none"
     if world > 1:
-        if args.comm == "nccl":
+        comm_used = args.comm
+        if args.comm == "peer":
+            # CUDA IPC can be unavailable (container without shared IPC namespace, no P2P): every
+            # rank must take the same path, so agree on the outcome before falling back to NCCL.
+            try:
+                pt.dist.connect_peers(ctx, P, dist, rank, world)
+                ok_local = 1.0
+            except Exception as e:  # noqa: BLE001
+                ok_local, peer_err = 0.0, str(e)
+            t = torch.tensor([ok_local], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if float(t.item()) < 1.0:
+                if rank == 0:
+                    print("peer-memory setup failed on some rank, using NCCL", file=sys.stderr)
+                comm_used = "nccl"
+        if comm_used == "nccl":
             pt.dist.init_nccl(ctx, abi, dist, rank, world)
-        else:
-            pt.dist.connect_peers(ctx, P, dist, rank, world)
     ndofs_global = P.n_global * P.bs
     nnz_global = allsum(float(P.nnz * P.bs * P.bs))
 
@@ -390,7 +404,7 @@ def main():
                        "fine_box": list(dims), "partition": f"z-slabs x{world}",
                        "comm": ("none" if world == 1 else
                                 "nvlink peer memory (halo pull + window all-reduce in the CG kernels)"
-                                if args.comm == "peer" else "nccl send/recv + allreduce"),
+                                if comm_used == "peer" else "nccl send/recv + allreduce"),
                        "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"
                              if P.nnz * 12 * P.bs > 3e8 else "working set near L2 size: small config",
                        "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "

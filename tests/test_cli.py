@@ -1,0 +1,81 @@
+"""dolfinx-scaling-test: the reference's command-line surface (src/main.cpp:54-115,170,186-205,
+226,232-233). CPU part: option handling and error exits; GPU part: a full run whose iteration
+count must match the oracle."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "performance-test_b200", "dolfinx-scaling-test")
+
+
+def _run(*args, timeout=300):
+    return subprocess.run([EXE, *args], capture_output=True, text=True, timeout=timeout)
+
+
+def test_help_lists_the_reference_options(pt):
+    r = _run("--help")
+    assert r.returncode == 0
+    for opt in ("--problem_type", "--mesh_type", "--memory_profiling", "--subcomm_partition",
+                "--scaling_type", "--output", "--ndofs", "--order", "--scatterer"):
+        assert opt in r.stdout
+    assert "(=poisson)" in r.stdout and "(=50000)" in r.stdout and "(=weak)" in r.stdout
+
+
+@pytest.mark.parametrize("args,msg", [
+    (["--scaling_type", "sideways"], "Scaling type 'sideways` unknown"),   # main.cpp:115
+    (["--problem_type", "stokes"], "Unknown problem type: stokes"),        # main.cpp:170
+    (["-pc_type", "gamg"], "AMG is out of scope"),
+    (["--ndofs"], "required argument"),
+])
+def test_bad_options_exit_non_zero(pt, args, msg):
+    r = _run(*args)
+    assert r.returncode != 0
+    assert msg in r.stderr
+
+
+def test_unregistered_options_are_ignored_until_the_gpu_is_needed(pt):
+    """allow_unregistered (main.cpp:76-82): unknown options do not fail parsing. Without a GPU the
+    run then stops at ptb_create with the no-fallback message; with one it completes."""
+    r = _run("--ndofs", "2000", "-ksp_view", "-log_view", "--some_future_flag=3")
+    assert "UnitCube (10x12x13) to be refined 0 times" in r.stdout  # mesh.cpp:190-194 + sizing
+    if r.returncode != 0:
+        assert "no CUDA device (there is no CPU fallback)" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ptype,ndofs", [("poisson", 40000), ("elasticity", 30000)])
+def test_full_run_matches_oracle(pt, oracle, ptype, ndofs):
+    r = _run("--problem_type", ptype, "--ndofs", str(ndofs), "-ksp_rtol", "1e-8")
+    assert r.returncode == 0, r.stderr
+    out = r.stdout
+    for row in ("ZZZ Create Mesh", "ZZZ FunctionSpace", "ZZZ Create boundary conditions",
+                "ZZZ Create RHS function", "ZZZ Assemble matrix", "ZZZ Assemble vector", "ZZZ Solve"):
+        assert row in out
+    assert ("ZZZ Assemble " in out) == (ptype == "poisson")  # enclosing timer: poisson only
+    assert "Test problem summary" in out and f"Problem type:    {ptype}" in out
+    its = int(re.search(r"\*\*\* Number of Krylov iterations: (\d+)", out).group(1))
+    norm = float(re.search(r"\*\*\* Solution norm:\s+([0-9.eE+-]+)", out).group(1))
+    dpn = 3 if ptype == "elasticity" else 1
+    Nx, Ny, Nz, rr = pt.host.cube_sizing(ndofs, False, dpn, 1, 1)
+    assert f"UnitCube ({Nx}x{Ny}x{Nz}) to be refined {rr} times" in out
+    P = pt.host.Problem(ptype, 1, Nx, Ny, Nz)
+    assert f"Total degrees of freedom:               {P.n_global * P.bs}" in out
+    A, b = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    x, k, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=10000, rtol=1e-8,
+                        precond="jacobi")
+    assert abs(its - k) <= 1
+    assert norm == pytest.approx(np.linalg.norm(x), rel=1e-5)
+
+
+@pytest.mark.gpu
+def test_cgpoisson_uses_cg_h_defaults(pt):
+    """cgpoisson: linalg::cg(u, b, action, 100, 1e-6), no preconditioner (cgpoisson_problem.cpp:233)."""
+    r = _run("--problem_type", "cgpoisson", "--ndofs", "200000")
+    assert r.returncode == 0, r.stderr
+    its = int(re.search(r"\*\*\* Number of Krylov iterations: (\d+)", r.stdout).group(1))
+    assert 1 <= its <= 100
+    assert "Gdof/s" in r.stdout
