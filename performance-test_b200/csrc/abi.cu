@@ -286,6 +286,13 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     c->vals.alloc(L.cols.size() * c->bs * c->bs);
     c->vals.zero(c->stream);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
+    // The host copy of the compressed slot map is only kept for inspection (parity tests); at
+    // HBM-capacity sizes (config C5: 0.8 G pairs) it would cost ~10 GB of host memory per rank.
+    if (c->h_adj.pairs.size() > (std::size_t(1) << 28))
+    {
+      std::vector<std::uint32_t>().swap(c->h_adj.pairs);
+      std::vector<std::uint16_t>().swap(c->h_so);
+    }
     c->have_pattern = true;
     c->matrix_assembled = false;
   });
@@ -675,6 +682,8 @@ int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32
 {
   return guarded(c, [&] {
     need(c->have_pattern, "ptb_get_slot_offsets: pattern not set");
+    need(!c->h_adj.pairs.empty() || c->h_adj.ptr.back() == 0,
+         "ptb_get_slot_offsets: the host copy is not retained above 2^28 pairs");
     if (n_pairs)
       *n_pairs = static_cast<std::int64_t>(c->h_adj.pairs.size());
     if (pair_ptr)

@@ -17,7 +17,8 @@ def pytest_configure(config):
 def pt():
     """The product package (hyphenated name -> importlib)."""
     mod = importlib.import_module("performance-test_b200")
-    if not (os.path.exists(mod.HOST_LIB) and os.path.exists(mod.ABI_LIB)):
+    exe = os.path.join(os.path.dirname(mod.HOST_LIB), "dolfinx-scaling-test")
+    if not (os.path.exists(mod.HOST_LIB) and os.path.exists(mod.ABI_LIB) and os.path.exists(exe)):
         mod.build()
     return mod
 
