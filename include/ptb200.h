@@ -35,6 +35,7 @@ typedef struct ptb_ctx ptb_ctx;
 
 enum { PTB_POISSON = 0, PTB_ELASTICITY = 1 };     /* src/Poisson.py, src/Elasticity.py */
 enum { PTB_PC_NONE = 0, PTB_PC_JACOBI = 1 };      /* cg.h as is | z = D^-1 r */
+enum { PTB_OP_ASSEMBLED = 0, PTB_OP_MATRIX_FREE = 1 };
 enum { PTB_STAGE_ASSEMBLE_MATRIX = 0, PTB_STAGE_ASSEMBLE_VECTOR = 1, PTB_STAGE_SOLVE = 2,
        PTB_STAGE_SPMV = 3, PTB_STAGE_COUNT = 4 };
 
@@ -100,6 +101,11 @@ int ptb_assemble_vector(ptb_ctx* ctx);
  * ptb_set_initial_guess was called) and b is the assembled RHS (or ptb_set_rhs). */
 int ptb_cg_solve(ptb_ctx* ctx, int kmax, double rtol, int precond, int* iterations,
                  double* rel_residual);
+/* Operator used by ptb_cg_solve / ptb_apply_operator: the assembled matrix (default) or, for
+ * Poisson P1, the matrix-free action of the reference's cgpoisson problem
+ * (src/cgpoisson_problem.cpp:193-230, form M of src/Poisson.py:33): y = sum_cells Ae(p_e) with the
+ * same Dirichlet treatment as the assembled operator. Needs the pattern, not the matrix. */
+int ptb_set_operator_mode(ptb_ctx* ctx, int mode);
 /* The `action` seam of cg.h:38-39 on its own: y = A p (halo update of p included); p_host has
  * (n_owned+n_ghost)*bs entries, y_host n_owned*bs. */
 int ptb_apply_operator(ptb_ctx* ctx, const double* p_host, double* y_host);

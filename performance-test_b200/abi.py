@@ -58,6 +58,7 @@ def lib():
         L.ptb_assemble_matrix.argtypes = [vp]
         L.ptb_assemble_vector.argtypes = [vp]
         L.ptb_cg_solve.argtypes = [vp, C.c_int, dbl, C.c_int, C.POINTER(C.c_int), C.POINTER(dbl)]
+        L.ptb_set_operator_mode.argtypes = [vp, C.c_int]
         L.ptb_apply_operator.argtypes = [vp, vp, vp]
         L.ptb_set_rhs.argtypes = [vp, vp]
         L.ptb_set_initial_guess.argtypes = [vp, vp]
@@ -207,6 +208,10 @@ class Context:
         self._check(lib().ptb_cg_solve(self._h, kmax, rtol, PRECOND[precond], C.byref(it),
                                        C.byref(rel)))
         return it.value, rel.value
+
+    def set_operator_mode(self, mode):
+        """'assembled' (default) or 'matrix_free' (Poisson P1: the cgpoisson action)."""
+        self._check(lib().ptb_set_operator_mode(self._h, {"assembled": 0, "matrix_free": 1}[mode]))
 
     def apply_operator(self, p):
         p = _a(p, np.float64)

@@ -80,6 +80,31 @@ std::int64_t ptb_ctx::device_bytes() const
          + peer.src_index.bytes();
 }
 
+namespace
+{
+VectorArgs vector_args(ptb_ctx* c)
+{
+  return VectorArgs{c->n_owned, c->n_slices, c->xyz.p, c->x_dofmap.p, c->dofmap.p, c->bc.p,
+                    c->adj_off.p, c->adj.p, c->adjrot.p, c->xdof.p, c->mat_off.p, c->cols.p,
+                    c->max_w, c->f.p, c->b.p};
+}
+
+// y = A p with the configured operator. `fused` only applies to the assembled operator in peer
+// mode; the caller has updated the ghosts of p otherwise.
+void apply_operator(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
+                    bool fused)
+{
+  if (c->operator_mode == PTB_OP_MATRIX_FREE)
+  {
+    launch_action_matrix_free(c, vector_args(c), p, y, st ? &st->py : nullptr);
+    if (st != nullptr)
+      launch_publish_py(c, st, epoch); // peer mode: hand the local p.y to the window all-reduce
+  }
+  else
+    launch_spmv(c, p, y, st, epoch, fused);
+}
+} // namespace
+
 extern "C" {
 
 int ptb_create(int device, ptb_ctx** out)
@@ -193,6 +218,7 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
          "ptb_set_space: bs must be 1 for Poisson and 3 for elasticity");
     need(n_owned > 0 && n_ghost >= 0 && dofmap, "ptb_set_space: empty space");
     c->problem = problem, c->order = order, c->bs = bs;
+    c->operator_mode = PTB_OP_ASSEMBLED;
     c->nd = (order + 1) * (order + 2) * (order + 3) / 6;
     c->n_owned = n_owned, c->n_ghost = n_ghost;
     need(static_cast<std::uint64_t>(c->n_cells) * c->nd <= 0xFFFFFFFEull,
@@ -452,8 +478,12 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
 {
   return guarded(c, [&] {
     use_device(c);
-    need(c->matrix_assembled, "ptb_cg_solve: matrix not assembled");
+    const bool mf = c->operator_mode == PTB_OP_MATRIX_FREE;
+    need(c->matrix_assembled || mf, "ptb_cg_solve: matrix not assembled");
+    need(c->have_pattern, "ptb_cg_solve: pattern not set");
     need(precond == PTB_PC_NONE || precond == PTB_PC_JACOBI, "ptb_cg_solve: unknown preconditioner");
+    need(!(mf && precond == PTB_PC_JACOBI && !c->matrix_assembled),
+         "ptb_cg_solve: Jacobi needs the assembled diagonal (call ptb_assemble_matrix once)");
     need(kmax >= 0, "ptb_cg_solve: kmax < 0");
     StageTimer t(c, PTB_STAGE_SOLVE);
     const double* dinv = precond == PTB_PC_JACOBI ? c->dinv.p : c->ones.p;
@@ -462,7 +492,7 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
       c->x.zero(c->stream);
     // r0 = b - A x0 (cg.h:46-47): the action is evaluated even for x0 = 0, like the reference.
     halo_forward(c, c->x.p);
-    launch_spmv(c, c->x.p, c->y.p, nullptr);
+    apply_operator(c, c->x.p, c->y.p, nullptr, 0, false);
     const unsigned int e0 = next_red_epoch(c);
     launch_cg_init(c, dinv, &st[1], e0);
     allreduce_sum(c, &st[1].rr, 2);
@@ -491,11 +521,11 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
           const char* e = std::getenv("PTB_FUSED_HALO");
           return !(e && e[0] == '0');
         }();
-        const bool fused = allow_fused && c->peer.enabled && !c->nbr_ranks.empty();
+        const bool fused = allow_fused && !mf && c->peer.enabled && !c->nbr_ranks.empty();
         if (!fused)
           halo_forward(c, c->p.p);
         const unsigned int ea = next_red_epoch(c), eb = next_red_epoch(c);
-        launch_spmv(c, c->p.p, c->y.p, cur, ea, fused);
+        apply_operator(c, c->p.p, c->y.p, cur, ea, fused);
         allreduce_sum(c, &cur->py, 1);
         launch_cg_update(c, dinv, cur, ea, eb);
         allreduce_sum(c, &cur->rr, 2);
@@ -527,16 +557,27 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
   });
 }
 
+int ptb_set_operator_mode(ptb_ctx* c, int mode)
+{
+  return guarded(c, [&] {
+    need(mode == PTB_OP_ASSEMBLED || mode == PTB_OP_MATRIX_FREE, "ptb_set_operator_mode: unknown mode");
+    need(mode == PTB_OP_ASSEMBLED || !c->have_space || (c->order == 1 && c->bs == 1),
+         "matrix-free operator: built for Poisson P1 only in this round");
+    c->operator_mode = mode;
+  });
+}
+
 int ptb_apply_operator(ptb_ctx* c, const double* p_host, double* y_host)
 {
   return guarded(c, [&] {
     use_device(c);
-    need(c->matrix_assembled, "ptb_apply_operator: matrix not assembled");
+    need(c->matrix_assembled || (c->operator_mode == PTB_OP_MATRIX_FREE && c->have_pattern),
+         "ptb_apply_operator: matrix not assembled");
     PTB_CUDA(cudaMemcpyAsync(c->p.p, p_host, n_local_entries(c) * sizeof(double),
                              cudaMemcpyHostToDevice, c->stream));
     StageTimer t(c, PTB_STAGE_SPMV);
     halo_forward(c, c->p.p);
-    launch_spmv(c, c->p.p, c->y.p, nullptr);
+    apply_operator(c, c->p.p, c->y.p, nullptr, 0, false);
     peer_neighbour_barrier(c); // peers may still be reading p
     t.stop();
     PTB_CUDA(cudaMemcpyAsync(y_host, c->y.p, n_owned_entries(c) * sizeof(double),

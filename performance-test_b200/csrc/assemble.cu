@@ -362,6 +362,138 @@ assemble_vector_p1(VectorArgs A)
     A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
 }
 
+// ------------------------------------------------------------------------------------------
+// Matrix-free operator, Poisson P1: y = A p without A (the `action` of the reference's cgpoisson
+// problem, cgpoisson_problem.cpp:193-230, where the operator is assemble_vector of the action form
+// M = action(a, un), Poisson.py:33). Same row-owner gather as the assembly: the row's star (edge
+// vectors and the values of p at the star's vertices) is staged once, then every cell contributes
+//   y_row += 1/(6|det|) * sum_t (c_0 . c_t) p_t
+// from registers. Dirichlet handling reproduces the assembled operator exactly: constrained
+// columns contribute nothing (bc->set(un, -1*g) with g = 0 / columns zeroed) and constrained rows
+// return p (unit diagonal), so assembled and matrix-free CG take the same iterates to rounding.
+// Also returns the local p.y partials (fused dot product, cg.h:65).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(MAT_THREADS_1)
+action_p1_poisson(VectorArgs A, const double* __restrict__ p, double* __restrict__ y,
+                  double* __restrict__ py_partials)
+{
+  extern __shared__ double smem[];
+  __shared__ double red[MAT_THREADS_1 / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const SliceView S = slice_view(A, blockIdx.x * (MAT_THREADS_1 / 32) + warp, lane);
+  const std::int32_t row = S.row;
+  const int per_slice = A.max_w * 4 * 32;
+  double* E = smem + warp * per_slice;
+  double* F = E + A.max_w * 3 * 32;
+
+  constexpr int W0 = 24;
+  std::uint32_t wd0[W0];
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    wd0[j] = j < S.wa ? __ldg(A.adjrot + S.ao + j * 32 + lane) : ADJ_INVALID_DEV;
+  const bool bc_row = S.live && A.bc[row];
+  const double p0 = S.live ? p[row] : 0.0;
+  const Vec3 X0 = S.live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  // stage E and p at the star (p of constrained columns counts as zero)
+  for (int k0 = 0; k0 < S.w; k0 += LD_CHUNK)
+  {
+    std::int32_t c[LD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      c[j] = k0 + j < S.w ? __ldg(A.cols + S.mo + (k0 + j) * 32 + lane) : -1;
+    Vec3 e[LD_CHUNK];
+    double pv[LD_CHUNK];
+    std::uint8_t bv[LD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        e[j] = load_point(A.xdof, c[j]);
+        pv[j] = p[c[j]];
+        bv[j] = __ldg(A.bc + c[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        const int k = k0 + j;
+        const Vec3 d = e[j] - X0;
+        E[(k * 3 + 0) * 32 + lane] = d.x;
+        E[(k * 3 + 1) * 32 + lane] = d.y;
+        E[(k * 3 + 2) * 32 + lane] = d.z;
+        F[k * 32 + lane] = bv[j] ? 0.0 : pv[j];
+      }
+  }
+  __syncwarp();
+
+  double sum = 0.0;
+  auto cell = [&](std::uint32_t word) {
+    if (word == ADJ_INVALID_DEV)
+      return;
+    const int o1 = (word >> 8) & 0xffu, o2 = (word >> 16) & 0xffu, o3 = word >> 24;
+    const P1Geom G = p1_geometry(star_edge(E, o1, lane), star_edge(E, o2, lane),
+                                 star_edge(E, o3, lane));
+    const double s = __drcp_rn(6.0 * fabs(G.det));
+    sum += s * (((dot(G.c0, G.c0) * p0 + dot(G.c0, G.c1) * F[o1 * 32 + lane])
+                 + dot(G.c0, G.c2) * F[o2 * 32 + lane])
+                + dot(G.c0, G.c3) * F[o3 * 32 + lane]);
+  };
+#pragma unroll
+  for (int j = 0; j < W0; ++j)
+    cell(wd0[j]);
+  for (int k0 = W0; k0 < S.wa; k0 += LD_CHUNK)
+  {
+    std::uint32_t wd[LD_CHUNK];
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      wd[j] = k0 + j < S.wa ? __ldg(A.adjrot + S.ao + (k0 + j) * 32 + lane) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < LD_CHUNK; ++j)
+      cell(wd[j]);
+  }
+  const double yr = bc_row ? p0 : sum;
+  double dotv = 0.0;
+  if (S.live)
+  {
+    y[row] = yr;
+    dotv = yr * p0;
+  }
+  // per-CTA partial of p.y in a fixed order (reduced by reduce_partials)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    dotv += __shfl_xor_sync(0xffffffffu, dotv, o);
+  if (lane == 0)
+    red[warp] = dotv;
+  __syncthreads();
+  if (tid == 0)
+  {
+    double t = 0.0;
+    for (int w = 0; w < MAT_THREADS_1 / 32; ++w)
+      t += red[w];
+    py_partials[blockIdx.x] = t;
+  }
+}
+
+// Deterministic sum of per-CTA partials (one CTA, fixed order).
+__global__ void __launch_bounds__(256)
+reduce_partials(std::int64_t n, const double* __restrict__ partials, double* out)
+{
+  __shared__ double sh[256];
+  double t = 0.0;
+  for (std::int64_t i = threadIdx.x; i < n; i += 256)
+    t += partials[i];
+  sh[threadIdx.x] = t;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1)
+  {
+    if (threadIdx.x < o)
+      sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    *out = sh[0];
+}
+
 // Exterior facets, P1 (Poisson.py:32 g*v*ds): thread = boundary row; facet mass = area/12 (1+delta).
 __global__ void assemble_facets_p1(FacetArgs A)
 {
@@ -520,6 +652,29 @@ void launch_sell_to_csr(ptb_ctx* c, double* out)
                                                                c->mat_off.p, c->vals.p, out);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
+}
+
+void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
+                               double* py_out)
+{
+  if (c->order != 1 || c->bs != 1)
+    throw std::runtime_error("matrix-free operator: built for Poisson P1 only in this round");
+  if (A.adjrot == nullptr)
+    throw std::runtime_error("matrix-free operator: a P1 row has more than 254 columns");
+  const int spc = MAT_THREADS_1 / 32;
+  const int grid = (A.n_slices + spc - 1) / spc;
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);
+  set_smem(action_p1_poisson, smem);
+  c->mf_partials.alloc(static_cast<std::size_t>(grid));
+  action_p1_poisson<<<grid, MAT_THREADS_1, smem, c->stream>>>(A, p, y, c->mf_partials.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  if (py_out != nullptr)
+  {
+    reduce_partials<<<1, 256, 0, c->stream>>>(grid, c->mf_partials.p, py_out);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+  }
 }
 
 void launch_pad_xyz(ptb_ctx* c)

@@ -658,6 +658,12 @@ cg_direction(std::int64_t n, const double* __restrict__ r, const double* __restr
   }
 }
 
+__global__ void publish_py(const CgState* st, PeerView P, unsigned int epoch)
+{
+  if (!st->conv)
+    peer_publish(P, epoch, st->py, 0.0);
+}
+
 __global__ void fill_kernel(double* v, std::int64_t n, double value)
 {
   for (std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i < n;
@@ -849,6 +855,15 @@ void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgS
   const std::int64_t n = static_cast<std::int64_t>(c->n_owned) * c->bs;
   cg_direction<<<vec_grid(c, cg_direction, n, 7), VEC_THREADS, 0, c->stream>>>(n, c->r.p, dinv, c->p.p, c->x.p, cur,
                                                               nxt, peer_view(c), epoch);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+}
+
+void launch_publish_py(ptb_ctx* c, CgState* st, unsigned int epoch)
+{
+  if (!c->peer.enabled)
+    return;
+  publish_py<<<1, 1, 0, c->stream>>>(st, peer_view(c), epoch);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }

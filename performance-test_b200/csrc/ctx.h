@@ -143,6 +143,10 @@ struct ptb_ctx
   ptb::DevBuf<double> tab_S, tab_M, tab_MF;
   int tab_order = 0;
 
+  // matrix-free operator mode (ptb_set_operator_mode) and its per-CTA dot partials
+  int operator_mode = 0;
+  ptb::DevBuf<double> mf_partials;
+
   // vectors
   ptb::DevBuf<double> f, g, b, dinv, ones, x, p, r, y;
   bool have_x0 = false;

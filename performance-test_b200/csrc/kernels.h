@@ -77,6 +77,9 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
+/// Matrix-free y = A p (Poisson P1); py_out (device, optional) receives the local p.y.
+void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
+                               double* py_out);
 void launch_sell_to_csr(ptb_ctx* c, double* out);
 /// xdof[d] = xyz[dof_vertex[d]] for vertex dofs.
 void launch_gather_xdof(ptb_ctx* c);
@@ -110,6 +113,8 @@ void launch_pack(ptb_ctx* c, const double* v, const std::int32_t* idx, std::int6
 void launch_unpack(ptb_ctx* c, const double* in, const std::int32_t* idx, std::int64_t n, int bs,
                    double* v);
 void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev);
+/// Peer mode: publish st->py (computed outside spmv_sell) to the window all-reduce; else no-op.
+void launch_publish_py(ptb_ctx* c, CgState* st, unsigned int epoch);
 
 // peer.cu
 PeerView peer_view(const ptb_ctx* c);

@@ -67,6 +67,12 @@ def _worker(rank, world, port, ptype, dims, comm, out):
         ctx.assemble_matrix()
         ctx.assemble_vector()
         k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        if ptype == "poisson":  # the matrix-free action must take the same iterates
+            ctx.set_operator_mode("matrix_free")
+            k_mf, rel_mf = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+            assert abs(k_mf - k) <= 1 and rel_mf < 1e-8
+            ctx.set_operator_mode("assembled")
+            k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
         x = ctx.solution()
         nrm = ctx.solution_norm()
         rng = np.random.default_rng(7)

@@ -212,3 +212,43 @@ def test_large_properties_elasticity(pt, ctx):
     assert rel < 1e-8
     r = b - ctx.apply_operator(ctx.solution())
     assert np.linalg.norm(r) / np.linalg.norm(b) < 1e-7
+
+
+@pytest.mark.parametrize("dims", [(5, 4, 6), (16, 15, 17), (1, 1, 1)])
+def test_matrix_free_action_equals_assembled_operator(pt, oracle, ctx, dims):
+    """cgpoisson's `action` (cgpoisson_problem.cpp:193-230): y = A p without A, same Dirichlet
+    treatment as the assembled operator; and linalg::cg(.., 100, 1e-6) on top of it."""
+    P = pt.host.Problem("poisson", 1, *dims)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    rng = np.random.default_rng(9)
+    p = rng.standard_normal(P.n_owned + P.n_ghost)
+    y_asm = ctx.apply_operator(p)
+    ctx.set_operator_mode("matrix_free")
+    y_mf = ctx.apply_operator(p)
+    assert np.abs(y_mf - y_asm).max() <= 1e-13 * np.abs(y_asm).max()
+    A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    x_ref, k_ref, rel_ref = oracle.cg(1, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref,
+                                      kmax=100, rtol=1e-6, precond="none")
+    k, rel = ctx.cg_solve(kmax=100, rtol=1e-6, precond="none")
+    assert abs(k - k_ref) <= 1
+    x = ctx.solution()[: P.n_owned]
+    assert np.linalg.norm(x - x_ref) <= 1e-5 * np.linalg.norm(x_ref)
+    ctx.set_operator_mode("assembled")
+
+
+def test_matrix_free_needs_no_matrix(pt, ctx):
+    P = pt.host.Problem("poisson", 1, 9, 8, 7)
+    ctx.set_problem(P)
+    ctx.assemble_vector()
+    ctx.set_operator_mode("matrix_free")
+    k, rel = ctx.cg_solve(kmax=500, rtol=1e-8, precond="none")
+    assert rel < 1e-8
+    with pytest.raises(RuntimeError, match="Jacobi needs the assembled diagonal"):
+        ctx.cg_solve(kmax=10, rtol=1e-8, precond="jacobi")
+    ctx.set_operator_mode("assembled")
+    P2 = pt.host.Problem("poisson", 2, 3, 3, 3)
+    ctx.set_problem(P2)
+    with pytest.raises(RuntimeError, match="Poisson P1 only"):
+        ctx.set_operator_mode("matrix_free")
