@@ -88,17 +88,33 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
       }
       else
       {
-        for (int kk = 0; kk < kn; ++kk)
+        // mixed slice: explicit indices sit at xp[rank * 32], rank = number of explicit entries
+        // before kk (from the ballot mask), so the four loads of a batch are independent
+        int kk = 0;
+        for (; kk + 4 <= kn; kk += 4)
+        {
+          std::int32_t c[4];
+          double vv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+          {
+            const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk + u);
+            const int rank = __popc(em & ((1u << (kk + u)) - 1u));
+            c[u] = ((em >> (kk + u)) & 1u) ? xp[rank * 32] : row + d;
+            vv[u] = v[(kk + u) * 32];
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            sum += vv[u] * ldp<L>(p + c[u]);
+        }
+        for (; kk < kn; ++kk)
         {
           const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
-          std::int32_t c = row + d;
-          if ((em >> kk) & 1u)
-          {
-            c = xp[0];
-            xp += 32;
-          }
+          const int rank = __popc(em & ((1u << kk) - 1u));
+          const std::int32_t c = ((em >> kk) & 1u) ? xp[rank * 32] : row + d;
           sum += v[kk * 32] * ldp<L>(p + c);
         }
+        xp += __popc(em) * 32;
       }
     }
     if (row < A.n_rows)
