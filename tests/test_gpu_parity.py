@@ -257,3 +257,37 @@ def test_matrix_free_needs_no_matrix(pt, ctx):
     ctx.set_problem(P2)
     with pytest.raises(RuntimeError, match="Poisson P1 only"):
         ctx.set_operator_mode("matrix_free")
+
+
+def test_opt_in_operator_variants_in_a_subprocess(pt):
+    """The TMA-staged SpMV (PTB_SPMV_TMA=1) and the clustered slice order (PTB_SLICE_CLUSTER=1) are
+    opt-in A/B variants read once per process: check them against the oracle in a child process."""
+    import os
+    import subprocess
+    import sys
+    code = """
+import importlib, sys
+import numpy as np
+sys.path.insert(0, %r)
+pt = importlib.import_module("performance-test_b200")
+import oracle
+for dims in ((16, 15, 17), (33, 9, 5)):
+    P = pt.host.Problem("poisson", 1, *dims)
+    ctx = pt.abi.Context(0)
+    ctx.set_problem(P)
+    ctx.assemble_matrix(); ctx.assemble_vector()
+    A = ctx.matrix_values()
+    p = np.random.default_rng(1).standard_normal(P.n_owned + P.n_ghost)
+    y, y_ref = ctx.apply_operator(p), oracle.spmv(1, P.n_owned, P["rowptr"], P["cols"], A, p)
+    assert np.abs(y - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+    k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8)
+    b = ctx.rhs()
+    r = b - ctx.apply_operator(ctx.solution())
+    assert rel < 1e-8 and np.linalg.norm(r) <= 5e-8 * np.linalg.norm(b)
+    ctx.close()
+print("variants ok")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PTB_SPMV_TMA="1", PTB_SLICE_CLUSTER="1")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
+                       env=env)
+    assert r.returncode == 0 and "variants ok" in r.stdout, r.stderr[-2000:]
