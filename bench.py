@@ -146,7 +146,12 @@ def run_reference(args):
     pt = importlib.import_module("performance-test_b200")
     import oracle
     oracle.build()
-    nthreads = oracle.max_threads()
+    # all host cores: the other ranks of a torchrun launch exit at once, and the oracle takes its
+    # thread count as an argument (torchrun's OMP_NUM_THREADS=1 does not apply)
+    try:
+        nthreads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        nthreads = os.cpu_count() or 1
     ptype, order, dims, base, scaling, ndofs = sizing(pt, args.workload, 1, args.cpu_sample_ndofs)
     P = pt.host.Problem(ptype, order, *dims)
     ndof = P.n_owned * P.bs
