@@ -102,7 +102,7 @@ int ptb_assemble_vector(ptb_ctx* ctx);
 int ptb_cg_solve(ptb_ctx* ctx, int kmax, double rtol, int precond, int* iterations,
                  double* rel_residual);
 /* Operator used by ptb_cg_solve / ptb_apply_operator: the assembled matrix (default) or, for
- * Poisson P1, the matrix-free action of the reference's cgpoisson problem
+ * the scalar Poisson spaces (P1-P3), the matrix-free action of the reference's cgpoisson problem
  * (src/cgpoisson_problem.cpp:193-230, form M of src/Poisson.py:33): y = sum_cells Ae(p_e) with the
  * same Dirichlet treatment as the assembled operator. Needs the pattern, not the matrix. */
 int ptb_set_operator_mode(ptb_ctx* ctx, int mode);

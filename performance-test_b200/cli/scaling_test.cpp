@@ -273,12 +273,9 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
   }
   if (cgp)
   {
-    // cgpoisson never assembles A (cgpoisson_problem.cpp:139-141): for P1 the operator is the
-    // matrix-free action; for P2/P3 (no matrix-free kernel yet) it is the assembled CSR
-    if (order == 1)
-      ok(c, ptb_set_operator_mode(c, PTB_OP_MATRIX_FREE));
-    else
-      ok(c, ptb_assemble_matrix(c));
+    // cgpoisson never assembles A (cgpoisson_problem.cpp:139-141): the operator is the matrix-free
+    // action of form M (Poisson.py:33)
+    ok(c, ptb_set_operator_mode(c, PTB_OP_MATRIX_FREE));
   }
   if (t1)
   {

@@ -561,8 +561,8 @@ int ptb_set_operator_mode(ptb_ctx* c, int mode)
 {
   return guarded(c, [&] {
     need(mode == PTB_OP_ASSEMBLED || mode == PTB_OP_MATRIX_FREE, "ptb_set_operator_mode: unknown mode");
-    need(mode == PTB_OP_ASSEMBLED || !c->have_space || (c->order == 1 && c->bs == 1),
-         "matrix-free operator: built for Poisson P1 only in this round");
+    need(mode == PTB_OP_ASSEMBLED || !c->have_space || c->bs == 1,
+         "matrix-free operator: built for the scalar Poisson space only");
     c->operator_mode = mode;
   });
 }

@@ -657,8 +657,10 @@ void launch_sell_to_csr(ptb_ctx* c, double* out)
 void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
                                double* py_out)
 {
-  if (c->order != 1 || c->bs != 1)
-    throw std::runtime_error("matrix-free operator: built for Poisson P1 only in this round");
+  if (c->bs != 1)
+    throw std::runtime_error("matrix-free operator: built for the scalar Poisson space only");
+  if (c->order != 1)
+    return launch_action_matrix_free_pk(c, A, p, y, py_out);
   if (A.adjrot == nullptr)
     throw std::runtime_error("matrix-free operator: a P1 row has more than 254 columns");
   const int spc = MAT_THREADS_1 / 32;
@@ -670,11 +672,14 @@ void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p,
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
   if (py_out != nullptr)
-  {
-    reduce_partials<<<1, 256, 0, c->stream>>>(grid, c->mf_partials.p, py_out);
-    PTB_CUDA(cudaGetLastError());
-    c->launches += 1;
-  }
+    launch_reduce_partials(c, grid, c->mf_partials.p, py_out);
+}
+
+void launch_reduce_partials(ptb_ctx* c, std::int64_t n, const double* partials, double* out)
+{
+  reduce_partials<<<1, 256, 0, c->stream>>>(n, partials, out);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
 }
 
 void launch_pad_xyz(ptb_ctx* c)

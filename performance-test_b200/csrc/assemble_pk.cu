@@ -196,6 +196,83 @@ __global__ void assemble_facets_pk(FacetArgs A, const double* __restrict__ MFg)
   A.b[row] += sum;
 }
 
+// Matrix-free operator for P2/P3 (the cgpoisson `action`, cgpoisson_problem.cpp:193-230, with the
+// form M = action(a, un) of Poisson.py:33): y_row = sum_cells sum_j Ae[li][j] p_j evaluated as
+// sum_m G_m (S_m[li][:] . p_cell), i.e. six length-nd dot products with the reference tensors and
+// six FMAs with the geometry factors per (row, cell). Constrained columns contribute nothing and
+// constrained rows return p (same operator as the assembled one). Per-CTA partials of p.y.
+template <int ND>
+__global__ void __launch_bounds__(PK_THREADS)
+action_pk(VectorArgs A, const double* __restrict__ Sg, const double* __restrict__ p,
+          double* __restrict__ y, double* __restrict__ py_partials)
+{
+  extern __shared__ double St[]; // [6][ND][ND]
+  __shared__ double red[PK_THREADS / 32];
+  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
+    St[i] = Sg[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
+  const std::int32_t row = slice * 32 + lane;
+  const bool active = slice < A.n_slices && row < A.n_rows;
+  double dotv = 0.0;
+  if (active)
+  {
+    const std::int64_t ao = A.adj_off[slice];
+    const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+    double sum = 0.0;
+    for (int k = 0; k < wa; ++k)
+    {
+      const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+      if (pair == ADJ_INVALID_DEV)
+        break; // lists are front-packed
+      const std::uint32_t cell = pair / ND;
+      const int li = pair - cell * ND;
+      const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+      const Vec3 X0 = load_point(A.xyz, v.x);
+      const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+                 e3 = load_point(A.xyz, v.w) - X0;
+      const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+      const double inv = 1.0 / fabs(dot(e1, c1));
+      const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
+                   G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+      const std::int32_t* dofs = A.dofmap + static_cast<std::int64_t>(cell) * ND;
+      const double* S = St + li * ND;
+      double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+      {
+        const std::int32_t dj = __ldg(dofs + j);
+        const double pj = A.bc[dj] ? 0.0 : p[dj];
+        t0 += S[0 * ND * ND + j] * pj;
+        t1 += S[1 * ND * ND + j] * pj;
+        t2 += S[2 * ND * ND + j] * pj;
+        t3 += S[3 * ND * ND + j] * pj;
+        t4 += S[4 * ND * ND + j] * pj;
+        t5 += S[5 * ND * ND + j] * pj;
+      }
+      sum += ((G00 * t0 + G01 * t1) + (G02 * t2 + G11 * t3)) + (G12 * t4 + G22 * t5);
+    }
+    const double p0 = p[row];
+    const double yr = A.bc[row] ? p0 : sum;
+    y[row] = yr;
+    dotv = yr * p0;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    dotv += __shfl_xor_sync(0xffffffffu, dotv, o);
+  if (lane == 0)
+    red[warp] = dotv;
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    double t = 0.0;
+    for (int w = 0; w < PK_THREADS / 32; ++w)
+      t += red[w];
+    py_partials[blockIdx.x] = t;
+  }
+}
+
 void ensure_tables(ptb_ctx* c)
 {
   if (c->tab_order == c->order)
@@ -244,6 +321,30 @@ void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A)
     launch_matrix<20>(c, A);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
+}
+
+void launch_action_matrix_free_pk(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
+                                  double* py_out)
+{
+  if (c->bs != 1)
+    throw std::runtime_error("matrix-free operator: built for the scalar Poisson space only");
+  ensure_tables(c);
+  const int grid = (A.n_slices + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
+  c->mf_partials.alloc(static_cast<std::size_t>(grid));
+  if (c->order == 2)
+  {
+    const std::size_t smem = 6 * 10 * 10 * sizeof(double);
+    action_pk<10><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p, p, y, c->mf_partials.p);
+  }
+  else
+  {
+    const std::size_t smem = 6 * 20 * 20 * sizeof(double);
+    action_pk<20><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p, p, y, c->mf_partials.p);
+  }
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  if (py_out != nullptr)
+    launch_reduce_partials(c, grid, c->mf_partials.p, py_out);
 }
 
 void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)

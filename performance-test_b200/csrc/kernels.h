@@ -80,6 +80,9 @@ void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs&
 /// Matrix-free y = A p (Poisson P1); py_out (device, optional) receives the local p.y.
 void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
                                double* py_out);
+void launch_action_matrix_free_pk(ptb_ctx* c, const VectorArgs& A, const double* p, double* y,
+                                  double* py_out);
+void launch_reduce_partials(ptb_ctx* c, std::int64_t n, const double* partials, double* out);
 void launch_sell_to_csr(ptb_ctx* c, double* out);
 /// xdof[d] = xyz[dof_vertex[d]] for vertex dofs.
 void launch_gather_xdof(ptb_ctx* c);

@@ -214,11 +214,13 @@ def test_large_properties_elasticity(pt, ctx):
     assert np.linalg.norm(r) / np.linalg.norm(b) < 1e-7
 
 
-@pytest.mark.parametrize("dims", [(5, 4, 6), (16, 15, 17), (1, 1, 1)])
-def test_matrix_free_action_equals_assembled_operator(pt, oracle, ctx, dims):
+@pytest.mark.parametrize("order,dims", [(1, (5, 4, 6)), (1, (16, 15, 17)), (1, (1, 1, 1)),
+                                        (2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)),
+                                        (3, (6, 5, 7))])
+def test_matrix_free_action_equals_assembled_operator(pt, oracle, ctx, order, dims):
     """cgpoisson's `action` (cgpoisson_problem.cpp:193-230): y = A p without A, same Dirichlet
     treatment as the assembled operator; and linalg::cg(.., 100, 1e-6) on top of it."""
-    P = pt.host.Problem("poisson", 1, *dims)
+    P = pt.host.Problem("poisson", order, *dims)
     ctx.set_problem(P)
     ctx.assemble_matrix()
     ctx.assemble_vector()
@@ -253,9 +255,9 @@ def test_matrix_free_needs_no_matrix(pt, ctx):
     with pytest.raises(RuntimeError, match="Jacobi needs the assembled diagonal"):
         ctx.cg_solve(kmax=10, rtol=1e-8, precond="jacobi")
     ctx.set_operator_mode("assembled")
-    P2 = pt.host.Problem("poisson", 2, 3, 3, 3)
-    ctx.set_problem(P2)
-    with pytest.raises(RuntimeError, match="Poisson P1 only"):
+    E = pt.host.Problem("elasticity", 1, 3, 3, 3)
+    ctx.set_problem(E)
+    with pytest.raises(RuntimeError, match="scalar Poisson space only"):
         ctx.set_operator_mode("matrix_free")
 
 
