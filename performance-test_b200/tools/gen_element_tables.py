@@ -10,7 +10,7 @@ CUDA element kernels in "tensor representation" (SURVEY B4):
 Route: 60-digit mpmath arithmetic, nodal basis by Vandermonde inversion in the monomial basis and
 the closed form int x^a y^b z^c = a! b! c! / (a+b+c+3)!  -- independent of the oracle, which
 tabulates the basis at Gauss-Jacobi points in double precision (oracle/tables.py).
-Run:  python performance-test_b200/tools/gen_element_tables.py
+Run:  python performance-test_b200/tools/gen_element_tables.py [output path]
 """
 import itertools
 import os
@@ -163,7 +163,9 @@ def main():
         emit(f"M_P{order}", [M], nd, out)
         emit(f"MF_P{order}", Mf, nd, out)
     out.append("} } // namespace ptb::tables")
-    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "element_tables.h")
+    import sys
+    path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(
+        os.path.dirname(os.path.abspath(__file__)), "..", "csrc", "element_tables.h")
     open(path, "w").write("\n".join(out) + "\n")
     print("wrote", os.path.normpath(path))
 
