@@ -233,3 +233,33 @@ def test_cg_none_reproduces_cg_h_semantics(pt, oracle):
         p = be * p + r
     assert abs(kk - k) <= 1
     np.testing.assert_allclose(x, xr, rtol=1e-6, atol=1e-10)
+
+
+@pytest.mark.parametrize("order,rate", [(1, 1.7), (2, 2.7), (3, 3.6)])
+def test_manufactured_solution_convergence_rates(pt, oracle, order, rate):
+    """-Laplace u = 2 pi^2 u with u = sin(pi x) cos(pi y): u = 0 on x = 0, 1 (the reference's
+    Dirichlet set) and zero flux on the other faces, so the reference's problem setup applies
+    unchanged with f = 2 pi^2 u, g = 0. The nodal error must fall like h^(k+1): this pins the
+    global consistency of the P2/P3 dofmaps (edge orientation, gll_warped points, face dofs) --
+    a wrong edge flip in one tet type would destroy the rate."""
+    errs = []
+    sizes = {1: (6, 12), 2: (3, 6), 3: (2, 4)}[order]
+    for n in sizes:
+        P = pt.host.Problem("poisson", order, n, n, n)
+        X = P["dof_x"].reshape(-1, 3)
+        u_ex = np.sin(np.pi * X[:, 0]) * np.cos(np.pi * X[:, 1])
+
+        class Q:
+            def __getattr__(s, k): return getattr(P, k)
+            def __getitem__(s, k):
+                if k == "f": return 2 * np.pi ** 2 * u_ex
+                if k == "g": return np.zeros(0)
+                return P[k]
+        A = oracle.assemble_matrix(P)
+        b = oracle.assemble_vector(Q())
+        x, k, rel = oracle.cg(1, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=5000, rtol=1e-12,
+                              precond="jacobi")
+        assert rel < 1e-12
+        errs.append(np.sqrt(np.mean((x - u_ex) ** 2)))
+    observed = np.log2(errs[0] / errs[1])
+    assert observed > rate, (errs, observed)
