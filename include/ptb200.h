@@ -136,6 +136,15 @@ int ptb_get_slot_offsets(ptb_ctx* ctx, int64_t* n_pairs, int64_t* pair_ptr, uint
 int ptb_debug_layout_roundtrip(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
                                const int32_t* cols, int32_t* cols_out, double* explicit_fraction);
 
+/* The P1 star walk the assembly kernels follow (host only, no GPU): for every owned row the
+ * step words in walk order, walk_out[pair_ptr[r] + k] for step k of row r (pair_ptr = dof -> cell
+ * adjacency offsets, as ptb_get_slot_offsets returns them). Byte p < 3 of a word = in-row offset
+ * of the vertex held in register position p after the step, byte 3 = mask of positions loaded in
+ * the step. loads_per_step (optional) receives the average number of vertices loaded per step. */
+int ptb_debug_star_walk(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, uint32_t* walk_out,
+                        double* loads_per_step);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

@@ -70,6 +70,7 @@ def lib():
         L.ptb_build_cell_slot_map.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp]
         L.ptb_debug_layout_roundtrip.argtypes = [i32, i64, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
+        L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
         L.ptb_stage_ms.restype = dbl
@@ -101,6 +102,20 @@ def build_cell_slot_map(dofmap, nd, n_owned, rowptr, cols):
     if rc != 0:
         raise RuntimeError(lib().ptb_last_error(None).decode())
     return out
+
+
+def star_walk(dofmap, n_owned, rowptr, cols):
+    """Host-only: P1 star-walk step words per (row, step), row-major; returns (words, loads/step)."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    n_cells = len(dm) // 4
+    n_pairs = int(np.count_nonzero(dm < n_owned))
+    out = np.zeros(n_pairs, dtype=np.uint32)
+    lps = C.c_double()
+    rc = lib().ptb_debug_star_walk(n_cells, _ptr(dm), n_owned, _ptr(rp), _ptr(cl), _ptr(out),
+                                   C.byref(lps))
+    if rc != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return out, lps.value
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

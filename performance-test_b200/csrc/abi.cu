@@ -73,7 +73,7 @@ std::int64_t ptb_ctx::device_bytes() const
 {
   return xyz.bytes() + xyz3.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
-         + adjso.bytes() + adjrot.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + adjso.bytes() + adjrot.bytes() + walk.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
          + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes()
@@ -301,6 +301,14 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->adjrot.release();
       c->adj.upload(L.adj, c->stream);
       c->adjso.upload(L.adjso, c->stream);
+    }
+    c->walk.release();
+    if (const char* env = std::getenv("PTB_ASM_WALK"); env && env[0] == '1' && !L.adjrot.empty())
+    {
+      // opt-in: star-walk assembly kernels (assemble_walk.cu)
+      const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);
+      c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
+      c->walk.upload(L.walk, c->stream);
     }
     {
       // visiting order of the operator kernels (ghost-reading slices last, clustered groups)
@@ -715,6 +723,28 @@ int ptb_debug_layout_roundtrip(int32_t n_rows, int64_t n_cols, const int64_t* ro
     }
     if (explicit_fraction)
       *explicit_fraction = L.cols.empty() ? 0.0 : static_cast<double>(L.colsx.size()) / L.cols.size();
+  });
+}
+
+int ptb_debug_star_walk(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, uint32_t* walk_out,
+                        double* loads_per_step)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && walk_out, "ptb_debug_star_walk: NULL argument");
+    RowAdjacency adj;
+    std::vector<std::uint16_t> so;
+    build_row_adjacency(dofmap, n_cells, 4, n_owned, adj);
+    const std::int64_t max_so = build_slot_offsets(dofmap, 4, n_owned, adj, rowptr, cols, so);
+    need(max_so >= 0 && max_so < 255, "ptb_debug_star_walk: pattern does not cover the cells / row too long");
+    SellLayout L;
+    build_sell_layout(n_owned, 4, rowptr, cols, adj, so, max_so, L);
+    const WalkStats st = build_walk(n_owned, adj, so, L);
+    for (std::int32_t r = 0; r < n_owned; ++r)
+      for (std::int64_t k = 0; k < adj.ptr[r + 1] - adj.ptr[r]; ++k)
+        walk_out[adj.ptr[r] + k] = L.walk[L.adj_off[r >> 5] + k * 32 + (r & 31)];
+    if (loads_per_step)
+      *loads_per_step = st.steps ? static_cast<double>(st.loads) / st.steps : 0.0;
   });
 }
 

@@ -1,0 +1,212 @@
+// P1 matrix assembly along the *star walk* (layout.h build_walk) -- second generation of the
+// row-owner gather of assemble.cu, same results to rounding, same reference region
+// (fem::assemble_matrix + set_diagonal, poisson_problem.cpp:129-137).
+//
+// Why: ncu on assemble_matrix_p1<1> (profiles/r01_ncu_full_poisson_assemble_spmv.csv) shows the
+// shared-memory pipe as the busiest unit -- per (row, cell) the kernel reads three edge vectors
+// (9 LDS.64) and read-modify-writes three accumulators (3 LDS.64 + 3 STS.64): 30 wavefronts. The
+// cells of a vertex star can be ordered so that consecutive cells share a face; then two of the
+// three edge vectors, one of the three cofactor vectors and two of the three accumulators carry
+// over in registers:
+//   step      one word per (row, step): which register positions are reloaded, and from where
+//   reload    position p: flush a_p into the shared-memory accumulator of its old column, load
+//             the new edge vector, a_p = 0                 (1 RMW + 3 LDS.64 instead of 3 RMW + 9)
+//   geometry  n_p = e_{p+1} x e_{p+2} is recomputed only if one of its factors changed
+//   element   det = e_0 . n_0, c_own = -(n_0 + n_1 + n_2), a_p += c_own . n_p / (6 |det|)
+// The step is branch-free (predicated reloads), so the unrolled chunk of steps schedules as one
+// block. Shared memory is private per lane (column `lane` of E and acc): no barrier anywhere.
+// Opt-in with PTB_ASM_WALK=1 until it has been measured against assemble_matrix_p1.
+#include "geom.cuh"
+#include "kernels.h"
+
+namespace ptb
+{
+namespace
+{
+
+constexpr int WALK_WARPS = 2; // slices per CTA: 2 x 15.4 KB (w = 15) -> 7 CTAs = 14 warps per SM
+constexpr int WALK_CHUNK = 8; // step words in flight per thread
+
+// 1/d for a normal, finite d: MUFU seed + one cubic and one quadratic Newton step, no slow path
+// (the element volume of a valid mesh is never denormal), so the step has no branch.
+__device__ __forceinline__ double rcp_fast(double d)
+{
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
+// Register positions of the walk (three non-owner vertices of the current cell).
+struct WalkState
+{
+  Vec3 e0, e1, e2; // edge vectors owner -> vertex
+  Vec3 n0, n1, n2; // n_p = e_{p+1} x e_{p+2}  (= det * grad phi_p)
+  double a0, a1, a2, dg;
+  std::uint32_t prev; // previous step word (bytes 0..2: columns the positions accumulate into)
+};
+
+__global__ void __launch_bounds__(WALK_WARPS * 32, 7)
+assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * WALK_WARPS + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int64_t mo = A.mat_off[slice], ao = A.adj_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+
+  double* E = smem + warp * (A.max_w * 4 * 32) + lane; // E[(k*3+d)*32], private column `lane`
+  double* acc = E + A.max_w * 3 * 32;                  // acc[k*32]
+
+  // ---- prologue: step words of the first chunk, row scalars, then the star ------------------
+  const std::uint32_t* wp = walk + ao + lane;
+  std::uint32_t wd[WALK_CHUNK];
+#pragma unroll
+  for (int j = 0; j < WALK_CHUNK; ++j)
+    wd[j] = j < wa ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+
+  std::uint32_t bcmask = 0; // bit k: column k of the row is constrained
+  int own = -1;             // position of the diagonal in the row
+  for (int k0 = 0; k0 < w; k0 += 2 * WALK_CHUNK)
+  {
+    std::int32_t c[2 * WALK_CHUNK];
+#pragma unroll
+    for (int j = 0; j < 2 * WALK_CHUNK; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+    {
+      Vec3 x[WALK_CHUNK];
+      std::uint8_t b[WALK_CHUNK];
+#pragma unroll
+      for (int j = 0; j < WALK_CHUNK; ++j)
+        if (c[h * WALK_CHUNK + j] >= 0)
+        {
+          x[j] = load_point(A.xdof, c[h * WALK_CHUNK + j]);
+          b[j] = __ldg(A.bc + c[h * WALK_CHUNK + j]);
+        }
+#pragma unroll
+      for (int j = 0; j < WALK_CHUNK; ++j)
+        if (c[h * WALK_CHUNK + j] >= 0)
+        {
+          const int k = k0 + h * WALK_CHUNK + j;
+          const Vec3 d = x[j] - X0;
+          E[(k * 3 + 0) * 32] = d.x;
+          E[(k * 3 + 1) * 32] = d.y;
+          E[(k * 3 + 2) * 32] = d.z;
+          acc[k * 32] = 0.0;
+          bcmask |= b[j] ? 1u << k : 0u;
+          own = c[h * WALK_CHUNK + j] == row && k < len ? k : own;
+        }
+    }
+  }
+
+  // ---- walk ---------------------------------------------------------------------------------
+  WalkState W;
+  W.e0 = W.e1 = W.e2 = W.n0 = W.n1 = W.n2 = Vec3{0.0, 0.0, 0.0};
+  W.a0 = W.a1 = W.a2 = W.dg = 0.0;
+  W.prev = 0;
+  auto step = [&](std::uint32_t word) {
+    const bool valid = word != ADJ_INVALID_DEV;
+    word = valid ? word : (W.prev & 0x00FFFFFFu); // padding: keep everything, add nothing
+    const int o0 = word & 0xFFu, o1 = (word >> 8) & 0xFFu, o2 = (word >> 16) & 0xFFu;
+    const int p0 = W.prev & 0xFFu, p1 = (W.prev >> 8) & 0xFFu, p2 = (W.prev >> 16) & 0xFFu;
+    const bool l0 = word & (1u << 24), l1 = word & (2u << 24), l2 = word & (4u << 24);
+    if (l0)
+    {
+      acc[p0 * 32] += W.a0;
+      W.e0 = Vec3{E[(o0 * 3 + 0) * 32], E[(o0 * 3 + 1) * 32], E[(o0 * 3 + 2) * 32]};
+      W.a0 = 0.0;
+    }
+    if (l1)
+    {
+      acc[p1 * 32] += W.a1;
+      W.e1 = Vec3{E[(o1 * 3 + 0) * 32], E[(o1 * 3 + 1) * 32], E[(o1 * 3 + 2) * 32]};
+      W.a1 = 0.0;
+    }
+    if (l2)
+    {
+      acc[p2 * 32] += W.a2;
+      W.e2 = Vec3{E[(o2 * 3 + 0) * 32], E[(o2 * 3 + 1) * 32], E[(o2 * 3 + 2) * 32]};
+      W.a2 = 0.0;
+    }
+    if (l1 || l2)
+      W.n0 = cross(W.e1, W.e2);
+    if (l2 || l0)
+      W.n1 = cross(W.e2, W.e0);
+    if (l0 || l1)
+      W.n2 = cross(W.e0, W.e1);
+    const double det = dot(W.e0, W.n0);
+    const double r = valid ? rcp_fast(6.0 * fabs(det)) : 0.0;
+    const Vec3 c0 = {-(W.n0.x + W.n1.x + W.n2.x), -(W.n0.y + W.n1.y + W.n2.y),
+                     -(W.n0.z + W.n1.z + W.n2.z)};
+    W.dg = fma(r, dot(c0, c0), W.dg);
+    W.a0 = fma(r, dot(c0, W.n0), W.a0);
+    W.a1 = fma(r, dot(c0, W.n1), W.a1);
+    W.a2 = fma(r, dot(c0, W.n2), W.a2);
+    W.prev = word;
+  };
+  for (int k0 = 0; k0 < wa; k0 += WALK_CHUNK)
+  {
+    std::uint32_t nx[WALK_CHUNK]; // next chunk in flight while this one is walked
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      nx[j] = k0 + WALK_CHUNK + j < wa ? __ldg(wp + (k0 + WALK_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      step(wd[j]);
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  acc[(W.prev & 0xFFu) * 32] += W.a0;
+  acc[((W.prev >> 8) & 0xFFu) * 32] += W.a1;
+  acc[((W.prev >> 16) & 0xFFu) * 32] += W.a2;
+
+  // ---- epilogue: BC rows/cols -> 0, BC diagonal -> 1, every stored value written once --------
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const bool real = k < len, is_own = k == own;
+    double val = is_own ? W.dg : acc[k * 32];
+    if (bc_row || ((bcmask >> k) & 1u))
+      val = is_own ? 1.0 : 0.0;
+    if (!real)
+      val = 0.0;
+    A.vals[mo + k * 32 + lane] = val;
+    diag = is_own ? val : diag;
+  }
+  if (live)
+    A.dinv[row] = 1.0 / diag;
+}
+
+} // namespace
+
+bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A)
+{
+  if (c->order != 1 || c->bs != 1 || c->walk.p == nullptr || c->max_w > 32)
+    return false;
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * WALK_WARPS * sizeof(double);
+  if (smem > 227 * 1024)
+    return false;
+  PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_p1_walk, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  assemble_matrix_p1_walk<<<(A.n_slices + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, smem,
+                            c->stream>>>(A, c->walk.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return true;
+}
+
+} // namespace ptb

@@ -131,6 +131,8 @@ struct ptb_ctx
   std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry
   ptb::DevBuf<std::uint32_t> adj, adjso, adjrot;
+  ptb::DevBuf<std::uint32_t> walk;     // P1 star walk (layout.h), uploaded when PTB_ASM_WALK=1
+  double walk_loads_per_step = 0.0;
   // host copies of the compressed slot map (parity inspection)
   ptb::RowAdjacency h_adj;
   std::vector<std::uint16_t> h_so;

@@ -1,0 +1,55 @@
+// Device helpers shared by the assembly kernels: small vector algebra, padded point loads and
+// the P1 cofactor geometry (see assemble.cu for the scheme).
+#pragma once
+#include <cstdint>
+
+namespace ptb
+{
+namespace
+{
+
+struct Vec3
+{
+  double x, y, z;
+};
+__device__ __forceinline__ Vec3 operator-(Vec3 a, Vec3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
+{
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ double comp(Vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
+
+__device__ __forceinline__ Vec3 load_point(const double* __restrict__ xyz4, std::int64_t v)
+{
+  // padded [n][4]: two 16-byte loads
+  const double2* p = reinterpret_cast<const double2*>(xyz4 + 4 * v);
+  const double2 a = __ldg(p), b = __ldg(p + 1);
+  return {a.x, a.y, b.x};
+}
+
+__device__ __forceinline__ int sel4(int4 v, int i)
+{
+  return i == 0 ? v.x : (i == 1 ? v.y : (i == 2 ? v.z : v.w));
+}
+
+// P1 geometry seen from the owner (local vertex 0 after rotation): scaled gradients
+// c_t = det * grad(phi_t) (cofactor vectors) from the three edge vectors. Ae[0][t] = c_0.c_t/(6|det|).
+struct P1Geom
+{
+  Vec3 c0, c1, c2, c3;
+  double det;
+};
+__device__ __forceinline__ P1Geom p1_geometry(Vec3 e1, Vec3 e2, Vec3 e3)
+{
+  P1Geom G;
+  G.c1 = cross(e2, e3);
+  G.c2 = cross(e3, e1);
+  G.c3 = cross(e1, e2);
+  G.det = dot(e1, G.c1);
+  G.c0 = {-(G.c1.x + G.c2.x + G.c3.x), -(G.c1.y + G.c2.y + G.c3.y), -(G.c1.z + G.c2.z + G.c3.z)};
+  return G;
+}
+
+} // namespace
+} // namespace ptb

@@ -94,6 +94,92 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
   }
 }
 
+WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
+                     const std::vector<std::uint16_t>& so, SellLayout& L)
+{
+  if (L.adjrot.empty())
+    throw std::runtime_error("build_walk: needs the rotated P1 slot words");
+  L.walk.assign(L.adjrot.size(), ADJ_INVALID);
+  const std::uint32_t* pairs = adj.pairs.data();
+  std::int64_t steps = 0, loads = 0;
+#pragma omp parallel reduction(+ : steps, loads)
+  {
+    std::vector<std::uint8_t> o;          // [c][3] offsets of the non-owner vertices, rotation order
+    std::vector<std::uint64_t> m;         // [c][4] the same as a 256-bit set
+    std::vector<char> visited;
+#pragma omp for schedule(static)
+    for (std::int32_t r = 0; r < n_rows; ++r)
+    {
+      const std::int64_t q0 = adj.ptr[r];
+      const int c = static_cast<int>(adj.ptr[r + 1] - q0);
+      if (c == 0)
+        continue;
+      o.resize(static_cast<std::size_t>(c) * 3);
+      m.assign(static_cast<std::size_t>(c) * 4, 0);
+      visited.assign(c, 0);
+      for (int j = 0; j < c; ++j)
+      {
+        const int li = pairs[q0 + j] & 3;
+        for (int t = 1; t < 4; ++t)
+        {
+          const std::uint8_t v = static_cast<std::uint8_t>(so[(q0 + j) * 4 + ((li + t) & 3)]);
+          o[j * 3 + t - 1] = v;
+          m[j * 4 + (v >> 6)] |= std::uint64_t(1) << (v & 63);
+        }
+      }
+      auto shared = [&](int a, int b) {
+        return __builtin_popcountll(m[a * 4] & m[b * 4]) + __builtin_popcountll(m[a * 4 + 1] & m[b * 4 + 1])
+               + __builtin_popcountll(m[a * 4 + 2] & m[b * 4 + 2])
+               + __builtin_popcountll(m[a * 4 + 3] & m[b * 4 + 3]);
+      };
+      const std::int64_t base = L.adj_off[r >> 5] + (r & 31);
+      int pos[3] = {o[0], o[1], o[2]};
+      int cur = 0;
+      visited[0] = 1;
+      L.walk[base] = pos[0] | (pos[1] << 8) | (pos[2] << 16) | (7u << 24);
+      steps += c, loads += 3;
+      for (int step = 1; step < c; ++step)
+      {
+        int best = -1, best_sh = -1;
+        for (int j = 0; j < c; ++j)
+        {
+          if (visited[j])
+            continue;
+          const int sh = shared(cur, j);
+          if (sh > best_sh)
+            best = j, best_sh = sh;
+          if (sh >= 2)
+            break; // a face neighbour: nothing later in the list can be preferred
+        }
+        // vertices of the new cell that are already held keep their position
+        bool held[3] = {false, false, false}, old[3] = {false, false, false};
+        for (int t = 0; t < 3; ++t)
+          for (int p = 0; p < 3; ++p)
+            if (!held[p] && !old[t] && pos[p] == o[best * 3 + t])
+              held[p] = true, old[t] = true;
+        unsigned mask = 0;
+        int p = 0;
+        for (int t = 0; t < 3; ++t)
+        {
+          if (old[t])
+            continue;
+          while (held[p])
+            ++p;
+          pos[p] = o[best * 3 + t];
+          held[p] = true;
+          mask |= 1u << p;
+          ++loads;
+        }
+        L.walk[base + static_cast<std::int64_t>(step) * 32]
+            = pos[0] | (pos[1] << 8) | (pos[2] << 16) | (mask << 24);
+        visited[best] = 1;
+        cur = best;
+      }
+    }
+  }
+  return {steps, loads};
+}
+
 void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64_t* rowptr,
                       SellLayout& L)
 {

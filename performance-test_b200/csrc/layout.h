@@ -22,6 +22,11 @@ struct SellLayout
   // P1 only (nd == 4, offsets < 255): the four in-row offsets of a pair rotated so that the
   // owner's own column comes first: byte t = offset of local vertex (li + t) & 3.
   std::vector<std::uint32_t> adjrot;
+  // P1 only, same indexing as adjrot: the row's cells re-ordered into a *walk* over its vertex
+  // star (build_walk). Word k of a row describes step k: bytes 0..2 = in-row offsets of the
+  // three non-owner vertices held in register positions 0..2 after the step, byte 3 = mask of
+  // the positions that were (re)loaded in this step (7 on the first cell). ADJ_INVALID = padding.
+  std::vector<std::uint32_t> walk;
   // Column-index compression for the SpMV (scalar matrices): cdelta[mat_off[s]/32 + k] = d when
   // every row r of slice s has col_k = r + d (translation-invariant stencil), else CDELTA_EXPLICIT
   // and the 32 indices are stored in colsx at xoff[s] + j*32 + lane (j-th explicit k of the slice).
@@ -39,6 +44,20 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
                        const std::int32_t* cols, const RowAdjacency& adj,
                        const std::vector<std::uint16_t>& so, std::int64_t max_so,
                        SellLayout& L);
+
+/// Star walk of every P1 row (requires L.adjrot, i.e. nd == 4 and offsets < 255). The cells of a
+/// row are visited so that consecutive cells share as many vertices as possible (greedy: most
+/// shared vertices with the current cell, ties to the earlier cell of the ascending list; the walk
+/// starts at the row's first cell). Vertices that stay keep their register position; new vertices
+/// take the freed positions in ascending order, in the cell's own rotation order (li+1, li+2, li+3),
+/// so the walk depends on the mesh topology and the cell order only, never on dof labels.
+/// On the Kuhn box every interior star (24 cells) is walked with one new vertex per step.
+struct WalkStats
+{
+  std::int64_t steps = 0, loads = 0; // loads = vertices (re)loaded over all steps
+};
+WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
+                     const std::vector<std::uint16_t>& so, SellLayout& L);
 
 /// Visiting order of the slices for the operator kernels. Slices without ghost columns come first
 /// (n_interior of them), so the fused halo pull overlaps with them. Inside each class the order is

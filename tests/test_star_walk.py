@@ -1,0 +1,159 @@
+"""P1 star walk (layout.cpp build_walk): the integer encoding the walk assembly kernels consume.
+
+CPU only. The walk re-orders the cells of a row so that consecutive cells share vertices and the
+kernel keeps them in registers; these tests check that
+  * every step word decodes to a cell of the row and every cell is visited exactly once;
+  * positions outside the step's mask keep their vertex; the first step loads all three;
+  * the interior star of the Kuhn box (24 cells) is walked with one new vertex per step;
+  * the walk of an owned row is the same on every partition (global vertex labels);
+  * a numpy restatement of the kernel arithmetic driven by the words (register positions, cached
+    cross products, flush-on-replace accumulators, BC epilogue) reproduces the oracle's matrix to
+    1e-12 of the row's diagonal -- this pins the encoding and the cofactor algebra, not the CUDA.
+"""
+import numpy as np
+import pytest
+
+
+def _pair_ptr(P):
+    dm = P["dofmap"]
+    cnt = np.bincount(dm[dm < P.n_owned], minlength=P.n_owned)
+    return np.concatenate([[0], np.cumsum(cnt)]).astype(np.int64)
+
+
+def _row_cells(P):
+    """Per owned row: list of (cell, li) ascending in the pair id cell*4 + li."""
+    dm = P["dofmap"].reshape(-1, 4)
+    out = [[] for _ in range(P.n_owned)]
+    for c in range(dm.shape[0]):
+        for li in range(4):
+            d = dm[c, li]
+            if d < P.n_owned:
+                out[d].append((c, li))
+    return out
+
+
+def _decode(word):
+    return (word & 0xFF, (word >> 8) & 0xFF, (word >> 16) & 0xFF), word >> 24
+
+
+CASES = [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1), ("poisson", (3, 2, 7), 1, 2),
+         ("elasticity", (4, 3, 3), 0, 1)]
+
+
+@pytest.mark.parametrize("ptype,dims,rank,nranks", CASES)
+def test_walk_visits_every_cell_once(pt, ptype, dims, rank, nranks):
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    words, lps = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    ptr, rp, cl = _pair_ptr(P), P["rowptr"], P["cols"]
+    dm = P["dofmap"].reshape(-1, 4)
+    cells = _row_cells(P)
+    assert len(words) == ptr[-1]
+    assert 1.0 <= lps <= 3.0
+    for r in range(P.n_owned):
+        want = sorted(tuple(sorted(int(dm[c, (li + t) & 3]) for t in (1, 2, 3))) for c, li in cells[r])
+        got, prev = [], None
+        for k in range(ptr[r], ptr[r + 1]):
+            pos, mask = _decode(int(words[k]))
+            assert mask <= 7
+            if prev is None:
+                assert mask == 7
+            else:
+                for p in range(3):
+                    if not (mask >> p) & 1:
+                        assert pos[p] == prev[p]
+            assert all(o < rp[r + 1] - rp[r] for o in pos)
+            got.append(tuple(sorted(int(cl[rp[r] + o]) for o in pos)))
+            prev = pos
+        assert sorted(got) == want
+
+
+def test_interior_star_is_walked_one_vertex_per_step(pt):
+    P = pt.host.Problem("poisson", 1, 4, 4, 4)
+    words, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    ptr = _pair_ptr(P)
+    n24 = 0
+    for r in range(P.n_owned):
+        if ptr[r + 1] - ptr[r] == 24:
+            masks = [int(w) >> 24 for w in words[ptr[r]:ptr[r + 1]]]
+            assert masks[0] == 7 and all(m in (1, 2, 4) for m in masks[1:])
+            n24 += 1
+    assert n24 == 27
+
+
+def test_walk_is_partition_independent(pt):
+    dims = (3, 4, 6)
+    G = pt.host.Problem("poisson", 1, *dims)
+    wg, _ = pt.abi.star_walk(G["dofmap"], G.n_owned, G["rowptr"], G["cols"])
+    pg, rpg, clg = _pair_ptr(G), G["rowptr"], G["cols"]
+    for rank in range(3):
+        P = pt.host.Problem("poisson", 1, *dims, rank, 3)
+        w, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+        ptr, rp, cl = _pair_ptr(P), P["rowptr"], P["cols"]
+        glob = np.concatenate([P.global_offset + np.arange(P.n_owned), P["ghost_global"]])
+        for r in range(P.n_owned):
+            R = int(glob[r])
+            assert ptr[r + 1] - ptr[r] == pg[R + 1] - pg[R]
+            for k in range(ptr[r + 1] - ptr[r]):
+                pos, mask = _decode(int(w[ptr[r] + k]))
+                posg, maskg = _decode(int(wg[pg[R] + k]))
+                assert mask == maskg
+                assert [int(glob[cl[rp[r] + o]]) for o in pos] == [int(clg[rpg[R] + o]) for o in posg]
+
+
+def _emulate_poisson(P, words):
+    """The walk kernel's arithmetic, lane by lane, in numpy (assemble_walk.cu, BS = 1)."""
+    ptr, rp, cl = _pair_ptr(P), P["rowptr"], P["cols"]
+    X = P["dof_x"].reshape(-1, 3)
+    bc = np.zeros(P.n_owned + P.n_ghost, bool)
+    bc[P["bc_dofs"]] = True
+    vals = np.zeros(rp[-1])
+    for r in range(P.n_owned):
+        w = int(rp[r + 1] - rp[r])
+        E = X[cl[rp[r]:rp[r + 1]]] - X[r]
+        acc = np.zeros(w)
+        s = [0, 0, 0]
+        e = [np.zeros(3)] * 3
+        n = [np.zeros(3)] * 3
+        a = [0.0, 0.0, 0.0]
+        dg = 0.0
+        for k in range(ptr[r], ptr[r + 1]):
+            pos, mask = _decode(int(words[k]))
+            for p in range(3):
+                if (mask >> p) & 1:
+                    acc[s[p]] += a[p]
+                    s[p], e[p], a[p] = pos[p], E[pos[p]], 0.0
+            if mask & 6:
+                n[0] = np.cross(e[1], e[2])
+            if mask & 5:
+                n[1] = np.cross(e[2], e[0])
+            if mask & 3:
+                n[2] = np.cross(e[0], e[1])
+            det = e[0] @ n[0]
+            rinv = 1.0 / (6.0 * abs(det))
+            c0 = -(n[0] + n[1] + n[2])
+            dg += rinv * (c0 @ c0)
+            for p in range(3):
+                a[p] += rinv * (c0 @ n[p])
+        for p in range(3):
+            acc[s[p]] += a[p]
+        for k in range(w):
+            col = cl[rp[r] + k]
+            v = dg if col == r else acc[k]
+            if bc[r] or bc[col]:
+                v = 1.0 if col == r else 0.0
+            vals[rp[r] + k] = v
+    return vals
+
+
+@pytest.mark.parametrize("dims,rank,nranks", [((5, 4, 6), 0, 1), ((1, 1, 1), 0, 1), ((4, 3, 5), 1, 2)])
+def test_walk_arithmetic_reproduces_the_oracle_matrix(pt, oracle, dims, rank, nranks):
+    P = pt.host.Problem("poisson", 1, *dims, rank, nranks)
+    words, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    got = _emulate_poisson(P, words)
+    ref = oracle.assemble_matrix(P)
+    rows = np.repeat(np.arange(P.n_owned), np.diff(P["rowptr"]))
+    diag = np.zeros(P.n_owned)
+    d = P["cols"] == rows
+    diag[rows[d]] = np.abs(ref[d])
+    err = np.abs(got - ref) / diag[rows]
+    assert err.max() <= 1e-12
