@@ -12,6 +12,13 @@ using namespace ptb;
 
 namespace
 {
+// Star-walk assembly (assemble_walk.cu): PTB_ASM_WALK=1/0 overrides the built-in default.
+constexpr bool kWalkDefault = true;
+bool walk_enabled()
+{
+  const char* env = std::getenv("PTB_ASM_WALK");
+  return env && env[0] ? env[0] == '1' : kWalkDefault;
+}
 thread_local std::string g_err;
 
 template <typename F>
@@ -303,7 +310,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->adjso.upload(L.adjso, c->stream);
     }
     c->walk.release();
-    if (const char* env = std::getenv("PTB_ASM_WALK"); env && env[0] == '1' && !L.adjrot.empty())
+    if (walk_enabled() && c->bs == 1 && !L.adjrot.empty() && L.max_w <= 32)
     {
       // opt-in: star-walk assembly kernels (assemble_walk.cu)
       const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);

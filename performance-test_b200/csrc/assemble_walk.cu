@@ -15,17 +15,28 @@
 //   element   det = e_0 . n_0, c_own = -(n_0 + n_1 + n_2), a_p += c_own . n_p / (6 |det|)
 // The step is branch-free (predicated reloads), so the unrolled chunk of steps schedules as one
 // block. Shared memory is private per lane (column `lane` of E and acc): no barrier anywhere.
-// Opt-in with PTB_ASM_WALK=1 until it has been measured against assemble_matrix_p1.
+// Default for scalar P1 (measured x1.48 against assemble_matrix_p1<1>, profiles/r01_walk_*);
+// PTB_ASM_WALK=0 selects the older kernel.
 #include "geom.cuh"
 #include "kernels.h"
+#include <cstdlib>
 
 namespace ptb
 {
 namespace
 {
 
-constexpr int WALK_WARPS = 2; // slices per CTA: 2 x 15.4 KB (w = 15) -> 7 CTAs = 14 warps per SM
+// Slices per CTA = template parameter WARPS (15.4 KB of shared memory per slice at w = 15).
+// Measured at 4 M DOFs (ms, prefetch off/on): 1 warp 0.613/0.599, 2 warps 0.660/0.642,
+// 4 warps 0.699/0.687, 7 warps 0.702/0.684 -> one-warp CTAs with the L2 prefetch are the default.
 constexpr int WALK_CHUNK = 8; // step words in flight per thread
+// L2 prefetch distance in slices: about two generations of resident warps (148 SMs x 14 warps).
+constexpr int WALK_PF_DIST = 4096;
+
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
 
 // 1/d for a normal, finite d: MUFU seed + one cubic and one quadratic Newton step, no slow path
 // (the element volume of a valid mesh is never denormal), so the step has no branch.
@@ -49,9 +60,11 @@ struct WalkState
   std::uint32_t prev; // previous step word (bytes 0..2: columns the positions accumulate into)
 };
 
-__global__ void __launch_bounds__(WALK_WARPS * 32, 7)
+template <int WARPS, bool PREFETCH>
+__global__ void __launch_bounds__(WARPS * 32, 14 / WARPS)
 assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
 {
+  constexpr int WALK_WARPS = WARPS;
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const std::int32_t slice = blockIdx.x * WALK_WARPS + warp;
@@ -75,6 +88,26 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
   const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
   const bool bc_row = live && A.bc[row];
   const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+
+  if constexpr (PREFETCH)
+  {
+    // Pull the streams of a slice two warp generations ahead into L2: its column indices and
+    // step words (one 128-byte line per lane), row pointers and coordinates. The widths of that
+    // slice are taken to be this slice's (a hint only: wrong guesses cost nothing but bandwidth).
+    const std::int32_t s2 = slice + WALK_PF_DIST;
+    if (s2 < A.n_slices)
+    {
+      const std::int64_t mo2 = A.mat_off[s2], ao2 = A.adj_off[s2];
+      if (lane < w)
+        prefetch_l2(A.cols + mo2 + lane * 32);
+      if (lane < wa)
+        prefetch_l2(walk + ao2 + lane * 32);
+      if (lane < 8)
+        prefetch_l2(A.xdof + (static_cast<std::int64_t>(s2) * 32 + lane * 4) * 4);
+      if (lane < 2)
+        prefetch_l2(A.rowptr + static_cast<std::int64_t>(s2) * 32 + lane * 16);
+    }
+  }
 
   std::uint32_t bcmask = 0; // bit k: column k of the row is constrained
   int own = -1;             // position of the diagonal in the row
@@ -193,20 +226,43 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
 
 } // namespace
 
+namespace
+{
+template <int WARPS, bool PREFETCH>
+bool launch_walk(ptb_ctx* c, const MatrixArgs& A)
+{
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * WARPS * sizeof(double);
+  if (smem > 227 * 1024)
+    return false;
+  auto kernel = assemble_matrix_p1_walk<WARPS, PREFETCH>;
+  PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->walk.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return true;
+}
+int env_int(const char* name, int dflt)
+{
+  const char* e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+} // namespace
+
 bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A)
 {
   if (c->order != 1 || c->bs != 1 || c->walk.p == nullptr || c->max_w > 32)
     return false;
-  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * WALK_WARPS * sizeof(double);
-  if (smem > 227 * 1024)
-    return false;
-  PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_p1_walk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(smem)));
-  assemble_matrix_p1_walk<<<(A.n_slices + WALK_WARPS - 1) / WALK_WARPS, WALK_WARPS * 32, smem,
-                            c->stream>>>(A, c->walk.p);
-  PTB_CUDA(cudaGetLastError());
-  c->launches += 1;
-  return true;
+  // tuning knobs of the opt-in path (A/B on the GPU): slices per CTA and the L2 prefetch
+  const int warps = env_int("PTB_WALK_WARPS", 1);
+  const bool pf = env_int("PTB_WALK_PREFETCH", 1) != 0;
+  switch (warps)
+  {
+  case 1: return pf ? launch_walk<1, true>(c, A) : launch_walk<1, false>(c, A);
+  case 4: return pf ? launch_walk<4, true>(c, A) : launch_walk<4, false>(c, A);
+  case 7: return pf ? launch_walk<7, true>(c, A) : launch_walk<7, false>(c, A);
+  default: return pf ? launch_walk<2, true>(c, A) : launch_walk<2, false>(c, A);
+  }
 }
 
 } // namespace ptb

@@ -1,0 +1,99 @@
+"""GPU smoke + A/B of the opt-in star-walk assembly kernel (PTB_ASM_WALK=1) against the default
+kernel. Small parity case first, then one timing case; results are appended to
+gpurun_out/walk_check.json after every stage so that a cut-off run still leaves evidence.
+
+    python performance-test_b200/tools/check_walk.py [ndofs_for_timing]
+"""
+import importlib
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+pt = importlib.import_module("performance-test_b200")
+OUT = os.path.join(ROOT, "gpurun_out", os.environ.get("WALK_CHECK_OUT", "walk_check.json"))
+res = {}
+
+
+def dump():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    with open(OUT, "w") as f:
+        json.dump(res, f, indent=1)
+    print(json.dumps(res), flush=True)
+
+
+def assemble(P, walk):
+    if walk:
+        os.environ["PTB_ASM_WALK"] = "1"
+    else:
+        os.environ.pop("PTB_ASM_WALK", None)
+    c = pt.abi.Context(0)
+    c.set_problem(P)
+    c.assemble_matrix()
+    return c
+
+
+def ab(ndofs):
+    """One walk context; launch-time knobs (PTB_WALK_WARPS, PTB_WALK_PREFETCH) varied in place."""
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    c = assemble(P, True)
+    res["ab_case"] = {"n_owned": P.n_owned, "nnz": P.nnz}
+    for warps in (2, 1, 4, 7):
+        for pf in (0, 1):
+            os.environ["PTB_WALK_WARPS"], os.environ["PTB_WALK_PREFETCH"] = str(warps), str(pf)
+            res[f"ms_warps{warps}_pf{pf}"] = c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 5)
+            dump()
+    c.close()
+
+
+def ncu_target(ndofs):
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    assemble(P, True).close()
+
+
+def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "ab":
+        return ab(int(sys.argv[2]))
+    if len(sys.argv) > 2 and sys.argv[1] == "ncu":
+        return ncu_target(int(sys.argv[2]))
+    t0 = time.time()
+    for dims in [(5, 4, 6), (16, 15, 17)]:
+        P = pt.host.Problem("poisson", 1, *dims)
+        c0, c1 = assemble(P, False), assemble(P, True)
+        a0, a1 = c0.matrix_values(), c1.matrix_values()
+        d0, d1 = c0.diagonal_inverse(), c1.diagonal_inverse()
+        scale = np.abs(a0).max()
+        res[f"parity_{dims}"] = {"max_abs_diff_over_max": float(np.abs(a0 - a1).max() / scale),
+                                 "dinv_rel": float(np.abs(d0 / d1 - 1).max()),
+                                 "nan": bool(np.isnan(a1).any())}
+        c0.close(), c1.close()
+        dump()
+    ndofs = int(sys.argv[1]) if len(sys.argv) > 1 else 4_000_000
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    res["timing_case"] = {"n_owned": P.n_owned, "nnz": P.nnz, "setup_s": time.time() - t0}
+    dump()
+    for walk in (False, True):
+        c = assemble(P, walk)
+        ms = c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 5)
+        res[f"assemble_matrix_ms_walk{int(walk)}"] = ms
+        res[f"gnnz_per_s_walk{int(walk)}"] = P.nnz / ms / 1e6
+        if walk:
+            res["checksum_walk"] = float(np.abs(c.matrix_values()).sum())
+        else:
+            res["checksum_default"] = float(np.abs(c.matrix_values()).sum())
+        c.close()
+        dump()
+
+
+if __name__ == "__main__":
+    main()

@@ -293,3 +293,21 @@ print("variants ok")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
                        env=env)
     assert r.returncode == 0 and "variants ok" in r.stdout, r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dims", [(5, 4, 6), (1, 1, 1), (16, 15, 17), (33, 3, 2)])
+def test_star_walk_and_cell_order_kernels_agree(pt, dims, monkeypatch):
+    """Scalar P1: the default star-walk kernel and the ascending-cell-order kernel
+    (PTB_ASM_WALK=0) assemble the same matrix and Jacobi diagonal (both are checked against the
+    oracle above; this pins them to each other at rounding level)."""
+    P = pt.host.Problem("poisson", 1, *dims)
+    out = {}
+    for walk in ("1", "0"):
+        monkeypatch.setenv("PTB_ASM_WALK", walk)
+        c = pt.abi.Context(0)
+        c.set_problem(P)
+        c.assemble_matrix()
+        out[walk] = (c.matrix_values(), c.diagonal_inverse())
+        c.close()
+    _check_matrix(P, out["1"][0], out["0"][0])
+    assert np.allclose(out["1"][1], out["0"][1], rtol=1e-13, atol=0)
