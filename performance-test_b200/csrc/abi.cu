@@ -19,6 +19,12 @@ bool walk_enabled()
   const char* env = std::getenv("PTB_ASM_WALK");
   return env && env[0] ? env[0] == '1' : kWalkDefault;
 }
+// Elasticity walk kernel: written after the round's GPU budget was spent, never run -> opt-in.
+bool walk3_enabled()
+{
+  const char* env = std::getenv("PTB_ASM_WALK3");
+  return env && env[0] == '1';
+}
 thread_local std::string g_err;
 
 template <typename F>
@@ -310,7 +316,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->adjso.upload(L.adjso, c->stream);
     }
     c->walk.release();
-    if (walk_enabled() && c->bs == 1 && !L.adjrot.empty() && L.max_w <= 32)
+    if (!L.adjrot.empty() && ((c->bs == 1 && walk_enabled() && L.max_w <= 32) || (c->bs == 3 && walk3_enabled())))
     {
       // opt-in: star-walk assembly kernels (assemble_walk.cu)
       const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);

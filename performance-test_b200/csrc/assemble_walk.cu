@@ -19,6 +19,7 @@
 // PTB_ASM_WALK=0 selects the older kernel.
 #include "geom.cuh"
 #include "kernels.h"
+#include <climits>
 #include <cstdlib>
 
 namespace ptb
@@ -224,6 +225,194 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
     A.dinv[row] = 1.0 / diag;
 }
 
+// ------------------------------------------------------------------------------------------
+// Elasticity (BS = 3) along the same walk. CTA = one slice = three warps; warp a accumulates row a
+// of the raw tensor  T_j = sum_cells c_own (x) c_j / (6|det|)  per neighbour j (three accumulators
+// per register position), and the material law (Elasticity.py:12-15, 33-39) is applied once per
+// stored block in the epilogue:   block[a][b] = mu (delta_ab tr T + T[b][a]) + lambda T[a][b],
+// which reads the other two warps' rows of T from shared memory. Per (row, cell) and warp this is
+// 40 FP64 instructions instead of ~93 (geometry 27 + q = c_own[a]/(6|det|) + 4 x 3 FMAs).
+// Shared memory per slice: E [3w][32] (shared star), T [3][3w][32], DG [9][32] (own block),
+// C [w][32] int32 columns with the Dirichlet flag in the top bit.
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): opt-in, PTB_ASM_WALK3=1.
+// ------------------------------------------------------------------------------------------
+template <bool PREFETCH>
+__global__ void __launch_bounds__(96, 4)
+assemble_matrix_p1_walk3(MatrixArgs A, const std::uint32_t* __restrict__ walk)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, a = threadIdx.x >> 5; // a = component row handled by this warp
+  const std::int32_t slice = blockIdx.x;
+  const std::int64_t mo = A.mat_off[slice], ao = A.adj_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const int mw = A.max_w;
+
+  double* E = smem + lane;                                  // E[(k*3+d)*32]
+  double* Tall = smem + mw * 3 * 32 + lane;                 // Tall[(x*mw*3 + k*3 + y)*32] = T_k[x][y]
+  double* T = Tall + a * (mw * 3 * 32);                     // this warp's row a
+  double* DG = smem + mw * 12 * 32 + lane;                  // DG[(x*3+y)*32]
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem + mw * 12 * 32 + 9 * 32) + lane; // C[k*32]
+
+  const std::uint32_t* wp = walk + ao + lane;
+  std::uint32_t wd[WALK_CHUNK];
+#pragma unroll
+  for (int j = 0; j < WALK_CHUNK; ++j)
+    wd[j] = j < wa ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+
+  if constexpr (PREFETCH)
+  {
+    const std::int32_t s2 = slice + WALK_PF_DIST / 3;
+    if (s2 < A.n_slices && a == 0)
+    {
+      const std::int64_t mo2 = A.mat_off[s2], ao2 = A.adj_off[s2];
+      if (lane < w)
+        prefetch_l2(A.cols + mo2 + lane * 32);
+      if (lane < wa)
+        prefetch_l2(walk + ao2 + lane * 32);
+      if (lane < 8)
+        prefetch_l2(A.xdof + (static_cast<std::int64_t>(s2) * 32 + lane * 4) * 4);
+      if (lane < 2)
+        prefetch_l2(A.rowptr + static_cast<std::int64_t>(s2) * 32 + lane * 16);
+    }
+  }
+
+  // ---- star: warp a stages columns a, a+3, ...; every warp clears its own row of T -----------
+  for (int k0 = a; k0 < w; k0 += 3 * WALK_CHUNK)
+  {
+    std::int32_t c[WALK_CHUNK];
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      c[j] = k0 + 3 * j < w ? __ldg(A.cols + mo + (k0 + 3 * j) * 32 + lane) : -1;
+    Vec3 x[WALK_CHUNK];
+    std::uint8_t b[WALK_CHUNK];
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        x[j] = load_point(A.xdof, c[j]);
+        b[j] = __ldg(A.bc + c[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        const int k = k0 + 3 * j;
+        const Vec3 d = x[j] - X0;
+        E[(k * 3 + 0) * 32] = d.x;
+        E[(k * 3 + 1) * 32] = d.y;
+        E[(k * 3 + 2) * 32] = d.z;
+        C[k * 32] = c[j] | (b[j] ? INT32_MIN : 0);
+      }
+  }
+  for (int k = 0; k < 3 * w; ++k)
+    T[k * 32] = 0.0;
+  __syncthreads();
+
+  // ---- walk ---------------------------------------------------------------------------------
+  Vec3 e0{0.0, 0.0, 0.0}, e1 = e0, e2 = e0, n0 = e0, n1 = e0, n2 = e0;
+  Vec3 t0 = e0, t1 = e0, t2 = e0, dg = e0; // row a of the tensor accumulators (x, y, z = b)
+  std::uint32_t prev = 0;
+  auto flush = [&](int slot, Vec3& t) {
+    T[(slot * 3 + 0) * 32] += t.x;
+    T[(slot * 3 + 1) * 32] += t.y;
+    T[(slot * 3 + 2) * 32] += t.z;
+    t = Vec3{0.0, 0.0, 0.0};
+  };
+  auto edge = [&](int o) { return Vec3{E[(o * 3 + 0) * 32], E[(o * 3 + 1) * 32], E[(o * 3 + 2) * 32]}; };
+  auto step = [&](std::uint32_t word) {
+    const bool valid = word != ADJ_INVALID_DEV;
+    word = valid ? word : (prev & 0x00FFFFFFu);
+    const bool l0 = word & (1u << 24), l1 = word & (2u << 24), l2 = word & (4u << 24);
+    if (l0)
+    {
+      flush(prev & 0xFFu, t0);
+      e0 = edge(word & 0xFFu);
+    }
+    if (l1)
+    {
+      flush((prev >> 8) & 0xFFu, t1);
+      e1 = edge((word >> 8) & 0xFFu);
+    }
+    if (l2)
+    {
+      flush((prev >> 16) & 0xFFu, t2);
+      e2 = edge((word >> 16) & 0xFFu);
+    }
+    if (l1 || l2)
+      n0 = cross(e1, e2);
+    if (l2 || l0)
+      n1 = cross(e2, e0);
+    if (l0 || l1)
+      n2 = cross(e0, e1);
+    const double det = dot(e0, n0);
+    const double r = valid ? rcp_fast(6.0 * fabs(det)) : 0.0;
+    const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
+    const double q = r * comp(c0, a);
+    dg = Vec3{fma(q, c0.x, dg.x), fma(q, c0.y, dg.y), fma(q, c0.z, dg.z)};
+    t0 = Vec3{fma(q, n0.x, t0.x), fma(q, n0.y, t0.y), fma(q, n0.z, t0.z)};
+    t1 = Vec3{fma(q, n1.x, t1.x), fma(q, n1.y, t1.y), fma(q, n1.z, t1.z)};
+    t2 = Vec3{fma(q, n2.x, t2.x), fma(q, n2.y, t2.y), fma(q, n2.z, t2.z)};
+    prev = word;
+  };
+  for (int k0 = 0; k0 < wa; k0 += WALK_CHUNK)
+  {
+    std::uint32_t nx[WALK_CHUNK];
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      nx[j] = k0 + WALK_CHUNK + j < wa ? __ldg(wp + (k0 + WALK_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      step(wd[j]);
+#pragma unroll
+    for (int j = 0; j < WALK_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  flush(prev & 0xFFu, t0);
+  flush((prev >> 8) & 0xFFu, t1);
+  flush((prev >> 16) & 0xFFu, t2);
+  DG[(a * 3 + 0) * 32] = dg.x;
+  DG[(a * 3 + 1) * 32] = dg.y;
+  DG[(a * 3 + 2) * 32] = dg.z;
+  __syncthreads();
+
+  // ---- epilogue: material law per stored block, BC rows/cols, one write per value -----------
+  constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
+  constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const std::int32_t cw = C[k * 32];
+    const bool real = k < len;
+    const bool own = real && (cw & INT32_MAX) == row;
+    const bool bc_any = bc_row || (real && cw < 0);
+    // entry [x][y] of the block's raw tensor: the own block lives in DG, the others in T of warp x
+    auto Txy = [&](int x, int y) {
+      return own ? DG[(x * 3 + y) * 32] : Tall[(x * mw * 3 + k * 3 + y) * 32];
+    };
+    const double tr = Txy(0, 0) + Txy(1, 1) + Txy(2, 2);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+    {
+      double val = mu * ((a == b ? tr : 0.0) + Txy(b, a)) + lmbda * Txy(a, b);
+      if (bc_any)
+        val = (own && a == b) ? 1.0 : 0.0;
+      if (!real)
+        val = 0.0;
+      A.vals[(mo + k * 32) * 9 + (a * 3 + b) * 32 + lane] = val;
+      if (own && a == b)
+        diag = val;
+    }
+  }
+  if (live)
+    A.dinv[static_cast<std::int64_t>(row) * 3 + a] = 1.0 / diag;
+}
+
 } // namespace
 
 namespace
@@ -251,7 +440,25 @@ int env_int(const char* name, int dflt)
 
 bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A)
 {
-  if (c->order != 1 || c->bs != 1 || c->walk.p == nullptr || c->max_w > 32)
+  if (c->order != 1 || c->walk.p == nullptr)
+    return false;
+  if (c->bs == 3)
+  {
+    const std::size_t smem
+        = (static_cast<std::size_t>(c->max_w) * 12 * 32 + 9 * 32) * sizeof(double)
+          + static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t);
+    if (smem > 227 * 1024)
+      return false;
+    const bool pf = env_int("PTB_WALK_PREFETCH", 1) != 0;
+    auto kernel = pf ? assemble_matrix_p1_walk3<true> : assemble_matrix_p1_walk3<false>;
+    PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    kernel<<<A.n_slices, 96, smem, c->stream>>>(A, c->walk.p);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return true;
+  }
+  if (c->bs != 1 || c->max_w > 32)
     return false;
   // tuning knobs of the opt-in path (A/B on the GPU): slices per CTA and the L2 prefetch
   const int warps = env_int("PTB_WALK_WARPS", 1);

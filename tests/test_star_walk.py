@@ -157,3 +157,69 @@ def test_walk_arithmetic_reproduces_the_oracle_matrix(pt, oracle, dims, rank, nr
     diag[rows[d]] = np.abs(ref[d])
     err = np.abs(got - ref) / diag[rows]
     assert err.max() <= 1e-12
+
+
+def _emulate_elasticity(P, words):
+    """The elasticity walk kernel (assemble_walk.cu, BS = 3): per neighbour the raw tensor
+    T = sum_cells c_own (x) c_t / (6|det|) is accumulated along the walk, the material law
+    (Elasticity.py:12-15, :33-39) is applied once per stored block in the epilogue:
+    block[a][b] = mu (delta_ab tr T + T[b][a]) + lambda T[a][b]."""
+    E_mod, nu = 1.0e6, 0.3
+    mu = E_mod / (2.0 * (1.0 + nu))
+    lmbda = E_mod * nu / ((1.0 + nu) * (1.0 - 2.0 * nu))
+    ptr, rp, cl = _pair_ptr(P), P["rowptr"], P["cols"]
+    X = P["dof_x"].reshape(-1, 3)
+    bc = np.zeros(P.n_owned + P.n_ghost, bool)
+    bc[P["bc_dofs"]] = True
+    vals = np.zeros((rp[-1], 3, 3))
+    for r in range(P.n_owned):
+        w = int(rp[r + 1] - rp[r])
+        E = X[cl[rp[r]:rp[r + 1]]] - X[r]
+        acc = np.zeros((w, 3, 3))
+        s = [0, 0, 0]
+        e = [np.zeros(3)] * 3
+        n = [np.zeros(3)] * 3
+        a = [np.zeros((3, 3)) for _ in range(3)]
+        dg = np.zeros((3, 3))
+        for k in range(ptr[r], ptr[r + 1]):
+            pos, mask = _decode(int(words[k]))
+            for p in range(3):
+                if (mask >> p) & 1:
+                    acc[s[p]] += a[p]
+                    s[p], e[p], a[p] = pos[p], E[pos[p]], np.zeros((3, 3))
+            if mask & 6:
+                n[0] = np.cross(e[1], e[2])
+            if mask & 5:
+                n[1] = np.cross(e[2], e[0])
+            if mask & 3:
+                n[2] = np.cross(e[0], e[1])
+            rinv = 1.0 / (6.0 * abs(e[0] @ n[0]))
+            c0 = -(n[0] + n[1] + n[2])
+            q = rinv * c0
+            dg += np.outer(q, c0)
+            for p in range(3):
+                a[p] += np.outer(q, n[p])
+        for p in range(3):
+            acc[s[p]] += a[p]
+        for k in range(w):
+            col = cl[rp[r] + k]
+            T = dg if col == r else acc[k]
+            B = mu * (np.trace(T) * np.eye(3) + T.T) + lmbda * T
+            if bc[r] or bc[col]:
+                B = np.eye(3) if col == r else np.zeros((3, 3))
+            vals[rp[r] + k] = B
+    return vals.reshape(-1)
+
+
+@pytest.mark.parametrize("dims,rank,nranks", [((4, 3, 5), 0, 1), ((1, 1, 2), 0, 1), ((3, 3, 4), 1, 2)])
+def test_walk_tensor_accumulation_reproduces_the_oracle_elasticity_matrix(pt, oracle, dims, rank, nranks):
+    P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+    words, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    got = _emulate_elasticity(P, words).reshape(-1, 9)
+    ref = oracle.assemble_matrix(P).reshape(-1, 9)
+    rows = np.repeat(np.arange(P.n_owned), np.diff(P["rowptr"]))
+    diag = np.zeros(P.n_owned)
+    d = P["cols"] == rows
+    diag[rows[d]] = np.abs(ref[d]).max(axis=1)
+    err = np.abs(got - ref).max(axis=1) / diag[rows]
+    assert err.max() <= 1e-12
