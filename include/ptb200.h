@@ -145,6 +145,15 @@ int ptb_debug_star_walk(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
                         const int64_t* rowptr, const int32_t* cols, uint32_t* walk_out,
                         double* loads_per_step);
 
+/* The single-reload form of the walk (one new vertex per step; SellLayout::walk1): step_ptr
+ * [n_owned + 1] receives the per-row step offsets, words (may be NULL to query sizes) the step
+ * words row by row. Step 0 of a row has the walk format; later steps: byte 0 = offset of the new
+ * vertex, byte 1 = offset of the evicted vertex, bits 16-17 = register position (3 = none),
+ * bit 18 = a cell is complete after the step. Host only. */
+int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                               const int64_t* rowptr, const int32_t* cols, int64_t* step_ptr,
+                               uint32_t* words);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

@@ -71,6 +71,7 @@ def lib():
         L.ptb_debug_layout_roundtrip.argtypes = [i32, i64, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
+        L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
         L.ptb_stage_ms.restype = dbl
@@ -116,6 +117,21 @@ def star_walk(dofmap, n_owned, rowptr, cols):
     if rc != 0:
         raise RuntimeError(lib().ptb_last_error(None).decode())
     return out, lps.value
+
+
+def star_walk_single(dofmap, n_owned, rowptr, cols):
+    """Host-only: the one-vertex-per-step walk; returns (step_ptr [n_owned+1], words)."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    n_cells = len(dm) // 4
+    ptr = np.zeros(n_owned + 1, dtype=np.int64)
+    for words in (None, "alloc"):
+        if words is not None:
+            words = np.zeros(int(ptr[-1]), dtype=np.uint32)
+        rc = lib().ptb_debug_star_walk_single(n_cells, _ptr(dm), n_owned, _ptr(rp), _ptr(cl),
+                                              _ptr(ptr), _ptr(words))
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+    return ptr, words
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

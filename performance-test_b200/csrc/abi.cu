@@ -25,6 +25,11 @@ bool walk3_enabled()
   const char* env = std::getenv("PTB_ASM_WALK3");
   return env && env[0] == '1';
 }
+bool gwalk_enabled()
+{
+  const char* env = std::getenv("PTB_ASM_GWALK");
+  return env && env[0] == '1';
+}
 thread_local std::string g_err;
 
 template <typename F>
@@ -86,7 +91,7 @@ std::int64_t ptb_ctx::device_bytes() const
 {
   return xyz.bytes() + xyz3.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
-         + adjso.bytes() + adjrot.bytes() + walk.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + adjso.bytes() + adjrot.bytes() + walk.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
          + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes()
@@ -322,6 +327,16 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);
       c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
       c->walk.upload(L.walk, c->stream);
+    }
+    c->walk1.release(), c->walk1_off.release();
+    if (gwalk_enabled() && !L.adjrot.empty() && (c->bs == 3 || L.max_w <= 32))
+    {
+      // opt-in: one-vertex-per-step walk for the direct-gather kernels (assemble_gwalk.cu)
+      if (L.walk.empty())
+        build_walk(N, c->h_adj, c->h_so, L);
+      build_walk_single(N, c->h_adj, L);
+      c->walk1.upload(L.walk1, c->stream);
+      c->walk1_off.upload(L.walk1_off, c->stream);
     }
     {
       // visiting order of the operator kernels (ghost-reading slices last, clustered groups)
@@ -758,6 +773,37 @@ int ptb_debug_star_walk(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
         walk_out[adj.ptr[r] + k] = L.walk[L.adj_off[r >> 5] + k * 32 + (r & 31)];
     if (loads_per_step)
       *loads_per_step = st.steps ? static_cast<double>(st.loads) / st.steps : 0.0;
+  });
+}
+
+int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                               const int64_t* rowptr, const int32_t* cols, int64_t* step_ptr,
+                               uint32_t* words)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && step_ptr, "ptb_debug_star_walk_single: NULL argument");
+    RowAdjacency adj;
+    std::vector<std::uint16_t> so;
+    build_row_adjacency(dofmap, n_cells, 4, n_owned, adj);
+    const std::int64_t max_so = build_slot_offsets(dofmap, 4, n_owned, adj, rowptr, cols, so);
+    need(max_so >= 0 && max_so < 255, "ptb_debug_star_walk_single: pattern does not cover the cells / row too long");
+    SellLayout L;
+    build_sell_layout(n_owned, 4, rowptr, cols, adj, so, max_so, L);
+    build_walk(n_owned, adj, so, L);
+    build_walk_single(n_owned, adj, L);
+    step_ptr[0] = 0;
+    for (std::int32_t r = 0; r < n_owned; ++r)
+    {
+      const std::int64_t base = L.walk1_off[r >> 5] + (r & 31);
+      const std::int64_t w1 = (L.walk1_off[(r >> 5) + 1] - L.walk1_off[r >> 5]) / 32;
+      std::int64_t n = 0;
+      while (n < w1 && L.walk1[base + n * 32] != ADJ_INVALID)
+        ++n;
+      if (words)
+        for (std::int64_t k = 0; k < n; ++k)
+          words[step_ptr[r] + k] = L.walk1[base + k * 32];
+      step_ptr[r + 1] = step_ptr[r] + n;
+    }
   });
 }
 

@@ -555,7 +555,7 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
     return launch_assemble_matrix_pk(c, A);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
-  if (launch_assemble_matrix_walk(c, A))
+  if (launch_assemble_matrix_gwalk(c, A) || launch_assemble_matrix_walk(c, A))
     return;
   if (c->bs == 1)
   {
@@ -581,6 +581,16 @@ void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
     return launch_assemble_vector_pk(c, A, F);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_vector: a P1 row has more than 254 columns");
+  if (launch_assemble_vector_gwalk(c, A))
+  {
+    if (F.n_frows > 0 && F.g != nullptr)
+    {
+      assemble_facets_p1<<<(F.n_frows + 127) / 128, 128, 0, c->stream>>>(F);
+      PTB_CUDA(cudaGetLastError());
+      c->launches += 1;
+    }
+    return;
+  }
   if (c->bs == 1)
   {
     const int spc = MAT_THREADS_1 / 32;

@@ -1,0 +1,405 @@
+// P1 assembly along the one-vertex-per-step star walk (layout.h SellLayout::walk1) with the new
+// vertex gathered straight from the coordinate array a few steps ahead -- third generation of the
+// row-owner gather (assemble.cu -> assemble_walk.cu -> here). Same reference regions:
+//   matrix  fem::assemble_matrix + set_diagonal      poisson_problem.cpp:129-137
+//   vector  fem::assemble_vector + bc->set           poisson_problem.cpp:150-155,
+//                                                    elasticity_problem.cpp:221-229
+//
+// Why: ncu on assemble_matrix_p1_walk (profiles/r01_ncu_full_poisson_assemble_walk_4M.csv) puts
+// 39 % of the stall samples into the prologue that stages the row star in shared memory
+// (mat_off -> columns -> coordinate gather, ~600 instructions, three dependent memory levels), and
+// the staged star (11.5 KB per slice) is what limits the kernel to 3.3 warps per scheduler -- yet
+// along the walk every staged edge vector is read only 1.7 times. Here nothing is staged: shared
+// memory holds the column list (for the gathers) and, for the matrix, the accumulators; step j
+// issues the two 16-byte loads of the vertex that step j + GW_AHEAD brings in, so the gather
+// latency is covered by four steps of arithmetic, and the footprint drops to 5.8 KB (matrix) /
+// 1.9 KB (vector) per slice.
+//
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): opt-in, PTB_ASM_GWALK=1.
+// The step encoding and the arithmetic are pinned on the CPU (tests/test_star_walk.py,
+// test_direct_gather_walk_reproduces_the_oracle).
+#include "geom.cuh"
+#include "kernels.h"
+#include <climits>
+#include <cstdlib>
+
+namespace ptb
+{
+namespace
+{
+
+constexpr int GW_CHUNK = 8; // step words in flight per thread
+constexpr int GW_AHEAD = 4; // gathers in flight per thread (steps of lookahead); divides GW_CHUNK
+
+__device__ __forceinline__ double gw_rcp(double d)
+{
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
+// A vertex in flight: the two 16-byte halves of its padded coordinates (+ the source term).
+template <int NF>
+struct InFlight
+{
+  double2 xy, z_;
+  double f[NF > 0 ? NF : 1];
+};
+
+// Issue the gather of the vertex a later step brings in. Padding / no-load steps fetch offset 0
+// (always a valid column) so the code stays branch-free.
+template <int NF>
+__device__ __forceinline__ InFlight<NF> gw_issue(std::uint32_t word, const std::int32_t* C,
+                                                 const double* __restrict__ xdof,
+                                                 const double* __restrict__ f, int bs, int a)
+{
+  const bool loads = word != ADJ_INVALID_DEV && ((word >> 16) & 3u) != 3u;
+  const int slot = loads ? static_cast<int>(word & 0xFFu) : 0;
+  const std::int64_t col = C[slot * 32];
+  const double2* p = reinterpret_cast<const double2*>(xdof + 4 * col);
+  InFlight<NF> v;
+  v.xy = __ldg(p);
+  v.z_ = __ldg(p + 1);
+  if constexpr (NF > 0)
+    v.f[0] = __ldg(f + col * bs + a);
+  return v;
+}
+
+struct StepBits
+{
+  bool p0, p1, p2, compute;
+  int nw, old;
+};
+__device__ __forceinline__ StepBits gw_decode(std::uint32_t word)
+{
+  const bool valid = word != ADJ_INVALID_DEV;
+  const unsigned pos = valid ? (word >> 16) & 3u : 3u;
+  return {pos == 0u, pos == 1u, pos == 2u, valid && ((word >> 18) & 1u) != 0u,
+          static_cast<int>(word & 0xFFu), static_cast<int>((word >> 8) & 0xFFu)};
+}
+
+// ------------------------------------------------------------------------------------------
+// Matrix, scalar P1. One warp = one slice; no barrier (shared memory is private per lane).
+// Shared memory per slice: C [w][32] int32 columns, acc [w][32] doubles.
+// ------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
+                         const std::int64_t* __restrict__ walk1_off)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * WARPS + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int64_t mo = A.mat_off[slice], so = walk1_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int w1 = static_cast<int>((walk1_off[slice + 1] - so) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const int mw = A.max_w;
+
+  // per slice: acc (mw doubles per lane) then C (mw int32 per lane)
+  double* acc = smem + static_cast<std::size_t>(warp) * (mw * 32 + (mw * 32 + 1) / 2) + lane;
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(acc - lane + mw * 32) + lane;
+
+  // ---- prologue -------------------------------------------------------------------------------
+  const std::uint32_t word0 = w1 > 0 ? __ldg(walk1 + so + lane) : ADJ_INVALID_DEV;
+  const std::uint32_t* wp = walk1 + so + 32 + lane; // step 1
+  const int nsteps = w1 - 1;
+  std::uint32_t wd[GW_CHUNK];
+#pragma unroll
+  for (int j = 0; j < GW_CHUNK; ++j)
+    wd[j] = j < nsteps ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+
+  int own = -1;             // position of the diagonal in the row
+  std::uint32_t bcmask = 0; // bit k: column k is constrained (w <= 32 checked by the launcher)
+  for (int k0 = 0; k0 < w; k0 += 16)
+  {
+    std::int32_t c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+    std::uint8_t b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c[j] >= 0)
+      {
+        const int k = k0 + j;
+        C[k * 32] = c[j];
+        acc[k * 32] = 0.0;
+        own = c[j] == row && k < len ? k : own;
+        b[j] = __ldg(A.bc + c[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c[j] >= 0)
+        bcmask |= b[j] ? 1u << (k0 + j) : 0u;
+  }
+
+  // ---- step 0 (three vertices) and the first GW_AHEAD gathers --------------------------------
+  const bool valid0 = word0 != ADJ_INVALID_DEV;
+  const int o0 = valid0 ? word0 & 0xFFu : 0, o1 = valid0 ? (word0 >> 8) & 0xFFu : 0,
+            o2 = valid0 ? (word0 >> 16) & 0xFFu : 0;
+  Vec3 e0 = load_point(A.xdof, C[o0 * 32]) - X0;
+  Vec3 e1 = load_point(A.xdof, C[o1 * 32]) - X0;
+  Vec3 e2 = load_point(A.xdof, C[o2 * 32]) - X0;
+  InFlight<0> q[GW_AHEAD];
+#pragma unroll
+  for (int j = 0; j < GW_AHEAD; ++j)
+    q[j] = gw_issue<0>(wd[j], C, A.xdof, nullptr, 1, 0);
+  int s0 = o0, s1 = o1, s2 = o2; // offsets the three accumulators belong to
+  Vec3 n0 = cross(e1, e2), n1 = cross(e2, e0), n2 = cross(e0, e1);
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, dg = 0.0;
+  auto cell = [&](bool compute) {
+    const double det = dot(e0, n0);
+    const double r = compute ? gw_rcp(6.0 * fabs(det)) : 0.0;
+    const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
+    dg = fma(r, dot(c0, c0), dg);
+    a0 = fma(r, dot(c0, n0), a0);
+    a1 = fma(r, dot(c0, n1), a1);
+    a2 = fma(r, dot(c0, n2), a2);
+  };
+  cell(valid0);
+
+  // ---- steps 1 .. : one new vertex per step ----------------------------------------------------
+  auto step = [&](std::uint32_t word, const InFlight<0>& v) {
+    const StepBits S = gw_decode(word);
+    const Vec3 xn = {v.xy.x, v.xy.y, v.z_.x};
+    // the subtraction writes the position's registers directly (no moves); one flush per step
+    const double aold = S.p0 ? a0 : (S.p1 ? a1 : a2);
+    if (S.p0 || S.p1 || S.p2)
+      acc[S.old * 32] += aold;
+    if (S.p0)
+      a0 = 0.0, e0 = xn - X0, s0 = S.nw;
+    if (S.p1)
+      a1 = 0.0, e1 = xn - X0, s1 = S.nw;
+    if (S.p2)
+      a2 = 0.0, e2 = xn - X0, s2 = S.nw;
+    if (S.p1 || S.p2)
+      n0 = cross(e1, e2);
+    if (S.p2 || S.p0)
+      n1 = cross(e2, e0);
+    if (S.p0 || S.p1)
+      n2 = cross(e0, e1);
+    cell(S.compute);
+  };
+  for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
+  {
+    std::uint32_t nx[GW_CHUNK]; // next chunk of step words, in flight while this one is walked
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      nx[j] = k0 + GW_CHUNK + j < nsteps ? __ldg(wp + (k0 + GW_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+    {
+      const InFlight<0> cur = q[j % GW_AHEAD];
+      const std::uint32_t ahead = j + GW_AHEAD < GW_CHUNK ? wd[(j + GW_AHEAD) % GW_CHUNK]
+                                                          : nx[(j + GW_AHEAD) % GW_CHUNK];
+      q[j % GW_AHEAD] = gw_issue<0>(ahead, C, A.xdof, nullptr, 1, 0);
+      step(wd[j], cur);
+    }
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  acc[s0 * 32] += a0;
+  acc[s1 * 32] += a1;
+  acc[s2 * 32] += a2;
+
+  // ---- epilogue: BC rows/cols -> 0, BC diagonal -> 1, every stored value written once --------
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const bool real = k < len, is_own = k == own;
+    double val = is_own ? dg : acc[k * 32];
+    if (bc_row || ((bcmask >> k) & 1u))
+      val = is_own ? 1.0 : 0.0;
+    if (!real)
+      val = 0.0;
+    A.vals[mo + k * 32 + lane] = val;
+    diag = is_own ? val : diag;
+  }
+  if (live)
+    A.dinv[row] = 1.0 / diag;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cell vector, P1, BS = 1 or 3: b[row*BS + a] = sum_cells |det|/120 (sum_j f_j + f_own).
+// One warp = (slice, component a); warps are independent (each keeps its own copy of the
+// column list: 1.9 KB), no barrier, no accumulators in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int BS, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
+                         const std::int64_t* __restrict__ walk1_off)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t gw = blockIdx.x * WARPS + warp;
+  const std::int32_t slice = gw / BS;
+  const int a = gw - slice * BS;
+  if (slice >= A.n_slices)
+    return;
+  const std::int64_t mo = A.mat_off[slice], so = walk1_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int w1 = static_cast<int>((walk1_off[slice + 1] - so) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem) + static_cast<std::size_t>(warp) * A.max_w * 32 + lane;
+
+  const std::uint32_t word0 = w1 > 0 ? __ldg(walk1 + so + lane) : ADJ_INVALID_DEV;
+  const std::uint32_t* wp = walk1 + so + 32 + lane;
+  const int nsteps = w1 - 1;
+  std::uint32_t wd[GW_CHUNK];
+#pragma unroll
+  for (int j = 0; j < GW_CHUNK; ++j)
+    wd[j] = j < nsteps ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const bool bc_row = live && A.bc[row];
+  const double f_own = live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < w; k0 += 16)
+  {
+    std::int32_t c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c[j] >= 0)
+        C[(k0 + j) * 32] = c[j];
+  }
+
+  const bool valid0 = word0 != ADJ_INVALID_DEV;
+  const int o0 = valid0 ? word0 & 0xFFu : 0, o1 = valid0 ? (word0 >> 8) & 0xFFu : 0,
+            o2 = valid0 ? (word0 >> 16) & 0xFFu : 0;
+  const std::int64_t c0 = C[o0 * 32], c1 = C[o1 * 32], c2 = C[o2 * 32];
+  Vec3 e0 = load_point(A.xdof, c0) - X0;
+  Vec3 e1 = load_point(A.xdof, c1) - X0;
+  Vec3 e2 = load_point(A.xdof, c2) - X0;
+  double f0 = __ldg(A.f + c0 * BS + a), f1 = __ldg(A.f + c1 * BS + a), f2 = __ldg(A.f + c2 * BS + a);
+  InFlight<1> q[GW_AHEAD];
+#pragma unroll
+  for (int j = 0; j < GW_AHEAD; ++j)
+    q[j] = gw_issue<1>(wd[j], C, A.xdof, A.f, BS, a);
+  double sum = 0.0;
+  auto cell = [&](bool compute) {
+    const double det = dot(e0, cross(e1, e2));
+    const double wgt = compute ? fabs(det) * (1.0 / 120.0) : 0.0;
+    sum = fma(wgt, ((f_own + f0) + (f1 + f2)) + f_own, sum);
+  };
+  cell(valid0);
+  auto step = [&](std::uint32_t word, const InFlight<1>& v) {
+    const StepBits S = gw_decode(word);
+    const Vec3 xn = {v.xy.x, v.xy.y, v.z_.x};
+    if (S.p0)
+      e0 = xn - X0, f0 = v.f[0];
+    if (S.p1)
+      e1 = xn - X0, f1 = v.f[0];
+    if (S.p2)
+      e2 = xn - X0, f2 = v.f[0];
+    cell(S.compute);
+  };
+  for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
+  {
+    std::uint32_t nx[GW_CHUNK];
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      nx[j] = k0 + GW_CHUNK + j < nsteps ? __ldg(wp + (k0 + GW_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+    {
+      const InFlight<1> cur = q[j % GW_AHEAD];
+      const std::uint32_t ahead = j + GW_AHEAD < GW_CHUNK ? wd[(j + GW_AHEAD) % GW_CHUNK]
+                                                          : nx[(j + GW_AHEAD) % GW_CHUNK];
+      q[j % GW_AHEAD] = gw_issue<1>(ahead, C, A.xdof, A.f, BS, a);
+      step(wd[j], cur);
+    }
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  if (live)
+    A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
+}
+
+int gw_env_int(const char* name, int dflt)
+{
+  const char* e = std::getenv(name);
+  return e && *e ? std::atoi(e) : dflt;
+}
+
+template <int WARPS>
+void launch_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
+{
+  const std::size_t per_slice = (static_cast<std::size_t>(c->max_w) * 32 + (static_cast<std::size_t>(c->max_w) * 32 + 1) / 2) * sizeof(double);
+  const std::size_t smem = per_slice * WARPS;
+  auto kernel = assemble_matrix_p1_gwalk<WARPS>;
+  PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
+}
+
+template <int BS, int WARPS>
+void launch_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
+{
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t) * WARPS;
+  auto kernel = assemble_vector_p1_gwalk<BS, WARPS>;
+  PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const std::int64_t warps = static_cast<std::int64_t>(A.n_slices) * BS;
+  kernel<<<static_cast<unsigned>((warps + WARPS - 1) / WARPS), WARPS * 32, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
+}
+
+} // namespace
+
+bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
+{
+  if (c->order != 1 || c->bs != 1 || c->walk1.p == nullptr || c->max_w > 32)
+    return false;
+  switch (gw_env_int("PTB_GWALK_WARPS", 4))
+  {
+  case 1: launch_matrix_gwalk<1>(c, A); break;
+  case 2: launch_matrix_gwalk<2>(c, A); break;
+  case 8: launch_matrix_gwalk<8>(c, A); break;
+  default: launch_matrix_gwalk<4>(c, A); break;
+  }
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return true;
+}
+
+bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
+{
+  if (c->order != 1 || c->walk1.p == nullptr)
+    return false;
+  const int warps = gw_env_int("PTB_GWALK_WARPS", 4);
+  if (c->bs == 1)
+  {
+    if (warps == 1)
+      launch_vector_gwalk<1, 1>(c, A);
+    else if (warps == 8)
+      launch_vector_gwalk<1, 8>(c, A);
+    else
+      launch_vector_gwalk<1, 4>(c, A);
+  }
+  else
+  {
+    if (warps == 1)
+      launch_vector_gwalk<3, 1>(c, A);
+    else if (warps == 8)
+      launch_vector_gwalk<3, 8>(c, A);
+    else
+      launch_vector_gwalk<3, 4>(c, A);
+  }
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return true;
+}
+
+} // namespace ptb

@@ -133,6 +133,8 @@ struct ptb_ctx
   ptb::DevBuf<std::uint32_t> adj, adjso, adjrot;
   ptb::DevBuf<std::uint32_t> walk;     // P1 star walk (layout.h), uploaded when PTB_ASM_WALK=1
   double walk_loads_per_step = 0.0;
+  ptb::DevBuf<std::uint32_t> walk1;    // one-vertex-per-step walk (layout.h), PTB_ASM_GWALK=1
+  ptb::DevBuf<std::int64_t> walk1_off;
   // host copies of the compressed slot map (parity inspection)
   ptb::RowAdjacency h_adj;
   std::vector<std::uint16_t> h_so;

@@ -180,6 +180,68 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
   return {steps, loads};
 }
 
+void build_walk_single(std::int32_t n_rows, const RowAdjacency& adj, SellLayout& L)
+{
+  if (L.walk.empty() && L.adj_off[L.n_slices] > 0)
+    throw std::runtime_error("build_walk_single: needs the star walk");
+  const std::int32_t S = L.n_slices;
+  auto steps_of = [&](std::int32_t r) {
+    const std::int64_t c = adj.ptr[r + 1] - adj.ptr[r];
+    const std::int64_t base = L.adj_off[r >> 5] + (r & 31);
+    std::int64_t n = c > 0 ? 1 : 0;
+    for (std::int64_t k = 1; k < c; ++k)
+      n += std::max(1, __builtin_popcount((L.walk[base + k * 32] >> 24) & 7u));
+    return n;
+  };
+  L.walk1_off.assign(S + 1, 0);
+  int max_w1 = 0;
+#pragma omp parallel for schedule(static) reduction(max : max_w1)
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    std::int64_t w = 0;
+    for (std::int32_t r = 32 * s; r < std::min(n_rows, 32 * s + 32); ++r)
+      w = std::max(w, steps_of(r));
+    L.walk1_off[s + 1] = 32 * w;
+    max_w1 = std::max<int>(max_w1, w);
+  }
+  L.max_w1 = max_w1;
+  for (std::int32_t s = 0; s < S; ++s)
+    L.walk1_off[s + 1] += L.walk1_off[s];
+  L.walk1.assign(static_cast<std::size_t>(L.walk1_off[S]), ADJ_INVALID);
+#pragma omp parallel for schedule(static)
+  for (std::int32_t r = 0; r < n_rows; ++r)
+  {
+    const std::int64_t c = adj.ptr[r + 1] - adj.ptr[r];
+    if (c == 0)
+      continue;
+    const std::int64_t src = L.adj_off[r >> 5] + (r & 31);
+    std::int64_t dst = L.walk1_off[r >> 5] + (r & 31);
+    std::uint32_t prev = L.walk[src];
+    L.walk1[dst] = prev;
+    dst += 32;
+    for (std::int64_t k = 1; k < c; ++k)
+    {
+      const std::uint32_t word = L.walk[src + k * 32];
+      const unsigned mask = (word >> 24) & 7u;
+      if (mask == 0)
+      {
+        L.walk1[dst] = (3u << 16) | (1u << 18); // same vertices again: nothing to load
+        dst += 32;
+      }
+      unsigned left = mask;
+      for (unsigned p = 0; p < 3; ++p)
+        if (mask & (1u << p))
+        {
+          left &= ~(1u << p);
+          const std::uint32_t nw = (word >> (8 * p)) & 0xFFu, old = (prev >> (8 * p)) & 0xFFu;
+          L.walk1[dst] = nw | (old << 8) | (p << 16) | (left == 0 ? 1u << 18 : 0u);
+          dst += 32;
+        }
+      prev = word;
+    }
+  }
+}
+
 void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64_t* rowptr,
                       SellLayout& L)
 {

@@ -27,6 +27,15 @@ struct SellLayout
   // three non-owner vertices held in register positions 0..2 after the step, byte 3 = mask of
   // the positions that were (re)loaded in this step (7 on the first cell). ADJ_INVALID = padding.
   std::vector<std::uint32_t> walk;
+  // The same walk with exactly one vertex (re)loaded per step (build_walk_single), for kernels that
+  // gather the new vertex straight from global memory a few steps ahead. Own SELL offsets walk1_off
+  // (a cell that brings two or three new vertices takes two or three steps). Step 0 of a row keeps
+  // the walk format (three offsets, mask 7). Later steps: byte 0 = in-row offset of the new vertex,
+  // byte 1 = offset of the vertex it evicts (the accumulator to flush), bits 16-17 = register
+  // position (3 = none), bit 18 = a cell is complete after this step. ADJ_INVALID = padding.
+  std::vector<std::uint32_t> walk1;
+  std::vector<std::int64_t> walk1_off; // [n_slices + 1], in entries
+  int max_w1 = 0;
   // Column-index compression for the SpMV (scalar matrices): cdelta[mat_off[s]/32 + k] = d when
   // every row r of slice s has col_k = r + d (translation-invariant stencil), else CDELTA_EXPLICIT
   // and the 32 indices are stored in colsx at xoff[s] + j*32 + lane (j-th explicit k of the slice).
@@ -58,6 +67,9 @@ struct WalkStats
 };
 WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
                      const std::vector<std::uint16_t>& so, SellLayout& L);
+
+/// Derive walk1 / walk1_off from L.walk (see SellLayout::walk1).
+void build_walk_single(std::int32_t n_rows, const RowAdjacency& adj, SellLayout& L);
 
 /// Visiting order of the slices for the operator kernels. Slices without ghost columns come first
 /// (n_interior of them), so the fused halo pull overlaps with them. Inside each class the order is
