@@ -153,6 +153,9 @@ int ptb_create(int device, ptb_ctx** out)
     c->partials.alloc(static_cast<std::size_t>(3) * c->num_sms * 8);
     c->tickets.alloc(4);
     c->tickets.zero(c->stream);
+    c->loop_bar.alloc(2);
+    c->loop_bar.zero(c->stream);
+    c->loop_sums.alloc(2);
     PTB_CUDA(cudaMallocHost(&c->h_cg, 2 * sizeof(CgState)));
     PTB_CUDA(cudaMallocHost(&c->h_scalar, 4 * sizeof(double)));
     PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -534,6 +537,42 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     allreduce_sum(c, &st[1].rr, 2);
     launch_cg_finish_init(c, &st[1], rtol, e0);
 
+    static const bool allow_fused = [] {
+      const char* e = std::getenv("PTB_FUSED_HALO");
+      return !(e && e[0] == '0');
+    }();
+    const bool fused = allow_fused && !mf && c->peer.enabled && !c->nbr_ranks.empty();
+    static const bool persistent = [] {
+      const char* e = std::getenv("PTB_CG_PERSISTENT");
+      return e && e[0] == '1';
+    }();
+    // Opt-in: the whole loop in one cooperative kernel (cg.cu cg_loop). Needs the assembled
+    // operator and, across GPUs, the peer-memory path with the fused halo (no NCCL inside a kernel).
+    bool looped = false;
+    if (persistent && !mf && kmax > 0 && (c->nranks == 1 || fused) && !c->nccl_comm)
+    {
+      const unsigned int ebase = c->peer.red_epoch + 1u;
+      need(ebase + 2u * static_cast<unsigned int>(kmax) > ebase, "ptb_cg_solve: reduction epochs would wrap");
+      looped = launch_cg_loop(c, dinv, 0, kmax, ebase, fused);
+      if (looped)
+      {
+        PTB_CUDA(cudaMemcpyAsync(c->h_cg, st, 2 * sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
+        PTB_CUDA(cudaStreamSynchronize(c->stream));
+        const CgState fin = c->h_cg[0].k >= c->h_cg[1].k ? c->h_cg[0] : c->h_cg[1];
+        // the loop consumed one halo epoch and two reduction epochs per iteration
+        c->peer.halo_epoch += static_cast<unsigned long long>(fin.k);
+        c->peer.red_epoch += 2u * static_cast<unsigned int>(fin.k);
+        halo_forward(c, c->x.p);
+        peer_neighbour_barrier(c);
+        t.stop();
+        if (iterations)
+          *iterations = fin.k;
+        if (rel_residual)
+          *rel_residual = std::sqrt(fin.rnorm / fin.rnorm0);
+        return;
+      }
+    }
+
     // Iterations are queued in batches; the stopping flag of batch j is read back while batch
     // j + 1 is already running, so the device never waits for the host. Kernels of iterations
     // after convergence return immediately.
@@ -553,11 +592,6 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
         ++it;
         CgState* cur = &st[it & 1];
         CgState* nxt = &st[(it + 1) & 1];
-        static const bool allow_fused = [] {
-          const char* e = std::getenv("PTB_FUSED_HALO");
-          return !(e && e[0] == '0');
-        }();
-        const bool fused = allow_fused && !mf && c->peer.enabled && !c->nbr_ranks.empty();
         if (!fused)
           halo_forward(c, c->p.p);
         const unsigned int ea = next_red_epoch(c), eb = next_red_epoch(c);

@@ -31,15 +31,23 @@ constexpr int VEC_THREADS = 256;
 enum class Ld
 {
   NC,
-  CG
+  CG,
+  CA // coherent cached load (ld.global.ca): the vector changes inside a persistent kernel, L1
+     // lines are dropped by the acquire of the grid barrier, never served from the .nc path
 };
 template <Ld L>
 __device__ __forceinline__ double ldp(const double* q)
 {
   if constexpr (L == Ld::NC)
     return __ldg(q);
-  else
+  else if constexpr (L == Ld::CG)
     return __ldcg(q);
+  else
+  {
+    double v;
+    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(q));
+    return v;
+  }
 }
 
 // One SELL-32 slice: y[row] = sum_k vals * p[col]; returns this row's p.y contribution.
@@ -230,6 +238,61 @@ __device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHa
   {
     __threadfence();
     st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
+  }
+}
+
+// Same pull with the epoch passed explicitly (the persistent loop advances it per iteration).
+__device__ __forceinline__ void halo_pull_share_at(const PeerView& P, const FusedHalo& FH,
+                                                   unsigned long long epoch)
+{
+  const PeerHalo& H = FH.H;
+  if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
+  {
+    __threadfence_system(); // p was completed by the previous kernel: publish "ready"
+    st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], epoch);
+  }
+  if (threadIdx.x < H.n_nbr)
+  {
+    const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
+    while (ld_acquire_sys(flag) < epoch)
+    {
+    }
+  }
+  __syncthreads();
+  constexpr int PULL_ILP = 4; // independent remote loads in flight per thread (NVLink ~2 us)
+  const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
+  const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
+  for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i0 < n;
+       i0 += step * PULL_ILP)
+  {
+    double val[PULL_ILP];
+    std::int64_t dst[PULL_ILP];
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
+    {
+      const std::int64_t i = i0 + u * step;
+      dst[u] = -1;
+      if (i < n)
+      {
+        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+        int nb = 0;
+        while (j >= H.recv_displ[nb + 1])
+          ++nb;
+        dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
+        val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
+      if (dst[u] >= 0)
+        FH.pw[dst[u]] = val[u];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0)
+  {
+    __threadfence();
+    st_release_gpu(&FH.ready[blockIdx.x], epoch);
   }
 }
 
@@ -726,6 +789,277 @@ sqnorm_kernel(std::int64_t n, const double* __restrict__ v, double* out, double*
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// The whole iteration loop of cg.h:57-84 in ONE cooperative kernel (opt-in, PTB_CG_PERSISTENT=1).
+// Same three phases and the same arithmetic as spmv_sell / cg_update / cg_direction, separated
+// by grid barriers instead of kernel boundaries:
+//   phase 1  y = A p (+ fused halo pull in peer mode), CTA partials of p.y
+//   barrier  the last CTA to arrive sums the partials in index order, publishes the local sum to
+//            the peers (LL window) and releases the barrier; every CTA collects the global sum
+//   phase 2  alpha, r -= alpha y, CTA partials of r.r and r.z
+//   barrier  as above (two values)
+//   phase 3  beta, stopping rule (cg.h:78), x += alpha p, p = beta p + D^-1 r
+//   barrier  p complete before the next operator application
+// Why: at 8 GPUs (elasticity, 1.25 M DOFs per GPU) an iteration takes 155 us against 97 us of
+// kernel time; the 7-10 us vector kernels pay a launch + drain + fill each, and every kernel
+// boundary adds to the skew the two all-reduces then wait for. Here the host launches once per
+// solve and reads the iteration count at the end.
+// Vectors that change inside the kernel (p, r, x, y) are never read through the non-coherent
+// path: gathers of p use ld.global.ca / .cg, the streaming phases use .cg loads.
+// NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
+// ------------------------------------------------------------------------------------------
+struct LoopArgs
+{
+  SpmvArgs A;
+  std::int64_t n; // owned entries
+  const double* dinv;
+  double *r, *p, *x, *y;
+  CgState* st;        // [2], indexed by iteration parity
+  double* partials;   // [2][gridDim.x]
+  unsigned int* bar;  // [0] arrivals, [1] generation
+  double* sums;       // [2] local sums broadcast by the last CTA
+  int it0, n_it;      // iterations it0+1 .. it0+n_it
+  unsigned int ebase; // reduction epochs: ebase + 2 (j-1) for p.y, + 1 for (r.r, r.z)
+};
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Grid barrier fused with a deterministic reduction of NV values per CTA (NV = 0: barrier only).
+// On return every thread holds the (peer-)global sums in out[].
+template <int NV>
+__device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], const LoopArgs& L,
+                                                 const PeerView& P, unsigned int epoch, double* red,
+                                                 double (&out)[NV > 0 ? NV : 1])
+{
+  __shared__ bool is_last;
+  __shared__ double bsum[2];
+  if constexpr (NV > 0)
+    block_sum<NV>(v, red);
+  unsigned int gen = 0;
+  if (threadIdx.x == 0)
+  {
+    if constexpr (NV > 0)
+    {
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+        L.partials[i * gridDim.x + blockIdx.x] = v[i];
+    }
+    gen = ld_acquire_gpu_u32(&L.bar[1]); // cannot advance before this CTA has arrived
+    __threadfence();
+    is_last = atomicAdd(&L.bar[0], 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last)
+  {
+    __threadfence();
+    if constexpr (NV > 0)
+    {
+      double acc[NV];
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+      {
+        acc[i] = 0.0;
+        for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x)
+          acc[i] += __ldcg(&L.partials[i * gridDim.x + j]);
+      }
+      __syncthreads(); // red is reused
+      block_sum<NV>(acc, red);
+      if (threadIdx.x == 0)
+      {
+        if (P.nranks > 1)
+          peer_publish(P, epoch, acc[0], NV > 1 ? acc[NV - 1] : 0.0);
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          L.sums[i] = acc[i];
+      }
+    }
+    if (threadIdx.x == 0)
+    {
+      L.bar[0] = 0u;
+      __threadfence();
+      st_release_gpu_u32(&L.bar[1], gen + 1u);
+    }
+  }
+  else if (threadIdx.x == 0)
+  {
+    while (ld_acquire_gpu_u32(&L.bar[1]) == gen)
+    {
+    }
+  }
+  if constexpr (NV > 0)
+  {
+    if (threadIdx.x == 0)
+    {
+      if (P.nranks > 1)
+      {
+        double s0, s1;
+        peer_collect(P, epoch, s0, s1);
+        bsum[0] = s0, bsum[1] = s1;
+      }
+      else
+      {
+#pragma unroll
+        for (int i = 0; i < NV; ++i)
+          bsum[i] = __ldcg(&L.sums[i]);
+      }
+    }
+  }
+  __syncthreads();
+  if constexpr (NV > 0)
+  {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      out[i] = bsum[i];
+    __syncthreads(); // bsum is reused by the next call
+  }
+}
+
+template <int BS, bool FUSED>
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
+{
+  __shared__ double red[64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int warps_per_cta = SPMV_THREADS / 32;
+  const SpmvArgs& A = L.A;
+  const bool first = blockIdx.x == 0 && threadIdx.x == 0;
+  const std::int64_t n2 = L.n >> 1;
+  const std::int64_t tid = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  const std::int64_t nthr = static_cast<std::int64_t>(gridDim.x) * blockDim.x;
+  const unsigned long long halo0 = FH.epoch; // epoch of the launch that precedes this loop
+
+  for (int j = 1; j <= L.n_it; ++j)
+  {
+    const int it = L.it0 + j;
+    const CgState* cur = &L.st[it & 1];
+    CgState* nxt = &L.st[(it + 1) & 1];
+    // cur was completed before the last barrier of the previous iteration (or by the host-side
+    // init kernels): every CTA reads the same values and takes the same exit
+    if (__ldcg(&cur->conv) != 0)
+      break;
+    const double rz_old = __ldcg(&cur->rz_old), rnorm0 = __ldcg(&cur->rnorm0),
+                 rtol2 = __ldcg(&cur->rtol2);
+    const int k_done = __ldcg(&cur->k);
+
+    // ---- phase 1: y = A p, local p.y --------------------------------------------------------
+    double dotv = 0.0;
+    if constexpr (FUSED)
+    {
+      const unsigned long long hep = halo0 + static_cast<unsigned long long>(j);
+      if (blockIdx.x < FH.npull)
+      {
+        halo_pull_share_at(P, FH, hep);
+        for (int base = 0; base < FH.npull; base += 32)
+        {
+          unsigned long long f;
+          do
+            f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
+          while (!__all_sync(0xffffffffu, f >= hep));
+        }
+        for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
+             s += FH.npull * warps_per_cta)
+          dotv += spmv_slice<BS, Ld::CG>(A, L.p, L.y, FH.order[s], lane);
+      }
+      else
+      {
+        const std::int32_t stride = (gridDim.x - FH.npull) * warps_per_cta;
+        for (std::int32_t s = (blockIdx.x - FH.npull) * warps_per_cta + warp; s < FH.n_interior;
+             s += stride)
+          dotv += spmv_slice<BS, Ld::CA>(A, L.p, L.y, FH.order[s], lane);
+      }
+    }
+    else
+    {
+      const std::int32_t stride = gridDim.x * warps_per_cta;
+      for (std::int32_t s = blockIdx.x * warps_per_cta + warp; s < A.n_slices; s += stride)
+        dotv += spmv_slice<BS, Ld::CA>(A, L.p, L.y, FH.order[s], lane);
+    }
+    const unsigned int ea = L.ebase + 2u * static_cast<unsigned int>(j - 1), eb = ea + 1u;
+    double v1[1] = {dotv}, py[1];
+    grid_reduce_sync<1>(v1, L, P, ea, red, py);
+    const double alpha = rz_old / py[0]; // cg.h:65
+
+    // ---- phase 2: r -= alpha y (cg.h:71), local r.r and r.z (cg.h:74) -----------------------
+    double v2[2] = {0.0, 0.0};
+    {
+      const double2* y2 = reinterpret_cast<const double2*>(L.y);
+      const double2* d2 = reinterpret_cast<const double2*>(L.dinv);
+      double2* r2 = reinterpret_cast<double2*>(L.r);
+      for (std::int64_t i = tid; i < n2; i += nthr)
+      {
+        const double2 yy = __ldcg(y2 + i), dd = __ldg(d2 + i);
+        double2 rr = __ldcg(r2 + i);
+        rr.x = -alpha * yy.x + rr.x;
+        rr.y = -alpha * yy.y + rr.y;
+        r2[i] = rr;
+        v2[0] += rr.x * rr.x;
+        v2[1] += rr.x * (dd.x * rr.x);
+        v2[0] += rr.y * rr.y;
+        v2[1] += rr.y * (dd.y * rr.y);
+      }
+      if ((L.n & 1) && first)
+      {
+        const double ri = -alpha * __ldcg(L.y + L.n - 1) + __ldcg(L.r + L.n - 1);
+        L.r[L.n - 1] = ri;
+        v2[0] += ri * ri;
+        v2[1] += ri * (__ldg(L.dinv + L.n - 1) * ri);
+      }
+    }
+    double rs[2];
+    grid_reduce_sync<2>(v2, L, P, eb, red, rs);
+    const double rr = rs[0], rz = rs[1];
+    const double beta = rz / rz_old;             // cg.h:75
+    const bool converged = rr / rnorm0 < rtol2;  // cg.h:78
+    if (first)
+    {
+      CgState s;
+      s.py = py[0], s.rr = rr, s.rz = rz, s.rz_old = rz, s.rnorm0 = rnorm0, s.rtol2 = rtol2;
+      s.rnorm = rr, s.alpha = alpha, s.k = k_done + 1, s.conv = converged ? 1 : 0;
+      *nxt = s;
+    }
+
+    // ---- phase 3: x += alpha p (cg.h:68), p = beta p + D^-1 r (cg.h:82) ------------------------
+    {
+      const double2* r2 = reinterpret_cast<const double2*>(L.r);
+      const double2* d2 = reinterpret_cast<const double2*>(L.dinv);
+      double2* p2 = reinterpret_cast<double2*>(L.p);
+      double2* x2 = reinterpret_cast<double2*>(L.x);
+      for (std::int64_t i = tid; i < n2; i += nthr)
+      {
+        double2 pp = __ldcg(p2 + i), xx = __ldcg(x2 + i);
+        xx.x = alpha * pp.x + xx.x;
+        xx.y = alpha * pp.y + xx.y;
+        x2[i] = xx;
+        if (!converged)
+        {
+          const double2 rv = __ldcg(r2 + i), dd = __ldg(d2 + i);
+          pp.x = beta * pp.x + dd.x * rv.x;
+          pp.y = beta * pp.y + dd.y * rv.y;
+          p2[i] = pp;
+        }
+      }
+      if ((L.n & 1) && first)
+      {
+        const double pv = __ldcg(L.p + L.n - 1);
+        L.x[L.n - 1] = alpha * pv + __ldcg(L.x + L.n - 1);
+        if (!converged)
+          L.p[L.n - 1] = beta * pv + __ldg(L.dinv + L.n - 1) * __ldcg(L.r + L.n - 1);
+      }
+    }
+    double none[1] = {0.0}, none_out[1];
+    grid_reduce_sync<0>(none, L, P, 0u, red, none_out);
+  }
+}
+
 // Grids are sized to exactly one resident wave: SMs x (CTAs of this kernel that fit on an SM),
 // capped by the work. A second partial wave would run at low occupancy and stretch the tail.
 template <typename K>
@@ -835,6 +1169,65 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
                                                         epoch, FH);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
+}
+
+bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned int ebase,
+                    bool fused_halo)
+{
+  if (c->bs != 1 && c->bs != 3)
+    return false;
+  LoopArgs L{};
+  L.A = SpmvArgs{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
+                 c->cdelta.p, c->colsx.p, c->xoff.p};
+  L.n = static_cast<std::int64_t>(c->n_owned) * c->bs;
+  L.dinv = dinv;
+  L.r = c->r.p, L.p = c->p.p, L.x = c->x.p, L.y = c->y.p;
+  L.st = c->cg.p;
+  L.bar = c->loop_bar.p;
+  L.sums = c->loop_sums.p;
+  L.it0 = it0, L.n_it = n_it, L.ebase = ebase;
+  PeerView P = peer_view(c);
+  FusedHalo FH{};
+  FH.order = c->slice_order.p;
+  FH.n_interior = c->n_interior_slices;
+  const void* kernel = nullptr;
+  int slot = 0;
+  if (fused_halo)
+    kernel = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, true>)
+                        : reinterpret_cast<const void*>(cg_loop<3, true>),
+    slot = c->bs == 1 ? 10 : 11;
+  else
+    kernel = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, false>)
+                        : reinterpret_cast<const void*>(cg_loop<3, false>),
+    slot = c->bs == 1 ? 12 : 13;
+  if (c->grid_cache[slot] == 0)
+  {
+    int per_sm = 0;
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
+    c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
+  }
+  const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
+  const int grid = static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
+  if (fused_halo)
+  {
+    if (grid < 4)
+      return false; // too little work to split into roles: the caller uses the kernel-per-phase path
+    FH.H = peer_halo(c);
+    FH.epoch = c->peer.halo_epoch; // iteration j of the loop uses epoch + j
+    FH.ready = c->peer.ready.p;
+    FH.pw = c->p.p;
+    const double share = c->n_slices > 0
+                             ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
+                             : 0.0;
+    int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
+    FH.npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
+  }
+  c->partials.alloc(std::max<std::size_t>(c->partials.n, static_cast<std::size_t>(2) * grid));
+  L.partials = c->partials.p;
+  void* args[] = {&L, &P, &FH};
+  PTB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(SPMV_THREADS), args, 0, c->stream));
+  c->launches += 1;
+  return true;
 }
 
 void launch_cg_init(ptb_ctx* c, const double* dinv, CgState* st, unsigned int epoch)

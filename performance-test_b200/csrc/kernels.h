@@ -109,6 +109,11 @@ void launch_cg_update(ptb_ctx* c, const double* dinv, CgState* cur, unsigned int
 /// beta, convergence test, bookkeeping into nxt; p = beta p + dinv r unless converged.
 void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgState* nxt,
                          unsigned int epoch);
+/// Iterations it0+1 .. it0+n_it of the CG loop in one cooperative kernel (cg.cu cg_loop); the
+/// state records must have been initialised (launch_cg_finish_init). Returns false when the path
+/// does not apply (the caller then queues the three kernels per iteration).
+bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned int ebase,
+                    bool fused_halo);
 /// Reduction epochs of the peer-memory all-reduce (never 0; see peer.cuh).
 inline unsigned int next_red_epoch(ptb_ctx* c)
 {

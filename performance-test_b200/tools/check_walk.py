@@ -52,6 +52,40 @@ def ab(ndofs):
     c.close()
 
 
+def ab2(ndofs):
+    """Matrix and vector assembly: default kernels against the opt-in ones (PTB_ASM_GWALK for
+    Poisson and elasticity, PTB_ASM_WALK3 for the elasticity matrix), one context per variant."""
+    for ptype, dpn in (("poisson", 1), ("elasticity", 3)):
+        nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, dpn, 1, 1)
+        f = 2 ** r
+        P = pt.host.Problem(ptype, 1, nx * f, ny * f, nz * f)
+        ref = None
+        variants = [("default", {}), ("gwalk", {"PTB_ASM_GWALK": "1"})]
+        if ptype == "elasticity":
+            variants.append(("walk3", {"PTB_ASM_WALK3": "1"}))
+        else:
+            variants.append(("cellorder", {"PTB_ASM_WALK": "0"}))
+        for name, env in variants:
+            for k in ("PTB_ASM_GWALK", "PTB_ASM_WALK3", "PTB_ASM_WALK"):
+                os.environ.pop(k, None)
+            os.environ.update(env)
+            c = pt.abi.Context(0)
+            c.set_problem(P)
+            c.assemble_matrix()
+            c.assemble_vector()
+            a, b = c.matrix_values(), c.rhs()
+            if ref is None:
+                ref = (a, b)
+            key = f"{ptype}_{name}"
+            res[key] = {"matrix_ms": c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 5),
+                        "vector_ms": c.time_kernel(pt.abi.KERNEL_ASSEMBLE_VECTOR, 5),
+                        "matrix_maxdiff": float(np.abs(a - ref[0]).max() / np.abs(ref[0]).max()),
+                        "vector_maxdiff": float(np.abs(b - ref[1]).max() / np.abs(ref[1]).max()),
+                        "n_owned": P.n_owned, "nnz": P.nnz}
+            c.close()
+            dump()
+
+
 def ncu_target(ndofs):
     nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
     f = 2 ** r
@@ -62,6 +96,8 @@ def ncu_target(ndofs):
 def main():
     if len(sys.argv) > 2 and sys.argv[1] == "ab":
         return ab(int(sys.argv[2]))
+    if len(sys.argv) > 2 and sys.argv[1] == "ab2":
+        return ab2(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ncu":
         return ncu_target(int(sys.argv[2]))
     t0 = time.time()
