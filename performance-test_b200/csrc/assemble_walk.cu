@@ -99,14 +99,18 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
     if (s2 < A.n_slices)
     {
       const std::int64_t mo2 = A.mat_off[s2], ao2 = A.adj_off[s2];
-      if (lane < w)
+      // never past the end of an array: clamp to that slice's own widths and to n_rows
+      const int w2 = static_cast<int>((A.mat_off[s2 + 1] - mo2) >> 5);
+      const int wa2 = static_cast<int>((A.adj_off[s2 + 1] - ao2) >> 5);
+      const std::int64_t r2 = static_cast<std::int64_t>(s2) * 32;
+      if (lane < w2)
         prefetch_l2(A.cols + mo2 + lane * 32);
-      if (lane < wa)
+      if (lane < wa2)
         prefetch_l2(walk + ao2 + lane * 32);
-      if (lane < 8)
-        prefetch_l2(A.xdof + (static_cast<std::int64_t>(s2) * 32 + lane * 4) * 4);
-      if (lane < 2)
-        prefetch_l2(A.rowptr + static_cast<std::int64_t>(s2) * 32 + lane * 16);
+      if (lane < 8 && r2 + lane * 4 < A.n_rows)
+        prefetch_l2(A.xdof + (r2 + lane * 4) * 4);
+      if (lane < 2 && r2 + lane * 16 < A.n_rows)
+        prefetch_l2(A.rowptr + r2 + lane * 16);
     }
   }
 
@@ -271,14 +275,17 @@ assemble_matrix_p1_walk3(MatrixArgs A, const std::uint32_t* __restrict__ walk)
     if (s2 < A.n_slices && a == 0)
     {
       const std::int64_t mo2 = A.mat_off[s2], ao2 = A.adj_off[s2];
-      if (lane < w)
+      const int w2 = static_cast<int>((A.mat_off[s2 + 1] - mo2) >> 5);
+      const int wa2 = static_cast<int>((A.adj_off[s2 + 1] - ao2) >> 5);
+      const std::int64_t r2 = static_cast<std::int64_t>(s2) * 32;
+      if (lane < w2)
         prefetch_l2(A.cols + mo2 + lane * 32);
-      if (lane < wa)
+      if (lane < wa2)
         prefetch_l2(walk + ao2 + lane * 32);
-      if (lane < 8)
-        prefetch_l2(A.xdof + (static_cast<std::int64_t>(s2) * 32 + lane * 4) * 4);
-      if (lane < 2)
-        prefetch_l2(A.rowptr + static_cast<std::int64_t>(s2) * 32 + lane * 16);
+      if (lane < 8 && r2 + lane * 4 < A.n_rows)
+        prefetch_l2(A.xdof + (r2 + lane * 4) * 4);
+      if (lane < 2 && r2 + lane * 16 < A.n_rows)
+        prefetch_l2(A.rowptr + r2 + lane * 16);
     }
   }
 

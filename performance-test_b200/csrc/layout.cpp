@@ -39,11 +39,15 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
     L.adj_off[s + 1] += L.adj_off[s];
   }
   L.cols.resize(static_cast<std::size_t>(L.mat_off[S]));
-  L.adj.resize(static_cast<std::size_t>(L.adj_off[S]));
-  L.adjso.resize(static_cast<std::size_t>(L.adj_off[S]) * L.so_words);
+  // P1 with short rows: the rotated one-word form replaces adj + adjso (the kernels read nothing else)
   const bool rot = nd == 4 && max_so < 255;
   if (rot)
     L.adjrot.resize(static_cast<std::size_t>(L.adj_off[S]));
+  else
+  {
+    L.adj.resize(static_cast<std::size_t>(L.adj_off[S]));
+    L.adjso.resize(static_cast<std::size_t>(L.adj_off[S]) * L.so_words);
+  }
   const std::uint32_t* pairs = adj.pairs.data();
 #pragma omp parallel for schedule(static)
   for (std::int32_t s = 0; s < S; ++s)
@@ -62,7 +66,6 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
       for (std::int64_t k = 0; k < wa; ++k)
       {
         const bool on = k < alen;
-        L.adj[ao + k * 32 + lane] = on ? pairs[adj.ptr[r] + k] : ADJ_INVALID;
         if (rot)
         {
           std::uint32_t word = ADJ_INVALID;
@@ -75,7 +78,9 @@ void build_sell_layout(std::int32_t n_rows, int nd, const std::int64_t* rowptr,
               word |= static_cast<std::uint32_t>(so[q * 4 + ((li + t) & 3)]) << (8 * t);
           }
           L.adjrot[ao + k * 32 + lane] = word;
+          continue;
         }
+        L.adj[ao + k * 32 + lane] = on ? pairs[adj.ptr[r] + k] : ADJ_INVALID;
         for (int wd = 0; wd < L.so_words; ++wd)
         {
           std::uint32_t word = 0;
@@ -107,6 +112,11 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
     std::vector<std::uint8_t> o;          // [c][3] offsets of the non-owner vertices, rotation order
     std::vector<std::uint64_t> m;         // [c][4] the same as a 256-bit set
     std::vector<char> visited;
+    // Rows with the same star (same offsets in the same cell order) have the same walk: on a
+    // structured mesh almost every row repeats its predecessor, so the last result is kept.
+    std::vector<std::uint8_t> last_o;
+    std::vector<std::uint32_t> last_words;
+    std::int64_t last_loads = 0;
 #pragma omp for schedule(static)
     for (std::int32_t r = 0; r < n_rows; ++r)
     {
@@ -115,18 +125,25 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
       if (c == 0)
         continue;
       o.resize(static_cast<std::size_t>(c) * 3);
-      m.assign(static_cast<std::size_t>(c) * 4, 0);
-      visited.assign(c, 0);
       for (int j = 0; j < c; ++j)
       {
         const int li = pairs[q0 + j] & 3;
         for (int t = 1; t < 4; ++t)
-        {
-          const std::uint8_t v = static_cast<std::uint8_t>(so[(q0 + j) * 4 + ((li + t) & 3)]);
-          o[j * 3 + t - 1] = v;
-          m[j * 4 + (v >> 6)] |= std::uint64_t(1) << (v & 63);
-        }
+          o[j * 3 + t - 1] = static_cast<std::uint8_t>(so[(q0 + j) * 4 + ((li + t) & 3)]);
       }
+      if (o == last_o)
+      {
+        const std::int64_t b0 = L.adj_off[r >> 5] + (r & 31);
+        for (int k = 0; k < c; ++k)
+          L.walk[b0 + static_cast<std::int64_t>(k) * 32] = last_words[k];
+        steps += c, loads += last_loads;
+        continue;
+      }
+      m.assign(static_cast<std::size_t>(c) * 4, 0);
+      visited.assign(c, 0);
+      for (int j = 0; j < c * 3; ++j)
+        m[(j / 3) * 4 + (o[j] >> 6)] |= std::uint64_t(1) << (o[j] & 63);
+      const std::int64_t loads_before = loads;
       auto shared = [&](int a, int b) {
         return __builtin_popcountll(m[a * 4] & m[b * 4]) + __builtin_popcountll(m[a * 4 + 1] & m[b * 4 + 1])
                + __builtin_popcountll(m[a * 4 + 2] & m[b * 4 + 2])
@@ -175,6 +192,11 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
         visited[best] = 1;
         cur = best;
       }
+      last_o = o;
+      last_words.resize(c);
+      for (int k = 0; k < c; ++k)
+        last_words[k] = L.walk[base + static_cast<std::int64_t>(k) * 32];
+      last_loads = loads - loads_before;
     }
   }
   return {steps, loads};
