@@ -1,5 +1,6 @@
 // extern "C" entry points of libptb200.so (include/ptb200.h).
 #include "comm.h"
+#include "envopt.h"
 #include "kernels.h"
 #include "layout.h"
 #include <algorithm>
@@ -13,23 +14,10 @@ using namespace ptb;
 namespace
 {
 // Star-walk assembly (assemble_walk.cu): PTB_ASM_WALK=1/0 overrides the built-in default.
-constexpr bool kWalkDefault = true;
-bool walk_enabled()
-{
-  const char* env = std::getenv("PTB_ASM_WALK");
-  return env && env[0] ? env[0] == '1' : kWalkDefault;
-}
-// Elasticity walk kernel: written after the round's GPU budget was spent, never run -> opt-in.
-bool walk3_enabled()
-{
-  const char* env = std::getenv("PTB_ASM_WALK3");
-  return env && env[0] == '1';
-}
-bool gwalk_enabled()
-{
-  const char* env = std::getenv("PTB_ASM_GWALK");
-  return env && env[0] == '1';
-}
+bool walk_enabled() { return env_flag("PTB_ASM_WALK", true); }
+// Written after the round's GPU budget was spent, never run -> opt-in.
+bool walk3_enabled() { return env_flag("PTB_ASM_WALK3", false); }
+bool gwalk_enabled() { return env_flag("PTB_ASM_GWALK", false); }
 thread_local std::string g_err;
 
 template <typename F>

@@ -19,6 +19,7 @@
 // The step encoding and the arithmetic are pinned on the CPU (tests/test_star_walk.py,
 // test_direct_gather_walk_reproduces_the_oracle).
 #include "geom.cuh"
+#include "envopt.h"
 #include "kernels.h"
 #include <climits>
 #include <cstdlib>
@@ -30,17 +31,6 @@ namespace
 
 constexpr int GW_CHUNK = 8; // step words in flight per thread
 constexpr int GW_AHEAD = 4; // gathers in flight per thread (steps of lookahead); divides GW_CHUNK
-
-__device__ __forceinline__ double gw_rcp(double d)
-{
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  e = fma(e, e, e);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  return fma(x, e, x);
-}
 
 // A vertex in flight: the two 16-byte halves of its padded coordinates (+ the source term).
 template <int NF>
@@ -160,7 +150,7 @@ assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, dg = 0.0;
   auto cell = [&](bool compute) {
     const double det = dot(e0, n0);
-    const double r = compute ? gw_rcp(6.0 * fabs(det)) : 0.0;
+    const double r = compute ? rcp_nr(6.0 * fabs(det)) : 0.0;
     const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
     dg = fma(r, dot(c0, c0), dg);
     a0 = fma(r, dot(c0, n0), a0);
@@ -330,12 +320,6 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
     A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
 }
 
-int gw_env_int(const char* name, int dflt)
-{
-  const char* e = std::getenv(name);
-  return e && *e ? std::atoi(e) : dflt;
-}
-
 template <int WARPS>
 void launch_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
 {
@@ -362,7 +346,7 @@ bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
 {
   if (c->order != 1 || c->bs != 1 || c->walk1.p == nullptr || c->max_w > 32)
     return false;
-  switch (gw_env_int("PTB_GWALK_WARPS", 4))
+  switch (env_int("PTB_GWALK_WARPS", 4))
   {
   case 1: launch_matrix_gwalk<1>(c, A); break;
   case 2: launch_matrix_gwalk<2>(c, A); break;
@@ -378,7 +362,7 @@ bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
 {
   if (c->order != 1 || c->walk1.p == nullptr)
     return false;
-  const int warps = gw_env_int("PTB_GWALK_WARPS", 4);
+  const int warps = env_int("PTB_GWALK_WARPS", 4);
   if (c->bs == 1)
   {
     if (warps == 1)

@@ -18,6 +18,7 @@
 // Default for scalar P1 (measured x1.48 against assemble_matrix_p1<1>, profiles/r01_walk_*);
 // PTB_ASM_WALK=0 selects the older kernel.
 #include "geom.cuh"
+#include "envopt.h"
 #include "kernels.h"
 #include <climits>
 #include <cstdlib>
@@ -33,24 +34,6 @@ namespace
 constexpr int WALK_CHUNK = 8; // step words in flight per thread
 // L2 prefetch distance in slices: about two generations of resident warps (148 SMs x 14 warps).
 constexpr int WALK_PF_DIST = 4096;
-
-__device__ __forceinline__ void prefetch_l2(const void* p)
-{
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
-
-// 1/d for a normal, finite d: MUFU seed + one cubic and one quadratic Newton step, no slow path
-// (the element volume of a valid mesh is never denormal), so the step has no branch.
-__device__ __forceinline__ double rcp_fast(double d)
-{
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  e = fma(e, e, e);
-  x = fma(x, e, x);
-  e = fma(-d, x, 1.0);
-  return fma(x, e, x);
-}
 
 // Register positions of the walk (three non-owner vertices of the current cell).
 struct WalkState
@@ -186,7 +169,7 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
     if (l0 || l1)
       W.n2 = cross(W.e0, W.e1);
     const double det = dot(W.e0, W.n0);
-    const double r = valid ? rcp_fast(6.0 * fabs(det)) : 0.0;
+    const double r = valid ? rcp_nr(6.0 * fabs(det)) : 0.0;
     const Vec3 c0 = {-(W.n0.x + W.n1.x + W.n2.x), -(W.n0.y + W.n1.y + W.n2.y),
                      -(W.n0.z + W.n1.z + W.n2.z)};
     W.dg = fma(r, dot(c0, c0), W.dg);
@@ -358,7 +341,7 @@ assemble_matrix_p1_walk3(MatrixArgs A, const std::uint32_t* __restrict__ walk)
     if (l0 || l1)
       n2 = cross(e0, e1);
     const double det = dot(e0, n0);
-    const double r = valid ? rcp_fast(6.0 * fabs(det)) : 0.0;
+    const double r = valid ? rcp_nr(6.0 * fabs(det)) : 0.0;
     const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
     const double q = r * comp(c0, a);
     dg = Vec3{fma(q, c0.x, dg.x), fma(q, c0.y, dg.y), fma(q, c0.z, dg.z)};
@@ -437,11 +420,6 @@ bool launch_walk(ptb_ctx* c, const MatrixArgs& A)
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
   return true;
-}
-int env_int(const char* name, int dflt)
-{
-  const char* e = std::getenv(name);
-  return e && *e ? std::atoi(e) : dflt;
 }
 } // namespace
 

@@ -51,5 +51,23 @@ __device__ __forceinline__ P1Geom p1_geometry(Vec3 e1, Vec3 e2, Vec3 e3)
   return G;
 }
 
+// 1/d for a normal, finite d: MUFU seed + one cubic and one quadratic Newton step. No slow path
+// (an element volume of a valid mesh is never denormal), so callers stay branch-free.
+__device__ __forceinline__ double rcp_nr(double d)
+{
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  x = fma(x, e, x);
+  e = fma(-d, x, 1.0);
+  return fma(x, e, x);
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p)
+{
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 } // namespace
 } // namespace ptb

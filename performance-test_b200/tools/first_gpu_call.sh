@@ -1,0 +1,29 @@
+#!/usr/bin/env bash
+# First GPU job after a round that ended with untested opt-in kernels:
+# parity first, then A/B timings. Everything lands in gpurun_out/first_call/. One GPU, ~3 minutes.
+#   gpurun --timeout 400 -- 'bash performance-test_b200/tools/first_gpu_call.sh'
+set -u
+cd "$(dirname "$0")/../.."
+out=gpurun_out/first_call
+mkdir -p "$out"
+export PTB_TEST_OPTIN=1
+echo "== opt-in parity tests"
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "opt_in or persistent or star_walk" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
+echo "== assembly A/B (4M DOFs)"
+WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
+echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"
+for persistent in 0 1; do
+  for wl in "--workload small" "--workload poisson --ndofs 3000000" "--workload elasticity --ndofs 1250000"; do
+    tag=$(echo "$wl" | tr -d ' -' | tr -c 'a-z0-9\n' '_')
+    PTB_CG_PERSISTENT=$persistent timeout 200 python bench.py $wl --steps 2 --warmup 1 --no-cpu-baseline \
+      > "$out/bench_${tag}_persistent${persistent}.json" 2> "$out/bench_${tag}_persistent${persistent}.err"
+    python - "$out/bench_${tag}_persistent${persistent}.json" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print(sys.argv[1], "value %.4g" % d["value"], "its", d.get("cg_iterations"), "launches", d.get("gpu_launches"), d.get("stage_ms"))
+except Exception as e:
+    print(sys.argv[1], "FAILED", e)
+PY
+  done
+done
