@@ -154,6 +154,15 @@ int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n
                                const int64_t* rowptr, const int32_t* cols, int64_t* step_ptr,
                                uint32_t* words);
 
+/* The SELL-32 arrays the P1 walk kernels read (host only): offsets [ceil(n_owned/32) + 1] first
+ * (pass NULL for the data arrays), then the data: padded columns, walk words, single-reload walk
+ * words, each in device order (offset[s] + k*32 + lane). Used by tests/emu, which runs the
+ * kernel sources on the host. */
+int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, int* max_w, int64_t* mat_off,
+                        int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
+                        uint32_t* walk1);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

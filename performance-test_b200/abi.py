@@ -72,6 +72,7 @@ def lib():
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
+        L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
         L.ptb_stage_ms.restype = dbl
@@ -132,6 +133,27 @@ def star_walk_single(dofmap, n_owned, rowptr, cols):
         if rc != 0:
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return ptr, words
+
+
+def p1_layout(dofmap, n_owned, rowptr, cols):
+    """Host-only: the SELL-32 arrays of the P1 walk kernels as a dict (device order)."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    n_cells, ns = len(dm) // 4, (n_owned + 31) // 32
+    mw = C.c_int()
+    off = {k: np.zeros(ns + 1, dtype=np.int64) for k in ("mat_off", "adj_off", "walk1_off")}
+    data = {}
+    for fill in (False, True):
+        if fill:
+            data = {"cols": np.zeros(int(off["mat_off"][-1]), dtype=np.int32),
+                    "walk": np.zeros(int(off["adj_off"][-1]), dtype=np.uint32),
+                    "walk1": np.zeros(int(off["walk1_off"][-1]), dtype=np.uint32)}
+        rc = lib().ptb_debug_p1_layout(n_cells, _ptr(dm), n_owned, _ptr(rp), _ptr(cl), C.byref(mw),
+                                       _ptr(off["mat_off"]), _ptr(off["adj_off"]),
+                                       _ptr(off["walk1_off"]), _ptr(data.get("cols")),
+                                       _ptr(data.get("walk")), _ptr(data.get("walk1")))
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+    return dict(off, **data, max_w=mw.value, n_slices=ns)
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

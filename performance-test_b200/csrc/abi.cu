@@ -829,6 +829,36 @@ int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n
   });
 }
 
+int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, int* max_w, int64_t* mat_off,
+                        int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
+                        uint32_t* walk1)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && mat_off && adj_off && walk1_off, "ptb_debug_p1_layout: NULL argument");
+    RowAdjacency adj;
+    std::vector<std::uint16_t> so;
+    build_row_adjacency(dofmap, n_cells, 4, n_owned, adj);
+    const std::int64_t max_so = build_slot_offsets(dofmap, 4, n_owned, adj, rowptr, cols, so);
+    need(max_so >= 0 && max_so < 255, "ptb_debug_p1_layout: pattern does not cover the cells / row too long");
+    SellLayout L;
+    build_sell_layout(n_owned, 4, rowptr, cols, adj, so, max_so, L);
+    build_walk(n_owned, adj, so, L);
+    build_walk_single(n_owned, adj, L);
+    if (max_w)
+      *max_w = L.max_w;
+    std::copy(L.mat_off.begin(), L.mat_off.end(), mat_off);
+    std::copy(L.adj_off.begin(), L.adj_off.end(), adj_off);
+    std::copy(L.walk1_off.begin(), L.walk1_off.end(), walk1_off);
+    if (cols_sell)
+      std::copy(L.cols.begin(), L.cols.end(), cols_sell);
+    if (walk)
+      std::copy(L.walk.begin(), L.walk.end(), walk);
+    if (walk1)
+      std::copy(L.walk1.begin(), L.walk1.end(), walk1);
+  });
+}
+
 int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets)
 {

@@ -320,6 +320,11 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
     A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
 }
 
+} // namespace
+
+#ifndef PTB_HOST_EMU // launchers: device build only
+namespace
+{
 template <int WARPS>
 void launch_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
 {
@@ -385,5 +390,7 @@ bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
   c->launches += 1;
   return true;
 }
+
+#endif // PTB_HOST_EMU
 
 } // namespace ptb

@@ -405,6 +405,7 @@ assemble_matrix_p1_walk3(MatrixArgs A, const std::uint32_t* __restrict__ walk)
 
 } // namespace
 
+#ifndef PTB_HOST_EMU // launchers: device build only
 namespace
 {
 template <int WARPS, bool PREFETCH>
@@ -456,5 +457,7 @@ bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A)
   default: return pf ? launch_walk<2, true>(c, A) : launch_walk<2, false>(c, A);
   }
 }
+
+#endif // PTB_HOST_EMU
 
 } // namespace ptb

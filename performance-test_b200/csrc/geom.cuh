@@ -55,6 +55,9 @@ __device__ __forceinline__ P1Geom p1_geometry(Vec3 e1, Vec3 e2, Vec3 e3)
 // (an element volume of a valid mesh is never denormal), so callers stay branch-free.
 __device__ __forceinline__ double rcp_nr(double d)
 {
+#ifdef PTB_HOST_EMU // tests/emu runs this directory's kernel sources on the host (test harness only)
+  return 1.0 / d;
+#else
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
   double e = fma(-d, x, 1.0);
@@ -62,11 +65,16 @@ __device__ __forceinline__ double rcp_nr(double d)
   x = fma(x, e, x);
   e = fma(-d, x, 1.0);
   return fma(x, e, x);
+#endif
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
+#ifdef PTB_HOST_EMU
+  (void)p;
+#else
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 } // namespace

@@ -1,0 +1,127 @@
+"""The P1 walk kernels' *sources* executed on the host (tests/emu/emu_kernels.cpp): one std::thread
+per CUDA thread, a barrier for __syncthreads, a plain array for shared memory. This checks what the
+numpy restatements cannot: the kernels' own indexing, shared-memory layouts, register-position
+logic and epilogues -- for the default star-walk kernel (which has also run on the B200: if the
+harness and the GPU disagree the harness is wrong) and for the opt-in kernels that have not yet
+seen a GPU. CPU only; nothing here is part of the product path.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "emu_kernels.cpp")
+OUT = os.path.join(HERE, "emu", "_build", "libemu.so")
+CSRC = os.path.join(os.path.dirname(HERE), "performance-test_b200", "csrc")
+
+
+@pytest.fixture(scope="module")
+def emu():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in
+                    ("assemble_walk.cu", "assemble_gwalk.cu", "geom.cuh", "kernels.h", "ctx.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        os.makedirs(os.path.dirname(OUT), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-o", OUT, SRC], check=True)
+    return C.CDLL(OUT)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _inputs(pt, P):
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    nl = P.n_owned + P.n_ghost
+    xdof = np.zeros((nl, 4))
+    xdof[:, :3] = P["dof_x"].reshape(-1, 3)
+    bc = np.zeros(nl, np.uint8)
+    bc[P["bc_dofs"]] = 1
+    return L, np.ascontiguousarray(xdof.reshape(-1)), bc
+
+
+def _sell_to_csr(P, L, vals_sell, bs2):
+    rp = P["rowptr"]
+    out = np.zeros((rp[-1], bs2))
+    for r in range(P.n_owned):
+        mo = L["mat_off"][r >> 5]
+        for k in range(rp[r + 1] - rp[r]):
+            for e in range(bs2):
+                out[rp[r] + k, e] = vals_sell[(mo + k * 32) * bs2 + e * 32 + (r & 31)]
+    return out.reshape(-1)
+
+
+def _row_diag(P, ref, bs2):
+    rows = np.repeat(np.arange(P.n_owned), np.diff(P["rowptr"]))
+    diag = np.zeros(P.n_owned)
+    d = P["cols"] == rows
+    diag[rows[d]] = np.abs(ref.reshape(-1, bs2)[d]).max(axis=1)
+    return np.repeat(diag[rows], bs2)
+
+
+MATRIX = [(0, "poisson", (5, 4, 6), 0, 1), (1, "poisson", (5, 4, 6), 0, 1), (0, "poisson", (1, 1, 1), 0, 1),
+          (3, "poisson", (5, 4, 6), 0, 1), (4, "poisson", (3, 7, 2), 0, 1), (3, "poisson", (1, 1, 1), 0, 1),
+          (3, "poisson", (4, 3, 5), 1, 2),
+          (2, "elasticity", (4, 3, 3), 0, 1), (2, "elasticity", (1, 1, 2), 0, 1), (2, "elasticity", (3, 3, 4), 1, 2)]
+
+
+@pytest.mark.parametrize("variant,ptype,dims,rank,nranks", MATRIX)
+def test_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emu, variant, ptype, dims, rank, nranks):
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    L, xdof, bc = _inputs(pt, P)
+    bs2 = P.bs * P.bs
+    vals = np.full(int(L["mat_off"][-1]) * bs2, np.nan)
+    dinv = np.full(P.n_owned * P.bs, np.nan)
+    rp = np.ascontiguousarray(P["rowptr"])
+    rc = emu.emu_assemble_matrix(variant, P.n_owned, L["n_slices"], L["max_w"], P.bs, _p(bc), _p(rp),
+                                 _p(L["mat_off"]), _p(L["adj_off"]), _p(L["cols"]), _p(xdof),
+                                 _p(L["walk"]), _p(L["walk1"]), _p(L["walk1_off"]), _p(vals), _p(dinv))
+    assert rc == 0
+    assert not np.isnan(vals).any(), "a stored value (padding included) was never written"
+    got = _sell_to_csr(P, L, vals, bs2)
+    ref = oracle.assemble_matrix(P)
+    assert (np.abs(got - ref) / _row_diag(P, ref, bs2)).max() <= 1e-12
+    A = ref.reshape(-1, P.bs, P.bs)
+    rows = np.repeat(np.arange(P.n_owned), np.diff(P["rowptr"]))
+    own = P["cols"] == rows
+    d = np.stack([A[own][:, i, i] for i in range(P.bs)], axis=1).reshape(-1)
+    assert np.allclose(dinv, 1.0 / d, rtol=1e-12, atol=0)
+    # padding entries of the SELL slices must be exact zeros (the SpMV multiplies them)
+    mask = np.ones(len(vals), bool)
+    for r in range(P.n_owned):
+        mo = L["mat_off"][r >> 5]
+        for k in range(P["rowptr"][r + 1] - P["rowptr"][r]):
+            for e in range(bs2):
+                mask[(mo + k * 32) * bs2 + e * 32 + (r & 31)] = False
+    assert np.all(vals[mask] == 0.0)
+
+
+VECTOR = [("poisson", (5, 4, 6), 0, 1, 4), ("poisson", (1, 1, 1), 0, 1, 1), ("poisson", (4, 3, 5), 1, 2, 4),
+          ("elasticity", (3, 4, 3), 0, 1, 4), ("elasticity", (2, 2, 5), 1, 2, 8)]
+
+
+@pytest.mark.parametrize("ptype,dims,rank,nranks,warps", VECTOR)
+def test_vector_kernel_source_reproduces_the_oracle(pt, oracle, emu, ptype, dims, rank, nranks, warps):
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    L, xdof, bc = _inputs(pt, P)
+    b = np.full(P.n_owned * P.bs, np.nan)
+    f = np.ascontiguousarray(P["f"])
+    rc = emu.emu_assemble_vector(P.bs, warps, P.n_owned, L["n_slices"], L["max_w"], _p(bc),
+                                 _p(L["mat_off"]), _p(L["cols"]), _p(xdof), _p(f), _p(L["walk1"]),
+                                 _p(L["walk1_off"]), _p(b))
+    assert rc == 0 and not np.isnan(b).any()
+    b_ref = oracle.assemble_vector(P)
+    keep = np.ones(P.n_owned, bool)
+    if ptype == "poisson":  # the g v ds facet term belongs to another kernel
+        touched = np.zeros(P.n_owned + P.n_ghost, bool)
+        dm = P["dofmap"].reshape(-1, 4)
+        for c, lf in zip(P["facet_cells"], P["facet_local"]):
+            touched[[dm[c, v] for v in range(4) if v != lf]] = True
+        keep = ~touched[:P.n_owned]
+    keep = np.repeat(keep, P.bs)
+    if keep.any():
+        assert np.abs(b - b_ref)[keep].max() <= 1e-12 * np.abs(b_ref).max()
