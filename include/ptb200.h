@@ -163,6 +163,12 @@ int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
                         int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
                         uint32_t* walk1);
 
+/* The compressed column indices of the scalar SpMV (layout.h: cdelta / xoff / colsx), host only:
+ * cdelta [mat_off[S]/32], xoff [S + 1]; colsx [xoff[S]] may be NULL on the first call. */
+int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
+                                 const int32_t* cols, int32_t* cdelta, int64_t* xoff,
+                                 int32_t* colsx);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

@@ -72,6 +72,7 @@ def lib():
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
+        L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
         L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
@@ -154,6 +155,23 @@ def p1_layout(dofmap, n_owned, rowptr, cols):
         if rc != 0:
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return dict(off, **data, max_w=mw.value, n_slices=ns)
+
+
+def compressed_columns(n_rows, n_cols, rowptr, cols, n_sell_entries):
+    """Host-only: (cdelta, xoff, colsx) of the scalar SpMV for a pattern whose SELL-32 layout has
+    n_sell_entries padded entries (mat_off[-1])."""
+    rp, cl = _a(rowptr, np.int64), _a(cols, np.int32)
+    cdelta = np.zeros(n_sell_entries // 32, dtype=np.int32)
+    xoff = np.zeros((n_rows + 31) // 32 + 1, dtype=np.int64)
+    colsx = None
+    for fill in (False, True):
+        if fill:
+            colsx = np.zeros(max(int(xoff[-1]), 1), dtype=np.int32)
+        rc = lib().ptb_debug_compressed_columns(n_rows, n_cols, _ptr(rp), _ptr(cl), _ptr(cdelta),
+                                                _ptr(xoff), _ptr(colsx))
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+    return cdelta, xoff, colsx
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

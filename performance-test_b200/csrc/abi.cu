@@ -859,6 +859,25 @@ int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
   });
 }
 
+int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
+                                 const int32_t* cols, int32_t* cdelta, int64_t* xoff,
+                                 int32_t* colsx)
+{
+  return guarded(nullptr, [&] {
+    need(rowptr && cols && cdelta && xoff, "ptb_debug_compressed_columns: NULL argument");
+    RowAdjacency adj;
+    adj.ptr.assign(static_cast<std::size_t>(n_rows) + 1, 0);
+    std::vector<std::uint16_t> so;
+    SellLayout L;
+    build_sell_layout(n_rows, 4, rowptr, cols, adj, so, 0, L);
+    compress_columns(n_rows, n_cols, rowptr, L);
+    std::copy(L.cdelta.begin(), L.cdelta.end(), cdelta);
+    std::copy(L.xoff.begin(), L.xoff.end(), xoff);
+    if (colsx)
+      std::copy(L.colsx.begin(), L.colsx.end(), colsx);
+  });
+}
+
 int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets)
 {

@@ -43,11 +43,7 @@ __device__ __forceinline__ double ldp(const double* q)
   else if constexpr (L == Ld::CG)
     return __ldcg(q);
   else
-  {
-    double v;
-    asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(q));
-    return v;
-  }
+    return ld_ca_f64(q);
 }
 
 // One SELL-32 slice: y[row] = sum_k vals * p[col]; returns this row's p.y contribution.
@@ -176,16 +172,6 @@ struct FusedHalo
   double* pw;                     // writable alias of p (ghost part)
 };
 
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // The pull of one CTA's share of the receive list (generic Scatterer index lists).
 __device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHalo& FH)
@@ -351,6 +337,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   }
 }
 
+#ifndef PTB_HOST_EMU // TMA / mbarrier PTX: device build only
 // ------------------------------------------------------------------------------------------
 // TMA-staged variant of the scalar operator (rows with <= 32 stored entries, i.e. P1).
 // With the column indices compressed away the kernel streams almost nothing but matrix values,
@@ -569,6 +556,8 @@ spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, 
     }
   }
 }
+
+#endif // PTB_HOST_EMU
 
 // Global sums for the consumer kernels: one thread per CTA collects the nranks partials from the
 // local window (peer mode) or reads the locally reduced / NCCL-reduced values.
@@ -822,16 +811,6 @@ struct LoopArgs
   unsigned int ebase; // reduction epochs: ebase + 2 (j-1) for p.y, + 1 for (r.r, r.z)
 };
 
-__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p)
-{
-  unsigned int v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v)
-{
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
 
 // Grid barrier fused with a deterministic reduction of NV values per CTA (NV = 0: barrier only).
 // On return every thread holds the (peer-)global sums in out[].
@@ -1060,6 +1039,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
   }
 }
 
+#ifndef PTB_HOST_EMU // host launchers: device build only
 // Grids are sized to exactly one resident wave: SMs x (CTAs of this kernel that fit on an SM),
 // capped by the work. A second partial wave would run at low occupancy and stretch the tail.
 template <typename K>
@@ -1314,5 +1294,9 @@ void launch_sqnorm(ptb_ctx* c, const double* v, std::int64_t n, double* out_dev)
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
+
+#else
+} // namespace
+#endif // PTB_HOST_EMU
 
 } // namespace ptb

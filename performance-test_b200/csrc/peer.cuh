@@ -1,31 +1,11 @@
 // Device-side primitives of the peer-memory path (structures and protocol: peer.h).
 #pragma once
 #include "peer.h"
+#include "sync_ops.cuh"
 #include <cuda_runtime.h>
 
 namespace ptb
 {
-
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
-{
-  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
-{
-  unsigned long long v;
-  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
 
 /// Publish this rank's two partial sums for reduction `epoch` to every rank (one thread).
 __device__ __forceinline__ void peer_publish(const PeerView& P, unsigned int epoch, double v0,

@@ -1,0 +1,80 @@
+// Scoped loads/stores of the synchronisation protocols (grid barrier, fused halo, peer windows)
+// in one place. Device build: the PTX below. PTB_HOST_EMU (tests/emu runs the kernel sources on
+// the host, test harness only): the GCC atomics with the same ordering.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ptb
+{
+
+#ifdef PTB_HOST_EMU
+template <typename T>
+__device__ __forceinline__ T emu_ld(const T* p, int order)
+{
+  return __atomic_load_n(p, order);
+}
+template <typename T>
+__device__ __forceinline__ void emu_st(T* p, T v, int order)
+{
+  __atomic_store_n(p, v, order);
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) { emu_st(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) { return emu_ld(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) { emu_st(p, v, __ATOMIC_RELAXED); }
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) { return emu_ld(p, __ATOMIC_RELAXED); }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p) { return emu_ld(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v) { emu_st(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return emu_ld(p, __ATOMIC_ACQUIRE); }
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) { emu_st(p, v, __ATOMIC_RELEASE); }
+__device__ __forceinline__ double ld_ca_f64(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
+#else
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long* p)
+{
+  unsigned long long v;
+  asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned long long v)
+{
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v)
+{
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// coherent cached load: L1 lines are dropped by the acquire of the grid barrier (never the .nc path)
+__device__ __forceinline__ double ld_ca_f64(const double* q)
+{
+  double v;
+  asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(q));
+  return v;
+}
+#endif
+
+} // namespace ptb

@@ -125,3 +125,79 @@ def test_vector_kernel_source_reproduces_the_oracle(pt, oracle, emu, ptype, dims
     keep = np.repeat(keep, P.bs)
     if keep.any():
         assert np.abs(b - b_ref)[keep].max() <= 1e-12 * np.abs(b_ref).max()
+
+
+# ---- the persistent CG loop (csrc/cg.cu cg_loop): G copies of the harness = G concurrent CTAs ------
+
+CG_SRC = os.path.join(HERE, "emu", "emu_cg.cpp")
+CGSTATE = np.dtype([("py", "f8"), ("rr", "f8"), ("rz", "f8"), ("rz_old", "f8"), ("rnorm0", "f8"),
+                    ("rtol2", "f8"), ("rnorm", "f8"), ("alpha", "f8"), ("k", "i4"), ("conv", "i4")])
+
+
+@pytest.fixture(scope="module")
+def emucg():
+    import shutil
+    base = os.path.join(HERE, "emu", "_build", "libemucg.so")
+    deps = [CG_SRC] + [os.path.join(CSRC, f) for f in
+                       ("cg.cu", "reduce.cuh", "peer.cuh", "peer.h", "sync_ops.cuh", "kernels.h", "ctx.h")]
+    if not os.path.exists(base) or any(os.path.getmtime(d) > os.path.getmtime(base) for d in deps):
+        os.makedirs(os.path.dirname(base), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-o", base, CG_SRC], check=True)
+    libs = []
+    for g in range(4):  # one copy per CTA: `__shared__` variables are statics of the copy
+        path = base.replace(".so", f"_{g}.so")
+        shutil.copyfile(base, path)
+        libs.append(C.CDLL(path))
+    assert libs[0].emu_cgstate_size() == CGSTATE.itemsize
+    return libs
+
+
+@pytest.mark.parametrize("ptype,dims,precond,grid", [("poisson", (6, 5, 7), "jacobi", 3),
+                                                     ("poisson", (6, 5, 7), "none", 1),
+                                                     ("poisson", (9, 2, 2), "jacobi", 4),
+                                                     ("elasticity", (3, 4, 3), "jacobi", 2)])
+def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptype, dims, precond, grid):
+    import threading
+    P = pt.host.Problem(ptype, 1, *dims)
+    bs, n, rtol = P.bs, P.n_owned * P.bs, 1e-8
+    A, b = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    x_ref, k_ref, _ = oracle.cg(bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=500, rtol=rtol,
+                                precond=precond)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    bs2 = bs * bs
+    vals = np.zeros(int(L["mat_off"][-1]) * bs2)
+    rp, Ab = P["rowptr"], A.reshape(-1, bs2)
+    for r in range(P.n_owned):
+        mo = L["mat_off"][r >> 5]
+        for k in range(rp[r + 1] - rp[r]):
+            vals[(mo + k * 32) * bs2 + np.arange(bs2) * 32 + (r & 31)] = Ab[rp[r] + k]
+    cdelta, xoff, colsx = pt.abi.compressed_columns(P.n_owned, P.n_owned + P.n_ghost, rp, P["cols"],
+                                                    int(L["mat_off"][-1]))
+    order = np.arange(L["n_slices"], dtype=np.int32)
+    rows = np.repeat(np.arange(P.n_owned), np.diff(rp))
+    own = P["cols"] == rows
+    diag = np.stack([A.reshape(-1, bs, bs)[own][:, i, i] for i in range(bs)], axis=1).reshape(-1)
+    dinv = 1.0 / diag if precond == "jacobi" else np.ones(n)
+    x, r, y = np.zeros(n), b.copy(), np.zeros(n)
+    p = dinv * r
+    st = np.zeros(2, dtype=CGSTATE)
+    rr, rz = float(r @ r), float(r @ (dinv * r))
+    st[1] = (0.0, rr, rz, rz, rr, rtol * rtol, rr, 0.0, 0, 0)
+    partials, bar, sums = np.zeros(2 * grid), np.zeros(2, np.uint32), np.zeros(2)
+    args = [P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(vals), _p(cdelta), _p(colsx),
+            _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(partials), _p(bar),
+            _p(sums), 500]
+    threads = [threading.Thread(target=emucg[g].emu_cg_loop_block, args=[bs, g, grid] + args)
+               for g in range(grid)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=240)
+        assert not t.is_alive(), "grid barrier did not release"
+    fin = st[int(np.argmax(st["k"]))]
+    assert fin["conv"] == 1 and abs(int(fin["k"]) - k_ref) <= 1
+    assert np.sqrt(fin["rnorm"] / fin["rnorm0"]) < rtol
+    assert np.abs(x - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
+    assert bar[0] == 0  # every barrier was released and reset
