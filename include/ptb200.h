@@ -169,6 +169,12 @@ int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* 
                                  const int32_t* cols, int32_t* cdelta, int64_t* xoff,
                                  int32_t* colsx);
 
+/* The slice visiting order of the operator kernels (layout.h build_slice_order; slices without
+ * ghost columns first), host only: order [ceil(n_rows/32)], *n_interior = number of leading
+ * slices that read no ghost column. */
+int ptb_debug_slice_order(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
+                          int32_t* order, int32_t* n_interior);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

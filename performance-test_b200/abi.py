@@ -72,6 +72,7 @@ def lib():
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
+        L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
         L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
@@ -172,6 +173,16 @@ def compressed_columns(n_rows, n_cols, rowptr, cols, n_sell_entries):
         if rc != 0:
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return cdelta, xoff, colsx
+
+
+def slice_order(n_rows, rowptr, cols):
+    """Host-only: (order, n_interior) of the operator kernels' slice visiting order."""
+    rp, cl = _a(rowptr, np.int64), _a(cols, np.int32)
+    order = np.zeros((n_rows + 31) // 32, dtype=np.int32)
+    ni = C.c_int32()
+    if lib().ptb_debug_slice_order(n_rows, _ptr(rp), _ptr(cl), _ptr(order), C.byref(ni)) != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return order, ni.value
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

@@ -878,6 +878,22 @@ int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* 
   });
 }
 
+int ptb_debug_slice_order(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
+                          int32_t* order, int32_t* n_interior)
+{
+  return guarded(nullptr, [&] {
+    need(rowptr && cols && order && n_interior, "ptb_debug_slice_order: NULL argument");
+    RowAdjacency adj;
+    adj.ptr.assign(static_cast<std::size_t>(n_rows) + 1, 0);
+    std::vector<std::uint16_t> so;
+    SellLayout L;
+    build_sell_layout(n_rows, 4, rowptr, cols, adj, so, 0, L);
+    std::vector<std::int32_t> ord;
+    build_slice_order(L, n_rows, 8, false, ord, *n_interior);
+    std::copy(ord.begin(), ord.end(), order);
+  });
+}
+
 int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets)
 {

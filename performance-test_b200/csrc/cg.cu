@@ -821,8 +821,13 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
 {
   __shared__ bool is_last;
   __shared__ double bsum[2];
+  // Thread 0 may only arrive for the CTA once every thread of the CTA has finished the phase:
+  // block_sum synchronises the CTA on its way; the plain barrier has to do it itself. (Found by
+  // the host harness, tests/emu: without it a neighbour could pull p while it was being written.)
   if constexpr (NV > 0)
     block_sum<NV>(v, red);
+  else
+    __syncthreads();
   unsigned int gen = 0;
   if (threadIdx.x == 0)
   {

@@ -143,5 +143,64 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
   return 0;
 }
 
+// One CTA of cg_loop<BS, true> (fused halo, peer windows) of rank `rank`; windows / peer_p are the
+// ranks' PeerWindow blocks and the neighbours' p vectors, all in host memory shared by the copies.
+int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, void** windows,
+                           int n_nbr, const int* nbr_rank, const int* recv_displ,
+                           const double** peer_p, const int32_t* remote_indices,
+                           const int32_t* src_index, int n_interior, int npull,
+                           unsigned long long* ready, int32_t n_rows, int32_t n_slices,
+                           const int64_t* mat_off, const int32_t* cols, const double* vals,
+                           const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
+                           const int32_t* order, const double* dinv, double* r, double* p,
+                           double* x, double* y, void* st, double* partials, unsigned int* bar,
+                           double* sums, int n_it)
+{
+  using namespace ptb;
+  LoopArgs L{};
+  L.A = SpmvArgs{n_rows, n_slices, mat_off, cols, vals, cdelta, colsx, xoff};
+  L.n = static_cast<std::int64_t>(n_rows) * bs;
+  L.dinv = dinv, L.r = r, L.p = p, L.x = x, L.y = y;
+  L.st = static_cast<CgState*>(st);
+  L.partials = partials, L.bar = bar, L.sums = sums;
+  L.it0 = 0, L.n_it = n_it, L.ebase = 1;
+  PeerView P{};
+  P.rank = rank, P.nranks = nranks;
+  for (int q = 0; q < nranks; ++q)
+    P.win[q] = static_cast<PeerWindow*>(windows[q]);
+  FusedHalo FH{};
+  FH.H.n_nbr = n_nbr, FH.H.bs = bs;
+  for (int q = 0; q < n_nbr; ++q)
+    FH.H.nbr_rank[q] = nbr_rank[q], FH.H.peer_p[q] = peer_p[q];
+  for (int q = 0; q <= n_nbr; ++q)
+    FH.H.recv_displ[q] = recv_displ[q];
+  FH.H.remote_indices = remote_indices, FH.H.src_index = src_index;
+  FH.order = order, FH.n_interior = n_interior, FH.npull = npull, FH.epoch = 0;
+  FH.ready = ready, FH.pw = p;
+  constexpr unsigned T = SPMV_THREADS;
+  gridDim.x = grid, blockDim.x = T;
+  std::barrier<> cta(T);
+  emu_cta = &cta;
+  std::vector<std::unique_ptr<std::barrier<>>> wb;
+  for (unsigned w = 0; w < T / 32; ++w)
+  {
+    wb.push_back(std::make_unique<std::barrier<>>(32));
+    emu_warp[w] = wb.back().get();
+  }
+  std::vector<std::thread> th;
+  for (unsigned t = 0; t < T; ++t)
+    th.emplace_back([=] {
+      threadIdx.x = t, blockIdx.x = block;
+      if (bs == 1)
+        cg_loop<1, true>(L, P, FH);
+      else
+        cg_loop<3, true>(L, P, FH);
+    });
+  for (auto& t : th)
+    t.join();
+  return 0;
+}
+
 int emu_cgstate_size() { return static_cast<int>(sizeof(ptb::CgState)); }
+int emu_peerwindow_size() { return static_cast<int>(sizeof(ptb::PeerWindow)); }
 }

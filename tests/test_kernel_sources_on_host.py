@@ -201,3 +201,85 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     assert np.sqrt(fin["rnorm"] / fin["rnorm0"]) < rtol
     assert np.abs(x - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
     assert bar[0] == 0  # every barrier was released and reset
+
+
+@pytest.mark.parametrize("ptype,dims", [("poisson", (4, 3, 9)), ("elasticity", (2, 3, 5))])
+def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
+    """Two ranks x two CTAs of cg_loop<BS, true>: CTA 0 of a rank is the puller (publishes 'p is
+    ready', waits for the neighbour, pulls the ghost values out of the neighbour's vector, takes
+    the ghost-reading slices), CTA 1 the worker; the dot products go through the LL windows. The
+    four CTAs are four copies of the harness running at once in one address space."""
+    import threading
+    rtol, grid, nranks = 1e-8, 2, 2
+    G = pt.host.Problem(ptype, 1, *dims)
+    x_ref, k_ref, _ = oracle.cg(G.bs, G.n_owned, G["rowptr"], G["cols"], oracle.assemble_matrix(G),
+                                oracle.assemble_vector(G), kmax=500, rtol=rtol, precond="jacobi")
+    assert emucg[0].emu_peerwindow_size() % 8 == 0
+    windows = [np.zeros(emucg[0].emu_peerwindow_size() // 8, np.uint64) for _ in range(nranks)]
+    win_ptrs = (C.c_void_p * nranks)(*[w.ctypes.data for w in windows])
+    R = []
+    for q in range(nranks):
+        P = pt.host.Problem(ptype, 1, *dims, q, nranks)
+        bs, n, nl = P.bs, P.n_owned * P.bs, (P.n_owned + P.n_ghost) * P.bs
+        bs2 = bs * bs
+        A, b = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+        L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+        vals = np.zeros(int(L["mat_off"][-1]) * bs2)
+        rp, Ab = P["rowptr"], A.reshape(-1, bs2)
+        for r in range(P.n_owned):
+            mo = L["mat_off"][r >> 5]
+            for k in range(rp[r + 1] - rp[r]):
+                vals[(mo + k * 32) * bs2 + np.arange(bs2) * 32 + (r & 31)] = Ab[rp[r] + k]
+        cdelta, xoff, colsx = pt.abi.compressed_columns(P.n_owned, P.n_owned + P.n_ghost, rp,
+                                                        P["cols"], int(L["mat_off"][-1]))
+        order, n_int = pt.abi.slice_order(P.n_owned, rp, P["cols"])
+        rows = np.repeat(np.arange(P.n_owned), np.diff(rp))
+        own = P["cols"] == rows
+        diag = np.stack([A.reshape(-1, bs, bs)[own][:, i, i] for i in range(bs)], axis=1).reshape(-1)
+        d = dict(P=P, L=L, vals=vals, cdelta=cdelta, xoff=xoff, colsx=colsx, order=order, n_int=n_int,
+                 dinv=1.0 / diag, x=np.zeros(nl), r=b.copy(), y=np.zeros(n), p=np.zeros(nl),
+                 st=np.zeros(2, dtype=CGSTATE), partials=np.zeros(2 * grid),
+                 bar=np.zeros(2, np.uint32), sums=np.zeros(2), ready=np.zeros(256, np.uint64),
+                 nbr=np.ascontiguousarray(P["nbr_ranks"], dtype=np.int32),
+                 recv_displ=np.ascontiguousarray(P["recv_displ"], dtype=np.int32),
+                 remote=np.ascontiguousarray(P["remote_indices"], dtype=np.int32))
+        d["p"][:n] = d["dinv"] * d["r"]
+        R.append(d)
+    rr = sum(float(d["r"] @ d["r"]) for d in R)
+    rz = sum(float(d["r"] @ (d["dinv"] * d["r"])) for d in R)
+    for q, d in enumerate(R):
+        d["st"][1] = (0.0, rr, rz, rz, rr, rtol * rtol, rr, 0.0, 0, 0)
+        src = []
+        for nb in d["nbr"]:
+            o = R[nb]["P"]
+            j = list(o["nbr_ranks"]).index(q)
+            src.append(np.array(o["local_indices"][o["send_displ"][j]:o["send_displ"][j + 1]]))
+        d["src"] = np.concatenate(src).astype(np.int32)
+        assert len(d["src"]) == d["recv_displ"][-1]
+        d["peer_p"] = (C.c_void_p * len(d["nbr"]))(*[R[nb]["p"].ctypes.data for nb in d["nbr"]])
+    threads = []
+    for q, d in enumerate(R):
+        P, L = d["P"], d["L"]
+        for g in range(grid):
+            args = [P.bs, g, grid, q, nranks, win_ptrs, len(d["nbr"]), _p(d["nbr"]), _p(d["recv_displ"]),
+                    d["peer_p"], _p(d["remote"]), _p(d["src"]), d["n_int"], 1, _p(d["ready"]),
+                    P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(d["vals"]),
+                    _p(d["cdelta"]), _p(d["colsx"]), _p(d["xoff"]), _p(d["order"]), _p(d["dinv"]),
+                    _p(d["r"]), _p(d["p"]), _p(d["x"]), _p(d["y"]), _p(d["st"]), _p(d["partials"]),
+                    _p(d["bar"]), _p(d["sums"]), 500]
+            threads.append(threading.Thread(target=emucg[q * grid + g].emu_cg_loop_block_peer, args=args))
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+        assert not t.is_alive(), "a CTA is stuck (grid barrier, halo flag or window all-reduce)"
+    ks = []
+    for d in R:
+        fin = d["st"][int(np.argmax(d["st"]["k"]))]
+        assert fin["conv"] == 1
+        ks.append(int(fin["k"]))
+        P = d["P"]
+        gidx = ((P.global_offset + np.arange(P.n_owned))[:, None] * P.bs + np.arange(P.bs)).reshape(-1)
+        err = np.abs(d["x"][:P.n_owned * P.bs] - x_ref[gidx]).max() / np.abs(x_ref).max()
+        assert err <= 1e-6, (err, ks, k_ref)
+    assert ks[0] == ks[1] and abs(ks[0] - k_ref) <= 1
