@@ -878,6 +878,7 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
     while (ld_acquire_gpu_u32(&L.bar[1]) == gen)
     {
     }
+    __threadfence(); // belt and braces: the CTA's later cached loads must not hit pre-barrier L1 lines
   }
   if constexpr (NV > 0)
   {

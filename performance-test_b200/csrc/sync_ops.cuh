@@ -3,15 +3,22 @@
 // the host, test harness only): the GCC atomics with the same ordering.
 #pragma once
 #include <cuda_runtime.h>
+#ifdef PTB_HOST_EMU
+#include <sched.h>
+#endif
 
 namespace ptb
 {
 
 #ifdef PTB_HOST_EMU
+// every scoped load sits in a spin loop somewhere: give the core away so that the hundreds of
+// host threads of the harness make progress
 template <typename T>
 __device__ __forceinline__ T emu_ld(const T* p, int order)
 {
-  return __atomic_load_n(p, order);
+  const T v = __atomic_load_n(p, order);
+  sched_yield();
+  return v;
 }
 template <typename T>
 __device__ __forceinline__ void emu_st(T* p, T v, int order)
