@@ -27,3 +27,10 @@ except Exception as e:
 PY
   done
 done
+
+# Two GPUs (gpurun --gpus 2): the existing 2-rank tests with the persistent loop switched on; the
+# spawned ranks inherit the environment, so no extra test code is needed:
+#   PTB_CG_PERSISTENT=1 timeout 300 python -m pytest tests/test_gpu_multi.py -q -k peer
+# then the strong-scaling point that motivated the kernel:
+#   for p in 0 1; do PTB_CG_PERSISTENT=$p python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
+#     --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --workload elasticity --steps 2 --warmup 1; done
