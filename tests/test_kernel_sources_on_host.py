@@ -283,3 +283,37 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
         err = np.abs(d["x"][:P.n_owned * P.bs] - x_ref[gidx]).max() / np.abs(x_ref).max()
         assert err <= 1e-6, (err, ks, k_ref)
     assert ks[0] == ks[1] and abs(ks[0] - k_ref) <= 1
+
+
+@pytest.mark.parametrize("variant,ptype", [(0, "poisson"), (3, "poisson"), (2, "elasticity")])
+def test_kernel_sources_assemble_partition_independent_bits(pt, emu, variant, ptype):
+    """The walk depends on the mesh topology and the ascending cell order only, so an owned row
+    gets bit-identical values on every partition -- checked here on the
+    kernels' own arithmetic order: 1 rank against the rows of a 3-rank partition."""
+    dims = (3, 2, 7)
+
+    def assemble(rank, nranks):
+        P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+        L, xdof, bc = _inputs(pt, P)
+        bs2 = P.bs * P.bs
+        vals = np.full(int(L["mat_off"][-1]) * bs2, np.nan)
+        dinv = np.full(P.n_owned * P.bs, np.nan)
+        rp = np.ascontiguousarray(P["rowptr"])
+        assert emu.emu_assemble_matrix(variant, P.n_owned, L["n_slices"], L["max_w"], P.bs, _p(bc), _p(rp),
+                                       _p(L["mat_off"]), _p(L["adj_off"]), _p(L["cols"]), _p(xdof),
+                                       _p(L["walk"]), _p(L["walk1"]), _p(L["walk1_off"]), _p(vals),
+                                       _p(dinv)) == 0
+        csr = _sell_to_csr(P, L, vals, bs2).reshape(-1, bs2)
+        glob = np.concatenate([P.global_offset + np.arange(P.n_owned), P["ghost_global"]])
+        out = {}
+        for r in range(P.n_owned):
+            for k in range(rp[r], rp[r + 1]):
+                out[(int(glob[r]), int(glob[P["cols"][k]]))] = csr[k].tobytes()
+        return out
+
+    whole = assemble(0, 1)
+    parts = {}
+    for q in range(3):
+        parts.update(assemble(q, 3))
+    assert parts.keys() == whole.keys()
+    assert all(parts[k] == whole[k] for k in whole)
