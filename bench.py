@@ -432,5 +432,17 @@ def main():
         dist.destroy_process_group()
 
 
+def _json_only_stdout():
+    """The contract is ONE JSON line on stdout. Libraries loaded below print banners of their own
+    (e.g. "NCCL version ..." from ncclCommInitRank writes straight to file descriptor 1), so the
+    process's stdout is pointed at stderr for the duration of the run and `print` keeps the real
+    stdout for the JSON line alone."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real, "w", buffering=1)
+
+
 if __name__ == "__main__":
+    _json_only_stdout()
     main()
