@@ -49,7 +49,7 @@ __device__ __forceinline__ InFlight<NF> gw_issue(std::uint32_t word, const std::
 {
   const bool loads = word != ADJ_INVALID_DEV && ((word >> 16) & 3u) != 3u;
   const int slot = loads ? static_cast<int>(word & 0xFFu) : 0;
-  const std::int64_t col = C[slot * 32];
+  const std::int64_t col = C[slot * 32] & INT32_MAX; // the top bit may carry the Dirichlet flag
   const double2* p = reinterpret_cast<const double2*>(xdof + 4 * col);
   InFlight<NF> v;
   v.xy = __ldg(p);
@@ -222,6 +222,178 @@ assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
 }
 
 // ------------------------------------------------------------------------------------------
+// Matrix, elasticity (BS = 3): the tensor accumulation of assemble_matrix_p1_walk3 (warp a keeps
+// row a of T_j = sum c_own (x) c_j / 6|det| per neighbour, material law in the epilogue) on the
+// one-vertex-per-step walk with direct gathers. CTA = one slice = three warps.
+// Shared memory per slice: T [3][3w][32], DG [9][32], C [w][32] int32 (Dirichlet flag in the top
+// bit): 36 KB at w = 15 instead of 50 KB with the staged star.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96, 5)
+assemble_matrix_p1_gwalk3(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
+                          const std::int64_t* __restrict__ walk1_off)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, a = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x;
+  const std::int64_t mo = A.mat_off[slice], so = walk1_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int w1 = static_cast<int>((walk1_off[slice + 1] - so) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const int mw = A.max_w;
+
+  double* Tall = smem + lane;                  // Tall[(x*mw*3 + k*3 + y)*32] = T_k[x][y]
+  double* T = Tall + a * (mw * 3 * 32);        // this warp's row a
+  double* DG = smem + mw * 9 * 32 + lane;      // DG[(x*3+y)*32]
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem + mw * 9 * 32 + 9 * 32) + lane; // C[k*32]
+
+  const std::uint32_t word0 = w1 > 0 ? __ldg(walk1 + so + lane) : ADJ_INVALID_DEV;
+  const std::uint32_t* wp = walk1 + so + 32 + lane;
+  const int nsteps = w1 - 1;
+  std::uint32_t wd[GW_CHUNK];
+#pragma unroll
+  for (int j = 0; j < GW_CHUNK; ++j)
+    wd[j] = j < nsteps ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+
+  // columns (warp a stages k = a, a+3, ...) and this warp's accumulators
+  for (int k0 = a; k0 < w; k0 += 3 * GW_CHUNK)
+  {
+    std::int32_t c[GW_CHUNK];
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      c[j] = k0 + 3 * j < w ? __ldg(A.cols + mo + (k0 + 3 * j) * 32 + lane) : -1;
+    std::uint8_t b[GW_CHUNK];
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      if (c[j] >= 0)
+        b[j] = __ldg(A.bc + c[j]);
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      if (c[j] >= 0)
+        C[(k0 + 3 * j) * 32] = c[j] | (b[j] ? INT32_MIN : 0);
+  }
+  for (int k = 0; k < 3 * w; ++k)
+    T[k * 32] = 0.0;
+  __syncthreads();
+
+  const bool valid0 = word0 != ADJ_INVALID_DEV;
+  const int o0 = valid0 ? word0 & 0xFFu : 0, o1 = valid0 ? (word0 >> 8) & 0xFFu : 0,
+            o2 = valid0 ? (word0 >> 16) & 0xFFu : 0;
+  Vec3 e0 = load_point(A.xdof, C[o0 * 32] & INT32_MAX) - X0;
+  Vec3 e1 = load_point(A.xdof, C[o1 * 32] & INT32_MAX) - X0;
+  Vec3 e2 = load_point(A.xdof, C[o2 * 32] & INT32_MAX) - X0;
+  InFlight<0> q[GW_AHEAD];
+#pragma unroll
+  for (int j = 0; j < GW_AHEAD; ++j)
+    q[j] = gw_issue<0>(wd[j], C, A.xdof, nullptr, 1, 0);
+  int s0 = o0, s1 = o1, s2 = o2;
+  Vec3 n0 = cross(e1, e2), n1 = cross(e2, e0), n2 = cross(e0, e1);
+  const Vec3 zero = {0.0, 0.0, 0.0};
+  Vec3 t0 = zero, t1 = zero, t2 = zero, dg = zero; // row a of the tensor accumulators
+  auto cell = [&](bool compute) {
+    const double det = dot(e0, n0);
+    const double r = compute ? rcp_nr(6.0 * fabs(det)) : 0.0;
+    const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
+    const double qa = r * comp(c0, a);
+    dg = Vec3{fma(qa, c0.x, dg.x), fma(qa, c0.y, dg.y), fma(qa, c0.z, dg.z)};
+    t0 = Vec3{fma(qa, n0.x, t0.x), fma(qa, n0.y, t0.y), fma(qa, n0.z, t0.z)};
+    t1 = Vec3{fma(qa, n1.x, t1.x), fma(qa, n1.y, t1.y), fma(qa, n1.z, t1.z)};
+    t2 = Vec3{fma(qa, n2.x, t2.x), fma(qa, n2.y, t2.y), fma(qa, n2.z, t2.z)};
+  };
+  cell(valid0);
+  auto flush = [&](int slot, const Vec3& t) {
+    T[(slot * 3 + 0) * 32] += t.x;
+    T[(slot * 3 + 1) * 32] += t.y;
+    T[(slot * 3 + 2) * 32] += t.z;
+  };
+  auto step = [&](std::uint32_t word, const InFlight<0>& v) {
+    const StepBits S = gw_decode(word);
+    const Vec3 xn = {v.xy.x, v.xy.y, v.z_.x};
+    if (S.p0)
+    {
+      flush(S.old, t0);
+      t0 = zero, e0 = xn - X0, s0 = S.nw;
+    }
+    if (S.p1)
+    {
+      flush(S.old, t1);
+      t1 = zero, e1 = xn - X0, s1 = S.nw;
+    }
+    if (S.p2)
+    {
+      flush(S.old, t2);
+      t2 = zero, e2 = xn - X0, s2 = S.nw;
+    }
+    if (S.p1 || S.p2)
+      n0 = cross(e1, e2);
+    if (S.p2 || S.p0)
+      n1 = cross(e2, e0);
+    if (S.p0 || S.p1)
+      n2 = cross(e0, e1);
+    cell(S.compute);
+  };
+  for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
+  {
+    std::uint32_t nx[GW_CHUNK];
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      nx[j] = k0 + GW_CHUNK + j < nsteps ? __ldg(wp + (k0 + GW_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+    {
+      const InFlight<0> cur = q[j % GW_AHEAD];
+      const std::uint32_t ahead = j + GW_AHEAD < GW_CHUNK ? wd[(j + GW_AHEAD) % GW_CHUNK]
+                                                          : nx[(j + GW_AHEAD) % GW_CHUNK];
+      q[j % GW_AHEAD] = gw_issue<0>(ahead, C, A.xdof, nullptr, 1, 0);
+      step(wd[j], cur);
+    }
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  flush(s0, t0);
+  flush(s1, t1);
+  flush(s2, t2);
+  DG[(a * 3 + 0) * 32] = dg.x;
+  DG[(a * 3 + 1) * 32] = dg.y;
+  DG[(a * 3 + 2) * 32] = dg.z;
+  __syncthreads();
+
+  // ---- epilogue: material law per stored block, BC rows/cols, one write per value -----------
+  constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
+  constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const std::int32_t cw = C[k * 32];
+    const bool real = k < len;
+    const bool own = real && (cw & INT32_MAX) == row;
+    const bool bc_any = bc_row || (real && cw < 0);
+    auto Txy = [&](int x, int y) {
+      return own ? DG[(x * 3 + y) * 32] : Tall[(x * mw * 3 + k * 3 + y) * 32];
+    };
+    const double tr = Txy(0, 0) + Txy(1, 1) + Txy(2, 2);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+    {
+      double val = mu * ((a == b ? tr : 0.0) + Txy(b, a)) + lmbda * Txy(a, b);
+      if (bc_any)
+        val = (own && a == b) ? 1.0 : 0.0;
+      if (!real)
+        val = 0.0;
+      A.vals[(mo + k * 32) * 9 + (a * 3 + b) * 32 + lane] = val;
+      if (own && a == b)
+        diag = val;
+    }
+  }
+  if (live)
+    A.dinv[static_cast<std::int64_t>(row) * 3 + a] = 1.0 / diag;
+}
+
+// ------------------------------------------------------------------------------------------
 // Cell vector, P1, BS = 1 or 3: b[row*BS + a] = sum_cells |det|/120 (sum_j f_j + f_own).
 // One warp = (slice, component a); warps are independent (each keeps its own copy of the
 // column list: 1.9 KB), no barrier, no accumulators in shared memory.
@@ -349,7 +521,22 @@ void launch_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
 
 bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
 {
-  if (c->order != 1 || c->bs != 1 || c->walk1.p == nullptr || c->max_w > 32)
+  if (c->order != 1 || c->walk1.p == nullptr)
+    return false;
+  if (c->bs == 3)
+  {
+    const std::size_t smem = (static_cast<std::size_t>(c->max_w) * 9 * 32 + 9 * 32) * sizeof(double)
+                             + static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t);
+    if (smem > 227 * 1024)
+      return false;
+    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_p1_gwalk3, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    assemble_matrix_p1_gwalk3<<<A.n_slices, 96, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return true;
+  }
+  if (c->bs != 1 || c->max_w > 32)
     return false;
   switch (env_int("PTB_GWALK_WARPS", 4))
   {

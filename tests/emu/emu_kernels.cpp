@@ -74,6 +74,7 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 extern "C" {
 
 // variant: 0 walk<1,true>  1 walk<2,false>  2 walk3<true>  3 gwalk matrix<4>  4 gwalk matrix<1>
+//          5 gwalk3 (elasticity)
 int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w, int bs,
                         const uint8_t* bc, const int64_t* rowptr, const int64_t* mat_off,
                         const int64_t* adj_off, const int32_t* cols, const double* xdof,
@@ -95,6 +96,11 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
     break;
   case 3: emu_launch(assemble_matrix_p1_gwalk<4>, (n_slices + 3) / 4, 128, A, walk1, walk1_off); break;
   case 4: emu_launch(assemble_matrix_p1_gwalk<1>, n_slices, 32, A, walk1, walk1_off); break;
+  case 5:
+    if (bs != 3)
+      return 2;
+    emu_launch(assemble_matrix_p1_gwalk3, n_slices, 96, A, walk1, walk1_off);
+    break;
   default: return 1;
   }
   return 0;

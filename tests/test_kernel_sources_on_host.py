@@ -66,7 +66,8 @@ def _row_diag(P, ref, bs2):
 MATRIX = [(0, "poisson", (5, 4, 6), 0, 1), (1, "poisson", (5, 4, 6), 0, 1), (0, "poisson", (1, 1, 1), 0, 1),
           (3, "poisson", (5, 4, 6), 0, 1), (4, "poisson", (3, 7, 2), 0, 1), (3, "poisson", (1, 1, 1), 0, 1),
           (3, "poisson", (4, 3, 5), 1, 2),
-          (2, "elasticity", (4, 3, 3), 0, 1), (2, "elasticity", (1, 1, 2), 0, 1), (2, "elasticity", (3, 3, 4), 1, 2)]
+          (2, "elasticity", (4, 3, 3), 0, 1), (2, "elasticity", (1, 1, 2), 0, 1), (2, "elasticity", (3, 3, 4), 1, 2),
+          (5, "elasticity", (4, 3, 3), 0, 1), (5, "elasticity", (1, 1, 2), 0, 1), (5, "elasticity", (3, 3, 4), 1, 2)]
 
 
 @pytest.mark.parametrize("variant,ptype,dims,rank,nranks", MATRIX)
@@ -285,7 +286,7 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
     assert ks[0] == ks[1] and abs(ks[0] - k_ref) <= 1
 
 
-@pytest.mark.parametrize("variant,ptype", [(0, "poisson"), (3, "poisson"), (2, "elasticity")])
+@pytest.mark.parametrize("variant,ptype", [(0, "poisson"), (3, "poisson"), (2, "elasticity"), (5, "elasticity")])
 def test_kernel_sources_assemble_partition_independent_bits(pt, emu, variant, ptype):
     """The walk depends on the mesh topology and the ascending cell order only, so an owned row
     gets bit-identical values on every partition -- checked here on the
