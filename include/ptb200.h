@@ -175,6 +175,15 @@ int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* 
 int ptb_debug_slice_order(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
                           int32_t* order, int32_t* n_interior);
 
+/* The SELL-32 arrays of the P2/P3 assembly kernels and the row-length bins of the binned matrix
+ * kernel (host only, used by tests/emu). info = {max_w, so_bits, so_words, n_bins}; offsets
+ * [ceil(n_owned/32) + 1]; bin_off [17], bin_w [16]; data arrays may be NULL on the first call:
+ * cols_sell [mat_off[S]], adj [adj_off[S]], adjso [adj_off[S] * so_words], bin_slices [S]. */
+int ptb_debug_pk_layout(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, int* info, int64_t* mat_off,
+                        int64_t* adj_off, int32_t* bin_off, int* bin_w, int32_t* cols_sell,
+                        uint32_t* adj, uint32_t* adjso, int32_t* bin_slices);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

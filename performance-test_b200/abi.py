@@ -72,6 +72,7 @@ def lib():
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
+        L.ptb_debug_pk_layout.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
         L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp]
@@ -183,6 +184,30 @@ def slice_order(n_rows, rowptr, cols):
     if lib().ptb_debug_slice_order(n_rows, _ptr(rp), _ptr(cl), _ptr(order), C.byref(ni)) != 0:
         raise RuntimeError(lib().ptb_last_error(None).decode())
     return order, ni.value
+
+
+def pk_layout(dofmap, nd, n_owned, rowptr, cols):
+    """Host-only: SELL-32 arrays of the P2/P3 assembly kernels + row-length bins, as a dict."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    n_cells, ns = len(dm) // nd, (n_owned + 31) // 32
+    info = np.zeros(4, dtype=np.int32)
+    d = {"mat_off": np.zeros(ns + 1, np.int64), "adj_off": np.zeros(ns + 1, np.int64),
+         "bin_off": np.zeros(17, np.int32), "bin_w": np.zeros(16, np.int32)}
+    data = {}
+    for fill in (False, True):
+        if fill:
+            data = {"cols": np.zeros(int(d["mat_off"][-1]), np.int32),
+                    "adj": np.zeros(int(d["adj_off"][-1]), np.uint32),
+                    "adjso": np.zeros(int(d["adj_off"][-1]) * int(info[2]), np.uint32),
+                    "bin_slices": np.zeros(ns, np.int32)}
+        rc = lib().ptb_debug_pk_layout(n_cells, nd, _ptr(dm), n_owned, _ptr(rp), _ptr(cl), _ptr(info),
+                                       _ptr(d["mat_off"]), _ptr(d["adj_off"]), _ptr(d["bin_off"]),
+                                       _ptr(d["bin_w"]), _ptr(data.get("cols")), _ptr(data.get("adj")),
+                                       _ptr(data.get("adjso")), _ptr(data.get("bin_slices")))
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+    return dict(d, **data, max_w=int(info[0]), so_bits=int(info[1]), so_words=int(info[2]),
+                n_bins=int(info[3]), n_slices=ns)
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

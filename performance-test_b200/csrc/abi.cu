@@ -319,6 +319,14 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
       c->walk.upload(L.walk, c->stream);
     }
+    c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
+    if (c->order > 1)
+    {
+      // width classes for the binned P2/P3 matrix kernel (assemble_pk.cu)
+      std::vector<std::int32_t> list;
+      build_width_bins(L, list, c->pk_bin_off, c->pk_bin_w);
+      c->pk_bin_slices.upload(list, c->stream);
+    }
     c->walk1.release(), c->walk1_off.release();
     if (gwalk_enabled() && !L.adjrot.empty() && (c->bs == 3 || L.max_w <= 32))
     {
@@ -891,6 +899,41 @@ int ptb_debug_slice_order(int32_t n_rows, const int64_t* rowptr, const int32_t* 
     std::vector<std::int32_t> ord;
     build_slice_order(L, n_rows, 8, false, ord, *n_interior);
     std::copy(ord.begin(), ord.end(), order);
+  });
+}
+
+int ptb_debug_pk_layout(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_owned,
+                        const int64_t* rowptr, const int32_t* cols, int* info, int64_t* mat_off,
+                        int64_t* adj_off, int32_t* bin_off, int* bin_w, int32_t* cols_sell,
+                        uint32_t* adj, uint32_t* adjso, int32_t* bin_slices)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && info && mat_off && adj_off && bin_off && bin_w,
+         "ptb_debug_pk_layout: NULL argument");
+    RowAdjacency a;
+    std::vector<std::uint16_t> so;
+    build_row_adjacency(dofmap, n_cells, nd, n_owned, a);
+    const std::int64_t max_so = build_slot_offsets(dofmap, nd, n_owned, a, rowptr, cols, so);
+    need(max_so >= 0, "ptb_debug_pk_layout: pattern does not cover the cells");
+    SellLayout L;
+    build_sell_layout(n_owned, nd, rowptr, cols, a, so, max_so, L);
+    std::vector<std::int32_t> list, off;
+    std::vector<int> width;
+    build_width_bins(L, list, off, width);
+    need(width.size() <= 16, "ptb_debug_pk_layout: more than 16 bins");
+    info[0] = L.max_w, info[1] = L.so_bits, info[2] = L.so_words, info[3] = static_cast<int>(width.size());
+    std::copy(L.mat_off.begin(), L.mat_off.end(), mat_off);
+    std::copy(L.adj_off.begin(), L.adj_off.end(), adj_off);
+    std::copy(off.begin(), off.end(), bin_off);
+    std::copy(width.begin(), width.end(), bin_w);
+    if (cols_sell)
+      std::copy(L.cols.begin(), L.cols.end(), cols_sell);
+    if (adj)
+      std::copy(L.adj.begin(), L.adj.end(), adj);
+    if (adjso)
+      std::copy(L.adjso.begin(), L.adjso.end(), adjso);
+    if (bin_slices)
+      std::copy(list.begin(), list.end(), bin_slices);
   });
 }
 

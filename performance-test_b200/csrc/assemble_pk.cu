@@ -11,6 +11,7 @@
 // Replaces the generated tabulate_tensor kernels of Poisson.py:31-32 for degree 2 and 3 and the
 // DOLFINx insertion loop (poisson_problem.cpp:129-137,150-155).
 #include "element_tables.h"
+#include "envopt.h"
 #include "kernels.h"
 
 namespace ptb
@@ -69,6 +70,91 @@ assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
   const std::int64_t ao = A.adj_off[slice];
   const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
   double* acc = smem + 6 * ND * ND + warp * (A.max_w * 32);
+  for (int k = 0; k < w; ++k)
+    acc[k * 32 + lane] = 0.0;
+  __syncwarp();
+
+  for (int k = 0; k < wa; ++k)
+  {
+    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+    if (pair == ADJ_INVALID_DEV)
+      continue;
+    std::uint32_t words[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+      words[q] = A.adjso[(ao + k * 32) * NW + q * 32 + lane];
+    const std::uint32_t cell = pair / ND;
+    const int li = pair - cell * ND;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    const Vec3 X0 = load_point(A.xyz, v.x);
+    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+               e3 = load_point(A.xyz, v.w) - X0;
+    // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
+    const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+    const double inv = 1.0 / fabs(dot(e1, c1));
+    const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
+                 G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+    const double* S = St + li * ND;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
+                         + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
+                         + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+      acc[slot_of<ND, WIDE>(words, j) * 32 + lane] += val;
+    }
+  }
+
+  const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
+  const bool bc_row = live && A.bc[row];
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const std::int32_t col = A.cols[mo + k * 32 + lane];
+    const bool real = k < len;
+    const bool own = real && col == row;
+    double val = acc[k * 32 + lane];
+    if (bc_row || (real && A.bc[col]))
+      val = own ? 1.0 : 0.0;
+    if (!real)
+      val = 0.0;
+    A.vals[mo + k * 32 + lane] = val;
+    if (own)
+      diag = val;
+  }
+  if (live)
+    A.dinv[row] = 1.0 / diag;
+}
+
+// The same kernel over a list of slices whose rows are at most bin_w long: the accumulators are
+// sized by the bin, not by the longest row of the matrix. For P3 the vertex rows (175 columns)
+// pin the kernel above to ONE CTA of four warps per SM (198 KB of shared memory) although 26 of 27
+// rows are edge and face dofs with 20-60 columns; binned, those run at 8-16 warps per SM.
+// Opt-in (PTB_PK_BINS=1): written after the round's GPU budget was spent, host-executed only.
+template <int ND, bool WIDE>
+__global__ void __launch_bounds__(PK_THREADS)
+assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
+                          const std::int32_t* __restrict__ slice_list, std::int32_t n_list, int bin_w)
+{
+  constexpr int NW = WIDE ? (ND + 1) / 2 : (ND + 3) / 4;
+  extern __shared__ double smem[];
+  double* St = smem; // [6][ND][ND]
+  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
+    St[i] = Sg[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t item = blockIdx.x * (PK_THREADS / 32) + warp;
+  if (item >= n_list)
+    return;
+  const std::int32_t slice = slice_list[item];
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const std::int64_t mo = A.mat_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const std::int64_t ao = A.adj_off[slice];
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  double* acc = smem + 6 * ND * ND + warp * (bin_w * 32);
   for (int k = 0; k < w; ++k)
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
@@ -273,6 +359,7 @@ action_pk(VectorArgs A, const double* __restrict__ Sg, const double* __restrict_
   }
 }
 
+#ifndef PTB_HOST_EMU // host launchers: device build only
 void ensure_tables(ptb_ctx* c)
 {
   if (c->tab_order == c->order)
@@ -285,9 +372,42 @@ void ensure_tables(ptb_ctx* c)
   c->tab_order = c->order;
 }
 
+template <int ND, bool WIDE>
+void launch_matrix_bins(ptb_ctx* c, const MatrixArgs& A)
+{
+  for (std::size_t b = 0; b + 1 < c->pk_bin_off.size(); ++b)
+  {
+    const std::int32_t n = c->pk_bin_off[b + 1] - c->pk_bin_off[b];
+    if (n == 0)
+      continue;
+    const int bin_w = c->pk_bin_w[b];
+    const std::size_t smem
+        = (static_cast<std::size_t>(6) * ND * ND + static_cast<std::size_t>(bin_w) * 32 * (PK_THREADS / 32))
+          * sizeof(double);
+    if (smem > 227 * 1024)
+      throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
+    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk_binned<ND, WIDE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int grid = (n + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
+    assemble_matrix_pk_binned<ND, WIDE><<<grid, PK_THREADS, smem, c->stream>>>(
+        A, c->tab_S.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+  }
+}
+
 template <int ND>
 void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
 {
+  if (env_flag("PTB_PK_BINS", false) && c->pk_bin_slices.p != nullptr)
+  {
+    if (c->so_bits == 8)
+      launch_matrix_bins<ND, false>(c, A);
+    else
+      launch_matrix_bins<ND, true>(c, A);
+    c->launches -= 1; // the caller counts one launch
+    return;
+  }
   const std::size_t smem
       = (static_cast<std::size_t>(6) * ND * ND + static_cast<std::size_t>(c->max_w) * 32 * (PK_THREADS / 32))
         * sizeof(double);
@@ -370,5 +490,9 @@ void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs&
     c->launches += 1;
   }
 }
+
+#else
+} // namespace
+#endif // PTB_HOST_EMU
 
 } // namespace ptb

@@ -145,6 +145,10 @@ struct ptb_ctx
 
   // reference tensors of the P2/P3 element (element_tables.h), uploaded on first use
   ptb::DevBuf<double> tab_S, tab_M, tab_MF;
+  // P2/P3 matrix assembly by row-length bins (PTB_PK_BINS=1): slices grouped by width class
+  ptb::DevBuf<std::int32_t> pk_bin_slices;
+  std::vector<std::int32_t> pk_bin_off; // [n_bins + 1] into pk_bin_slices
+  std::vector<int> pk_bin_w;            // accumulator width of each bin
   int tab_order = 0;
 
   // matrix-free operator mode (ptb_set_operator_mode) and its per-CTA dot partials

@@ -327,6 +327,34 @@ void compress_columns(std::int32_t n_rows, std::int64_t n_cols, const std::int64
   }
 }
 
+void build_width_bins(const SellLayout& L, std::vector<std::int32_t>& list,
+                      std::vector<std::int32_t>& off, std::vector<int>& width)
+{
+  std::vector<int> bounds;
+  for (int b : {32, 64, 96, 128, 192})
+    if (b < L.max_w)
+      bounds.push_back(b);
+  for (int b = 256; b < L.max_w; b += 128)
+    bounds.push_back(b);
+  bounds.push_back(std::max(1, L.max_w));
+  width = bounds;
+  const std::int32_t S = L.n_slices;
+  std::vector<std::vector<std::int32_t>> bins(bounds.size());
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    const int w = static_cast<int>((L.mat_off[s + 1] - L.mat_off[s]) / 32);
+    const std::size_t b = std::lower_bound(bounds.begin(), bounds.end(), w) - bounds.begin();
+    bins[std::min(b, bounds.size() - 1)].push_back(s);
+  }
+  list.clear();
+  off.assign(1, 0);
+  for (const auto& v : bins)
+  {
+    list.insert(list.end(), v.begin(), v.end());
+    off.push_back(static_cast<std::int32_t>(list.size()));
+  }
+}
+
 void build_slice_order(const SellLayout& L, std::int32_t n_rows, int group, bool cluster,
                        std::vector<std::int32_t>& order, std::int32_t& n_interior)
 {

@@ -71,6 +71,12 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
 /// Derive walk1 / walk1_off from L.walk (see SellLayout::walk1).
 void build_walk_single(std::int32_t n_rows, const RowAdjacency& adj, SellLayout& L);
 
+/// Slices grouped by row-length class (SELL width <= 32, 64, 96, 128, 192, 256, ... max_w): list =
+/// slice indices bin after bin (ascending inside a bin), off = [n_bins + 1] offsets into list,
+/// width = accumulator width of each bin (the class bound, capped by max_w).
+void build_width_bins(const SellLayout& L, std::vector<std::int32_t>& list,
+                      std::vector<std::int32_t>& off, std::vector<int>& width);
+
 /// Visiting order of the slices for the operator kernels. Slices without ghost columns come first
 /// (n_interior of them), so the fused halo pull overlaps with them. Inside each class the order is
 /// built from groups of `group` slices that reference each other's rows (breadth-first over the

@@ -86,6 +86,27 @@ def ab2(ndofs):
             dump()
 
 
+def abpk(ndofs):
+    """P2 / P3 matrix assembly: one launch over all slices against the row-length bins."""
+    for order in (2, 3):
+        nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, order, 1)
+        f = 2 ** r
+        P = pt.host.Problem("poisson", order, nx * f, ny * f, nz * f)
+        c = pt.abi.Context(0)
+        c.set_problem(P)
+        ref = None
+        for bins in ("0", "1"):
+            os.environ["PTB_PK_BINS"] = bins
+            c.assemble_matrix()
+            a = c.matrix_values()
+            ref = a if ref is None else ref
+            res[f"p{order}_bins{bins}"] = {"matrix_ms": c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 3),
+                                           "maxdiff": float(np.abs(a - ref).max() / np.abs(ref).max()),
+                                           "n_owned": P.n_owned, "nnz": P.nnz}
+            dump()
+        c.close()
+
+
 def ncu_target(ndofs):
     nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
     f = 2 ** r
@@ -98,6 +119,8 @@ def main():
         return ab(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ab2":
         return ab2(int(sys.argv[2]))
+    if len(sys.argv) > 2 and sys.argv[1] == "abpk":
+        return abpk(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ncu":
         return ncu_target(int(sys.argv[2]))
     t0 = time.time()

@@ -8,9 +8,11 @@ out=gpurun_out/first_call
 mkdir -p "$out"
 export PTB_TEST_OPTIN=1
 echo "== opt-in parity tests"
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "opt_in or persistent or star_walk" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "opt_in or persistent or star_walk or binned" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
 echo "== assembly A/B (4M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
+echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
+WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
 echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"
 for persistent in 0 1; do
   for wl in "--workload small" "--workload poisson --ndofs 3000000" "--workload elasticity --ndofs 1250000"; do

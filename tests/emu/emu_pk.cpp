@@ -1,0 +1,106 @@
+// TEST INFRASTRUCTURE -- runs the source of the P2/P3 matrix assembly kernels (csrc/assemble_pk.cu)
+// on the host, like emu_kernels.cpp does for the P1 walk kernels. Nothing here is linked into the
+// product libraries; the product path never sees PTB_HOST_EMU.
+#define PTB_HOST_EMU 1
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+struct EmuIdx
+{
+  unsigned x = 0, y = 0, z = 0;
+};
+static thread_local EmuIdx threadIdx, blockIdx;
+static EmuIdx blockDim, gridDim;
+static std::barrier<>* emu_barrier = nullptr;
+static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) {} // the accumulators are private per lane
+template <typename T>
+static inline T __ldg(const T* p) { return *p; }
+// declared for the other kernels of the file (matrix-free action), which this harness does not run
+static inline double __shfl_xor_sync(unsigned, double v, int) { return v; }
+
+namespace ptb
+{
+namespace
+{
+alignas(16) double smem[232448 / 8];
+}
+} // namespace ptb
+
+#include "../../performance-test_b200/csrc/assemble_pk.cu"
+
+namespace
+{
+template <typename K, typename... Args>
+void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
+{
+  gridDim.x = grid, blockDim.x = block;
+  for (unsigned b = 0; b < grid; ++b)
+  {
+    std::barrier<> bar(block);
+    emu_barrier = &bar;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < block; ++t)
+      th.emplace_back([=] {
+        threadIdx.x = t, blockIdx.x = b;
+        kernel(args...);
+        emu_barrier->arrive_and_drop();
+      });
+    for (auto& x : th)
+      x.join();
+  }
+}
+} // namespace
+
+extern "C" {
+
+// binned = 0: assemble_matrix_pk over all slices; 1: assemble_matrix_pk_binned, bin after bin
+int emu_assemble_matrix_pk(int binned, int nd, int so_bits, int32_t n_rows, int32_t n_slices,
+                           int max_w, const double* xyz4, const int32_t* x_dofmap,
+                           const uint8_t* bc, const int64_t* rowptr, const int64_t* mat_off,
+                           const int64_t* adj_off, const int32_t* cols, const uint32_t* adj,
+                           const uint32_t* adjso, int n_bins, const int32_t* bin_off,
+                           const int* bin_w, const int32_t* bin_slices, double* vals, double* dinv)
+{
+  using namespace ptb;
+  MatrixArgs A{};
+  A.n_rows = n_rows, A.n_slices = n_slices, A.xyz = xyz4, A.x_dofmap = x_dofmap, A.bc = bc;
+  A.rowptr = rowptr, A.mat_off = mat_off, A.adj_off = adj_off, A.cols = cols, A.adj = adj;
+  A.adjso = adjso, A.max_w = max_w, A.vals = vals, A.dinv = dinv;
+  const double* S = nd == 10 ? tables::S_P2 : tables::S_P3;
+  auto run = [&](auto ND, auto WIDE) {
+    constexpr int N = decltype(ND)::value;
+    constexpr bool W = decltype(WIDE)::value;
+    if (!binned)
+      emu_launch(assemble_matrix_pk<N, W>, (n_slices + 3) / 4, PK_THREADS, A, S);
+    else
+      for (int b = 0; b < n_bins; ++b)
+      {
+        const std::int32_t n = bin_off[b + 1] - bin_off[b];
+        if (n > 0)
+          emu_launch(assemble_matrix_pk_binned<N, W>, (n + 3) / 4, PK_THREADS, A, S,
+                     bin_slices + bin_off[b], n, bin_w[b]);
+      }
+  };
+  if (nd == 10 && so_bits == 8)
+    run(std::integral_constant<int, 10>{}, std::false_type{});
+  else if (nd == 10)
+    run(std::integral_constant<int, 10>{}, std::true_type{});
+  else if (nd == 20 && so_bits == 8)
+    run(std::integral_constant<int, 20>{}, std::false_type{});
+  else if (nd == 20)
+    run(std::integral_constant<int, 20>{}, std::true_type{});
+  else
+    return 1;
+  return 0;
+}
+}

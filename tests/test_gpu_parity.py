@@ -385,3 +385,19 @@ print("persistent ok")
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300,
                        env=env)
     assert r.returncode == 0 and "persistent ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
+
+
+@OPTIN
+@pytest.mark.parametrize("order,dims", [(2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)), (3, (6, 5, 7))])
+def test_binned_p2_p3_matrix_kernel_matches_oracle(pt, oracle, monkeypatch, order, dims):
+    P = pt.host.Problem("poisson", order, *dims)
+    monkeypatch.setenv("PTB_PK_BINS", "1")
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P)
+        n0 = c.launch_count()
+        c.assemble_matrix()
+        assert c.launch_count() - n0 >= 1
+        _check_matrix(P, c.matrix_values(), oracle.assemble_matrix(P))
+    finally:
+        c.close()

@@ -318,3 +318,50 @@ def test_kernel_sources_assemble_partition_independent_bits(pt, emu, variant, pt
         parts.update(assemble(q, 3))
     assert parts.keys() == whole.keys()
     assert all(parts[k] == whole[k] for k in whole)
+
+
+# ---- P2 / P3 matrix kernels (csrc/assemble_pk.cu): all slices at once, and bin after bin -------------
+
+PK_SRC = os.path.join(HERE, "emu", "emu_pk.cpp")
+
+
+@pytest.fixture(scope="module")
+def emupk():
+    out = os.path.join(HERE, "emu", "_build", "libemupk.so")
+    deps = [PK_SRC] + [os.path.join(CSRC, f) for f in ("assemble_pk.cu", "element_tables.h", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-o", out, PK_SRC], check=True)
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("binned", [0, 1])
+@pytest.mark.parametrize("order,dims,rank,nranks", [(2, (3, 2, 4), 0, 1), (3, (2, 3, 2), 0, 1),
+                                                    (3, (2, 2, 4), 1, 2)])
+def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, order, dims, rank, nranks, binned):
+    P = pt.host.Problem("poisson", order, *dims, rank, nranks)
+    L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+    nv = len(P["x"]) // 3
+    xyz4 = np.zeros((nv, 4))
+    xyz4[:, :3] = P["x"].reshape(-1, 3)
+    xyz4 = np.ascontiguousarray(xyz4.reshape(-1))
+    bc = np.zeros(P.n_owned + P.n_ghost, np.uint8)
+    bc[P["bc_dofs"]] = 1
+    vals = np.full(int(L["mat_off"][-1]), np.nan)
+    dinv = np.full(P.n_owned, np.nan)
+    rp, xd = np.ascontiguousarray(P["rowptr"]), np.ascontiguousarray(P["x_dofmap"])
+    if binned:  # the bins partition the slices, every bin is wide enough for its rows
+        assert sorted(L["bin_slices"].tolist()) == list(range(L["n_slices"]))
+        for b in range(L["n_bins"]):
+            for s in L["bin_slices"][L["bin_off"][b]:L["bin_off"][b + 1]]:
+                assert (L["mat_off"][s + 1] - L["mat_off"][s]) // 32 <= L["bin_w"][b]
+    rc = emupk.emu_assemble_matrix_pk(binned, P.nd, L["so_bits"], P.n_owned, L["n_slices"], L["max_w"],
+                                      _p(xyz4), _p(xd), _p(bc), _p(rp), _p(L["mat_off"]), _p(L["adj_off"]),
+                                      _p(L["cols"]), _p(L["adj"]), _p(L["adjso"]), L["n_bins"],
+                                      _p(L["bin_off"]), _p(L["bin_w"]), _p(L["bin_slices"]), _p(vals), _p(dinv))
+    assert rc == 0 and not np.isnan(vals).any() and not np.isnan(dinv).any()
+    got = _sell_to_csr(P, L, vals, 1)
+    ref = oracle.assemble_matrix(P)
+    assert (np.abs(got - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
