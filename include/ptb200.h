@@ -156,12 +156,12 @@ int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n
 
 /* The SELL-32 arrays the P1 walk kernels read (host only): offsets [ceil(n_owned/32) + 1] first
  * (pass NULL for the data arrays), then the data: padded columns, walk words, single-reload walk
- * words, each in device order (offset[s] + k*32 + lane). Used by tests/emu, which runs the
+ * words, rotated cell words (adjrot, indexed like walk), each in device order (offset[s] + k*32 + lane). Used by tests/emu, which runs the
  * kernel sources on the host. */
 int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
                         const int64_t* rowptr, const int32_t* cols, int* max_w, int64_t* mat_off,
                         int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
-                        uint32_t* walk1);
+                        uint32_t* walk1, uint32_t* adjrot);
 
 /* The compressed column indices of the scalar SpMV (layout.h: cdelta / xoff / colsx), host only:
  * cdelta [mat_off[S]/32], xoff [S + 1]; colsx [xoff[S]] may be NULL on the first call. */

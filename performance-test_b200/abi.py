@@ -75,7 +75,7 @@ def lib():
         L.ptb_debug_pk_layout.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
-        L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp]
+        L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
         L.ptb_stage_ms.restype = dbl
@@ -149,11 +149,13 @@ def p1_layout(dofmap, n_owned, rowptr, cols):
         if fill:
             data = {"cols": np.zeros(int(off["mat_off"][-1]), dtype=np.int32),
                     "walk": np.zeros(int(off["adj_off"][-1]), dtype=np.uint32),
-                    "walk1": np.zeros(int(off["walk1_off"][-1]), dtype=np.uint32)}
+                    "walk1": np.zeros(int(off["walk1_off"][-1]), dtype=np.uint32),
+                    "adjrot": np.zeros(int(off["adj_off"][-1]), dtype=np.uint32)}
         rc = lib().ptb_debug_p1_layout(n_cells, _ptr(dm), n_owned, _ptr(rp), _ptr(cl), C.byref(mw),
                                        _ptr(off["mat_off"]), _ptr(off["adj_off"]),
                                        _ptr(off["walk1_off"]), _ptr(data.get("cols")),
-                                       _ptr(data.get("walk")), _ptr(data.get("walk1")))
+                                       _ptr(data.get("walk")), _ptr(data.get("walk1")),
+                                       _ptr(data.get("adjrot")))
         if rc != 0:
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return dict(off, **data, max_w=mw.value, n_slices=ns)

@@ -840,7 +840,7 @@ int ptb_debug_star_walk_single(int64_t n_cells, const int32_t* dofmap, int32_t n
 int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
                         const int64_t* rowptr, const int32_t* cols, int* max_w, int64_t* mat_off,
                         int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
-                        uint32_t* walk1)
+                        uint32_t* walk1, uint32_t* adjrot)
 {
   return guarded(nullptr, [&] {
     need(dofmap && rowptr && cols && mat_off && adj_off && walk1_off, "ptb_debug_p1_layout: NULL argument");
@@ -864,6 +864,8 @@ int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
       std::copy(L.walk.begin(), L.walk.end(), walk);
     if (walk1)
       std::copy(L.walk1.begin(), L.walk1.end(), walk1);
+    if (adjrot)
+      std::copy(L.adjrot.begin(), L.adjrot.end(), adjrot);
   });
 }
 

@@ -538,6 +538,7 @@ __global__ void pad_xyz(std::int64_t n, const double* __restrict__ x3, double* _
   q[1] = make_double2(x3[3 * i + 2], 0.0);
 }
 
+#ifndef PTB_HOST_EMU // host launchers: device build only
 template <typename K>
 void set_smem(K kernel, std::size_t smem)
 {
@@ -668,5 +669,9 @@ void launch_gather_xdof(ptb_ctx* c)
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
+
+#else
+} // namespace
+#endif // PTB_HOST_EMU
 
 } // namespace ptb

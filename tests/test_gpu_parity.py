@@ -401,3 +401,28 @@ def test_binned_p2_p3_matrix_kernel_matches_oracle(pt, oracle, monkeypatch, orde
         _check_matrix(P, c.matrix_values(), oracle.assemble_matrix(P))
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (7, 6, 8)), ("elasticity", 1, (5, 6, 4)),
+                                              ("poisson", 2, (4, 3, 5)), ("poisson", 3, (3, 4, 2))])
+def test_assembly_and_solve_on_a_jittered_mesh(pt, oracle, perturbed, ctx, ptype, order, dims):
+    """Every other case runs on the regular lattice, where many products of the element kernels
+    vanish or coincide. Here the vertices are moved by up to 0.15 cell widths (ptb_update_geometry)
+    and the oracle reads the same coordinates: all terms, and the orientation handling of the star
+    walk, are exercised."""
+    P = pt.host.Problem(ptype, order, *dims)
+    Q = perturbed(P)
+    ctx.set_problem(P)
+    ctx.update_geometry(Q["x"])
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref, b_ref = oracle.assemble_matrix(Q), oracle.assemble_vector(Q)
+    assert np.abs(A_ref - oracle.assemble_matrix(P)).max() > 1e-3 * np.abs(A_ref).max()  # it did move
+    _check_matrix(P, ctx.matrix_values(), A_ref)
+    assert np.abs(ctx.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+    x_ref, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000,
+                                rtol=1e-8, precond="jacobi")
+    assert abs(k - k_ref) <= 1 and rel < 1e-8
+    x = ctx.solution()[: P.n_owned * P.bs]
+    assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)

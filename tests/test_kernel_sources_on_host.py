@@ -70,9 +70,13 @@ MATRIX = [(0, "poisson", (5, 4, 6), 0, 1), (1, "poisson", (5, 4, 6), 0, 1), (0, 
           (5, "elasticity", (4, 3, 3), 0, 1), (5, "elasticity", (1, 1, 2), 0, 1), (5, "elasticity", (3, 3, 4), 1, 2)]
 
 
+@pytest.mark.parametrize("jitter", [False, True])
 @pytest.mark.parametrize("variant,ptype,dims,rank,nranks", MATRIX)
-def test_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emu, variant, ptype, dims, rank, nranks):
+def test_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emu, perturbed, variant, ptype, dims, rank,
+                                                    nranks, jitter):
     P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
     L, xdof, bc = _inputs(pt, P)
     bs2 = P.bs * P.bs
     vals = np.full(int(L["mat_off"][-1]) * bs2, np.nan)
@@ -105,9 +109,13 @@ VECTOR = [("poisson", (5, 4, 6), 0, 1, 4), ("poisson", (1, 1, 1), 0, 1, 1), ("po
           ("elasticity", (3, 4, 3), 0, 1, 4), ("elasticity", (2, 2, 5), 1, 2, 8)]
 
 
+@pytest.mark.parametrize("jitter", [False, True])
 @pytest.mark.parametrize("ptype,dims,rank,nranks,warps", VECTOR)
-def test_vector_kernel_source_reproduces_the_oracle(pt, oracle, emu, ptype, dims, rank, nranks, warps):
+def test_vector_kernel_source_reproduces_the_oracle(pt, oracle, emu, perturbed, ptype, dims, rank, nranks,
+                                                    warps, jitter):
     P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
     L, xdof, bc = _inputs(pt, P)
     b = np.full(P.n_owned * P.bs, np.nan)
     f = np.ascontiguousarray(P["f"])
@@ -340,8 +348,11 @@ def emupk():
 @pytest.mark.parametrize("binned", [0, 1])
 @pytest.mark.parametrize("order,dims,rank,nranks", [(2, (3, 2, 4), 0, 1), (3, (2, 3, 2), 0, 1),
                                                     (3, (2, 2, 4), 1, 2)])
-def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, order, dims, rank, nranks, binned):
+def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, perturbed, order, dims, rank,
+                                                          nranks, binned):
     P = pt.host.Problem("poisson", order, *dims, rank, nranks)
+    if binned:  # the binned runs also take the jittered mesh
+        P = perturbed(P)
     L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
     nv = len(P["x"]) // 3
     xyz4 = np.zeros((nv, 4))
@@ -365,3 +376,47 @@ def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, ord
     got = _sell_to_csr(P, L, vals, 1)
     ref = oracle.assemble_matrix(P)
     assert (np.abs(got - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
+
+
+# ---- the ascending-cell-order P1 kernels (csrc/assemble.cu): default for elasticity and for b --------
+
+P1_SRC = os.path.join(HERE, "emu", "emu_p1.cpp")
+
+
+@pytest.fixture(scope="module")
+def emup1():
+    out = os.path.join(HERE, "emu", "_build", "libemup1.so")
+    deps = [P1_SRC] + [os.path.join(CSRC, f) for f in ("assemble.cu", "geom.cuh", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-o", out, P1_SRC], check=True)
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("elasticity", (4, 3, 3), 0, 1),
+                                                    ("elasticity", (1, 1, 2), 0, 1), ("elasticity", (3, 3, 4), 1, 2)])
+def test_cell_order_kernel_sources_reproduce_the_oracle(pt, oracle, emup1, perturbed, ptype, dims, rank, nranks,
+                                                        jitter):
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
+    L, xdof, bc = _inputs(pt, P)
+    bs2 = P.bs * P.bs
+    vals = np.full(int(L["mat_off"][-1]) * bs2, np.nan)
+    dinv = np.full(P.n_owned * P.bs, np.nan)
+    b = np.full(P.n_owned * P.bs, np.nan)
+    rp, f = np.ascontiguousarray(P["rowptr"]), np.ascontiguousarray(P["f"])
+    assert emup1.emu_p1_matrix(P.bs, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(rp), _p(L["mat_off"]),
+                               _p(L["adj_off"]), _p(L["cols"]), _p(L["adjrot"]), _p(xdof), _p(vals),
+                               _p(dinv)) == 0
+    assert emup1.emu_p1_vector(P.bs, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(L["mat_off"]),
+                               _p(L["adj_off"]), _p(L["cols"]), _p(L["adjrot"]), _p(xdof), _p(f), _p(b)) == 0
+    assert not np.isnan(vals).any() and not np.isnan(b).any()
+    ref = oracle.assemble_matrix(P)
+    assert (np.abs(_sell_to_csr(P, L, vals, bs2) - ref) / _row_diag(P, ref, bs2)).max() <= 1e-12
+    b_ref = oracle.assemble_vector(P)
+    if ptype == "elasticity":  # Poisson's b also carries the facet term of another kernel
+        assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()

@@ -146,8 +146,9 @@ def _emulate_poisson(P, words):
 
 
 @pytest.mark.parametrize("dims,rank,nranks", [((5, 4, 6), 0, 1), ((1, 1, 1), 0, 1), ((4, 3, 5), 1, 2)])
-def test_walk_arithmetic_reproduces_the_oracle_matrix(pt, oracle, dims, rank, nranks):
-    P = pt.host.Problem("poisson", 1, *dims, rank, nranks)
+def test_walk_arithmetic_reproduces_the_oracle_matrix(pt, oracle, perturbed, dims, rank, nranks):
+    P = perturbed(pt.host.Problem("poisson", 1, *dims, rank, nranks)) if rank else \
+        pt.host.Problem("poisson", 1, *dims, rank, nranks)
     words, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
     got = _emulate_poisson(P, words)
     ref = oracle.assemble_matrix(P)
@@ -212,8 +213,11 @@ def _emulate_elasticity(P, words):
 
 
 @pytest.mark.parametrize("dims,rank,nranks", [((4, 3, 5), 0, 1), ((1, 1, 2), 0, 1), ((3, 3, 4), 1, 2)])
-def test_walk_tensor_accumulation_reproduces_the_oracle_elasticity_matrix(pt, oracle, dims, rank, nranks):
+def test_walk_tensor_accumulation_reproduces_the_oracle_elasticity_matrix(pt, oracle, perturbed, dims, rank,
+                                                                         nranks):
     P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+    if rank:  # the partitioned case runs on the jittered mesh
+        P = perturbed(P)
     words, _ = pt.abi.star_walk(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
     got = _emulate_elasticity(P, words).reshape(-1, 9)
     ref = oracle.assemble_matrix(P).reshape(-1, 9)
@@ -319,8 +323,10 @@ def _emulate_gwalk(P, ptr1, words1):
 @pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1),
                                                     ("poisson", (4, 3, 5), 1, 2), ("elasticity", (3, 4, 3), 0, 1),
                                                     ("elasticity", (2, 2, 5), 1, 2)])
-def test_direct_gather_walk_reproduces_the_oracle(pt, oracle, ptype, dims, rank, nranks):
+def test_direct_gather_walk_reproduces_the_oracle(pt, oracle, perturbed, ptype, dims, rank, nranks):
     P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    if rank:  # the partitioned cases run on the jittered mesh
+        P = perturbed(P)
     ptr1, words1 = pt.abi.star_walk_single(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
     vals, b = _emulate_gwalk(P, ptr1, words1)
     b_ref = oracle.assemble_vector(P)
