@@ -33,7 +33,11 @@ namespace
 // 4 warps 0.699/0.687, 7 warps 0.702/0.684 -> one-warp CTAs with the L2 prefetch are the default.
 constexpr int WALK_CHUNK = 8; // step words in flight per thread
 // L2 prefetch distance in slices: about two generations of resident warps (148 SMs x 14 warps).
+#ifdef PTB_HOST_EMU
+constexpr int WALK_PF_DIST = 3; // tests/emu: tiny meshes must reach the prefetch address arithmetic
+#else
 constexpr int WALK_PF_DIST = 4096;
+#endif
 
 // Register positions of the walk (three non-owner vertices of the current cell).
 struct WalkState
