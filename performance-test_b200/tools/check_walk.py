@@ -114,7 +114,21 @@ def ncu_target(ndofs):
     assemble(P, True).close()
 
 
+def ncu_target2(ndofs):
+    """Matrix + vector assembly once with whatever switches the environment carries."""
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    c = pt.abi.Context(0)
+    c.set_problem(P)
+    c.assemble_matrix()
+    c.assemble_vector()
+    c.close()
+
+
 def main():
+    if len(sys.argv) > 2 and sys.argv[1] == "ncu2":
+        return ncu_target2(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ab":
         return ab(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ab2":

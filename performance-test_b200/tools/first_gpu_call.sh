@@ -11,6 +11,9 @@ echo "== opt-in parity tests"
 timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "opt_in or persistent or star_walk or binned" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
 echo "== assembly A/B (4M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
+echo "== ncu --set full of the direct-gather kernels (Poisson 4M): read it with tools/ncu_summary.py"
+PTB_ASM_GWALK=1 timeout 200 ncu --set full --import-source on --clock-control none -k regex:gwalk -c 2 -f \
+  -o "$out/prof_gwalk" python performance-test_b200/tools/check_walk.py ncu2 4000000 2>&1 | tail -3
 echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
 echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"
