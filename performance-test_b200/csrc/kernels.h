@@ -1,5 +1,11 @@
 // Kernel argument blocks and launchers shared by the .cu files.
 #pragma once
+// PTB_HOST_EMU exists for tests/emu only (the g++ harness that executes kernel *sources* on the
+// host to check their indexing). It must never reach a device build: there is no CPU path in the
+// product, and a library built with it would be one.
+#if defined(PTB_HOST_EMU) && defined(__CUDACC__)
+#error "PTB_HOST_EMU is a test-harness switch (tests/emu); it is not valid in an nvcc build"
+#endif
 #include "ctx.h"
 #include "peer.h"
 
