@@ -184,6 +184,14 @@ int ptb_debug_pk_layout(int64_t n_cells, int nd, const int32_t* dofmap, int32_t 
                         int64_t* adj_off, int32_t* bin_off, int* bin_w, int32_t* cols_sell,
                         uint32_t* adj, uint32_t* adjso, int32_t* bin_slices);
 
+/* The boundary-facet gather lists of assemble_vector (layout.h build_facet_rows), host only.
+ * Capacities: row_ids [n_rows], row_ptr [n_rows + 1], ent [2 * 10 * n_facets]; *n_frows and
+ * *n_ent receive the used lengths (ent holds *n_ent (cell, local_facet*nd + li) pairs). */
+int ptb_debug_facet_rows(int64_t n_facets, const int32_t* cells, const int32_t* local_facets,
+                         const int32_t* dofmap, int nd, int order, int32_t n_rows,
+                         int32_t* n_frows, int32_t* n_ent, int32_t* row_ids, int32_t* row_ptr,
+                         int32_t* ent);
+
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */
 double ptb_stage_ms(const ptb_ctx* ctx, int stage);

@@ -72,6 +72,8 @@ def lib():
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
+        L.ptb_debug_facet_rows.argtypes = [i64, vp, vp, vp, C.c_int, C.c_int, i32, C.POINTER(i32),
+                                           C.POINTER(i32), vp, vp, vp]
         L.ptb_debug_pk_layout.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
@@ -210,6 +212,19 @@ def pk_layout(dofmap, nd, n_owned, rowptr, cols):
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return dict(d, **data, max_w=int(info[0]), so_bits=int(info[1]), so_words=int(info[2]),
                 n_bins=int(info[3]), n_slices=ns)
+
+
+def facet_rows(facet_cells, facet_local, dofmap, nd, order, n_rows):
+    """Host-only: (row_ids, row_ptr, ent) of the boundary-facet gather (ent = int32 pairs)."""
+    fc, fl, dm = _a(facet_cells, np.int32), _a(facet_local, np.int32), _a(dofmap, np.int32)
+    ids, ptr = np.zeros(max(n_rows, 1), np.int32), np.zeros(n_rows + 1, np.int32)
+    ent = np.zeros(max(20 * len(fc), 2), np.int32)
+    nf, ne = C.c_int32(), C.c_int32()
+    rc = lib().ptb_debug_facet_rows(len(fc), _ptr(fc), _ptr(fl), _ptr(dm), nd, order, n_rows,
+                                    C.byref(nf), C.byref(ne), _ptr(ids), _ptr(ptr), _ptr(ent))
+    if rc != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return ids[:nf.value].copy(), ptr[:nf.value + 1].copy(), ent[:2 * ne.value].copy()
 
 
 def layout_roundtrip(n_rows, n_cols, rowptr, cols):

@@ -939,6 +939,25 @@ int ptb_debug_pk_layout(int64_t n_cells, int nd, const int32_t* dofmap, int32_t 
   });
 }
 
+int ptb_debug_facet_rows(int64_t n_facets, const int32_t* cells, const int32_t* local_facets,
+                         const int32_t* dofmap, int nd, int order, int32_t n_rows,
+                         int32_t* n_frows, int32_t* n_ent, int32_t* row_ids, int32_t* row_ptr,
+                         int32_t* ent)
+{
+  return guarded(nullptr, [&] {
+    need(cells && local_facets && dofmap && n_frows && n_ent && row_ids && row_ptr && ent,
+         "ptb_debug_facet_rows: NULL argument");
+    std::vector<std::int32_t> ids, ptr, e;
+    build_facet_rows(n_facets, cells, local_facets, dofmap, nd, order, n_rows, ids, ptr, e);
+    need(e.size() <= static_cast<std::size_t>(20) * n_facets, "ptb_debug_facet_rows: capacity");
+    *n_frows = static_cast<std::int32_t>(ids.size());
+    *n_ent = static_cast<std::int32_t>(e.size() / 2);
+    std::copy(ids.begin(), ids.end(), row_ids);
+    std::copy(ptr.begin(), ptr.end(), row_ptr);
+    std::copy(e.begin(), e.end(), ent);
+  });
+}
+
 int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets)
 {

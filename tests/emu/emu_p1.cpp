@@ -96,4 +96,16 @@ int emu_p1_vector(int bs, int32_t n_rows, int32_t n_slices, int max_w, const uin
     emu_launch(assemble_vector_p1<3>, (n_slices + 1) / 2, MAT_THREADS_3, A);
   return 0;
 }
+
+// exterior facets of the scalar P1 space (assemble_facets_p1): adds g v ds into b
+int emu_p1_facets(int32_t n_frows, const double* xyz4, const int32_t* x_dofmap,
+                  const int32_t* dofmap, const uint8_t* bc, const int32_t* frow_ids,
+                  const int32_t* frow_ptr, const int32_t* fent, const double* g, double* b)
+{
+  using namespace ptb;
+  FacetArgs F{n_frows, xyz4, x_dofmap, dofmap, bc, frow_ids, frow_ptr, fent, g, b};
+  if (n_frows > 0)
+    emu_launch(assemble_facets_p1, (n_frows + 127) / 128, 128, F);
+  return 0;
+}
 }

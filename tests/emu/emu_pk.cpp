@@ -36,7 +36,10 @@ alignas(16) double smem[232448 / 8];
 }
 } // namespace ptb
 
-#include "../../performance-test_b200/csrc/assemble_pk.cu"
+// The test fixture writes a copy of csrc/assemble_pk.cu in which `extern __shared__` (dynamic shared
+// memory -> the array above) reads `extern` and every other `__shared__` (static shared memory ->
+// one instance per CTA; CTAs run one at a time here) reads `static`, and passes its path.
+#include PTB_EMU_PK_SOURCE
 
 namespace
 {
@@ -99,6 +102,35 @@ int emu_assemble_matrix_pk(int binned, int nd, int so_bits, int32_t n_rows, int3
     run(std::integral_constant<int, 20>{}, std::false_type{});
   else if (nd == 20)
     run(std::integral_constant<int, 20>{}, std::true_type{});
+  else
+    return 1;
+  return 0;
+}
+
+// cell vector + exterior facets of the P2/P3 space (assemble_vector_pk, assemble_facets_pk)
+int emu_assemble_vector_pk(int nd, int32_t n_rows, int32_t n_slices, const double* xyz4,
+                           const int32_t* x_dofmap, const int32_t* dofmap, const uint8_t* bc,
+                           const int64_t* adj_off, const uint32_t* adj, const double* f,
+                           int32_t n_frows, const int32_t* frow_ids, const int32_t* frow_ptr,
+                           const int32_t* fent, const double* g, double* b)
+{
+  using namespace ptb;
+  VectorArgs A{};
+  A.n_rows = n_rows, A.n_slices = n_slices, A.xyz = xyz4, A.x_dofmap = x_dofmap, A.dofmap = dofmap;
+  A.bc = bc, A.adj_off = adj_off, A.adj = adj, A.f = f, A.b = b;
+  FacetArgs F{n_frows, xyz4, x_dofmap, dofmap, bc, frow_ids, frow_ptr, fent, g, b};
+  if (nd == 10)
+  {
+    emu_launch(assemble_vector_pk<10>, (n_slices + 3) / 4, PK_THREADS, A, tables::M_P2);
+    if (n_frows > 0)
+      emu_launch(assemble_facets_pk<10>, (n_frows + 127) / 128, 128, F, tables::MF_P2);
+  }
+  else if (nd == 20)
+  {
+    emu_launch(assemble_vector_pk<20>, (n_slices + 3) / 4, PK_THREADS, A, tables::M_P3);
+    if (n_frows > 0)
+      emu_launch(assemble_facets_pk<20>, (n_frows + 127) / 128, 128, F, tables::MF_P3);
+  }
   else
     return 1;
   return 0;

@@ -339,9 +339,16 @@ def emupk():
     deps = [PK_SRC] + [os.path.join(CSRC, f) for f in ("assemble_pk.cu", "element_tables.h", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
+        # static shared arrays must be one per CTA, not one per host thread (see emu_pk.cpp)
+        text = open(os.path.join(CSRC, "assemble_pk.cu")).read()
+        text = text.replace("extern __shared__", "extern").replace("__shared__", "static")
+        copy = os.path.join(os.path.dirname(out), "assemble_pk_emu.cu")
+        with open(copy, "w") as f:
+            f.write(text)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
         subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
-                        "-I", cuda_inc, "-o", out, PK_SRC], check=True)
+                        "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_PK_SOURCE="{copy}"', "-o", out, PK_SRC],
+                       check=True)
     return C.CDLL(out)
 
 
@@ -417,6 +424,41 @@ def test_cell_order_kernel_sources_reproduce_the_oracle(pt, oracle, emup1, pertu
     assert not np.isnan(vals).any() and not np.isnan(b).any()
     ref = oracle.assemble_matrix(P)
     assert (np.abs(_sell_to_csr(P, L, vals, bs2) - ref) / _row_diag(P, ref, bs2)).max() <= 1e-12
+    if ptype == "poisson":  # + g v ds over the exterior facets (assemble_facets_p1)
+        ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], 4, 1, P.n_owned)
+        nv = len(P["x"]) // 3
+        xyz4 = np.zeros((nv, 4))
+        xyz4[:, :3] = np.array(P["x"]).reshape(-1, 3)
+        xyz4 = np.ascontiguousarray(xyz4.reshape(-1))
+        xd, dm, g = (np.ascontiguousarray(P["x_dofmap"]), np.ascontiguousarray(P["dofmap"]),
+                     np.ascontiguousarray(P["g"]))
+        assert emup1.emu_p1_facets(len(ids), _p(xyz4), _p(xd), _p(dm), _p(bc), _p(ids), _p(ptr), _p(ent),
+                                   _p(g), _p(b)) == 0
     b_ref = oracle.assemble_vector(P)
-    if ptype == "elasticity":  # Poisson's b also carries the facet term of another kernel
-        assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("order,dims,rank,nranks", [(2, (3, 2, 4), 0, 1), (3, (2, 3, 2), 0, 1), (2, (2, 2, 5), 1, 2)])
+def test_p2_p3_vector_and_facet_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, perturbed, order, dims,
+                                                                     rank, nranks, jitter):
+    P = pt.host.Problem("poisson", order, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
+    L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+    ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], P.nd, order, P.n_owned)
+    nv = len(P["x"]) // 3
+    xyz4 = np.zeros((nv, 4))
+    xyz4[:, :3] = np.array(P["x"]).reshape(-1, 3)
+    xyz4 = np.ascontiguousarray(xyz4.reshape(-1))
+    bc = np.zeros(P.n_owned + P.n_ghost, np.uint8)
+    bc[P["bc_dofs"]] = 1
+    b = np.full(P.n_owned, np.nan)
+    xd, dm = np.ascontiguousarray(P["x_dofmap"]), np.ascontiguousarray(P["dofmap"])
+    f, g = np.ascontiguousarray(P["f"]), np.ascontiguousarray(P["g"])
+    rc = emupk.emu_assemble_vector_pk(P.nd, P.n_owned, L["n_slices"], _p(xyz4), _p(xd), _p(dm), _p(bc),
+                                      _p(L["adj_off"]), _p(L["adj"]), _p(f), len(ids), _p(ids), _p(ptr),
+                                      _p(ent), _p(g), _p(b))
+    assert rc == 0 and not np.isnan(b).any()
+    b_ref = oracle.assemble_vector(P)
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
