@@ -634,6 +634,8 @@ void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p,
     return launch_action_matrix_free_pk(c, A, p, y, py_out);
   if (A.adjrot == nullptr)
     throw std::runtime_error("matrix-free operator: a P1 row has more than 254 columns");
+  if (launch_action_gwalk(c, A, p, y, py_out))
+    return;
   const int spc = MAT_THREADS_1 / 32;
   const int grid = (A.n_slices + spc - 1) / spc;
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);

@@ -38,6 +38,7 @@ struct InFlight
 {
   double2 xy, z_;
   double f[NF > 0 ? NF : 1];
+  std::int32_t cw; // the column word it was gathered through (top bit: flag set by the stager)
 };
 
 // Issue the gather of the vertex a later step brings in. Padding / no-load steps fetch offset 0
@@ -49,9 +50,11 @@ __device__ __forceinline__ InFlight<NF> gw_issue(std::uint32_t word, const std::
 {
   const bool loads = word != ADJ_INVALID_DEV && ((word >> 16) & 3u) != 3u;
   const int slot = loads ? static_cast<int>(word & 0xFFu) : 0;
-  const std::int64_t col = C[slot * 32] & INT32_MAX; // the top bit may carry the Dirichlet flag
+  const std::int32_t cw = C[slot * 32];
+  const std::int64_t col = cw & INT32_MAX; // the top bit may carry the Dirichlet flag
   const double2* p = reinterpret_cast<const double2*>(xdof + 4 * col);
   InFlight<NF> v;
+  v.cw = cw;
   v.xy = __ldg(p);
   v.z_ = __ldg(p + 1);
   if constexpr (NF > 0)
@@ -492,6 +495,134 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
     A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
 }
 
+// ------------------------------------------------------------------------------------------
+// Matrix-free operator, Poisson P1: y = A p without A (the `action` of the reference's cgpoisson
+// problem, cgpoisson_problem.cpp:193-230; form M = action(a, un), Poisson.py:33) along the same
+// walk: the new vertex brings its coordinates and its entry of p, the three values of p sit in
+// registers next to the edge vectors, no accumulator ever leaves the thread. Dirichlet handling as
+// in action_p1_poisson (assemble.cu): constrained columns count as zero, constrained rows return
+// p. One warp = one slice; its p.y partial goes to py_partials[slice] (fixed-order reduction by
+// reduce_partials). Shared memory: the column list with the Dirichlet flag in the top bit.
+// ------------------------------------------------------------------------------------------
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+action_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
+                const std::int64_t* __restrict__ walk1_off, const double* __restrict__ p,
+                double* __restrict__ y, double* __restrict__ py_partials)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * WARPS + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int64_t mo = A.mat_off[slice], so = walk1_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const int w1 = static_cast<int>((walk1_off[slice + 1] - so) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem) + static_cast<std::size_t>(warp) * A.max_w * 32 + lane;
+
+  const std::uint32_t word0 = w1 > 0 ? __ldg(walk1 + so + lane) : ADJ_INVALID_DEV;
+  const std::uint32_t* wp = walk1 + so + 32 + lane;
+  const int nsteps = w1 - 1;
+  std::uint32_t wd[GW_CHUNK];
+#pragma unroll
+  for (int j = 0; j < GW_CHUNK; ++j)
+    wd[j] = j < nsteps ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
+  const bool bc_row = live && A.bc[row];
+  const double p_own = live ? __ldg(p + row) : 0.0;
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  for (int k0 = 0; k0 < w; k0 += 16)
+  {
+    std::int32_t c[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+    std::uint8_t b[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c[j] >= 0)
+        b[j] = __ldg(A.bc + c[j]);
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      if (c[j] >= 0)
+        C[(k0 + j) * 32] = c[j] | (b[j] ? INT32_MIN : 0);
+  }
+
+  const bool valid0 = word0 != ADJ_INVALID_DEV;
+  const int o0 = valid0 ? word0 & 0xFFu : 0, o1 = valid0 ? (word0 >> 8) & 0xFFu : 0,
+            o2 = valid0 ? (word0 >> 16) & 0xFFu : 0;
+  const std::int32_t w0c = C[o0 * 32], w1c = C[o1 * 32], w2c = C[o2 * 32];
+  Vec3 e0 = load_point(A.xdof, w0c & INT32_MAX) - X0;
+  Vec3 e1 = load_point(A.xdof, w1c & INT32_MAX) - X0;
+  Vec3 e2 = load_point(A.xdof, w2c & INT32_MAX) - X0;
+  double p0 = w0c < 0 ? 0.0 : __ldg(p + (w0c & INT32_MAX));
+  double p1 = w1c < 0 ? 0.0 : __ldg(p + (w1c & INT32_MAX));
+  double p2 = w2c < 0 ? 0.0 : __ldg(p + (w2c & INT32_MAX));
+  InFlight<1> q[GW_AHEAD];
+#pragma unroll
+  for (int j = 0; j < GW_AHEAD; ++j)
+    q[j] = gw_issue<1>(wd[j], C, A.xdof, p, 1, 0);
+  Vec3 n0 = cross(e1, e2), n1 = cross(e2, e0), n2 = cross(e0, e1);
+  double sum = 0.0;
+  auto cell = [&](bool compute) {
+    const double det = dot(e0, n0);
+    const double r = compute ? rcp_nr(6.0 * fabs(det)) : 0.0;
+    const Vec3 c0 = {-(n0.x + n1.x + n2.x), -(n0.y + n1.y + n2.y), -(n0.z + n1.z + n2.z)};
+    sum = fma(r, ((dot(c0, c0) * p_own + dot(c0, n0) * p0) + dot(c0, n1) * p1) + dot(c0, n2) * p2, sum);
+  };
+  cell(valid0);
+  auto step = [&](std::uint32_t word, const InFlight<1>& v) {
+    const StepBits S = gw_decode(word);
+    const Vec3 xn = {v.xy.x, v.xy.y, v.z_.x};
+    const double pn = v.cw < 0 ? 0.0 : v.f[0];
+    if (S.p0)
+      e0 = xn - X0, p0 = pn;
+    if (S.p1)
+      e1 = xn - X0, p1 = pn;
+    if (S.p2)
+      e2 = xn - X0, p2 = pn;
+    if (S.p1 || S.p2)
+      n0 = cross(e1, e2);
+    if (S.p2 || S.p0)
+      n1 = cross(e2, e0);
+    if (S.p0 || S.p1)
+      n2 = cross(e0, e1);
+    cell(S.compute);
+  };
+  for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
+  {
+    std::uint32_t nx[GW_CHUNK];
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      nx[j] = k0 + GW_CHUNK + j < nsteps ? __ldg(wp + (k0 + GW_CHUNK + j) * 32) : ADJ_INVALID_DEV;
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+    {
+      const InFlight<1> cur = q[j % GW_AHEAD];
+      const std::uint32_t ahead = j + GW_AHEAD < GW_CHUNK ? wd[(j + GW_AHEAD) % GW_CHUNK]
+                                                          : nx[(j + GW_AHEAD) % GW_CHUNK];
+      q[j % GW_AHEAD] = gw_issue<1>(ahead, C, A.xdof, p, 1, 0);
+      step(wd[j], cur);
+    }
+#pragma unroll
+    for (int j = 0; j < GW_CHUNK; ++j)
+      wd[j] = nx[j];
+  }
+  const double yr = bc_row ? p_own : sum;
+  double dotv = 0.0;
+  if (live)
+  {
+    y[row] = yr;
+    dotv = yr * p_own;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    dotv += __shfl_xor_sync(0xffffffffu, dotv, o);
+  if (lane == 0)
+    py_partials[slice] = dotv;
+}
+
 } // namespace
 
 #ifndef PTB_HOST_EMU // launchers: device build only
@@ -547,6 +678,24 @@ bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
   }
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
+  return true;
+}
+
+bool launch_action_gwalk(ptb_ctx* c, const VectorArgs& A, const double* p, double* y, double* py_out)
+{
+  if (c->order != 1 || c->bs != 1 || c->walk1.p == nullptr)
+    return false;
+  constexpr int WARPS = 4;
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t) * WARPS;
+  PTB_CUDA(cudaFuncSetAttribute(action_p1_gwalk<WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                static_cast<int>(smem)));
+  c->mf_partials.alloc(static_cast<std::size_t>(A.n_slices));
+  action_p1_gwalk<WARPS><<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(
+      A, c->walk1.p, c->walk1_off.p, p, y, c->mf_partials.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  if (py_out != nullptr)
+    launch_reduce_partials(c, A.n_slices, c->mf_partials.p, py_out);
   return true;
 }
 

@@ -87,6 +87,7 @@ bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A);
 /// Direct-gather walk kernels (assemble_gwalk.cu, opt-in PTB_ASM_GWALK=1); same convention.
 bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A);
 bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A);
+bool launch_action_gwalk(ptb_ctx* c, const VectorArgs& A, const double* p, double* y, double* py_out);
 void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 /// Matrix-free y = A p (Poisson P1); py_out (device, optional) receives the local p.y.

@@ -107,6 +107,29 @@ def abpk(ndofs):
         c.close()
 
 
+def abmf(ndofs):
+    """Matrix-free CG (cgpoisson's action) on Poisson P1: staged-star kernel vs direct-gather walk,
+    next to the assembled operator; DOF-iterations/s from the device time of the solve stage."""
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    for name, env in (("staged", {}), ("gwalk", {"PTB_ASM_GWALK": "1"})):
+        os.environ.pop("PTB_ASM_GWALK", None)
+        os.environ.update(env)
+        c = pt.abi.Context(0)
+        c.set_problem(P)
+        c.assemble_matrix()
+        c.assemble_vector()
+        for mode in ("assembled", "matrix_free"):
+            c.set_operator_mode(mode)
+            k, rel = c.cg_solve(kmax=200, rtol=1e-30)
+            ms = c.stage_ms(pt.abi.STAGE_SOLVE)
+            res[f"cg_{name}_{mode}"] = {"iterations": k, "solve_ms": ms,
+                                        "gdof_it_per_s": k * P.n_owned / ms / 1e6}
+            dump()
+        c.close()
+
+
 def ncu_target(ndofs):
     nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
     f = 2 ** r
@@ -133,6 +156,8 @@ def main():
         return ab(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ab2":
         return ab2(int(sys.argv[2]))
+    if len(sys.argv) > 2 and sys.argv[1] == "abmf":
+        return abmf(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "abpk":
         return abpk(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ncu":

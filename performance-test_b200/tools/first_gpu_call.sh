@@ -14,6 +14,8 @@ WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-tes
 echo "== ncu --set full of the direct-gather kernels (Poisson 4M): read it with tools/ncu_summary.py"
 PTB_ASM_GWALK=1 timeout 200 ncu --set full --import-source on --clock-control none -k regex:gwalk -c 2 -f \
   -o "$out/prof_gwalk" python performance-test_b200/tools/check_walk.py ncu2 4000000 2>&1 | tail -3
+echo "== matrix-free CG (cgpoisson action), staged star vs direct-gather walk (4M DOFs)"
+WALK_CHECK_OUT=first_call/matrix_free_4M.json timeout 200 python performance-test_b200/tools/check_walk.py abmf 4000000 2>&1 | tail -2
 echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
 echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"

@@ -35,6 +35,18 @@ static inline T __ldg(const T* p)
 {
   return *p;
 }
+// warp shuffle (only the matrix-free action uses one): the 32 threads of a warp meet at a barrier
+static std::barrier<>* emu_warp[32];
+static double emu_xd[32][32];
+static inline double __shfl_xor_sync(unsigned, double v, int o)
+{
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  emu_xd[w][l] = v;
+  emu_warp[w]->arrive_and_wait();
+  const double r = emu_xd[w][l ^ o];
+  emu_warp[w]->arrive_and_wait();
+  return r;
+}
 
 namespace ptb
 {
@@ -57,6 +69,12 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
   {
     std::barrier<> bar(block);
     emu_barrier = &bar;
+    std::vector<std::unique_ptr<std::barrier<>>> wb;
+    for (unsigned w = 0; w < (block + 31) / 32; ++w)
+    {
+      wb.push_back(std::make_unique<std::barrier<>>(32));
+      emu_warp[w] = wb.back().get();
+    }
     std::vector<std::thread> th;
     th.reserve(block);
     for (unsigned t = 0; t < block; ++t)
@@ -103,6 +121,19 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
     break;
   default: return 1;
   }
+  return 0;
+}
+
+// y = A p without A (action_p1_gwalk) + the per-slice partials of p.y
+int emu_action(int32_t n_rows, int32_t n_slices, int max_w, const uint8_t* bc, const int64_t* mat_off,
+               const int32_t* cols, const double* xdof, const uint32_t* walk1,
+               const int64_t* walk1_off, const double* p, double* y, double* partials)
+{
+  using namespace ptb;
+  VectorArgs A{};
+  A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.mat_off = mat_off, A.cols = cols;
+  A.xdof = xdof, A.max_w = max_w;
+  emu_launch(action_p1_gwalk<4>, (n_slices + 3) / 4, 128, A, walk1, walk1_off, p, y, partials);
   return 0;
 }
 

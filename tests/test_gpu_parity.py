@@ -426,3 +426,26 @@ def test_assembly_and_solve_on_a_jittered_mesh(pt, oracle, perturbed, ctx, ptype
     assert abs(k - k_ref) <= 1 and rel < 1e-8
     x = ctx.solution()[: P.n_owned * P.bs]
     assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
+@OPTIN
+@pytest.mark.parametrize("dims", [(5, 4, 6), (16, 15, 17), (1, 1, 1)])
+def test_opt_in_matrix_free_action_equals_assembled_operator(pt, monkeypatch, dims):
+    """PTB_ASM_GWALK=1 also switches the matrix-free P1 operator to action_p1_gwalk."""
+    P = pt.host.Problem("poisson", 1, *dims)
+    monkeypatch.setenv("PTB_ASM_GWALK", "1")
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P)
+        c.assemble_matrix()
+        c.assemble_vector()
+        p = np.random.default_rng(5).standard_normal(P.n_owned + P.n_ghost)
+        y_a = c.apply_operator(p)
+        k_a, _ = c.cg_solve(kmax=5000, rtol=1e-8)
+        c.set_operator_mode("matrix_free")
+        y_m = c.apply_operator(p)
+        assert np.abs(y_m - y_a).max() <= 1e-12 * np.abs(y_a).max()
+        k_m, rel = c.cg_solve(kmax=5000, rtol=1e-8)
+        assert abs(k_m - k_a) <= 1 and rel < 1e-8
+    finally:
+        c.close()

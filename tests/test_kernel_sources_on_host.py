@@ -462,3 +462,26 @@ def test_p2_p3_vector_and_facet_kernel_sources_reproduce_the_oracle(pt, oracle, 
     assert rc == 0 and not np.isnan(b).any()
     b_ref = oracle.assemble_vector(P)
     assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("dims,rank,nranks", [((5, 4, 6), 0, 1), ((1, 1, 1), 0, 1), ((4, 3, 5), 1, 2)])
+def test_matrix_free_action_source_equals_the_assembled_operator(pt, oracle, emu, perturbed, dims, rank, nranks,
+                                                                 jitter):
+    """action_p1_gwalk (the cgpoisson `action` without A) against the oracle's assembled matrix: same
+    Dirichlet treatment (constrained columns count as zero, constrained rows return p), and the
+    per-slice partials add up to p.y."""
+    P = pt.host.Problem("poisson", 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
+    L, xdof, bc = _inputs(pt, P)
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal(P.n_owned + P.n_ghost)
+    y = np.full(P.n_owned, np.nan)
+    partials = np.full(L["n_slices"], np.nan)
+    assert emu.emu_action(P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(L["mat_off"]), _p(L["cols"]),
+                          _p(xdof), _p(L["walk1"]), _p(L["walk1_off"]), _p(p), _p(y), _p(partials)) == 0
+    A = oracle.assemble_matrix(P)
+    y_ref = oracle.spmv(1, P.n_owned, P["rowptr"], P["cols"], A, p)
+    assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
+    assert abs(partials.sum() - y_ref @ p[:P.n_owned]) <= 1e-12 * abs(y_ref @ p[:P.n_owned]) + 1e-13
