@@ -413,7 +413,16 @@ def main():
                        "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"
                              if P.nnz * 12 * P.bs > 3e8 else "working set near L2 size: small config",
                        "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "
-                                            "Plaza refinement (same entity counts)" if base[3] else None},
+                                            "Plaza refinement (same entity counts)" if base[3] else None,
+                       "switches": {k: v for k, v in os.environ.items() if k.startswith("PTB_")},
+                       "matrix_kernel": ("assemble_matrix_pk" if order > 1 else
+                                         "assemble_matrix_p1<3> (cell order)" if ptype == "elasticity"
+                                         and os.environ.get("PTB_ASM_WALK3") != "1"
+                                         and os.environ.get("PTB_ASM_GWALK") != "1" else
+                                         "assemble_matrix_p1_walk (star walk)" if ptype == "poisson"
+                                         and os.environ.get("PTB_ASM_WALK", "1") != "0"
+                                         and os.environ.get("PTB_ASM_GWALK") != "1" else
+                                         "see switches")},
             "e2e": {"value": e2e_value, "unit": "DOF-iters/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "note": "per step: x, f, g host->device from pinned memory, assemble A and b, "
