@@ -159,53 +159,93 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
 
-  for (int k = 0; k < wa; ++k)
+  // Cell loop, two cells per trip: the three dependent load levels of a cell (pair and slot words
+  // -> vertex ids -> coordinates) are issued for both cells before either is consumed.
+  constexpr int CB = 2;
+  for (int k0 = 0; k0 < wa; k0 += CB)
   {
-    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
-    if (pair == ADJ_INVALID_DEV)
-      continue;
-    std::uint32_t words[NW];
+    std::uint32_t pair[CB], words[CB][NW];
 #pragma unroll
-    for (int q = 0; q < NW; ++q)
-      words[q] = A.adjso[(ao + k * 32) * NW + q * 32 + lane];
-    const std::uint32_t cell = pair / ND;
-    const int li = pair - cell * ND;
-    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
-    const Vec3 X0 = load_point(A.xyz, v.x);
-    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
-               e3 = load_point(A.xyz, v.w) - X0;
-    // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
-    const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
-    const double inv = 1.0 / fabs(dot(e1, c1));
-    const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
-                 G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
-    const double* S = St + li * ND;
-#pragma unroll
-    for (int j = 0; j < ND; ++j)
+    for (int u = 0; u < CB; ++u)
     {
-      const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
-                         + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
-                         + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
-      acc[slot_of<ND, WIDE>(words, j) * 32 + lane] += val;
+      const bool in = k0 + u < wa;
+      pair[u] = in ? A.adj[ao + (k0 + u) * 32 + lane] : ADJ_INVALID_DEV;
+#pragma unroll
+      for (int q = 0; q < NW; ++q)
+        words[u][q] = in ? A.adjso[(ao + (k0 + u) * 32) * NW + q * 32 + lane] : 0u;
+    }
+    int4 v[CB];
+    int li[CB];
+#pragma unroll
+    for (int u = 0; u < CB; ++u)
+    {
+      const std::uint32_t cell = pair[u] == ADJ_INVALID_DEV ? 0u : pair[u] / ND; // padding reads cell 0
+      li[u] = pair[u] == ADJ_INVALID_DEV ? 0 : static_cast<int>(pair[u] - cell * ND);
+      v[u] = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    }
+    Vec3 X[CB][4];
+#pragma unroll
+    for (int u = 0; u < CB; ++u)
+    {
+      X[u][0] = load_point(A.xyz, v[u].x), X[u][1] = load_point(A.xyz, v[u].y);
+      X[u][2] = load_point(A.xyz, v[u].z), X[u][3] = load_point(A.xyz, v[u].w);
+    }
+#pragma unroll
+    for (int u = 0; u < CB; ++u)
+    {
+      if (pair[u] == ADJ_INVALID_DEV)
+        continue;
+      const Vec3 e1 = X[u][1] - X[u][0], e2 = X[u][2] - X[u][0], e3 = X[u][3] - X[u][0];
+      // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
+      const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+      const double inv = 1.0 / fabs(dot(e1, c1));
+      const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
+                   G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+      const double* S = St + li[u] * ND;
+#pragma unroll
+      for (int j = 0; j < ND; ++j)
+      {
+        const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
+                           + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
+                           + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+        acc[slot_of<ND, WIDE>(words[u], j) * 32 + lane] += val;
+      }
     }
   }
 
+  // Epilogue in chunks of eight entries: column indices, then their Dirichlet flags, then the
+  // stores -- two exposed load latencies per eight values instead of two per value.
   const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
   const bool bc_row = live && A.bc[row];
   double diag = 1.0;
-  for (int k = 0; k < w; ++k)
+  constexpr int EB = 8;
+  for (int k0 = 0; k0 < w; k0 += EB)
   {
-    const std::int32_t col = A.cols[mo + k * 32 + lane];
-    const bool real = k < len;
-    const bool own = real && col == row;
-    double val = acc[k * 32 + lane];
-    if (bc_row || (real && A.bc[col]))
-      val = own ? 1.0 : 0.0;
-    if (!real)
-      val = 0.0;
-    A.vals[mo + k * 32 + lane] = val;
-    if (own)
-      diag = val;
+    std::int32_t col[EB];
+    std::uint8_t flag[EB];
+#pragma unroll
+    for (int u = 0; u < EB; ++u)
+      col[u] = k0 + u < w ? A.cols[mo + (k0 + u) * 32 + lane] : 0;
+#pragma unroll
+    for (int u = 0; u < EB; ++u)
+      flag[u] = A.bc[col[u]];
+#pragma unroll
+    for (int u = 0; u < EB; ++u)
+    {
+      const int k = k0 + u;
+      if (k >= w)
+        break;
+      const bool real = k < len;
+      const bool own = real && col[u] == row;
+      double val = acc[k * 32 + lane];
+      if (bc_row || (real && flag[u]))
+        val = own ? 1.0 : 0.0;
+      if (!real)
+        val = 0.0;
+      A.vals[mo + k * 32 + lane] = val;
+      if (own)
+        diag = val;
+    }
   }
   if (live)
     A.dinv[row] = 1.0 / diag;
