@@ -348,3 +348,41 @@ def test_direct_gather_walk_reproduces_the_oracle(pt, oracle, perturbed, ptype, 
             assert np.abs(b - b_ref)[keep].max() <= 1e-12 * np.abs(b_ref).max()
     else:
         assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
+# ---- random boxes and partitions ------------------------------------------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=12, deadline=None)
+@given(nx=st.integers(1, 4), ny=st.integers(1, 4), nz=st.integers(1, 5), nranks=st.integers(1, 3),
+       rank_pick=st.integers(0, 2), elastic=st.booleans())
+def test_walks_on_random_boxes_and_partitions(pt, nx, ny, nz, nranks, rank_pick, elastic):
+    """Both walk encodings on arbitrary small boxes / z-slab partitions: every cell once, consistent
+    register positions, evictions name the vertex the position held, and walk1 replays walk."""
+    nranks = min(nranks, nz)
+    rank = rank_pick % nranks
+    P = pt.host.Problem("elasticity" if elastic else "poisson", 1, nx, ny, nz, rank, nranks)
+    args = (P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    words, _ = pt.abi.star_walk(*args)
+    ptr1, words1 = pt.abi.star_walk_single(*args)
+    ptr, rp, cl = _pair_ptr(P), P["rowptr"], P["cols"]
+    dm = P["dofmap"].reshape(-1, 4)
+    cells = _row_cells(P)
+    for r in range(P.n_owned):
+        want = sorted(tuple(sorted(int(dm[c, (li + t) & 3]) for t in (1, 2, 3))) for c, li in cells[r])
+        ref = [_decode(int(w)) for w in words[ptr[r]:ptr[r + 1]]]
+        assert sorted(tuple(sorted(int(cl[rp[r] + o]) for o in pos)) for pos, _ in ref) == want
+        assert ref[0][1] == 7
+        for (p0, _), (p1, m1) in zip(ref, ref[1:]):
+            assert all(p1[p] == p0[p] for p in range(3) if not (m1 >> p) & 1)
+        pos, seen = list(ref[0][0]), [tuple(ref[0][0])]
+        assert _decode(int(words1[ptr1[r]])) == ref[0]
+        for w in words1[ptr1[r] + 1:ptr1[r + 1]]:
+            new, old, p, compute = _decode1(int(w))
+            if p < 3:
+                assert pos[p] == old
+                pos[p] = new
+            if compute:
+                seen.append(tuple(pos))
+        assert seen == [pos_ for pos_, _ in ref]
