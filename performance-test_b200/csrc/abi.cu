@@ -82,7 +82,7 @@ std::int64_t ptb_ctx::device_bytes() const
          + adjso.bytes() + adjrot.bytes() + walk.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
-         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes()
+         + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes() + zcnt_w.bytes() + zcnt_x.bytes() + mat_off_z.bytes() + xoff_z.bytes() + vals_z.bytes() + cdelta_z.bytes() + colsx_z.bytes()
          + peer.src_index.bytes();
 }
 
@@ -356,6 +356,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     }
     c->have_pattern = true;
     c->matrix_assembled = false;
+    c->have_compact = false;
   });
 }
 
@@ -486,6 +487,9 @@ int ptb_assemble_matrix(ptb_ctx* c)
                  c->dofmap.p, c->bc.p, c->rowptr.p, c->mat_off.p, c->adj_off.p, c->cols.p,
                  c->adj.p, c->adjso.p, c->adjrot.p, c->xdof.p, c->max_w, c->vals.p, c->dinv.p};
     launch_assemble_matrix(c, A);
+    c->have_compact = false;
+    if (env_flag("PTB_SPMV_COMPACT", false))
+      compact_operator(c); // part of the assembly stage: the SpMV then skips all-zero positions
     t.stop();
     c->matrix_assembled = true;
   });

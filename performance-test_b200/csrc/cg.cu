@@ -1086,8 +1086,7 @@ int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, s
 void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
                  bool fused_halo)
 {
-  SpmvArgs A{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
-             c->cdelta.p, c->colsx.p, c->xoff.p};
+  const SpmvArgs A = spmv_args(c);
   const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const PeerView P = peer_view(c);
   FusedHalo FH{};
@@ -1163,8 +1162,7 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   if (c->bs != 1 && c->bs != 3)
     return false;
   LoopArgs L{};
-  L.A = SpmvArgs{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
-                 c->cdelta.p, c->colsx.p, c->xoff.p};
+  L.A = spmv_args(c);
   L.n = static_cast<std::int64_t>(c->n_owned) * c->bs;
   L.dinv = dinv;
   L.r = c->r.p, L.p = c->p.p, L.x = c->x.p, L.y = c->y.p;

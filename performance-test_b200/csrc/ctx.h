@@ -127,6 +127,12 @@ struct ptb_ctx
   ptb::DevBuf<std::int32_t> cdelta, colsx; // compressed column indices for the scalar SpMV
   ptb::DevBuf<std::int64_t> xoff;
   double cols_explicit_frac = 1.0;
+  // zero-column compaction of the scalar operator for the SpMV (compact.cu, PTB_SPMV_COMPACT=1)
+  ptb::DevBuf<std::int64_t> zcnt_w, zcnt_x, mat_off_z, xoff_z;
+  ptb::DevBuf<double> vals_z;
+  ptb::DevBuf<std::int32_t> cdelta_z, colsx_z;
+  bool have_compact = false;
+  std::int64_t compact_nnz = 0; // stored entries (padding included) of the compacted copy
   ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)
   std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry

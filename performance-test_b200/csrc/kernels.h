@@ -79,6 +79,18 @@ struct SpmvArgs
   const std::int64_t* xoff;
 };
 
+/// The operator view the SpMV kernels read: the compacted copy when one is current (compact.cu).
+inline SpmvArgs spmv_args(const ptb_ctx* c)
+{
+  if (c->have_compact)
+    return SpmvArgs{c->n_owned, c->n_slices, c->mat_off_z.p, c->cols.p, c->vals_z.p,
+                    c->cdelta_z.p, c->colsx_z.p, c->xoff_z.p};
+  return SpmvArgs{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
+                  c->cdelta.p, c->colsx.p, c->xoff.p};
+}
+/// Build the zero-column-compacted copy of the assembled scalar operator (no-op for bs = 3).
+void compact_operator(ptb_ctx* c);
+
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 /// Star-walk variant (assemble_walk.cu); returns false when it does not apply (no walk uploaded,

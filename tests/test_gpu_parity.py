@@ -449,3 +449,25 @@ def test_opt_in_matrix_free_action_equals_assembled_operator(pt, monkeypatch, di
         assert abs(k_m - k_a) <= 1 and rel < 1e-8
     finally:
         c.close()
+
+
+@OPTIN
+@pytest.mark.parametrize("dims", [(16, 15, 17), (5, 4, 6), (1, 1, 1), (33, 9, 5)])
+def test_opt_in_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, dims):
+    """PTB_SPMV_COMPACT=1: the SpMV runs on a copy of A without the all-zero SELL positions; y is
+    unchanged to the bit, CG takes the same iterations, the C ABI still returns the full pattern."""
+    P = pt.host.Problem("poisson", 1, *dims)
+    p = np.random.default_rng(9).standard_normal(P.n_owned + P.n_ghost)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("PTB_SPMV_COMPACT", flag)
+        c = pt.abi.Context(0)
+        c.set_problem(P)
+        c.assemble_matrix()
+        c.assemble_vector()
+        out[flag] = (c.apply_operator(p), c.cg_solve(kmax=5000, rtol=1e-8), c.matrix_values())
+        c.close()
+    assert np.array_equal(out["0"][0], out["1"][0])
+    assert out["0"][1][0] == out["1"][1][0]
+    assert np.array_equal(out["0"][2], out["1"][2])
+    _check_matrix(P, out["1"][2], oracle.assemble_matrix(P))

@@ -485,3 +485,81 @@ def test_matrix_free_action_source_equals_the_assembled_operator(pt, oracle, emu
     y_ref = oracle.spmv(1, P.n_owned, P["rowptr"], P["cols"], A, p)
     assert np.abs(y - y_ref).max() <= 1e-12 * np.abs(y_ref).max()
     assert abs(partials.sum() - y_ref @ p[:P.n_owned]) <= 1e-12 * abs(y_ref @ p[:P.n_owned]) + 1e-13
+
+
+# ---- zero-column compaction of the scalar operator (csrc/compact.cu) --------------------------------
+
+CP_SRC = os.path.join(HERE, "emu", "emu_compact.cpp")
+
+
+@pytest.fixture(scope="module")
+def emucp():
+    out = os.path.join(HERE, "emu", "_build", "libemucompact.so")
+    deps = [CP_SRC] + [os.path.join(CSRC, f) for f in ("compact.cu", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        text = open(os.path.join(CSRC, "compact.cu")).read().replace("__shared__", "static")
+        copy = os.path.join(os.path.dirname(out), "compact_emu.cu")
+        with open(copy, "w") as f:
+            f.write(text)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_COMPACT_SOURCE="{copy}"', "-o", out, CP_SRC],
+                       check=True)
+    return C.CDLL(out)
+
+
+def _sell_spmv(n_rows, mat_off, vals, cdelta, colsx, xoff, p):
+    """numpy restatement of spmv_slice<1> on the compressed SELL-32 arrays."""
+    y = np.zeros(n_rows)
+    for s in range(len(mat_off) - 1):
+        mo, w = int(mat_off[s]), int(mat_off[s + 1] - mat_off[s]) // 32
+        jx = 0
+        for k in range(w):
+            d = int(cdelta[mo // 32 + k])
+            for lane in range(32):
+                r = 32 * s + lane
+                if r >= n_rows:
+                    continue
+                c = int(colsx[int(xoff[s]) + jx * 32 + lane]) if d == -2 ** 31 else r + d
+                y[r] += vals[mo + k * 32 + lane] * p[c]
+            jx += d == -2 ** 31
+    return y
+
+
+@pytest.mark.parametrize("dims,rank,nranks,jitter", [((6, 5, 7), 0, 1, False), ((9, 3, 4), 1, 2, False),
+                                                     ((5, 4, 6), 0, 1, True)])
+def test_operator_compaction_source_keeps_the_operator(pt, oracle, emucp, perturbed, dims, rank, nranks, jitter):
+    P = pt.host.Problem("poisson", 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
+    A = oracle.assemble_matrix(P)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    S, rp = L["n_slices"], P["rowptr"]
+    vals = np.zeros(int(L["mat_off"][-1]))
+    for r in range(P.n_owned):
+        mo = L["mat_off"][r >> 5]
+        vals[mo + np.arange(rp[r + 1] - rp[r]) * 32 + (r & 31)] = A[rp[r]:rp[r + 1]]
+    cdelta, xoff, colsx = pt.abi.compressed_columns(P.n_owned, P.n_owned + P.n_ghost, rp, P["cols"],
+                                                    int(L["mat_off"][-1]))
+    cw, cx = np.zeros(S, np.int64), np.zeros(S, np.int64)
+    moz, xoz = np.full(S + 1, -1, np.int64), np.full(S + 1, -1, np.int64)
+    assert emucp.emu_compact_offsets(S, _p(L["mat_off"]), _p(vals), _p(cdelta), _p(cw), _p(cx), _p(moz),
+                                     _p(xoz)) == 0
+    assert moz[0] == 0 and np.array_equal(np.diff(moz), cw) and np.array_equal(np.diff(xoz), cx)
+    vz = np.full(int(moz[-1]), np.nan)
+    cdz = np.zeros(int(moz[-1]) // 32, np.int32)
+    cxz = np.zeros(max(int(xoz[-1]), 1), np.int32)
+    assert emucp.emu_compact_copy(S, _p(L["mat_off"]), _p(vals), _p(cdelta), _p(colsx), _p(xoff), _p(moz),
+                                  _p(xoz), _p(vz), _p(cdz), _p(cxz)) == 0
+    assert not np.isnan(vz).any()
+    p = np.random.default_rng(2).standard_normal(P.n_owned + P.n_ghost)
+    y0 = _sell_spmv(P.n_owned, L["mat_off"], vals, cdelta, colsx, xoff, p)
+    y1 = _sell_spmv(P.n_owned, moz, vz, cdz, cxz, xoz, p)
+    assert np.array_equal(y0, y1)                      # the dropped terms were exact zeros
+    assert np.abs(y0 - oracle.spmv(1, P.n_owned, rp, P["cols"], A, p)).max() <= 1e-13 * np.abs(y0).max()
+    kept = moz[-1] / L["mat_off"][-1]
+    if jitter:
+        assert kept > 0.9                              # a general mesh has (almost) no exact zeros
+    else:
+        assert kept < 0.75                             # the lattice operator is the 7-point stencil
