@@ -375,9 +375,13 @@ def main():
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": spmv_b, "ms_per_launch": t_spmv,
                 "cols_explicit_fraction": ctx.cols_explicit_fraction(),
+                "spmv_stored_entries": ctx.spmv_stored_entries(),
+                "pattern_entries": P.nnz,
                 "note": ("achieved counts the ALGORITHMIC CSR bytes (8 B value + 4 B column per nnz); "
                          "the kernel stores one delta per 32 rows where the stencil is translation "
-                         "invariant, so it moves fewer index bytes than that and frac can exceed 1"),
+                         "invariant, so it moves fewer index bytes than that and frac can exceed 1. "
+                         "spmv_stored_entries < pattern_entries means PTB_SPMV_COMPACT dropped the "
+                         "SELL positions that are 0.0 in all 32 rows of a slice (y unchanged)"),
                 "other_kernels": {
                     "cg_update": {"ms": t_upd, "GBps": 32.0 * P.n_owned * P.bs / t_upd / 1e6},
                     "cg_direction": {"ms": t_dir, "GBps": 48.0 * P.n_owned * P.bs / t_dir / 1e6},

@@ -203,6 +203,9 @@ enum { PTB_KERNEL_SPMV = 0, PTB_KERNEL_CG_UPDATE = 1, PTB_KERNEL_CG_DIRECTION = 
 int ptb_time_kernel(ptb_ctx* ctx, int which, int reps, double* ms_avg);
 /* Kernels launched by this context so far. */
 int64_t ptb_launch_count(const ptb_ctx* ctx);
+/* Block entries (SELL padding included) the operator kernels actually stream per application:
+ * the full pattern, or the zero-compacted copy when PTB_SPMV_COMPACT=1 built one. */
+int64_t ptb_spmv_stored_entries(const ptb_ctx* ctx);
 /* Fraction of the SpMV's column indices stored explicitly (the rest are one warp-uniform
  * delta per 32 rows; scalar matrices only, 1.0 otherwise). */
 double ptb_cols_explicit_fraction(const ptb_ctx* ctx);

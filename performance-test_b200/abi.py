@@ -85,6 +85,8 @@ def lib():
         L.ptb_launch_count.restype = i64
         L.ptb_cols_explicit_fraction.argtypes = [vp]
         L.ptb_cols_explicit_fraction.restype = dbl
+        L.ptb_spmv_stored_entries.argtypes = [vp]
+        L.ptb_spmv_stored_entries.restype = i64
         L.ptb_device_bytes.argtypes = [vp]
         L.ptb_device_bytes.restype = i64
         _lib = L
@@ -404,6 +406,9 @@ class Context:
 
     def cols_explicit_fraction(self):
         return lib().ptb_cols_explicit_fraction(self._h)
+
+    def spmv_stored_entries(self):
+        return lib().ptb_spmv_stored_entries(self._h)
 
     def device_bytes(self):
         return lib().ptb_device_bytes(self._h)

@@ -1034,5 +1034,12 @@ double ptb_stage_ms(const ptb_ctx* c, int stage)
 int64_t ptb_launch_count(const ptb_ctx* c) { return c ? c->launches : 0; }
 int64_t ptb_device_bytes(const ptb_ctx* c) { return c ? c->device_bytes() : 0; }
 double ptb_cols_explicit_fraction(const ptb_ctx* c) { return c ? c->cols_explicit_frac : 1.0; }
+int64_t ptb_spmv_stored_entries(const ptb_ctx* c)
+{
+  if (!c)
+    return 0;
+  return c->have_compact ? c->compact_nnz
+                         : static_cast<std::int64_t>(c->vals.n) / std::max(1, c->bs * c->bs);
+}
 
 } // extern "C"
