@@ -7,7 +7,9 @@
 // After assembly this pass builds a second SELL-32 copy of the matrix in which a position k of a
 // slice is dropped when all 32 rows hold 0.0 there. Dropping whole positions keeps the
 // translation-invariant column deltas of layout.h intact, so the SpMV kernels run unchanged on
-// the compacted arrays; y is bit-identical (the dropped terms were +-0 * p). The assembled values
+// the compacted arrays; y is bit-identical (the dropped terms were +-0 * p). An optional tolerance
+// (PTB_SPMV_COMPACT_TOL, relative to the row's diagonal) also drops rounding residue of analytic
+// zeros; then y changes at that level. The assembled values
 // the C ABI hands out (ptb_get_matrix_values) stay the full pattern.
 //   count   one warp per slice: kept positions / kept explicit positions
 //   scan    exclusive prefix sums -> mat_off, xoff of the compacted copy
@@ -16,6 +18,7 @@
 // tests/emu against the uncompacted operator.
 #include "kernels.h"
 #include <climits>
+#include <cstdlib>
 
 namespace ptb
 {
@@ -24,16 +27,25 @@ namespace
 
 constexpr int CP_THREADS = 256;
 
+// A position survives when some row of the slice holds more than `floor` there; floor = tol * |a_rr|
+// of the lane's row (tol = 0: exact zeros only).
 __device__ __forceinline__ bool position_kept(const double* __restrict__ vals, std::int64_t mo, int k,
-                                              int lane)
+                                              int lane, double floor)
 {
-  return __ballot_sync(0xffffffffu, vals[mo + static_cast<std::int64_t>(k) * 32 + lane] != 0.0) != 0u;
+  return __ballot_sync(0xffffffffu, fabs(vals[mo + static_cast<std::int64_t>(k) * 32 + lane]) > floor) != 0u;
+}
+__device__ __forceinline__ double row_floor(const double* __restrict__ dinv, std::int32_t n_rows,
+                                            std::int32_t s, int lane, double tol)
+{
+  const std::int32_t row = s * 32 + lane;
+  return tol > 0.0 && row < n_rows ? tol / fabs(dinv[row]) : 0.0;
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
-compact_count(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
+compact_count(std::int32_t n_rows, std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
               const double* __restrict__ vals, const std::int32_t* __restrict__ cdelta,
-              std::int64_t* __restrict__ cnt_w, std::int64_t* __restrict__ cnt_x)
+              const double* __restrict__ dinv, double tol, std::int64_t* __restrict__ cnt_w,
+              std::int64_t* __restrict__ cnt_x)
 {
   const int lane = threadIdx.x & 31;
   const std::int32_t s = blockIdx.x * (CP_THREADS / 32) + (threadIdx.x >> 5);
@@ -41,9 +53,10 @@ compact_count(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
     return;
   const std::int64_t mo = mat_off[s];
   const int w = static_cast<int>((mat_off[s + 1] - mo) >> 5);
+  const double floor = row_floor(dinv, n_rows, s, lane, tol);
   int kept = 0, kept_x = 0;
   for (int k = 0; k < w; ++k)
-    if (position_kept(vals, mo, k, lane))
+    if (position_kept(vals, mo, k, lane, floor))
     {
       ++kept;
       kept_x += cdelta[(mo >> 5) + k] == INT32_MIN ? 1 : 0;
@@ -89,8 +102,9 @@ scan_exclusive(std::int64_t n, const std::int64_t* __restrict__ in, std::int64_t
 }
 
 __global__ void __launch_bounds__(CP_THREADS)
-compact_copy(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
+compact_copy(std::int32_t n_rows, std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
              const double* __restrict__ vals, const std::int32_t* __restrict__ cdelta,
+             const double* __restrict__ dinv, double tol,
              const std::int32_t* __restrict__ colsx, const std::int64_t* __restrict__ xoff,
              const std::int64_t* __restrict__ mat_off_z, const std::int64_t* __restrict__ xoff_z,
              double* __restrict__ vals_z, std::int32_t* __restrict__ cdelta_z,
@@ -103,12 +117,13 @@ compact_copy(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
   const std::int64_t mo = mat_off[s], moz = mat_off_z[s];
   const std::int64_t xo = xoff[s], xoz = xoff_z[s];
   const int w = static_cast<int>((mat_off[s + 1] - mo) >> 5);
+  const double floor = row_floor(dinv, n_rows, s, lane, tol);
   int j = 0, ix = 0, jx = 0; // kept so far; explicit positions seen / kept so far
   for (int k = 0; k < w; ++k)
   {
     const std::int32_t d = cdelta[(mo >> 5) + k];
     const bool explicit_k = d == INT32_MIN;
-    if (position_kept(vals, mo, k, lane))
+    if (position_kept(vals, mo, k, lane, floor))
     {
       vals_z[moz + static_cast<std::int64_t>(j) * 32 + lane] = vals[mo + static_cast<std::int64_t>(k) * 32 + lane];
       if (lane == 0)
@@ -137,8 +152,13 @@ void compact_operator(ptb_ctx* c)
   c->mat_off_z.alloc(static_cast<std::size_t>(S) + 1);
   c->xoff_z.alloc(static_cast<std::size_t>(S) + 1);
   const int grid = (S + CP_THREADS / 32 - 1) / (CP_THREADS / 32);
-  compact_count<<<grid, CP_THREADS, 0, c->stream>>>(S, c->mat_off.p, c->vals.p, c->cdelta.p,
-                                                     c->zcnt_w.p, c->zcnt_x.p);
+  // PTB_SPMV_COMPACT_TOL (default 0 = exact zeros only): entries below tol * |a_rr| count as zero.
+  // With fused multiply-adds the analytic zeros of the lattice operator may come out as rounding
+  // residue (1e-17 |a_rr|) instead of 0.0; a tolerance of 1e-14 treats them as what they are.
+  const char* te = std::getenv("PTB_SPMV_COMPACT_TOL");
+  const double tol = te && *te ? std::atof(te) : 0.0;
+  compact_count<<<grid, CP_THREADS, 0, c->stream>>>(c->n_owned, S, c->mat_off.p, c->vals.p, c->cdelta.p,
+                                                     c->dinv.p, tol, c->zcnt_w.p, c->zcnt_x.p);
   scan_exclusive<<<1, 1024, 0, c->stream>>>(S, c->zcnt_w.p, c->mat_off_z.p);
   scan_exclusive<<<1, 1024, 0, c->stream>>>(S, c->zcnt_x.p, c->xoff_z.p);
   PTB_CUDA(cudaGetLastError());
@@ -154,8 +174,8 @@ void compact_operator(ptb_ctx* c)
     c->cdelta_z.alloc(static_cast<std::size_t>(tot[0] / 32));
   if (c->colsx_z.n < static_cast<std::size_t>(std::max<std::int64_t>(tot[1], 1)))
     c->colsx_z.alloc(static_cast<std::size_t>(std::max<std::int64_t>(tot[1], 1)));
-  compact_copy<<<grid, CP_THREADS, 0, c->stream>>>(S, c->mat_off.p, c->vals.p, c->cdelta.p, c->colsx.p,
-                                                    c->xoff.p, c->mat_off_z.p, c->xoff_z.p, c->vals_z.p,
+  compact_copy<<<grid, CP_THREADS, 0, c->stream>>>(c->n_owned, S, c->mat_off.p, c->vals.p, c->cdelta.p,
+                                                    c->dinv.p, tol, c->colsx.p, c->xoff.p, c->mat_off_z.p, c->xoff_z.p, c->vals_z.p,
                                                     c->cdelta_z.p, c->colsx_z.p);
   PTB_CUDA(cudaGetLastError());
   c->launches += 4;

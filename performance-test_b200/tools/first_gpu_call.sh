@@ -8,7 +8,7 @@ out=gpurun_out/first_call
 mkdir -p "$out"
 export PTB_TEST_OPTIN=1
 echo "== opt-in parity tests"
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
+timeout 300 python -m pytest tests/test_gpu_parity.py -q -s -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
 echo "== assembly A/B (4M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
 echo "== ncu --set full of the direct-gather kernels (Poisson 4M): read it with tools/ncu_summary.py"
@@ -19,10 +19,11 @@ WALK_CHECK_OUT=first_call/matrix_free_4M.json timeout 200 python performance-tes
 echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
 echo "== SpMV on the zero-compacted operator (Poisson 20M: the headline line), off / on"
-for z in 0 1; do
-  PTB_SPMV_COMPACT=$z timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
-    > "$out/bench_poisson20M_compact${z}.json" 2> "$out/bench_poisson20M_compact${z}.err"
-  python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], 'value %.4g' % d['value'], d['stage_ms'], d['roofline']['ms_per_launch'])" "$out/bench_poisson20M_compact${z}.json" || echo FAILED
+for z in "0 0" "1 0" "1 1e-14"; do
+  set -- $z
+  PTB_SPMV_COMPACT=$1 PTB_SPMV_COMPACT_TOL=$2 timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
+    > "$out/bench_poisson20M_compact$1_tol$2.json" 2> "$out/bench_poisson20M_compact$1_tol$2.err"
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); r=d['roofline']; print(sys.argv[1], 'value %.4g' % d['value'], d['stage_ms'], 'spmv ms', r['ms_per_launch'], 'stored/pattern', r['spmv_stored_entries'], r['pattern_entries'])" "$out/bench_poisson20M_compact$1_tol$2.json" || echo FAILED
 done
 echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"
 for persistent in 0 1; do

@@ -74,25 +74,27 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 extern "C" {
 
 // stage 1: counts + both scans (the caller sizes the compacted arrays from mat_off_z[S], xoff_z[S])
-int emu_compact_offsets(int32_t n_slices, const int64_t* mat_off, const double* vals,
-                        const int32_t* cdelta, int64_t* cnt_w, int64_t* cnt_x, int64_t* mat_off_z,
-                        int64_t* xoff_z)
+int emu_compact_offsets(int32_t n_rows, int32_t n_slices, const int64_t* mat_off, const double* vals,
+                        const int32_t* cdelta, const double* dinv, double tol, int64_t* cnt_w,
+                        int64_t* cnt_x, int64_t* mat_off_z, int64_t* xoff_z)
 {
   using namespace ptb;
-  emu_launch(compact_count, (n_slices + 7) / 8, CP_THREADS, n_slices, mat_off, vals, cdelta, cnt_w, cnt_x);
+  emu_launch(compact_count, (n_slices + 7) / 8, CP_THREADS, n_rows, n_slices, mat_off, vals, cdelta, dinv,
+             tol, cnt_w, cnt_x);
   emu_launch(scan_exclusive, 1, 1024, static_cast<std::int64_t>(n_slices), (const std::int64_t*)cnt_w, mat_off_z);
   emu_launch(scan_exclusive, 1, 1024, static_cast<std::int64_t>(n_slices), (const std::int64_t*)cnt_x, xoff_z);
   return 0;
 }
 
-int emu_compact_copy(int32_t n_slices, const int64_t* mat_off, const double* vals,
-                     const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
+int emu_compact_copy(int32_t n_rows, int32_t n_slices, const int64_t* mat_off, const double* vals,
+                     const int32_t* cdelta, const double* dinv, double tol, const int32_t* colsx,
+                     const int64_t* xoff,
                      const int64_t* mat_off_z, const int64_t* xoff_z, double* vals_z,
                      int32_t* cdelta_z, int32_t* colsx_z)
 {
   using namespace ptb;
-  emu_launch(compact_copy, (n_slices + 7) / 8, CP_THREADS, n_slices, mat_off, vals, cdelta, colsx, xoff,
-             mat_off_z, xoff_z, vals_z, cdelta_z, colsx_z);
+  emu_launch(compact_copy, (n_slices + 7) / 8, CP_THREADS, n_rows, n_slices, mat_off, vals, cdelta, dinv, tol,
+             colsx, xoff, mat_off_z, xoff_z, vals_z, cdelta_z, colsx_z);
   return 0;
 }
 }

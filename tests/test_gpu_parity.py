@@ -471,3 +471,28 @@ def test_opt_in_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, 
     assert out["0"][1][0] == out["1"][1][0]
     assert np.array_equal(out["0"][2], out["1"][2])
     _check_matrix(P, out["1"][2], oracle.assemble_matrix(P))
+
+
+@OPTIN
+@pytest.mark.parametrize("tol", ["0", "1e-14"])
+def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol):
+    """How many SELL positions survive on the lattice, with exact zeros only (tol 0) and with the
+    rounding residue of analytic zeros counted as zero (tol 1e-14 of the row's diagonal). With
+    fused multiply-adds the first number may be close to 1."""
+    P = pt.host.Problem("poisson", 1, 40, 38, 41)
+    p = np.random.default_rng(9).standard_normal(P.n_owned + P.n_ghost)
+    monkeypatch.setenv("PTB_SPMV_COMPACT", "0")
+    c = pt.abi.Context(0)
+    c.set_problem(P)
+    c.assemble_matrix()
+    y_full, full = c.apply_operator(p), c.spmv_stored_entries()
+    monkeypatch.setenv("PTB_SPMV_COMPACT", "1")
+    monkeypatch.setenv("PTB_SPMV_COMPACT_TOL", tol)
+    c.assemble_matrix()
+    y, kept = c.apply_operator(p), c.spmv_stored_entries()
+    c.close()
+    print(f"compaction tol={tol}: {kept} of {full} stored entries ({kept / full:.3f})")
+    assert kept <= full
+    assert np.abs(y - y_full).max() <= (0 if tol == "0" else 1e-13) * np.abs(y_full).max()
+    if tol != "0":
+        assert kept < 0.6 * full
