@@ -129,6 +129,13 @@ int ptb_build_cell_slot_map(int64_t n_cells, int nd, const int32_t* dofmap, int3
  * cell*nd+local index, ascending) and in-row offsets [n_pairs*nd]. Pass NULL to query sizes. */
 int ptb_get_slot_offsets(ptb_ctx* ctx, int64_t* n_pairs, int64_t* pair_ptr, uint32_t* pairs,
                          uint16_t* offsets);
+/* The P1 assembly maps as they sit on the device, downloaded (needs the GPU): adj_off
+ * [n_slices + 1], the rotated slot words and the star-walk words [adj_off[n_slices]] (layout:
+ * DESIGN.md section 3). Built on the host by default, by the setup kernels with PTB_GPU_SETUP=1
+ * (*built_on_device reports which); tests compare them with ptb_debug_p1_layout bit for bit.
+ * adjrot / walk may be NULL; *have_walk = 0 when the context holds no walk. */
+int ptb_get_p1_maps(ptb_ctx* ctx, int64_t* adj_off, uint32_t* adjrot, uint32_t* walk,
+                    int* have_walk, int* built_on_device);
 
 /* Round trip of the device matrix layout on the host (no GPU): builds the SELL-32 layout and the
  * compressed column indices from a CSR pattern, decodes them again into cols_out (CSR order) and

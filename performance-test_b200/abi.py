@@ -70,6 +70,7 @@ def lib():
         L.ptb_build_cell_slot_map.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp]
         L.ptb_debug_layout_roundtrip.argtypes = [i32, i64, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
+        L.ptb_get_p1_maps.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
         L.ptb_debug_facet_rows.argtypes = [i64, vp, vp, vp, C.c_int, C.c_int, i32, C.POINTER(i32),
@@ -390,6 +391,19 @@ class Context:
         self._check(lib().ptb_get_slot_offsets(self._h, C.byref(n), _ptr(ptr), _ptr(pairs),
                                                _ptr(off)))
         return ptr, pairs, off
+
+    def p1_maps(self):
+        """The P1 assembly maps downloaded from the device: dict(adj_off, adjrot, walk | None,
+        built_on_device)."""
+        ns = (self.n_owned + 31) // 32
+        adj_off = np.empty(ns + 1, dtype=np.int64)
+        hw, dev = C.c_int(), C.c_int()
+        self._check(lib().ptb_get_p1_maps(self._h, _ptr(adj_off), None, None, C.byref(hw), C.byref(dev)))
+        adjrot = np.empty(int(adj_off[-1]), dtype=np.uint32)
+        walk = np.empty(int(adj_off[-1]), dtype=np.uint32) if hw.value else None
+        self._check(lib().ptb_get_p1_maps(self._h, _ptr(adj_off), _ptr(adjrot), _ptr(walk), C.byref(hw),
+                                          C.byref(dev)))
+        return {"adj_off": adj_off, "adjrot": adjrot, "walk": walk, "built_on_device": bool(dev.value)}
 
     # ---- instrumentation -------------------------------------------------------------------
     def stage_ms(self, stage):

@@ -18,6 +18,7 @@ bool walk_enabled() { return env_flag("PTB_ASM_WALK", true); }
 // Written after the round's GPU budget was spent, never run -> opt-in.
 bool walk3_enabled() { return env_flag("PTB_ASM_WALK3", false); }
 bool gwalk_enabled() { return env_flag("PTB_ASM_GWALK", false); }
+bool gpu_setup_enabled() { return env_flag("PTB_GPU_SETUP", false); }
 thread_local std::string g_err;
 
 template <typename F>
@@ -277,18 +278,32 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     const std::int32_t N = c->n_owned;
     c->nnz = rowptr[N];
     const std::vector<std::int32_t>& dm = c->h_dofmap;
-    build_row_adjacency(dm.data(), c->n_cells, c->nd, N, c->h_adj);
-    const std::int64_t max_so
-        = build_slot_offsets(dm.data(), c->nd, N, c->h_adj, rowptr, cols, c->h_so);
-    need(max_so >= 0, "ptb_set_pattern: a cell's (row, col) pair is missing from the pattern");
     SellLayout L;
-    build_sell_layout(N, c->nd, rowptr, cols, c->h_adj, c->h_so, max_so, L);
-    c->n_slices = L.n_slices, c->max_w = L.max_w, c->max_wa = L.max_wa;
-    c->so_bits = L.so_bits, c->so_words = L.so_words;
+    // The adjacency side (cell lists, slot words, star walk) comes from the host build below or,
+    // opt-in for P1, from the device (setup.cu); the column side is always laid out here.
+    bool dev_maps = gpu_setup_enabled() && c->nd == 4 && !gwalk_enabled();
+    auto host_layout = [&](bool with_adjacency) {
+      std::int64_t max_so = 0;
+      if (with_adjacency)
+      {
+        build_row_adjacency(dm.data(), c->n_cells, c->nd, N, c->h_adj);
+        max_so = build_slot_offsets(dm.data(), c->nd, N, c->h_adj, rowptr, cols, c->h_so);
+        need(max_so >= 0, "ptb_set_pattern: a cell's (row, col) pair is missing from the pattern");
+      }
+      else
+      {
+        c->h_adj.ptr.assign(static_cast<std::size_t>(N) + 1, 0);
+        c->h_adj.pairs.clear(), c->h_so.clear();
+      }
+      L = SellLayout();
+      build_sell_layout(N, c->nd, rowptr, cols, c->h_adj, c->h_so, max_so, L);
+      c->n_slices = L.n_slices, c->max_w = L.max_w, c->max_wa = L.max_wa;
+      c->so_bits = L.so_bits, c->so_words = L.so_words;
+    };
+    host_layout(!dev_maps);
     c->h_rowptr.assign(rowptr, rowptr + N + 1);
     c->rowptr.upload(c->h_rowptr, c->stream);
     c->mat_off.upload(L.mat_off, c->stream);
-    c->adj_off.upload(L.adj_off, c->stream);
     c->cols.upload(L.cols, c->stream);
     if (c->bs == 1)
     {
@@ -299,25 +314,54 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       c->cols_explicit_frac
           = L.cols.empty() ? 0.0 : static_cast<double>(L.colsx.size()) / L.cols.size();
     }
-    if (!L.adjrot.empty())
-    {
-      // P1: the rotated one-word slot map is all the kernels need
-      c->adjrot.upload(L.adjrot, c->stream);
-      c->adj.release(), c->adjso.release();
-    }
-    else
-    {
-      c->adjrot.release();
-      c->adj.upload(L.adj, c->stream);
-      c->adjso.upload(L.adjso, c->stream);
-    }
+    const auto want_walk = [&] {
+      return (c->bs == 1 && walk_enabled() && L.max_w <= 32) || (c->bs == 3 && walk3_enabled());
+    };
     c->walk.release();
-    if (!L.adjrot.empty() && ((c->bs == 1 && walk_enabled() && L.max_w <= 32) || (c->bs == 3 && walk3_enabled())))
+    c->walk_loads_per_step = 0.0;
+    c->maps_on_device = false;
+    if (dev_maps)
     {
-      // opt-in: star-walk assembly kernels (assemble_walk.cu)
-      const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);
-      c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
-      c->walk.upload(L.walk, c->stream);
+      // opt-in (PTB_GPU_SETUP=1): adj_off, the rotated slot words and the walk are built by the
+      // setup kernels from the uploaded dofmap and columns. A pattern the device build cannot
+      // express (missing pair, offsets beyond a byte, a star of more than 64 cells) falls back to
+      // the host build, which also owns the error messages.
+      int max_wa = 0;
+      if (L.max_w < 255 && gpu_setup_p1(c, want_walk(), &max_wa))
+      {
+        c->max_wa = max_wa;
+        c->adj.release(), c->adjso.release();
+        c->maps_on_device = true;
+      }
+      else
+      {
+        c->walk.release();
+        dev_maps = false;
+        host_layout(true);
+      }
+    }
+    if (!dev_maps)
+    {
+      c->adj_off.upload(L.adj_off, c->stream);
+      if (!L.adjrot.empty())
+      {
+        // P1: the rotated one-word slot map is all the kernels need
+        c->adjrot.upload(L.adjrot, c->stream);
+        c->adj.release(), c->adjso.release();
+      }
+      else
+      {
+        c->adjrot.release();
+        c->adj.upload(L.adj, c->stream);
+        c->adjso.upload(L.adjso, c->stream);
+      }
+      if (!L.adjrot.empty() && want_walk())
+      {
+        // star-walk assembly kernels (assemble_walk.cu)
+        const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);
+        c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
+        c->walk.upload(L.walk, c->stream);
+      }
     }
     c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
     if (c->order > 1)
@@ -967,6 +1011,8 @@ int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32
 {
   return guarded(c, [&] {
     need(c->have_pattern, "ptb_get_slot_offsets: pattern not set");
+    need(!c->maps_on_device, "ptb_get_slot_offsets: the maps were built on the device (PTB_GPU_SETUP=1); "
+                             "use ptb_get_p1_maps");
     need(!c->h_adj.pairs.empty() || c->h_adj.ptr.back() == 0,
          "ptb_get_slot_offsets: the host copy is not retained above 2^28 pairs");
     if (n_pairs)
@@ -977,6 +1023,26 @@ int ptb_get_slot_offsets(ptb_ctx* c, int64_t* n_pairs, int64_t* pair_ptr, uint32
       std::copy(c->h_adj.pairs.begin(), c->h_adj.pairs.end(), pairs);
     if (offsets)
       std::copy(c->h_so.begin(), c->h_so.end(), offsets);
+  });
+}
+
+int ptb_get_p1_maps(ptb_ctx* c, int64_t* adj_off, uint32_t* adjrot, uint32_t* walk, int* have_walk,
+                    int* built_on_device)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_pattern && c->adjrot.p != nullptr, "ptb_get_p1_maps: no P1 pattern set");
+    need(adj_off != nullptr, "ptb_get_p1_maps: NULL adj_off");
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    PTB_CUDA(cudaMemcpy(adj_off, c->adj_off.p, c->adj_off.bytes(), cudaMemcpyDeviceToHost));
+    if (adjrot)
+      PTB_CUDA(cudaMemcpy(adjrot, c->adjrot.p, c->adjrot.bytes(), cudaMemcpyDeviceToHost));
+    if (walk && c->walk.p)
+      PTB_CUDA(cudaMemcpy(walk, c->walk.p, c->walk.bytes(), cudaMemcpyDeviceToHost));
+    if (have_walk)
+      *have_walk = c->walk.p != nullptr;
+    if (built_on_device)
+      *built_on_device = c->maps_on_device;
   });
 }
 

@@ -91,6 +91,11 @@ inline SpmvArgs spmv_args(const ptb_ctx* c)
 /// Build the zero-column-compacted copy of the assembled scalar operator (no-op for bs = 3).
 void compact_operator(ptb_ctx* c);
 
+/// Device-side construction of the P1 assembly maps (setup.cu, opt-in PTB_GPU_SETUP=1): fills
+/// c->adj_off, c->adjrot and, if want_walk, c->walk from the uploaded dofmap, rowptr, mat_off and
+/// padded columns. Returns false when the pattern cannot be expressed (the caller builds on the host).
+bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
+
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 /// Star-walk variant (assemble_walk.cu); returns false when it does not apply (no walk uploaded,

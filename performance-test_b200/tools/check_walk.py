@@ -130,6 +130,30 @@ def abmf(ndofs):
         c.close()
 
 
+def absetup(ndofs):
+    """ptb_set_* wall time with the P1 assembly maps built on the host and on the device
+    (PTB_GPU_SETUP=1, csrc/setup.cu); the assembled matrices must be identical."""
+    nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
+    f = 2 ** r
+    P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
+    res["setup_case"] = {"n_owned": P.n_owned, "nnz": P.nnz}
+    sums = {}
+    for dev in ("0", "1", "0", "1"):
+        os.environ["PTB_GPU_SETUP"] = dev
+        c = pt.abi.Context(0)
+        t0 = time.perf_counter()
+        c.set_problem(P)
+        res[f"set_problem_s_gpu_setup{dev}"] = min(res.get(f"set_problem_s_gpu_setup{dev}", 1e9),
+                                                  time.perf_counter() - t0)
+        res[f"built_on_device_gpu_setup{dev}"] = c.p1_maps()["built_on_device"]
+        c.assemble_matrix()
+        sums[dev] = float(np.abs(c.matrix_values()).sum())
+        c.close()
+        dump()
+    res["setup_checksums_equal"] = sums["0"] == sums["1"]
+    dump()
+
+
 def ncu_target(ndofs):
     nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
     f = 2 ** r
@@ -158,6 +182,8 @@ def main():
         return ab2(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "abmf":
         return abmf(int(sys.argv[2]))
+    if len(sys.argv) > 2 and sys.argv[1] == "absetup":
+        return absetup(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "abpk":
         return abpk(int(sys.argv[2]))
     if len(sys.argv) > 2 and sys.argv[1] == "ncu":

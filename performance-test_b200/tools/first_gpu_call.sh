@@ -18,6 +18,8 @@ echo "== matrix-free CG (cgpoisson action), staged star vs direct-gather walk (4
 WALK_CHECK_OUT=first_call/matrix_free_4M.json timeout 200 python performance-test_b200/tools/check_walk.py abmf 4000000 2>&1 | tail -2
 echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
+echo "== P1 assembly maps built on the host vs on the device (PTB_GPU_SETUP, 4M DOFs)"
+WALK_CHECK_OUT=first_call/setup_4M.json timeout 200 python performance-test_b200/tools/check_walk.py absetup 4000000 2>&1 | tail -2
 echo "== SpMV on the zero-compacted operator (Poisson 20M: the headline line), off / on"
 for z in "0 0" "1 0" "1 1e-14"; do
   set -- $z

@@ -1,0 +1,103 @@
+// TEST INFRASTRUCTURE -- runs the source of the device-side P1 setup kernels (csrc/setup.cu) on the
+// host. Nothing here is linked into the product libraries; the product path never sees PTB_HOST_EMU.
+#define PTB_HOST_EMU 1
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+#ifndef __launch_bounds__
+#define __launch_bounds__(...)
+#endif
+
+struct EmuIdx
+{
+  unsigned x = 0, y = 0, z = 0;
+};
+static thread_local EmuIdx threadIdx, blockIdx;
+static EmuIdx blockDim, gridDim;
+static std::barrier<>* emu_barrier = nullptr;
+static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
+// the threads of a CTA run concurrently here, so the atomics are real ones
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v)
+{
+  return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
+}
+using std::max;
+using std::min;
+
+// the fixture passes a copy of csrc/setup.cu in which `__shared__` reads `static` (one CTA at a time)
+#include PTB_EMU_SETUP_SOURCE
+
+namespace
+{
+template <typename K, typename... Args>
+void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
+{
+  gridDim.x = grid, blockDim.x = block;
+  for (unsigned b = 0; b < grid; ++b)
+  {
+    std::barrier<> bar(block);
+    emu_barrier = &bar;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < block; ++t)
+      th.emplace_back([=] {
+        threadIdx.x = t, blockIdx.x = b;
+        kernel(args...);
+        emu_barrier->arrive_and_drop();
+      });
+    for (auto& x : th)
+      x.join();
+  }
+}
+} // namespace
+
+extern "C" {
+
+// The launch sequence of gpu_setup_p1 (setup.cu) with host vectors in place of the device buffers.
+// adj_off [n_slices + 1] is always written; adjrot / walk hold `cap` words each and are written
+// when the device-side total fits (returns -1 otherwise). flags[0..1] as in setup.cu.
+// shuffle != 0 reverses the pairs of every row before the per-row sort: the order in which the
+// atomics of setup_fill land is arbitrary on a GPU, the result must not depend on it.
+int emu_setup_p1(int64_t n_cells, const int32_t* dofmap, int32_t n_rows, int32_t n_slices,
+                 const int64_t* rowptr, const int64_t* mat_off, const int32_t* cols_sell, int shuffle,
+                 int64_t cap, int64_t* adj_off, uint32_t* adjrot, uint32_t* walk, int* flags)
+{
+  using namespace ptb;
+  const std::int64_t n_entries = n_cells * 4;
+  const unsigned ge = static_cast<unsigned>((n_entries + SU_THREADS - 1) / SU_THREADS);
+  std::vector<unsigned long long> cnt(static_cast<std::size_t>(n_rows), 0), wa(static_cast<std::size_t>(n_slices), 0);
+  std::vector<std::int64_t> ptr(static_cast<std::size_t>(n_rows) + 1, -1);
+  emu_launch(setup_count, ge, SU_THREADS, n_entries, dofmap, n_rows, cnt.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(),
+             ptr.data(), static_cast<std::int64_t>(1));
+  std::vector<std::uint32_t> pairs(static_cast<std::size_t>(ptr[n_rows]), 0xFFFFFFFFu);
+  std::fill(cnt.begin(), cnt.end(), 0ull);
+  emu_launch(setup_fill, ge, SU_THREADS, n_entries, dofmap, n_rows, (const std::int64_t*)ptr.data(), cnt.data(),
+             pairs.data());
+  if (shuffle)
+    for (std::int32_t r = 0; r < n_rows; ++r)
+      std::reverse(pairs.begin() + ptr[r], pairs.begin() + ptr[r + 1]);
+  emu_launch(setup_sort, (n_rows + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, (const std::int64_t*)ptr.data(),
+             pairs.data());
+  emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
+             (const std::int64_t*)ptr.data(), wa.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off,
+             static_cast<std::int64_t>(32));
+  if (adj_off[n_slices] > cap)
+    return -1;
+  flags[0] = flags[1] = 0;
+  const unsigned gl = static_cast<unsigned>((static_cast<std::int64_t>(n_slices) * 32 + SU_THREADS - 1) / SU_THREADS);
+  emu_launch(setup_adjrot, gl, SU_THREADS, n_rows, n_slices, dofmap, rowptr, mat_off, cols_sell,
+             (const std::int64_t*)ptr.data(), (const std::uint32_t*)pairs.data(), (const std::int64_t*)adj_off, adjrot,
+             flags);
+  emu_launch(setup_walk, gl, SU_THREADS, n_rows, n_slices, (const std::int64_t*)ptr.data(),
+             (const std::int64_t*)adj_off, (const std::uint32_t*)adjrot, walk, flags);
+  return 0;
+}
+}

@@ -496,3 +496,32 @@ def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol
     assert np.abs(y - y_full).max() <= (0 if tol == "0" else 1e-13) * np.abs(y_full).max()
     if tol != "0":
         assert kept < 0.6 * full
+
+
+@OPTIN
+@pytest.mark.parametrize("ptype,dims", [("poisson", (5, 4, 6)), ("poisson", (1, 1, 1)), ("poisson", (33, 2, 1)),
+                                        ("poisson", (40, 38, 41)), ("elasticity", (12, 11, 13))])
+def test_opt_in_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype, dims):
+    """PTB_GPU_SETUP=1: adj_off, the rotated slot words and the star walk built by the setup kernels
+    (csrc/setup.cu) equal the host build word for word, and assembly through them matches the oracle."""
+    P = pt.host.Problem(ptype, 1, *dims)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    monkeypatch.setenv("PTB_GPU_SETUP", "1")
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P)
+        M = c.p1_maps()
+        assert M["built_on_device"]
+        assert np.array_equal(M["adj_off"], L["adj_off"])
+        assert np.array_equal(M["adjrot"], L["adjrot"])
+        if M["walk"] is not None:
+            assert np.array_equal(M["walk"], L["walk"])
+        else:
+            assert ptype == "elasticity"      # its walk kernel is a separate opt-in (PTB_ASM_WALK3)
+        c.assemble_matrix()
+        c.assemble_vector()
+        _check_matrix(P, c.matrix_values(), oracle.assemble_matrix(P))
+        b_ref = oracle.assemble_vector(P)
+        assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    finally:
+        c.close()

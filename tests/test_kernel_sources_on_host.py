@@ -575,3 +575,71 @@ def test_operator_compaction_source_keeps_the_operator(pt, oracle, emucp, pertur
         assert kept > 0.9                              # a general mesh has (almost) no exact zeros
     else:
         assert kept < 0.75                             # the lattice operator is the 7-point stencil
+
+
+# ---- device-side construction of the P1 assembly maps (csrc/setup.cu) -------------------------------
+
+SU_SRC = os.path.join(HERE, "emu", "emu_setup.cpp")
+
+
+@pytest.fixture(scope="module")
+def emusu():
+    out = os.path.join(HERE, "emu", "_build", "libemusetup.so")
+    deps = [SU_SRC] + [os.path.join(CSRC, f) for f in ("setup.cu", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        text = open(os.path.join(CSRC, "setup.cu")).read().replace("__shared__", "static")
+        copy = os.path.join(os.path.dirname(out), "setup_emu.cu")
+        with open(copy, "w") as f:
+            f.write(text)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+                        "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_SETUP_SOURCE="{copy}"', "-o", out, SU_SRC],
+                       check=True)
+    return C.CDLL(out)
+
+
+@pytest.mark.parametrize("shuffle", [0, 1])
+@pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1),
+                                                    ("poisson", (33, 2, 1), 0, 1), ("poisson", (4, 3, 5), 1, 2),
+                                                    ("poisson", (3, 3, 7), 2, 3), ("elasticity", (3, 4, 3), 0, 1),
+                                                    ("elasticity", (2, 2, 5), 1, 2)])
+def test_device_setup_source_builds_the_host_maps_bit_for_bit(pt, emusu, ptype, dims, rank, nranks, shuffle):
+    """adj_off, the rotated slot words and the star walk built by the setup kernels equal the host
+    build (common/intmaps.cpp + layout.cpp) word for word, whatever order the fill atomics land in."""
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    S, cap = L["n_slices"], int(L["adj_off"][-1])
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rp = np.ascontiguousarray(P["rowptr"], np.int64)
+    adj_off = np.full(S + 1, -1, np.int64)
+    adjrot = np.full(cap, 0xDEADBEEF, np.uint32)
+    walk = np.full(cap, 0xDEADBEEF, np.uint32)
+    flags = np.full(2, -1, np.int32)
+    rc = emusu.emu_setup_p1(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]),
+                            _p(L["cols"]), shuffle, C.c_int64(cap), _p(adj_off), _p(adjrot), _p(walk), _p(flags))
+    assert rc == 0
+    assert np.array_equal(adj_off, L["adj_off"])
+    assert flags.tolist() == [0, 0]
+    assert np.array_equal(adjrot, L["adjrot"])
+    assert np.array_equal(walk, L["walk"])
+
+
+def test_device_setup_source_flags_a_pattern_that_misses_a_cell_pair(pt, emusu):
+    """A (row, column) pair of a cell that is absent from the caller's pattern must raise flag 0
+    (the host build refuses the pattern: ptb_set_pattern 'pair is missing')."""
+    P = pt.host.Problem("poisson", 1, 3, 3, 3)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    S, cap = L["n_slices"], int(L["adj_off"][-1])
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rp = np.ascontiguousarray(P["rowptr"], np.int64)
+    cols = L["cols"].copy()
+    r = 20                                   # an interior-ish row: replace one real neighbour column
+    mo, k = int(L["mat_off"][r >> 5]), int(rp[r + 1] - rp[r]) - 1
+    assert cols[mo + k * 32 + (r & 31)] != r
+    cols[mo + k * 32 + (r & 31)] = P.n_owned + P.n_ghost + 5
+    adj_off, flags = np.zeros(S + 1, np.int64), np.zeros(2, np.int32)
+    adjrot, walk = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32)
+    assert emusu.emu_setup_p1(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]), _p(cols),
+                              0, C.c_int64(cap), _p(adj_off), _p(adjrot), _p(walk), _p(flags)) == 0
+    assert flags[0] == 1
