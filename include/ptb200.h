@@ -60,6 +60,14 @@ int ptb_set_space(ptb_ctx* ctx, int problem, int order, int bs, int32_t n_owned,
 /* Sparsity pattern of the owned rows (fem::create_sparsity_pattern / create_matrix,
  * poisson_problem.cpp:122-123). Builds the cell -> CSR-slot map and the device layout. */
 int ptb_set_pattern(ptb_ctx* ctx, const int64_t* rowptr, const int32_t* cols);
+/* The same pattern built on the device from the dofmap of ptb_set_space instead of being passed in
+ * (fem::create_sparsity_pattern + create_matrix, poisson_problem.cpp:122-123, which the reference
+ * times inside "ZZZ Assemble matrix"): per owned row the ascending union of the dofs of its cells.
+ * Equivalent to ptb_set_pattern with that pattern; *nnz receives rowptr[n_owned]. The caller reads
+ * the CSR arrays back with ptb_get_pattern to create its own Mat (rowptr [n_owned + 1], cols [nnz];
+ * either may be NULL). */
+int ptb_build_pattern(ptb_ctx* ctx, int64_t* nnz);
+int ptb_get_pattern(ptb_ctx* ctx, int64_t* rowptr, int32_t* cols);
 /* bc->dof_indices(): constrained block dofs (owned and ghost); all bs components constrained,
  * boundary value 0 (u0 = 0, poisson_problem.cpp:53-54). */
 int ptb_set_bc(ptb_ctx* ctx, int32_t n_bc, const int32_t* bc_dofs);

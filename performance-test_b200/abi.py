@@ -47,6 +47,8 @@ def lib():
         L.ptb_update_geometry.argtypes = [vp, vp]
         L.ptb_set_space.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32, i32, vp]
         L.ptb_set_pattern.argtypes = [vp, vp, vp]
+        L.ptb_build_pattern.argtypes = [vp, C.POINTER(i64)]
+        L.ptb_get_pattern.argtypes = [vp, vp, vp]
         L.ptb_set_bc.argtypes = [vp, i32, vp]
         L.ptb_set_exterior_facets.argtypes = [vp, i64, vp, vp]
         L.ptb_set_source.argtypes = [vp, vp, vp]
@@ -276,8 +278,10 @@ class Context:
             pass
 
     # ---- setup ---------------------------------------------------------------------------
-    def set_problem(self, P, source=True):
-        """Upload everything a host problem (host.Problem or the oracle's RefProblem) holds."""
+    def set_problem(self, P, source=True, build_pattern=False):
+        """Upload everything a host problem (host.Problem or the oracle's RefProblem) holds. With
+        build_pattern the sparsity pattern is built on the device from the dofmap
+        (ptb_build_pattern) instead of being uploaded."""
         self.P = P
         self.bs, self.nd = P.bs, P.nd
         self.n_owned, self.n_ghost, self.nnz = P.n_owned, P.n_ghost, P.nnz
@@ -286,8 +290,13 @@ class Context:
         dm = _a(P["dofmap"], np.int32)
         self._check(lib().ptb_set_space(self._h, PROBLEMS[P.problem_type], P.order, P.bs,
                                         P.n_owned, P.n_ghost, _ptr(dm)))
-        rp, cl = _a(P["rowptr"], np.int64), _a(P["cols"], np.int32)
-        self._check(lib().ptb_set_pattern(self._h, _ptr(rp), _ptr(cl)))
+        if build_pattern:
+            nnz = C.c_int64()
+            self._check(lib().ptb_build_pattern(self._h, C.byref(nnz)))
+            self.nnz = nnz.value
+        else:
+            rp, cl = _a(P["rowptr"], np.int64), _a(P["cols"], np.int32)
+            self._check(lib().ptb_set_pattern(self._h, _ptr(rp), _ptr(cl)))
         bc = _a(P["bc_dofs"], np.int32)
         self._check(lib().ptb_set_bc(self._h, len(bc), _ptr(bc)))
         fc, fl = _a(P["facet_cells"], np.int32), _a(P["facet_local"], np.int32)
@@ -391,6 +400,14 @@ class Context:
         self._check(lib().ptb_get_slot_offsets(self._h, C.byref(n), _ptr(ptr), _ptr(pairs),
                                                _ptr(off)))
         return ptr, pairs, off
+
+    def pattern(self):
+        """(rowptr, cols) of a pattern built by ptb_build_pattern."""
+        rp = np.empty(self.n_owned + 1, dtype=np.int64)
+        self._check(lib().ptb_get_pattern(self._h, _ptr(rp), None))
+        cl = np.empty(int(rp[-1]), dtype=np.int32)
+        self._check(lib().ptb_get_pattern(self._h, _ptr(rp), _ptr(cl)))
+        return rp, cl
 
     def p1_maps(self):
         """The P1 assembly maps downloaded from the device: dict(adj_off, adjrot, walk | None,

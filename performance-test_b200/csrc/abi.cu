@@ -401,6 +401,45 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     c->have_pattern = true;
     c->matrix_assembled = false;
     c->have_compact = false;
+    std::vector<std::int32_t>().swap(c->h_cols); // ptb_build_pattern keeps its own copy after this call
+  });
+}
+
+int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
+{
+  std::vector<std::int64_t> rowptr;
+  std::vector<std::int32_t> cols;
+  const int rc = guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_build_pattern: call ptb_set_space first");
+    if (!gpu_build_pattern(c, rowptr, cols))
+    {
+      // a row beyond the device kernels' capacity: same pattern from the host builder
+      RowAdjacency adj;
+      build_row_adjacency(c->h_dofmap.data(), c->n_cells, c->nd, c->n_owned, adj);
+      build_pattern(c->h_dofmap.data(), c->nd, c->n_owned, adj, rowptr, cols);
+    }
+  });
+  if (rc != 0)
+    return rc;
+  const int rc2 = ptb_set_pattern(c, rowptr.data(), cols.data());
+  if (rc2 != 0)
+    return rc2;
+  c->h_cols.swap(cols);
+  if (nnz)
+    *nnz = c->nnz;
+  return 0;
+}
+
+int ptb_get_pattern(ptb_ctx* c, int64_t* rowptr, int32_t* cols)
+{
+  return guarded(c, [&] {
+    need(c->have_pattern && c->h_cols.size() == static_cast<std::size_t>(c->nnz),
+         "ptb_get_pattern: the pattern was not built by ptb_build_pattern");
+    if (rowptr)
+      std::copy(c->h_rowptr.begin(), c->h_rowptr.end(), rowptr);
+    if (cols)
+      std::copy(c->h_cols.begin(), c->h_cols.end(), cols);
   });
 }
 

@@ -139,6 +139,7 @@ struct ptb_ctx
   ptb::DevBuf<std::uint32_t> adj, adjso, adjrot;
   ptb::DevBuf<std::uint32_t> walk;     // P1 star walk (layout.h), uploaded when PTB_ASM_WALK=1
   double walk_loads_per_step = 0.0;
+  std::vector<std::int32_t> h_cols;    // CSR columns, kept only when ptb_build_pattern built them
   bool maps_on_device = false;         // adj_off / adjrot / walk built by setup.cu (PTB_GPU_SETUP=1)
   ptb::DevBuf<std::uint32_t> walk1;    // one-vertex-per-step walk (layout.h), PTB_ASM_GWALK=1
   ptb::DevBuf<std::int64_t> walk1_off;

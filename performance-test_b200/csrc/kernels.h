@@ -1,5 +1,6 @@
 // Kernel argument blocks and launchers shared by the .cu files.
 #pragma once
+#include <vector>
 // PTB_HOST_EMU exists for tests/emu only (the g++ harness that executes kernel *sources* on the
 // host to check their indexing). It must never reach a device build: there is no CPU path in the
 // product, and a library built with it would be one.
@@ -95,6 +96,9 @@ void compact_operator(ptb_ctx* c);
 /// c->adj_off, c->adjrot and, if want_walk, c->walk from the uploaded dofmap, rowptr, mat_off and
 /// padded columns. Returns false when the pattern cannot be expressed (the caller builds on the host).
 bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
+/// The sparsity pattern of the owned rows built on the device from the uploaded dofmap (setup.cu) and
+/// downloaded; false when a row is too long for the device build.
+bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols);
 
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);

@@ -10,6 +10,10 @@
 //   rotated words                per (row, cell): binary search of the cell's four vertices in the
 //                                row's column list, packed with the owner first (adjrot)
 //   walk                         the greedy star walk of layout.cpp build_walk, one thread per row
+//   pattern count / scan / fill  the sparsity pattern itself (common/intmaps.cpp build_pattern; the
+//                                reference builds it in fem::create_matrix, poisson_problem.cpp:122-123,
+//                                inside the timed assembly stage): per owned row the ascending union of
+//                                the dofs of its cells, any Lagrange order (ptb_build_pattern)
 // The column side (mat_off, padded columns, column compression, slice order) stays on the host: it
 // only needs the caller's CSR pattern, no adjacency.
 // NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
@@ -172,6 +176,73 @@ __global__ void setup_adjrot(std::int32_t n_rows, std::int32_t n_slices,
   }
 }
 
+// Ascending union of the dofs of the row's cells, built by sorted insertion into a thread-local
+// list (P1 rows hold ~15 columns, P3 vertex rows 175). Returns the count, -1 when CAP is exceeded.
+constexpr int SU_MAX_COLS = 192;
+__device__ __forceinline__ int row_columns(std::int32_t r, int nd, const std::int32_t* __restrict__ dofmap,
+                                           const std::int64_t* __restrict__ ptr,
+                                           const std::uint32_t* __restrict__ pairs, std::int32_t* list)
+{
+  int n = 0;
+  for (std::int64_t q = ptr[r]; q < ptr[r + 1]; ++q)
+  {
+    const std::int64_t cell = pairs[q] / static_cast<std::uint32_t>(nd);
+    for (int j = 0; j < nd; ++j)
+    {
+      const std::int32_t col = dofmap[cell * nd + j];
+      int lo = 0, hi = n;
+      while (lo < hi)
+      {
+        const int mid = (lo + hi) >> 1;
+        if (list[mid] < col)
+          lo = mid + 1;
+        else
+          hi = mid;
+      }
+      if (lo < n && list[lo] == col)
+        continue;
+      if (n == SU_MAX_COLS)
+        return -1;
+      for (int t = n; t > lo; --t)
+        list[t] = list[t - 1];
+      list[lo] = col;
+      ++n;
+    }
+  }
+  return n;
+}
+
+// columns per row; flags[2] is set when a row has more than SU_MAX_COLS columns
+__global__ void setup_pattern_count(std::int32_t n_rows, int nd, const std::int32_t* __restrict__ dofmap,
+                                    const std::int64_t* __restrict__ ptr,
+                                    const std::uint32_t* __restrict__ pairs,
+                                    unsigned long long* __restrict__ cnt, int* __restrict__ flags)
+{
+  const std::int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows)
+    return;
+  std::int32_t list[SU_MAX_COLS];
+  const int n = row_columns(r, nd, dofmap, ptr, pairs, list);
+  if (n < 0)
+    flags[2] = 1;
+  cnt[r] = static_cast<unsigned long long>(n < 0 ? 0 : n);
+}
+
+__global__ void setup_pattern_fill(std::int32_t n_rows, int nd, const std::int32_t* __restrict__ dofmap,
+                                   const std::int64_t* __restrict__ ptr,
+                                   const std::uint32_t* __restrict__ pairs,
+                                   const std::int64_t* __restrict__ rowptr, std::int32_t* __restrict__ cols)
+{
+  const std::int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n_rows)
+    return;
+  std::int32_t list[SU_MAX_COLS];
+  const int n = row_columns(r, nd, dofmap, ptr, pairs, list);
+  std::int32_t* out = cols + rowptr[r];
+  for (int k = 0; k < n; ++k)
+    out[k] = list[k];
+}
+
 // The greedy star walk of layout.cpp build_walk: start at the row's first cell; next = the
 // unvisited cell sharing most vertices with the current one, ties to the earlier cell; vertices
 // that stay keep their register position, new ones take the freed positions in ascending order,
@@ -260,19 +331,18 @@ __global__ void setup_walk(std::int32_t n_rows, std::int32_t n_slices,
 // Builds adj_off, adjrot and (if want_walk) walk on the device from the dofmap and the already
 // uploaded column side (rowptr, mat_off, padded columns). Returns false when the device build does
 // not apply (a row with too many cells / offsets beyond a byte): the caller then uses the host build.
-bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
+namespace
 {
-  const std::int32_t N = c->n_owned, S = c->n_slices;
-  const std::int64_t n_entries = c->n_cells * 4;
-  DevBuf<unsigned long long> cnt, wa;
-  DevBuf<std::int64_t> ptr;
-  DevBuf<std::uint32_t> pairs;
-  DevBuf<int> flags;
+// dof -> (cell, local index) pairs of the owned rows, ascending per row: ptr [N + 1], pairs [ptr[N]].
+// Five launches.
+void build_pairs(ptb_ctx* c, DevBuf<std::int64_t>& ptr, DevBuf<std::uint32_t>& pairs)
+{
+  const std::int32_t N = c->n_owned;
+  const std::int64_t n_entries = c->n_cells * c->nd;
+  DevBuf<unsigned long long> cnt;
   cnt.alloc(static_cast<std::size_t>(N));
   cnt.zero(c->stream);
   ptr.alloc(static_cast<std::size_t>(N) + 1);
-  flags.alloc(2);
-  flags.zero(c->stream);
   const int ge = static_cast<int>((n_entries + SU_THREADS - 1) / SU_THREADS);
   setup_count<<<ge, SU_THREADS, 0, c->stream>>>(n_entries, c->dofmap.p, N, cnt.p);
   setup_scan<<<1, 1024, 0, c->stream>>>(N, cnt.p, ptr.p, 1);
@@ -283,6 +353,60 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
   cnt.zero(c->stream); // reused as the fill cursor
   setup_fill<<<ge, SU_THREADS, 0, c->stream>>>(n_entries, c->dofmap.p, N, ptr.p, cnt.p, pairs.p);
   setup_sort<<<(N + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, ptr.p, pairs.p);
+  PTB_CUDA(cudaGetLastError());
+  PTB_CUDA(cudaStreamSynchronize(c->stream)); // cnt dies here
+  c->launches += 5;
+}
+} // namespace
+
+// The sparsity pattern of the owned rows built on the device and downloaded (any order). Returns
+// false when a row has more than SU_MAX_COLS columns (the caller builds the pattern on the host).
+bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols)
+{
+  const std::int32_t N = c->n_owned;
+  DevBuf<std::int64_t> ptr, rp;
+  DevBuf<std::uint32_t> pairs;
+  DevBuf<unsigned long long> cnt;
+  DevBuf<std::int32_t> cl;
+  DevBuf<int> flags;
+  build_pairs(c, ptr, pairs);
+  cnt.alloc(static_cast<std::size_t>(N));
+  rp.alloc(static_cast<std::size_t>(N) + 1);
+  flags.alloc(3);
+  flags.zero(c->stream);
+  const int gr = (N + SU_THREADS - 1) / SU_THREADS;
+  setup_pattern_count<<<gr, SU_THREADS, 0, c->stream>>>(N, c->nd, c->dofmap.p, ptr.p, pairs.p, cnt.p, flags.p);
+  setup_scan<<<1, 1024, 0, c->stream>>>(N, cnt.p, rp.p, 1);
+  rowptr.resize(static_cast<std::size_t>(N) + 1);
+  int h_flags[3] = {0, 0, 0};
+  PTB_CUDA(cudaMemcpyAsync(rowptr.data(), rp.p, rowptr.size() * sizeof(std::int64_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+  PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  c->launches += 2;
+  if (h_flags[2] != 0)
+    return false;
+  cl.alloc(static_cast<std::size_t>(rowptr[N]));
+  setup_pattern_fill<<<gr, SU_THREADS, 0, c->stream>>>(N, c->nd, c->dofmap.p, ptr.p, pairs.p, rp.p, cl.p);
+  PTB_CUDA(cudaGetLastError());
+  cols.resize(static_cast<std::size_t>(rowptr[N]));
+  PTB_CUDA(cudaMemcpyAsync(cols.data(), cl.p, cols.size() * sizeof(std::int32_t), cudaMemcpyDeviceToHost,
+                           c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  c->launches += 1;
+  return true;
+}
+
+bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
+{
+  const std::int32_t N = c->n_owned, S = c->n_slices;
+  DevBuf<unsigned long long> wa;
+  DevBuf<std::int64_t> ptr;
+  DevBuf<std::uint32_t> pairs;
+  DevBuf<int> flags;
+  build_pairs(c, ptr, pairs);
+  flags.alloc(2);
+  flags.zero(c->stream);
   wa.alloc(static_cast<std::size_t>(S));
   setup_widths<<<(S + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, wa.p);
   c->adj_off.alloc(static_cast<std::size_t>(S) + 1);
@@ -309,7 +433,7 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
   int h_flags[2] = {0, 0};
   PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += want_walk ? 9 : 8;
+  c->launches += want_walk ? 4 : 3;
   return h_flags[0] == 0 && h_flags[1] == 0;
 }
 #endif // PTB_HOST_EMU

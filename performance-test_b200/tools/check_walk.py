@@ -151,6 +151,15 @@ def absetup(ndofs):
         c.close()
         dump()
     res["setup_checksums_equal"] = sums["0"] == sums["1"]
+    # the pattern itself (the reference's create_matrix step) on the device, then the maps
+    os.environ["PTB_GPU_SETUP"] = "1"
+    c = pt.abi.Context(0)
+    t0 = time.perf_counter()
+    c.set_problem(P, build_pattern=True)
+    res["set_problem_s_device_pattern_and_maps"] = time.perf_counter() - t0
+    rp, cl = c.pattern()
+    res["device_pattern_equal"] = bool(np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"]))
+    c.close()
     dump()
 
 

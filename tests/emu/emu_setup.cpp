@@ -57,7 +57,55 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 }
 } // namespace
 
+namespace
+{
+// dof -> (cell, local index) pairs as build_pairs (setup.cu) launches them
+void emu_pairs(int64_t n_entries, const int32_t* dofmap, int32_t n_rows, int shuffle, std::vector<std::int64_t>& ptr,
+               std::vector<std::uint32_t>& pairs)
+{
+  using namespace ptb;
+  const unsigned ge = static_cast<unsigned>((n_entries + SU_THREADS - 1) / SU_THREADS);
+  std::vector<unsigned long long> cnt(static_cast<std::size_t>(n_rows), 0);
+  ptr.assign(static_cast<std::size_t>(n_rows) + 1, -1);
+  emu_launch(setup_count, ge, SU_THREADS, n_entries, dofmap, n_rows, cnt.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(),
+             ptr.data(), static_cast<std::int64_t>(1));
+  pairs.assign(static_cast<std::size_t>(ptr[n_rows]), 0xFFFFFFFFu);
+  std::fill(cnt.begin(), cnt.end(), 0ull);
+  emu_launch(setup_fill, ge, SU_THREADS, n_entries, dofmap, n_rows, (const std::int64_t*)ptr.data(), cnt.data(),
+             pairs.data());
+  if (shuffle)
+    for (std::int32_t r = 0; r < n_rows; ++r)
+      std::reverse(pairs.begin() + ptr[r], pairs.begin() + ptr[r + 1]);
+  emu_launch(setup_sort, (n_rows + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, (const std::int64_t*)ptr.data(),
+             pairs.data());
+}
+} // namespace
+
 extern "C" {
+
+// The launch sequence of gpu_build_pattern (setup.cu). rowptr [n_rows + 1] is always written; cols
+// (capacity cap) when the total fits (returns -1 otherwise). flags[2] as in setup.cu.
+int emu_build_pattern(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_rows, int64_t cap, int64_t* rowptr,
+                      int32_t* cols, int* flags)
+{
+  using namespace ptb;
+  std::vector<std::int64_t> ptr;
+  std::vector<std::uint32_t> pairs;
+  emu_pairs(n_cells * nd, dofmap, n_rows, 0, ptr, pairs);
+  std::vector<unsigned long long> cnt(static_cast<std::size_t>(n_rows), 0);
+  flags[0] = flags[1] = flags[2] = 0;
+  const unsigned gr = (n_rows + SU_THREADS - 1) / SU_THREADS;
+  emu_launch(setup_pattern_count, gr, SU_THREADS, n_rows, nd, dofmap, (const std::int64_t*)ptr.data(),
+             (const std::uint32_t*)pairs.data(), cnt.data(), flags);
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(), rowptr,
+             static_cast<std::int64_t>(1));
+  if (flags[2] != 0 || rowptr[n_rows] > cap)
+    return -1;
+  emu_launch(setup_pattern_fill, gr, SU_THREADS, n_rows, nd, dofmap, (const std::int64_t*)ptr.data(),
+             (const std::uint32_t*)pairs.data(), (const std::int64_t*)rowptr, cols);
+  return 0;
+}
 
 // The launch sequence of gpu_setup_p1 (setup.cu) with host vectors in place of the device buffers.
 // adj_off [n_slices + 1] is always written; adjrot / walk hold `cap` words each and are written
@@ -69,22 +117,10 @@ int emu_setup_p1(int64_t n_cells, const int32_t* dofmap, int32_t n_rows, int32_t
                  int64_t cap, int64_t* adj_off, uint32_t* adjrot, uint32_t* walk, int* flags)
 {
   using namespace ptb;
-  const std::int64_t n_entries = n_cells * 4;
-  const unsigned ge = static_cast<unsigned>((n_entries + SU_THREADS - 1) / SU_THREADS);
-  std::vector<unsigned long long> cnt(static_cast<std::size_t>(n_rows), 0), wa(static_cast<std::size_t>(n_slices), 0);
-  std::vector<std::int64_t> ptr(static_cast<std::size_t>(n_rows) + 1, -1);
-  emu_launch(setup_count, ge, SU_THREADS, n_entries, dofmap, n_rows, cnt.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(),
-             ptr.data(), static_cast<std::int64_t>(1));
-  std::vector<std::uint32_t> pairs(static_cast<std::size_t>(ptr[n_rows]), 0xFFFFFFFFu);
-  std::fill(cnt.begin(), cnt.end(), 0ull);
-  emu_launch(setup_fill, ge, SU_THREADS, n_entries, dofmap, n_rows, (const std::int64_t*)ptr.data(), cnt.data(),
-             pairs.data());
-  if (shuffle)
-    for (std::int32_t r = 0; r < n_rows; ++r)
-      std::reverse(pairs.begin() + ptr[r], pairs.begin() + ptr[r + 1]);
-  emu_launch(setup_sort, (n_rows + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, (const std::int64_t*)ptr.data(),
-             pairs.data());
+  std::vector<unsigned long long> wa(static_cast<std::size_t>(n_slices), 0);
+  std::vector<std::int64_t> ptr;
+  std::vector<std::uint32_t> pairs;
+  emu_pairs(n_cells * 4, dofmap, n_rows, shuffle, ptr, pairs);
   emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
              (const std::int64_t*)ptr.data(), wa.data());
   emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off,

@@ -525,3 +525,31 @@ def test_opt_in_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype
         assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
     finally:
         c.close()
+
+
+@OPTIN
+@pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
+                                              ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
+                                              ("poisson", 3, (4, 5, 3))])
+def test_opt_in_device_built_pattern_equals_the_host_pattern(pt, oracle, monkeypatch, ptype, order, dims):
+    """ptb_build_pattern (the reference's create_matrix step, on the device) returns the host
+    pattern bit for bit; matrix, vector and solve through it match the oracle. With PTB_GPU_SETUP=1
+    the whole integer side of a P1 problem (pattern, slot words, walk) is device-built."""
+    P = pt.host.Problem(ptype, order, *dims)
+    monkeypatch.setenv("PTB_GPU_SETUP", "1")
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P, build_pattern=True)
+        rp, cl = c.pattern()
+        assert c.nnz == P.nnz and np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"])
+        c.assemble_matrix()
+        c.assemble_vector()
+        A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+        _check_matrix(P, c.matrix_values(), A_ref)
+        assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
+                                precond="jacobi")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8
+    finally:
+        c.close()

@@ -643,3 +643,22 @@ def test_device_setup_source_flags_a_pattern_that_misses_a_cell_pair(pt, emusu):
     assert emusu.emu_setup_p1(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]), _p(cols),
                               0, C.c_int64(cap), _p(adj_off), _p(adjrot), _p(walk), _p(flags)) == 0
     assert flags[0] == 1
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (1, 1, 1), 0, 1),
+                                                          ("poisson", 1, (4, 3, 5), 1, 2), ("elasticity", 1, (3, 4, 3), 0, 1),
+                                                          ("poisson", 2, (3, 2, 4), 0, 1), ("poisson", 2, (2, 2, 5), 1, 2),
+                                                          ("poisson", 3, (2, 3, 2), 0, 1), ("poisson", 3, (2, 2, 4), 2, 3)])
+def test_device_pattern_source_equals_the_host_pattern(pt, emusu, ptype, order, dims, rank, nranks):
+    """ptb_build_pattern's kernels (pairs -> per-row ascending union -> scan -> fill) against the
+    pattern the host stand-in builds (common/intmaps.cpp build_pattern), P1-P3, with ghost columns."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rowptr = np.full(P.n_owned + 1, -1, np.int64)
+    cols = np.full(P.nnz, -1, np.int32)
+    flags = np.full(3, -1, np.int32)
+    rc = emusu.emu_build_pattern(C.c_int64(len(dm) // P.nd), P.nd, _p(dm), P.n_owned, C.c_int64(P.nnz), _p(rowptr),
+                                 _p(cols), _p(flags))
+    assert rc == 0 and flags.tolist() == [0, 0, 0]
+    assert np.array_equal(rowptr, P["rowptr"])
+    assert np.array_equal(cols, P["cols"])
