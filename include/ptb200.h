@@ -71,11 +71,25 @@ int ptb_get_pattern(ptb_ctx* ctx, int64_t* rowptr, int32_t* cols);
 /* bc->dof_indices(): constrained block dofs (owned and ghost); all bs components constrained,
  * boundary value 0 (u0 = 0, poisson_problem.cpp:53-54). */
 int ptb_set_bc(ptb_ctx* ctx, int32_t n_bc, const int32_t* bc_dofs);
+/* "ZZZ Create boundary conditions" on the device (poisson_problem.cpp:51-79,
+ * elasticity_problem.cpp:117-146): marks the facets whose three vertices satisfy the reference's
+ * predicate (Poisson |x0| < 1e-8 or |x0 - 1| < 1e-8; elasticity |x1| < 1e-8), constrains the dofs of
+ * their closure, and replaces ptb_set_bc. *n_bc receives the number of constrained local block dofs;
+ * ptb_get_bc copies them out in ascending order (bdofs of fem::locate_dofs_topological). */
+int ptb_locate_bc(ptb_ctx* ctx, int32_t* n_bc);
+int ptb_get_bc(ptb_ctx* ctx, int32_t* bc_dofs);
 /* Exterior facets as (cell, local_facet) pairs for the g*v*ds term (Poisson.py:32). */
 int ptb_set_exterior_facets(ptb_ctx* ctx, int64_t n_facets, const int32_t* cells,
                             const int32_t* local_facets);
 /* Coefficients of L: f->x()->array() [(n_owned+n_ghost)*bs] and g (Poisson only, else NULL). */
 int ptb_set_source(ptb_ctx* ctx, const double* f, const double* g);
+/* "ZZZ Create RHS function" on the device (poisson_problem.cpp:82-108, elasticity_problem.cpp:150-178):
+ * evaluates the reference's interpolation lambdas at the dof coordinates and replaces ptb_set_source.
+ * dof_x [(n_owned+n_ghost)*3] = V->tabulate_dof_coordinates(); NULL for order 1, where the dofs sit
+ * on the vertices the context already holds. ptb_get_source copies f [(n_owned+n_ghost)*bs] and g
+ * [(n_owned+n_ghost)] (Poisson; may be NULL) back. */
+int ptb_interpolate_source(ptb_ctx* ctx, const double* dof_x);
+int ptb_get_source(ptb_ctx* ctx, double* f, double* g);
 /* Re-upload geometry coordinates only (same topology). */
 int ptb_update_geometry(ptb_ctx* ctx, const double* x);
 /* common::Scatterer lists (cgpoisson_problem.cpp:187-229): forward scatter owner -> ghost. */

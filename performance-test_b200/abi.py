@@ -49,6 +49,10 @@ def lib():
         L.ptb_set_pattern.argtypes = [vp, vp, vp]
         L.ptb_build_pattern.argtypes = [vp, C.POINTER(i64)]
         L.ptb_get_pattern.argtypes = [vp, vp, vp]
+        L.ptb_locate_bc.argtypes = [vp, C.POINTER(i32)]
+        L.ptb_get_bc.argtypes = [vp, vp]
+        L.ptb_interpolate_source.argtypes = [vp, vp]
+        L.ptb_get_source.argtypes = [vp, vp, vp]
         L.ptb_set_bc.argtypes = [vp, i32, vp]
         L.ptb_set_exterior_facets.argtypes = [vp, i64, vp, vp]
         L.ptb_set_source.argtypes = [vp, vp, vp]
@@ -278,10 +282,11 @@ class Context:
             pass
 
     # ---- setup ---------------------------------------------------------------------------
-    def set_problem(self, P, source=True, build_pattern=False):
+    def set_problem(self, P, source=True, build_pattern=False, device_data=False):
         """Upload everything a host problem (host.Problem or the oracle's RefProblem) holds. With
         build_pattern the sparsity pattern is built on the device from the dofmap
-        (ptb_build_pattern) instead of being uploaded."""
+        (ptb_build_pattern) instead of being uploaded; with device_data the Dirichlet dofs and the
+        source terms are evaluated on the device (ptb_locate_bc, ptb_interpolate_source)."""
         self.P = P
         self.bs, self.nd = P.bs, P.nd
         self.n_owned, self.n_ghost, self.nnz = P.n_owned, P.n_ghost, P.nnz
@@ -297,11 +302,16 @@ class Context:
         else:
             rp, cl = _a(P["rowptr"], np.int64), _a(P["cols"], np.int32)
             self._check(lib().ptb_set_pattern(self._h, _ptr(rp), _ptr(cl)))
-        bc = _a(P["bc_dofs"], np.int32)
-        self._check(lib().ptb_set_bc(self._h, len(bc), _ptr(bc)))
+        if device_data:
+            self.locate_bc()
+        else:
+            bc = _a(P["bc_dofs"], np.int32)
+            self._check(lib().ptb_set_bc(self._h, len(bc), _ptr(bc)))
         fc, fl = _a(P["facet_cells"], np.int32), _a(P["facet_local"], np.int32)
         self._check(lib().ptb_set_exterior_facets(self._h, len(fc), _ptr(fc), _ptr(fl)))
-        if source:
+        if source and device_data:
+            self.interpolate_source(None if P.order == 1 else P["dof_x"])
+        elif source:
             self.set_source(P["f"], P["g"] if len(P["g"]) else None)
         if P.n_nbr > 0:
             self._check(lib().ptb_set_halo(
@@ -313,6 +323,27 @@ class Context:
         f = _a(f, np.float64)
         g = None if g is None else _a(g, np.float64)
         self._check(lib().ptb_set_source(self._h, _ptr(f), _ptr(g)))
+
+    def locate_bc(self):
+        """Dirichlet dofs located on the device (ascending local block dofs)."""
+        n = C.c_int32()
+        self._check(lib().ptb_locate_bc(self._h, C.byref(n)))
+        out = np.empty(n.value, dtype=np.int32)
+        if n.value:
+            self._check(lib().ptb_get_bc(self._h, _ptr(out)))
+        return out
+
+    def interpolate_source(self, dof_x=None):
+        x = None if dof_x is None else _a(dof_x, np.float64)
+        self._check(lib().ptb_interpolate_source(self._h, _ptr(x)))
+
+    def source(self):
+        """(f, g | None) as the device holds them."""
+        n = self.n_owned + self.n_ghost
+        f = np.empty(n * self.bs, dtype=np.float64)
+        g = np.empty(n, dtype=np.float64) if self.bs == 1 else None
+        self._check(lib().ptb_get_source(self._h, _ptr(f), _ptr(g)))
+        return f, g
 
     def update_geometry(self, x):
         x = _a(x, np.float64)

@@ -462,6 +462,34 @@ int ptb_set_bc(ptb_ctx* c, int32_t n_bc, const int32_t* bc_dofs)
   });
 }
 
+int ptb_locate_bc(ptb_ctx* c, int32_t* n_bc)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_locate_bc: call ptb_set_space first");
+    const std::int64_t nl = static_cast<std::int64_t>(c->n_owned) + c->n_ghost;
+    launch_locate_bc(c);
+    std::vector<std::uint8_t> m(static_cast<std::size_t>(nl));
+    PTB_CUDA(cudaMemcpyAsync(m.data(), c->bc.p, m.size(), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->h_bc_dofs.clear();
+    for (std::int64_t d = 0; d < nl; ++d)
+      if (m[d])
+        c->h_bc_dofs.push_back(static_cast<std::int32_t>(d));
+    if (n_bc)
+      *n_bc = static_cast<std::int32_t>(c->h_bc_dofs.size());
+    c->matrix_assembled = c->vector_assembled = false;
+  });
+}
+
+int ptb_get_bc(ptb_ctx* c, int32_t* bc_dofs)
+{
+  return guarded(c, [&] {
+    need(c->have_space && bc_dofs, "ptb_get_bc: no space set / NULL output");
+    std::copy(c->h_bc_dofs.begin(), c->h_bc_dofs.end(), bc_dofs);
+  });
+}
+
 int ptb_set_exterior_facets(ptb_ctx* c, int64_t n_facets, const int32_t* cells,
                             const int32_t* local_facets)
 {
@@ -496,6 +524,47 @@ int ptb_set_source(ptb_ctx* c, const double* f, const double* g)
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     c->have_source = true;
     c->vector_assembled = false;
+  });
+}
+
+int ptb_interpolate_source(ptb_ctx* c, const double* dof_x)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space, "ptb_interpolate_source: call ptb_set_space first");
+    need(dof_x || c->order == 1, "ptb_interpolate_source: dof coordinates are required for order > 1");
+    const std::size_t nl = static_cast<std::size_t>(c->n_owned) + c->n_ghost;
+    c->f.alloc(nl * c->bs);
+    if (c->problem == PTB_POISSON)
+      c->g.alloc(nl);
+    else
+      c->g.release();
+    if (dof_x)
+    {
+      DevBuf<double> X;
+      X.upload(dof_x, nl * 3, c->stream);
+      launch_interpolate_source(c, X.p, 3);
+      PTB_CUDA(cudaStreamSynchronize(c->stream)); // X dies here
+    }
+    else
+    {
+      launch_interpolate_source(c, c->xdof.p, 4);
+      PTB_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    c->have_source = true;
+    c->vector_assembled = false;
+  });
+}
+
+int ptb_get_source(ptb_ctx* c, double* f, double* g)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_source && f, "ptb_get_source: no source set / NULL output");
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    PTB_CUDA(cudaMemcpy(f, c->f.p, c->f.bytes(), cudaMemcpyDeviceToHost));
+    if (g && c->g.p)
+      PTB_CUDA(cudaMemcpy(g, c->g.p, c->g.bytes(), cudaMemcpyDeviceToHost));
   });
 }
 

@@ -100,6 +100,11 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
 /// downloaded; false when a row is too long for the device build.
 bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols);
 
+/// Device-side problem data (problem_data.cu): Dirichlet markers from the reference's facet predicate
+/// + facet closure into c->bc; the source terms at the dof coordinates X (stride 3 or 4) into c->f, c->g.
+void launch_locate_bc(ptb_ctx* c);
+void launch_interpolate_source(ptb_ctx* c, const double* X, int stride);
+
 void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 /// Star-walk variant (assemble_walk.cu); returns false when it does not apply (no walk uploaded,

@@ -553,3 +553,35 @@ def test_opt_in_device_built_pattern_equals_the_host_pattern(pt, oracle, monkeyp
         assert abs(k - k_ref) <= 1 and rel < 1e-8
     finally:
         c.close()
+
+
+@OPTIN
+@pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
+                                              ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
+                                              ("poisson", 3, (4, 5, 3))])
+def test_opt_in_device_problem_data_matches_the_host(pt, oracle, ptype, order, dims):
+    """ptb_locate_bc / ptb_interpolate_source (the reference's 'ZZZ Create boundary conditions' and
+    'ZZZ Create RHS function' on the device): the same Dirichlet dofs; f and g within 4 ulp of the
+    host's libm (the arguments of exp / sin / sqrt are identical, only the functions round
+    differently); assembly and solve through them match the oracle."""
+    P = pt.host.Problem(ptype, order, *dims)
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P, device_data=True)
+        assert np.array_equal(c.locate_bc(), np.sort(P["bc_dofs"]))
+        f, g = c.source()
+        ulp = np.finfo(np.float64).eps
+        assert np.abs(f - P["f"]).max() <= 4 * ulp * np.abs(P["f"]).max()
+        if g is not None:
+            assert np.abs(g - P["g"]).max() <= 4 * ulp
+        c.assemble_matrix()
+        c.assemble_vector()
+        A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+        _check_matrix(P, c.matrix_values(), A_ref)
+        assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
+                                precond="jacobi")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8
+    finally:
+        c.close()

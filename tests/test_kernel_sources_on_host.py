@@ -662,3 +662,63 @@ def test_device_pattern_source_equals_the_host_pattern(pt, emusu, ptype, order, 
     assert rc == 0 and flags.tolist() == [0, 0, 0]
     assert np.array_equal(rowptr, P["rowptr"])
     assert np.array_equal(cols, P["cols"])
+
+
+# ---- device-side problem data: Dirichlet dofs and source terms (csrc/problem_data.cu) ---------------
+
+PD_SRC = os.path.join(HERE, "emu", "emu_problem_data.cpp")
+
+
+@pytest.fixture(scope="module")
+def emupd():
+    out = os.path.join(HERE, "emu", "_build", "libemuproblemdata.so")
+    deps = [PD_SRC] + [os.path.join(CSRC, f) for f in ("problem_data.cu", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                        "-I", cuda_inc, "-I", CSRC, "-o", out, PD_SRC], check=True)
+    return C.CDLL(out)
+
+
+PROBLEM_DATA = [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (1, 1, 1), 0, 1), ("poisson", 1, (4, 3, 5), 1, 2),
+                ("elasticity", 1, (3, 4, 3), 0, 1), ("elasticity", 1, (2, 2, 5), 1, 2), ("poisson", 2, (3, 2, 4), 0, 1),
+                ("poisson", 2, (2, 2, 5), 1, 2), ("poisson", 3, (2, 3, 2), 0, 1), ("poisson", 3, (2, 2, 4), 2, 3)]
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", PROBLEM_DATA)
+def test_bc_location_source_finds_the_reference_dofs(pt, emupd, ptype, order, dims, rank, nranks):
+    """Facet marker + facet closure (locate_entities + locate_dofs_topological) on every local cell
+    gives exactly the stand-in's Dirichlet dofs, owned and ghost, P1-P3, on partitions too."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    x = np.asarray(P["x"]).reshape(-1, 3)
+    xyz4 = np.zeros((len(x), 4))
+    xyz4[:, :3] = x
+    xd = np.ascontiguousarray(P["x_dofmap"], np.int32)
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    bc = np.zeros(P.n_owned + P.n_ghost, np.uint8)
+    assert emupd.emu_locate_bc(C.c_int64(len(xd) // 4), pt.abi.PROBLEMS[ptype], order, P.nd, _p(xyz4), _p(xd), _p(dm),
+                               _p(bc)) == 0
+    assert np.array_equal(np.flatnonzero(bc), np.sort(P["bc_dofs"]))
+    assert bc.max() <= 1
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", PROBLEM_DATA)
+def test_source_interpolation_source_equals_the_host_lambdas(pt, emupd, ptype, order, dims, rank, nranks):
+    """f and g at the dof coordinates, bit for bit on the host (same libm, no contraction); for P1
+    also through the padded by-dof vertex coordinates the context holds."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    n = P.n_owned + P.n_ghost
+    X = np.ascontiguousarray(P["dof_x"], np.float64)
+    variants = [(X, 3)]
+    if order == 1:
+        X4 = np.zeros((n, 4))
+        X4[:, :3] = X.reshape(-1, 3)
+        variants.append((np.ascontiguousarray(X4.reshape(-1)), 4))
+    for Xv, stride in variants:
+        f = np.full(n * P.bs, np.nan)
+        g = np.full(n, np.nan)
+        assert emupd.emu_interpolate_source(C.c_int64(n), pt.abi.PROBLEMS[ptype], _p(Xv), stride, _p(f), _p(g)) == 0
+        assert np.array_equal(f, P["f"])
+        if ptype == "poisson":
+            assert np.array_equal(g, P["g"])
