@@ -409,22 +409,59 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
 {
   std::vector<std::int64_t> rowptr;
   std::vector<std::int32_t> cols;
+  bool done = false;
   const int rc = guarded(c, [&] {
     use_device(c);
     need(c->have_space, "ptb_build_pattern: call ptb_set_space first");
-    if (!gpu_build_pattern(c, rowptr, cols))
+    DevBuf<std::int64_t> rp;
+    DevBuf<std::int32_t> cl;
+    if (!gpu_build_pattern(c, rowptr, cols, rp, cl))
     {
       // a row beyond the device kernels' capacity: same pattern from the host builder
       RowAdjacency adj;
       build_row_adjacency(c->h_dofmap.data(), c->n_cells, c->nd, c->n_owned, adj);
       build_pattern(c->h_dofmap.data(), c->nd, c->n_owned, adj, rowptr, cols);
+      return;
     }
+    if (!(gpu_setup_enabled() && c->nd == 4 && !gwalk_enabled()))
+      return;
+    // P1 with PTB_GPU_SETUP=1: the pattern never leaves the device on its way into the layouts --
+    // column side (setup.cu gpu_setup_columns) and adjacency side (gpu_setup_p1) are built there;
+    // this is ptb_set_pattern without its host loops.
+    c->nnz = rowptr[c->n_owned];
+    gpu_setup_columns(c, rp, cl);
+    const bool want_walk
+        = (c->bs == 1 && walk_enabled() && c->max_w <= 32) || (c->bs == 3 && walk3_enabled());
+    int max_wa = 0;
+    c->walk.release();
+    if (c->max_w >= 255 || !gpu_setup_p1(c, want_walk, &max_wa))
+      return; // not expressible in one-byte offsets: ptb_set_pattern below rebuilds everything
+    c->max_wa = max_wa;
+    c->so_bits = 8, c->so_words = 1;
+    c->h_rowptr = rowptr;
+    c->h_adj.ptr.assign(static_cast<std::size_t>(c->n_owned) + 1, 0);
+    c->h_adj.pairs.clear(), c->h_so.clear();
+    c->adj.release(), c->adjso.release();
+    c->walk1.release(), c->walk1_off.release();
+    c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
+    c->walk_loads_per_step = 0.0;
+    c->vals.alloc(c->cols.n * c->bs * c->bs);
+    c->vals.zero(c->stream);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->maps_on_device = true;
+    c->have_pattern = true;
+    c->matrix_assembled = false;
+    c->have_compact = false;
+    done = true;
   });
   if (rc != 0)
     return rc;
-  const int rc2 = ptb_set_pattern(c, rowptr.data(), cols.data());
-  if (rc2 != 0)
-    return rc2;
+  if (!done)
+  {
+    const int rc2 = ptb_set_pattern(c, rowptr.data(), cols.data());
+    if (rc2 != 0)
+      return rc2;
+  }
   c->h_cols.swap(cols);
   if (nnz)
     *nnz = c->nnz;

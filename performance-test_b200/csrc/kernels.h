@@ -98,7 +98,12 @@ void compact_operator(ptb_ctx* c);
 bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
 /// The sparsity pattern of the owned rows built on the device from the uploaded dofmap (setup.cu) and
 /// downloaded; false when a row is too long for the device build.
-bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols);
+/// rp / cl keep the device copies (CSR).
+bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols,
+                       DevBuf<std::int64_t>& rp, DevBuf<std::int32_t>& cl);
+/// Column side of ptb_set_pattern (SELL-32 offsets and padded columns, column compression, slice
+/// order) from a CSR pattern on the device; takes rp over as c->rowptr.
+void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl);
 
 /// Device-side problem data (problem_data.cu): Dirichlet markers from the reference's facet predicate
 /// + facet closure into c->bc; the source terms at the dof coordinates X (stride 3 or 4) into c->f, c->g.

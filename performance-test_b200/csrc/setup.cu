@@ -10,12 +10,18 @@
 //   rotated words                per (row, cell): binary search of the cell's four vertices in the
 //                                row's column list, packed with the owner first (adjrot)
 //   walk                         the greedy star walk of layout.cpp build_walk, one thread per row
+//   sell cols / cdelta / colsx   the column side of ptb_set_pattern (layout.cpp build_sell_layout,
+//   slice flags / order          compress_columns, build_slice_order without clustering): SELL-32
+//                                offsets and padded columns, one delta per (slice, k) where the 32
+//                                rows share col - row, explicit indices elsewhere, and the visiting
+//                                order "slices without ghost columns first"
 //   pattern count / scan / fill  the sparsity pattern itself (common/intmaps.cpp build_pattern; the
 //                                reference builds it in fem::create_matrix, poisson_problem.cpp:122-123,
 //                                inside the timed assembly stage): per owned row the ascending union of
 //                                the dofs of its cells, any Lagrange order (ptb_build_pattern)
-// The column side (mat_off, padded columns, column compression, slice order) stays on the host: it
-// only needs the caller's CSR pattern, no adjacency.
+// With a caller-supplied pattern (ptb_set_pattern) the column side stays on the host: it only needs
+// the CSR arrays, no adjacency. With ptb_build_pattern the pattern is already on the device and the
+// column side is built there too (gpu_setup_columns), so no O(nnz) host loop is left for P1.
 // NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
 #include "kernels.h"
 #include <climits>
@@ -174,6 +180,114 @@ __global__ void setup_adjrot(std::int32_t n_rows, std::int32_t n_slices,
     }
     adjrot[ao + static_cast<std::int64_t>(k) * 32 + lane] = word;
   }
+}
+
+// ---- column side ---------------------------------------------------------------------------------
+// widths of the matrix slices: setup_widths on rowptr. Padded columns: thread = (slice, lane);
+// positions past the row's length repeat its first column (0 past n_rows), as build_sell_layout does.
+__global__ void setup_sell_cols(std::int32_t n_rows, std::int32_t n_slices, const std::int64_t* __restrict__ rowptr,
+                                const std::int32_t* __restrict__ cols, const std::int64_t* __restrict__ mat_off,
+                                std::int32_t* __restrict__ cols_sell)
+{
+  const std::int64_t t = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  const std::int32_t s = static_cast<std::int32_t>(t >> 5);
+  const int lane = static_cast<int>(t & 31);
+  if (s >= n_slices)
+    return;
+  const std::int32_t r = 32 * s + lane;
+  const std::int64_t mo = mat_off[s], w = (mat_off[s + 1] - mo) >> 5;
+  const std::int64_t len = r < n_rows ? rowptr[r + 1] - rowptr[r] : 0;
+  const std::int32_t pad = len > 0 ? cols[rowptr[r]] : 0;
+  for (std::int64_t k = 0; k < w; ++k)
+    cols_sell[mo + k * 32 + lane] = k < len ? cols[rowptr[r] + k] : pad;
+}
+
+// compress_columns, first half: one thread per slice decides every (slice, k) and counts the
+// explicit ones. A partial last slice stays explicit (row + delta may overrun).
+__global__ void setup_cdelta(std::int32_t n_rows, std::int64_t n_cols, std::int32_t n_slices,
+                             const std::int64_t* __restrict__ rowptr, const std::int64_t* __restrict__ mat_off,
+                             const std::int32_t* __restrict__ cols_sell, std::int32_t* __restrict__ cdelta,
+                             unsigned long long* __restrict__ xcnt)
+{
+  const std::int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slices)
+    return;
+  const std::int64_t mo = mat_off[s], w = (mat_off[s + 1] - mo) >> 5;
+  const std::int32_t r0 = 32 * s;
+  const bool full = r0 + 32 <= n_rows;
+  unsigned long long nx = 0;
+  for (std::int64_t k = 0; k < w; ++k)
+  {
+    bool uniform = full, have = false;
+    std::int64_t d = 0;
+    for (int lane = 0; lane < 32 && uniform; ++lane)
+    {
+      const std::int32_t r = r0 + lane;
+      if (k >= rowptr[r + 1] - rowptr[r])
+        continue; // padding: free to choose
+      const std::int64_t dl = static_cast<std::int64_t>(cols_sell[mo + k * 32 + lane]) - r;
+      if (!have)
+        d = dl, have = true;
+      else if (dl != d)
+        uniform = false;
+    }
+    if (uniform && !have)
+      d = 0; // all padding: point at the row itself
+    if (uniform && (r0 + d < 0 || static_cast<std::int64_t>(r0) + 31 + d >= n_cols))
+      uniform = false;
+    cdelta[mo / 32 + k] = uniform ? static_cast<std::int32_t>(d) : INT_MIN;
+    nx += uniform ? 0 : 1;
+  }
+  xcnt[s] = nx;
+}
+
+// compress_columns, second half: the explicit index lines, thread = (slice, lane)
+__global__ void setup_colsx(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
+                            const std::int32_t* __restrict__ cols_sell, const std::int32_t* __restrict__ cdelta,
+                            const std::int64_t* __restrict__ xoff, std::int32_t* __restrict__ colsx)
+{
+  const std::int64_t t = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  const std::int32_t s = static_cast<std::int32_t>(t >> 5);
+  const int lane = static_cast<int>(t & 31);
+  if (s >= n_slices)
+    return;
+  const std::int64_t mo = mat_off[s], w = (mat_off[s + 1] - mo) >> 5;
+  std::int64_t j = 0;
+  for (std::int64_t k = 0; k < w; ++k)
+    if (cdelta[mo / 32 + k] == INT_MIN)
+    {
+      colsx[xoff[s] + j * 32 + lane] = cols_sell[mo + k * 32 + lane];
+      ++j;
+    }
+}
+
+// build_slice_order without clustering: interior[s] = 1 when no stored column of the slice is a ghost
+__global__ void setup_slice_flags(std::int32_t n_rows, std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
+                                  const std::int32_t* __restrict__ cols_sell, unsigned long long* __restrict__ interior)
+{
+  const std::int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slices)
+    return;
+  unsigned long long in = 1;
+  for (std::int64_t q = mat_off[s]; q < mat_off[s + 1]; ++q)
+    if (cols_sell[q] >= n_rows)
+    {
+      in = 0;
+      break;
+    }
+  interior[s] = in;
+}
+
+// interior slices first (ascending), then the ghost-reading ones (ascending); pos = exclusive scan
+// of the interior flags, pos[n_slices] = number of interior slices
+__global__ void setup_slice_order(std::int32_t n_slices, const unsigned long long* __restrict__ interior,
+                                  const std::int64_t* __restrict__ pos, std::int32_t* __restrict__ order)
+{
+  const std::int32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_slices)
+    return;
+  const std::int64_t at = interior[s] ? pos[s] : pos[n_slices] + (s - pos[s]);
+  order[at] = s;
 }
 
 // Ascending union of the dofs of the row's cells, built by sorted insertion into a thread-local
@@ -361,13 +475,13 @@ void build_pairs(ptb_ctx* c, DevBuf<std::int64_t>& ptr, DevBuf<std::uint32_t>& p
 
 // The sparsity pattern of the owned rows built on the device and downloaded (any order). Returns
 // false when a row has more than SU_MAX_COLS columns (the caller builds the pattern on the host).
-bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols)
+bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols,
+                       DevBuf<std::int64_t>& rp, DevBuf<std::int32_t>& cl)
 {
   const std::int32_t N = c->n_owned;
-  DevBuf<std::int64_t> ptr, rp;
+  DevBuf<std::int64_t> ptr;
   DevBuf<std::uint32_t> pairs;
   DevBuf<unsigned long long> cnt;
-  DevBuf<std::int32_t> cl;
   DevBuf<int> flags;
   build_pairs(c, ptr, pairs);
   cnt.alloc(static_cast<std::size_t>(N));
@@ -395,6 +509,65 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
   PTB_CUDA(cudaStreamSynchronize(c->stream));
   c->launches += 1;
   return true;
+}
+
+// The column side of ptb_set_pattern from a CSR pattern that is already on the device: c->rowptr,
+// mat_off, cols (SELL-32, padded), for scalar problems cdelta / colsx / xoff, and the slice order.
+// Sets n_slices, max_w, cols_explicit_frac, n_interior_slices. Eight launches (five for bs = 3).
+void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl)
+{
+  const std::int32_t N = c->n_owned, S = (N + 31) / 32;
+  const std::int64_t n_cols = static_cast<std::int64_t>(N) + c->n_ghost;
+  c->n_slices = S;
+  DevBuf<unsigned long long> w;
+  w.alloc(static_cast<std::size_t>(S));
+  const int gs = (S + SU_THREADS - 1) / SU_THREADS;
+  const int gl = static_cast<int>((static_cast<std::int64_t>(S) * 32 + SU_THREADS - 1) / SU_THREADS);
+  setup_widths<<<gs, SU_THREADS, 0, c->stream>>>(N, S, rp.p, w.p);
+  c->mat_off.alloc(static_cast<std::size_t>(S) + 1);
+  setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, c->mat_off.p, 32);
+  std::int64_t n_sell = 0;
+  std::vector<unsigned long long> h_w(static_cast<std::size_t>(S));
+  PTB_CUDA(cudaMemcpyAsync(&n_sell, c->mat_off.p + S, sizeof(n_sell), cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA(cudaMemcpyAsync(h_w.data(), w.p, h_w.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                           c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  c->max_w = 0;
+  for (unsigned long long v : h_w)
+    c->max_w = std::max(c->max_w, static_cast<int>(v));
+  c->cols.alloc(static_cast<std::size_t>(n_sell));
+  setup_sell_cols<<<gl, SU_THREADS, 0, c->stream>>>(N, S, rp.p, cl.p, c->mat_off.p, c->cols.p);
+  c->launches += 3;
+  if (c->bs == 1)
+  {
+    c->cdelta.alloc(static_cast<std::size_t>(n_sell / 32));
+    setup_cdelta<<<gs, SU_THREADS, 0, c->stream>>>(N, n_cols, S, rp.p, c->mat_off.p, c->cols.p, c->cdelta.p, w.p);
+    c->xoff.alloc(static_cast<std::size_t>(S) + 1);
+    setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, c->xoff.p, 32);
+    std::int64_t n_x = 0;
+    PTB_CUDA(cudaMemcpyAsync(&n_x, c->xoff.p + S, sizeof(n_x), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->colsx.alloc(static_cast<std::size_t>(n_x));
+    if (n_x > 0)
+      setup_colsx<<<gl, SU_THREADS, 0, c->stream>>>(S, c->mat_off.p, c->cols.p, c->cdelta.p, c->xoff.p, c->colsx.p);
+    c->cols_explicit_frac = n_sell > 0 ? static_cast<double>(n_x) / static_cast<double>(n_sell) : 0.0;
+    c->launches += 3;
+  }
+  DevBuf<std::int64_t> pos;
+  pos.alloc(static_cast<std::size_t>(S) + 1);
+  c->slice_order.alloc(static_cast<std::size_t>(S));
+  setup_slice_flags<<<gs, SU_THREADS, 0, c->stream>>>(N, S, c->mat_off.p, c->cols.p, w.p);
+  setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, pos.p, 1);
+  setup_slice_order<<<gs, SU_THREADS, 0, c->stream>>>(S, w.p, pos.p, c->slice_order.p);
+  PTB_CUDA(cudaGetLastError());
+  std::int64_t n_int = 0;
+  PTB_CUDA(cudaMemcpyAsync(&n_int, pos.p + S, sizeof(n_int), cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream)); // w, pos die here
+  c->n_interior_slices = static_cast<std::int32_t>(n_int);
+  c->launches += 3;
+  // the kernels read rowptr from the context: take the device copy over instead of re-uploading it
+  std::swap(c->rowptr.p, rp.p);
+  std::swap(c->rowptr.n, rp.n);
 }
 
 bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)

@@ -3,6 +3,7 @@
 #define PTB_HOST_EMU 1
 #include <algorithm>
 #include <barrier>
+#include <climits>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -104,6 +105,42 @@ int emu_build_pattern(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_
     return -1;
   emu_launch(setup_pattern_fill, gr, SU_THREADS, n_rows, nd, dofmap, (const std::int64_t*)ptr.data(),
              (const std::uint32_t*)pairs.data(), (const std::int64_t*)rowptr, cols);
+  return 0;
+}
+
+// The launch sequence of gpu_setup_columns (setup.cu) for a scalar problem. mat_off, xoff, order
+// [n_slices (+ 1)] are always written; cols_sell / cdelta (capacity cap, cap / 32) and colsx
+// (capacity capx) when the totals fit (returns -1 otherwise). *n_interior = interior slices.
+int emu_setup_columns(int32_t n_rows, int64_t n_cols, int32_t n_slices, const int64_t* rowptr, const int32_t* cols,
+                      int64_t cap, int64_t capx, int64_t* mat_off, int32_t* cols_sell, int32_t* cdelta, int64_t* xoff,
+                      int32_t* colsx, int32_t* order, int32_t* n_interior)
+{
+  using namespace ptb;
+  std::vector<unsigned long long> w(static_cast<std::size_t>(n_slices), 0);
+  const unsigned gs = (n_slices + SU_THREADS - 1) / SU_THREADS;
+  const unsigned gl = static_cast<unsigned>((static_cast<std::int64_t>(n_slices) * 32 + SU_THREADS - 1) / SU_THREADS);
+  emu_launch(setup_widths, gs, SU_THREADS, n_rows, n_slices, rowptr, w.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), mat_off,
+             static_cast<std::int64_t>(32));
+  if (mat_off[n_slices] > cap)
+    return -1;
+  emu_launch(setup_sell_cols, gl, SU_THREADS, n_rows, n_slices, rowptr, cols, (const std::int64_t*)mat_off, cols_sell);
+  emu_launch(setup_cdelta, gs, SU_THREADS, n_rows, n_cols, n_slices, rowptr, (const std::int64_t*)mat_off,
+             (const std::int32_t*)cols_sell, cdelta, w.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), xoff,
+             static_cast<std::int64_t>(32));
+  if (xoff[n_slices] > capx)
+    return -1;
+  emu_launch(setup_colsx, gl, SU_THREADS, n_slices, (const std::int64_t*)mat_off, (const std::int32_t*)cols_sell,
+             (const std::int32_t*)cdelta, (const std::int64_t*)xoff, colsx);
+  std::vector<std::int64_t> pos(static_cast<std::size_t>(n_slices) + 1, -1);
+  emu_launch(setup_slice_flags, gs, SU_THREADS, n_rows, n_slices, (const std::int64_t*)mat_off,
+             (const std::int32_t*)cols_sell, w.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), pos.data(),
+             static_cast<std::int64_t>(1));
+  emu_launch(setup_slice_order, gs, SU_THREADS, n_slices, (const unsigned long long*)w.data(),
+             (const std::int64_t*)pos.data(), order);
+  *n_interior = static_cast<std::int32_t>(pos[n_slices]);
   return 0;
 }
 

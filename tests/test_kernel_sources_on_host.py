@@ -722,3 +722,39 @@ def test_source_interpolation_source_equals_the_host_lambdas(pt, emupd, ptype, o
         assert np.array_equal(f, P["f"])
         if ptype == "poisson":
             assert np.array_equal(g, P["g"])
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (1, 1, 1), 0, 1),
+                                                          ("poisson", 1, (33, 2, 1), 0, 1), ("poisson", 1, (4, 3, 5), 1, 2),
+                                                          ("poisson", 1, (3, 3, 7), 2, 3), ("poisson", 1, (3, 3, 7), 0, 3),
+                                                          ("poisson", 1, (12, 11, 13), 0, 1), ("poisson", 2, (3, 2, 4), 1, 2)])
+def test_device_column_layout_source_equals_the_host_layout(pt, emusu, ptype, order, dims, rank, nranks):
+    """SELL-32 offsets and padded columns, the compressed column indices (one delta per 32 rows /
+    explicit lines) and the slice visiting order from the setup kernels equal layout.cpp's
+    build_sell_layout / compress_columns / build_slice_order on single and partitioned boxes."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    rp = np.ascontiguousarray(P["rowptr"], np.int64)
+    cl = np.ascontiguousarray(P["cols"], np.int32)
+    S = (P.n_owned + 31) // 32
+    if order == 1:
+        L = pt.abi.p1_layout(P["dofmap"], P.n_owned, rp, cl)
+        mat_off_ref, cols_ref = L["mat_off"], L["cols"]
+    else:
+        L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, rp, cl)
+        mat_off_ref, cols_ref = L["mat_off"], L["cols"]
+    cap = int(mat_off_ref[-1])
+    cd_ref, xoff_ref, cx_ref = pt.abi.compressed_columns(P.n_owned, P.n_owned + P.n_ghost, rp, cl, cap)
+    order_ref, ni_ref = pt.abi.slice_order(P.n_owned, rp, cl)
+    mat_off, xoff = np.full(S + 1, -1, np.int64), np.full(S + 1, -1, np.int64)
+    cols_sell, cdelta = np.full(cap, -7, np.int32), np.full(cap // 32, -7, np.int32)
+    capx = int(xoff_ref[-1])
+    colsx, so = np.full(max(capx, 1), -7, np.int32), np.full(S, -7, np.int32)
+    ni = C.c_int32(-1)
+    rc = emusu.emu_setup_columns(P.n_owned, C.c_int64(P.n_owned + P.n_ghost), S, _p(rp), _p(cl), C.c_int64(cap),
+                                 C.c_int64(capx), _p(mat_off), _p(cols_sell), _p(cdelta), _p(xoff), _p(colsx), _p(so),
+                                 C.byref(ni))
+    assert rc == 0
+    assert np.array_equal(mat_off, mat_off_ref) and np.array_equal(cols_sell, cols_ref)
+    assert np.array_equal(cdelta, cd_ref) and np.array_equal(xoff, xoff_ref)
+    assert np.array_equal(colsx[:capx], cx_ref[:capx])
+    assert ni.value == ni_ref and np.array_equal(so, order_ref)
