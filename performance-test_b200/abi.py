@@ -47,6 +47,9 @@ def lib():
         L.ptb_update_geometry.argtypes = [vp, vp]
         L.ptb_set_space.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32, i32, vp]
         L.ptb_set_pattern.argtypes = [vp, vp, vp]
+        L.ptb_create_box_p1.argtypes = [vp, C.c_int, C.c_int, i64, i64, i64, C.c_int, C.c_int, vp]
+        L.ptb_get_mesh.argtypes = [vp, vp, vp]
+        L.ptb_get_dofmap.argtypes = [vp, vp]
         L.ptb_build_pattern.argtypes = [vp, C.POINTER(i64)]
         L.ptb_get_pattern.argtypes = [vp, vp, vp]
         L.ptb_locate_bc.argtypes = [vp, C.POINTER(i32)]
@@ -318,6 +321,43 @@ class Context:
                 self._h, P.n_nbr, _ptr(_a(P["nbr_ranks"], np.int32)),
                 _ptr(_a(P["send_displ"], np.int32)), _ptr(_a(P["local_indices"], np.int32)),
                 _ptr(_a(P["recv_displ"], np.int32)), _ptr(_a(P["remote_indices"], np.int32))))
+
+    def set_problem_on_device(self, P):
+        """The whole setup of a P1 problem generated on the device: mesh and
+        dofmap (ptb_create_box_p1), pattern and layouts (ptb_build_pattern; with PTB_GPU_SETUP=1
+        also the assembly maps), Dirichlet dofs, source terms. Only the surface-sized lists (exterior
+        facets, halo) come from the host problem P, which also names the box and the rank."""
+        assert P.order == 1
+        self.P = P
+        self.bs, self.nd = P.bs, P.nd
+        sizes = np.zeros(4, dtype=np.int64)
+        self._check(lib().ptb_create_box_p1(self._h, PROBLEMS[P.problem_type], P.bs, P.nx, P.ny, P.nz,
+                                            P.rank, P.nranks, _ptr(sizes)))
+        self.n_vertices, self.n_cells, self.n_owned, self.n_ghost = (int(v) for v in sizes)
+        nnz = C.c_int64()
+        self._check(lib().ptb_build_pattern(self._h, C.byref(nnz)))
+        self.nnz = nnz.value
+        self.locate_bc()
+        fc, fl = _a(P["facet_cells"], np.int32), _a(P["facet_local"], np.int32)
+        self._check(lib().ptb_set_exterior_facets(self._h, len(fc), _ptr(fc), _ptr(fl)))
+        self.interpolate_source(None)
+        if P.n_nbr > 0:
+            self._check(lib().ptb_set_halo(
+                self._h, P.n_nbr, _ptr(_a(P["nbr_ranks"], np.int32)),
+                _ptr(_a(P["send_displ"], np.int32)), _ptr(_a(P["local_indices"], np.int32)),
+                _ptr(_a(P["recv_displ"], np.int32)), _ptr(_a(P["remote_indices"], np.int32))))
+
+    def mesh(self):
+        """(x, x_dofmap) as the device holds them."""
+        x = np.empty(self.n_vertices * 3, dtype=np.float64)
+        xd = np.empty(self.n_cells * 4, dtype=np.int32)
+        self._check(lib().ptb_get_mesh(self._h, _ptr(x), _ptr(xd)))
+        return x, xd
+
+    def dofmap(self):
+        dm = np.empty(self.n_cells * self.nd, dtype=np.int32)
+        self._check(lib().ptb_get_dofmap(self._h, _ptr(dm)))
+        return dm
 
     def set_source(self, f, g=None):
         f = _a(f, np.float64)

@@ -63,6 +63,16 @@ std::int64_t n_local_entries(const ptb_ctx* c)
 {
   return (static_cast<std::int64_t>(c->n_owned) + c->n_ghost) * c->bs;
 }
+// The host copy of the dofmap (integer maps built on the host); a space generated on the device
+// (ptb_create_box_p1) has none until someone asks.
+void host_dofmap(ptb_ctx* c)
+{
+  if (!c->h_dofmap.empty())
+    return;
+  c->h_dofmap.resize(c->dofmap.n);
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  PTB_CUDA(cudaMemcpy(c->h_dofmap.data(), c->dofmap.p, c->dofmap.bytes(), cudaMemcpyDeviceToHost));
+}
 std::int64_t n_owned_entries(const ptb_ctx* c) { return static_cast<std::int64_t>(c->n_owned) * c->bs; }
 
 void alloc_vectors(ptb_ctx* c)
@@ -269,6 +279,59 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
   });
 }
 
+int ptb_create_box_p1(ptb_ctx* c, int problem, int bs, int64_t nx, int64_t ny, int64_t nz, int rank, int nranks,
+                      int64_t sizes[4])
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(problem == PTB_POISSON || problem == PTB_ELASTICITY, "ptb_create_box_p1: unknown problem");
+    need((problem == PTB_POISSON && bs == 1) || (problem == PTB_ELASTICITY && bs == 3),
+         "ptb_create_box_p1: bs must be 1 for Poisson and 3 for elasticity");
+    need(nx >= 1 && ny >= 1 && nz >= 1, "ptb_create_box_p1: box dimensions must be positive");
+    need(nranks >= 1 && rank >= 0 && rank < nranks && nz >= nranks,
+         "ptb_create_box_p1: need 0 <= rank < nranks <= nz");
+    gpu_create_box_p1(c, nx, ny, nz, rank, nranks);
+    c->have_mesh = true;
+    c->problem = problem, c->order = 1, c->bs = bs, c->nd = 4;
+    c->operator_mode = PTB_OP_ASSEMBLED;
+    c->h_dofmap.clear(); // downloaded on demand (ptb_set_pattern's host build)
+    c->bc.alloc(static_cast<std::size_t>(c->n_owned) + c->n_ghost);
+    c->bc.zero(c->stream);
+    c->h_bc_dofs.clear();
+    c->xdof.alloc((static_cast<std::size_t>(c->n_owned) + c->n_ghost) * 4);
+    launch_gather_xdof(c);
+    alloc_vectors(c);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    c->have_space = true, c->have_pattern = false, c->have_source = false;
+    c->matrix_assembled = c->vector_assembled = false;
+    if (sizes)
+      sizes[0] = c->n_vertices, sizes[1] = c->n_cells, sizes[2] = c->n_owned, sizes[3] = c->n_ghost;
+  });
+}
+
+int ptb_get_mesh(ptb_ctx* c, double* x, int32_t* x_dofmap)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_mesh, "ptb_get_mesh: no mesh set");
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    if (x)
+      PTB_CUDA(cudaMemcpy(x, c->xyz3.p, c->xyz3.bytes(), cudaMemcpyDeviceToHost));
+    if (x_dofmap)
+      PTB_CUDA(cudaMemcpy(x_dofmap, c->x_dofmap.p, c->x_dofmap.bytes(), cudaMemcpyDeviceToHost));
+  });
+}
+
+int ptb_get_dofmap(ptb_ctx* c, int32_t* dofmap)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && dofmap, "ptb_get_dofmap: no space set / NULL output");
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    PTB_CUDA(cudaMemcpy(dofmap, c->dofmap.p, c->dofmap.bytes(), cudaMemcpyDeviceToHost));
+  });
+}
+
 int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
 {
   return guarded(c, [&] {
@@ -277,6 +340,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     need(rowptr && cols, "ptb_set_pattern: NULL pattern");
     const std::int32_t N = c->n_owned;
     c->nnz = rowptr[N];
+    host_dofmap(c);
     const std::vector<std::int32_t>& dm = c->h_dofmap;
     SellLayout L;
     // The adjacency side (cell lists, slot words, star walk) comes from the host build below or,
@@ -418,6 +482,7 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
     if (!gpu_build_pattern(c, rowptr, cols, rp, cl))
     {
       // a row beyond the device kernels' capacity: same pattern from the host builder
+      host_dofmap(c);
       RowAdjacency adj;
       build_row_adjacency(c->h_dofmap.data(), c->n_cells, c->nd, c->n_owned, adj);
       build_pattern(c->h_dofmap.data(), c->nd, c->n_owned, adj, rowptr, cols);
@@ -533,6 +598,7 @@ int ptb_set_exterior_facets(ptb_ctx* c, int64_t n_facets, const int32_t* cells,
   return guarded(c, [&] {
     use_device(c);
     need(c->have_space, "ptb_set_exterior_facets: call ptb_set_space first");
+    host_dofmap(c);
     const std::vector<std::int32_t>& dm = c->h_dofmap;
     for (std::int64_t k = 0; k < n_facets; ++k)
       need(cells[k] >= 0 && cells[k] < c->n_cells, "exterior facet: cell index out of range");

@@ -105,6 +105,8 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
 /// order) from a CSR pattern on the device; takes rp over as c->rowptr.
 void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl);
 
+/// The local z-slab of the unit-cube Kuhn mesh and its P1 dofmap generated on the device (box.cu).
+void gpu_create_box_p1(ptb_ctx* c, std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);
 /// Device-side problem data (problem_data.cu): Dirichlet markers from the reference's facet predicate
 /// + facet closure into c->bc; the source terms at the dof coordinates X (stride 3 or 4) into c->f, c->g.
 void launch_locate_bc(ptb_ctx* c);

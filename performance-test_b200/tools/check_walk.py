@@ -161,6 +161,15 @@ def absetup(ndofs):
     res["device_pattern_equal"] = bool(np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"]))
     c.close()
     dump()
+    # everything generated on the device: mesh, dofmap, pattern, layouts, maps, Dirichlet dofs, sources
+    c = pt.abi.Context(0)
+    t0 = time.perf_counter()
+    c.set_problem_on_device(P)
+    res["set_problem_on_device_s"] = time.perf_counter() - t0
+    c.assemble_matrix()
+    res["on_device_checksum_equal"] = float(np.abs(c.matrix_values()).sum()) == sums["1"]
+    c.close()
+    dump()
 
 
 def ncu_target(ndofs):

@@ -594,3 +594,36 @@ def test_opt_in_device_problem_data_matches_the_host(pt, oracle, ptype, order, d
         assert abs(k - k_ref) <= 1 and rel < 1e-8
     finally:
         c.close()
+
+
+@OPTIN
+@pytest.mark.parametrize("gpu_setup", ["0", "1"])
+@pytest.mark.parametrize("ptype,dims", [("poisson", (16, 15, 17)), ("poisson", (1, 1, 1)), ("elasticity", (8, 9, 7))])
+def test_opt_in_whole_p1_setup_generated_on_the_device(pt, oracle, monkeypatch, ptype, dims, gpu_setup):
+    """ptb_create_box_p1 + ptb_build_pattern + ptb_locate_bc + ptb_interpolate_source: mesh, dofmap,
+    pattern and Dirichlet dofs equal the host stand-in's arrays bit for bit, and the hot path on top
+    of them matches the oracle. With PTB_GPU_SETUP=1 the layouts and assembly maps are device-built too."""
+    P = pt.host.Problem(ptype, 1, *dims)
+    monkeypatch.setenv("PTB_GPU_SETUP", gpu_setup)
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem_on_device(P)
+        assert (c.n_vertices, c.n_cells, c.n_owned, c.n_ghost) == (P.n_vertices, P.n_cells, P.n_owned, P.n_ghost)
+        x, xd = c.mesh()
+        assert np.array_equal(x, P["x"]) and np.array_equal(xd, P["x_dofmap"])
+        assert np.array_equal(c.dofmap(), P["dofmap"])
+        rp, cl = c.pattern()
+        assert np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"])
+        assert c.p1_maps()["built_on_device"] == (gpu_setup == "1")
+        c.assemble_matrix()
+        c.assemble_vector()
+        A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+        _check_matrix(P, c.matrix_values(), A_ref)
+        # f and g come from the device's exp / sin: a few ulp of the host's, see the problem-data test
+        assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
+                                precond="jacobi")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8
+    finally:
+        c.close()

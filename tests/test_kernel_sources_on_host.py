@@ -758,3 +758,58 @@ def test_device_column_layout_source_equals_the_host_layout(pt, emusu, ptype, or
     assert np.array_equal(cdelta, cd_ref) and np.array_equal(xoff, xoff_ref)
     assert np.array_equal(colsx[:capx], cx_ref[:capx])
     assert ni.value == ni_ref and np.array_equal(so, order_ref)
+
+
+# ---- device-side mesh and P1 dofmap of the unit cube (csrc/box.cu) ----------------------------------
+
+BX_SRC = os.path.join(HERE, "emu", "emu_box.cpp")
+
+
+@pytest.fixture(scope="module")
+def emubx():
+    out = os.path.join(HERE, "emu", "_build", "libemubox.so")
+    deps = [BX_SRC] + [os.path.join(CSRC, f) for f in ("box.cu", "kernels.h", "ctx.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                        "-I", cuda_inc, "-I", CSRC, "-o", out, BX_SRC], check=True)
+    return C.CDLL(out)
+
+
+def box_dims(nx, ny, nz, rank, nranks):
+    """BoxDims as gpu_create_box_p1 (box.cu) computes it: z-slabs, one ghost layer of cells below."""
+    base, rem = divmod(nz, nranks)
+    L0 = rank * base + min(rank, rem)
+    L1 = L0 + base + (1 if rank < rem else 0)
+    last = rank == nranks - 1
+    nvp = (nx + 1) * (ny + 1)
+    l0 = L0 - 1 if rank > 0 else L0
+    G0, G1 = L0 * nvp, ((nz + 1) * nvp if last else L1 * nvp)
+    return np.array([nx, ny, nz, l0, L1, G0, G1, l0 * nvp, G1 if last else G1 + nvp], np.int64)
+
+
+@pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1),
+                                                    ("poisson", (4, 3, 5), 0, 2), ("poisson", (4, 3, 5), 1, 2),
+                                                    ("elasticity", (3, 3, 7), 1, 3), ("poisson", (3, 3, 7), 2, 3),
+                                                    ("poisson", (2, 7, 8), 5, 8)])
+def test_box_generator_source_equals_the_host_mesh_and_dofmap(pt, emubx, ptype, dims, rank, nranks):
+    """Vertices, cell -> vertex map, P1 dofmap and the dof -> vertex inverse from the generator
+    kernels equal the host stand-in's arrays bit for bit on every rank of a z-slab partition."""
+    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+    B = box_dims(*dims, rank, nranks)
+    x_ref = np.asarray(P["x"])
+    nv, nc = len(x_ref) // 3, len(P["x_dofmap"]) // 4
+    n = P.n_owned + P.n_ghost
+    assert int(B[6] - B[5]) == P.n_owned and int((B[5] - B[7]) + (B[8] - B[6])) == P.n_ghost
+    xyz3, xyz4 = np.full(nv * 3, np.nan), np.full(nv * 4, np.nan)
+    dv = np.full(n, -5, np.int32)
+    xd, dm = np.full(nc * 4, -5, np.int32), np.full(nc * 4, -5, np.int32)
+    assert emubx.emu_create_box_p1(_p(B), _p(xyz3), _p(xyz4), _p(dv), _p(xd), _p(dm)) == 0
+    assert np.array_equal(xyz3, x_ref)
+    assert np.array_equal(xyz4.reshape(-1, 4)[:, :3].reshape(-1), x_ref) and np.all(xyz4.reshape(-1, 4)[:, 3] == 0)
+    assert np.array_equal(xd, P["x_dofmap"]) and np.array_equal(dm, P["dofmap"])
+    # dof -> vertex is the inverse of the vertex dofs of the cells
+    inv = np.full(n, -1, np.int32)
+    inv[np.asarray(P["dofmap"])] = np.asarray(P["x_dofmap"])
+    assert np.array_equal(dv, inv)
