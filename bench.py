@@ -265,7 +265,13 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
     ctx = abi.Context(local_rank, stream=stream)
     t0 = time.perf_counter()
-    ctx.set_problem(P)
+    # opt-in (not yet run on a GPU): mesh, dofmap, pattern, Dirichlet dofs and
+    # sources generated on the device; with PTB_GPU_SETUP=1 the layouts and assembly maps too
+    device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1" and order == 1
+    if device_setup:
+        ctx.set_problem_on_device(P)
+    else:
+        ctx.set_problem(P)
     t_upload = time.perf_counter() - t0
     comm_used = "none"
     if world > 1:
@@ -435,7 +441,8 @@ def main():
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,
-            "setup_s": {"host_mesh_dofmap_pattern": t_host, "slot_map_and_upload": t_upload},
+            "setup_s": {"host_mesh_dofmap_pattern": t_host, "slot_map_and_upload": t_upload,
+                        "device_setup": device_setup},
             "device_bytes": ctx.device_bytes(),
         }
         print(json.dumps(line), flush=True)

@@ -20,6 +20,10 @@ echo "== P2/P3 matrix assembly: all slices vs row-length bins (2M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_pk_2M.json timeout 200 python performance-test_b200/tools/check_walk.py abpk 2000000 2>&1 | tail -2
 echo "== P1 assembly maps built on the host vs on the device (PTB_GPU_SETUP, 4M DOFs)"
 WALK_CHECK_OUT=first_call/setup_4M.json timeout 200 python performance-test_b200/tools/check_walk.py absetup 4000000 2>&1 | tail -2
+echo "== bench line with the whole P1 setup generated on the device (20M DOFs): setup_s and value against the default line"
+PTB_GPU_SETUP=1 PTB_BENCH_DEVICE_SETUP=1 timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
+  > "$out/bench_poisson20M_device_setup.json" 2> "$out/bench_poisson20M_device_setup.err"
+python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], 'value %.4g' % d['value'], d['setup_s'], d['stage_ms'], 'its', d['cg_iterations'])" "$out/bench_poisson20M_device_setup.json" || echo FAILED
 echo "== SpMV on the zero-compacted operator (Poisson 20M: the headline line), off / on"
 for z in "0 0" "1 0" "1 1e-14"; do
   set -- $z
