@@ -232,6 +232,13 @@ int ptb_debug_facet_rows(int64_t n_facets, const int32_t* cells, const int32_t* 
                          const int32_t* dofmap, int nd, int order, int32_t n_rows,
                          int32_t* n_frows, int32_t* n_ent, int32_t* row_ids, int32_t* row_ptr,
                          int32_t* ent);
+/* The same lists from the dofmap rows of the facets' cells only, gathered [n_facets * nd] with
+ * gathered[k*nd + j] = dofmap[cells[k]*nd + j] (the route ptb_set_exterior_facets takes when the
+ * dofmap was generated on the device). */
+int ptb_debug_facet_rows_gathered(int64_t n_facets, const int32_t* cells, const int32_t* local_facets,
+                         const int32_t* gathered, int nd, int order, int32_t n_rows,
+                         int32_t* n_frows, int32_t* n_ent, int32_t* row_ids, int32_t* row_ptr,
+                         int32_t* ent);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 /* Device time (CUDA events on the launching stream) of the last call of a stage, in ms. */

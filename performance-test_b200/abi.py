@@ -84,6 +84,7 @@ def lib():
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
         L.ptb_debug_facet_rows.argtypes = [i64, vp, vp, vp, C.c_int, C.c_int, i32, C.POINTER(i32),
                                            C.POINTER(i32), vp, vp, vp]
+        L.ptb_debug_facet_rows_gathered.argtypes = L.ptb_debug_facet_rows.argtypes
         L.ptb_debug_pk_layout.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
@@ -226,14 +227,16 @@ def pk_layout(dofmap, nd, n_owned, rowptr, cols):
                 n_bins=int(info[3]), n_slices=ns)
 
 
-def facet_rows(facet_cells, facet_local, dofmap, nd, order, n_rows):
-    """Host-only: (row_ids, row_ptr, ent) of the boundary-facet gather (ent = int32 pairs)."""
+def facet_rows(facet_cells, facet_local, dofmap, nd, order, n_rows, gathered=False):
+    """Host-only: (row_ids, row_ptr, ent) of the boundary-facet gather (ent = int32 pairs). With
+    gathered, `dofmap` holds only the rows of the facets' cells ([n_facets * nd])."""
     fc, fl, dm = _a(facet_cells, np.int32), _a(facet_local, np.int32), _a(dofmap, np.int32)
     ids, ptr = np.zeros(max(n_rows, 1), np.int32), np.zeros(n_rows + 1, np.int32)
     ent = np.zeros(max(20 * len(fc), 2), np.int32)
     nf, ne = C.c_int32(), C.c_int32()
-    rc = lib().ptb_debug_facet_rows(len(fc), _ptr(fc), _ptr(fl), _ptr(dm), nd, order, n_rows,
-                                    C.byref(nf), C.byref(ne), _ptr(ids), _ptr(ptr), _ptr(ent))
+    fn = lib().ptb_debug_facet_rows_gathered if gathered else lib().ptb_debug_facet_rows
+    rc = fn(len(fc), _ptr(fc), _ptr(fl), _ptr(dm), nd, order, n_rows,
+            C.byref(nf), C.byref(ne), _ptr(ids), _ptr(ptr), _ptr(ent))
     if rc != 0:
         raise RuntimeError(lib().ptb_last_error(None).decode())
     return ids[:nf.value].copy(), ptr[:nf.value + 1].copy(), ent[:2 * ne.value].copy()

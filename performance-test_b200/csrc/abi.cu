@@ -598,13 +598,29 @@ int ptb_set_exterior_facets(ptb_ctx* c, int64_t n_facets, const int32_t* cells,
   return guarded(c, [&] {
     use_device(c);
     need(c->have_space, "ptb_set_exterior_facets: call ptb_set_space first");
-    host_dofmap(c);
-    const std::vector<std::int32_t>& dm = c->h_dofmap;
     for (std::int64_t k = 0; k < n_facets; ++k)
       need(cells[k] >= 0 && cells[k] < c->n_cells, "exterior facet: cell index out of range");
     std::vector<std::int32_t> ids, ptr, ent;
-    build_facet_rows(n_facets, cells, local_facets, dm.data(), c->nd, c->order, c->n_owned, ids,
-                     ptr, ent);
+    if (c->h_dofmap.empty() && n_facets > 0)
+    {
+      // the dofmap was generated on the device (ptb_create_box_p1): fetch the rows of the facets'
+      // cells only -- surface-sized, not the whole map
+      DevBuf<std::int32_t> d_cells, d_rows;
+      d_cells.upload(cells, static_cast<std::size_t>(n_facets), c->stream);
+      d_rows.alloc(static_cast<std::size_t>(n_facets) * c->nd);
+      launch_gather_dofmap_rows(c, n_facets, d_cells.p, d_rows.p);
+      std::vector<std::int32_t> rows(d_rows.n);
+      PTB_CUDA(cudaMemcpyAsync(rows.data(), d_rows.p, d_rows.bytes(), cudaMemcpyDeviceToHost, c->stream));
+      PTB_CUDA(cudaStreamSynchronize(c->stream));
+      build_facet_rows_gathered(n_facets, cells, local_facets, rows.data(), c->nd, c->order, c->n_owned, ids,
+                                ptr, ent);
+    }
+    else
+    {
+      host_dofmap(c);
+      build_facet_rows(n_facets, cells, local_facets, c->h_dofmap.data(), c->nd, c->order, c->n_owned, ids,
+                       ptr, ent);
+    }
     c->n_frows = static_cast<std::int32_t>(ids.size());
     c->frow_ids.upload(ids, c->stream);
     c->frow_ptr.upload(ptr, c->stream);
@@ -1209,6 +1225,25 @@ int ptb_debug_facet_rows(int64_t n_facets, const int32_t* cells, const int32_t* 
     std::vector<std::int32_t> ids, ptr, e;
     build_facet_rows(n_facets, cells, local_facets, dofmap, nd, order, n_rows, ids, ptr, e);
     need(e.size() <= static_cast<std::size_t>(20) * n_facets, "ptb_debug_facet_rows: capacity");
+    *n_frows = static_cast<std::int32_t>(ids.size());
+    *n_ent = static_cast<std::int32_t>(e.size() / 2);
+    std::copy(ids.begin(), ids.end(), row_ids);
+    std::copy(ptr.begin(), ptr.end(), row_ptr);
+    std::copy(e.begin(), e.end(), ent);
+  });
+}
+
+int ptb_debug_facet_rows_gathered(int64_t n_facets, const int32_t* cells, const int32_t* local_facets,
+                                  const int32_t* gathered, int nd, int order, int32_t n_rows,
+                                  int32_t* n_frows, int32_t* n_ent, int32_t* row_ids, int32_t* row_ptr,
+                                  int32_t* ent)
+{
+  return guarded(nullptr, [&] {
+    need(cells && local_facets && gathered && n_frows && n_ent && row_ids && row_ptr && ent,
+         "ptb_debug_facet_rows_gathered: NULL argument");
+    std::vector<std::int32_t> ids, ptr, e;
+    build_facet_rows_gathered(n_facets, cells, local_facets, gathered, nd, order, n_rows, ids, ptr, e);
+    need(e.size() <= static_cast<std::size_t>(20) * n_facets, "ptb_debug_facet_rows_gathered: capacity");
     *n_frows = static_cast<std::int32_t>(ids.size());
     *n_ent = static_cast<std::int32_t>(e.size() / 2);
     std::copy(ids.begin(), ids.end(), row_ids);

@@ -78,9 +78,29 @@ __global__ void box_cells_p1(BoxDims B, std::int32_t* __restrict__ x_dofmap, std
     }
 }
 
+// the dofmap rows of a list of cells (thread per entry): what the host needs of a device-generated
+// dofmap to build the exterior-facet row lists
+__global__ void gather_dofmap_rows(std::int64_t n, int nd, const std::int32_t* __restrict__ cells,
+                                   const std::int32_t* __restrict__ dofmap, std::int32_t* __restrict__ out)
+{
+  const std::int64_t i = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  if (i >= n * nd)
+    return;
+  out[i] = dofmap[static_cast<std::int64_t>(cells[i / nd]) * nd + i % nd];
+}
+
 } // namespace
 
 #ifndef PTB_HOST_EMU // host side: device build only
+void launch_gather_dofmap_rows(ptb_ctx* c, std::int64_t n, const std::int32_t* cells, std::int32_t* out)
+{
+  const std::int64_t t = n * c->nd;
+  gather_dofmap_rows<<<static_cast<unsigned>((t + BX_THREADS - 1) / BX_THREADS), BX_THREADS, 0, c->stream>>>(
+      n, c->nd, cells, c->dofmap.p, out);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+}
+
 // Generates the local slab of rank `rank` of `nranks` on the device and fills what ptb_set_mesh and
 // the mesh-dependent half of ptb_set_space fill: n_vertices, n_cells, x_dofmap, xyz3, xyz, n_owned,
 // n_ghost, dofmap, dof_vertex. Two launches.

@@ -107,6 +107,8 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
 
 /// The local z-slab of the unit-cube Kuhn mesh and its P1 dofmap generated on the device (box.cu).
 void gpu_create_box_p1(ptb_ctx* c, std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);
+/// out[k*nd + j] = dofmap[cells[k]*nd + j] for the n listed cells (box.cu).
+void launch_gather_dofmap_rows(ptb_ctx* c, std::int64_t n, const std::int32_t* cells, std::int32_t* out);
 /// Device-side problem data (problem_data.cu): Dirichlet markers from the reference's facet predicate
 /// + facet closure into c->bc; the source terms at the dof coordinates X (stride 3 or 4) into c->f, c->g.
 void launch_locate_bc(ptb_ctx* c);

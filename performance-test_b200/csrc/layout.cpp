@@ -455,4 +455,19 @@ void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
   }
 }
 
+void build_facet_rows_gathered(std::int64_t n_facets, const std::int32_t* cells,
+                               const std::int32_t* local_facets, const std::int32_t* gathered, int nd,
+                               int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
+                               std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent)
+{
+  // facet k plays the role of "cell k" of the gathered rows; the entries keep the facet order, so
+  // putting the real cell index back afterwards gives build_facet_rows' lists exactly
+  std::vector<std::int32_t> k(static_cast<std::size_t>(n_facets));
+  for (std::int64_t i = 0; i < n_facets; ++i)
+    k[i] = static_cast<std::int32_t>(i);
+  build_facet_rows(n_facets, k.data(), local_facets, gathered, nd, order, n_rows, row_ids, row_ptr, ent);
+  for (std::size_t i = 0; i < ent.size(); i += 2)
+    ent[i] = cells[ent[i]];
+}
+
 } // namespace ptb

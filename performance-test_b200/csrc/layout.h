@@ -93,4 +93,12 @@ void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
                       int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
                       std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent);
 
+/// The same lists from the dofmap rows of the facets' cells only (gathered[k*nd + j] =
+/// dofmap[cells[k]*nd + j]): what a context whose dofmap lives on the device downloads instead of
+/// the whole dofmap.
+void build_facet_rows_gathered(std::int64_t n_facets, const std::int32_t* cells,
+                               const std::int32_t* local_facets, const std::int32_t* gathered, int nd,
+                               int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
+                               std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent);
+
 } // namespace ptb

@@ -50,4 +50,11 @@ int emu_create_box_p1(const int64_t* dims, double* xyz3, double* xyz4, int32_t* 
   emu_launch(box_cells_p1, B.nx * B.ny * (B.l1 - B.l0), BX_THREADS, B, x_dofmap, dofmap);
   return 0;
 }
+
+int emu_gather_dofmap_rows(int64_t n, int nd, const int32_t* cells, const int32_t* dofmap, int32_t* out)
+{
+  using namespace ptb;
+  emu_launch(gather_dofmap_rows, n * nd, BX_THREADS, n, nd, cells, dofmap, out);
+  return 0;
+}
 }

@@ -813,3 +813,19 @@ def test_box_generator_source_equals_the_host_mesh_and_dofmap(pt, emubx, ptype, 
     inv = np.full(n, -1, np.int32)
     inv[np.asarray(P["dofmap"])] = np.asarray(P["x_dofmap"])
     assert np.array_equal(dv, inv)
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (4, 3, 5), 1, 2),
+                                                          ("poisson", 2, (3, 2, 4), 0, 1), ("poisson", 3, (2, 3, 2), 1, 2)])
+def test_facet_rows_from_gathered_dofmap_rows(pt, emubx, ptype, order, dims, rank, nranks):
+    """A context whose dofmap lives on the device downloads the rows of the exterior facets' cells
+    only (gather kernel) and builds the same boundary-facet row lists from them."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    fc = np.ascontiguousarray(P["facet_cells"], np.int32)
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rows = np.full(len(fc) * P.nd, -3, np.int32)
+    assert emubx.emu_gather_dofmap_rows(C.c_int64(len(fc)), P.nd, _p(fc), _p(dm), _p(rows)) == 0
+    assert np.array_equal(rows, dm.reshape(-1, P.nd)[fc].reshape(-1))
+    ref = pt.abi.facet_rows(fc, P["facet_local"], dm, P.nd, order, P.n_owned)
+    got = pt.abi.facet_rows(fc, P["facet_local"], rows, P.nd, order, P.n_owned, gathered=True)
+    assert all(np.array_equal(a, b) for a, b in zip(ref, got)) and len(ref[0]) > 0
