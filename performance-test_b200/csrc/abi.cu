@@ -345,7 +345,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     SellLayout L;
     // The adjacency side (cell lists, slot words, star walk) comes from the host build below or,
     // opt-in for P1, from the device (setup.cu); the column side is always laid out here.
-    bool dev_maps = gpu_setup_enabled() && c->nd == 4 && !gwalk_enabled();
+    bool dev_maps = gpu_setup_enabled() && !gwalk_enabled();
     auto host_layout = [&](bool with_adjacency) {
       std::int64_t max_so = 0;
       if (with_adjacency)
@@ -391,10 +391,17 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       // express (missing pair, offsets beyond a byte, a star of more than 64 cells) falls back to
       // the host build, which also owns the error messages.
       int max_wa = 0;
-      if (L.max_w < 255 && gpu_setup_p1(c, want_walk(), &max_wa))
+      if (c->nd == 4 && L.max_w < 255 && gpu_setup_p1(c, want_walk(), &max_wa))
       {
         c->max_wa = max_wa;
         c->adj.release(), c->adjso.release();
+        c->maps_on_device = true;
+      }
+      else if (c->nd != 4 && L.max_w <= 256 && gpu_setup_pk(c, &max_wa))
+      {
+        // P2/P3: 8-bit offsets, as the host chooses for rows of at most 256 columns
+        c->max_wa = max_wa;
+        c->adjrot.release();
         c->maps_on_device = true;
       }
       else

@@ -96,6 +96,8 @@ void compact_operator(ptb_ctx* c);
 /// c->adj_off, c->adjrot and, if want_walk, c->walk from the uploaded dofmap, rowptr, mat_off and
 /// padded columns. Returns false when the pattern cannot be expressed (the caller builds on the host).
 bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
+/// The same for P2/P3: c->adj_off, c->adj, c->adjso with 8-bit offsets (rows of at most 256 columns).
+bool gpu_setup_pk(ptb_ctx* c, int* max_wa);
 /// The sparsity pattern of the owned rows built on the device from the uploaded dofmap (setup.cu) and
 /// downloaded; false when a row is too long for the device build.
 /// rp / cl keep the device copies (CSR).

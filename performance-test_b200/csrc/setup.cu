@@ -357,6 +357,62 @@ __global__ void setup_pattern_fill(std::int32_t n_rows, int nd, const std::int32
     out[k] = list[k];
 }
 
+// P2/P3 form of the slot map: adj = the pair itself (cell * nd + local index), adjso = the nd in-row
+// offsets of the cell's dofs packed so_bits wide (layout.cpp build_sell_layout). thread = (slice, lane).
+__global__ void setup_adj_pk(std::int32_t n_rows, std::int32_t n_slices, int nd, int so_bits,
+                             const std::int32_t* __restrict__ dofmap, const std::int64_t* __restrict__ rowptr,
+                             const std::int64_t* __restrict__ mat_off, const std::int32_t* __restrict__ cols_sell,
+                             const std::int64_t* __restrict__ ptr, const std::uint32_t* __restrict__ pairs,
+                             const std::int64_t* __restrict__ adj_off, std::uint32_t* __restrict__ adj,
+                             std::uint32_t* __restrict__ adjso, int* __restrict__ flags)
+{
+  const std::int64_t t = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  const std::int32_t s = static_cast<std::int32_t>(t >> 5);
+  const int lane = static_cast<int>(t & 31);
+  if (s >= n_slices)
+    return;
+  const std::int32_t r = 32 * s + lane;
+  const bool live = r < n_rows;
+  const std::int64_t ao = adj_off[s], mo = mat_off[s];
+  const int wa = static_cast<int>((adj_off[s + 1] - ao) >> 5);
+  const int len = live ? static_cast<int>(rowptr[r + 1] - rowptr[r]) : 0;
+  const int alen = live ? static_cast<int>(ptr[r + 1] - ptr[r]) : 0;
+  const int per_word = 32 / so_bits, so_words = (nd + per_word - 1) / per_word;
+  const std::int32_t* rc = cols_sell + mo + lane; // entry k at rc[k * 32]
+  for (int k = 0; k < wa; ++k)
+  {
+    const bool on = k < alen;
+    const std::uint32_t pair = on ? pairs[ptr[r] + k] : ADJ_INVALID_DEV;
+    adj[ao + static_cast<std::int64_t>(k) * 32 + lane] = pair;
+    const std::int64_t cell = pair / static_cast<std::uint32_t>(nd);
+    for (int wd = 0; wd < so_words; ++wd)
+    {
+      std::uint32_t word = 0;
+      if (on)
+        for (int q = 0; q < per_word; ++q)
+        {
+          const int j = wd * per_word + q;
+          if (j >= nd)
+            break;
+          const std::int32_t col = dofmap[cell * nd + j];
+          int lo = 0, hi = len; // lower_bound over the row's columns
+          while (lo < hi)
+          {
+            const int mid = (lo + hi) >> 1;
+            if (rc[mid * 32] < col)
+              lo = mid + 1;
+            else
+              hi = mid;
+          }
+          if (lo >= len || rc[lo * 32] != col || lo >= (1 << so_bits))
+            flags[0] = 1;
+          word |= static_cast<std::uint32_t>(lo) << (q * so_bits);
+        }
+      adjso[(ao + static_cast<std::int64_t>(k) * 32) * so_words + wd * 32 + lane] = word;
+    }
+  }
+}
+
 // The greedy star walk of layout.cpp build_walk: start at the row's first cell; next = the
 // unvisited cell sharing most vertices with the current one, ties to the earlier cell; vertices
 // that stay keep their register position, new ones take the freed positions in ascending order,
@@ -568,6 +624,46 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
   // the kernels read rowptr from the context: take the device copy over instead of re-uploading it
   std::swap(c->rowptr.p, rp.p);
   std::swap(c->rowptr.n, rp.n);
+}
+
+// P2/P3: adj_off, adj and adjso on the device (so_bits = 8: rows of at most 256 columns). Returns
+// false when the pattern does not cover a cell (the host build then reports it).
+bool gpu_setup_pk(ptb_ctx* c, int* max_wa)
+{
+  const std::int32_t N = c->n_owned, S = c->n_slices;
+  const int so_bits = 8, so_words = (c->nd + 3) / 4;
+  DevBuf<unsigned long long> wa;
+  DevBuf<std::int64_t> ptr;
+  DevBuf<std::uint32_t> pairs;
+  DevBuf<int> flags;
+  build_pairs(c, ptr, pairs);
+  flags.alloc(2);
+  flags.zero(c->stream);
+  wa.alloc(static_cast<std::size_t>(S));
+  setup_widths<<<(S + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, wa.p);
+  c->adj_off.alloc(static_cast<std::size_t>(S) + 1);
+  setup_scan<<<1, 1024, 0, c->stream>>>(S, wa.p, c->adj_off.p, 32);
+  std::int64_t n_adj = 0;
+  PTB_CUDA(cudaMemcpyAsync(&n_adj, c->adj_off.p + S, sizeof(n_adj), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<unsigned long long> h_wa(static_cast<std::size_t>(S));
+  PTB_CUDA(cudaMemcpyAsync(h_wa.data(), wa.p, h_wa.size() * sizeof(unsigned long long),
+                           cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  *max_wa = 0;
+  for (unsigned long long v : h_wa)
+    *max_wa = std::max(*max_wa, static_cast<int>(v));
+  c->adj.alloc(static_cast<std::size_t>(n_adj));
+  c->adjso.alloc(static_cast<std::size_t>(n_adj) * so_words);
+  const int gl = static_cast<int>((static_cast<std::int64_t>(S) * 32 + SU_THREADS - 1) / SU_THREADS);
+  setup_adj_pk<<<gl, SU_THREADS, 0, c->stream>>>(N, S, c->nd, so_bits, c->dofmap.p, c->rowptr.p, c->mat_off.p,
+                                                 c->cols.p, ptr.p, pairs.p, c->adj_off.p, c->adj.p, c->adjso.p,
+                                                 flags.p);
+  PTB_CUDA(cudaGetLastError());
+  int h_flags[2] = {0, 0};
+  PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
+  PTB_CUDA(cudaStreamSynchronize(c->stream));
+  c->launches += 3;
+  return h_flags[0] == 0;
 }
 
 bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)

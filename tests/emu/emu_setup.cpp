@@ -144,6 +144,31 @@ int emu_setup_columns(int32_t n_rows, int64_t n_cols, int32_t n_slices, const in
   return 0;
 }
 
+// The launch sequence of gpu_setup_pk (setup.cu): adj_off always; adj (capacity cap) and adjso
+// (capacity cap * so_words) when the total fits (returns -1 otherwise).
+int emu_setup_pk(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_rows, int32_t n_slices,
+                 const int64_t* rowptr, const int64_t* mat_off, const int32_t* cols_sell, int64_t cap,
+                 int64_t* adj_off, uint32_t* adj, uint32_t* adjso, int* flags)
+{
+  using namespace ptb;
+  std::vector<unsigned long long> wa(static_cast<std::size_t>(n_slices), 0);
+  std::vector<std::int64_t> ptr;
+  std::vector<std::uint32_t> pairs;
+  emu_pairs(n_cells * nd, dofmap, n_rows, 1, ptr, pairs);
+  emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
+             (const std::int64_t*)ptr.data(), wa.data());
+  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off,
+             static_cast<std::int64_t>(32));
+  if (adj_off[n_slices] > cap)
+    return -1;
+  flags[0] = flags[1] = 0;
+  const unsigned gl = static_cast<unsigned>((static_cast<std::int64_t>(n_slices) * 32 + SU_THREADS - 1) / SU_THREADS);
+  emu_launch(setup_adj_pk, gl, SU_THREADS, n_rows, n_slices, nd, 8, dofmap, rowptr, mat_off, cols_sell,
+             (const std::int64_t*)ptr.data(), (const std::uint32_t*)pairs.data(), (const std::int64_t*)adj_off, adj,
+             adjso, flags);
+  return 0;
+}
+
 // The launch sequence of gpu_setup_p1 (setup.cu) with host vectors in place of the device buffers.
 // adj_off [n_slices + 1] is always written; adjrot / walk hold `cap` words each and are written
 // when the device-side total fits (returns -1 otherwise). flags[0..1] as in setup.cu.

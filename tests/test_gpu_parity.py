@@ -499,6 +499,28 @@ def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol
 
 
 @OPTIN
+@pytest.mark.parametrize("order,dims", [(2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)), (3, (6, 5, 7))])
+def test_opt_in_device_setup_p2_p3_slot_words(pt, oracle, monkeypatch, order, dims):
+    """PTB_GPU_SETUP=1 for P2/P3: pair words and packed slot offsets built by setup_adj_pk; the
+    assembled matrix and vector match the oracle (the words themselves are compared with the host
+    build on the CPU by tests/test_kernel_sources_on_host.py)."""
+    P = pt.host.Problem("poisson", order, *dims)
+    monkeypatch.setenv("PTB_GPU_SETUP", "1")
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P)
+        c.assemble_matrix()
+        c.assemble_vector()
+        _check_matrix(P, c.matrix_values(), oracle.assemble_matrix(P))
+        b_ref = oracle.assemble_vector(P)
+        assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        with pytest.raises(RuntimeError, match="built on the device"):
+            c.slot_offsets()
+    finally:
+        c.close()
+
+
+@OPTIN
 @pytest.mark.parametrize("ptype,dims", [("poisson", (5, 4, 6)), ("poisson", (1, 1, 1)), ("poisson", (33, 2, 1)),
                                         ("poisson", (40, 38, 41)), ("elasticity", (12, 11, 13))])
 def test_opt_in_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype, dims):

@@ -829,3 +829,26 @@ def test_facet_rows_from_gathered_dofmap_rows(pt, emubx, ptype, order, dims, ran
     ref = pt.abi.facet_rows(fc, P["facet_local"], dm, P.nd, order, P.n_owned)
     got = pt.abi.facet_rows(fc, P["facet_local"], rows, P.nd, order, P.n_owned, gathered=True)
     assert all(np.array_equal(a, b) for a, b in zip(ref, got)) and len(ref[0]) > 0
+
+
+@pytest.mark.parametrize("order,dims,rank,nranks", [(2, (3, 2, 4), 0, 1), (2, (2, 2, 5), 1, 2), (3, (2, 3, 2), 0, 1),
+                                                    (3, (2, 2, 4), 2, 3)])
+def test_device_setup_source_builds_the_p2_p3_slot_words(pt, emusu, order, dims, rank, nranks):
+    """adj_off, the pair words and the packed 8-bit slot offsets of the P2/P3 assembly kernels from
+    setup_adj_pk equal layout.cpp's build_sell_layout word for word (pairs reversed before the sort)."""
+    P = pt.host.Problem("poisson", order, *dims, rank, nranks)
+    L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+    assert L["so_bits"] == 8 and L["so_words"] == (P.nd + 3) // 4
+    S, cap = L["n_slices"], int(L["adj_off"][-1])
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rp = np.ascontiguousarray(P["rowptr"], np.int64)
+    adj_off = np.full(S + 1, -1, np.int64)
+    adj = np.full(cap, 0xDEADBEEF, np.uint32)
+    adjso = np.full(cap * L["so_words"], 0xDEADBEEF, np.uint32)
+    flags = np.full(2, -1, np.int32)
+    rc = emusu.emu_setup_pk(C.c_int64(len(dm) // P.nd), P.nd, _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]),
+                            _p(L["cols"]), C.c_int64(cap), _p(adj_off), _p(adj), _p(adjso), _p(flags))
+    assert rc == 0 and flags.tolist() == [0, 0]
+    assert np.array_equal(adj_off, L["adj_off"])
+    assert np.array_equal(adj, L["adj"])
+    assert np.array_equal(adjso, L["adjso"])
