@@ -1,14 +1,15 @@
 #!/usr/bin/env bash
 # First GPU job after a round that ended with untested opt-in kernels:
-# parity first, then A/B timings. Everything lands in gpurun_out/first_call/. One GPU, ~3 minutes.
-#   gpurun --timeout 400 -- 'bash performance-test_b200/tools/first_gpu_call.sh'
+# parity first, then A/B timings. Everything lands in gpurun_out/first_call/. One GPU, ~12 minutes
+# (the parity tests are the first two; every later step has its own timeout and can be cut).
+#   gpurun --timeout 1200 -- 'bash performance-test_b200/tools/first_gpu_call.sh'
 set -u
 cd "$(dirname "$0")/../.."
 out=gpurun_out/first_call
 mkdir -p "$out"
 export PTB_TEST_OPTIN=1
 echo "== opt-in parity tests"
-timeout 300 python -m pytest tests/test_gpu_parity.py -q -s -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -25 | tee "$out/optin_tests.txt"
+timeout 400 python -m pytest tests/test_gpu_parity.py -q -s -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -40 | tee "$out/optin_tests.txt"
 echo "== assembly A/B (4M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
 echo "== ncu --set full of the direct-gather kernels (Poisson 4M): read it with tools/ncu_summary.py"
