@@ -495,27 +495,42 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
       build_pattern(c->h_dofmap.data(), c->nd, c->n_owned, adj, rowptr, cols);
       return;
     }
-    if (!(gpu_setup_enabled() && c->nd == 4 && !gwalk_enabled()))
+    if (!(gpu_setup_enabled() && !gwalk_enabled()))
       return;
-    // P1 with PTB_GPU_SETUP=1: the pattern never leaves the device on its way into the layouts --
-    // column side (setup.cu gpu_setup_columns) and adjacency side (gpu_setup_p1) are built there;
-    // this is ptb_set_pattern without its host loops.
+    // PTB_GPU_SETUP=1: the pattern never leaves the device on its way into the layouts -- column
+    // side (setup.cu gpu_setup_columns) and adjacency side (gpu_setup_p1 / gpu_setup_pk) are built
+    // there; this is ptb_set_pattern without its host loops.
     c->nnz = rowptr[c->n_owned];
-    gpu_setup_columns(c, rp, cl);
+    SellLayout L; // host side keeps the slice offsets only
+    gpu_setup_columns(c, rp, cl, L.mat_off);
+    L.n_slices = c->n_slices, L.max_w = c->max_w;
     const bool want_walk
         = (c->bs == 1 && walk_enabled() && c->max_w <= 32) || (c->bs == 3 && walk3_enabled());
     int max_wa = 0;
     c->walk.release();
-    if (c->max_w >= 255 || !gpu_setup_p1(c, want_walk, &max_wa))
-      return; // not expressible in one-byte offsets: ptb_set_pattern below rebuilds everything
+    c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
+    if (c->nd == 4)
+    {
+      if (c->max_w >= 255 || !gpu_setup_p1(c, want_walk, &max_wa))
+        return; // not expressible in one-byte offsets: ptb_set_pattern below rebuilds everything
+      c->adj.release(), c->adjso.release();
+    }
+    else
+    {
+      if (c->max_w > 256 || !gpu_setup_pk(c, &max_wa))
+        return;
+      c->adjrot.release();
+      // width classes for the binned P2/P3 matrix kernel (assemble_pk.cu)
+      std::vector<std::int32_t> list;
+      build_width_bins(L, list, c->pk_bin_off, c->pk_bin_w);
+      c->pk_bin_slices.upload(list, c->stream);
+    }
     c->max_wa = max_wa;
-    c->so_bits = 8, c->so_words = 1;
+    c->so_bits = 8, c->so_words = (c->nd + 3) / 4;
     c->h_rowptr = rowptr;
     c->h_adj.ptr.assign(static_cast<std::size_t>(c->n_owned) + 1, 0);
     c->h_adj.pairs.clear(), c->h_so.clear();
-    c->adj.release(), c->adjso.release();
     c->walk1.release(), c->walk1_off.release();
-    c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
     c->walk_loads_per_step = 0.0;
     c->vals.alloc(c->cols.n * c->bs * c->bs);
     c->vals.zero(c->stream);

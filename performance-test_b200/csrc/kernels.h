@@ -104,8 +104,9 @@ bool gpu_setup_pk(ptb_ctx* c, int* max_wa);
 bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vector<std::int32_t>& cols,
                        DevBuf<std::int64_t>& rp, DevBuf<std::int32_t>& cl);
 /// Column side of ptb_set_pattern (SELL-32 offsets and padded columns, column compression, slice
-/// order) from a CSR pattern on the device; takes rp over as c->rowptr.
-void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl);
+/// order) from a CSR pattern on the device; takes rp over as c->rowptr. h_mat_off = host copy of mat_off.
+void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl,
+                       std::vector<std::int64_t>& h_mat_off);
 
 /// The local z-slab of the unit-cube Kuhn mesh and its P1 dofmap generated on the device (box.cu).
 void gpu_create_box_p1(ptb_ctx* c, std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);

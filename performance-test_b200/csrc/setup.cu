@@ -570,7 +570,8 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
 // The column side of ptb_set_pattern from a CSR pattern that is already on the device: c->rowptr,
 // mat_off, cols (SELL-32, padded), for scalar problems cdelta / colsx / xoff, and the slice order.
 // Sets n_slices, max_w, cols_explicit_frac, n_interior_slices. Eight launches (five for bs = 3).
-void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl)
+void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl,
+                       std::vector<std::int64_t>& h_mat_off)
 {
   const std::int32_t N = c->n_owned, S = (N + 31) / 32;
   const std::int64_t n_cols = static_cast<std::int64_t>(N) + c->n_ghost;
@@ -589,8 +590,12 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
                            c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
   c->max_w = 0;
-  for (unsigned long long v : h_w)
-    c->max_w = std::max(c->max_w, static_cast<int>(v));
+  h_mat_off.assign(static_cast<std::size_t>(S) + 1, 0); // host copy of the offsets (O(n_slices))
+  for (std::int32_t s = 0; s < S; ++s)
+  {
+    c->max_w = std::max(c->max_w, static_cast<int>(h_w[s]));
+    h_mat_off[s + 1] = h_mat_off[s] + 32 * static_cast<std::int64_t>(h_w[s]);
+  }
   c->cols.alloc(static_cast<std::size_t>(n_sell));
   setup_sell_cols<<<gl, SU_THREADS, 0, c->stream>>>(N, S, rp.p, cl.p, c->mat_off.p, c->cols.p);
   c->launches += 3;
