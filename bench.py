@@ -267,7 +267,7 @@ def main():
     t0 = time.perf_counter()
     # opt-in (not yet run on a GPU): mesh, dofmap, pattern, Dirichlet dofs and
     # sources generated on the device; with PTB_GPU_SETUP=1 the layouts and assembly maps too
-    device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1" and order == 1
+    device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1"
     if device_setup:
         ctx.set_problem_on_device(P)
     else:

@@ -57,18 +57,20 @@ int ptb_set_mesh(ptb_ctx* ctx, int64_t n_vertices, const double* x, int64_t n_ce
  * size bs (1 Poisson, 3 elasticity), dofmap[n_cells * nd] local block indices. */
 int ptb_set_space(ptb_ctx* ctx, int problem, int order, int bs, int32_t n_owned, int32_t n_ghost,
                   const int32_t* dofmap);
-/* "ZZZ Create Mesh" + "ZZZ FunctionSpace" on the device for the reference's unit cube at order 1
+/* "ZZZ Create Mesh" + "ZZZ FunctionSpace" on the device for the reference's unit cube
  * (mesh.cpp:184-186 mesh::create_box(tetrahedron); poisson_problem.cpp:33-47,
  * elasticity_problem.cpp:100-112): replaces ptb_set_mesh + ptb_set_space. nx x ny x nz cubes, six
  * tetrahedra each; rank owns a z-slab of cube layers plus one ghost layer of cells below it (the
- * shared_vertex ghost mode the row-owner assembly needs); P1 dofs are the vertices, owned planes
- * first, then the ghost plane below, then the ghost plane above. sizes receives n_vertices,
- * n_cells, n_owned, n_ghost. ptb_get_mesh / ptb_get_dofmap copy the arrays back (x [n_vertices*3],
- * x_dofmap [n_cells*4], dofmap [n_cells*4]; any may be NULL). */
-int ptb_create_box_p1(ptb_ctx* ctx, int problem, int bs, int64_t nx, int64_t ny, int64_t nz, int rank,
-                      int nranks, int64_t sizes[4]);
+ * shared_vertex ghost mode the row-owner assembly needs); Lagrange order 1..3, dofs numbered
+ * level-major by entity kind: owned levels first, then the ghost level below, then the ghost plane
+ * above. sizes receives n_vertices, n_cells, n_owned, n_ghost. ptb_get_mesh / ptb_get_dofmap /
+ * ptb_get_dof_coordinates copy the arrays back (x [n_vertices*3], x_dofmap [n_cells*4], dofmap
+ * [n_cells*nd], dof_x [(n_owned+n_ghost)*3]; any may be NULL). */
+int ptb_create_box(ptb_ctx* ctx, int problem, int bs, int order, int64_t nx, int64_t ny, int64_t nz,
+                   int rank, int nranks, int64_t sizes[4]);
 int ptb_get_mesh(ptb_ctx* ctx, double* x, int32_t* x_dofmap);
 int ptb_get_dofmap(ptb_ctx* ctx, int32_t* dofmap);
+int ptb_get_dof_coordinates(ptb_ctx* ctx, double* dof_x);
 /* Sparsity pattern of the owned rows (fem::create_sparsity_pattern / create_matrix,
  * poisson_problem.cpp:122-123). Builds the cell -> CSR-slot map and the device layout. */
 int ptb_set_pattern(ptb_ctx* ctx, const int64_t* rowptr, const int32_t* cols);
@@ -98,7 +100,7 @@ int ptb_set_source(ptb_ctx* ctx, const double* f, const double* g);
 /* "ZZZ Create RHS function" on the device (poisson_problem.cpp:82-108, elasticity_problem.cpp:150-178):
  * evaluates the reference's interpolation lambdas at the dof coordinates and replaces ptb_set_source.
  * dof_x [(n_owned+n_ghost)*3] = V->tabulate_dof_coordinates(); NULL for order 1, where the dofs sit
- * on the vertices the context already holds. ptb_get_source copies f [(n_owned+n_ghost)*bs] and g
+ * on the vertices the context already holds, and for a space generated by ptb_create_box. ptb_get_source copies f [(n_owned+n_ghost)*bs] and g
  * [(n_owned+n_ghost)] (Poisson; may be NULL) back. */
 int ptb_interpolate_source(ptb_ctx* ctx, const double* dof_x);
 int ptb_get_source(ptb_ctx* ctx, double* f, double* g);

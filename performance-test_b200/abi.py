@@ -47,7 +47,8 @@ def lib():
         L.ptb_update_geometry.argtypes = [vp, vp]
         L.ptb_set_space.argtypes = [vp, C.c_int, C.c_int, C.c_int, i32, i32, vp]
         L.ptb_set_pattern.argtypes = [vp, vp, vp]
-        L.ptb_create_box_p1.argtypes = [vp, C.c_int, C.c_int, i64, i64, i64, C.c_int, C.c_int, vp]
+        L.ptb_create_box.argtypes = [vp, C.c_int, C.c_int, C.c_int, i64, i64, i64, C.c_int, C.c_int, vp]
+        L.ptb_get_dof_coordinates.argtypes = [vp, vp]
         L.ptb_get_mesh.argtypes = [vp, vp, vp]
         L.ptb_get_dofmap.argtypes = [vp, vp]
         L.ptb_build_pattern.argtypes = [vp, C.POINTER(i64)]
@@ -326,16 +327,15 @@ class Context:
                 _ptr(_a(P["recv_displ"], np.int32)), _ptr(_a(P["remote_indices"], np.int32))))
 
     def set_problem_on_device(self, P):
-        """The whole setup of a P1 problem generated on the device: mesh and
-        dofmap (ptb_create_box_p1), pattern and layouts (ptb_build_pattern; with PTB_GPU_SETUP=1
+        """The whole setup of a problem generated on the device: mesh and
+        dofmap (ptb_create_box), pattern and layouts (ptb_build_pattern; with PTB_GPU_SETUP=1
         also the assembly maps), Dirichlet dofs, source terms. Only the surface-sized lists (exterior
         facets, halo) come from the host problem P, which also names the box and the rank."""
-        assert P.order == 1
         self.P = P
         self.bs, self.nd = P.bs, P.nd
         sizes = np.zeros(4, dtype=np.int64)
-        self._check(lib().ptb_create_box_p1(self._h, PROBLEMS[P.problem_type], P.bs, P.nx, P.ny, P.nz,
-                                            P.rank, P.nranks, _ptr(sizes)))
+        self._check(lib().ptb_create_box(self._h, PROBLEMS[P.problem_type], P.bs, P.order, P.nx, P.ny, P.nz,
+                                         P.rank, P.nranks, _ptr(sizes)))
         self.n_vertices, self.n_cells, self.n_owned, self.n_ghost = (int(v) for v in sizes)
         nnz = C.c_int64()
         self._check(lib().ptb_build_pattern(self._h, C.byref(nnz)))
@@ -361,6 +361,11 @@ class Context:
         dm = np.empty(self.n_cells * self.nd, dtype=np.int32)
         self._check(lib().ptb_get_dofmap(self._h, _ptr(dm)))
         return dm
+
+    def dof_coordinates(self):
+        x = np.empty((self.n_owned + self.n_ghost) * 3, dtype=np.float64)
+        self._check(lib().ptb_get_dof_coordinates(self._h, _ptr(x)))
+        return x
 
     def set_source(self, f, g=None):
         f = _a(f, np.float64)

@@ -64,7 +64,7 @@ std::int64_t n_local_entries(const ptb_ctx* c)
   return (static_cast<std::int64_t>(c->n_owned) + c->n_ghost) * c->bs;
 }
 // The host copy of the dofmap (integer maps built on the host); a space generated on the device
-// (ptb_create_box_p1) has none until someone asks.
+// (ptb_create_box) has none until someone asks.
 void host_dofmap(ptb_ctx* c)
 {
   if (!c->h_dofmap.empty())
@@ -243,6 +243,7 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
     c->n_owned = n_owned, c->n_ghost = n_ghost;
     need(static_cast<std::uint64_t>(c->n_cells) * c->nd <= 0xFFFFFFFEull,
          "ptb_set_space: n_cells * nd exceeds the 32-bit pair index");
+    c->dof_x.release();
     c->h_dofmap.assign(dofmap, dofmap + static_cast<std::size_t>(c->n_cells) * c->nd);
     c->dofmap.upload(c->h_dofmap, c->stream);
     c->bc.alloc(static_cast<std::size_t>(n_owned) + n_ghost);
@@ -279,20 +280,22 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
   });
 }
 
-int ptb_create_box_p1(ptb_ctx* c, int problem, int bs, int64_t nx, int64_t ny, int64_t nz, int rank, int nranks,
-                      int64_t sizes[4])
+int ptb_create_box(ptb_ctx* c, int problem, int bs, int order, int64_t nx, int64_t ny, int64_t nz, int rank,
+                   int nranks, int64_t sizes[4])
 {
   return guarded(c, [&] {
     use_device(c);
-    need(problem == PTB_POISSON || problem == PTB_ELASTICITY, "ptb_create_box_p1: unknown problem");
+    need(problem == PTB_POISSON || problem == PTB_ELASTICITY, "ptb_create_box: unknown problem");
     need((problem == PTB_POISSON && bs == 1) || (problem == PTB_ELASTICITY && bs == 3),
-         "ptb_create_box_p1: bs must be 1 for Poisson and 3 for elasticity");
-    need(nx >= 1 && ny >= 1 && nz >= 1, "ptb_create_box_p1: box dimensions must be positive");
+         "ptb_create_box: bs must be 1 for Poisson and 3 for elasticity");
+    need(nx >= 1 && ny >= 1 && nz >= 1, "ptb_create_box: box dimensions must be positive");
     need(nranks >= 1 && rank >= 0 && rank < nranks && nz >= nranks,
-         "ptb_create_box_p1: need 0 <= rank < nranks <= nz");
-    gpu_create_box_p1(c, nx, ny, nz, rank, nranks);
+         "ptb_create_box: need 0 <= rank < nranks <= nz");
+    need(order >= 1 && order <= 3, "Order not supported");
+    gpu_create_box(c, order, nx, ny, nz, rank, nranks);
     c->have_mesh = true;
-    c->problem = problem, c->order = 1, c->bs = bs, c->nd = 4;
+    c->problem = problem, c->order = order, c->bs = bs;
+    c->nd = (order + 1) * (order + 2) * (order + 3) / 6;
     c->operator_mode = PTB_OP_ASSEMBLED;
     c->h_dofmap.clear(); // downloaded on demand (ptb_set_pattern's host build)
     c->bc.alloc(static_cast<std::size_t>(c->n_owned) + c->n_ghost);
@@ -329,6 +332,25 @@ int ptb_get_dofmap(ptb_ctx* c, int32_t* dofmap)
     need(c->have_space && dofmap, "ptb_get_dofmap: no space set / NULL output");
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     PTB_CUDA(cudaMemcpy(dofmap, c->dofmap.p, c->dofmap.bytes(), cudaMemcpyDeviceToHost));
+  });
+}
+
+int ptb_get_dof_coordinates(ptb_ctx* c, double* dof_x)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_space && dof_x, "ptb_get_dof_coordinates: no space set / NULL output");
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    if (c->dof_x.p)
+      PTB_CUDA(cudaMemcpy(dof_x, c->dof_x.p, c->dof_x.bytes(), cudaMemcpyDeviceToHost));
+    else
+    {
+      // order 1 (or a caller-supplied space): the vertex-dof coordinates, unpadded
+      need(c->order == 1, "ptb_get_dof_coordinates: only for order 1 or a space made by ptb_create_box");
+      const std::size_t nl = static_cast<std::size_t>(c->n_owned) + c->n_ghost;
+      PTB_CUDA(cudaMemcpy2D(dof_x, 3 * sizeof(double), c->xdof.p, 4 * sizeof(double), 3 * sizeof(double), nl,
+                            cudaMemcpyDeviceToHost));
+    }
   });
 }
 
@@ -625,7 +647,7 @@ int ptb_set_exterior_facets(ptb_ctx* c, int64_t n_facets, const int32_t* cells,
     std::vector<std::int32_t> ids, ptr, ent;
     if (c->h_dofmap.empty() && n_facets > 0)
     {
-      // the dofmap was generated on the device (ptb_create_box_p1): fetch the rows of the facets'
+      // the dofmap was generated on the device (ptb_create_box): fetch the rows of the facets'
       // cells only -- surface-sized, not the whole map
       DevBuf<std::int32_t> d_cells, d_rows;
       d_cells.upload(cells, static_cast<std::size_t>(n_facets), c->stream);
@@ -673,7 +695,8 @@ int ptb_interpolate_source(ptb_ctx* c, const double* dof_x)
   return guarded(c, [&] {
     use_device(c);
     need(c->have_space, "ptb_interpolate_source: call ptb_set_space first");
-    need(dof_x || c->order == 1, "ptb_interpolate_source: dof coordinates are required for order > 1");
+    need(dof_x || c->order == 1 || c->dof_x.p,
+         "ptb_interpolate_source: dof coordinates are required for order > 1");
     const std::size_t nl = static_cast<std::size_t>(c->n_owned) + c->n_ghost;
     c->f.alloc(nl * c->bs);
     if (c->problem == PTB_POISSON)
@@ -689,7 +712,10 @@ int ptb_interpolate_source(ptb_ctx* c, const double* dof_x)
     }
     else
     {
-      launch_interpolate_source(c, c->xdof.p, 4);
+      if (c->order == 1)
+        launch_interpolate_source(c, c->xdof.p, 4);
+      else
+        launch_interpolate_source(c, c->dof_x.p, 3);
       PTB_CUDA(cudaStreamSynchronize(c->stream));
     }
     c->have_source = true;

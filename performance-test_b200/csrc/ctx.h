@@ -112,6 +112,7 @@ struct ptb_ctx
   // geometry + dofmaps
   ptb::DevBuf<double> xyz;        // [n_vertices][4] padded
   ptb::DevBuf<double> xyz3;       // [n_vertices][3] staging of the caller's layout
+  ptb::DevBuf<double> dof_x;      // [n_local dofs][3] dof coordinates of a device-generated P2/P3 space (box.cu)
   ptb::DevBuf<double> xdof;       // [n_local dofs][4]: coordinates of vertex dofs, by dof index
   ptb::DevBuf<std::int32_t> dof_vertex; // [n_local dofs] geometry vertex of a vertex dof, else -1
   ptb::DevBuf<std::int32_t> x_dofmap, dofmap;

@@ -108,8 +108,9 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
 void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl,
                        std::vector<std::int64_t>& h_mat_off);
 
-/// The local z-slab of the unit-cube Kuhn mesh and its P1 dofmap generated on the device (box.cu).
-void gpu_create_box_p1(ptb_ctx* c, std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);
+/// The local z-slab of the unit-cube Kuhn mesh and its Lagrange dofmap (order 1..3) generated on the
+/// device (box.cu).
+void gpu_create_box(ptb_ctx* c, int order, std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);
 /// out[k*nd + j] = dofmap[cells[k]*nd + j] for the n listed cells (box.cu).
 void launch_gather_dofmap_rows(ptb_ctx* c, std::int64_t n, const std::int32_t* cells, std::int32_t* out);
 /// Device-side problem data (problem_data.cu): Dirichlet markers from the reference's facet predicate

@@ -15,6 +15,7 @@ struct EmuIdx
 };
 static EmuIdx threadIdx, blockIdx, blockDim, gridDim;
 static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
 
 #include "../../performance-test_b200/csrc/box.cu"
 
@@ -37,17 +38,45 @@ void emu_launch(K kernel, std::int64_t n_threads, unsigned block, Args... args)
 
 extern "C" {
 
-// dims = nx, ny, nz, l0, l1, G0, G1, Glow, Ghigh (BoxDims as gpu_create_box_p1 fills it)
-int emu_create_box_p1(const int64_t* dims, double* xyz3, double* xyz4, int32_t* dof_vertex, int32_t* x_dofmap,
-                      int32_t* dofmap)
+// dims = nx, ny, nz, l0, l1, G0, G1, Glow, Ghigh (BoxDims as make_box_dims of box.cu fills it; the
+// test computes it independently). The numbering and the local table come from common/kuhn_space.h
+// exactly as make_space_dims packs them. dofmap [n_cells * nd]; dof_x [(n_owned + n_ghost) * 3].
+int emu_create_box(const int64_t* dims, int order, double* xyz3, double* xyz4, int32_t* dof_vertex,
+                   int32_t* x_dofmap, int32_t* dofmap, double* dof_x, int* flags)
 {
   using namespace ptb;
   BoxDims B{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]};
-  const std::int64_t nvp = (B.nx + 1) * (B.ny + 1);
+  const kuhn::Numbering K(B.nx, B.ny, B.nz, order);
+  std::vector<kuhn::LocalDof> tab;
+  kuhn::build_local_table(order, tab);
+  SpaceDims N{};
+  N.order = order, N.nd = kuhn::lagrange_ndofs(order);
+  N.PS = K.PS, N.LS = K.LS;
+  for (int k = 0; k < kuhn::NK; ++k)
+  {
+    N.koff[k] = K.koff[k], N.kw[k] = K.kw[k], N.ksub[k] = K.ksub[k];
+    N.kdim[k] = kuhn::kinds[k].dim, N.kd1[k] = kuhn::kinds[k].d1, N.kd2[k] = kuhn::kinds[k].d2;
+    N.klayer[k] = kuhn::kinds[k].layer ? 1 : 0;
+  }
+  for (std::size_t e = 0; e < tab.size(); ++e)
+    N.tkind[e] = tab[e].kind, N.tsub[e] = tab[e].sub, N.tbx[e] = tab[e].bx, N.tby[e] = tab[e].by, N.tbz[e] = tab[e].bz;
+  for (int s = 0; s < order - 1 && s < 2; ++s)
+    N.edge_t[s] = kuhn::edge_param(order, s);
+  const std::int64_t nvp = (B.nx + 1) * (B.ny + 1), n_cubes = B.nx * B.ny * (B.l1 - B.l0);
   const double hx = 1.0 / static_cast<double>(B.nx), hy = 1.0 / static_cast<double>(B.ny),
                hz = 1.0 / static_cast<double>(B.nz);
-  emu_launch(box_vertices, nvp * (B.l1 - B.l0 + 1), BX_THREADS, B, hx, hy, hz, xyz3, xyz4, dof_vertex);
-  emu_launch(box_cells_p1, B.nx * B.ny * (B.l1 - B.l0), BX_THREADS, B, x_dofmap, dofmap);
+  emu_launch(box_vertices, nvp * (B.l1 - B.l0 + 1), BX_THREADS, B, N.PS + N.LS, hx, hy, hz, xyz3, xyz4, dof_vertex);
+  flags[0] = 0;
+  if (order == 1)
+    emu_launch(box_cells_p1, n_cubes, BX_THREADS, B, x_dofmap, dofmap);
+  else
+  {
+    std::vector<std::int32_t> scratch(static_cast<std::size_t>(n_cubes) * 24);
+    emu_launch(box_cells_p1, n_cubes, BX_THREADS, B, x_dofmap, scratch.data());
+    emu_launch(box_cells_dofmap, 6 * n_cubes, BX_THREADS, B, N, dofmap, flags);
+  }
+  // the coordinate kernel runs for every order here (the product launches it for order > 1 only)
+  emu_launch(box_dof_coordinates, B.Ghigh - B.Glow, BX_THREADS, B, N, hx, hy, hz, dof_x);
   return 0;
 }
 

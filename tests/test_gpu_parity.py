@@ -620,12 +620,15 @@ def test_opt_in_device_problem_data_matches_the_host(pt, oracle, ptype, order, d
 
 @OPTIN
 @pytest.mark.parametrize("gpu_setup", ["0", "1"])
-@pytest.mark.parametrize("ptype,dims", [("poisson", (16, 15, 17)), ("poisson", (1, 1, 1)), ("elasticity", (8, 9, 7))])
-def test_opt_in_whole_p1_setup_generated_on_the_device(pt, oracle, monkeypatch, ptype, dims, gpu_setup):
-    """ptb_create_box_p1 + ptb_build_pattern + ptb_locate_bc + ptb_interpolate_source: mesh, dofmap,
-    pattern and Dirichlet dofs equal the host stand-in's arrays bit for bit, and the hot path on top
-    of them matches the oracle. With PTB_GPU_SETUP=1 the layouts and assembly maps are device-built too."""
-    P = pt.host.Problem(ptype, 1, *dims)
+@pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
+                                              ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
+                                              ("poisson", 3, (4, 5, 3))])
+def test_opt_in_whole_setup_generated_on_the_device(pt, oracle, monkeypatch, ptype, order, dims, gpu_setup):
+    """ptb_create_box + ptb_build_pattern + ptb_locate_bc + ptb_interpolate_source: mesh, dofmap, dof
+    coordinates, pattern and Dirichlet dofs equal the host stand-in's arrays bit for bit, and the hot
+    path on top of them matches the oracle. With PTB_GPU_SETUP=1 the layouts and assembly maps are
+    device-built too."""
+    P = pt.host.Problem(ptype, order, *dims)
     monkeypatch.setenv("PTB_GPU_SETUP", gpu_setup)
     c = pt.abi.Context(0)
     try:
@@ -634,9 +637,11 @@ def test_opt_in_whole_p1_setup_generated_on_the_device(pt, oracle, monkeypatch, 
         x, xd = c.mesh()
         assert np.array_equal(x, P["x"]) and np.array_equal(xd, P["x_dofmap"])
         assert np.array_equal(c.dofmap(), P["dofmap"])
+        assert np.array_equal(c.dof_coordinates(), P["dof_x"])
         rp, cl = c.pattern()
         assert np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"])
-        assert c.p1_maps()["built_on_device"] == (gpu_setup == "1")
+        if order == 1:
+            assert c.p1_maps()["built_on_device"] == (gpu_setup == "1")
         c.assemble_matrix()
         c.assemble_vector()
         A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)

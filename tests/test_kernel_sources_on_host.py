@@ -777,41 +777,55 @@ def emubx():
     return C.CDLL(out)
 
 
-def box_dims(nx, ny, nz, rank, nranks):
-    """BoxDims as gpu_create_box_p1 (box.cu) computes it: z-slabs, one ghost layer of cells below."""
+def box_dims(nx, ny, nz, rank, nranks, order=1):
+    """BoxDims as make_box_dims (box.cu) computes it: z-slabs, one ghost layer of cells below; the
+    level stride of the numbering from the entity counts of one lattice level."""
     base, rem = divmod(nz, nranks)
     L0 = rank * base + min(rank, rem)
     L1 = L0 + base + (1 if rank < rem else 0)
     last = rank == nranks - 1
-    nvp = (nx + 1) * (ny + 1)
+    ne, nf = order - 1, (order - 1) * (order - 2) // 2
+    # plane block: vertices, x / y / xy edges, two faces per square; layer block: z / xz / yz / xyz
+    # edges, six faces per cube interior + the rising faces over the x- and y-edges of the plane
+    PS = ((nx + 1) * (ny + 1) + ne * (nx * (ny + 1) + (nx + 1) * ny + nx * ny) + nf * 2 * nx * ny)
+    LS = (ne * ((nx + 1) * (ny + 1) + nx * (ny + 1) + (nx + 1) * ny + nx * ny)
+          + nf * (6 * nx * ny + 2 * (nx + 1) * ny + 2 * nx * (ny + 1)))
+    S = PS + LS
     l0 = L0 - 1 if rank > 0 else L0
-    G0, G1 = L0 * nvp, ((nz + 1) * nvp if last else L1 * nvp)
-    return np.array([nx, ny, nz, l0, L1, G0, G1, l0 * nvp, G1 if last else G1 + nvp], np.int64)
+    G0, G1 = L0 * S, (nz * S + PS if last else L1 * S)
+    return np.array([nx, ny, nz, l0, L1, G0, G1, l0 * S, G1 if last else G1 + PS], np.int64)
 
 
-@pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1),
-                                                    ("poisson", (4, 3, 5), 0, 2), ("poisson", (4, 3, 5), 1, 2),
-                                                    ("elasticity", (3, 3, 7), 1, 3), ("poisson", (3, 3, 7), 2, 3),
-                                                    ("poisson", (2, 7, 8), 5, 8)])
-def test_box_generator_source_equals_the_host_mesh_and_dofmap(pt, emubx, ptype, dims, rank, nranks):
-    """Vertices, cell -> vertex map, P1 dofmap and the dof -> vertex inverse from the generator
-    kernels equal the host stand-in's arrays bit for bit on every rank of a z-slab partition."""
-    P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
-    B = box_dims(*dims, rank, nranks)
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (1, 1, 1), 0, 1),
+                                                          ("poisson", 1, (4, 3, 5), 0, 2), ("poisson", 1, (4, 3, 5), 1, 2),
+                                                          ("elasticity", 1, (3, 3, 7), 1, 3), ("poisson", 1, (3, 3, 7), 2, 3),
+                                                          ("poisson", 1, (2, 7, 8), 5, 8), ("poisson", 2, (3, 2, 4), 0, 1),
+                                                          ("poisson", 2, (2, 2, 5), 1, 2), ("poisson", 3, (2, 3, 2), 0, 1),
+                                                          ("poisson", 3, (2, 2, 4), 2, 3), ("poisson", 3, (1, 1, 3), 1, 3)])
+def test_box_generator_source_equals_the_host_mesh_and_dofmap(pt, emubx, ptype, order, dims, rank, nranks):
+    """Vertices, cell -> vertex map, Lagrange dofmap (P1-P3), dof coordinates and the dof -> vertex
+    inverse from the generator kernels equal the host stand-in's arrays bit for bit on every rank of
+    a z-slab partition."""
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    B = box_dims(*dims, rank, nranks, order)
     x_ref = np.asarray(P["x"])
     nv, nc = len(x_ref) // 3, len(P["x_dofmap"]) // 4
     n = P.n_owned + P.n_ghost
     assert int(B[6] - B[5]) == P.n_owned and int((B[5] - B[7]) + (B[8] - B[6])) == P.n_ghost
     xyz3, xyz4 = np.full(nv * 3, np.nan), np.full(nv * 4, np.nan)
-    dv = np.full(n, -5, np.int32)
-    xd, dm = np.full(nc * 4, -5, np.int32), np.full(nc * 4, -5, np.int32)
-    assert emubx.emu_create_box_p1(_p(B), _p(xyz3), _p(xyz4), _p(dv), _p(xd), _p(dm)) == 0
+    dv = np.full(n, -1, np.int32)
+    xd, dm = np.full(nc * 4, -5, np.int32), np.full(nc * P.nd, -5, np.int32)
+    dof_x = np.full(n * 3, np.nan)
+    flags = np.full(1, -1, np.int32)
+    assert emubx.emu_create_box(_p(B), order, _p(xyz3), _p(xyz4), _p(dv), _p(xd), _p(dm), _p(dof_x), _p(flags)) == 0
+    assert flags[0] == 0
     assert np.array_equal(xyz3, x_ref)
     assert np.array_equal(xyz4.reshape(-1, 4)[:, :3].reshape(-1), x_ref) and np.all(xyz4.reshape(-1, 4)[:, 3] == 0)
     assert np.array_equal(xd, P["x_dofmap"]) and np.array_equal(dm, P["dofmap"])
-    # dof -> vertex is the inverse of the vertex dofs of the cells
+    assert np.array_equal(dof_x, P["dof_x"])
+    # dof -> vertex is the inverse of the vertex dofs of the cells, -1 for edge and face dofs
     inv = np.full(n, -1, np.int32)
-    inv[np.asarray(P["dofmap"])] = np.asarray(P["x_dofmap"])
+    inv[np.asarray(P["dofmap"]).reshape(-1, P.nd)[:, :4].reshape(-1)] = np.asarray(P["x_dofmap"])
     assert np.array_equal(dv, inv)
 
 
