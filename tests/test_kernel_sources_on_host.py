@@ -603,7 +603,8 @@ def emusu():
 @pytest.mark.parametrize("ptype,dims,rank,nranks", [("poisson", (5, 4, 6), 0, 1), ("poisson", (1, 1, 1), 0, 1),
                                                     ("poisson", (33, 2, 1), 0, 1), ("poisson", (4, 3, 5), 1, 2),
                                                     ("poisson", (3, 3, 7), 2, 3), ("elasticity", (3, 4, 3), 0, 1),
-                                                    ("elasticity", (2, 2, 5), 1, 2)])
+                                                    ("elasticity", (2, 2, 5), 1, 2),
+                                                    ("poisson", (12, 11, 13), 0, 1)])  # > 1024 rows: scan chunks > 1
 def test_device_setup_source_builds_the_host_maps_bit_for_bit(pt, emusu, ptype, dims, rank, nranks, shuffle):
     """adj_off, the rotated slot words and the star walk built by the setup kernels equal the host
     build (common/intmaps.cpp + layout.cpp) word for word, whatever order the fill atomics land in."""
@@ -648,7 +649,8 @@ def test_device_setup_source_flags_a_pattern_that_misses_a_cell_pair(pt, emusu):
 @pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (1, 1, 1), 0, 1),
                                                           ("poisson", 1, (4, 3, 5), 1, 2), ("elasticity", 1, (3, 4, 3), 0, 1),
                                                           ("poisson", 2, (3, 2, 4), 0, 1), ("poisson", 2, (2, 2, 5), 1, 2),
-                                                          ("poisson", 3, (2, 3, 2), 0, 1), ("poisson", 3, (2, 2, 4), 2, 3)])
+                                                          ("poisson", 3, (2, 3, 2), 0, 1), ("poisson", 3, (2, 2, 4), 2, 3),
+                                                          ("poisson", 1, (12, 11, 13), 0, 1), ("poisson", 3, (4, 4, 3), 0, 1)])
 def test_device_pattern_source_equals_the_host_pattern(pt, emusu, ptype, order, dims, rank, nranks):
     """ptb_build_pattern's kernels (pairs -> per-row ascending union -> scan -> fill) against the
     pattern the host stand-in builds (common/intmaps.cpp build_pattern), P1-P3, with ghost columns."""
