@@ -58,7 +58,7 @@ struct Options
 {
   std::string problem_type = "poisson", mesh_type = "cube", scaling_type = "weak", output = "",
               scatterer = "neighbor", comm = "peer", pc_type = "jacobi";
-  bool help = false, memory_profiling = false, subcomm_partition = false;
+  bool help = false, memory_profiling = false, subcomm_partition = false, device_setup = false;
   std::size_t ndofs = 50000, order = 1;
   int nprocs = 0; // > 0: fork that many ranks on this node
   double ksp_rtol = 1e-8;
@@ -80,6 +80,7 @@ const char* USAGE = R"(Allowed options:
 B200 additions:
   --nprocs arg                      start this many ranks (one per GPU) on this node
   --comm arg (=peer)                multi-GPU transport: peer (NVLink peer memory) or nccl
+  --device_setup                    mesh, dofmap, sparsity, boundary conditions and RHS on the GPU
   -ksp_rtol arg (=1e-8)  -ksp_max_it arg (=10000)  -pc_type arg (=jacobi) none|jacobi
 )";
 
@@ -112,6 +113,7 @@ Options parse(int argc, char* argv[])
     else if (a == "--scatterer") o.scatterer = value();
     else if (a == "--nprocs") o.nprocs = std::stoi(value());
     else if (a == "--comm") o.comm = value();
+    else if (a == "--device_setup") o.device_setup = true;
     else if (a == "-ksp_rtol") o.ksp_rtol = std::stod(value()), o.rtol_set = true;
     else if (a == "-ksp_max_it") o.ksp_max_it = std::stoi(value()), o.maxit_set = true;
     else if (a == "-pc_type")
@@ -166,8 +168,21 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
   const bool cgp = type == "cgpoisson";
   ptb_ctx* c = gpu->c;
 
+  // --device_setup (opt-in): the arrays of every setup region are generated
+  // on the device (ptb_create_box, ptb_locate_bc, ptb_interpolate_source, ptb_build_pattern); the
+  // host keeps the sizes and the surface-sized lists (ghost/halo lists, exterior facets).
+  const bool dev = opt.device_setup;
   Timer t0("ZZZ FunctionSpace");
-  auto V = std::make_shared<FunctionSpace>(create_functionspace(mesh, order, elasticity ? 3 : 1));
+  auto V = std::make_shared<FunctionSpace>(create_functionspace(mesh, order, elasticity ? 3 : 1, !dev));
+  if (dev)
+  {
+    std::int64_t sizes[4];
+    ok(c, ptb_create_box(c, elasticity ? PTB_ELASTICITY : PTB_POISSON, V->bs, order, mesh.nx, mesh.ny, mesh.nz,
+                         mesh.rank, mesh.nranks, sizes));
+    if (sizes[0] != mesh.n_vertices_local() || sizes[1] != mesh.n_cells_local() || sizes[2] != V->n_owned
+        || sizes[3] != V->n_ghost)
+      throw std::runtime_error("device-generated slab does not match the host sizing");
+  }
   t0.stop();
   t0.flush();
   ndofs_global = V->n_global * V->bs;
@@ -177,13 +192,23 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
     t1 = std::make_unique<Timer>("ZZZ Assemble");
 
   Timer t2("ZZZ Create boundary conditions");
-  const std::vector<std::int32_t> bdofs = locate_bc_dofs(mesh, *V, type);
+  std::vector<std::int32_t> bdofs;
+  if (dev)
+  {
+    std::int32_t n_bc = 0;
+    ok(c, ptb_locate_bc(c, &n_bc));
+  }
+  else
+    bdofs = locate_bc_dofs(mesh, *V, type);
   t2.stop();
   t2.flush();
 
   Timer t3("ZZZ Create RHS function");
   std::vector<double> f, g;
-  interpolate_rhs(*V, type, f, g);
+  if (dev)
+    ok(c, ptb_interpolate_source(c, nullptr));
+  else
+    interpolate_rhs(*V, type, f, g);
   t3.stop();
   t3.flush();
 
@@ -192,20 +217,30 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
     if (elasticity)
       tf = std::make_unique<Timer>("ZZZ Create forms");
     // create_matrix: sparsity pattern (poisson_problem.cpp:122-123) + device setup
-    ptb::RowAdjacency adj;
-    std::vector<std::int64_t> rowptr;
-    std::vector<std::int32_t> cols, fc, fl;
-    ptb::build_row_adjacency(V->dofmap.data(), mesh.n_cells_local(), V->nd, V->n_owned, adj);
-    ptb::build_pattern(V->dofmap.data(), V->nd, V->n_owned, adj, rowptr, cols);
+    std::vector<std::int32_t> fc, fl;
     exterior_facets(mesh, fc, fl);
-    ok(c, ptb_set_mesh(c, mesh.n_vertices_local(), mesh.x.data(), mesh.n_cells_local(),
-                       mesh.x_dofmap.data()));
-    ok(c, ptb_set_space(c, elasticity ? PTB_ELASTICITY : PTB_POISSON, order, V->bs, V->n_owned,
-                        V->n_ghost, V->dofmap.data()));
-    ok(c, ptb_set_pattern(c, rowptr.data(), cols.data()));
-    ok(c, ptb_set_bc(c, static_cast<std::int32_t>(bdofs.size()), bdofs.data()));
-    ok(c, ptb_set_exterior_facets(c, static_cast<std::int64_t>(fc.size()), fc.data(), fl.data()));
-    ok(c, ptb_set_source(c, f.data(), g.empty() ? nullptr : g.data()));
+    if (dev)
+    {
+      std::int64_t nnz = 0;
+      ok(c, ptb_build_pattern(c, &nnz)); // with PTB_GPU_SETUP=1 the layouts and maps as well
+      ok(c, ptb_set_exterior_facets(c, static_cast<std::int64_t>(fc.size()), fc.data(), fl.data()));
+    }
+    else
+    {
+      ptb::RowAdjacency adj;
+      std::vector<std::int64_t> rowptr;
+      std::vector<std::int32_t> cols;
+      ptb::build_row_adjacency(V->dofmap.data(), mesh.n_cells_local(), V->nd, V->n_owned, adj);
+      ptb::build_pattern(V->dofmap.data(), V->nd, V->n_owned, adj, rowptr, cols);
+      ok(c, ptb_set_mesh(c, mesh.n_vertices_local(), mesh.x.data(), mesh.n_cells_local(),
+                         mesh.x_dofmap.data()));
+      ok(c, ptb_set_space(c, elasticity ? PTB_ELASTICITY : PTB_POISSON, order, V->bs, V->n_owned,
+                          V->n_ghost, V->dofmap.data()));
+      ok(c, ptb_set_pattern(c, rowptr.data(), cols.data()));
+      ok(c, ptb_set_bc(c, static_cast<std::int32_t>(bdofs.size()), bdofs.data()));
+      ok(c, ptb_set_exterior_facets(c, static_cast<std::int64_t>(fc.size()), fc.data(), fl.data()));
+      ok(c, ptb_set_source(c, f.data(), g.empty() ? nullptr : g.data()));
+    }
     if (boot.world() > 1)
     {
       ok(c, ptb_set_halo(c, static_cast<int>(V->nbr_ranks.size()), V->nbr_ranks.data(),
@@ -360,8 +395,9 @@ void solve(const Options& opt, Bootstrap& boot, int local_rank)
                 << (sz.Ny << sz.r) << "x" << (sz.Nz << sz.r)
                 << ") box: same entity counts as the refined mesh" << std::endl;
   }
+  // --device_setup: sizes and ranges only; the arrays are generated on the device in problem()
   const BoxMesh mesh = create_box_mesh(sz.Nx << sz.r, sz.Ny << sz.r, sz.Nz << sz.r, boot.rank(),
-                                       boot.world());
+                                       boot.world(), !opt.device_setup);
   t0.stop();
   t0.flush();
 

@@ -92,7 +92,8 @@ std::array<std::int64_t, 2> slab_range(std::int64_t nz, int rank, int nranks)
   return {lo, lo + base + (rank < rem ? 1 : 0)};
 }
 
-BoxMesh create_box_mesh(std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks)
+BoxMesh create_box_mesh(std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks,
+                        bool with_arrays)
 {
   if (nx < 1 || ny < 1 || nz < 1)
     throw std::runtime_error("create_box_mesh: box dimensions must be positive");
@@ -110,6 +111,8 @@ BoxMesh create_box_mesh(std::int64_t nx, std::int64_t ny, std::int64_t nz, int r
   const std::int64_t nvx = nx + 1, nvy = ny + 1, nvp = nvx * nvy;
   if (m.n_vertices_local() > INT32_MAX || m.n_cells_local() * 4 > (std::int64_t)UINT32_MAX)
     throw std::runtime_error("create_box_mesh: local slab exceeds 32-bit local indexing");
+  if (!with_arrays)
+    return m;
 
   // Geometry as DOLFINx's create_box lays it out: x = a + ix * ((b - a) / nx), a = 0, b = 1.
   const double hx = 1.0 / static_cast<double>(nx), hy = 1.0 / static_cast<double>(ny),

@@ -65,7 +65,9 @@ struct BoxMesh
 /// Layers owned by `rank` when nz layers are split as evenly as possible over nranks slabs.
 std::array<std::int64_t, 2> slab_range(std::int64_t nz, int rank, int nranks);
 
-/// Build the local slab (geometry + cell->vertex map).
-BoxMesh create_box_mesh(std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks);
+/// Build the local slab (geometry + cell->vertex map). with_arrays = false fills the sizes and ranges
+/// only (x and x_dofmap stay empty): for callers that generate the arrays on the device.
+BoxMesh create_box_mesh(std::int64_t nx, std::int64_t ny, std::int64_t nz, int rank, int nranks,
+                        bool with_arrays = true);
 
 } // namespace ptb::host

@@ -44,7 +44,7 @@ LocalRanges local_ranges(const BoxMesh& m, const Numbering& N)
 }
 } // namespace
 
-FunctionSpace create_functionspace(const BoxMesh& m, int order, int bs)
+FunctionSpace create_functionspace(const BoxMesh& m, int order, int bs, bool with_dofmap)
 {
   if (order < 1 || order > 3)
     throw std::runtime_error("Order not supported");
@@ -95,6 +95,9 @@ FunctionSpace create_functionspace(const BoxMesh& m, int order, int bs)
     V.send_displ.push_back(static_cast<std::int32_t>(V.local_indices.size()));
     V.recv_displ.push_back(static_cast<std::int32_t>(V.remote_indices.size()));
   }
+
+  if (!with_dofmap)
+    return V;
 
   // Cell dofmap from the per-tet-type table.
   std::vector<LocalDof> tab;

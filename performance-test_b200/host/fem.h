@@ -41,7 +41,9 @@ struct FunctionSpace
   std::vector<std::int32_t> local_indices, remote_indices;  // block indices
 };
 
-FunctionSpace create_functionspace(const BoxMesh& mesh, int order, int bs);
+/// with_dofmap = false fills the sizes, ghost and halo lists only (dofmap and dof_x stay empty): for
+/// callers that generate the dofmap on the device.
+FunctionSpace create_functionspace(const BoxMesh& mesh, int order, int bs, bool with_dofmap = true);
 
 /// Block dofs (owned and ghost, ascending) on the Dirichlet boundary:
 /// "poisson": x = 0 or x = 1 (poisson_problem.cpp:60-71); "elasticity": y = 0

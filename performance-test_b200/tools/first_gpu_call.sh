@@ -10,6 +10,13 @@ mkdir -p "$out"
 export PTB_TEST_OPTIN=1
 echo "== opt-in parity tests"
 timeout 400 python -m pytest tests/test_gpu_parity.py -q -s -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -40 | tee "$out/optin_tests.txt"
+timeout 200 python -m pytest tests/test_cli.py -q -k device_setup 2>&1 | tail -5 | tee -a "$out/optin_tests.txt"
+echo "== the reference's timing table with the setup on the host and on the device (Poisson 4M DOFs)"
+for ds in "" "--device_setup"; do
+  PTB_GPU_SETUP=1 timeout 200 performance-test_b200/dolfinx-scaling-test --ndofs 4000000 -ksp_rtol 1e-8 $ds \
+    > "$out/cli_poisson4M${ds:+_device_setup}.txt" 2>&1
+  grep -E "ZZZ|Krylov|Solution norm" "$out/cli_poisson4M${ds:+_device_setup}.txt" | head -20
+done
 echo "== assembly A/B (4M DOFs)"
 WALK_CHECK_OUT=first_call/assembly_ab_4M.json timeout 200 python performance-test_b200/tools/check_walk.py ab2 4000000 2>&1 | tail -2
 echo "== ncu --set full of the direct-gather kernels (Poisson 4M): read it with tools/ncu_summary.py"

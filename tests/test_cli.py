@@ -73,6 +73,27 @@ def test_full_run_matches_oracle(pt, oracle, ptype, ndofs):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(os.environ.get("PTB_TEST_OPTIN") != "1",
+                    reason="opt-in path not yet validated on a GPU (PTB_TEST_OPTIN=1)")
+@pytest.mark.parametrize("ptype,order,ndofs", [("poisson", 1, 40000), ("elasticity", 1, 30000), ("poisson", 2, 30000)])
+def test_device_setup_run_equals_the_host_setup_run(pt, ptype, order, ndofs):
+    """--device_setup (mesh, dofmap, pattern, boundary conditions, RHS generated on the GPU; with
+    PTB_GPU_SETUP=1 the layouts too) must print the same iteration count and solution norm as the
+    default run whose setup arrays come from the host stand-in."""
+    out = {}
+    for flag in ([], ["--device_setup"]):
+        env = dict(os.environ, PTB_GPU_SETUP="1" if flag else "0")
+        r = subprocess.run([EXE, "--problem_type", ptype, "--order", str(order), "--ndofs", str(ndofs),
+                            "-ksp_rtol", "1e-8", *flag], capture_output=True, text=True, timeout=300, env=env)
+        assert r.returncode == 0, r.stderr
+        its = int(re.search(r"\*\*\* Number of Krylov iterations: (\d+)", r.stdout).group(1))
+        norm = float(re.search(r"\*\*\* Solution norm:\s+([0-9.eE+-]+)", r.stdout).group(1))
+        out[bool(flag)] = (its, norm)
+    assert abs(out[True][0] - out[False][0]) <= 1
+    assert out[True][1] == pytest.approx(out[False][1], rel=1e-6)
+
+
+@pytest.mark.gpu
 def test_cgpoisson_uses_cg_h_defaults(pt):
     """cgpoisson: linalg::cg(u, b, action, 100, 1e-6), no preconditioner (cgpoisson_problem.cpp:233)."""
     r = _run("--problem_type", "cgpoisson", "--ndofs", "200000")
