@@ -79,6 +79,67 @@ setup_scan(std::int64_t n, const unsigned long long* __restrict__ in, std::int64
   }
 }
 
+// Long inputs: the same prefix sum in three passes over tiles of SC_TILE elements -- tile sums, a
+// scan of the tile sums (setup_scan above), and the tiles themselves: every thread owns SC_ITEMS
+// consecutive elements (a warp reads 2 KB contiguously), the thread sums are scanned in shared
+// memory (Hillis-Steele, two buffers), the tile offset is added on the way out.
+constexpr int SC_THREADS = 1024, SC_ITEMS = 8, SC_TILE = SC_THREADS * SC_ITEMS;
+
+__global__ void __launch_bounds__(SC_THREADS)
+setup_scan_tile_sums(std::int64_t n, const unsigned long long* __restrict__ in, std::int64_t scale,
+                     unsigned long long* __restrict__ tile_sum)
+{
+  __shared__ std::int64_t part[SC_THREADS];
+  const std::int64_t base = static_cast<std::int64_t>(blockIdx.x) * SC_TILE + threadIdx.x * SC_ITEMS;
+  std::int64_t sum = 0;
+  for (int j = 0; j < SC_ITEMS; ++j)
+    if (base + j < n)
+      sum += static_cast<std::int64_t>(in[base + j]) * scale;
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (int h = SC_THREADS / 2; h > 0; h >>= 1)
+  {
+    if (static_cast<int>(threadIdx.x) < h)
+      part[threadIdx.x] += part[threadIdx.x + h];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    tile_sum[blockIdx.x] = static_cast<unsigned long long>(part[0]);
+}
+
+__global__ void __launch_bounds__(SC_THREADS)
+setup_scan_tiles(std::int64_t n, const unsigned long long* __restrict__ in, std::int64_t scale,
+                 const std::int64_t* __restrict__ tile_off, std::int64_t n_tiles, std::int64_t* __restrict__ out)
+{
+  __shared__ std::int64_t buf[2][SC_THREADS];
+  const std::int64_t base = static_cast<std::int64_t>(blockIdx.x) * SC_TILE + threadIdx.x * SC_ITEMS;
+  std::int64_t v[SC_ITEMS], sum = 0;
+  for (int j = 0; j < SC_ITEMS; ++j)
+  {
+    v[j] = base + j < n ? static_cast<std::int64_t>(in[base + j]) * scale : 0;
+    sum += v[j];
+  }
+  int cur = 0;
+  buf[0][threadIdx.x] = sum;
+  __syncthreads();
+  for (int d = 1; d < SC_THREADS; d <<= 1) // inclusive scan of the thread sums
+  {
+    const std::int64_t x = buf[cur][threadIdx.x] + (static_cast<int>(threadIdx.x) >= d ? buf[cur][threadIdx.x - d] : 0);
+    buf[cur ^ 1][threadIdx.x] = x;
+    cur ^= 1;
+    __syncthreads();
+  }
+  std::int64_t run = tile_off[blockIdx.x] + buf[cur][threadIdx.x] - sum;
+  for (int j = 0; j < SC_ITEMS; ++j)
+    if (base + j < n)
+    {
+      out[base + j] = run;
+      run += v[j];
+    }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    out[n] = tile_off[n_tiles];
+}
+
 // place pair k at the next free position of its row (cursor starts at zero)
 __global__ void setup_fill(std::int64_t n_entries, const std::int32_t* __restrict__ dofmap,
                            std::int32_t n_rows, const std::int64_t* __restrict__ ptr,
@@ -503,8 +564,30 @@ __global__ void setup_walk(std::int32_t n_rows, std::int32_t n_slices,
 // not apply (a row with too many cells / offsets beyond a byte): the caller then uses the host build.
 namespace
 {
+// out[0..n] = exclusive prefix sum of in[0..n) * scale (out[n] = total): one CTA for short inputs,
+// the three tile passes above otherwise.
+void device_scan(ptb_ctx* c, std::int64_t n, const unsigned long long* in, std::int64_t* out, std::int64_t scale)
+{
+  if (n <= SC_TILE)
+  {
+    setup_scan<<<1, 1024, 0, c->stream>>>(n, in, out, scale);
+    c->launches += 1;
+    return;
+  }
+  const std::int64_t n_tiles = (n + SC_TILE - 1) / SC_TILE;
+  DevBuf<unsigned long long> tile_sum;
+  DevBuf<std::int64_t> tile_off;
+  tile_sum.alloc(static_cast<std::size_t>(n_tiles));
+  tile_off.alloc(static_cast<std::size_t>(n_tiles) + 1);
+  setup_scan_tile_sums<<<static_cast<unsigned>(n_tiles), SC_THREADS, 0, c->stream>>>(n, in, scale, tile_sum.p);
+  setup_scan<<<1, 1024, 0, c->stream>>>(n_tiles, tile_sum.p, tile_off.p, 1);
+  setup_scan_tiles<<<static_cast<unsigned>(n_tiles), SC_THREADS, 0, c->stream>>>(n, in, scale, tile_off.p, n_tiles, out);
+  PTB_CUDA(cudaGetLastError());
+  PTB_CUDA(cudaStreamSynchronize(c->stream)); // the tile buffers die here
+  c->launches += 3;
+}
+
 // dof -> (cell, local index) pairs of the owned rows, ascending per row: ptr [N + 1], pairs [ptr[N]].
-// Five launches.
 void build_pairs(ptb_ctx* c, DevBuf<std::int64_t>& ptr, DevBuf<std::uint32_t>& pairs)
 {
   const std::int32_t N = c->n_owned;
@@ -515,7 +598,7 @@ void build_pairs(ptb_ctx* c, DevBuf<std::int64_t>& ptr, DevBuf<std::uint32_t>& p
   ptr.alloc(static_cast<std::size_t>(N) + 1);
   const int ge = static_cast<int>((n_entries + SU_THREADS - 1) / SU_THREADS);
   setup_count<<<ge, SU_THREADS, 0, c->stream>>>(n_entries, c->dofmap.p, N, cnt.p);
-  setup_scan<<<1, 1024, 0, c->stream>>>(N, cnt.p, ptr.p, 1);
+  device_scan(c, N, cnt.p, ptr.p, 1);
   std::int64_t n_pairs = 0;
   PTB_CUDA(cudaMemcpyAsync(&n_pairs, ptr.p + N, sizeof(n_pairs), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -525,7 +608,7 @@ void build_pairs(ptb_ctx* c, DevBuf<std::int64_t>& ptr, DevBuf<std::uint32_t>& p
   setup_sort<<<(N + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, ptr.p, pairs.p);
   PTB_CUDA(cudaGetLastError());
   PTB_CUDA(cudaStreamSynchronize(c->stream)); // cnt dies here
-  c->launches += 5;
+  c->launches += 3;
 }
 } // namespace
 
@@ -546,14 +629,14 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
   flags.zero(c->stream);
   const int gr = (N + SU_THREADS - 1) / SU_THREADS;
   setup_pattern_count<<<gr, SU_THREADS, 0, c->stream>>>(N, c->nd, c->dofmap.p, ptr.p, pairs.p, cnt.p, flags.p);
-  setup_scan<<<1, 1024, 0, c->stream>>>(N, cnt.p, rp.p, 1);
+  device_scan(c, N, cnt.p, rp.p, 1);
   rowptr.resize(static_cast<std::size_t>(N) + 1);
   int h_flags[3] = {0, 0, 0};
   PTB_CUDA(cudaMemcpyAsync(rowptr.data(), rp.p, rowptr.size() * sizeof(std::int64_t), cudaMemcpyDeviceToHost,
                            c->stream));
   PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += 2;
+  c->launches += 1;
   if (h_flags[2] != 0)
     return false;
   cl.alloc(static_cast<std::size_t>(rowptr[N]));
@@ -569,7 +652,7 @@ bool gpu_build_pattern(ptb_ctx* c, std::vector<std::int64_t>& rowptr, std::vecto
 
 // The column side of ptb_set_pattern from a CSR pattern that is already on the device: c->rowptr,
 // mat_off, cols (SELL-32, padded), for scalar problems cdelta / colsx / xoff, and the slice order.
-// Sets n_slices, max_w, cols_explicit_frac, n_interior_slices. Eight launches (five for bs = 3).
+// Sets n_slices, max_w, cols_explicit_frac, n_interior_slices.
 void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::int32_t>& cl,
                        std::vector<std::int64_t>& h_mat_off)
 {
@@ -582,7 +665,7 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
   const int gl = static_cast<int>((static_cast<std::int64_t>(S) * 32 + SU_THREADS - 1) / SU_THREADS);
   setup_widths<<<gs, SU_THREADS, 0, c->stream>>>(N, S, rp.p, w.p);
   c->mat_off.alloc(static_cast<std::size_t>(S) + 1);
-  setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, c->mat_off.p, 32);
+  device_scan(c, S, w.p, c->mat_off.p, 32);
   std::int64_t n_sell = 0;
   std::vector<unsigned long long> h_w(static_cast<std::size_t>(S));
   PTB_CUDA(cudaMemcpyAsync(&n_sell, c->mat_off.p + S, sizeof(n_sell), cudaMemcpyDeviceToHost, c->stream));
@@ -598,13 +681,13 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
   }
   c->cols.alloc(static_cast<std::size_t>(n_sell));
   setup_sell_cols<<<gl, SU_THREADS, 0, c->stream>>>(N, S, rp.p, cl.p, c->mat_off.p, c->cols.p);
-  c->launches += 3;
+  c->launches += 2;
   if (c->bs == 1)
   {
     c->cdelta.alloc(static_cast<std::size_t>(n_sell / 32));
     setup_cdelta<<<gs, SU_THREADS, 0, c->stream>>>(N, n_cols, S, rp.p, c->mat_off.p, c->cols.p, c->cdelta.p, w.p);
     c->xoff.alloc(static_cast<std::size_t>(S) + 1);
-    setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, c->xoff.p, 32);
+    device_scan(c, S, w.p, c->xoff.p, 32);
     std::int64_t n_x = 0;
     PTB_CUDA(cudaMemcpyAsync(&n_x, c->xoff.p + S, sizeof(n_x), cudaMemcpyDeviceToHost, c->stream));
     PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -612,20 +695,20 @@ void gpu_setup_columns(ptb_ctx* c, DevBuf<std::int64_t>& rp, const DevBuf<std::i
     if (n_x > 0)
       setup_colsx<<<gl, SU_THREADS, 0, c->stream>>>(S, c->mat_off.p, c->cols.p, c->cdelta.p, c->xoff.p, c->colsx.p);
     c->cols_explicit_frac = n_sell > 0 ? static_cast<double>(n_x) / static_cast<double>(n_sell) : 0.0;
-    c->launches += 3;
+    c->launches += 2;
   }
   DevBuf<std::int64_t> pos;
   pos.alloc(static_cast<std::size_t>(S) + 1);
   c->slice_order.alloc(static_cast<std::size_t>(S));
   setup_slice_flags<<<gs, SU_THREADS, 0, c->stream>>>(N, S, c->mat_off.p, c->cols.p, w.p);
-  setup_scan<<<1, 1024, 0, c->stream>>>(S, w.p, pos.p, 1);
+  device_scan(c, S, w.p, pos.p, 1);
   setup_slice_order<<<gs, SU_THREADS, 0, c->stream>>>(S, w.p, pos.p, c->slice_order.p);
   PTB_CUDA(cudaGetLastError());
   std::int64_t n_int = 0;
   PTB_CUDA(cudaMemcpyAsync(&n_int, pos.p + S, sizeof(n_int), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream)); // w, pos die here
   c->n_interior_slices = static_cast<std::int32_t>(n_int);
-  c->launches += 3;
+  c->launches += 2;
   // the kernels read rowptr from the context: take the device copy over instead of re-uploading it
   std::swap(c->rowptr.p, rp.p);
   std::swap(c->rowptr.n, rp.n);
@@ -647,7 +730,7 @@ bool gpu_setup_pk(ptb_ctx* c, int* max_wa)
   wa.alloc(static_cast<std::size_t>(S));
   setup_widths<<<(S + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, wa.p);
   c->adj_off.alloc(static_cast<std::size_t>(S) + 1);
-  setup_scan<<<1, 1024, 0, c->stream>>>(S, wa.p, c->adj_off.p, 32);
+  device_scan(c, S, wa.p, c->adj_off.p, 32);
   std::int64_t n_adj = 0;
   PTB_CUDA(cudaMemcpyAsync(&n_adj, c->adj_off.p + S, sizeof(n_adj), cudaMemcpyDeviceToHost, c->stream));
   std::vector<unsigned long long> h_wa(static_cast<std::size_t>(S));
@@ -667,7 +750,7 @@ bool gpu_setup_pk(ptb_ctx* c, int* max_wa)
   int h_flags[2] = {0, 0};
   PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += 3;
+  c->launches += 2;
   return h_flags[0] == 0;
 }
 
@@ -684,7 +767,7 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
   wa.alloc(static_cast<std::size_t>(S));
   setup_widths<<<(S + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, wa.p);
   c->adj_off.alloc(static_cast<std::size_t>(S) + 1);
-  setup_scan<<<1, 1024, 0, c->stream>>>(S, wa.p, c->adj_off.p, 32);
+  device_scan(c, S, wa.p, c->adj_off.p, 32);
   std::int64_t n_adj = 0;
   PTB_CUDA(cudaMemcpyAsync(&n_adj, c->adj_off.p + S, sizeof(n_adj), cudaMemcpyDeviceToHost, c->stream));
   std::vector<unsigned long long> h_wa(static_cast<std::size_t>(S));
@@ -707,7 +790,7 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
   int h_flags[2] = {0, 0};
   PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
-  c->launches += want_walk ? 4 : 3;
+  c->launches += want_walk ? 3 : 2;
   return h_flags[0] == 0 && h_flags[1] == 0;
 }
 #endif // PTB_HOST_EMU

@@ -60,6 +60,25 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 
 namespace
 {
+// device_scan of setup.cu: one CTA for short inputs, the three tile passes otherwise
+void emu_scan(std::int64_t n, const unsigned long long* in, std::int64_t* out, std::int64_t scale)
+{
+  using namespace ptb;
+  if (n <= SC_TILE)
+  {
+    emu_launch(setup_scan, 1, 1024, n, in, out, scale);
+    return;
+  }
+  const std::int64_t n_tiles = (n + SC_TILE - 1) / SC_TILE;
+  std::vector<unsigned long long> tile_sum(static_cast<std::size_t>(n_tiles), 0);
+  std::vector<std::int64_t> tile_off(static_cast<std::size_t>(n_tiles) + 1, -1);
+  emu_launch(setup_scan_tile_sums, static_cast<unsigned>(n_tiles), SC_THREADS, n, in, scale, tile_sum.data());
+  emu_launch(setup_scan, 1, 1024, n_tiles, (const unsigned long long*)tile_sum.data(), tile_off.data(),
+             static_cast<std::int64_t>(1));
+  emu_launch(setup_scan_tiles, static_cast<unsigned>(n_tiles), SC_THREADS, n, in, scale,
+             (const std::int64_t*)tile_off.data(), n_tiles, out);
+}
+
 // dof -> (cell, local index) pairs as build_pairs (setup.cu) launches them
 void emu_pairs(int64_t n_entries, const int32_t* dofmap, int32_t n_rows, int shuffle, std::vector<std::int64_t>& ptr,
                std::vector<std::uint32_t>& pairs)
@@ -69,8 +88,7 @@ void emu_pairs(int64_t n_entries, const int32_t* dofmap, int32_t n_rows, int shu
   std::vector<unsigned long long> cnt(static_cast<std::size_t>(n_rows), 0);
   ptr.assign(static_cast<std::size_t>(n_rows) + 1, -1);
   emu_launch(setup_count, ge, SU_THREADS, n_entries, dofmap, n_rows, cnt.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(),
-             ptr.data(), static_cast<std::int64_t>(1));
+  emu_scan(static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(), ptr.data(), static_cast<std::int64_t>(1));
   pairs.assign(static_cast<std::size_t>(ptr[n_rows]), 0xFFFFFFFFu);
   std::fill(cnt.begin(), cnt.end(), 0ull);
   emu_launch(setup_fill, ge, SU_THREADS, n_entries, dofmap, n_rows, (const std::int64_t*)ptr.data(), cnt.data(),
@@ -84,6 +102,13 @@ void emu_pairs(int64_t n_entries, const int32_t* dofmap, int32_t n_rows, int shu
 } // namespace
 
 extern "C" {
+
+// the prefix sum alone (both routes of device_scan)
+int emu_scan_only(int64_t n, const unsigned long long* in, int64_t scale, int64_t* out)
+{
+  emu_scan(n, in, out, scale);
+  return 0;
+}
 
 // The launch sequence of gpu_build_pattern (setup.cu). rowptr [n_rows + 1] is always written; cols
 // (capacity cap) when the total fits (returns -1 otherwise). flags[2] as in setup.cu.
@@ -99,8 +124,7 @@ int emu_build_pattern(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_
   const unsigned gr = (n_rows + SU_THREADS - 1) / SU_THREADS;
   emu_launch(setup_pattern_count, gr, SU_THREADS, n_rows, nd, dofmap, (const std::int64_t*)ptr.data(),
              (const std::uint32_t*)pairs.data(), cnt.data(), flags);
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(), rowptr,
-             static_cast<std::int64_t>(1));
+  emu_scan(static_cast<std::int64_t>(n_rows), (const unsigned long long*)cnt.data(), rowptr, static_cast<std::int64_t>(1));
   if (flags[2] != 0 || rowptr[n_rows] > cap)
     return -1;
   emu_launch(setup_pattern_fill, gr, SU_THREADS, n_rows, nd, dofmap, (const std::int64_t*)ptr.data(),
@@ -120,15 +144,13 @@ int emu_setup_columns(int32_t n_rows, int64_t n_cols, int32_t n_slices, const in
   const unsigned gs = (n_slices + SU_THREADS - 1) / SU_THREADS;
   const unsigned gl = static_cast<unsigned>((static_cast<std::int64_t>(n_slices) * 32 + SU_THREADS - 1) / SU_THREADS);
   emu_launch(setup_widths, gs, SU_THREADS, n_rows, n_slices, rowptr, w.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), mat_off,
-             static_cast<std::int64_t>(32));
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), mat_off, static_cast<std::int64_t>(32));
   if (mat_off[n_slices] > cap)
     return -1;
   emu_launch(setup_sell_cols, gl, SU_THREADS, n_rows, n_slices, rowptr, cols, (const std::int64_t*)mat_off, cols_sell);
   emu_launch(setup_cdelta, gs, SU_THREADS, n_rows, n_cols, n_slices, rowptr, (const std::int64_t*)mat_off,
              (const std::int32_t*)cols_sell, cdelta, w.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), xoff,
-             static_cast<std::int64_t>(32));
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), xoff, static_cast<std::int64_t>(32));
   if (xoff[n_slices] > capx)
     return -1;
   emu_launch(setup_colsx, gl, SU_THREADS, n_slices, (const std::int64_t*)mat_off, (const std::int32_t*)cols_sell,
@@ -136,8 +158,7 @@ int emu_setup_columns(int32_t n_rows, int64_t n_cols, int32_t n_slices, const in
   std::vector<std::int64_t> pos(static_cast<std::size_t>(n_slices) + 1, -1);
   emu_launch(setup_slice_flags, gs, SU_THREADS, n_rows, n_slices, (const std::int64_t*)mat_off,
              (const std::int32_t*)cols_sell, w.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), pos.data(),
-             static_cast<std::int64_t>(1));
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)w.data(), pos.data(), static_cast<std::int64_t>(1));
   emu_launch(setup_slice_order, gs, SU_THREADS, n_slices, (const unsigned long long*)w.data(),
              (const std::int64_t*)pos.data(), order);
   *n_interior = static_cast<std::int32_t>(pos[n_slices]);
@@ -157,8 +178,7 @@ int emu_setup_pk(int64_t n_cells, int nd, const int32_t* dofmap, int32_t n_rows,
   emu_pairs(n_cells * nd, dofmap, n_rows, 1, ptr, pairs);
   emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
              (const std::int64_t*)ptr.data(), wa.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off,
-             static_cast<std::int64_t>(32));
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off, static_cast<std::int64_t>(32));
   if (adj_off[n_slices] > cap)
     return -1;
   flags[0] = flags[1] = 0;
@@ -185,8 +205,7 @@ int emu_setup_p1(int64_t n_cells, const int32_t* dofmap, int32_t n_rows, int32_t
   emu_pairs(n_cells * 4, dofmap, n_rows, shuffle, ptr, pairs);
   emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
              (const std::int64_t*)ptr.data(), wa.data());
-  emu_launch(setup_scan, 1, 1024, static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off,
-             static_cast<std::int64_t>(32));
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off, static_cast<std::int64_t>(32));
   if (adj_off[n_slices] > cap)
     return -1;
   flags[0] = flags[1] = 0;

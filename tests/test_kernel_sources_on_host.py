@@ -868,3 +868,15 @@ def test_device_setup_source_builds_the_p2_p3_slot_words(pt, emusu, order, dims,
     assert np.array_equal(adj_off, L["adj_off"])
     assert np.array_equal(adj, L["adj"])
     assert np.array_equal(adjso, L["adjso"])
+
+
+@pytest.mark.parametrize("n,scale", [(1, 1), (1000, 32), (8192, 1), (8193, 1), (16384, 32), (20001, 1)])
+def test_device_scan_source_both_routes(emusu, n, scale):
+    """The prefix sum of the setup kernels: one CTA up to a tile (8192 elements), three tile passes
+    beyond; exclusive, scaled, total at out[n]."""
+    rng = np.random.default_rng(n)
+    a = rng.integers(0, 50, size=n).astype(np.uint64)
+    out = np.full(n + 1, -1, np.int64)
+    assert emusu.emu_scan_only(C.c_int64(n), _p(a), C.c_int64(scale), _p(out)) == 0
+    ref = np.concatenate([[0], np.cumsum(a.astype(np.int64) * scale)])
+    assert np.array_equal(out, ref)
