@@ -48,7 +48,11 @@ struct WalkState
   std::uint32_t prev; // previous step word (bytes 0..2: columns the positions accumulate into)
 };
 
-template <int WARPS, bool PREFETCH>
+// EXACT: cofactor vectors by cross_rn (no FMA contraction), so that entries that vanish
+// analytically on the lattice are exact zeros -- selected when the operator is going to be
+// compacted (PTB_SPMV_COMPACT=1) or by PTB_ASM_EXACT_ZEROS=1; three more FP64 instructions per
+// recomputed cofactor vector.
+template <int WARPS, bool PREFETCH, bool EXACT = false>
 __global__ void __launch_bounds__(WARPS * 32, 14 / WARPS)
 assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
 {
@@ -166,12 +170,24 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
       W.e2 = Vec3{E[(o2 * 3 + 0) * 32], E[(o2 * 3 + 1) * 32], E[(o2 * 3 + 2) * 32]};
       W.a2 = 0.0;
     }
-    if (l1 || l2)
-      W.n0 = cross(W.e1, W.e2);
-    if (l2 || l0)
-      W.n1 = cross(W.e2, W.e0);
-    if (l0 || l1)
-      W.n2 = cross(W.e0, W.e1);
+    if constexpr (EXACT)
+    {
+      if (l1 || l2)
+        W.n0 = cross_rn(W.e1, W.e2);
+      if (l2 || l0)
+        W.n1 = cross_rn(W.e2, W.e0);
+      if (l0 || l1)
+        W.n2 = cross_rn(W.e0, W.e1);
+    }
+    else
+    {
+      if (l1 || l2)
+        W.n0 = cross(W.e1, W.e2);
+      if (l2 || l0)
+        W.n1 = cross(W.e2, W.e0);
+      if (l0 || l1)
+        W.n2 = cross(W.e0, W.e1);
+    }
     const double det = dot(W.e0, W.n0);
     const double r = valid ? rcp_nr(6.0 * fabs(det)) : 0.0;
     const Vec3 c0 = {-(W.n0.x + W.n1.x + W.n2.x), -(W.n0.y + W.n1.y + W.n2.y),
@@ -418,7 +434,9 @@ bool launch_walk(ptb_ctx* c, const MatrixArgs& A)
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * WARPS * sizeof(double);
   if (smem > 227 * 1024)
     return false;
-  auto kernel = assemble_matrix_p1_walk<WARPS, PREFETCH>;
+  // not yet run on a GPU: the EXACT variant; the default stays the measured kernel
+  const bool exact = env_flag("PTB_ASM_EXACT_ZEROS", env_flag("PTB_SPMV_COMPACT", false));
+  auto kernel = exact ? assemble_matrix_p1_walk<WARPS, PREFETCH, true> : assemble_matrix_p1_walk<WARPS, PREFETCH, false>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 static_cast<int>(smem)));
   kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->walk.p);

@@ -17,6 +17,16 @@ __device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
 {
   return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
 }
+// The same without FMA contraction: with `a.y * b.z - a.z * b.y` contracted into fma(a.y, b.z, -(a.z * b.y))
+// a component that cancels analytically (both products of the same factors, as for the axis-aligned
+// edges of the reference's lattice) comes out as the rounding error of one product, ~1e-17 of the
+// entry's scale, instead of 0.0. Two rounded products and a subtraction give the exact zero, so the
+// assembled lattice operator holds exact zeros where the 7-point stencil has none (compact.cu drops them).
+__device__ __forceinline__ Vec3 cross_rn(Vec3 a, Vec3 b)
+{
+  return {__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
+          __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x))};
+}
 __device__ __forceinline__ double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ double comp(Vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }
 

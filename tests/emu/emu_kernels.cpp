@@ -30,6 +30,9 @@ static thread_local EmuIdx threadIdx, blockIdx;
 static EmuIdx blockDim, gridDim;
 static std::barrier<>* emu_barrier = nullptr;
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
+// the non-contracting intrinsics (cross_rn): plain operations, the harness is built without FMA
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T>
 static inline T __ldg(const T* p)
 {
@@ -106,6 +109,7 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
   switch (variant)
   {
   case 0: emu_launch(assemble_matrix_p1_walk<1, true>, n_slices, 32, A, walk); break;
+  case 6: emu_launch(assemble_matrix_p1_walk<1, true, true>, n_slices, 32, A, walk); break; // cross_rn
   case 1: emu_launch(assemble_matrix_p1_walk<2, false>, (n_slices + 1) / 2, 64, A, walk); break;
   case 2:
     if (bs != 3)
