@@ -24,8 +24,12 @@ __device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
 // assembled lattice operator holds exact zeros where the 7-point stencil has none (compact.cu drops them).
 __device__ __forceinline__ Vec3 cross_rn(Vec3 a, Vec3 b)
 {
+#ifdef PTB_HOST_EMU // tests/emu: built without FMA contraction, the plain form is already the exact one
+  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+#else
   return {__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
           __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x))};
+#endif
 }
 __device__ __forceinline__ double dot(Vec3 a, Vec3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ double comp(Vec3 a, int i) { return i == 0 ? a.x : (i == 1 ? a.y : a.z); }

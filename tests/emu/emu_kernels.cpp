@@ -30,9 +30,6 @@ static thread_local EmuIdx threadIdx, blockIdx;
 static EmuIdx blockDim, gridDim;
 static std::barrier<>* emu_barrier = nullptr;
 static inline void __syncthreads() { emu_barrier->arrive_and_wait(); }
-// the non-contracting intrinsics (cross_rn): plain operations, the harness is built without FMA
-static inline double __dmul_rn(double a, double b) { return a * b; }
-static inline double __dsub_rn(double a, double b) { return a - b; }
 template <typename T>
 static inline T __ldg(const T* p)
 {
