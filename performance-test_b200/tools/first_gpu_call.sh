@@ -10,7 +10,7 @@ mkdir -p "$out"
 export PTB_TEST_OPTIN=1
 echo "== opt-in parity tests"
 timeout 400 python -m pytest tests/test_gpu_parity.py -q -s -k "opt_in or persistent or star_walk or binned or compaction" 2>&1 | tail -40 | tee "$out/optin_tests.txt"
-timeout 200 python -m pytest tests/test_cli.py -q -k device_setup 2>&1 | tail -5 | tee -a "$out/optin_tests.txt"
+timeout 200 python -m pytest tests/test_cli.py tests/test_gpu_multi.py -q -k "device_setup or device_generated" 2>&1 | tail -5 | tee -a "$out/optin_tests.txt"
 echo "== the reference's timing table with the setup on the host and on the device (Poisson 4M DOFs)"
 for ds in "" "--device_setup"; do
   PTB_GPU_SETUP=1 timeout 200 performance-test_b200/dolfinx-scaling-test --ndofs 4000000 -ksp_rtol 1e-8 $ds \
@@ -59,6 +59,7 @@ done
 # Two GPUs (gpurun --gpus 2): the existing 2-rank tests with the persistent loop switched on; the
 # spawned ranks inherit the environment, so no extra test code is needed:
 #   PTB_CG_PERSISTENT=1 timeout 300 python -m pytest tests/test_gpu_multi.py -q -k peer
+#   PTB_TEST_DEVICE_SETUP=1 PTB_GPU_SETUP=1 timeout 300 python -m pytest tests/test_gpu_multi.py -q -k two_rank
 # then the strong-scaling point that motivated the kernel:
 #   for p in 0 1; do PTB_CG_PERSISTENT=$p python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 \
 #     --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --workload elasticity --steps 2 --warmup 1; done

@@ -47,6 +47,46 @@ def test_partitioned_assembly_is_partition_independent(pt, ptype, order, dims, w
     ctx.close()
 
 
+@pytest.mark.skipif(os.environ.get("PTB_TEST_OPTIN") != "1",
+                    reason="opt-in path not yet validated on a GPU (PTB_TEST_OPTIN=1)")
+@pytest.mark.parametrize("ptype,order,dims,world",
+                         [("poisson", 1, (9, 8, 10), 3), ("elasticity", 1, (6, 5, 8), 2),
+                          ("poisson", 2, (4, 5, 6), 2), ("poisson", 3, (3, 3, 5), 2)])
+def test_opt_in_device_generated_slabs_are_partition_independent(pt, monkeypatch, ptype, order, dims, world):
+    """The same check with every rank's slab generated on the device (ptb_create_box with rank > 0:
+    ghost layer below, ghost plane above; pattern, layouts and maps device-built with
+    PTB_GPU_SETUP=1): rows and right-hand side equal the serial host-built ones bit for bit, except
+    that f and g come from the device's exp / sin (<= 4 ulp), so b is compared to 1e-14."""
+    S = pt.host.Problem(ptype, order, *dims)
+    monkeypatch.setenv("PTB_GPU_SETUP", "1")
+    ctx = pt.abi.Context(0)
+    ctx.set_problem(S)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_s, b_s = ctx.matrix_values().copy(), ctx.rhs().copy()
+    bs = S.bs
+    for rank in range(world):
+        P = pt.host.Problem(ptype, order, *dims, rank, world)
+        ctx.set_problem_on_device(P)
+        assert np.array_equal(ctx.dofmap(), P["dofmap"]) and np.array_equal(ctx.mesh()[0], P["x"])
+        rp, cl = ctx.pattern()
+        assert np.array_equal(rp, P["rowptr"]) and np.array_equal(cl, P["cols"])
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        A, b = ctx.matrix_values(), ctx.rhs()
+        off, n = P.global_offset, P.n_owned
+        assert np.abs(b - b_s[off * bs:(off + n) * bs]).max() <= 1e-14 * np.abs(b_s).max()
+        l2g = np.concatenate([np.arange(off, off + n), P["ghost_global"]])
+        for r in range(n):
+            g = l2g[cl[rp[r]:rp[r + 1]]]
+            o = np.argsort(g)
+            srow = slice(S["rowptr"][off + r], S["rowptr"][off + r + 1])
+            assert np.array_equal(g[o], S["cols"][srow])
+            assert np.array_equal(A.reshape(-1, bs * bs)[rp[r]:rp[r + 1]][o],
+                                  A_s.reshape(-1, bs * bs)[srow])
+    ctx.close()
+
+
 def _worker(rank, world, port, ptype, dims, comm, out):
     sys.path.insert(0, ROOT)
     import torch
@@ -59,7 +99,10 @@ def _worker(rank, world, port, ptype, dims, comm, out):
         pt = importlib.import_module("performance-test_b200")
         ctx = pt.abi.Context(rank)
         P = pt.host.Problem(ptype, 1, *dims, rank, world)
-        ctx.set_problem(P)
+        if os.environ.get("PTB_TEST_DEVICE_SETUP") == "1":  # opt-in: the slab generated on the device
+            ctx.set_problem_on_device(P)
+        else:
+            ctx.set_problem(P)
         if comm == "nccl":
             pt.dist.init_nccl(ctx, pt.abi, dist, rank, world)
         else:
