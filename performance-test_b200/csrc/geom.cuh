@@ -24,8 +24,10 @@ __device__ __forceinline__ Vec3 cross(Vec3 a, Vec3 b)
 // assembled lattice operator holds exact zeros where the 7-point stencil has none (compact.cu drops them).
 __device__ __forceinline__ Vec3 cross_rn(Vec3 a, Vec3 b)
 {
-#ifdef PTB_HOST_EMU // tests/emu: built without FMA contraction, the plain form is already the exact one
-  return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+#ifdef PTB_HOST_EMU // tests/emu: the products go through volatile so that a harness built with
+                    // -ffp-contract=fast (the FMA variant of the tests) cannot contract them either
+  volatile double p0 = a.y * b.z, q0 = a.z * b.y, p1 = a.z * b.x, q1 = a.x * b.z, p2 = a.x * b.y, q2 = a.y * b.x;
+  return {p0 - q0, p1 - q1, p2 - q2};
 #else
   return {__dsub_rn(__dmul_rn(a.y, b.z), __dmul_rn(a.z, b.y)), __dsub_rn(__dmul_rn(a.z, b.x), __dmul_rn(a.x, b.z)),
           __dsub_rn(__dmul_rn(a.x, b.y), __dmul_rn(a.y, b.x))};

@@ -13,8 +13,13 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+# PTB_EMU_FMA=1 builds every harness the way nvcc builds the kernels -- products and sums contracted
+# into fused multiply-adds -- into its own directory: the 1e-12 parity bounds must hold there too.
+FMA = os.environ.get("PTB_EMU_FMA") == "1"
+CXXFLAGS = ["-O2", "-mfma", "-ffp-contract=fast"] if FMA else ["-O1"]
+BUILD = "_build_fma" if FMA else "_build"
 SRC = os.path.join(HERE, "emu", "emu_kernels.cpp")
-OUT = os.path.join(HERE, "emu", "_build", "libemu.so")
+OUT = os.path.join(HERE, "emu", BUILD, "libemu.so")
 CSRC = os.path.join(os.path.dirname(HERE), "performance-test_b200", "csrc")
 
 
@@ -25,9 +30,28 @@ def emu():
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-o", OUT, SRC], check=True)
     return C.CDLL(OUT)
+
+
+OUT_FMA = os.path.join(HERE, "emu", "_build", "libemu_fma.so")  # always the FMA build
+
+
+@pytest.fixture(scope="module")
+def emu_fma():
+    """The same harness built the way nvcc builds the kernels: products and sums contracted into
+    fused multiply-adds (-mfma -ffp-contract=fast). Needs a host CPU with FMA."""
+    if "fma" not in open("/proc/cpuinfo").read().split():
+        pytest.skip("host CPU without FMA")
+    deps = [SRC] + [os.path.join(CSRC, f) for f in
+                    ("assemble_walk.cu", "assemble_gwalk.cu", "geom.cuh", "kernels.h", "ctx.h")]
+    if not os.path.exists(OUT_FMA) or any(os.path.getmtime(d) > os.path.getmtime(OUT_FMA) for d in deps):
+        os.makedirs(os.path.dirname(OUT_FMA), exist_ok=True)
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O2", "-mfma", "-ffp-contract=fast", "-fPIC", "-shared",
+                        "-pthread", "-w", "-I", cuda_inc, "-o", OUT_FMA, SRC], check=True)
+    return C.CDLL(OUT_FMA)
 
 
 def _p(a):
@@ -109,6 +133,39 @@ def test_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emu, perturbed, 
         assert np.array_equal(got == 0.0, ref == 0.0) and (ref == 0.0).mean() > 0.3
 
 
+@pytest.mark.parametrize("dims,rank,nranks", [((5, 4, 6), 0, 1), ((7, 3, 5), 1, 2)])
+def test_contracted_arithmetic_leaves_residue_where_the_exact_variant_has_zeros(pt, oracle, emu_fma, perturbed, dims,
+                                                                                 rank, nranks):
+    """What fused multiply-adds do to the lattice operator, shown on the host: with contraction the
+    default star-walk kernel leaves rounding residue (~1e-17 of the diagonal) in entries that vanish
+    analytically, its EXACT instantiation (cofactor vectors without contraction) gives the oracle's
+    exact zeros -- the reason PTB_SPMV_COMPACT=1 selects it. Both stay within 1e-12 of the oracle,
+    on the lattice and on a jittered mesh."""
+    for jitter in (False, True):
+        P = pt.host.Problem("poisson", 1, *dims, rank, nranks)
+        if jitter:
+            P = perturbed(P)
+        L, xdof, bc = _inputs(pt, P)
+        ref = oracle.assemble_matrix(P)
+        rp = np.ascontiguousarray(P["rowptr"])
+        got = {}
+        for variant in (0, 6):
+            vals = np.full(int(L["mat_off"][-1]), np.nan)
+            dinv = np.full(P.n_owned, np.nan)
+            assert emu_fma.emu_assemble_matrix(variant, P.n_owned, L["n_slices"], L["max_w"], 1, _p(bc), _p(rp),
+                                               _p(L["mat_off"]), _p(L["adj_off"]), _p(L["cols"]), _p(xdof),
+                                               _p(L["walk"]), _p(L["walk1"]), _p(L["walk1_off"]), _p(vals),
+                                               _p(dinv)) == 0
+            got[variant] = _sell_to_csr(P, L, vals, 1)
+            assert (np.abs(got[variant] - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
+        if not jitter:
+            zeros = ref == 0.0
+            assert zeros.mean() > 0.3                                   # the 7-point stencil in 15 entries
+            assert np.array_equal(got[6] == 0.0, zeros)                 # exact variant: exact zeros
+            residue = np.abs(got[0][zeros]) / _row_diag(P, ref, 1)[zeros]
+            assert np.count_nonzero(residue) > 0 and residue.max() < 1e-15   # contracted: residue
+
+
 VECTOR = [("poisson", (5, 4, 6), 0, 1, 4), ("poisson", (1, 1, 1), 0, 1, 1), ("poisson", (4, 3, 5), 1, 2, 4),
           ("elasticity", (3, 4, 3), 0, 1, 4), ("elasticity", (2, 2, 5), 1, 2, 8)]
 
@@ -150,13 +207,13 @@ CGSTATE = np.dtype([("py", "f8"), ("rr", "f8"), ("rz", "f8"), ("rz_old", "f8"), 
 @pytest.fixture(scope="module")
 def emucg():
     import shutil
-    base = os.path.join(HERE, "emu", "_build", "libemucg.so")
+    base = os.path.join(HERE, "emu", BUILD, "libemucg.so")
     deps = [CG_SRC] + [os.path.join(CSRC, f) for f in
                        ("cg.cu", "reduce.cuh", "peer.cuh", "peer.h", "sync_ops.cuh", "kernels.h", "ctx.h")]
     if not os.path.exists(base) or any(os.path.getmtime(d) > os.path.getmtime(base) for d in deps):
         os.makedirs(os.path.dirname(base), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-o", base, CG_SRC], check=True)
     libs = []
     for g in range(4):  # one copy per CTA: `__shared__` variables are statics of the copy
@@ -339,7 +396,7 @@ PK_SRC = os.path.join(HERE, "emu", "emu_pk.cpp")
 
 @pytest.fixture(scope="module")
 def emupk():
-    out = os.path.join(HERE, "emu", "_build", "libemupk.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemupk.so")
     deps = [PK_SRC] + [os.path.join(CSRC, f) for f in ("assemble_pk.cu", "element_tables.h", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -350,7 +407,7 @@ def emupk():
         with open(copy, "w") as f:
             f.write(text)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_PK_SOURCE="{copy}"', "-o", out, PK_SRC],
                        check=True)
     return C.CDLL(out)
@@ -396,12 +453,12 @@ P1_SRC = os.path.join(HERE, "emu", "emu_p1.cpp")
 
 @pytest.fixture(scope="module")
 def emup1():
-    out = os.path.join(HERE, "emu", "_build", "libemup1.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemup1.so")
     deps = [P1_SRC] + [os.path.join(CSRC, f) for f in ("assemble.cu", "geom.cuh", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-o", out, P1_SRC], check=True)
     return C.CDLL(out)
 
@@ -498,7 +555,7 @@ CP_SRC = os.path.join(HERE, "emu", "emu_compact.cpp")
 
 @pytest.fixture(scope="module")
 def emucp():
-    out = os.path.join(HERE, "emu", "_build", "libemucompact.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemucompact.so")
     deps = [CP_SRC] + [os.path.join(CSRC, f) for f in ("compact.cu", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -507,7 +564,7 @@ def emucp():
         with open(copy, "w") as f:
             f.write(text)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_COMPACT_SOURCE="{copy}"', "-o", out, CP_SRC],
                        check=True)
     return C.CDLL(out)
@@ -588,7 +645,7 @@ SU_SRC = os.path.join(HERE, "emu", "emu_setup.cpp")
 
 @pytest.fixture(scope="module")
 def emusu():
-    out = os.path.join(HERE, "emu", "_build", "libemusetup.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemusetup.so")
     deps = [SU_SRC] + [os.path.join(CSRC, f) for f in ("setup.cu", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
@@ -597,7 +654,7 @@ def emusu():
         with open(copy, "w") as f:
             f.write(text)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-fPIC", "-shared", "-pthread", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-fPIC", "-shared", "-pthread", "-w",
                         "-I", cuda_inc, "-I", CSRC, f'-DPTB_EMU_SETUP_SOURCE="{copy}"', "-o", out, SU_SRC],
                        check=True)
     return C.CDLL(out)
@@ -677,12 +734,12 @@ PD_SRC = os.path.join(HERE, "emu", "emu_problem_data.cpp")
 
 @pytest.fixture(scope="module")
 def emupd():
-    out = os.path.join(HERE, "emu", "_build", "libemuproblemdata.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemuproblemdata.so")
     deps = [PD_SRC] + [os.path.join(CSRC, f) for f in ("problem_data.cu", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-ffp-contract=off", "-fPIC", "-shared", "-w",
                         "-I", cuda_inc, "-I", CSRC, "-o", out, PD_SRC], check=True)
     return C.CDLL(out)
 
@@ -773,12 +830,12 @@ BX_SRC = os.path.join(HERE, "emu", "emu_box.cpp")
 
 @pytest.fixture(scope="module")
 def emubx():
-    out = os.path.join(HERE, "emu", "_build", "libemubox.so")
+    out = os.path.join(HERE, "emu", BUILD, "libemubox.so")
     deps = [BX_SRC] + [os.path.join(CSRC, f) for f in ("box.cu", "kernels.h", "ctx.h")]
     if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
         os.makedirs(os.path.dirname(out), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
-        subprocess.run(["/usr/bin/g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+        subprocess.run(["/usr/bin/g++", "-std=c++20", *CXXFLAGS, "-ffp-contract=off", "-fPIC", "-shared", "-w",
                         "-I", cuda_inc, "-I", CSRC, "-o", out, BX_SRC], check=True)
     return C.CDLL(out)
 
