@@ -1,6 +1,5 @@
 #include "layout.h"
 #include <algorithm>
-#include <map>
 #include <stdexcept>
 
 namespace ptb
@@ -432,7 +431,14 @@ void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
     for (int s = 0; s < nf; ++s)
       on[lf].push_back(4 + 6 * ne + lf * nf + s);
   }
-  std::map<std::int32_t, std::vector<std::int32_t>> rows; // ordered by row; entries ascending in k
+  // (row, cell, local_facet*nd + li) for every facet dof on an owned row, in facet order; a stable
+  // sort by row then gives the rows ascending with their entries ascending in k
+  struct Ent
+  {
+    std::int32_t row, cell, code;
+  };
+  std::vector<Ent> all;
+  all.reserve(static_cast<std::size_t>(n_facets) * on[0].size());
   for (std::int64_t k = 0; k < n_facets; ++k)
   {
     const std::int32_t c = cells[k], lf = local_facets[k];
@@ -442,17 +448,25 @@ void build_facet_rows(std::int64_t n_facets, const std::int32_t* cells,
     {
       const std::int32_t r = dofmap[static_cast<std::int64_t>(c) * nd + li];
       if (r < n_rows)
-        rows[r].push_back(c), rows[r].push_back(lf * nd + li);
+        all.push_back({r, c, lf * nd + li});
     }
   }
+  std::stable_sort(all.begin(), all.end(), [](const Ent& a, const Ent& b) { return a.row < b.row; });
   row_ids.clear(), ent.clear();
   row_ptr.assign(1, 0);
-  for (auto& [r, v] : rows)
+  ent.reserve(all.size() * 2);
+  for (std::size_t i = 0; i < all.size(); ++i)
   {
-    row_ids.push_back(r);
-    ent.insert(ent.end(), v.begin(), v.end());
-    row_ptr.push_back(static_cast<std::int32_t>(ent.size() / 2));
+    if (i == 0 || all[i].row != all[i - 1].row)
+    {
+      if (i > 0)
+        row_ptr.push_back(static_cast<std::int32_t>(i));
+      row_ids.push_back(all[i].row);
+    }
+    ent.push_back(all[i].cell), ent.push_back(all[i].code);
   }
+  if (!all.empty())
+    row_ptr.push_back(static_cast<std::int32_t>(all.size()));
 }
 
 void build_facet_rows_gathered(std::int64_t n_facets, const std::int32_t* cells,

@@ -126,3 +126,34 @@ def test_no_cpu_fallback(pt):
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CUDA device"):
         pt.abi.Context(0)
+
+
+@pytest.mark.parametrize("ptype,order,dims,rank,nranks", [("poisson", 1, (5, 4, 6), 0, 1), ("poisson", 1, (4, 3, 5), 1, 2),
+                                                          ("poisson", 2, (3, 2, 4), 0, 1), ("poisson", 3, (2, 3, 2), 1, 2),
+                                                          ("elasticity", 1, (3, 4, 3), 0, 1)])
+def test_facet_rows_equal_a_numpy_restatement(pt, ptype, order, dims, rank, nranks):
+    """Boundary-facet gather lists of assemble_vector (layout.cpp build_facet_rows): for every owned
+    row the (cell, local_facet*nd + li) entries of the exterior facets that contain the dof, rows
+    ascending, entries in facet order. Closure of a facet in the Basix layout: vertices, edges, faces."""
+    import numpy as np
+    P = pt.host.Problem(ptype, order, *dims, rank, nranks)
+    nd, ne, nf = P.nd, order - 1, (order - 1) * (order - 2) // 2
+    edges = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]
+    on = []
+    for lf in range(4):
+        dofs = [v for v in range(4) if v != lf]
+        dofs += [4 + e * ne + s for e, (a, b) in enumerate(edges) if a != lf and b != lf for s in range(ne)]
+        dofs += [4 + 6 * ne + lf * nf + s for s in range(nf)]
+        on.append(dofs)
+    dm = np.asarray(P["dofmap"]).reshape(-1, nd)
+    rows = {}
+    for c, lf in zip(P["facet_cells"], P["facet_local"]):
+        for li in on[lf]:
+            r = int(dm[c, li])
+            if r < P.n_owned:
+                rows.setdefault(r, []).extend([int(c), int(lf) * nd + li])
+    ids_ref = np.array(sorted(rows), np.int32)
+    ent_ref = np.array([v for r in sorted(rows) for v in rows[r]], np.int32)
+    ptr_ref = np.concatenate([[0], np.cumsum([len(rows[r]) // 2 for r in sorted(rows)])]).astype(np.int32)
+    ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], nd, order, P.n_owned)
+    assert np.array_equal(ids, ids_ref) and np.array_equal(ptr, ptr_ref) and np.array_equal(ent, ent_ref)
