@@ -459,6 +459,9 @@ def test_opt_in_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, 
     P = pt.host.Problem("poisson", 1, *dims)
     p = np.random.default_rng(9).standard_normal(P.n_owned + P.n_ghost)
     out = {}
+    # the same matrix kernel in both runs: PTB_SPMV_COMPACT=1 alone would also switch the assembly
+    # to its EXACT instantiation, whose values differ from the default's in the last bits
+    monkeypatch.setenv("PTB_ASM_EXACT_ZEROS", "1")
     for flag in ("0", "1"):
         monkeypatch.setenv("PTB_SPMV_COMPACT", flag)
         c = pt.abi.Context(0)
@@ -482,6 +485,7 @@ def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol
     (cross_rn), so the analytic zeros of the lattice are exact zeros and tol 0 already drops them."""
     P = pt.host.Problem("poisson", 1, 40, 38, 41)
     p = np.random.default_rng(9).standard_normal(P.n_owned + P.n_ghost)
+    monkeypatch.setenv("PTB_ASM_EXACT_ZEROS", "1")   # one matrix kernel for the full and the compacted run
     monkeypatch.setenv("PTB_SPMV_COMPACT", "0")
     c = pt.abi.Context(0)
     c.set_problem(P)
