@@ -79,11 +79,18 @@ __device__ __forceinline__ StepBits gw_decode(std::uint32_t word)
 // Matrix, scalar P1. One warp = one slice; no barrier (shared memory is private per lane).
 // Shared memory per slice: C [w][32] int32 columns, acc [w][32] doubles.
 // ------------------------------------------------------------------------------------------
-template <int WARPS>
+// EXACT: cofactor vectors without FMA contraction (geom.cuh cross_rn), as in assemble_matrix_p1_walk.
+template <int WARPS, bool EXACT = false>
 __global__ void __launch_bounds__(WARPS * 32)
 assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
                          const std::int64_t* __restrict__ walk1_off)
 {
+  auto cofactor = [](Vec3 a, Vec3 b) {
+    if constexpr (EXACT)
+      return cross_rn(a, b);
+    else
+      return cross(a, b);
+  };
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const std::int32_t slice = blockIdx.x * WARPS + warp;
@@ -149,7 +156,7 @@ assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
   for (int j = 0; j < GW_AHEAD; ++j)
     q[j] = gw_issue<0>(wd[j], C, A.xdof, nullptr, 1, 0);
   int s0 = o0, s1 = o1, s2 = o2; // offsets the three accumulators belong to
-  Vec3 n0 = cross(e1, e2), n1 = cross(e2, e0), n2 = cross(e0, e1);
+  Vec3 n0 = cofactor(e1, e2), n1 = cofactor(e2, e0), n2 = cofactor(e0, e1);
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, dg = 0.0;
   auto cell = [&](bool compute) {
     const double det = dot(e0, n0);
@@ -177,11 +184,11 @@ assemble_matrix_p1_gwalk(MatrixArgs A, const std::uint32_t* __restrict__ walk1,
     if (S.p2)
       a2 = 0.0, e2 = xn - X0, s2 = S.nw;
     if (S.p1 || S.p2)
-      n0 = cross(e1, e2);
+      n0 = cofactor(e1, e2);
     if (S.p2 || S.p0)
-      n1 = cross(e2, e0);
+      n1 = cofactor(e2, e0);
     if (S.p0 || S.p1)
-      n2 = cross(e0, e1);
+      n2 = cofactor(e0, e1);
     cell(S.compute);
   };
   for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
@@ -633,7 +640,8 @@ void launch_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A)
 {
   const std::size_t per_slice = (static_cast<std::size_t>(c->max_w) * 32 + (static_cast<std::size_t>(c->max_w) * 32 + 1) / 2) * sizeof(double);
   const std::size_t smem = per_slice * WARPS;
-  auto kernel = assemble_matrix_p1_gwalk<WARPS>;
+  const bool exact = env_flag("PTB_ASM_EXACT_ZEROS", env_flag("PTB_SPMV_COMPACT", false));
+  auto kernel = exact ? assemble_matrix_p1_gwalk<WARPS, true> : assemble_matrix_p1_gwalk<WARPS, false>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
 }

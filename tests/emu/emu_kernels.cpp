@@ -115,6 +115,7 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
     break;
   case 3: emu_launch(assemble_matrix_p1_gwalk<4>, (n_slices + 3) / 4, 128, A, walk1, walk1_off); break;
   case 4: emu_launch(assemble_matrix_p1_gwalk<1>, n_slices, 32, A, walk1, walk1_off); break;
+  case 7: emu_launch(assemble_matrix_p1_gwalk<1, true>, n_slices, 32, A, walk1, walk1_off); break; // cross_rn
   case 5:
     if (bs != 3)
       return 2;

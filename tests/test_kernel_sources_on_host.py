@@ -90,6 +90,7 @@ def _row_diag(P, ref, bs2):
 MATRIX = [(0, "poisson", (5, 4, 6), 0, 1), (1, "poisson", (5, 4, 6), 0, 1), (0, "poisson", (1, 1, 1), 0, 1),
           (3, "poisson", (5, 4, 6), 0, 1), (4, "poisson", (3, 7, 2), 0, 1), (3, "poisson", (1, 1, 1), 0, 1),
           (3, "poisson", (4, 3, 5), 1, 2), (6, "poisson", (5, 4, 6), 0, 1), (6, "poisson", (4, 3, 5), 1, 2),
+          (7, "poisson", (5, 4, 6), 0, 1), (7, "poisson", (4, 3, 5), 1, 2),
           (2, "elasticity", (4, 3, 3), 0, 1), (2, "elasticity", (1, 1, 2), 0, 1), (2, "elasticity", (3, 3, 4), 1, 2),
           (5, "elasticity", (4, 3, 3), 0, 1), (5, "elasticity", (1, 1, 2), 0, 1), (5, "elasticity", (3, 3, 4), 1, 2)]
 
@@ -127,7 +128,7 @@ def test_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emu, perturbed, 
             for e in range(bs2):
                 mask[(mo + k * 32) * bs2 + e * 32 + (r & 31)] = False
     assert np.all(vals[mask] == 0.0)
-    if variant == 6 and not jitter:
+    if variant in (6, 7) and not jitter:
         # the EXACT variant on the lattice: every entry that the oracle (no FMA) computes as an exact
         # zero is an exact zero here too -- the 7-point stencil inside the 15-entry pattern
         assert np.array_equal(got == 0.0, ref == 0.0) and (ref == 0.0).mean() > 0.3
@@ -149,7 +150,7 @@ def test_contracted_arithmetic_leaves_residue_where_the_exact_variant_has_zeros(
         ref = oracle.assemble_matrix(P)
         rp = np.ascontiguousarray(P["rowptr"])
         got = {}
-        for variant in (0, 6):
+        for variant in (0, 6, 4, 7):
             vals = np.full(int(L["mat_off"][-1]), np.nan)
             dinv = np.full(P.n_owned, np.nan)
             assert emu_fma.emu_assemble_matrix(variant, P.n_owned, L["n_slices"], L["max_w"], 1, _p(bc), _p(rp),
@@ -161,9 +162,10 @@ def test_contracted_arithmetic_leaves_residue_where_the_exact_variant_has_zeros(
         if not jitter:
             zeros = ref == 0.0
             assert zeros.mean() > 0.3                                   # the 7-point stencil in 15 entries
-            assert np.array_equal(got[6] == 0.0, zeros)                 # exact variant: exact zeros
-            residue = np.abs(got[0][zeros]) / _row_diag(P, ref, 1)[zeros]
-            assert np.count_nonzero(residue) > 0 and residue.max() < 1e-15   # contracted: residue
+            for exact, plain in ((6, 0), (7, 4)):                       # star walk, direct-gather walk
+                assert np.array_equal(got[exact] == 0.0, zeros)         # exact variant: exact zeros
+                residue = np.abs(got[plain][zeros]) / _row_diag(P, ref, 1)[zeros]
+                assert np.count_nonzero(residue) > 0 and residue.max() < 1e-15   # contracted: residue
 
 
 VECTOR = [("poisson", (5, 4, 6), 0, 1, 4), ("poisson", (1, 1, 1), 0, 1, 1), ("poisson", (4, 3, 5), 1, 2, 4),
