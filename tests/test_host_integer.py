@@ -157,3 +157,21 @@ def test_facet_rows_equal_a_numpy_restatement(pt, ptype, order, dims, rank, nran
     ptr_ref = np.concatenate([[0], np.cumsum([len(rows[r]) // 2 for r in sorted(rows)])]).astype(np.int32)
     ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], nd, order, P.n_owned)
     assert np.array_equal(ids, ids_ref) and np.array_equal(ptr, ptr_ref) and np.array_equal(ent, ent_ref)
+
+
+def test_host_sizes_only_modes_agree_with_the_full_build(tmp_path):
+    """create_box_mesh(..., with_arrays=false) and create_functionspace(..., with_dofmap=false) --
+    what the CLI keeps on the host under --device_setup -- give the same sizes, ranges, ghost, halo
+    and exterior-facet lists as the full build, on every rank of a partition, P1-P3."""
+    import ctypes
+    import os
+    import subprocess
+    here = os.path.dirname(os.path.abspath(__file__))
+    out = str(tmp_path / "libhostmodes.so")
+    subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-fopenmp", "-w", "-o", out,
+                    os.path.join(here, "emu", "host_header_modes.cpp")], check=True)
+    lib = ctypes.CDLL(out)
+    lib.header_modes_agree.argtypes = [ctypes.c_int, ctypes.c_int] + [ctypes.c_long] * 3 + [ctypes.c_int] * 2
+    for order, bs, dims, nranks in ((1, 1, (5, 4, 6), 1), (1, 3, (3, 3, 7), 3), (2, 1, (3, 2, 5), 2), (3, 1, (2, 2, 4), 4)):
+        for rank in range(nranks):
+            assert lib.header_modes_agree(order, bs, *dims, rank, nranks) == 0, (order, dims, rank, nranks)
