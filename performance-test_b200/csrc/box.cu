@@ -173,18 +173,6 @@ __global__ void gather_dofmap_rows(std::int64_t n, int nd, const std::int32_t* _
   out[i] = dofmap[static_cast<std::int64_t>(cells[i / nd]) * nd + i % nd];
 }
 
-} // namespace
-
-#ifndef PTB_HOST_EMU // host side: device build only
-void launch_gather_dofmap_rows(ptb_ctx* c, std::int64_t n, const std::int32_t* cells, std::int32_t* out)
-{
-  const std::int64_t t = n * c->nd;
-  gather_dofmap_rows<<<static_cast<unsigned>((t + BX_THREADS - 1) / BX_THREADS), BX_THREADS, 0, c->stream>>>(
-      n, c->nd, cells, c->dofmap.p, out);
-  PTB_CUDA(cudaGetLastError());
-  c->launches += 1;
-}
-
 // The numbering of the order by value (common/kuhn_space.h: Numbering + local table).
 SpaceDims make_space_dims(std::int64_t nx, std::int64_t ny, std::int64_t nz, int order)
 {
@@ -227,6 +215,18 @@ BoxDims make_box_dims(std::int64_t nx, std::int64_t ny, std::int64_t nz, int ran
   B.Glow = B.l0 * S;
   B.Ghigh = last ? B.G1 : B.G1 + N.PS;
   return B;
+}
+
+} // namespace
+
+#ifndef PTB_HOST_EMU // host side: device build only
+void launch_gather_dofmap_rows(ptb_ctx* c, std::int64_t n, const std::int32_t* cells, std::int32_t* out)
+{
+  const std::int64_t t = n * c->nd;
+  gather_dofmap_rows<<<static_cast<unsigned>((t + BX_THREADS - 1) / BX_THREADS), BX_THREADS, 0, c->stream>>>(
+      n, c->nd, cells, c->dofmap.p, out);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
 }
 
 // Generates the local slab on the device and fills what ptb_set_mesh and the mesh-dependent half

@@ -38,30 +38,20 @@ void emu_launch(K kernel, std::int64_t n_threads, unsigned block, Args... args)
 
 extern "C" {
 
-// dims = nx, ny, nz, l0, l1, G0, G1, Glow, Ghigh (BoxDims as make_box_dims of box.cu fills it; the
-// test computes it independently). The numbering and the local table come from common/kuhn_space.h
-// exactly as make_space_dims packs them. dofmap [n_cells * nd]; dof_x [(n_owned + n_ghost) * 3].
-int emu_create_box(const int64_t* dims, int order, double* xyz3, double* xyz4, int32_t* dof_vertex,
-                   int32_t* x_dofmap, int32_t* dofmap, double* dof_x, int* flags)
+// The slab of `rank` of `nranks` exactly as gpu_create_box sets it up: make_space_dims and
+// make_box_dims are the product's own host functions. dims_out receives the BoxDims (nx, ny, nz, l0,
+// l1, G0, G1, Glow, Ghigh) for the test's independent check. dofmap [n_cells * nd]; dof_x
+// [(n_owned + n_ghost) * 3].
+int emu_create_box(int64_t nx, int64_t ny, int64_t nz, int rank, int nranks, int order, int64_t* dims_out,
+                   double* xyz3, double* xyz4, int32_t* dof_vertex, int32_t* x_dofmap, int32_t* dofmap,
+                   double* dof_x, int* flags)
 {
   using namespace ptb;
-  BoxDims B{dims[0], dims[1], dims[2], dims[3], dims[4], dims[5], dims[6], dims[7], dims[8]};
-  const kuhn::Numbering K(B.nx, B.ny, B.nz, order);
-  std::vector<kuhn::LocalDof> tab;
-  kuhn::build_local_table(order, tab);
-  SpaceDims N{};
-  N.order = order, N.nd = kuhn::lagrange_ndofs(order);
-  N.PS = K.PS, N.LS = K.LS;
-  for (int k = 0; k < kuhn::NK; ++k)
-  {
-    N.koff[k] = K.koff[k], N.kw[k] = K.kw[k], N.ksub[k] = K.ksub[k];
-    N.kdim[k] = kuhn::kinds[k].dim, N.kd1[k] = kuhn::kinds[k].d1, N.kd2[k] = kuhn::kinds[k].d2;
-    N.klayer[k] = kuhn::kinds[k].layer ? 1 : 0;
-  }
-  for (std::size_t e = 0; e < tab.size(); ++e)
-    N.tkind[e] = tab[e].kind, N.tsub[e] = tab[e].sub, N.tbx[e] = tab[e].bx, N.tby[e] = tab[e].by, N.tbz[e] = tab[e].bz;
-  for (int s = 0; s < order - 1 && s < 2; ++s)
-    N.edge_t[s] = kuhn::edge_param(order, s);
+  const SpaceDims N = make_space_dims(nx, ny, nz, order);
+  const BoxDims B = make_box_dims(nx, ny, nz, rank, nranks, N);
+  const std::int64_t d[9] = {B.nx, B.ny, B.nz, B.l0, B.l1, B.G0, B.G1, B.Glow, B.Ghigh};
+  for (int i = 0; i < 9; ++i)
+    dims_out[i] = d[i];
   const std::int64_t nvp = (B.nx + 1) * (B.ny + 1), n_cubes = B.nx * B.ny * (B.l1 - B.l0);
   const double hx = 1.0 / static_cast<double>(B.nx), hy = 1.0 / static_cast<double>(B.ny),
                hz = 1.0 / static_cast<double>(B.nz);

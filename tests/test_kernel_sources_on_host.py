@@ -882,8 +882,11 @@ def test_box_generator_source_equals_the_host_mesh_and_dofmap(pt, emubx, ptype, 
     xd, dm = np.full(nc * 4, -5, np.int32), np.full(nc * P.nd, -5, np.int32)
     dof_x = np.full(n * 3, np.nan)
     flags = np.full(1, -1, np.int32)
-    assert emubx.emu_create_box(_p(B), order, _p(xyz3), _p(xyz4), _p(dv), _p(xd), _p(dm), _p(dof_x), _p(flags)) == 0
+    dims_out = np.full(9, -1, np.int64)
+    assert emubx.emu_create_box(C.c_int64(dims[0]), C.c_int64(dims[1]), C.c_int64(dims[2]), rank, nranks, order,
+                                _p(dims_out), _p(xyz3), _p(xyz4), _p(dv), _p(xd), _p(dm), _p(dof_x), _p(flags)) == 0
     assert flags[0] == 0
+    assert np.array_equal(dims_out, B)          # the product's slab / range computation (make_box_dims)
     assert np.array_equal(xyz3, x_ref)
     assert np.array_equal(xyz4.reshape(-1, 4)[:, :3].reshape(-1), x_ref) and np.all(xyz4.reshape(-1, 4)[:, 3] == 0)
     assert np.array_equal(xd, P["x_dofmap"]) and np.array_equal(dm, P["dofmap"])
