@@ -31,13 +31,13 @@ WALK_CHECK_OUT=first_call/setup_4M.json timeout 200 python performance-test_b200
 echo "== bench line with the whole P1 setup generated on the device (20M DOFs): setup_s and value against the default line"
 PTB_GPU_SETUP=1 PTB_BENCH_DEVICE_SETUP=1 timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
   > "$out/bench_poisson20M_device_setup.json" 2> "$out/bench_poisson20M_device_setup.err"
-python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], 'value %.4g' % d['value'], d['setup_s'], d['stage_ms'], 'its', d['cg_iterations'])" "$out/bench_poisson20M_device_setup.json" || echo FAILED
+python -c "import json,sys; d=json.load(open(sys.argv[1])); print(sys.argv[1], 'value %.4g' % d['value'], d['setup_s'], d['stage_ms'], 'its', d['cg_iterations'])" "$out/bench_poisson20M_device_setup.json" 2>/dev/null || echo "FAILED (see $out/bench_poisson20M_device_setup.err)"
 echo "== SpMV on the zero-compacted operator (Poisson 20M: the headline line), off / on"
 for z in "0 0" "1 0" "1 1e-14"; do
   set -- $z
   PTB_SPMV_COMPACT=$1 PTB_SPMV_COMPACT_TOL=$2 timeout 400 python bench.py --steps 2 --warmup 1 --no-cpu-baseline \
     > "$out/bench_poisson20M_compact$1_tol$2.json" 2> "$out/bench_poisson20M_compact$1_tol$2.err"
-  python -c "import json,sys; d=json.load(open(sys.argv[1])); r=d['roofline']; print(sys.argv[1], 'value %.4g' % d['value'], d['stage_ms'], 'spmv ms', r['ms_per_launch'], 'stored/pattern', r['spmv_stored_entries'], r['pattern_entries'])" "$out/bench_poisson20M_compact$1_tol$2.json" || echo FAILED
+  python -c "import json,sys; d=json.load(open(sys.argv[1])); r=d['roofline']; print(sys.argv[1], 'value %.4g' % d['value'], d['stage_ms'], 'spmv ms', r['ms_per_launch'], 'stored/pattern', r['spmv_stored_entries'], r['pattern_entries'])" "$out/bench_poisson20M_compact$1_tol$2.json" 2>/dev/null || echo "FAILED (see the .err file)"
 done
 echo "== CG loop: three kernels per iteration vs persistent kernel, small problem (config 1) and 3M DOFs"
 for persistent in 0 1; do
