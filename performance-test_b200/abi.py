@@ -298,6 +298,7 @@ class Context:
         self.bs, self.nd = P.bs, P.nd
         self.n_owned, self.n_ghost, self.nnz = P.n_owned, P.n_ghost, P.nnz
         x, xd = _a(P["x"], np.float64), _a(P["x_dofmap"], np.int32)
+        self.n_vertices, self.n_cells = len(x) // 3, len(xd) // 4
         self._check(lib().ptb_set_mesh(self._h, len(x) // 3, _ptr(x), len(xd) // 4, _ptr(xd)))
         dm = _a(P["dofmap"], np.int32)
         self._check(lib().ptb_set_space(self._h, PROBLEMS[P.problem_type], P.order, P.bs,
