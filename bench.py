@@ -429,6 +429,11 @@ def main():
                                          "assemble_matrix_p1<3> (cell order)" if ptype == "elasticity"
                                          and os.environ.get("PTB_ASM_WALK3") != "1"
                                          and os.environ.get("PTB_ASM_GWALK") != "1" else
+                                         "assemble_matrix_p1_walk (star walk, EXACT cofactors)" if ptype == "poisson"
+                                         and os.environ.get("PTB_ASM_WALK", "1") != "0"
+                                         and os.environ.get("PTB_ASM_GWALK") != "1"
+                                         and os.environ.get("PTB_ASM_EXACT_ZEROS",
+                                                            os.environ.get("PTB_SPMV_COMPACT", "0")) == "1" else
                                          "assemble_matrix_p1_walk (star walk)" if ptype == "poisson"
                                          and os.environ.get("PTB_ASM_WALK", "1") != "0"
                                          and os.environ.get("PTB_ASM_GWALK") != "1" else
