@@ -4,8 +4,14 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 import this package. It is the checker, never the product: the product path is
 ``performance-test_b200`` (CUDA, no CPU fallback).
 
-parity unpinned: FEniCS/performance-test has no golden vectors / KATs for this path and cannot be
-built or imported here; see oracle.c's header for what is restated from where.
+Pinning: the reference has no golden vectors or KATs and its assembly lives
+in DOLFINx/FFCx/PETSc, which cannot be built here -- but its OWN code on this path can: src/cg.h
+(unchanged), the sizing arithmetic of src/mesh.cpp, the BC predicates / source lambdas and
+pack_fn/unpack_fn are compiled from /root/reference into oracle/_ref/libref.so (oracle/ref/,
+loader oracle/ref.py) and this restatement is checked against them bit for bit
+(tests/test_ref_pin.py, tests/golden/ref_cg.json, tests/golden/sizing.json). The element kernels,
+assembly loop and the Jacobi extension of the CG loop remain "parity unpinned": restated from
+published DOLFINx/FFCx semantics and pinned by analytic KATs only (tests/test_oracle_kats.py).
 """
 from __future__ import annotations
 
@@ -26,6 +32,8 @@ def build():
     r = subprocess.run(["make", "-C", _HERE, "all"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    from . import ref as _ref
+    _ref.build()   # oracle/_ref from /root/reference when it is present (no-op on the GPU box)
 
 
 def _lib(fast=False):

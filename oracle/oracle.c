@@ -3,10 +3,13 @@
  * CPU restatement of the reference's hot path (FEniCS/performance-test), used only by tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg.
  *
- * parity unpinned: the reference holds no golden vectors or known-answer tests for this path
- * (.github/workflows/ccpp.yml:56-197 only checks exit codes) and cannot be built here (DOLFINx,
- * Basix, FFCx, PETSc, MPI are not vendored and not installed). What is restated exactly from
- * in-repo code: src/cg.h:18-86. What is restated from the published behaviour of the un-vendored
+ * Pinning: the reference holds no golden vectors or known-answer tests for this path
+ * (.github/workflows/ccpp.yml:56-197 only checks exit codes) and as a whole cannot be built here
+ * (DOLFINx, Basix, FFCx, PETSc, MPI are not vendored and not installed). Its own self-contained
+ * code CAN: src/cg.h is compiled unchanged into oracle/_ref/libref.so (oracle/ref/), and orc_cg
+ * with precond = 0 reproduces it bit for bit (tests/test_ref_pin.py: same iteration counts, same
+ * x). Everything else in this file is "parity unpinned": the Jacobi extension of the loop, and
+ * what is restated from the published behaviour of the un-vendored
  * dependencies (DOLFINx main / FFCx main / PETSc, unpinned by the reference: ccpp.yml:31-50):
  * fem::assemble_matrix / assemble_vector / set_diagonal / DirichletBC::set and
  * MatSetValuesLocal(ADD_VALUES), as called at src/poisson_problem.cpp:125-157 and
@@ -410,8 +413,19 @@ static double dot(const double* a, const double* b, int64_t n, int nthreads)
   double s = 0.0;
   if (nthreads <= 1)
   {
-    for (int64_t i = 0; i < n; ++i) /* la::inner_product: sequential over owned entries */
-      s += a[i] * b[i];
+    /* la::inner_product / squared_norm (cg.h:53,65,74) reduce the owned entries with
+     * std::transform_reduce; libstdc++ evaluates it four entries at a time, ((p0+p1)+(p2+p3))
+     * added to the running sum, then the remainder one by one. Restated here so that this
+     * loop and the reference's cg.h compiled into oracle/_ref produce the same bits. */
+    int64_t i = 0;
+    for (; i + 4 <= n; i += 4)
+    {
+      const double v1 = a[i] * b[i] + a[i + 1] * b[i + 1];
+      const double v2 = a[i + 2] * b[i + 2] + a[i + 3] * b[i + 3];
+      s = s + (v1 + v2);
+    }
+    for (; i < n; ++i)
+      s = s + a[i] * b[i];
     return s;
   }
 #pragma omp parallel for schedule(static) reduction(+ : s) num_threads(nthreads)

@@ -1,11 +1,17 @@
-"""Generates tests/golden/sizing.json: an independent pure-Python replay of the reference's mesh
-sizing (/root/reference/src/mesh.cpp:44-74 entity/dof counts, :86-151 search) for the BASELINE.json
-configs and the nine CI configurations (.github/workflows/ccpp.yml:56-197). The reference itself
-cannot run here; this script restates its integer arithmetic literally and the C++ host code is
-checked against the stored table. Run: python tests/golden/make_sizing.py
+"""Generates tests/golden/sizing.json FROM THE REFERENCE'S OWN CODE: oracle/_ref/libref.so holds
+src/mesh.cpp:44-74 (num_entities / num_pdofs) and :82-151 (the create_cube_mesh search) compiled
+from /root/reference by oracle/ref/Makefile; this script calls it for the BASELINE.json configs, the
+nine CI configurations (.github/workflows/ccpp.yml:56-197) and a few edge cases, and stores the
+answers so that the GPU box (no /root/reference) and later rounds check against fixed numbers.
+A pure-Python replay of the same arithmetic runs next to it as a second route; the two must agree
+before anything is written. Run here: python tests/golden/make_sizing.py
 """
 import json
 import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
 
 
 def num_entities(i, j, k, nrefine):
@@ -56,16 +62,26 @@ CASES = [  # (name, target, total, dofs_per_node, order, nproc)
     ("CI elasticity serial", 100000, False, 3, 1, 1), ("CI elasticity weak np2", 100000, False, 3, 1, 2),
     ("CI elasticity P3 weak np2", 100000, False, 3, 3, 2), ("CI elasticity strong np2", 500000, True, 3, 1, 2),
     ("default --ndofs 50000 P2", 50000, False, 1, 2, 1), ("tiny", 10, True, 1, 1, 1),
+    ("P4 (counts only in the reference)", 200000, True, 1, 4, 1),
+    ("Nx_max boundary P1", 8120601, True, 1, 1, 1), ("just above Nx_max P1", 8300000, True, 1, 1, 1),
+    ("P2 refined", 300000000, True, 1, 2, 1), ("weak x64 elasticity P2", 500000, False, 3, 2, 64),
 ]
 
 if __name__ == "__main__":
+    from oracle import ref
+    if not ref.build():
+        raise SystemExit("needs /root/reference (run in the build container)")
     out = []
     for name, target, total, dpn, order, nproc in CASES:
-        Nx, Ny, Nz, r = sizing(target, total, dpn, order, nproc)
-        ent = num_entities(Nx, Ny, Nz, r)
+        got = list(ref.cube_sizing(target, total, dpn, order, nproc))
+        assert got == sizing(target, total, dpn, order, nproc), (name, got)
+        Nx, Ny, Nz, r = got
+        ent = list(ref.num_entities(Nx, Ny, Nz, r))
+        assert ent == list(num_entities(Nx, Ny, Nz, r))
+        pd = ref.num_pdofs(Nx, Ny, Nz, r, order)
+        assert pd == num_pdofs(Nx, Ny, Nz, r, order)
         out.append(dict(name=name, target=target, total=total, dofs_per_node=dpn, order=order,
-                        nproc=nproc, sizing=[Nx, Ny, Nz, r], entities=list(ent),
-                        pdofs=num_pdofs(Nx, Ny, Nz, r, order)))
+                        nproc=nproc, sizing=got, entities=ent, pdofs=pd))
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "sizing.json")
     json.dump(out, open(path, "w"), indent=1)
-    print("wrote", path, len(out), "cases")
+    print("wrote", path, len(out), "cases (source: oracle/_ref/libref.so = src/mesh.cpp compiled here)")
