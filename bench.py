@@ -19,9 +19,11 @@ assemble b, solve to rtol 1e-8. Prints ONE JSON line (rank 0):
                  measured HBM copy bandwidth in MEASURED_PEAKS.json
   cpu_baseline   the CPU oracle ("port": restatement, not DOLFINx/PETSc) on a bounded sample
 
-Workloads (BASELINE.json configs): default = configs[1] "Poisson P1 weak scaling 20M DOFs/GPU";
---workload elasticity = configs[2] "Elasticity P1 strong scaling 10M DOFs"; --workload small =
-configs[0] "Poisson P1 500k".
+Workloads (BASELINE.json configs). Default = the north-star target, configs[2] "Elasticity P1
+strong scaling 10M DOFs total" as the headline line, and configs[1] "Poisson P1 weak scaling 20M
+DOFs/GPU" measured in the same run and reported under "secondary" (same keys). --workload X runs
+one workload only: elasticity | poisson | small (configs[0]) | poisson_p2 | poisson_p3 (configs[3])
+| elasticity_weak (configs[4], 100M DOFs/GPU, set up on the device).
 """
 import argparse
 import importlib
@@ -50,7 +52,9 @@ WORKLOADS = {
     "small": ("poisson", "weak", 500_000, 1, "Poisson P1 unit cube 500k DOFs/GPU, CG+Jacobi rtol 1e-8"),
     "poisson_p2": ("poisson", "strong", 50_000_000, 2, "Poisson P2 50M DOFs total (strong), CG+Jacobi rtol 1e-8"),
     "poisson_p3": ("poisson", "strong", 50_000_000, 3, "Poisson P3 50M DOFs total (strong), CG+Jacobi rtol 1e-8"),
+    "elasticity_weak": ("elasticity", "weak", 100_000_000, 1, "Elasticity P1 weak scaling 100M DOFs/GPU, CG+Jacobi rtol 1e-8"),
 }
+DEFAULT_HEADLINE, DEFAULT_SECONDARY = "elasticity", "poisson"
 KMAX = 10000  # PETSc's default -ksp_max_it; cg.h's own default of 50 never converges at these sizes
 
 
@@ -60,7 +64,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="poisson", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                    help="one workload only (default: elasticity headline + poisson secondary)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--kmax", type=int, default=KMAX)
     ap.add_argument("--ndofs", type=int, default=None, help="override the workload's --ndofs")
     ap.add_argument("--cpu-sample-ndofs", type=int, default=2_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -152,7 +159,8 @@ def run_reference(args):
         nthreads = len(os.sched_getaffinity(0))
     except AttributeError:
         nthreads = os.cpu_count() or 1
-    ptype, order, dims, base, scaling, ndofs = sizing(pt, args.workload, 1, args.cpu_sample_ndofs)
+    wl_name = args.workload or DEFAULT_HEADLINE
+    ptype, order, dims, base, scaling, ndofs = sizing(pt, wl_name, 1, args.cpu_sample_ndofs)
     P = pt.host.Problem(ptype, order, *dims)
     ndof = P.n_owned * P.bs
 
@@ -175,7 +183,7 @@ def run_reference(args):
     iters = sum(t[3] for t in ts)
     total = sum(t[0] + t[1] + t[2] for t in ts)
     value = iters * ndof / t_solve
-    wl = WORKLOADS[args.workload]
+    wl = WORKLOADS[wl_name]
     sample = (f"{ptype} P{order} at --ndofs {args.cpu_sample_ndofs} ({ndof} DOFs, {P.n_cells} cells), "
               f"full hot path to rtol 1e-8, {nthreads} OpenMP threads")
     line = {
@@ -194,11 +202,11 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(pt, args):
+def cpu_baseline(pt, args, wl_name):
     """Oracle on 1 core on a bounded sample (rank 0, N = 1 only)."""
     import oracle
     oracle.build()
-    ptype, order, dims, base, scaling, ndofs = sizing(pt, args.workload, 1, args.cpu_sample_ndofs)
+    ptype, order, dims, base, scaling, ndofs = sizing(pt, wl_name, 1, args.cpu_sample_ndofs)
     P = pt.host.Problem(ptype, order, *dims)
     t0 = time.perf_counter()
     A = oracle.assemble_matrix(P, nthreads=1, fast=True)
@@ -218,6 +226,223 @@ def cpu_baseline(pt, args):
                        f"{t3 - t2:.2f} s")}
 
 
+def measure(pt, env, wl_name, args, steps, warmup, with_cpu):
+    """One workload through the C ABI on this rank's GPU; returns the JSON fields (rank 0) or None."""
+    import torch
+    abi = pt.abi
+    world, rank, local_rank, dist = env["world"], env["rank"], env["local_rank"], env["dist"]
+    barrier, allmax, allsum = env["barrier"], env["allmax"], env["allsum"]
+
+    # ---- setup (untimed): host mesh/dofmap/pattern, upload, NCCL / peer bootstrap ------------
+    ptype, order, dims, base, scaling, ndofs_arg = sizing(pt, wl_name, world, args.ndofs)
+    # configs[4] (100M DOFs/GPU) is generated on the device: the host stand-in would need ~10 GB per
+    # rank; PTB_BENCH_DEVICE_SETUP=1 forces the same route for any workload
+    device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1" or wl_name == "elasticity_weak"
+    t_setup0 = time.perf_counter()
+    P = pt.host.Problem(ptype, order, *dims, rank, world, with_dofmap=not device_setup)
+    t_host = time.perf_counter() - t_setup0
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = abi.Context(local_rank, stream=stream)
+    t0 = time.perf_counter()
+    if device_setup:
+        ctx.set_problem_on_device(P)
+    else:
+        ctx.set_problem(P)
+    t_upload = time.perf_counter() - t0
+    comm_used = "none"
+    if world > 1:
+        comm_used = args.comm
+        if args.comm == "peer":
+            # CUDA IPC can be unavailable (container without shared IPC namespace, no P2P): every
+            # rank must take the same path, so agree on the outcome before falling back to NCCL.
+            try:
+                pt.dist.connect_peers(ctx, P, dist, rank, world)
+                ok_local = 1.0
+            except Exception as e:  # noqa: BLE001
+                ok_local = 0.0
+                print(f"rank {rank}: peer-memory setup failed: {e}", file=sys.stderr)
+            t = torch.tensor([ok_local], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if float(t.item()) < 1.0:
+                if rank == 0:
+                    print("peer-memory setup failed on some rank, using NCCL", file=sys.stderr)
+                comm_used = "nccl"
+        if comm_used == "nccl":
+            pt.dist.init_nccl(ctx, abi, dist, rank, world)   # ptb_comm_init drops any peer state
+    ndofs_global = P.n_global * P.bs
+    nnz_local = ctx.nnz if device_setup else P.nnz
+    nnz_global = allsum(float(nnz_local * P.bs * P.bs))
+
+    # pinned host buffers for the e2e leg (host-resident inputs of the hot path)
+    nl = (P.n_owned + P.n_ghost) * P.bs
+    if device_setup:
+        x_host, _ = ctx.mesh()
+        f_host, g_host = ctx.source()
+    else:
+        x_host, f_host = np.array(P["x"]), np.array(P["f"])
+        g_host = np.array(P["g"]) if len(P["g"]) else None
+    x_pin = torch.from_numpy(x_host).pin_memory()
+    f_pin = torch.from_numpy(f_host).pin_memory()
+    g_pin = torch.from_numpy(g_host).pin_memory() if g_host is not None else None
+    b_pin = torch.empty(P.n_owned * P.bs, dtype=torch.float64).pin_memory()
+    u_pin = torch.empty(nl, dtype=torch.float64).pin_memory()
+    h2d = x_pin.numel() * 8 + f_pin.numel() * 8 + (g_pin.numel() * 8 if g_pin is not None else 0)
+    d2h = b_pin.numel() * 8 + u_pin.numel() * 8
+
+    state = {}
+
+    def step(e2e=False):
+        if e2e:
+            ctx.update_geometry(x_pin.numpy())
+            ctx.set_source(f_pin.numpy(), None if g_pin is None else g_pin.numpy())
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        k, rel = ctx.cg_solve(kmax=args.kmax, rtol=1e-8, precond="jacobi")
+        if e2e:
+            ctx.rhs(out=b_pin.numpy())
+            ctx.solution(out=u_pin.numpy())
+        state.update(k=k, rel=rel, am=ctx.stage_ms(abi.STAGE_ASSEMBLE_MATRIX),
+                     av=ctx.stage_ms(abi.STAGE_ASSEMBLE_VECTOR), sv=ctx.stage_ms(abi.STAGE_SOLVE))
+        return k
+
+    for _ in range(warmup):
+        step()
+
+    def timed(nsteps, e2e):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        am = sv = 0.0
+        iters = 0
+        barrier()
+        ev0.record()
+        for _ in range(nsteps):
+            iters += step(e2e)
+            am += state["am"]
+            sv += state["sv"]
+        ev1.record()
+        barrier()
+        ms = allmax(ev0.elapsed_time(ev1))
+        return ms, allmax(am), allmax(sv), iters
+
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, am_ms, sv_ms, iters = timed(steps, e2e=False)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, am_e2e, sv_e2e, iters_e2e = timed(steps, e2e=True)
+
+    value = iters * ndofs_global / (sv_ms * 1e-3)
+    nnz_per_s = nnz_global * steps / (am_ms * 1e-3)
+    # e2e: (iterations * DOFs) / whole time of the host-buffer steps -- copies and assembly included
+    e2e_value = iters_e2e * ndofs_global / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (SpMV inside CG), timed live with CUDA events on this
+    # rank's stream: the plain operator kernel on resident data (no halo wait, no reduction
+    # publish), so the number is this GPU's kernel time at any N; max over ranks is reported ----
+    step()  # leaves p, r, x in their end-of-solve state
+    t_spmv = allmax(ctx.time_kernel(abi.KERNEL_SPMV, 30))
+    t_upd = allmax(ctx.time_kernel(abi.KERNEL_CG_UPDATE, 30))
+    t_dir = allmax(ctx.time_kernel(abi.KERNEL_CG_DIRECTION, 30))
+    t_am = allmax(ctx.time_kernel(abi.KERNEL_ASSEMBLE_MATRIX, 5))
+    t_av = allmax(ctx.time_kernel(abi.KERNEL_ASSEMBLE_VECTOR, 5))
+    n, bs = P.n_owned, P.bs
+    spmv_b = 12 * nnz_local + 20 * n if bs == 1 else 76 * nnz_local + 52 * n
+    cg_b = spmv_b + 96 * n * bs
+    asm_b = 8 * nnz_local * bs * bs + P.n_cells * (16 + 4 * P.nd) + 25 * (n + P.n_ghost)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    achieved = spmv_b / (t_spmv * 1e-3) / 1e9
+    # ncu traffic belongs to one capture: only quoted when this run has the capture's configuration
+    traffic, traffic_src = None, None
+    switches = {k: v for k, v in os.environ.items() if k.startswith("PTB_")}
+    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
+    if os.path.exists(tpath) and world == 1 and args.ndofs is None and not switches:
+        try:
+            tj = json.load(open(tpath)).get(wl_name, {})
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        except Exception:
+            pass
+    it_ms = sv_ms / max(iters, 1)
+    roofline = {"bound": "hbm", "kernel": f"spmv_sell<{bs}> (y = A p + p.y inside CG)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": spmv_b, "ms_per_launch": t_spmv,
+                "cols_explicit_fraction": ctx.cols_explicit_fraction(),
+                "spmv_stored_entries": ctx.spmv_stored_entries(),
+                "pattern_entries": nnz_local,
+                "note": ("per-rank kernel time (max over ranks), launched back to back on resident data; "
+                         "achieved counts the ALGORITHMIC CSR bytes (8 B value + 4 B column per nnz, "
+                         "76 B per 3x3 block); scalar matrices store one column delta per 32 rows where "
+                         "the stencil is translation invariant (cols_explicit_fraction), so frac can "
+                         "exceed 1 there -- block matrices store every column index"),
+                "other_kernels": {
+                    "cg_update": {"ms": t_upd, "GBps": 32.0 * n * bs / t_upd / 1e6},
+                    "cg_direction": {"ms": t_dir, "GBps": 48.0 * n * bs / t_dir / 1e6},
+                    "assemble_matrix": {"ms": t_am, "GBps": asm_b / t_am / 1e6,
+                                        "frac_of_hbm_peak": asm_b / t_am / 1e6 / peak,
+                                        "nnz_per_s": nnz_local * bs * bs / (t_am * 1e-3)},
+                    "assemble_vector": {"ms": t_av}},
+                "cg_iteration": {"ms_measured": it_ms, "ms_sum_of_kernels": t_spmv + t_upd + t_dir,
+                                 "overhead_frac": it_ms / (t_spmv + t_upd + t_dir) - 1.0,
+                                 "frac_of_hbm_roofline": cg_b / (it_ms * 1e-3) / 1e9 / peak}}
+
+    cpu = cpu_baseline(pt, args, wl_name) if (with_cpu and rank == 0 and world == 1) else None
+
+    out = None
+    if rank == 0:
+        wl = WORKLOADS[wl_name]
+        walk3 = os.environ.get("PTB_ASM_WALK3", "1") != "0"
+        walk = os.environ.get("PTB_ASM_WALK", "1") != "0"
+        out = {
+            "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": wl[1],
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "assembled_nnz_per_s": nnz_per_s,
+            "stage_ms": {"assemble_matrix": am_ms / steps, "assemble_vector": state["av"],
+                         "solve": sv_ms / steps},
+            "cg_iterations": iters // steps, "rel_residual": state["rel"],
+            "ndofs_global": ndofs_global, "nnz_global": nnz_global,
+            "config": {"workload": wl[4], "problem_type": ptype, "order": order,
+                       "ndofs_arg": ndofs_arg, "scaling_type": scaling,
+                       "base_box": list(base[:3]), "refinements": base[3],
+                       "fine_box": list(dims), "partition": f"z-slabs x{world}",
+                       "comm": ("none" if world == 1 else
+                                "nvlink peer memory (halo pull + window all-reduce in the CG kernels)"
+                                if comm_used == "peer" else "nccl send/recv + allreduce"),
+                       "l2": "inputs larger than L2 (matrix + vectors >> 126 MB per GPU)"
+                             if nnz_local * 12 * bs > 3e8 else
+                             "per-GPU working set near L2 size (strong scaling / small config)",
+                       "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "
+                                            "Plaza refinement (same entity counts)" if base[3] else None,
+                       "switches": switches,
+                       "matrix_kernel": ("assemble_matrix_pk_binned" if order > 1 else
+                                         ("assemble_matrix_p1_walk3 (star walk)" if walk3 else
+                                          "assemble_matrix_p1<3> (cell order)") if ptype == "elasticity" else
+                                         "assemble_matrix_p1_walk (star walk)" if walk else
+                                         "assemble_matrix_p1<1> (cell order)")},
+            "e2e": {"value": e2e_value, "unit": "DOF-iters/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / steps,
+                    "note": "per step: x, f, g host->device from pinned memory, assemble A and b, "
+                            "solve, b and u device->host; value = iterations*DOFs / whole e2e time"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "setup_s": {"host_mesh_dofmap_pattern": t_host, "slot_map_and_upload": t_upload,
+                        "device_setup": device_setup},
+            "device_bytes": ctx.device_bytes(),
+        }
+    barrier()
+    ctx.close()
+    del ctx, P
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -226,7 +451,6 @@ def main():
     import torch
     import torch.distributed as dist
     pt = importlib.import_module("performance-test_b200")
-    abi = pt.abi
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -257,202 +481,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---- setup (untimed): host mesh/dofmap/pattern, upload, NCCL bootstrap -------------------
-    ptype, order, dims, base, scaling, ndofs_arg = sizing(pt, args.workload, world, args.ndofs)
-    t_setup0 = time.perf_counter()
-    P = pt.host.Problem(ptype, order, *dims, rank, world)
-    t_host = time.perf_counter() - t_setup0
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = abi.Context(local_rank, stream=stream)
-    t0 = time.perf_counter()
-    # opt-in (not yet run on a GPU): mesh, dofmap, pattern, Dirichlet dofs and
-    # sources generated on the device; with PTB_GPU_SETUP=1 the layouts and assembly maps too
-    device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1"
-    if device_setup:
-        ctx.set_problem_on_device(P)
-    else:
-        ctx.set_problem(P)
-    t_upload = time.perf_counter() - t0
-    comm_used = "none"
-    if world > 1:
-        comm_used = args.comm
-        if args.comm == "peer":
-            # CUDA IPC can be unavailable (container without shared IPC namespace, no P2P): every
-            # rank must take the same path, so agree on the outcome before falling back to NCCL.
-            try:
-                pt.dist.connect_peers(ctx, P, dist, rank, world)
-                ok_local = 1.0
-            except Exception as e:  # noqa: BLE001
-                ok_local, peer_err = 0.0, str(e)
-            t = torch.tensor([ok_local], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MIN)
-            if float(t.item()) < 1.0:
-                if rank == 0:
-                    print("peer-memory setup failed on some rank, using NCCL", file=sys.stderr)
-                comm_used = "nccl"
-        if comm_used == "nccl":
-            pt.dist.init_nccl(ctx, abi, dist, rank, world)
-    ndofs_global = P.n_global * P.bs
-    nnz_global = allsum(float(P.nnz * P.bs * P.bs))
-
-    # pinned host buffers for the e2e leg
-    nl = (P.n_owned + P.n_ghost) * P.bs
-    x_pin = torch.from_numpy(np.array(P["x"])).pin_memory()
-    f_pin = torch.from_numpy(np.array(P["f"])).pin_memory()
-    g_pin = torch.from_numpy(np.array(P["g"])).pin_memory() if len(P["g"]) else None
-    b_pin = torch.empty(P.n_owned * P.bs, dtype=torch.float64).pin_memory()
-    u_pin = torch.empty(nl, dtype=torch.float64).pin_memory()
-    h2d = x_pin.numel() * 8 + f_pin.numel() * 8 + (g_pin.numel() * 8 if g_pin is not None else 0)
-    d2h = b_pin.numel() * 8 + u_pin.numel() * 8
-
-    state = {}
-
-    def step(e2e=False):
-        if e2e:
-            ctx.update_geometry(x_pin.numpy())
-            ctx.set_source(f_pin.numpy(), None if g_pin is None else g_pin.numpy())
-        ctx.assemble_matrix()
-        ctx.assemble_vector()
-        k, rel = ctx.cg_solve(kmax=KMAX, rtol=1e-8, precond="jacobi")
-        if e2e:
-            ctx.rhs(out=b_pin.numpy())
-            ctx.solution(out=u_pin.numpy())
-        state.update(k=k, rel=rel, am=ctx.stage_ms(abi.STAGE_ASSEMBLE_MATRIX),
-                     av=ctx.stage_ms(abi.STAGE_ASSEMBLE_VECTOR), sv=ctx.stage_ms(abi.STAGE_SOLVE))
-        return k
-
-    for _ in range(args.warmup):
-        step()
-
-    def timed(nsteps, e2e):
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        am = sv = 0.0
-        iters = 0
-        barrier()
-        ev0.record()
-        for _ in range(nsteps):
-            iters += step(e2e)
-            am += state["am"]
-            sv += state["sv"]
-        ev1.record()
-        barrier()
-        ms = allmax(ev0.elapsed_time(ev1))
-        return ms, allmax(am), allmax(sv), iters
-
-    launches0 = ctx.launch_count()
-    sampler = ClockSampler(local_rank)
+    env = dict(world=world, rank=rank, local_rank=local_rank, dist=dist, barrier=barrier,
+               allmax=allmax, allsum=allsum)
+    head = args.workload or DEFAULT_HEADLINE
+    line = measure(pt, env, head, args, args.steps, args.warmup, with_cpu=not args.no_cpu_baseline)
+    if args.workload is None and not args.no_secondary:
+        # the weak-scaling config of BASELINE.json in the same run: same keys, under "secondary"
+        sec = measure(pt, env, DEFAULT_SECONDARY, args, min(args.steps, 3), min(args.warmup, 3),
+                      with_cpu=False)
+        if rank == 0:
+            line["secondary"] = sec
     if rank == 0:
-        sampler.start()
-    ms, am_ms, sv_ms, iters = timed(args.steps, e2e=False)
-    launches = ctx.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    ms_e2e, am_e2e, sv_e2e, iters_e2e = timed(args.steps, e2e=True)
-
-    value = iters * ndofs_global / (sv_ms * 1e-3)
-    nnz_per_s = nnz_global * args.steps / (am_ms * 1e-3)
-    # e2e: the same metric with the whole host-buffer step as the denominator share of the solve:
-    # (iterations * DOFs) / (time of the e2e steps minus nothing) -- copies and assembly included.
-    e2e_value = iters_e2e * ndofs_global / (ms_e2e * 1e-3)
-
-    # ---- roofline of the dominant kernel (SpMV inside CG), timed live with CUDA events -------
-    step()  # leaves p, r, x in their end-of-solve state
-    t_spmv = ctx.time_kernel(abi.KERNEL_SPMV, 30)
-    t_upd = ctx.time_kernel(abi.KERNEL_CG_UPDATE, 30)
-    t_dir = ctx.time_kernel(abi.KERNEL_CG_DIRECTION, 30)
-    t_am = ctx.time_kernel(abi.KERNEL_ASSEMBLE_MATRIX, 5)
-    t_av = ctx.time_kernel(abi.KERNEL_ASSEMBLE_VECTOR, 5)
-    spmv_b, cg_b, asm_b = algorithmic_bytes(P)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = spmv_b / (t_spmv * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            traffic = tj.get(args.workload, {}).get("dram_bytes_per_launch")
-        except Exception:
-            pass
-    roofline = {"bound": "hbm", "kernel": "spmv_sell (y = A p + p.y inside CG)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": spmv_b, "ms_per_launch": t_spmv,
-                "cols_explicit_fraction": ctx.cols_explicit_fraction(),
-                "spmv_stored_entries": ctx.spmv_stored_entries(),
-                "pattern_entries": P.nnz,
-                "note": ("achieved counts the ALGORITHMIC CSR bytes (8 B value + 4 B column per nnz); "
-                         "the kernel stores one delta per 32 rows where the stencil is translation "
-                         "invariant, so it moves fewer index bytes than that and frac can exceed 1. "
-                         "spmv_stored_entries < pattern_entries means PTB_SPMV_COMPACT dropped the "
-                         "SELL positions that are 0.0 in all 32 rows of a slice (y unchanged)"),
-                "other_kernels": {
-                    "cg_update": {"ms": t_upd, "GBps": 32.0 * P.n_owned * P.bs / t_upd / 1e6},
-                    "cg_direction": {"ms": t_dir, "GBps": 48.0 * P.n_owned * P.bs / t_dir / 1e6},
-                    "assemble_matrix": {"ms": t_am, "GBps": asm_b / t_am / 1e6,
-                                        "nnz_per_s": P.nnz * P.bs * P.bs / (t_am * 1e-3)},
-                    "assemble_vector": {"ms": t_av}},
-                "cg_iteration_frac_of_hbm_roofline":
-                    cg_b / ((t_spmv + t_upd + t_dir) * 1e-3) / 1e9 / peak}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(pt, args)
-
-    if rank == 0:
-        wl = WORKLOADS[args.workload]
-        line = {
-            "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": wl[1],
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "assembled_nnz_per_s": nnz_per_s,
-            "stage_ms": {"assemble_matrix": am_ms / args.steps, "assemble_vector": state["av"],
-                         "solve": sv_ms / args.steps},
-            "cg_iterations": iters // args.steps, "rel_residual": state["rel"],
-            "ndofs_global": ndofs_global, "nnz_global": nnz_global,
-            "config": {"workload": wl[4], "problem_type": ptype, "order": order,
-                       "ndofs_arg": ndofs_arg, "scaling_type": scaling,
-                       "base_box": list(base[:3]), "refinements": base[3],
-                       "fine_box": list(dims), "partition": f"z-slabs x{world}",
-                       "comm": ("none" if world == 1 else
-                                "nvlink peer memory (halo pull + window all-reduce in the CG kernels)"
-                                if comm_used == "peer" else "nccl send/recv + allreduce"),
-                       "l2": "inputs larger than L2 (matrix + vectors >> 126 MB)"
-                             if P.nnz * 12 * P.bs > 3e8 else "working set near L2 size: small config",
-                       "refined_mesh_note": "r>0 generated as the (N<<r) box directly, not by "
-                                            "Plaza refinement (same entity counts)" if base[3] else None,
-                       "switches": {k: v for k, v in os.environ.items() if k.startswith("PTB_")},
-                       "matrix_kernel": ("assemble_matrix_pk" if order > 1 else
-                                         "assemble_matrix_p1<3> (cell order)" if ptype == "elasticity"
-                                         and os.environ.get("PTB_ASM_WALK3") != "1"
-                                         and os.environ.get("PTB_ASM_GWALK") != "1" else
-                                         "assemble_matrix_p1_walk (star walk, EXACT cofactors)" if ptype == "poisson"
-                                         and os.environ.get("PTB_ASM_WALK", "1") != "0"
-                                         and os.environ.get("PTB_ASM_GWALK") != "1"
-                                         and os.environ.get("PTB_ASM_EXACT_ZEROS",
-                                                            os.environ.get("PTB_SPMV_COMPACT", "0")) == "1" else
-                                         "assemble_matrix_p1_walk (star walk)" if ptype == "poisson"
-                                         and os.environ.get("PTB_ASM_WALK", "1") != "0"
-                                         and os.environ.get("PTB_ASM_GWALK") != "1" else
-                                         "see switches")},
-            "e2e": {"value": e2e_value, "unit": "DOF-iters/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "note": "per step: x, f, g host->device from pinned memory, assemble A and b, "
-                            "solve, b and u device->host; value = iterations*DOFs / whole e2e time"},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": roofline,
-            "cpu_baseline": cpu,
-            "setup_s": {"host_mesh_dofmap_pattern": t_host, "slot_map_and_upload": t_upload,
-                        "device_setup": device_setup},
-            "device_bytes": ctx.device_bytes(),
-        }
         print(json.dumps(line), flush=True)
     barrier()
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
 

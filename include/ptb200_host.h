@@ -33,6 +33,12 @@ int pth_cube_sizing(uint64_t target_dofs, int target_dofs_total, uint64_t dofs_p
  * problem_type: "poisson" | "elasticity" (cgpoisson uses the poisson data). */
 int pth_problem_create(const char* problem_type, int order, int64_t nx, int64_t ny, int64_t nz,
                        int rank, int nranks, pth_problem** out);
+/* The same object with the surface-sized data only (sizes, ghost and halo lists, exterior facets):
+ * for callers that generate mesh, dofmap, pattern, Dirichlet dofs and sources on the device
+ * (ptb_create_box, ptb_build_pattern, ptb_locate_bc, ptb_interpolate_source). x, x_dofmap, dofmap,
+ * dof_x, rowptr/cols, bc_dofs, f, g stay empty; nnz and n_bc read 0. */
+int pth_problem_create_sizes_only(const char* problem_type, int order, int64_t nx, int64_t ny,
+                                  int64_t nz, int rank, int nranks, pth_problem** out);
 void pth_problem_destroy(pth_problem* p);
 
 /* Named scalar: n_cells, n_cells_owned, n_ghost_cells_front, cell_global_offset, n_cells_global,

@@ -17,9 +17,12 @@ namespace
 {
 // Star-walk assembly (assemble_walk.cu): PTB_ASM_WALK=1/0 overrides the built-in default.
 bool walk_enabled() { return env_flag("PTB_ASM_WALK", true); }
-// Written after the round's GPU budget was spent, never run -> opt-in.
-bool walk3_enabled() { return env_flag("PTB_ASM_WALK3", false); }
-bool gwalk_enabled() { return env_flag("PTB_ASM_GWALK", false); }
+// Elasticity matrix along the star walk (assemble_matrix_p1_walk3): default since round 2
+// (1.40 -> 0.91 ms at 1.33 M nodes, profiles/r02/assembly_ab_4M.json); 0 = first-generation kernel.
+bool walk3_enabled() { return env_flag("PTB_ASM_WALK3", true); }
+// P1 cell vector by direct gather along the single-reload walk (assemble_gwalk.cu): default.
+bool gwalk_enabled() { return env_flag("PTB_VEC_GWALK", true); }
+// Assembly maps and column layout built by the setup kernels (setup.cu) instead of the host loops.
 bool gpu_setup_enabled() { return env_flag("PTB_GPU_SETUP", false); }
 using ptb::abi::g_err;
 using ptb::abi::guarded;
@@ -206,6 +209,9 @@ int ptb_update_geometry(ptb_ctx* c, const double* x)
     if (c->have_space)
       launch_gather_xdof(c);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
+    // the operator, its Jacobi diagonal and b belong to the old coordinates
+    c->matrix_assembled = c->vector_assembled = false;
+    c->have_compact = false;
   });
 }
 
@@ -220,6 +226,7 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
     need((problem == PTB_POISSON && bs == 1) || (problem == PTB_ELASTICITY && bs == 3),
          "ptb_set_space: bs must be 1 for Poisson and 3 for elasticity");
     need(n_owned > 0 && n_ghost >= 0 && dofmap, "ptb_set_space: empty space");
+    peer_disconnect(c); // peers hold IPC mappings of the old x / p: export and connect again
     c->problem = problem, c->order = order, c->bs = bs;
     c->operator_mode = PTB_OP_ASSEMBLED;
     c->nd = (order + 1) * (order + 2) * (order + 3) / 6;
@@ -243,12 +250,12 @@ int ptb_set_space(ptb_ctx* c, int problem, int order, int bs, int32_t n_owned, i
       bool bad = false;
 #pragma omp parallel for schedule(static) reduction(|| : bad)
       for (std::int64_t cell = 0; cell < c->n_cells; ++cell)
-        for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < nd; ++i)
         {
           const std::int32_t d = dofmap[cell * nd + i];
           if (d < 0 || d >= nl)
             bad = true;
-          else
+          else if (i < 4)
             dv[d] = xd[cell * 4 + i]; // every writer of dv[d] stores the same vertex
         }
       need(!bad, "ptb_set_space: dofmap entry out of range");
@@ -275,6 +282,7 @@ int ptb_create_box(ptb_ctx* c, int problem, int bs, int order, int64_t nx, int64
     need(nranks >= 1 && rank >= 0 && rank < nranks && nz >= nranks,
          "ptb_create_box: need 0 <= rank < nranks <= nz");
     need(order >= 1 && order <= 3, "Order not supported");
+    peer_disconnect(c);
     gpu_create_box(c, order, nx, ny, nz, rank, nranks);
     c->have_mesh = true;
     c->problem = problem, c->order = order, c->bs = bs;
@@ -350,7 +358,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     SellLayout L;
     // The adjacency side (cell lists, slot words, star walk) comes from the host build below or,
     // opt-in for P1, from the device (setup.cu); the column side is always laid out here.
-    bool dev_maps = gpu_setup_enabled() && !gwalk_enabled();
+    bool dev_maps = gpu_setup_enabled();
     auto host_layout = [&](bool with_adjacency) {
       std::int64_t max_so = 0;
       if (with_adjacency)
@@ -450,7 +458,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
     c->walk1.release(), c->walk1_off.release();
     if (gwalk_enabled() && !L.adjrot.empty() && (c->bs == 3 || L.max_w <= 32))
     {
-      // opt-in: one-vertex-per-step walk for the direct-gather kernels (assemble_gwalk.cu)
+      // one-vertex-per-step walk for the direct-gather vector kernel (assemble_gwalk.cu)
       if (L.walk.empty())
         build_walk(N, c->h_adj, c->h_so, L);
       build_walk_single(N, c->h_adj, L);
@@ -500,7 +508,7 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
       build_pattern(c->h_dofmap.data(), c->nd, c->n_owned, adj, rowptr, cols);
       return;
     }
-    if (!(gpu_setup_enabled() && !gwalk_enabled()))
+    if (!gpu_setup_enabled())
       return;
     // PTB_GPU_SETUP=1: the pattern never leaves the device on its way into the layouts -- column
     // side (setup.cu gpu_setup_columns) and adjacency side (gpu_setup_p1 / gpu_setup_pk) are built
@@ -725,6 +733,7 @@ int ptb_set_halo(ptb_ctx* c, int n_nbr, const int32_t* nbr_ranks, const int32_t*
   return guarded(c, [&] {
     use_device(c);
     need(c->have_space, "ptb_set_halo: call ptb_set_space first");
+    peer_disconnect(c); // src_index of a connected peer set belongs to the old lists
     c->nbr_ranks.assign(nbr_ranks, nbr_ranks + n_nbr);
     c->send_displ.assign(send_displ, send_displ + n_nbr + 1);
     c->recv_displ.assign(recv_displ, recv_displ + n_nbr + 1);
@@ -826,6 +835,7 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     need(!(mf && precond == PTB_PC_JACOBI && !c->matrix_assembled),
          "ptb_cg_solve: Jacobi needs the assembled diagonal (call ptb_assemble_matrix once)");
     need(kmax >= 0, "ptb_cg_solve: kmax < 0");
+    need(!mf || c->bs == 1, "matrix-free operator: built for the scalar Poisson space only");
     StageTimer t(c, PTB_STAGE_SOLVE);
     const double* dinv = precond == PTB_PC_JACOBI ? c->dinv.p : c->ones.p;
     CgState* st = c->cg.p;
@@ -882,7 +892,17 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     int it = 0;
     int pending = -1;
     bool done = false;
-    cudaEvent_t evs[2];
+    struct EventPair // destroyed on every exit path, a throwing PTB_CUDA inside the loop included
+    {
+      cudaEvent_t e[2] = {nullptr, nullptr};
+      ~EventPair()
+      {
+        for (cudaEvent_t x : e)
+          if (x)
+            cudaEventDestroy(x);
+      }
+      cudaEvent_t& operator[](int i) { return e[i]; }
+    } evs;
     PTB_CUDA(cudaEventCreateWithFlags(&evs[0], cudaEventDisableTiming));
     PTB_CUDA(cudaEventCreateWithFlags(&evs[1], cudaEventDisableTiming));
     int slot = 0;
@@ -919,8 +939,6 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     halo_forward(c, c->x.p); // leave the ghosts of the solution current (cg.h:36-37)
     peer_neighbour_barrier(c); // peers may still be reading x
     t.stop();
-    cudaEventDestroy(evs[0]);
-    cudaEventDestroy(evs[1]);
     const CgState fin = c->h_cg[0];
     if (iterations)
       *iterations = kmax == 0 ? 0 : fin.k;
@@ -945,6 +963,8 @@ int ptb_apply_operator(ptb_ctx* c, const double* p_host, double* y_host)
     use_device(c);
     need(c->matrix_assembled || (c->operator_mode == PTB_OP_MATRIX_FREE && c->have_pattern),
          "ptb_apply_operator: matrix not assembled");
+    need(c->operator_mode == PTB_OP_ASSEMBLED || c->bs == 1,
+         "matrix-free operator: built for the scalar Poisson space only");
     PTB_CUDA(cudaMemcpyAsync(c->p.p, p_host, n_local_entries(c) * sizeof(double),
                              cudaMemcpyHostToDevice, c->stream));
     StageTimer t(c, PTB_STAGE_SPMV);

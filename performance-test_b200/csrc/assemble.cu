@@ -556,7 +556,7 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
     return launch_assemble_matrix_pk(c, A);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
-  if (launch_assemble_matrix_gwalk(c, A) || launch_assemble_matrix_walk(c, A))
+  if (launch_assemble_matrix_walk(c, A))
     return;
   if (c->bs == 1)
   {
@@ -634,8 +634,6 @@ void launch_action_matrix_free(ptb_ctx* c, const VectorArgs& A, const double* p,
     return launch_action_matrix_free_pk(c, A, p, y, py_out);
   if (A.adjrot == nullptr)
     throw std::runtime_error("matrix-free operator: a P1 row has more than 254 columns");
-  if (launch_action_gwalk(c, A, p, y, py_out))
-    return;
   const int spc = MAT_THREADS_1 / 32;
   const int grid = (A.n_slices + spc - 1) / spc;
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * spc * sizeof(double);

@@ -439,7 +439,7 @@ void launch_matrix_bins(ptb_ctx* c, const MatrixArgs& A)
 template <int ND>
 void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
 {
-  if (env_flag("PTB_PK_BINS", false) && c->pk_bin_slices.p != nullptr)
+  if (env_flag("PTB_PK_BINS", true) && c->pk_bin_slices.p != nullptr)
   {
     if (c->so_bits == 8)
       launch_matrix_bins<ND, false>(c, A);

@@ -79,6 +79,9 @@ void comm_init(ptb_ctx* c, int rank, int nranks, const void* id128)
   if (nranks < 1 || rank < 0 || rank >= nranks)
     throw std::runtime_error("comm_init: bad rank / nranks");
   c->rank = rank, c->nranks = nranks;
+  // Choosing NCCL is a decision for the whole job: a rank whose peer-memory setup succeeded must
+  // not keep reducing through its windows while another rank, whose setup failed, waits in NCCL.
+  peer_disconnect(c);
   if (nranks == 1)
     return;
   ncclUniqueId id;

@@ -123,10 +123,9 @@ void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
 /// Star-walk variant (assemble_walk.cu); returns false when it does not apply (no walk uploaded,
 /// not scalar P1, rows longer than 32 columns) and the caller falls through to the default kernel.
 bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A);
-/// Direct-gather walk kernels (assemble_gwalk.cu, opt-in PTB_ASM_GWALK=1); same convention.
-bool launch_assemble_matrix_gwalk(ptb_ctx* c, const MatrixArgs& A);
+/// Direct-gather walk kernel of the P1 cell vector (assemble_gwalk.cu); same convention: false
+/// when the single-reload walk is not on the device (PTB_VEC_GWALK=0, device-built maps).
 bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A);
-bool launch_action_gwalk(ptb_ctx* c, const VectorArgs& A, const double* p, double* y, double* py_out);
 void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A);
 void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F);
 /// Matrix-free y = A p (Poisson P1); py_out (device, optional) receives the local p.y.

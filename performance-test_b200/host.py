@@ -31,6 +31,7 @@ def lib():
                                       C.POINTER(C.c_int64)]
         L.pth_problem_create.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.pth_problem_create_sizes_only.argtypes = L.pth_problem_create.argtypes
         L.pth_problem_destroy.argtypes = [C.c_void_p]
         L.pth_problem_destroy.restype = None
         L.pth_problem_scalar.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
@@ -69,10 +70,12 @@ class Problem:
     """Mesh slab + function space + BC + RHS + sparsity pattern for one rank (host memory)."""
 
     def __init__(self, problem_type: str, order: int, nx: int, ny: int, nz: int,
-                 rank: int = 0, nranks: int = 1):
+                 rank: int = 0, nranks: int = 1, with_dofmap: bool = True):
+        """with_dofmap=False: sizes, halo lists and exterior facets only (the arrays are generated
+        on the device by Context.set_problem_on_device)."""
         self._h = C.c_void_p()
-        _check(lib().pth_problem_create(problem_type.encode(), order, nx, ny, nz, rank, nranks,
-                                        C.byref(self._h)))
+        create = lib().pth_problem_create if with_dofmap else lib().pth_problem_create_sizes_only
+        _check(create(problem_type.encode(), order, nx, ny, nz, rank, nranks, C.byref(self._h)))
         self.problem_type = problem_type
         for name in SCALARS:
             v = C.c_int64()

@@ -91,6 +91,23 @@ int pth_problem_create(const char* problem_type, int order, int64_t nx, int64_t 
   });
 }
 
+int pth_problem_create_sizes_only(const char* problem_type, int order, int64_t nx, int64_t ny,
+                                  int64_t nz, int rank, int nranks, pth_problem** out)
+{
+  return guarded([&] {
+    const std::string type(problem_type);
+    if (type != "poisson" && type != "cgpoisson" && type != "elasticity")
+      throw std::runtime_error("Unknown problem type: " + type);
+    auto p = std::make_unique<pth_problem>();
+    p->type = type;
+    p->mesh = create_box_mesh(nx, ny, nz, rank, nranks, false);
+    p->V = create_functionspace(p->mesh, order, type == "elasticity" ? 3 : 1, false);
+    exterior_facets(p->mesh, p->facet_cells, p->facet_local);
+    p->rowptr.assign(1, 0);
+    *out = p.release();
+  });
+}
+
 void pth_problem_destroy(pth_problem* p) { delete p; }
 
 int pth_problem_scalar(const pth_problem* p, const char* name, int64_t* out)

@@ -53,20 +53,21 @@ def ab(ndofs):
 
 
 def ab2(ndofs):
-    """Matrix and vector assembly: default kernels against the opt-in ones (PTB_ASM_GWALK for
-    Poisson and elasticity, PTB_ASM_WALK3 for the elasticity matrix), one context per variant."""
+    """Matrix and vector assembly: the default kernels against the generation they replaced
+    (PTB_VEC_GWALK=0 staged-star vector kernel, PTB_ASM_WALK3=0 / PTB_ASM_WALK=0 cell-order matrix
+    kernels), one context per variant."""
     for ptype, dpn in (("poisson", 1), ("elasticity", 3)):
         nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, dpn, 1, 1)
         f = 2 ** r
         P = pt.host.Problem(ptype, 1, nx * f, ny * f, nz * f)
         ref = None
-        variants = [("default", {}), ("gwalk", {"PTB_ASM_GWALK": "1"})]
+        variants = [("default", {}), ("staged_vector", {"PTB_VEC_GWALK": "0"})]
         if ptype == "elasticity":
-            variants.append(("walk3", {"PTB_ASM_WALK3": "1"}))
+            variants.append(("cellorder", {"PTB_ASM_WALK3": "0"}))
         else:
             variants.append(("cellorder", {"PTB_ASM_WALK": "0"}))
         for name, env in variants:
-            for k in ("PTB_ASM_GWALK", "PTB_ASM_WALK3", "PTB_ASM_WALK"):
+            for k in ("PTB_VEC_GWALK", "PTB_ASM_WALK3", "PTB_ASM_WALK"):
                 os.environ.pop(k, None)
             os.environ.update(env)
             c = pt.abi.Context(0)
@@ -108,26 +109,22 @@ def abpk(ndofs):
 
 
 def abmf(ndofs):
-    """Matrix-free CG (cgpoisson's action) on Poisson P1: staged-star kernel vs direct-gather walk,
-    next to the assembled operator; DOF-iterations/s from the device time of the solve stage."""
+    """Matrix-free CG (cgpoisson's action) on Poisson P1 next to the assembled operator;
+    DOF-iterations/s from the device time of the solve stage."""
     nx, ny, nz, r = pt.host.cube_sizing(ndofs, True, 1, 1, 1)
     f = 2 ** r
     P = pt.host.Problem("poisson", 1, nx * f, ny * f, nz * f)
-    for name, env in (("staged", {}), ("gwalk", {"PTB_ASM_GWALK": "1"})):
-        os.environ.pop("PTB_ASM_GWALK", None)
-        os.environ.update(env)
-        c = pt.abi.Context(0)
-        c.set_problem(P)
-        c.assemble_matrix()
-        c.assemble_vector()
-        for mode in ("assembled", "matrix_free"):
-            c.set_operator_mode(mode)
-            k, rel = c.cg_solve(kmax=200, rtol=1e-30)
-            ms = c.stage_ms(pt.abi.STAGE_SOLVE)
-            res[f"cg_{name}_{mode}"] = {"iterations": k, "solve_ms": ms,
-                                        "gdof_it_per_s": k * P.n_owned / ms / 1e6}
-            dump()
-        c.close()
+    c = pt.abi.Context(0)
+    c.set_problem(P)
+    c.assemble_matrix()
+    c.assemble_vector()
+    for mode in ("assembled", "matrix_free"):
+        c.set_operator_mode(mode)
+        k, rel = c.cg_solve(kmax=200, rtol=1e-30)
+        ms = c.stage_ms(pt.abi.STAGE_SOLVE)
+        res[f"cg_{mode}"] = {"iterations": k, "solve_ms": ms, "gdof_it_per_s": k * P.n_owned / ms / 1e6}
+        dump()
+    c.close()
 
 
 def absetup(ndofs):

@@ -91,8 +91,7 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 
 extern "C" {
 
-// variant: 0 walk<1,true>  1 walk<2,false>  2 walk3<true>  3 gwalk matrix<4>  4 gwalk matrix<1>
-//          5 gwalk3 (elasticity)
+// variant: 0 walk<1,true>  1 walk<2,false>  2 walk3<true>  6 walk<1,true,EXACT>
 int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w, int bs,
                         const uint8_t* bc, const int64_t* rowptr, const int64_t* mat_off,
                         const int64_t* adj_off, const int32_t* cols, const double* xdof,
@@ -113,29 +112,8 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
       return 2;
     emu_launch(assemble_matrix_p1_walk3<true>, n_slices, 96, A, walk);
     break;
-  case 3: emu_launch(assemble_matrix_p1_gwalk<4>, (n_slices + 3) / 4, 128, A, walk1, walk1_off); break;
-  case 4: emu_launch(assemble_matrix_p1_gwalk<1>, n_slices, 32, A, walk1, walk1_off); break;
-  case 7: emu_launch(assemble_matrix_p1_gwalk<1, true>, n_slices, 32, A, walk1, walk1_off); break; // cross_rn
-  case 5:
-    if (bs != 3)
-      return 2;
-    emu_launch(assemble_matrix_p1_gwalk3, n_slices, 96, A, walk1, walk1_off);
-    break;
   default: return 1;
   }
-  return 0;
-}
-
-// y = A p without A (action_p1_gwalk) + the per-slice partials of p.y
-int emu_action(int32_t n_rows, int32_t n_slices, int max_w, const uint8_t* bc, const int64_t* mat_off,
-               const int32_t* cols, const double* xdof, const uint32_t* walk1,
-               const int64_t* walk1_off, const double* p, double* y, double* partials)
-{
-  using namespace ptb;
-  VectorArgs A{};
-  A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.mat_off = mat_off, A.cols = cols;
-  A.xdof = xdof, A.max_w = max_w;
-  emu_launch(action_p1_gwalk<4>, (n_slices + 3) / 4, 128, A, walk1, walk1_off, p, y, partials);
   return 0;
 }
 

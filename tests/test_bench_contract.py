@@ -43,3 +43,14 @@ def test_algorithmic_byte_model(pt):
     spmv, cg, asm = bench.algorithmic_bytes(E)
     assert spmv == 76 * E.nnz + 52 * E.n_owned             # 3x3 BCSR
     assert cg == spmv + 96 * 3 * E.n_owned
+
+
+def test_default_run_is_the_north_star_target():
+    """No flags = BASELINE configs[2] (elasticity P1 strong 10M) as the headline line, configs[1]
+    (Poisson P1 weak 20M/GPU) under "secondary"."""
+    sys.path.insert(0, ROOT)
+    import bench
+    assert bench.DEFAULT_HEADLINE == "elasticity" and bench.DEFAULT_SECONDARY == "poisson"
+    assert bench.WORKLOADS["elasticity"][:4] == ("elasticity", "strong", 10_000_000, 1)
+    assert bench.WORKLOADS["poisson"][:4] == ("poisson", "weak", 20_000_000, 1)
+    assert bench.WORKLOADS["elasticity_weak"][:4] == ("elasticity", "weak", 100_000_000, 1)

@@ -73,8 +73,6 @@ def test_full_run_matches_oracle(pt, oracle, ptype, ndofs):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("PTB_TEST_OPTIN") != "1",
-                    reason="opt-in path not yet validated on a GPU (PTB_TEST_OPTIN=1)")
 @pytest.mark.parametrize("ptype,order,ndofs", [("poisson", 1, 40000), ("elasticity", 1, 30000), ("poisson", 2, 30000)])
 def test_device_setup_run_equals_the_host_setup_run(pt, ptype, order, ndofs):
     """--device_setup (mesh, dofmap, pattern, boundary conditions, RHS generated on the GPU; with

@@ -47,12 +47,10 @@ def test_partitioned_assembly_is_partition_independent(pt, ptype, order, dims, w
     ctx.close()
 
 
-@pytest.mark.skipif(os.environ.get("PTB_TEST_OPTIN") != "1",
-                    reason="opt-in path not yet validated on a GPU (PTB_TEST_OPTIN=1)")
 @pytest.mark.parametrize("ptype,order,dims,world",
                          [("poisson", 1, (9, 8, 10), 3), ("elasticity", 1, (6, 5, 8), 2),
                           ("poisson", 2, (4, 5, 6), 2), ("poisson", 3, (3, 3, 5), 2)])
-def test_opt_in_device_generated_slabs_are_partition_independent(pt, monkeypatch, ptype, order, dims, world):
+def test_device_generated_slabs_are_partition_independent(pt, monkeypatch, ptype, order, dims, world):
     """The same check with every rank's slab generated on the device (ptb_create_box with rank > 0:
     ghost layer below, ghost plane above; pattern, layouts and maps device-built with
     PTB_GPU_SETUP=1): rows and right-hand side equal the serial host-built ones bit for bit, except

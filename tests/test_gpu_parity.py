@@ -261,7 +261,7 @@ def test_matrix_free_needs_no_matrix(pt, ctx):
         ctx.set_operator_mode("matrix_free")
 
 
-def test_opt_in_operator_variants_in_a_subprocess(pt):
+def test_operator_variants_in_a_subprocess(pt):
     """The TMA-staged SpMV (PTB_SPMV_TMA=1) and the clustered slice order (PTB_SLICE_CLUSTER=1) are
     opt-in A/B variants read once per process: check them against the oracle in a child process."""
     import os
@@ -313,24 +313,32 @@ def test_star_walk_and_cell_order_kernels_agree(pt, dims, monkeypatch):
     assert np.allclose(out["1"][1], out["0"][1], rtol=1e-13, atol=0)
 
 
-# Kernels written after round 1's GPU budget was spent: compiled, pinned on the CPU through their
-# numpy restatements (tests/test_star_walk.py), never executed. PTB_TEST_OPTIN=1 runs them.
+# Kernels written at the end of round 1 and first executed on a B200 in round 2
+# (profiles/r02/first_call.log): defaults or kept switches now, their tests run un-gated.
 import os  # noqa: E402
 
-OPTIN = pytest.mark.skipif(os.environ.get("PTB_TEST_OPTIN") != "1",
-                           reason="opt-in kernels not yet validated on a GPU (PTB_TEST_OPTIN=1)")
+
+def _check_cg(k, rel, k_ref, rel_ref, rtol=1e-8):
+    """Iteration count +-1 and a converged residual -- or, on a mesh whose dofs are all constrained
+    (b = 0, |r0| = 0), cg.h's unguarded NaN ratio: never converges, k = kmax on both sides."""
+    if np.isnan(rel_ref):
+        assert np.isnan(rel) and k == k_ref
+    else:
+        assert abs(k - k_ref) <= 1 and rel < rtol
 
 
-@OPTIN
 @pytest.mark.parametrize("env,ptype,dims", [
     ("PTB_ASM_WALK3", "elasticity", (4, 5, 3)), ("PTB_ASM_WALK3", "elasticity", (1, 1, 2)),
     ("PTB_ASM_WALK3", "elasticity", (12, 11, 13)),
-    ("PTB_ASM_GWALK", "poisson", (5, 4, 6)), ("PTB_ASM_GWALK", "poisson", (1, 1, 1)),
-    ("PTB_ASM_GWALK", "poisson", (16, 15, 17)), ("PTB_ASM_GWALK", "poisson", (33, 3, 2)),
-    ("PTB_ASM_GWALK", "elasticity", (4, 5, 3)), ("PTB_ASM_GWALK", "elasticity", (12, 11, 13))])
-def test_opt_in_assembly_kernels_match_oracle(pt, oracle, monkeypatch, env, ptype, dims):
+    ("PTB_VEC_GWALK", "poisson", (5, 4, 6)), ("PTB_VEC_GWALK", "poisson", (1, 1, 1)),
+    ("PTB_VEC_GWALK", "poisson", (16, 15, 17)), ("PTB_VEC_GWALK", "poisson", (33, 3, 2)),
+    ("PTB_VEC_GWALK", "elasticity", (4, 5, 3)), ("PTB_VEC_GWALK", "elasticity", (12, 11, 13))])
+@pytest.mark.parametrize("on", ["1", "0"])
+def test_both_generations_of_the_p1_assembly_kernels_match_oracle(pt, oracle, monkeypatch, env, ptype, dims, on):
+    """The round-2 defaults (elasticity matrix along the star walk, cell vector by direct gather;
+    on = 1) and the kernels they replaced (on = 0), same oracle, same tolerances."""
     P = pt.host.Problem(ptype, 1, *dims)
-    monkeypatch.setenv(env, "1")
+    monkeypatch.setenv(env, on)
     c = pt.abi.Context(0)
     try:
         c.set_problem(P)
@@ -349,7 +357,6 @@ def test_opt_in_assembly_kernels_match_oracle(pt, oracle, monkeypatch, env, ptyp
         c.close()
 
 
-@OPTIN
 def test_persistent_cg_loop_in_a_subprocess(pt):
     """PTB_CG_PERSISTENT=1 (one cooperative kernel for the whole loop, cg.cu cg_loop) against the
     oracle's iteration counts and the true residual; the switch is read once per process."""
@@ -369,10 +376,14 @@ for ptype, dims in (("poisson", (16, 15, 17)), ("poisson", (1, 1, 2)), ("elastic
     ctx.assemble_matrix(); ctx.assemble_vector()
     for precond in ("jacobi", "none"):
         ctx.set_initial_guess(None)
-        k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond=precond)
         A, b = ctx.matrix_values(), ctx.rhs()
-        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b,
-                                kmax=5000, rtol=1e-8, precond=precond)
+        kmax = 5000 if b.any() else 40    # (1, 1, 2): every dof constrained, b = 0, cg.h runs kmax iterations on NaNs
+        k, rel = ctx.cg_solve(kmax=kmax, rtol=1e-8, precond=precond)
+        _, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b,
+                                      kmax=kmax, rtol=1e-8, precond=precond)
+        if np.isnan(rel_ref):
+            assert np.isnan(rel) and k == k_ref == kmax, (ptype, dims, precond, k, k_ref, rel)
+            continue
         assert abs(k - k_ref) <= 1, (ptype, dims, precond, k, k_ref)
         r = b - ctx.apply_operator(ctx.solution())
         assert rel < 1e-8 and np.linalg.norm(r) <= 5e-8 * np.linalg.norm(b)
@@ -387,7 +398,6 @@ print("persistent ok")
     assert r.returncode == 0 and "persistent ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
 
 
-@OPTIN
 @pytest.mark.parametrize("order,dims", [(2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)), (3, (6, 5, 7))])
 def test_binned_p2_p3_matrix_kernel_matches_oracle(pt, oracle, monkeypatch, order, dims):
     P = pt.host.Problem("poisson", order, *dims)
@@ -428,32 +438,8 @@ def test_assembly_and_solve_on_a_jittered_mesh(pt, oracle, perturbed, ctx, ptype
     assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
 
 
-@OPTIN
-@pytest.mark.parametrize("dims", [(5, 4, 6), (16, 15, 17), (1, 1, 1)])
-def test_opt_in_matrix_free_action_equals_assembled_operator(pt, monkeypatch, dims):
-    """PTB_ASM_GWALK=1 also switches the matrix-free P1 operator to action_p1_gwalk."""
-    P = pt.host.Problem("poisson", 1, *dims)
-    monkeypatch.setenv("PTB_ASM_GWALK", "1")
-    c = pt.abi.Context(0)
-    try:
-        c.set_problem(P)
-        c.assemble_matrix()
-        c.assemble_vector()
-        p = np.random.default_rng(5).standard_normal(P.n_owned + P.n_ghost)
-        y_a = c.apply_operator(p)
-        k_a, _ = c.cg_solve(kmax=5000, rtol=1e-8)
-        c.set_operator_mode("matrix_free")
-        y_m = c.apply_operator(p)
-        assert np.abs(y_m - y_a).max() <= 1e-12 * np.abs(y_a).max()
-        k_m, rel = c.cg_solve(kmax=5000, rtol=1e-8)
-        assert abs(k_m - k_a) <= 1 and rel < 1e-8
-    finally:
-        c.close()
-
-
-@OPTIN
 @pytest.mark.parametrize("dims", [(16, 15, 17), (5, 4, 6), (1, 1, 1), (33, 9, 5)])
-def test_opt_in_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, dims):
+def test_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, dims):
     """PTB_SPMV_COMPACT=1: the SpMV runs on a copy of A without the all-zero SELL positions; y is
     unchanged to the bit, CG takes the same iterations, the C ABI still returns the full pattern."""
     P = pt.host.Problem("poisson", 1, *dims)
@@ -476,9 +462,8 @@ def test_opt_in_operator_compaction_keeps_the_operator(pt, oracle, monkeypatch, 
     _check_matrix(P, out["1"][2], oracle.assemble_matrix(P))
 
 
-@OPTIN
 @pytest.mark.parametrize("tol", ["0", "1e-14"])
-def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol):
+def test_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol):
     """How many SELL positions survive on the lattice, with exact zeros only (tol 0) and with the
     rounding residue of analytic zeros counted as zero (tol 1e-14 of the row's diagonal). With
     PTB_SPMV_COMPACT=1 the matrix kernel computes its cofactor vectors without FMA contraction
@@ -502,9 +487,8 @@ def test_opt_in_operator_compaction_reports_what_it_dropped(pt, monkeypatch, tol
     assert kept < 0.6 * full
 
 
-@OPTIN
 @pytest.mark.parametrize("order,dims", [(2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)), (3, (6, 5, 7))])
-def test_opt_in_device_setup_p2_p3_slot_words(pt, oracle, monkeypatch, order, dims):
+def test_device_setup_p2_p3_slot_words(pt, oracle, monkeypatch, order, dims):
     """PTB_GPU_SETUP=1 for P2/P3: pair words and packed slot offsets built by setup_adj_pk; the
     assembled matrix and vector match the oracle (the words themselves are compared with the host
     build on the CPU by tests/test_kernel_sources_on_host.py)."""
@@ -524,10 +508,9 @@ def test_opt_in_device_setup_p2_p3_slot_words(pt, oracle, monkeypatch, order, di
         c.close()
 
 
-@OPTIN
 @pytest.mark.parametrize("ptype,dims", [("poisson", (5, 4, 6)), ("poisson", (1, 1, 1)), ("poisson", (33, 2, 1)),
                                         ("poisson", (40, 38, 41)), ("elasticity", (12, 11, 13))])
-def test_opt_in_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype, dims):
+def test_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype, dims):
     """PTB_GPU_SETUP=1: adj_off, the rotated slot words and the star walk built by the setup kernels
     (csrc/setup.cu) equal the host build word for word, and assembly through them matches the oracle."""
     P = pt.host.Problem(ptype, 1, *dims)
@@ -553,11 +536,10 @@ def test_opt_in_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype
         c.close()
 
 
-@OPTIN
 @pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
                                               ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
                                               ("poisson", 3, (4, 5, 3))])
-def test_opt_in_device_built_pattern_equals_the_host_pattern(pt, oracle, monkeypatch, ptype, order, dims):
+def test_device_built_pattern_equals_the_host_pattern(pt, oracle, monkeypatch, ptype, order, dims):
     """ptb_build_pattern (the reference's create_matrix step, on the device) returns the host
     pattern bit for bit; matrix, vector and solve through it match the oracle. With PTB_GPU_SETUP=1
     the whole integer side of a P1 problem (pattern, slot words, walk) is device-built."""
@@ -582,19 +564,19 @@ def test_opt_in_device_built_pattern_equals_the_host_pattern(pt, oracle, monkeyp
         y_ref = oracle.spmv(P.bs, P.n_owned, P["rowptr"], P["cols"], c.matrix_values(), p)
         assert np.abs(c.apply_operator(p) - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
         assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
-        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
-        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
-                                precond="jacobi")
-        assert abs(k - k_ref) <= 1 and rel < 1e-8
+        kmax = 5000 if b_ref.any() else 40
+        k, rel = c.cg_solve(kmax=kmax, rtol=1e-8, precond="jacobi")
+        _, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=kmax, rtol=1e-8,
+                                      precond="jacobi")
+        _check_cg(k, rel, k_ref, rel_ref)
     finally:
         c.close()
 
 
-@OPTIN
 @pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
                                               ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
                                               ("poisson", 3, (4, 5, 3))])
-def test_opt_in_device_problem_data_matches_the_host(pt, oracle, ptype, order, dims):
+def test_device_problem_data_matches_the_host(pt, oracle, ptype, order, dims):
     """ptb_locate_bc / ptb_interpolate_source (the reference's 'ZZZ Create boundary conditions' and
     'ZZZ Create RHS function' on the device): the same Dirichlet dofs; f and g within 4 ulp of the
     host's libm (the arguments of exp / sin / sqrt are identical, only the functions round
@@ -614,20 +596,20 @@ def test_opt_in_device_problem_data_matches_the_host(pt, oracle, ptype, order, d
         A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
         _check_matrix(P, c.matrix_values(), A_ref)
         assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
-        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
-        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
-                                precond="jacobi")
-        assert abs(k - k_ref) <= 1 and rel < 1e-8
+        kmax = 5000 if b_ref.any() else 40
+        k, rel = c.cg_solve(kmax=kmax, rtol=1e-8, precond="jacobi")
+        _, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=kmax, rtol=1e-8,
+                                      precond="jacobi")
+        _check_cg(k, rel, k_ref, rel_ref)
     finally:
         c.close()
 
 
-@OPTIN
 @pytest.mark.parametrize("gpu_setup", ["0", "1"])
 @pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (16, 15, 17)), ("poisson", 1, (1, 1, 1)),
                                               ("elasticity", 1, (8, 9, 7)), ("poisson", 2, (6, 5, 7)),
                                               ("poisson", 3, (4, 5, 3))])
-def test_opt_in_whole_setup_generated_on_the_device(pt, oracle, monkeypatch, ptype, order, dims, gpu_setup):
+def test_whole_setup_generated_on_the_device(pt, oracle, monkeypatch, ptype, order, dims, gpu_setup):
     """ptb_create_box + ptb_build_pattern + ptb_locate_bc + ptb_interpolate_source: mesh, dofmap, dof
     coordinates, pattern and Dirichlet dofs equal the host stand-in's arrays bit for bit, and the hot
     path on top of them matches the oracle. With PTB_GPU_SETUP=1 the layouts and assembly maps are
@@ -652,9 +634,10 @@ def test_opt_in_whole_setup_generated_on_the_device(pt, oracle, monkeypatch, pty
         _check_matrix(P, c.matrix_values(), A_ref)
         # f and g come from the device's exp / sin: a few ulp of the host's, see the problem-data test
         assert np.abs(c.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
-        k, rel = c.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
-        _, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000, rtol=1e-8,
-                                precond="jacobi")
-        assert abs(k - k_ref) <= 1 and rel < 1e-8
+        kmax = 5000 if b_ref.any() else 40
+        k, rel = c.cg_solve(kmax=kmax, rtol=1e-8, precond="jacobi")
+        _, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=kmax, rtol=1e-8,
+                                      precond="jacobi")
+        _check_cg(k, rel, k_ref, rel_ref)
     finally:
         c.close()
