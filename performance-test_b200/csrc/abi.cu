@@ -49,6 +49,29 @@ std::int64_t n_local_entries(const ptb_ctx* c)
 {
   return (static_cast<std::int64_t>(c->n_owned) + c->n_ghost) * c->bs;
 }
+
+// L2 plan of the operator kernels: B200 has 126 MB of L2. The six solver
+// vectors (x, p, r, y, b, D^-1) are re-read every CG iteration, the matrix is a pure stream. When
+// the vectors fit (strong scaling: 10 M DOFs over 8 GPUs = 60 MB per GPU) the matrix stream is
+// loaded evict_first so that it cannot push them out, and a prefix of the matrix as large as the
+// rest of the budget is loaded evict_last, i.e. stays resident from one iteration to the next.
+// PTB_L2_POLICY=0 switches the hints off, PTB_L2_BUDGET_MB sets the budget (default 96 of 126 MB),
+// PTB_L2_PIN_MB overrides the size of the pinned prefix.
+void plan_l2(ptb_ctx* c)
+{
+  c->l2_mode = env_flag("PTB_L2_POLICY", true) ? 1 : 0;
+  c->l2_pin_entries = 0;
+  if (!c->l2_mode)
+    return;
+  const double budget = 1048576.0 * env_int("PTB_L2_BUDGET_MB", 96);
+  const double vec_bytes = 6.0 * 8.0 * static_cast<double>(n_local_entries(c));
+  double pin = vec_bytes < budget ? budget - vec_bytes : 0.0;
+  const int pin_mb = env_int("PTB_L2_PIN_MB", -1);
+  if (pin_mb >= 0)
+    pin = 1048576.0 * pin_mb;
+  const double bytes_per_entry = c->bs == 1 ? 12.0 : 76.0; // value(s) + column index
+  c->l2_pin_entries = static_cast<std::int64_t>(pin / bytes_per_entry);
+}
 // The host copy of the dofmap (integer maps built on the host); a space generated on the device
 // (ptb_create_box) has none until someone asks.
 void host_dofmap(ptb_ctx* c)
@@ -482,6 +505,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       std::vector<std::uint32_t>().swap(c->h_adj.pairs);
       std::vector<std::uint16_t>().swap(c->h_so);
     }
+    plan_l2(c);
     c->have_pattern = true;
     c->matrix_assembled = false;
     c->have_compact = false;
@@ -549,6 +573,7 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
     c->vals.zero(c->stream);
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     c->maps_on_device = true;
+    plan_l2(c);
     c->have_pattern = true;
     c->matrix_assembled = false;
     c->have_compact = false;

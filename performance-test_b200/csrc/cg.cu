@@ -47,11 +47,24 @@ __device__ __forceinline__ double ldp(const double* q)
 }
 
 // One SELL-32 slice: y[row] = sum_k vals * p[col]; returns this row's p.y contribution.
+// Matrix values and column indices go through ld_stream with the slice's L2 policy (pinned prefix:
+// evict_last, streamed rest: evict_first; sync_ops.cuh), the gathers of p through ldp<L>.
+struct L2Plan
+{
+  unsigned long long stream, pinned;
+};
+__device__ __forceinline__ L2Plan l2_plan(const SpmvArgs& A)
+{
+  return A.l2_mode ? L2Plan{l2_policy(1), l2_policy(2)} : L2Plan{l2_policy(0), l2_policy(0)};
+}
+
 template <int BS, Ld L>
-__device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __restrict__ p,
-                                             double* __restrict__ y, std::int32_t slice, int lane)
+__device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP,
+                                             const double* __restrict__ p, double* __restrict__ y,
+                                             std::int32_t slice, int lane)
 {
   const std::int64_t mo = A.mat_off[slice];
+  const unsigned long long pol = mo < A.pin_entries ? LP.pinned : LP.stream;
   const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
   const std::int32_t row = slice * 32 + lane;
   if constexpr (BS == 1)
@@ -67,7 +80,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
     for (int k0 = 0; k0 < w; k0 += 32)
     {
       const int kn = min(32, w - k0);
-      const std::int32_t dl = lane < kn ? __ldg(dp + k0 + lane) : 0;
+      const std::int32_t dl = lane < kn ? ld_stream(dp + k0 + lane, pol) : 0;
       const unsigned int em = __ballot_sync(0xffffffffu, lane < kn && dl == INT32_MIN);
       const double* __restrict__ v = vp + static_cast<std::int64_t>(k0) * 32;
       if (em == 0u)
@@ -80,7 +93,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
 #pragma unroll
           for (int u = 0; u < U; ++u)
           {
-            vv[u] = v[(kk + u) * 32];
+            vv[u] = ld_stream(v + (kk + u) * 32, pol);
             pp[u] = ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk + u)));
           }
 #pragma unroll
@@ -88,7 +101,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
             sum += vv[u] * pp[u];
         }
         for (; kk < kn; ++kk)
-          sum += v[kk * 32] * ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk)));
+          sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk)));
       }
       else
       {
@@ -104,8 +117,8 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
           {
             const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk + u);
             const int rank = __popc(em & ((1u << (kk + u)) - 1u));
-            c[u] = ((em >> (kk + u)) & 1u) ? xp[rank * 32] : row + d;
-            vv[u] = v[(kk + u) * 32];
+            c[u] = ((em >> (kk + u)) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
+            vv[u] = ld_stream(v + (kk + u) * 32, pol);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -115,8 +128,8 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
         {
           const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
           const int rank = __popc(em & ((1u << kk) - 1u));
-          const std::int32_t c = ((em >> kk) & 1u) ? xp[rank * 32] : row + d;
-          sum += v[kk * 32] * ldp<L>(p + c);
+          const std::int32_t c = ((em >> kk) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
+          sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + c);
         }
         xp += __popc(em) * 32;
       }
@@ -135,12 +148,16 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const double* __
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int k = 0; k < w; ++k)
     {
-      const std::int64_t c = cp[k * 32];
+      const std::int64_t c = ld_stream(cp + k * 32, pol);
       const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
+      double a[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e)
+        a[e] = ld_stream(v + e * 32, pol);
       const double p0 = ldp<L>(p + 3 * c), p1 = ldp<L>(p + 3 * c + 1), p2 = ldp<L>(p + 3 * c + 2);
-      s0 += v[0 * 32] * p0 + v[1 * 32] * p1 + v[2 * 32] * p2;
-      s1 += v[3 * 32] * p0 + v[4 * 32] * p1 + v[5 * 32] * p2;
-      s2 += v[6 * 32] * p0 + v[7 * 32] * p1 + v[8 * 32] * p2;
+      s0 += a[0] * p0 + a[1] * p1 + a[2] * p2;
+      s1 += a[3] * p0 + a[4] * p1 + a[5] * p2;
+      s2 += a[6] * p0 + a[7] * p1 + a[8] * p2;
     }
     if (row < A.n_rows)
     {
@@ -292,6 +309,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
     return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int warps_per_cta = SPMV_THREADS / 32;
+  const L2Plan LP = l2_plan(A);
   double dotv = 0.0;
   if constexpr (FUSED)
   {
@@ -308,21 +326,21 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
       }
       for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
            it += FH.npull * warps_per_cta)
-        dotv += spmv_slice<BS, Ld::CG>(A, p, y, FH.order[it], lane);
+        dotv += spmv_slice<BS, Ld::CG>(A, LP, p, y, FH.order[it], lane);
     }
     else
     {
       const std::int32_t stride = (gridDim.x - FH.npull) * warps_per_cta;
       for (std::int32_t it = (blockIdx.x - FH.npull) * warps_per_cta + warp; it < FH.n_interior;
            it += stride)
-        dotv += spmv_slice<BS, Ld::NC>(A, p, y, FH.order[it], lane);
+        dotv += spmv_slice<BS, Ld::NC>(A, LP, p, y, FH.order[it], lane);
     }
   }
   else
   {
     const std::int32_t stride = gridDim.x * warps_per_cta;
     for (std::int32_t it = blockIdx.x * warps_per_cta + warp; it < A.n_slices; it += stride)
-      dotv += spmv_slice<BS, Ld::NC>(A, p, y, FH.order[it], lane);
+      dotv += spmv_slice<BS, Ld::NC>(A, LP, p, y, FH.order[it], lane);
   }
   if (st != nullptr)
   {
@@ -916,6 +934,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int warps_per_cta = SPMV_THREADS / 32;
   const SpmvArgs& A = L.A;
+  const L2Plan LP = l2_plan(A);
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
   const std::int64_t n2 = L.n >> 1;
   const std::int64_t tid = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
@@ -952,21 +971,21 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
         }
         for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
              s += FH.npull * warps_per_cta)
-          dotv += spmv_slice<BS, Ld::CG>(A, L.p, L.y, FH.order[s], lane);
+          dotv += spmv_slice<BS, Ld::CG>(A, LP, L.p, L.y, FH.order[s], lane);
       }
       else
       {
         const std::int32_t stride = (gridDim.x - FH.npull) * warps_per_cta;
         for (std::int32_t s = (blockIdx.x - FH.npull) * warps_per_cta + warp; s < FH.n_interior;
              s += stride)
-          dotv += spmv_slice<BS, Ld::CA>(A, L.p, L.y, FH.order[s], lane);
+          dotv += spmv_slice<BS, Ld::CA>(A, LP, L.p, L.y, FH.order[s], lane);
       }
     }
     else
     {
       const std::int32_t stride = gridDim.x * warps_per_cta;
       for (std::int32_t s = blockIdx.x * warps_per_cta + warp; s < A.n_slices; s += stride)
-        dotv += spmv_slice<BS, Ld::CA>(A, L.p, L.y, FH.order[s], lane);
+        dotv += spmv_slice<BS, Ld::CA>(A, LP, L.p, L.y, FH.order[s], lane);
     }
     const unsigned int ea = L.ebase + 2u * static_cast<unsigned int>(j - 1), eb = ea + 1u;
     double v1[1] = {dotv}, py[1];

@@ -134,6 +134,9 @@ struct ptb_ctx
   ptb::DevBuf<std::int32_t> cdelta_z, colsx_z;
   bool have_compact = false;
   std::int64_t compact_nnz = 0; // stored entries (padding included) of the compacted copy
+  // L2 plan of the operator kernels (abi.cu plan_l2): hints on/off, pinned prefix in mat_off units
+  int l2_mode = 0;
+  std::int64_t l2_pin_entries = 0;
   ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)
   std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry

@@ -78,6 +78,10 @@ struct SpmvArgs
   const std::int32_t* cdelta; // scalar matrices: compressed columns (nullptr: use cols)
   const std::int32_t* colsx;
   const std::int64_t* xoff;
+  // L2 plan (sync_ops.cuh l2_policy): l2_mode 0 = no hints; 1 = slices stored below pin_entries
+  // (mat_off units) are loaded evict_last, the rest evict_first
+  int l2_mode;
+  std::int64_t pin_entries;
 };
 
 /// The operator view the SpMV kernels read: the compacted copy when one is current (compact.cu).
@@ -85,9 +89,9 @@ inline SpmvArgs spmv_args(const ptb_ctx* c)
 {
   if (c->have_compact)
     return SpmvArgs{c->n_owned, c->n_slices, c->mat_off_z.p, c->cols.p, c->vals_z.p,
-                    c->cdelta_z.p, c->colsx_z.p, c->xoff_z.p};
+                    c->cdelta_z.p, c->colsx_z.p, c->xoff_z.p, c->l2_mode, c->l2_pin_entries};
   return SpmvArgs{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
-                  c->cdelta.p, c->colsx.p, c->xoff.p};
+                  c->cdelta.p, c->colsx.p, c->xoff.p, c->l2_mode, c->l2_pin_entries};
 }
 /// Build the zero-column-compacted copy of the assembled scalar operator (no-op for bs = 3).
 void compact_operator(ptb_ctx* c);

@@ -34,6 +34,9 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return emu_ld(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) { emu_st(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ double ld_ca_f64(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
+__device__ __forceinline__ unsigned long long l2_policy(int) { return 0ull; }
+__device__ __forceinline__ double ld_stream(const double* q, unsigned long long) { return *q; }
+__device__ __forceinline__ int ld_stream(const int* q, unsigned long long) { return *q; }
 #else
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
 {
@@ -80,6 +83,34 @@ __device__ __forceinline__ double ld_ca_f64(const double* q)
 {
   double v;
   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(q));
+  return v;
+}
+// L2 residency control for the operator stream ("L2 plan"). The matrix is read
+// once per CG iteration and never again before ~0.5-4 GB of other traffic has passed, while the
+// vectors (and a fixed prefix of the matrix, sized to what is left of the 126 MB L2) are re-read
+// every iteration: matrix loads carry an L2 eviction-priority hint and bypass L1.
+//   kind 0: evict_normal   1: evict_first (streamed part)   2: evict_last (pinned prefix)
+__device__ __forceinline__ unsigned long long l2_policy(int kind)
+{
+  unsigned long long pol;
+  if (kind == 1)
+    asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  else if (kind == 2)
+    asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  else
+    asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ double ld_stream(const double* q, unsigned long long pol)
+{
+  double v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.f64 %0, [%1], %2;" : "=d"(v) : "l"(q), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int ld_stream(const int* q, unsigned long long pol)
+{
+  int v;
+  asm("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(q), "l"(pol));
   return v;
 }
 #endif

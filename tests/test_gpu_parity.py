@@ -189,6 +189,117 @@ def test_config1_full_size_against_oracle(pt, oracle, ctx):
     assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
 
 
+@pytest.mark.parametrize("ptype,order,dims", [("poisson", 1, (12, 11, 13)), ("poisson", 2, (5, 4, 6)),
+                                              ("elasticity", 1, (7, 6, 8))])
+def test_unpreconditioned_cg_equals_the_reference_cg_h(pt, oracle, ctx, ptype, order, dims):
+    """PTB_PC_NONE against linalg::cg of the reference COMPILED UNCHANGED (oracle/_ref/libref.so,
+    src/cg.h:38-86) on the matrix and right-hand side the GPU assembled: the same iteration count
+    (these cases are not borderline: the golden counts of tests/golden/ref_cg.json) and the same x
+    -- the dot products are summed in a different order on the device and CG amplifies that with
+    the iteration count, hence the graded tolerances; cg.h:78 is applied to the same quantity."""
+    from oracle import ref
+    if not ref.available():
+        pytest.skip("oracle/_ref/libref.so not shipped")
+    P = pt.host.Problem(ptype, order, *dims)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A, b = ctx.matrix_values(), ctx.rhs()
+    # x: 1e-12 |x|_inf after 7 iterations, 1e-9 after 25; at convergence the two runs have taken
+    # rounding-different Lanczos paths to the same tolerance (measured 1e-6 for elasticity, 218
+    # iterations, on the first GPU run), so there only the stopping iteration is compared strictly
+    for kmax, rtol, xtol in ((5000, 1e-8, 1e-5), (7, 1e-30, 1e-12), (25, 1e-30, 1e-9), (100, 1e-6, 1e-4)):
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=kmax, rtol=rtol, precond="none")
+        xs, k_ref = ref.cg([dict(bs=P.bs, n_owned=P.n_owned, n_ghost=0, rowptr=P["rowptr"], cols=P["cols"],
+                                 vals=A, b=b)], kmax=kmax, rtol=rtol)
+        assert k == k_ref, (kmax, rtol, k, k_ref)
+        x = ctx.solution()[: P.n_owned * P.bs]
+        err = np.abs(x - xs[0]).max() / np.abs(xs[0]).max()
+        assert err <= xtol, (kmax, rtol, err)
+
+
+def test_config3_full_size_against_oracle(pt, oracle, ctx):
+    """BASELINE configs[2], the north-star target: elasticity P1, --ndofs 10000000 strong
+    (148x148x149, 9 990 450 DOFs). A and b against the threaded oracle (same cell order per row, so
+    the thread count does not change a bit), the first 50 CG + Jacobi iterations through the
+    relative residual after 10 / 25 / 50 iterations (1e-10 relative) and x after 50. The full solve
+    (iteration count +-1) runs with PTB_TEST_FULLSIZE=1 (about two CPU-minutes for the oracle)."""
+    Nx, Ny, Nz, r = pt.host.cube_sizing(10_000_000, True, 3, 1, 1)
+    assert (Nx, Ny, Nz, r) == (148, 148, 149, 0)
+    P = pt.host.Problem("elasticity", 1, Nx, Ny, Nz)
+    assert (P.n_owned * 3, P.n_cells, P.nnz) == (9990450, 19582176, 49418832)
+    nt = oracle.max_threads()
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref, b_ref = oracle.assemble_matrix(P, nthreads=nt), oracle.assemble_vector(P)
+    A = ctx.matrix_values()
+    _check_matrix(P, A, A_ref)
+    del A
+    assert np.abs(ctx.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    for kmax in (10, 25, 50):
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=kmax, rtol=1e-8, precond="jacobi")
+        x_ref, k_ref, rel_ref = oracle.cg(3, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=kmax,
+                                          rtol=1e-8, precond="jacobi", nthreads=nt)
+        assert k == k_ref == kmax
+        assert abs(rel - rel_ref) <= 1e-10 * rel_ref, (kmax, rel, rel_ref)
+    x = ctx.solution()[: P.n_owned * 3]
+    assert np.abs(x - x_ref).max() <= 1e-10 * np.abs(x_ref).max()
+    if os.environ.get("PTB_TEST_FULLSIZE") == "1":
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=10000, rtol=1e-8, precond="jacobi")
+        x_ref, k_ref, rel_ref = oracle.cg(3, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=10000,
+                                          rtol=1e-8, precond="jacobi", nthreads=nt)
+        print(f"C3 full solve: GPU {k} iterations rel {rel:.6e}; oracle {k_ref} rel {rel_ref:.6e}")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8 and rel_ref < 1e-8
+        x = ctx.solution()[: P.n_owned * 3]
+        assert np.linalg.norm(x - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
+def test_config2_sampled_row_blocks_against_oracle(pt, oracle):
+    """BASELINE configs[1] at full size (Poisson P1 weak 20M DOFs/GPU, the 272x262x278 box): A and b
+    of the one-GPU problem against the oracle on sampled row blocks. A block = the rows owned by
+    rank q of a 24-slab partition of the same box, assembled by the oracle from that slab alone;
+    rows are partition independent (tests/test_distributed_cpu.py), so they must equal the rows
+    [offset, offset + n) of the GPU's matrix to the usual 1e-12 |A_rr|."""
+    Nx, Ny, Nz, r = pt.host.cube_sizing(20_000_000, False, 1, 1, 1)
+    dims = (Nx << r, Ny << r, Nz << r)
+    assert dims == (272, 262, 278)
+    P = pt.host.Problem("poisson", 1, *dims)
+    assert (P.n_owned, P.nnz) == (20031921, 298711329)
+    c = pt.abi.Context(0)
+    try:
+        c.set_problem(P)
+        c.assemble_matrix()
+        c.assemble_vector()
+        A, b = c.matrix_values(), c.rhs()
+    finally:
+        c.close()
+    rp = P["rowptr"]
+    for q in (0, 11, 23):
+        S = pt.host.Problem("poisson", 1, *dims, q, 24)
+        A_ref, b_ref = oracle.assemble_matrix(S, nthreads=oracle.max_threads()), oracle.assemble_vector(S)
+        off, n = S.global_offset, S.n_owned
+        # the slab's columns are local (owned then ghost): compare row by row through global ids
+        l2g = np.concatenate([np.arange(off, off + n), S["ghost_global"]])
+        srp, scl = S["rowptr"], S["cols"]
+        g_lo, g_hi = rp[off], rp[off + n]
+        assert g_hi - g_lo == srp[-1]
+        gcols = l2g[scl]
+        rows = np.repeat(np.arange(n), np.diff(srp))
+        order_ = np.lexsort((gcols, rows))          # slab rows re-sorted by global column
+        assert np.array_equal(gcols[order_], P["cols"][g_lo:g_hi])
+        ref_vals = A_ref[order_]
+        diag = np.zeros(n)
+        own = gcols[order_] == rows[order_] + off
+        diag[rows[order_][own]] = np.abs(ref_vals[own])
+        err = np.abs(A[g_lo:g_hi] - ref_vals) / diag[rows[order_]]
+        assert err.max() <= 1e-12, (q, err.max())
+        assert np.abs(b[off:off + n] - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
 def test_large_properties_elasticity(pt, ctx):
     """Size-independent properties at a size the oracle would not finish quickly (3.2M DOFs):
     symmetry via <Au, v> = <u, Av>, rigid-body modes in the kernel away from the BC, and the CG
