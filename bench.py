@@ -69,7 +69,8 @@ def parse():
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--kmax", type=int, default=KMAX)
     ap.add_argument("--ndofs", type=int, default=None, help="override the workload's --ndofs")
-    ap.add_argument("--cpu-sample-ndofs", type=int, default=2_000_000)
+    ap.add_argument("--cpu-kcap", type=int, default=200,
+                    help="CG iteration cap of the CPU arm (the metric is a rate)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"],
                     help="N>1: NVLink peer-memory kernels (default) or NCCL send/recv + all-reduce")
@@ -143,87 +144,96 @@ def algorithmic_bytes(P):
     return spmv, cg_iter, asm
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_arm(pt, wl_name, n_gpus, steps, warmup, kcap, ndofs_override=None):
+    """The reference's CPU path for this workload on the host cores, as BASELINE.md section 3 (ii)
+    plans it: the SAME mesh and --ndofs as the GPU arm at n_gpus GPUs, split into P partitions on
+    P threads -- each thread assembles its rank's rows with the sequential cell loop and the solve
+    runs with a halo exchange and rank-ordered reductions (the analogue of `mpirun -np P`). The
+    code is the oracle (kind "port": DOLFINx/PETSc cannot be installed here; its CG loop is pinned
+    bit for bit to the reference's cg.h compiled into oracle/_ref, tests/test_ref_pin.py), built
+    -Ofast like src/CMakeLists.txt:19-20. The solve is capped at kcap iterations: the metric is a
+    rate (DOF-iterations/s), and the full solve would take minutes per step."""
+    import oracle
+    oracle.build()
+    ptype, order, dims, base, scaling, ndofs = sizing(pt, wl_name, n_gpus, ndofs_override)
+    nthreads = host_threads()
+    nparts = max(1, min(nthreads, dims[2]))
+    t0 = time.perf_counter()
+    probs = [pt.host.Problem(ptype, order, *dims, q, nparts) for q in range(nparts)]
+    t_setup = time.perf_counter() - t0
+    ndof = probs[0].n_global * probs[0].bs
+    nnz = sum(P.nnz * P.bs * P.bs for P in probs)
+
+    def step():
+        mats, rhs, t_am, t_av = oracle.assemble_partitions(probs, fast=True)
+        t0 = time.perf_counter()
+        xs, k, rel = oracle.cg_partitioned(probs, mats, rhs, kmax=kcap, rtol=1e-8, precond="jacobi",
+                                           fast=True)
+        return t_am, t_av, time.perf_counter() - t0, k
+
+    for _ in range(warmup):
+        step()
+    ts = [step() for _ in range(steps)]
+    t_am, t_av = sum(t[0] for t in ts), sum(t[1] for t in ts)
+    t_solve, iters = sum(t[2] for t in ts), sum(t[3] for t in ts)
+    wl = WORKLOADS[wl_name]
+    sample = (f"same mesh as the GPU arm at {n_gpus} GPU(s): {ptype} P{order} --ndofs {ndofs} "
+              f"({scaling}) = {dims[0]}x{dims[1]}x{dims[2]} box, {ndof} DOFs; {nparts} partitions on "
+              f"{nparts} threads (z-slabs, halo exchange per iteration); per step: matrix assembly "
+              f"{t_am / steps:.2f} s, vector {t_av / steps:.2f} s, first {iters // steps} CG+Jacobi "
+              f"iterations (capped at {kcap}; the metric is a rate) {t_solve / steps:.2f} s")
+    return {"value": iters * ndof / t_solve, "unit": "DOF-iters/s", "cores": nparts, "kind": "port",
+            "sample": sample, "assembled_nnz_per_s": nnz * steps / t_am,
+            "ms_per_step": 1e3 * (t_am + t_av + t_solve) / steps, "cg_iterations": iters // steps,
+            "same_mesh_as_gpu_arm": True, "ndofs_global": ndof, "host_setup_s": t_setup,
+            "workload": wl[4]}
+
+
 def run_reference(args):
-    """--impl reference: the CPU restatement (oracle, -Ofast like src/CMakeLists.txt:19-20) with
-    all host threads, on a bounded sample of the same workload. DOLFINx/PETSc/MPI are not
-    installable here, so this is kind='port' (BASELINE.md section 2)."""
+    """--impl reference: the reference's CPU path (cpu_arm above) with all host threads, on the GPU
+    arm's own config. Rank 0 alone runs; the other ranks of a torchrun launch exit at once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     pt = importlib.import_module("performance-test_b200")
-    import oracle
-    oracle.build()
-    # all host cores: the other ranks of a torchrun launch exit at once, and the oracle takes its
-    # thread count as an argument (torchrun's OMP_NUM_THREADS=1 does not apply)
-    try:
-        nthreads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        nthreads = os.cpu_count() or 1
     wl_name = args.workload or DEFAULT_HEADLINE
-    ptype, order, dims, base, scaling, ndofs = sizing(pt, wl_name, 1, args.cpu_sample_ndofs)
-    P = pt.host.Problem(ptype, order, *dims)
-    ndof = P.n_owned * P.bs
-
-    def step():
-        t0 = time.perf_counter()
-        A = oracle.assemble_matrix(P, nthreads=nthreads, fast=True)
-        t1 = time.perf_counter()
-        b = oracle.assemble_vector(P, fast=True)
-        t2 = time.perf_counter()
-        x, k, rel = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=KMAX, rtol=1e-8,
-                              precond="jacobi", nthreads=nthreads, fast=True)
-        t3 = time.perf_counter()
-        return t1 - t0, t2 - t1, t3 - t2, k
-
-    for _ in range(min(args.warmup, 1)):
-        step()
-    ts = [step() for _ in range(args.steps)]
-    t_am = sum(t[0] for t in ts)
-    t_solve = sum(t[2] for t in ts)
-    iters = sum(t[3] for t in ts)
-    total = sum(t[0] + t[1] + t[2] for t in ts)
-    value = iters * ndof / t_solve
     wl = WORKLOADS[wl_name]
-    sample = (f"{ptype} P{order} at --ndofs {args.cpu_sample_ndofs} ({ndof} DOFs, {P.n_cells} cells), "
-              f"full hot path to rtol 1e-8, {nthreads} OpenMP threads")
+    c = cpu_arm(pt, wl_name, args.gpus, args.steps, min(args.warmup, 1), args.cpu_kcap, args.ndofs)
     line = {
-        "impl": "reference", "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
+        "impl": "reference", "metric": "cg_dof_iters_per_s", "value": c["value"], "unit": "DOF-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
+        "ms_per_step": c["ms_per_step"], "higher_is_better": True,
         "scaling": wl[1], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "assembled_nnz_per_s": P.nnz * P.bs * P.bs * args.steps / t_am,
-        "cg_iterations": iters // args.steps,
-        "config": {"workload": wl[4], "cpu_sample": sample},
-        "cpu_baseline": {"value": value, "unit": "DOF-iters/s", "cores": nthreads, "kind": "port",
-                         "sample": sample},
-        "e2e": {"value": value, "unit": "DOF-iters/s", "h2d_bytes_per_step": 0,
+        "assembled_nnz_per_s": c["assembled_nnz_per_s"], "cg_iterations": c["cg_iterations"],
+        "ndofs_global": c["ndofs_global"],
+        "config": {"workload": wl[4], "cpu_sample": c["sample"]},
+        "cpu_baseline": {"value": c["value"], "unit": "DOF-iters/s", "cores": c["cores"],
+                         "kind": "port", "sample": c["sample"]},
+        "e2e": {"value": c["value"], "unit": "DOF-iters/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
+    if args.workload is None and not args.no_secondary and args.gpus == 1:
+        s = cpu_arm(pt, DEFAULT_SECONDARY, 1, 1, 0, min(args.cpu_kcap, 100))
+        line["secondary"] = {"value": s["value"], "unit": "DOF-iters/s", "scaling": "weak",
+                             "assembled_nnz_per_s": s["assembled_nnz_per_s"],
+                             "cpu_baseline": {"value": s["value"], "unit": "DOF-iters/s",
+                                              "cores": s["cores"], "kind": "port", "sample": s["sample"]},
+                             "config": {"workload": s["workload"]}}
     print(json.dumps(line), flush=True)
 
 
 def cpu_baseline(pt, args, wl_name):
-    """Oracle on 1 core on a bounded sample (rank 0, N = 1 only)."""
-    import oracle
-    oracle.build()
-    ptype, order, dims, base, scaling, ndofs = sizing(pt, wl_name, 1, args.cpu_sample_ndofs)
-    P = pt.host.Problem(ptype, order, *dims)
-    t0 = time.perf_counter()
-    A = oracle.assemble_matrix(P, nthreads=1, fast=True)
-    t1 = time.perf_counter()
-    b = oracle.assemble_vector(P, fast=True)
-    kcap = 60  # bounded: 60 CG iterations are enough for a stable per-iteration rate
-    t2 = time.perf_counter()
-    x, k, rel = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=kcap, rtol=1e-8,
-                          precond="jacobi", nthreads=1, fast=True)
-    t3 = time.perf_counter()
-    ndof = P.n_owned * P.bs
-    return {"value": k * ndof / (t3 - t2), "unit": "DOF-iters/s", "cores": 1, "kind": "port",
-            "assembled_nnz_per_s": P.nnz * P.bs * P.bs / (t1 - t0),
-            "sample": (f"CPU restatement (oracle, gcc -Ofast, 1 core; not DOLFINx/PETSc): {ptype} "
-                       f"P{order} at --ndofs {args.cpu_sample_ndofs} ({ndof} DOFs): matrix assembly "
-                       f"{t1 - t0:.2f} s, vector {t2 - t1:.2f} s, first {k} CG+Jacobi iterations "
-                       f"{t3 - t2:.2f} s")}
+    """The in-run baseline of the default line (rank 0, N = 1): one bounded step of cpu_arm."""
+    c = cpu_arm(pt, wl_name, 1, 1, 0, min(args.cpu_kcap, 100), args.ndofs)
+    return {k: c[k] for k in ("value", "unit", "cores", "kind", "sample", "assembled_nnz_per_s",
+                              "same_mesh_as_gpu_arm")}
 
 
 def measure(pt, env, wl_name, args, steps, warmup, with_cpu):

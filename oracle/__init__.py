@@ -157,3 +157,52 @@ def cg(bs, n_rows, rowptr, cols, vals, b, x0=None, kmax=50, rtol=1e-8, precond="
                           C.c_int({"none": 0, "jacobi": 1}[precond]), C.byref(rel),
                           C.c_int(nthreads))
     return x, k, rel.value
+
+
+class _Part(C.Structure):
+    _fields_ = [("bs", C.c_int32), ("n_owned", C.c_int32), ("n_ghost", C.c_int32),
+                ("n_nbr", C.c_int32), ("rowptr", C.c_void_p), ("cols", C.c_void_p),
+                ("vals", C.c_void_p), ("b", C.c_void_p), ("x", C.c_void_p),
+                ("nbr_ranks", C.c_void_p), ("send_displ", C.c_void_p),
+                ("local_indices", C.c_void_p), ("recv_displ", C.c_void_p),
+                ("remote_indices", C.c_void_p)]
+
+
+def cg_partitioned(problems, mats, rhs, kmax=50, rtol=1e-8, precond="none", fast=False):
+    """The solve on len(problems) partitions, one thread per partition (the analogue of
+    `mpirun -np P`): halo update of p with the Scatterer lists, dot products reduced in rank
+    order. problems: host.Problem per rank; mats / rhs: their owned-row matrices and vectors.
+    Returns ([x per rank, owned + ghost], iterations, rel_res)."""
+    keep, arr, xs = [], (_Part * len(problems))(), []
+    for q, (P, A, b) in enumerate(zip(problems, mats, rhs)):
+        x = np.zeros((P.n_owned + P.n_ghost) * P.bs)
+        fields = [_arr(P["rowptr"], np.int64), _arr(P["cols"], np.int32), _arr(A, np.float64),
+                  _arr(b, np.float64), x]
+        halo = [_arr(P[k] if len(P[k]) else np.zeros(1 if "displ" in k else 0), np.int32)
+                for k in ("nbr_ranks", "send_displ", "local_indices", "recv_displ", "remote_indices")]
+        keep += fields + halo
+        xs.append(x)
+        arr[q] = _Part(P.bs, P.n_owned, P.n_ghost, P.n_nbr, *[_ptr(f) for f in fields],
+                       *[_ptr(h) for h in halo])
+    k, rel = C.c_int(), C.c_double()
+    rc = _lib(fast).orc_cg_partitioned(C.c_int(len(problems)), arr, C.c_int(kmax), C.c_double(rtol),
+                                       C.c_int({"none": 0, "jacobi": 1}[precond]), C.byref(k),
+                                       C.byref(rel))
+    if rc != 0:
+        raise RuntimeError("oracle: inconsistent halo lists between partitions")
+    return xs, k.value, rel.value
+
+
+def assemble_partitions(problems, fast=False):
+    """ZZZ Assemble matrix / vector of every partition at once, one thread per partition (each runs
+    the sequential cell loop of its rank, like the ranks of an MPI job). Returns (mats, rhs,
+    seconds_matrix, seconds_vector)."""
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=len(problems)) as ex:
+        t0 = time.perf_counter()
+        mats = list(ex.map(lambda P: assemble_matrix(P, nthreads=1, fast=fast), problems))
+        t1 = time.perf_counter()
+        rhs = list(ex.map(lambda P: assemble_vector(P, fast=fast), problems))
+        t2 = time.perf_counter()
+    return mats, rhs, t1 - t0, t2 - t1

@@ -509,3 +509,144 @@ int orc_cg(int bs, int32_t n_rows, const int64_t* rowptr, const int32_t* cols, c
 }
 
 int orc_max_threads(void) { return omp_get_max_threads(); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* The solve on P partitions at once: the analogue of `mpirun -np P` for the timed CPU arm       */
+/* (BASELINE.md section 3 (ii)). One OpenMP thread plays one rank: it owns a block of rows       */
+/* [owned | ghost] exactly as a DOLFINx rank does, updates the ghosts of p before every operator */
+/* application with the Scatterer lists (pack -> neighbour copy -> unpack,                       */
+/* cgpoisson_problem.cpp:32-44,223-229) and reduces the dot products over ranks in rank order    */
+/* (MPI_Allreduce in la::inner_product). Same loop as orc_cg (cg.h:38-86 + optional Jacobi).     */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct
+{
+  int32_t bs, n_owned, n_ghost, n_nbr;
+  const int64_t* rowptr;
+  const int32_t* cols;
+  const double* vals;
+  const double* b; /* owned entries */
+  double* x;       /* [(n_owned + n_ghost) * bs] in: initial guess, out: solution */
+  const int32_t *nbr_ranks, *send_displ, *local_indices, *recv_displ, *remote_indices;
+} orc_part;
+
+static void part_spmv(const orc_part* P, const double* p, double* y)
+{
+  orc_spmv(P->bs, P->n_owned, P->rowptr, P->cols, P->vals, p, y, 1);
+}
+
+int orc_cg_partitioned(int nparts, const orc_part* parts, int kmax, double rtol, int precond,
+                       int* iterations, double* rel_res)
+{
+  double* red = (double*)calloc((size_t)4 * 2 * nparts, sizeof(double)); /* ring of 4 reductions x 2 values */
+  double** sendbuf = (double**)calloc(nparts, sizeof(double*));
+  int k_out = 0, bad = 0;
+  double rel_out = 0.0;
+#pragma omp parallel num_threads(nparts)
+  {
+    const int q = omp_get_thread_num();
+    const orc_part* P = &parts[q];
+    const int bs = P->bs;
+    const int64_t n = (int64_t)P->n_owned * bs, nl = (int64_t)(P->n_owned + P->n_ghost) * bs;
+    double* r = (double*)malloc(sizeof(double) * n);
+    double* y = (double*)malloc(sizeof(double) * n);
+    double* z = (double*)malloc(sizeof(double) * n);
+    double* p = (double*)calloc(nl, sizeof(double));
+    double* dinv = (double*)malloc(sizeof(double) * n);
+    sendbuf[q] = (double*)malloc(sizeof(double) * (size_t)(P->send_displ[P->n_nbr] * bs + 1));
+    for (int32_t row = 0; row < P->n_owned; ++row)
+    {
+      const int64_t s = find_col(P->cols, P->rowptr[row], P->rowptr[row + 1], row);
+      for (int a = 0; a < bs; ++a)
+        dinv[(int64_t)bs * row + a] = precond ? 1.0 / P->vals[bs * bs * s + bs * a + a] : 1.0;
+    }
+    int ring = 0;
+#define ORC_ALLREDUCE2(v0, v1, s0, s1)                                                            \
+  do                                                                                              \
+  {                                                                                               \
+    double* slot = red + (size_t)(ring & 3) * 2 * nparts;                                         \
+    slot[2 * q] = (v0), slot[2 * q + 1] = (v1);                                                   \
+    _Pragma("omp barrier") (s0) = 0.0, (s1) = 0.0;                                                \
+    for (int t = 0; t < nparts; ++t)                                                              \
+      (s0) += slot[2 * t], (s1) += slot[2 * t + 1];                                               \
+    ++ring;                                                                                       \
+  } while (0)
+#define ORC_HALO(v)                                                                               \
+  do                                                                                              \
+  {                                                                                               \
+    for (int32_t i = 0; i < P->send_displ[P->n_nbr]; ++i)                                         \
+      for (int a = 0; a < bs; ++a)                                                                \
+        sendbuf[q][(int64_t)i * bs + a] = (v)[(int64_t)P->local_indices[i] * bs + a];             \
+    _Pragma("omp barrier") for (int i = 0; i < P->n_nbr; ++i)                                     \
+    {                                                                                             \
+      const orc_part* O = &parts[P->nbr_ranks[i]];                                                \
+      int me = 0;                                                                                 \
+      while (me < O->n_nbr && O->nbr_ranks[me] != q)                                              \
+        ++me;                                                                                     \
+      if (me == O->n_nbr                                                                          \
+          || O->send_displ[me + 1] - O->send_displ[me] != P->recv_displ[i + 1] - P->recv_displ[i]) \
+      {                                                                                           \
+        bad = 1;                                                                                  \
+        continue;                                                                                 \
+      }                                                                                           \
+      const double* src = sendbuf[P->nbr_ranks[i]] + (int64_t)O->send_displ[me] * bs;             \
+      for (int32_t j = P->recv_displ[i]; j < P->recv_displ[i + 1]; ++j)                           \
+        for (int a = 0; a < bs; ++a)                                                              \
+          (v)[(int64_t)P->remote_indices[j] * bs + a] = src[(int64_t)(j - P->recv_displ[i]) * bs + a]; \
+    }                                                                                             \
+    _Pragma("omp barrier")                                                                        \
+  } while (0)
+
+    /* r0 = b - A x0 (cg.h:46-47) */
+    ORC_HALO(P->x);
+    part_spmv(P, P->x, y);
+    for (int64_t i = 0; i < n; ++i)
+    {
+      r[i] = -1.0 * y[i] + P->b[i];
+      z[i] = dinv[i] * r[i];
+      p[i] = z[i];
+    }
+    double rnorm0, rz, rnorm;
+    ORC_ALLREDUCE2(dot(r, r, n, 1), dot(r, z, n, 1), rnorm0, rz);
+    rnorm = rnorm0;
+    const double rtol2 = rtol * rtol;
+    int k = 0;
+    while (k < kmax)
+    {
+      ++k;
+      ORC_HALO(p);
+      part_spmv(P, p, y);                                        /* cg.h:62 */
+      double py, unused;
+      ORC_ALLREDUCE2(dot(p, y, n, 1), 0.0, py, unused);          /* cg.h:65 */
+      (void)unused;
+      const double alpha = rz / py;
+      for (int64_t i = 0; i < n; ++i)
+      {
+        P->x[i] = alpha * p[i] + P->x[i];                        /* cg.h:68 */
+        r[i] = -alpha * y[i] + r[i];                             /* cg.h:71 */
+        z[i] = dinv[i] * r[i];
+      }
+      double rnorm_new, rz_new;
+      ORC_ALLREDUCE2(dot(r, r, n, 1), dot(r, z, n, 1), rnorm_new, rz_new); /* cg.h:74 */
+      const double beta = rz_new / rz;                           /* cg.h:75 */
+      rz = rz_new, rnorm = rnorm_new;
+      if (rnorm / rnorm0 < rtol2)                                /* cg.h:78 */
+        break;
+      for (int64_t i = 0; i < n; ++i)
+        p[i] = beta * p[i] + z[i];                               /* cg.h:82 */
+    }
+    ORC_HALO(P->x); /* ghosts of the solution current on return (KrylovSolver::solve) */
+    if (q == 0)
+      k_out = k, rel_out = sqrt(rnorm / rnorm0);
+    free(r), free(y), free(z), free(p), free(dinv);
+#undef ORC_ALLREDUCE2
+#undef ORC_HALO
+  }
+  for (int q = 0; q < nparts; ++q)
+    free(sendbuf[q]);
+  free(sendbuf), free(red);
+  if (iterations)
+    *iterations = k_out;
+  if (rel_res)
+    *rel_res = rel_out;
+  return bad;
+}

@@ -161,9 +161,6 @@ int ptb_create(int device, ptb_ctx** out)
     c->partials.alloc(static_cast<std::size_t>(3) * c->num_sms * 8);
     c->tickets.alloc(4);
     c->tickets.zero(c->stream);
-    c->loop_bar.alloc(2);
-    c->loop_bar.zero(c->stream);
-    c->loop_sums.alloc(2);
     PTB_CUDA(cudaMallocHost(&c->h_cg, 2 * sizeof(CgState)));
     PTB_CUDA(cudaMallocHost(&c->h_scalar, 4 * sizeof(double)));
     PTB_CUDA(cudaStreamSynchronize(c->stream));
@@ -888,9 +885,10 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     bool looped = false;
     if (persistent && !mf && kmax > 0 && (c->nranks == 1 || fused) && !c->nccl_comm)
     {
-      const unsigned int ebase = c->peer.red_epoch + 1u;
+      const unsigned int ebase = c->peer.red_epoch + 1u, lbase = c->loop_epoch + 1u;
       need(ebase + 2u * static_cast<unsigned int>(kmax) > ebase, "ptb_cg_solve: reduction epochs would wrap");
-      looped = launch_cg_loop(c, dinv, 0, kmax, ebase, fused);
+      need(lbase + 3u * static_cast<unsigned int>(kmax) > lbase, "ptb_cg_solve: barrier epochs would wrap");
+      looped = launch_cg_loop(c, dinv, 0, kmax, ebase, lbase, fused);
       if (looped)
       {
         PTB_CUDA(cudaMemcpyAsync(c->h_cg, st, 2 * sizeof(CgState), cudaMemcpyDeviceToHost, c->stream));
@@ -899,6 +897,7 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
         // the loop consumed one halo epoch and two reduction epochs per iteration
         c->peer.halo_epoch += static_cast<unsigned long long>(fin.k);
         c->peer.red_epoch += 2u * static_cast<unsigned int>(fin.k);
+        c->loop_epoch += 3u * static_cast<unsigned int>(fin.k); // three grid barriers per iteration
         halo_forward(c, c->x.p);
         peer_neighbour_barrier(c);
         t.stop();

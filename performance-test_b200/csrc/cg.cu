@@ -821,23 +821,28 @@ struct LoopArgs
   std::int64_t n; // owned entries
   const double* dinv;
   double *r, *p, *x, *y;
-  CgState* st;        // [2], indexed by iteration parity
-  double* partials;   // [2][gridDim.x]
-  unsigned int* bar;  // [0] arrivals, [1] generation
-  double* sums;       // [2] local sums broadcast by the last CTA
-  int it0, n_it;      // iterations it0+1 .. it0+n_it
-  unsigned int ebase; // reduction epochs: ebase + 2 (j-1) for p.y, + 1 for (r.r, r.z)
+  CgState* st;               // [2], indexed by iteration parity
+  unsigned long long* slots; // [gridDim.x + 1][4] LL records: one arrival record per CTA + the release
+  int it0, n_it;             // iterations it0+1 .. it0+n_it
+  unsigned int ebase;        // peer reduction epochs: ebase + 2 (j-1) for p.y, + 1 for (r.r, r.z)
+  unsigned int lbase;        // grid barrier epochs: lbase + 3 (j-1) + {0, 1, 2}
 };
 
 
 // Grid barrier fused with a deterministic reduction of NV values per CTA (NV = 0: barrier only).
-// On return every thread holds the (peer-)global sums in out[].
+// No atomics: every CTA stores one LL arrival record (its partial sums + the barrier epoch in the
+// same 8-byte words); CTA 0 collects the records in index order, adds them with the fixed block
+// tree, publishes the local sums to the peers (LL window) and stores the release record; every
+// CTA waits for the release (single GPU) or for all ranks' window slots (which contain this rank's
+// own, written after the collection) and holds the (peer-)global sums in out[] on return.
+// 592 same-address atomics cost ~27 cycles each when they arrive together (B300_MICROARCH.md,
+// "L2-atom multi-CTA"): ~8 us per barrier, three barriers per iteration -- the records do not queue.
 template <int NV>
 __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], const LoopArgs& L,
-                                                 const PeerView& P, unsigned int epoch, double* red,
+                                                 const PeerView& P, unsigned int lepoch,
+                                                 unsigned int pepoch, double* red,
                                                  double (&out)[NV > 0 ? NV : 1])
 {
-  __shared__ bool is_last;
   __shared__ double bsum[2];
   // Thread 0 may only arrive for the CTA once every thread of the CTA has finished the phase:
   // block_sum synchronises the CTA on its way; the plain barrier has to do it itself. (Found by
@@ -846,84 +851,50 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
     block_sum<NV>(v, red);
   else
     __syncthreads();
-  unsigned int gen = 0;
+  const bool peers = NV > 0 && P.nranks > 1;
   if (threadIdx.x == 0)
   {
-    if constexpr (NV > 0)
-    {
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-        L.partials[i * gridDim.x + blockIdx.x] = v[i];
-    }
-    gen = ld_acquire_gpu_u32(&L.bar[1]); // cannot advance before this CTA has arrived
-    __threadfence();
-    is_last = atomicAdd(&L.bar[0], 1u) == gridDim.x - 1;
+    __threadfence(); // the CTA's writes of this phase are ordered before its arrival record
+    ll_write(L.slots + 4 * static_cast<std::size_t>(blockIdx.x), lepoch, NV > 0 ? v[0] : 0.0,
+             NV > 1 ? v[NV - 1] : 0.0);
   }
-  __syncthreads();
-  if (is_last)
+  if (blockIdx.x == 0)
   {
-    __threadfence();
-    if constexpr (NV > 0)
+    double acc[2] = {0.0, 0.0};
+    for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x)
     {
-      double acc[NV];
-#pragma unroll
-      for (int i = 0; i < NV; ++i)
-      {
-        acc[i] = 0.0;
-        for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x)
-          acc[i] += __ldcg(&L.partials[i * gridDim.x + j]);
-      }
-      __syncthreads(); // red is reused
-      block_sum<NV>(acc, red);
-      if (threadIdx.x == 0)
-      {
-        if (P.nranks > 1)
-          peer_publish(P, epoch, acc[0], NV > 1 ? acc[NV - 1] : 0.0);
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          L.sums[i] = acc[i];
-      }
+      double a, b;
+      ll_read(L.slots + 4 * static_cast<std::size_t>(j), lepoch, a, b);
+      acc[0] += a, acc[1] += b;
     }
+    __syncthreads(); // red is reused
+    block_sum<2>(acc, red);
     if (threadIdx.x == 0)
     {
-      L.bar[0] = 0u;
-      __threadfence();
-      st_release_gpu_u32(&L.bar[1], gen + 1u);
+      __threadfence(); // every arrival is ordered before the release
+      if (peers)
+        peer_publish(P, pepoch, acc[0], acc[1]);
+      ll_write(L.slots + 4 * static_cast<std::size_t>(gridDim.x), lepoch, acc[0], acc[1]);
     }
   }
-  else if (threadIdx.x == 0)
+  if (threadIdx.x == 0)
   {
-    while (ld_acquire_gpu_u32(&L.bar[1]) == gen)
-    {
-    }
-    __threadfence(); // belt and braces: the CTA's later cached loads must not hit pre-barrier L1 lines
-  }
-  if constexpr (NV > 0)
-  {
-    if (threadIdx.x == 0)
-    {
-      if (P.nranks > 1)
-      {
-        double s0, s1;
-        peer_collect(P, epoch, s0, s1);
-        bsum[0] = s0, bsum[1] = s1;
-      }
-      else
-      {
-#pragma unroll
-        for (int i = 0; i < NV; ++i)
-          bsum[i] = __ldcg(&L.sums[i]);
-      }
-    }
+    double s0, s1;
+    if (peers)
+      peer_collect(P, pepoch, s0, s1); // rank order; contains this rank's own slot
+    else
+      ll_read(L.slots + 4 * static_cast<std::size_t>(gridDim.x), lepoch, s0, s1);
+    __threadfence(); // acquire: later loads (and the L1) must not see pre-barrier data
+    bsum[0] = s0, bsum[1] = s1;
   }
   __syncthreads();
   if constexpr (NV > 0)
   {
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-      out[i] = bsum[i];
-    __syncthreads(); // bsum is reused by the next call
+    out[0] = bsum[0];
+    if constexpr (NV > 1)
+      out[NV - 1] = bsum[1];
   }
+  __syncthreads(); // bsum is reused by the next call
 }
 
 template <int BS, bool FUSED>
@@ -988,8 +959,9 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
         dotv += spmv_slice<BS, Ld::CA>(A, LP, L.p, L.y, FH.order[s], lane);
     }
     const unsigned int ea = L.ebase + 2u * static_cast<unsigned int>(j - 1), eb = ea + 1u;
+    const unsigned int la = L.lbase + 3u * static_cast<unsigned int>(j - 1);
     double v1[1] = {dotv}, py[1];
-    grid_reduce_sync<1>(v1, L, P, ea, red, py);
+    grid_reduce_sync<1>(v1, L, P, la, ea, red, py);
     const double alpha = rz_old / py[0]; // cg.h:65
 
     // ---- phase 2: r -= alpha y (cg.h:71), local r.r and r.z (cg.h:74) -----------------------
@@ -1019,7 +991,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       }
     }
     double rs[2];
-    grid_reduce_sync<2>(v2, L, P, eb, red, rs);
+    grid_reduce_sync<2>(v2, L, P, la + 1u, eb, red, rs);
     const double rr = rs[0], rz = rs[1];
     const double beta = rz / rz_old;             // cg.h:75
     const bool converged = rr / rnorm0 < rtol2;  // cg.h:78
@@ -1060,7 +1032,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       }
     }
     double none[1] = {0.0}, none_out[1];
-    grid_reduce_sync<0>(none, L, P, 0u, red, none_out);
+    grid_reduce_sync<0>(none, L, P, la + 2u, 0u, red, none_out);
   }
 }
 
@@ -1176,7 +1148,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
 }
 
 bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned int ebase,
-                    bool fused_halo)
+                    unsigned int lbase, bool fused_halo)
 {
   if (c->bs != 1 && c->bs != 3)
     return false;
@@ -1186,9 +1158,7 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   L.dinv = dinv;
   L.r = c->r.p, L.p = c->p.p, L.x = c->x.p, L.y = c->y.p;
   L.st = c->cg.p;
-  L.bar = c->loop_bar.p;
-  L.sums = c->loop_sums.p;
-  L.it0 = it0, L.n_it = n_it, L.ebase = ebase;
+  L.it0 = it0, L.n_it = n_it, L.ebase = ebase, L.lbase = lbase;
   PeerView P = peer_view(c);
   FusedHalo FH{};
   FH.order = c->slice_order.p;
@@ -1225,8 +1195,12 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
     FH.npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
   }
-  c->partials.alloc(std::max<std::size_t>(c->partials.n, static_cast<std::size_t>(2) * grid));
-  L.partials = c->partials.p;
+  if (c->loop_slots.n < static_cast<std::size_t>(grid + 1) * 4)
+  {
+    c->loop_slots.alloc(static_cast<std::size_t>(grid + 1) * 4);
+    c->loop_slots.zero(c->stream); // epoch 0 = never written; the host counter starts at 1
+  }
+  L.slots = c->loop_slots.p;
   void* args[] = {&L, &P, &FH};
   PTB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(SPMV_THREADS), args, 0, c->stream));
   c->launches += 1;

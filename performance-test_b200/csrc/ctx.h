@@ -175,8 +175,8 @@ struct ptb_ctx
   ptb::DevBuf<ptb::CgState> cg;          // [2]
   ptb::DevBuf<double> partials;          // [3 * max_grid]
   ptb::DevBuf<unsigned int> tickets;     // [4]
-  ptb::DevBuf<unsigned int> loop_bar;    // [2] grid barrier of the persistent CG loop
-  ptb::DevBuf<double> loop_sums;         // [2] its broadcast slots
+  ptb::DevBuf<unsigned long long> loop_slots; // [grid + 1][4] LL records of the persistent loop's barrier
+  unsigned int loop_epoch = 0;                // last barrier epoch used (monotone across solves)
   ptb::CgState* h_cg = nullptr;          // pinned [2]
   double* h_scalar = nullptr;            // pinned [4]
 

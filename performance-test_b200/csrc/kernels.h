@@ -162,7 +162,7 @@ void launch_cg_direction(ptb_ctx* c, const double* dinv, const CgState* cur, CgS
 /// state records must have been initialised (launch_cg_finish_init). Returns false when the path
 /// does not apply (the caller then queues the three kernels per iteration).
 bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned int ebase,
-                    bool fused_halo);
+                    unsigned int lbase, bool fused_halo);
 /// Reduction epochs of the peer-memory all-reduce (never 0; see peer.cuh).
 inline unsigned int next_red_epoch(ptb_ctx* c)
 {

@@ -7,6 +7,37 @@
 namespace ptb
 {
 
+/// LL record of two doubles: four 8-byte words, each = 32 payload bits | epoch << 32, so that every
+/// aligned 8-byte store carries its own flag (no fence between data and flag). One thread.
+__device__ __forceinline__ void ll_write(unsigned long long* dst, unsigned int epoch, double v0, double v1)
+{
+  const unsigned long long b0 = static_cast<unsigned long long>(__double_as_longlong(v0));
+  const unsigned long long b1 = static_cast<unsigned long long>(__double_as_longlong(v1));
+  const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
+  st_relaxed_sys(dst + 0, (b0 & 0xffffffffull) | tag);
+  st_relaxed_sys(dst + 1, (b0 >> 32) | tag);
+  st_relaxed_sys(dst + 2, (b1 & 0xffffffffull) | tag);
+  st_relaxed_sys(dst + 3, (b1 >> 32) | tag);
+}
+/// Spin until all four words of the record carry `epoch`, then decode.
+__device__ __forceinline__ void ll_read(const unsigned long long* src, unsigned int epoch, double& v0, double& v1)
+{
+  unsigned long long w[4];
+  bool ok;
+  do
+  {
+    ok = true;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+    {
+      w[i] = ld_relaxed_sys(src + i);
+      ok = ok && static_cast<unsigned int>(w[i] >> 32) == epoch;
+    }
+  } while (!ok);
+  v0 = __longlong_as_double(static_cast<long long>((w[0] & 0xffffffffull) | (w[1] << 32)));
+  v1 = __longlong_as_double(static_cast<long long>((w[2] & 0xffffffffull) | (w[3] << 32)));
+}
+
 /// Publish this rank's two partial sums for reduction `epoch` to every rank (one thread).
 __device__ __forceinline__ void peer_publish(const PeerView& P, unsigned int epoch, double v0,
                                              double v1)

@@ -104,8 +104,7 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
                       const int64_t* mat_off, const int32_t* cols, const double* vals,
                       const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                       const int32_t* order, const double* dinv, double* r, double* p, double* x,
-                      double* y, void* st, double* partials, unsigned int* bar, double* sums,
-                      int n_it)
+                      double* y, void* st, unsigned long long* slots, int n_it)
 {
   using namespace ptb;
   LoopArgs L{};
@@ -113,8 +112,8 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
   L.n = static_cast<std::int64_t>(n_rows) * bs;
   L.dinv = dinv, L.r = r, L.p = p, L.x = x, L.y = y;
   L.st = static_cast<CgState*>(st);
-  L.partials = partials, L.bar = bar, L.sums = sums;
-  L.it0 = 0, L.n_it = n_it, L.ebase = 1;
+  L.slots = slots;
+  L.it0 = 0, L.n_it = n_it, L.ebase = 1, L.lbase = 1;
   PeerView P{};
   P.rank = 0, P.nranks = 1;
   FusedHalo FH{};
@@ -153,8 +152,7 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
                            const int64_t* mat_off, const int32_t* cols, const double* vals,
                            const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                            const int32_t* order, const double* dinv, double* r, double* p,
-                           double* x, double* y, void* st, double* partials, unsigned int* bar,
-                           double* sums, int n_it)
+                           double* x, double* y, void* st, unsigned long long* slots, int n_it)
 {
   using namespace ptb;
   LoopArgs L{};
@@ -162,8 +160,8 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
   L.n = static_cast<std::int64_t>(n_rows) * bs;
   L.dinv = dinv, L.r = r, L.p = p, L.x = x, L.y = y;
   L.st = static_cast<CgState*>(st);
-  L.partials = partials, L.bar = bar, L.sums = sums;
-  L.it0 = 0, L.n_it = n_it, L.ebase = 1;
+  L.slots = slots;
+  L.it0 = 0, L.n_it = n_it, L.ebase = 1, L.lbase = 1;
   PeerView P{};
   P.rank = rank, P.nranks = nranks;
   for (int q = 0; q < nranks; ++q)

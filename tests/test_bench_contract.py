@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_json_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
-                        "--steps", "1", "--warmup", "0", "--cpu-sample-ndofs", "20000"],
+                        "--steps", "1", "--warmup", "0", "--ndofs", "20000", "--workload", "elasticity",
+                        "--cpu-kcap", "40"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -18,7 +19,8 @@ def test_reference_arm_prints_one_json_line():
     j = json.loads(lines[0])
     assert j["impl"] == "reference" and j["metric"] == "cg_dof_iters_per_s"
     assert j["unit"] == "DOF-iters/s" and j["higher_is_better"] is True and j["dtype"] == "f64"
-    assert j["value"] > 0 and j["cg_iterations"] > 10
+    assert j["value"] > 0 and j["cg_iterations"] == 40
+    assert "same mesh as the GPU arm" in j["cpu_baseline"]["sample"]
     assert j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"] == {"value": j["value"], "unit": "DOF-iters/s", "h2d_bytes_per_step": 0,
                         "d2h_bytes_per_step": 0}

@@ -255,10 +255,9 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     st = np.zeros(2, dtype=CGSTATE)
     rr, rz = float(r @ r), float(r @ (dinv * r))
     st[1] = (0.0, rr, rz, rz, rr, rtol * rtol, rr, 0.0, 0, 0)
-    partials, bar, sums = np.zeros(2 * grid), np.zeros(2, np.uint32), np.zeros(2)
+    slots = np.zeros(4 * (grid + 1), np.uint64)   # LL arrival records of the CTAs + the release record
     args = [P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(vals), _p(cdelta), _p(colsx),
-            _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(partials), _p(bar),
-            _p(sums), 500]
+            _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(slots), 500]
     threads = [threading.Thread(target=emucg[g].emu_cg_loop_block, args=[bs, g, grid] + args)
                for g in range(grid)]
     for t in threads:
@@ -270,7 +269,8 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     assert fin["conv"] == 1 and abs(int(fin["k"]) - k_ref) <= 1
     assert np.sqrt(fin["rnorm"] / fin["rnorm0"]) < rtol
     assert np.abs(x - x_ref).max() <= 1e-6 * np.abs(x_ref).max()
-    assert bar[0] == 0  # every barrier was released and reset
+    # every record carries the epoch of the last barrier: lbase + 3 * iterations - 1
+    assert np.all(slots >> np.uint64(32) == np.uint64(3 * int(fin["k"])))
 
 
 @pytest.mark.parametrize("ptype,dims", [("poisson", (4, 3, 9)), ("elasticity", (2, 3, 5))])
@@ -308,8 +308,8 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
         diag = np.stack([A.reshape(-1, bs, bs)[own][:, i, i] for i in range(bs)], axis=1).reshape(-1)
         d = dict(P=P, L=L, vals=vals, cdelta=cdelta, xoff=xoff, colsx=colsx, order=order, n_int=n_int,
                  dinv=1.0 / diag, x=np.zeros(nl), r=b.copy(), y=np.zeros(n), p=np.zeros(nl),
-                 st=np.zeros(2, dtype=CGSTATE), partials=np.zeros(2 * grid),
-                 bar=np.zeros(2, np.uint32), sums=np.zeros(2), ready=np.zeros(256, np.uint64),
+                 st=np.zeros(2, dtype=CGSTATE), slots=np.zeros(4 * (grid + 1), np.uint64),
+                 ready=np.zeros(256, np.uint64),
                  nbr=np.ascontiguousarray(P["nbr_ranks"], dtype=np.int32),
                  recv_displ=np.ascontiguousarray(P["recv_displ"], dtype=np.int32),
                  remote=np.ascontiguousarray(P["remote_indices"], dtype=np.int32))
@@ -335,8 +335,7 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
                     d["peer_p"], _p(d["remote"]), _p(d["src"]), d["n_int"], 1, _p(d["ready"]),
                     P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(d["vals"]),
                     _p(d["cdelta"]), _p(d["colsx"]), _p(d["xoff"]), _p(d["order"]), _p(d["dinv"]),
-                    _p(d["r"]), _p(d["p"]), _p(d["x"]), _p(d["y"]), _p(d["st"]), _p(d["partials"]),
-                    _p(d["bar"]), _p(d["sums"]), 500]
+                    _p(d["r"]), _p(d["p"]), _p(d["x"]), _p(d["y"]), _p(d["st"]), _p(d["slots"]), 500]
             threads.append(threading.Thread(target=emucg[q * grid + g].emu_cg_loop_block_peer, args=args))
     for t in threads:
         t.start()

@@ -200,3 +200,35 @@ def test_oracle_cg_against_golden_reference_vectors(pt, oracle, case):
     sample = np.asarray(case["x_sample"])
     assert np.abs(x[case["sample_idx"]] - sample).max() <= 1e-12 * case["x_absmax"]
     assert abs(np.linalg.norm(x) - case["x_norm"]) <= 1e-12 * case["x_norm"]
+
+
+# ---- the timed CPU arm (bench.py cpu_arm): partitions on threads --------------------------------
+@needs_ref
+@pytest.mark.parametrize("ptype,dims,nranks", [("poisson", (5, 4, 9), 3), ("elasticity", (4, 4, 7), 2)])
+def test_partitioned_port_equals_the_partitioned_reference_cg(pt, oracle, ptype, dims, nranks):
+    """oracle.cg_partitioned (what bench.py times as the CPU arm) with precond = none against cg.h
+    compiled unchanged and run on the same partitions: same iteration count, same bits in x."""
+    probs = [pt.host.Problem(ptype, 1, *dims, q, nranks) for q in range(nranks)]
+    mats, rhs, _, _ = oracle.assemble_partitions(probs)
+    xp, kp, _ = oracle.cg_partitioned(probs, mats, rhs, kmax=5000, rtol=1e-8, precond="none")
+    xr, kr = ref.cg([_part(P, A, b) for P, A, b in zip(probs, mats, rhs)], kmax=5000, rtol=1e-8)
+    assert kp == kr
+    for a, b in zip(xp, xr):
+        assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ptype,dims,nranks", [("poisson", (6, 5, 8), 4), ("elasticity", (4, 4, 7), 3)])
+def test_partitioned_port_with_jacobi_matches_the_serial_oracle(pt, oracle, ptype, dims, nranks):
+    S = pt.host.Problem(ptype, 1, *dims)
+    A, b = oracle.assemble_matrix(S), oracle.assemble_vector(S)
+    xs, ks, _ = oracle.cg(S.bs, S.n_owned, S["rowptr"], S["cols"], A, b, kmax=5000, rtol=1e-8, precond="jacobi")
+    probs = [pt.host.Problem(ptype, 1, *dims, q, nranks) for q in range(nranks)]
+    mats, rhs, _, _ = oracle.assemble_partitions(probs)
+    xp, kp, rel = oracle.cg_partitioned(probs, mats, rhs, kmax=5000, rtol=1e-8, precond="jacobi")
+    assert abs(kp - ks) <= 1 and rel < 1e-8
+    bs = S.bs
+    for P, x in zip(probs, xp):
+        own = xs[P.global_offset * bs:(P.global_offset + P.n_owned) * bs]
+        assert np.abs(x[: P.n_owned * bs] - own).max() <= 1e-7 * np.abs(xs).max()
+        assert np.array_equal(x.reshape(-1, bs)[P.n_owned:],
+                              np.concatenate([p_[: q.n_owned * bs].reshape(-1, bs) for q, p_ in zip(probs, xp)])[P["ghost_global"]])
