@@ -248,6 +248,8 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu):
     # configs[4] (100M DOFs/GPU) is generated on the device: the host stand-in would need ~10 GB per
     # rank; PTB_BENCH_DEVICE_SETUP=1 forces the same route for any workload
     device_setup = os.environ.get("PTB_BENCH_DEVICE_SETUP") == "1" or wl_name == "elasticity_weak"
+    if device_setup:
+        os.environ.setdefault("PTB_GPU_SETUP", "1")  # layouts and assembly maps on the device too
     t_setup0 = time.perf_counter()
     P = pt.host.Problem(ptype, order, *dims, rank, world, with_dofmap=not device_setup)
     t_host = time.perf_counter() - t_setup0
@@ -280,13 +282,17 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu):
         if comm_used == "nccl":
             pt.dist.init_nccl(ctx, abi, dist, rank, world)   # ptb_comm_init drops any peer state
     ndofs_global = P.n_global * P.bs
+    if world > 1 and comm_used == "peer":
+        # the persistent CG loop pays below ~2 M DOFs per GPU; every rank must
+        # take the same path, so the decision comes from the global size
+        ctx.set_cg_persistent(1 if ndofs_global / world <= 2_000_000 else 0)
     nnz_local = ctx.nnz if device_setup else P.nnz
     nnz_global = allsum(float(nnz_local * P.bs * P.bs))
 
     # pinned host buffers for the e2e leg (host-resident inputs of the hot path)
     nl = (P.n_owned + P.n_ghost) * P.bs
     if device_setup:
-        x_host, _ = ctx.mesh()
+        x_host, _ = ctx.mesh(topology=False)
         f_host, g_host = ctx.source()
     else:
         x_host, f_host = np.array(P["x"]), np.array(P["f"])

@@ -137,6 +137,13 @@ int ptb_assemble_vector(ptb_ctx* ctx);
  * ptb_set_initial_guess was called) and b is the assembled RHS (or ptb_set_rhs). */
 int ptb_cg_solve(ptb_ctx* ctx, int kmax, double rtol, int precond, int* iterations,
                  double* rel_residual);
+/* How ptb_cg_solve runs the loop of cg.h:57-84: 1 = one persistent cooperative kernel (grid barriers
+ * instead of three launches per iteration; pays when the per-GPU problem is small, i.e. under
+ * strong scaling), 0 = three kernels per iteration, -1 = automatic (default: a single GPU decides by
+ * its row count; across GPUs the loop is only taken when the caller asks for it, because EVERY rank
+ * must pass the same value -- decide from the global size, e.g. global DOFs / ranks <= 2 M).
+ * Results are identical either way (same kernels' arithmetic, same reduction order). */
+int ptb_set_cg_persistent(ptb_ctx* ctx, int mode);
 /* Operator used by ptb_cg_solve / ptb_apply_operator: the assembled matrix (default) or, for
  * the scalar Poisson spaces (P1-P3), the matrix-free action of the reference's cgpoisson problem
  * (src/cgpoisson_problem.cpp:193-230, form M of src/Poisson.py:33): y = sum_cells Ae(p_e) with the

@@ -69,6 +69,7 @@ def lib():
         L.ptb_assemble_vector.argtypes = [vp]
         L.ptb_cg_solve.argtypes = [vp, C.c_int, dbl, C.c_int, C.POINTER(C.c_int), C.POINTER(dbl)]
         L.ptb_set_operator_mode.argtypes = [vp, C.c_int]
+        L.ptb_set_cg_persistent.argtypes = [vp, C.c_int]
         L.ptb_apply_operator.argtypes = [vp, vp, vp]
         L.ptb_set_rhs.argtypes = [vp, vp]
         L.ptb_set_initial_guess.argtypes = [vp, vp]
@@ -351,11 +352,12 @@ class Context:
                 _ptr(_a(P["send_displ"], np.int32)), _ptr(_a(P["local_indices"], np.int32)),
                 _ptr(_a(P["recv_displ"], np.int32)), _ptr(_a(P["remote_indices"], np.int32))))
 
-    def mesh(self):
-        """(x, x_dofmap) as the device holds them."""
+    def mesh(self, topology=True):
+        """(x, x_dofmap) as the device holds them; topology=False skips the cell -> vertex map
+        (returns None for it)."""
         x = np.empty(self.n_vertices * 3, dtype=np.float64)
-        xd = np.empty(self.n_cells * 4, dtype=np.int32)
-        self._check(lib().ptb_get_mesh(self._h, _ptr(x), _ptr(xd)))
+        xd = np.empty(self.n_cells * 4, dtype=np.int32) if topology else None
+        self._check(lib().ptb_get_mesh(self._h, _ptr(x), None if xd is None else _ptr(xd)))
         return x, xd
 
     def dofmap(self):
@@ -428,6 +430,11 @@ class Context:
     def set_operator_mode(self, mode):
         """'assembled' (default) or 'matrix_free' (Poisson P1: the cgpoisson action)."""
         self._check(lib().ptb_set_operator_mode(self._h, {"assembled": 0, "matrix_free": 1}[mode]))
+
+    def set_cg_persistent(self, mode):
+        """-1 auto, 0 three kernels per iteration, 1 persistent loop; across GPUs every rank must
+        pass the same value (decide from the global size)."""
+        self._check(lib().ptb_set_cg_persistent(self._h, int(mode)))
 
     def apply_operator(self, p):
         p = _a(p, np.float64)

@@ -334,11 +334,16 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
   const int pc = (cgp || opt.pc_type == "none") ? PTB_PC_NONE : PTB_PC_JACOBI;
   const std::int64_t nglob = ndofs_global;
   const int rank = boot.rank();
-  SolverFunction solver_function = [gpu, kmax, rtol, pc, cgp, nglob, rank,
+  const int world = boot.world();
+  SolverFunction solver_function = [gpu, kmax, rtol, pc, cgp, nglob, rank, world,
                                     &solve_seconds](Vector& u, const Vector& b) {
     ptb_ctx* c = gpu->c;
     int its = 0;
     double rel = 0.0;
+    // across GPUs every rank must run the same form of the loop: decide from the global size
+    // (include/ptb200.h ptb_set_cg_persistent); a single GPU decides by itself
+    if (world > 1)
+      ok(c, ptb_set_cg_persistent(c, nglob / world <= 2000000 ? 1 : 0));
     ok(c, ptb_set_rhs(c, b.array.data()));
     Timer tcg;
     ok(c, ptb_cg_solve(c, kmax, rtol, pc, &its, &rel));

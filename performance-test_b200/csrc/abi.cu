@@ -50,25 +50,24 @@ std::int64_t n_local_entries(const ptb_ctx* c)
   return (static_cast<std::int64_t>(c->n_owned) + c->n_ghost) * c->bs;
 }
 
-// L2 plan of the operator kernels: B200 has 126 MB of L2. The six solver
-// vectors (x, p, r, y, b, D^-1) are re-read every CG iteration, the matrix is a pure stream. When
-// the vectors fit (strong scaling: 10 M DOFs over 8 GPUs = 60 MB per GPU) the matrix stream is
-// loaded evict_first so that it cannot push them out, and a prefix of the matrix as large as the
-// rest of the budget is loaded evict_last, i.e. stays resident from one iteration to the next.
-// PTB_L2_POLICY=0 switches the hints off, PTB_L2_BUDGET_MB sets the budget (default 96 of 126 MB),
-// PTB_L2_PIN_MB overrides the size of the pinned prefix.
+// L2 plan of the operator kernels: B200 has 126 MB of L2. The solver vectors
+// (x, p, r, y, D^-1) are re-read every CG iteration, the matrix is a pure stream: its loads carry
+// the evict_first priority and bypass L1, so the stream cannot push the vectors (strong scaling:
+// 10 M DOFs over 8 GPUs = 50 MB per GPU) or the gathered part of p out of L2.
+// Measured (profiles/r02/ab_call4/summary.txt, elasticity, 1.25 M DOFs on one GPU = the 8-GPU share
+// of config 3): 134.6 -> 122.6 us per CG iteration; 2.5 M DOFs 221.8 -> 214.8; 10 M 789.6 -> 776.2;
+// Poisson 20 M unchanged within noise. PTB_L2_POLICY=0 switches the hints off.
+// PTB_L2_PIN_MB=m additionally loads the first m MB of the matrix evict_last (resident from one
+// iteration to the next): the kernel alone gains (99.6 -> 85.2 us with 36 MB) but inside the loop
+// the pinned lines displace the vectors (129.2 us per iteration with 36 MB against 122.6 with 0),
+// so the default is 0.
 void plan_l2(ptb_ctx* c)
 {
   c->l2_mode = env_flag("PTB_L2_POLICY", true) ? 1 : 0;
   c->l2_pin_entries = 0;
   if (!c->l2_mode)
     return;
-  const double budget = 1048576.0 * env_int("PTB_L2_BUDGET_MB", 96);
-  const double vec_bytes = 6.0 * 8.0 * static_cast<double>(n_local_entries(c));
-  double pin = vec_bytes < budget ? budget - vec_bytes : 0.0;
-  const int pin_mb = env_int("PTB_L2_PIN_MB", -1);
-  if (pin_mb >= 0)
-    pin = 1048576.0 * pin_mb;
+  const double pin = 1048576.0 * std::max(0, env_int("PTB_L2_PIN_MB", 0));
   const double bytes_per_entry = c->bs == 1 ? 12.0 : 76.0; // value(s) + column index
   c->l2_pin_entries = static_cast<std::int64_t>(pin / bytes_per_entry);
 }
@@ -876,12 +875,21 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
       return !(e && e[0] == '0');
     }();
     const bool fused = allow_fused && !mf && c->peer.enabled && !c->nbr_ranks.empty();
-    static const bool persistent = [] {
-      const char* e = std::getenv("PTB_CG_PERSISTENT");
-      return e && e[0] == '1';
-    }();
-    // Opt-in: the whole loop in one cooperative kernel (cg.cu cg_loop). Needs the assembled
+    // The whole loop in one cooperative kernel (cg.cu cg_loop) when the per-GPU problem is small
+    // enough for launch gaps and kernel ramps to matter: measured on one GPU (elasticity,
+    // profiles/r02/ab_call4/summary.txt) 134.6 -> 125.8 us per iteration at 1.25 M DOFs, a tie at
+    // 2.5 M, 4 % slower at 10 M. PTB_CG_PERSISTENT=1 / 0 forces it on / off. Needs the assembled
     // operator and, across GPUs, the peer-memory path with the fused halo (no NCCL inside a kernel).
+    static const int persistent_env = env_int("PTB_CG_PERSISTENT", -1);
+    const std::int64_t persistent_max = env_int("PTB_CG_PERSISTENT_MAX_DOFS", 2000000);
+    // Across GPUs every rank must take the same path (the two paths consume the peer epochs
+    // differently), and the ranks' row counts differ: there the caller decides from the global size
+    // (ptb_set_cg_persistent), here only a single GPU decides by itself.
+    const bool persistent = persistent_env >= 0    ? persistent_env == 1
+                            : c->cg_persistent >= 0 ? c->cg_persistent == 1
+                            : c->nranks == 1 && !c->peer.enabled
+                                ? static_cast<std::int64_t>(c->n_owned) * c->bs <= persistent_max
+                                : false;
     bool looped = false;
     if (persistent && !mf && kmax > 0 && (c->nranks == 1 || fused) && !c->nccl_comm)
     {
@@ -968,6 +976,14 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
       *iterations = kmax == 0 ? 0 : fin.k;
     if (rel_residual)
       *rel_residual = std::sqrt(fin.rnorm / fin.rnorm0);
+  });
+}
+
+int ptb_set_cg_persistent(ptb_ctx* c, int mode)
+{
+  return guarded(c, [&] {
+    need(mode >= -1 && mode <= 1, "ptb_set_cg_persistent: mode must be -1 (auto), 0 or 1");
+    c->cg_persistent = mode;
   });
 }
 

@@ -10,6 +10,7 @@
 // Dot products use the deterministic last-block reduction of reduce.cuh (la::inner_product /
 // squared_norm sum owned entries only: cg.h:53,65,74).
 #include "comm.h"
+#include "envopt.h"
 #include "kernels.h"
 #include "peer.cuh"
 #include "reduce.cuh"
@@ -1070,6 +1071,9 @@ int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, s
     int per_sm = 0;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
+    const int forced = env_int("PTB_SPMV_CTAS", 0); // A/B: CTA count of the operator kernels
+    if (forced > 0 && slot <= 4)
+      c->grid_cache[slot] = forced;
   }
   return static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
 }
@@ -1178,6 +1182,9 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     int per_sm = 0;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
     c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
+    const int forced = env_int("PTB_LOOP_CTAS", 0); // A/B: must stay co-resident (cooperative launch)
+    if (forced > 0)
+      c->grid_cache[slot] = std::min(forced, c->grid_cache[slot]);
   }
   const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const int grid = static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
