@@ -25,6 +25,7 @@ def declared_symbols():
     """Every function include/ptb200.h declares (used by the CPU-side export test)."""
     from . import INCLUDE_DIR
     src = open(os.path.join(INCLUDE_DIR, "ptb200.h")).read()
+    src += open(os.path.join(INCLUDE_DIR, "ptb200_debug.h")).read()   # test hooks, same library
     return sorted(set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", src)))
 
 

@@ -1,4 +1,5 @@
-// Host-only inspection entry points of libptb200.so (include/ptb200.h "integer side, host only"):
+// Host-only inspection entry points of libptb200.so (include/ptb200_debug.h: test hooks, not part of
+// the drop-in boundary; ptb_build_cell_slot_map of include/ptb200.h "integer side, host only"):
 // the integer structures the kernels read, rebuilt from their inputs without a GPU, for the CPU tests.
 #include "abi_util.h"
 #include "layout.h"

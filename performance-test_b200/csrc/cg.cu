@@ -191,61 +191,8 @@ struct FusedHalo
 };
 
 
-// The pull of one CTA's share of the receive list (generic Scatterer index lists).
-__device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHalo& FH)
-{
-  const PeerHalo& H = FH.H;
-  if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
-  {
-    __threadfence_system(); // p was completed by the previous kernel: publish "ready"
-    st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], FH.epoch);
-  }
-  if (threadIdx.x < H.n_nbr)
-  {
-    const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
-    while (ld_acquire_sys(flag) < FH.epoch)
-    {
-    }
-  }
-  __syncthreads();
-  constexpr int PULL_ILP = 4; // independent remote loads in flight per thread (NVLink ~2 us)
-  const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
-  const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
-  for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i0 < n;
-       i0 += step * PULL_ILP)
-  {
-    double val[PULL_ILP];
-    std::int64_t dst[PULL_ILP];
-#pragma unroll
-    for (int u = 0; u < PULL_ILP; ++u)
-    {
-      const std::int64_t i = i0 + u * step;
-      dst[u] = -1;
-      if (i < n)
-      {
-        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
-        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
-        int nb = 0;
-        while (j >= H.recv_displ[nb + 1])
-          ++nb;
-        dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
-        val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < PULL_ILP; ++u)
-      if (dst[u] >= 0)
-        FH.pw[dst[u]] = val[u];
-  }
-  __syncthreads();
-  if (threadIdx.x == 0)
-  {
-    __threadfence();
-    st_release_gpu(&FH.ready[blockIdx.x], FH.epoch);
-  }
-}
-
-// Same pull with the epoch passed explicitly (the persistent loop advances it per iteration).
+// The pull of one CTA's share of the receive list (generic Scatterer index lists) for halo epoch
+// `epoch` (the persistent loop advances the epoch per iteration).
 __device__ __forceinline__ void halo_pull_share_at(const PeerView& P, const FusedHalo& FH,
                                                    unsigned long long epoch)
 {
@@ -298,6 +245,11 @@ __device__ __forceinline__ void halo_pull_share_at(const PeerView& P, const Fuse
     __threadfence();
     st_release_gpu(&FH.ready[blockIdx.x], epoch);
   }
+}
+
+__device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHalo& FH)
+{
+  halo_pull_share_at(P, FH, FH.epoch);
 }
 
 template <int BS, bool FUSED>

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../include/ptb200.h"
+#include "../../include/ptb200_debug.h"
 #include "../common/intmaps.h"
 
 namespace ptb
