@@ -502,6 +502,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       std::vector<std::uint16_t>().swap(c->h_so);
     }
     plan_l2(c);
+    c->balance[0].grid = c->balance[1].grid = -1; // plans belong to the old pattern
     c->have_pattern = true;
     c->matrix_assembled = false;
     c->have_compact = false;
@@ -570,6 +571,7 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
     PTB_CUDA(cudaStreamSynchronize(c->stream));
     c->maps_on_device = true;
     plan_l2(c);
+    c->balance[0].grid = c->balance[1].grid = -1; // plans belong to the old pattern
     c->have_pattern = true;
     c->matrix_assembled = false;
     c->have_compact = false;

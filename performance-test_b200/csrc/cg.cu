@@ -14,6 +14,7 @@
 #include "kernels.h"
 #include "peer.cuh"
 #include "reduce.cuh"
+#include <algorithm>
 #include <climits>
 #include <cmath>
 #include <cstdlib>
@@ -59,7 +60,18 @@ __device__ __forceinline__ L2Plan l2_plan(const SpmvArgs& A)
   return A.l2_mode ? L2Plan{l2_policy(1), l2_policy(2)} : L2Plan{l2_policy(0), l2_policy(0)};
 }
 
-template <int BS, Ld L>
+template <bool POL, typename T>
+__device__ __forceinline__ T ldm(const T* q, unsigned long long pol)
+{
+  if constexpr (POL)
+    return ld_stream(q, pol);
+  else
+    return __ldg(q);
+}
+
+// POL = false: plain read-only loads of the matrix (the scalar kernels of large problems, where the
+// hints measured no gain: Poisson 20 M DOFs 0.519 vs 0.525 ms).
+template <int BS, Ld L, bool POL = true>
 __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP,
                                              const double* __restrict__ p, double* __restrict__ y,
                                              std::int32_t slice, int lane)
@@ -81,7 +93,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
     for (int k0 = 0; k0 < w; k0 += 32)
     {
       const int kn = min(32, w - k0);
-      const std::int32_t dl = lane < kn ? ld_stream(dp + k0 + lane, pol) : 0;
+      const std::int32_t dl = lane < kn ? ldm<POL>(dp + k0 + lane, pol) : 0;
       const unsigned int em = __ballot_sync(0xffffffffu, lane < kn && dl == INT32_MIN);
       const double* __restrict__ v = vp + static_cast<std::int64_t>(k0) * 32;
       if (em == 0u)
@@ -94,7 +106,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
 #pragma unroll
           for (int u = 0; u < U; ++u)
           {
-            vv[u] = ld_stream(v + (kk + u) * 32, pol);
+            vv[u] = ldm<POL>(v + (kk + u) * 32, pol);
             pp[u] = ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk + u)));
           }
 #pragma unroll
@@ -102,7 +114,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
             sum += vv[u] * pp[u];
         }
         for (; kk < kn; ++kk)
-          sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk)));
+          sum += ldm<POL>(v + kk * 32, pol) * ldp<L>(p + (row + __shfl_sync(0xffffffffu, dl, kk)));
       }
       else
       {
@@ -118,8 +130,8 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
           {
             const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk + u);
             const int rank = __popc(em & ((1u << (kk + u)) - 1u));
-            c[u] = ((em >> (kk + u)) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
-            vv[u] = ld_stream(v + (kk + u) * 32, pol);
+            c[u] = ((em >> (kk + u)) & 1u) ? ldm<POL>(xp + rank * 32, pol) : row + d;
+            vv[u] = ldm<POL>(v + (kk + u) * 32, pol);
           }
 #pragma unroll
           for (int u = 0; u < 4; ++u)
@@ -129,8 +141,8 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
         {
           const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
           const int rank = __popc(em & ((1u << kk) - 1u));
-          const std::int32_t c = ((em >> kk) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
-          sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + c);
+          const std::int32_t c = ((em >> kk) & 1u) ? ldm<POL>(xp + rank * 32, pol) : row + d;
+          sum += ldm<POL>(v + kk * 32, pol) * ldp<L>(p + c);
         }
         xp += __popc(em) * 32;
       }
@@ -149,12 +161,12 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int k = 0; k < w; ++k)
     {
-      const std::int64_t c = ld_stream(cp + k * 32, pol);
+      const std::int64_t c = ldm<POL>(cp + k * 32, pol);
       const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
       double a[9];
 #pragma unroll
       for (int e = 0; e < 9; ++e)
-        a[e] = ld_stream(v + e * 32, pol);
+        a[e] = ldm<POL>(v + e * 32, pol);
       const double p0 = ldp<L>(p + 3 * c), p1 = ldp<L>(p + 3 * c + 1), p2 = ldp<L>(p + 3 * c + 2);
       s0 += a[0] * p0 + a[1] * p1 + a[2] * p2;
       s1 += a[3] * p0 + a[4] * p1 + a[5] * p2;
@@ -168,6 +180,185 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
     }
     return 0.0;
   }
+}
+
+// ------------------------------------------------------------------------------------------
+// Balanced operator application for SMALL per-GPU problems (strong scaling). With whole slices as
+// work items a warp gets 2.2 slices on average at 1.25 M DOFs per GPU: 20 % of the warps carry a
+// third slice and the kernel spends its last third with a fifth of its warps
+// (profiles/r02/ncu_spmv_elasticity_1250k.csv: 51 % warps active against 62.5 % launched, DRAM at
+// 57 % of peak where the 10 M-DOF launch reaches 78 %). Here the work unit is one k-step of a slice
+// (32 rows x one stored entry): every CTA owns a contiguous run of slices chosen on the host so
+// that all CTAs hold the same number of units (+- one slice), and the CTA's warps cut that run
+// into equal unit ranges, splitting slices where the cuts fall. A warp that starts inside a slice
+// leaves its partial row sums in shared memory; the warp that holds the slice's first entries
+// adds the partials in warp order after a CTA barrier, stores y and takes the p.y contribution.
+// Same arithmetic per stored entry, fixed order, no atomics; a split row is summed in (at most
+// eight) pieces instead of one, so y may differ from the slice-per-warp kernel in the last bit.
+// ------------------------------------------------------------------------------------------
+constexpr int BAL_MAX_SLICES = 64; // slices per CTA the shared-memory prefix can hold
+
+// Partial row sums of one slice over its entries [kb, ke).
+template <int BS, Ld L>
+__device__ __forceinline__ void spmv_slice_part(const SpmvArgs& A, const L2Plan& LP,
+                                                const double* __restrict__ p, std::int32_t slice,
+                                                int kb, int ke, int lane, double (&s)[BS])
+{
+  const std::int64_t mo = A.mat_off[slice];
+  const unsigned long long pol = mo < A.pin_entries ? LP.pinned : LP.stream;
+  const std::int32_t row = slice * 32 + lane;
+  if constexpr (BS == 1)
+  {
+    // rows of at most 32 stored entries (P1): one batch of column deltas
+    const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+    const double* __restrict__ v = A.vals + mo + lane;
+    const std::int32_t dl = lane < w ? ld_stream(A.cdelta + (mo >> 5) + lane, pol) : 0;
+    const unsigned int em = __ballot_sync(0xffffffffu, lane < w && dl == INT32_MIN);
+    const std::int32_t* __restrict__ xp = A.colsx + A.xoff[slice] + lane;
+    double sum = 0.0;
+    int kk = kb;
+    for (; kk + 4 <= ke; kk += 4)
+    {
+      std::int32_t c[4];
+      double vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+      {
+        const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk + u);
+        const int rank = __popc(em & ((1u << (kk + u)) - 1u));
+        c[u] = ((em >> (kk + u)) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
+        vv[u] = ld_stream(v + (kk + u) * 32, pol);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        sum += vv[u] * ldp<L>(p + c[u]);
+    }
+    for (; kk < ke; ++kk)
+    {
+      const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
+      const int rank = __popc(em & ((1u << kk) - 1u));
+      const std::int32_t c = ((em >> kk) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
+      sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + c);
+    }
+    s[0] = sum;
+  }
+  else
+  {
+    const std::int32_t* __restrict__ cp = A.cols + mo + lane;
+    const double* __restrict__ vp = A.vals + mo * 9 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int k = kb; k < ke; ++k)
+    {
+      const std::int64_t c = ld_stream(cp + k * 32, pol);
+      const double* __restrict__ v = vp + static_cast<std::int64_t>(k) * 9 * 32;
+      double a[9];
+#pragma unroll
+      for (int e = 0; e < 9; ++e)
+        a[e] = ld_stream(v + e * 32, pol);
+      const double p0 = ldp<L>(p + 3 * c), p1 = ldp<L>(p + 3 * c + 1), p2 = ldp<L>(p + 3 * c + 2);
+      s0 += a[0] * p0 + a[1] * p1 + a[2] * p2;
+      s1 += a[3] * p0 + a[4] * p1 + a[5] * p2;
+      s2 += a[6] * p0 + a[7] * p1 + a[8] * p2;
+    }
+    s[0] = s0, s[1] = s1, s[2] = s2;
+  }
+}
+
+// The slices at positions [i0, i1) of `order`, shared evenly by the warps of this CTA.
+// Every thread of the CTA must call this (it contains CTA barriers). Returns the thread's p.y share.
+template <int BS, Ld L>
+__device__ __forceinline__ double spmv_cta_balanced(const SpmvArgs& A, const L2Plan& LP,
+                                                    const double* __restrict__ p,
+                                                    double* __restrict__ y,
+                                                    const std::int32_t* __restrict__ order,
+                                                    std::int32_t i0, std::int32_t i1)
+{
+  constexpr int W = SPMV_THREADS / 32;
+  __shared__ std::int32_t su[BAL_MAX_SLICES + 1]; // unit prefix of the CTA's slices, from 0
+  __shared__ double head[W][32 * BS];             // partial sums of the slice a warp starts inside
+  __shared__ std::int32_t head_pos[W];            // its position in the CTA's run, -1 = none
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = i1 - i0;
+  __syncthreads(); // the previous use of the shared arrays (persistent loop) is over
+  for (int t = threadIdx.x; t <= n; t += blockDim.x)
+    su[t] = A.ounit[i0 + t] - A.ounit[i0];
+  if (lane == 0)
+    head_pos[warp] = -1;
+  __syncthreads();
+  const std::int32_t total = su[n];
+  const std::int32_t u0 = static_cast<std::int32_t>(static_cast<std::int64_t>(total) * warp / W);
+  const std::int32_t u1 = static_cast<std::int32_t>(static_cast<std::int64_t>(total) * (warp + 1) / W);
+  // position j with su[j] <= u0 < su[j + 1] (n <= 64: two probes per lane)
+  int j = 0;
+  {
+    const bool a = lane < n && su[lane + 1] <= u0, b = lane + 32 < n && su[lane + 33] <= u0;
+    j = __popc(__ballot_sync(0xffffffffu, a)) + __popc(__ballot_sync(0xffffffffu, b));
+  }
+  double dotv = 0.0;
+  double pend[BS];
+  int pend_j = -1;
+  std::int32_t u = u0;
+  while (u < u1)
+  {
+    const int kb = u - su[j];
+    const int wj = su[j + 1] - su[j];
+    const int ke = min(su[j + 1], u1) - su[j];
+    const std::int32_t slice = order[i0 + j];
+    double s[BS];
+    spmv_slice_part<BS, L>(A, LP, p, slice, kb, ke, lane, s);
+    if (kb == 0 && ke == wj)
+    {
+      const std::int32_t row = slice * 32 + lane;
+      if (row < A.n_rows)
+      {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+        {
+          y[static_cast<std::int64_t>(row) * BS + a] = s[a];
+          dotv += s[a] * ldp<L>(p + static_cast<std::int64_t>(row) * BS + a);
+        }
+      }
+    }
+    else if (kb == 0)
+    {
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        pend[a] = s[a];
+      pend_j = j; // the rest of this slice belongs to the following warps
+    }
+    else
+    {
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+        head[warp][lane * BS + a] = s[a];
+      if (lane == 0)
+        head_pos[warp] = j;
+    }
+    u = su[j] + ke;
+    ++j;
+  }
+  __syncthreads();
+  if (pend_j >= 0)
+  {
+    for (int w2 = warp + 1; w2 < W; ++w2)
+      if (head_pos[w2] == pend_j)
+      {
+#pragma unroll
+        for (int a = 0; a < BS; ++a)
+          pend[a] += head[w2][lane * BS + a];
+      }
+    const std::int32_t row = order[i0 + pend_j] * 32 + lane;
+    if (row < A.n_rows)
+    {
+#pragma unroll
+      for (int a = 0; a < BS; ++a)
+      {
+        y[static_cast<std::int64_t>(row) * BS + a] = pend[a];
+        dotv += pend[a] * ldp<L>(p + static_cast<std::int64_t>(row) * BS + a);
+      }
+    }
+  }
+  return dotv;
 }
 
 // Halo exchange fused into the operator (peer mode). The CTAs split into two roles:
@@ -252,8 +443,8 @@ __device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHa
   halo_pull_share_at(P, FH, FH.epoch);
 }
 
-template <int BS, bool FUSED>
-__global__ void __launch_bounds__(SPMV_THREADS, 5)
+template <int BS, bool FUSED, bool BAL = false>
+__global__ void __launch_bounds__(SPMV_THREADS, BAL ? 4 : 5)
 spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,
           double* partials, unsigned int* ticket, PeerView P, unsigned int epoch, FusedHalo FH)
 {
@@ -264,6 +455,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   constexpr int warps_per_cta = SPMV_THREADS / 32;
   const L2Plan LP = l2_plan(A);
   double dotv = 0.0;
+  constexpr bool balanced = BAL; // the host passes A.bal_begin / A.ounit with this instantiation
   if constexpr (FUSED)
   {
     if (blockIdx.x < FH.npull)
@@ -277,23 +469,35 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
           f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
         while (!__all_sync(0xffffffffu, f >= FH.epoch));
       }
-      for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
-           it += FH.npull * warps_per_cta)
-        dotv += spmv_slice<BS, Ld::CG>(A, LP, p, y, FH.order[it], lane);
+      if constexpr (balanced)
+        dotv = spmv_cta_balanced<BS, Ld::CG>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
+                                             A.bal_begin[blockIdx.x + 1]);
+      else
+        for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
+             it += FH.npull * warps_per_cta)
+          dotv += spmv_slice<BS, Ld::CG, BS == 3>(A, LP, p, y, FH.order[it], lane);
+    }
+    else if constexpr (balanced)
+    {
+      const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
+      dotv = spmv_cta_balanced<BS, Ld::NC>(A, LP, p, y, FH.order, A.bal_begin[b], A.bal_begin[b + 1]);
     }
     else
     {
       const std::int32_t stride = (gridDim.x - FH.npull) * warps_per_cta;
       for (std::int32_t it = (blockIdx.x - FH.npull) * warps_per_cta + warp; it < FH.n_interior;
            it += stride)
-        dotv += spmv_slice<BS, Ld::NC>(A, LP, p, y, FH.order[it], lane);
+        dotv += spmv_slice<BS, Ld::NC, BS == 3>(A, LP, p, y, FH.order[it], lane);
     }
   }
+  else if constexpr (balanced)
+    dotv = spmv_cta_balanced<BS, Ld::NC>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
+                                         A.bal_begin[blockIdx.x + 1]);
   else
   {
     const std::int32_t stride = gridDim.x * warps_per_cta;
     for (std::int32_t it = blockIdx.x * warps_per_cta + warp; it < A.n_slices; it += stride)
-      dotv += spmv_slice<BS, Ld::NC>(A, LP, p, y, FH.order[it], lane);
+      dotv += spmv_slice<BS, Ld::NC, BS == 3>(A, LP, p, y, FH.order[it], lane);
   }
   if (st != nullptr)
   {
@@ -850,7 +1054,7 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
   __syncthreads(); // bsum is reused by the next call
 }
 
-template <int BS, bool FUSED>
+template <int BS, bool FUSED, bool BAL = false>
 __global__ void __launch_bounds__(SPMV_THREADS, 4)
 cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
 {
@@ -880,6 +1084,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
 
     // ---- phase 1: y = A p, local p.y --------------------------------------------------------
     double dotv = 0.0;
+    constexpr bool balanced = BAL;
     if constexpr (FUSED)
     {
       const unsigned long long hep = halo0 + static_cast<unsigned long long>(j);
@@ -893,9 +1098,18 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
             f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
           while (!__all_sync(0xffffffffu, f >= hep));
         }
-        for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
-             s += FH.npull * warps_per_cta)
-          dotv += spmv_slice<BS, Ld::CG>(A, LP, L.p, L.y, FH.order[s], lane);
+        if constexpr (balanced)
+          dotv = spmv_cta_balanced<BS, Ld::CG>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                               A.bal_begin[blockIdx.x + 1]);
+        else
+          for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
+               s += FH.npull * warps_per_cta)
+            dotv += spmv_slice<BS, Ld::CG>(A, LP, L.p, L.y, FH.order[s], lane);
+      }
+      else if constexpr (balanced)
+      {
+        const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
+        dotv = spmv_cta_balanced<BS, Ld::CA>(A, LP, L.p, L.y, FH.order, A.bal_begin[b], A.bal_begin[b + 1]);
       }
       else
       {
@@ -905,6 +1119,9 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
           dotv += spmv_slice<BS, Ld::CA>(A, LP, L.p, L.y, FH.order[s], lane);
       }
     }
+    else if constexpr (balanced)
+      dotv = spmv_cta_balanced<BS, Ld::CA>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                           A.bal_begin[blockIdx.x + 1]);
     else
     {
       const std::int32_t stride = gridDim.x * warps_per_cta;
@@ -1024,16 +1241,84 @@ int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, s
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
     const int forced = env_int("PTB_SPMV_CTAS", 0); // A/B: CTA count of the operator kernels
-    if (forced > 0 && slot <= 4)
+    if (forced > 0 && (slot <= 4 || (slot >= 16 && slot <= 19)))
       c->grid_cache[slot] = forced;
   }
   return static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
 }
 
+// Host side of the balanced split (spmv_cta_balanced): unit prefix over the slice order and the
+// CTAs' runs of positions, equal in units up to one slice. which = 0 spmv_sell, 1 cg_loop; npull < 0:
+// no roles. Sets A.ounit / A.bal_begin when the split applies: a problem small enough for slice
+// quantisation to matter (fewer than 8 slices per warp), big enough to give every warp work, block
+// rows or P1 rows (one batch of column deltas), at most BAL_MAX_SLICES slices per CTA.
+void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
+{
+  static const bool enabled = env_flag("PTB_SPMV_BALANCE", true);
+  ptb_ctx::Balance& B = c->balance[which];
+  const bool compact = c->have_compact;
+  if (B.grid != grid || B.npull != npull || B.compact != compact)
+  {
+    B.grid = grid, B.npull = npull, B.compact = compact, B.ok = false;
+    const std::int32_t S = A.n_slices;
+    const std::int64_t warps = static_cast<std::int64_t>(grid) * (SPMV_THREADS / 32);
+    const bool shape_ok = c->bs == 3 || (c->bs == 1 && c->max_w <= 32 && A.cdelta != nullptr);
+    if (enabled && shape_ok && S >= warps && S < 8 * warps && grid >= 1 && (npull < 0 || npull < grid))
+    {
+      std::vector<std::int64_t> mo(static_cast<std::size_t>(S) + 1);
+      std::vector<std::int32_t> order(S);
+      PTB_CUDA(cudaStreamSynchronize(c->stream));
+      PTB_CUDA(cudaMemcpy(mo.data(), A.mat_off, mo.size() * sizeof(std::int64_t), cudaMemcpyDeviceToHost));
+      PTB_CUDA(cudaMemcpy(order.data(), c->slice_order.p, order.size() * sizeof(std::int32_t),
+                          cudaMemcpyDeviceToHost));
+      std::vector<std::int32_t> ou(static_cast<std::size_t>(S) + 1, 0);
+      for (std::int32_t i = 0; i < S; ++i)
+        ou[i + 1] = ou[i] + static_cast<std::int32_t>((mo[order[i] + 1] - mo[order[i]]) >> 5);
+      std::vector<std::int32_t> begin;
+      bool ok = true;
+      auto split = [&](std::int32_t a, std::int32_t b, int ctas) {
+        // boundaries at the slice edges nearest to the equal-unit cuts
+        const std::int64_t lo = ou[a], len = ou[b] - ou[a];
+        std::int32_t prev = a;
+        for (int t = 0; t <= ctas; ++t)
+        {
+          const std::int64_t target = lo + len * t / ctas;
+          std::int32_t i = static_cast<std::int32_t>(std::lower_bound(ou.begin() + a, ou.begin() + b + 1, target) - ou.begin());
+          if (i > a && target - ou[i - 1] < ou[i] - target)
+            --i;
+          i = std::max(i, prev);
+          if (t == ctas)
+            i = b;
+          if (t > 0 && i - prev > BAL_MAX_SLICES)
+            ok = false;
+          begin.push_back(i);
+          prev = i;
+        }
+      };
+      if (npull >= 0)
+      {
+        split(c->n_interior_slices, S, std::max(npull, 1));
+        split(0, c->n_interior_slices, grid - npull);
+      }
+      else
+        split(0, S, grid);
+      if (ok)
+      {
+        B.ounit.upload(ou, c->stream);
+        B.begin.upload(begin, c->stream);
+        PTB_CUDA(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+        B.ok = true;
+      }
+    }
+  }
+  if (B.ok)
+    A.ounit = B.ounit.p, A.bal_begin = B.begin.p;
+}
+
 void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned int epoch,
                  bool fused_halo)
 {
-  const SpmvArgs A = spmv_args(c);
+  SpmvArgs A = spmv_args(c);
   const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
   const PeerView P = peer_view(c);
   FusedHalo FH{};
@@ -1043,6 +1328,15 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
     const char* e = std::getenv("PTB_SPMV_TMA");
     return e && e[0] == '1';
   }();
+  // pullers get the ghost-reading slices: size their number to that share of the work (+25 %
+  // for the pull itself), at least 8 when the grid allows so the remote loads have parallelism
+  auto pullers = [&](int grid) {
+    const double share = c->n_slices > 0
+                             ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
+                             : 0.0;
+    const int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
+    return std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
+  };
   int fused_grid = 0;
   if (fused_halo)
   {
@@ -1059,25 +1353,35 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   }
   if (fused_halo)
   {
-    const int grid = fused_grid;
     FH.H = peer_halo(c);
     FH.epoch = ++c->peer.halo_epoch;
     FH.ready = c->peer.ready.p;
     FH.pw = c->p.p;
-    // pullers get the ghost-reading slices: size their number to that share of the work (+25 %
-    // for the pull itself), at least 8 when the grid allows so the remote loads have parallelism
-    const double share = c->n_slices > 0
-                             ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
-                             : 0.0;
-    int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
-    npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
-    FH.npull = npull;
-    if (c->bs == 1)
-      spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
-                                                               c->tickets.p, P, epoch, FH);
+    // small problem: the balanced instantiation (one resident wave of ITS occupancy), see spmv_cta_balanced
+    const int gbal = c->bs == 1 ? cached_grid(c, 16, spmv_sell<1, true, true>, SPMV_THREADS, 0, need)
+                                : cached_grid(c, 17, spmv_sell<3, true, true>, SPMV_THREADS, 0, need);
+    FH.npull = pullers(gbal);
+    ensure_balance(c, A, 0, gbal, FH.npull);
+    if (A.bal_begin != nullptr)
+    {
+      if (c->bs == 1)
+        spmv_sell<1, true, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                       c->tickets.p, P, epoch, FH);
+      else
+        spmv_sell<3, true, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                       c->tickets.p, P, epoch, FH);
+    }
     else
-      spmv_sell<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
-                                                               c->tickets.p, P, epoch, FH);
+    {
+      const int grid = fused_grid;
+      FH.npull = pullers(grid);
+      if (c->bs == 1)
+        spmv_sell<1, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                 c->tickets.p, P, epoch, FH);
+      else
+        spmv_sell<3, true><<<grid, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                 c->tickets.p, P, epoch, FH);
+    }
   }
   else if (c->bs == 1 && c->max_w <= 32 && use_tma)
   {
@@ -1092,13 +1396,27 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
                                                           P, epoch, FH, stage_doubles);
   }
   else if (c->bs == 1)
-    spmv_sell<1, false><<<cached_grid(c, 3, spmv_sell<1, false>, SPMV_THREADS, 0, need),
-                          SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
-                                                        epoch, FH);
+  {
+    const int gbal = cached_grid(c, 18, spmv_sell<1, false, true>, SPMV_THREADS, 0, need);
+    ensure_balance(c, A, 0, gbal, -1);
+    if (A.bal_begin != nullptr)
+      spmv_sell<1, false, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                      c->tickets.p, P, epoch, FH);
+    else
+      spmv_sell<1, false><<<cached_grid(c, 3, spmv_sell<1, false>, SPMV_THREADS, 0, need), SPMV_THREADS, 0,
+                            c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
+  }
   else
-    spmv_sell<3, false><<<cached_grid(c, 4, spmv_sell<3, false>, SPMV_THREADS, 0, need),
-                          SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P,
-                                                        epoch, FH);
+  {
+    const int gbal = cached_grid(c, 19, spmv_sell<3, false, true>, SPMV_THREADS, 0, need);
+    ensure_balance(c, A, 0, gbal, -1);
+    if (A.bal_begin != nullptr)
+      spmv_sell<3, false, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
+                                                                      c->tickets.p, P, epoch, FH);
+    else
+      spmv_sell<3, false><<<cached_grid(c, 4, spmv_sell<3, false>, SPMV_THREADS, 0, need), SPMV_THREADS, 0,
+                            c->stream>>>(A, p, y, st, c->partials.p, c->tickets.p, P, epoch, FH);
+  }
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
 }
@@ -1120,20 +1438,27 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   FH.order = c->slice_order.p;
   FH.n_interior = c->n_interior_slices;
   const void* kernel = nullptr;
+  const void* kernel_bal = nullptr; // the balanced instantiation (spmv_cta_balanced) for small problems
   int slot = 0;
   if (fused_halo)
     kernel = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, true>)
                         : reinterpret_cast<const void*>(cg_loop<3, true>),
+    kernel_bal = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, true, true>)
+                            : reinterpret_cast<const void*>(cg_loop<3, true, true>),
     slot = c->bs == 1 ? 10 : 11;
   else
     kernel = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, false>)
                         : reinterpret_cast<const void*>(cg_loop<3, false>),
+    kernel_bal = c->bs == 1 ? reinterpret_cast<const void*>(cg_loop<1, false, true>)
+                            : reinterpret_cast<const void*>(cg_loop<3, false, true>),
     slot = c->bs == 1 ? 12 : 13;
   if (c->grid_cache[slot] == 0)
   {
-    int per_sm = 0;
+    // one grid for both instantiations: the smaller of their co-resident capacities
+    int per_sm = 0, per_sm_bal = 0;
     PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
-    c->grid_cache[slot] = c->num_sms * std::max(1, std::min(per_sm, 8));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bal, kernel_bal, SPMV_THREADS, 0));
+    c->grid_cache[slot] = c->num_sms * std::max(1, std::min(std::min(per_sm, per_sm_bal), 8));
     const int forced = env_int("PTB_LOOP_CTAS", 0); // A/B: must stay co-resident (cooperative launch)
     if (forced > 0)
       c->grid_cache[slot] = std::min(forced, c->grid_cache[slot]);
@@ -1154,6 +1479,7 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
     FH.npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
   }
+  ensure_balance(c, L.A, 1, grid, fused_halo ? FH.npull : -1);
   if (c->loop_slots.n < static_cast<std::size_t>(grid + 1) * 4)
   {
     c->loop_slots.alloc(static_cast<std::size_t>(grid + 1) * 4);
@@ -1161,7 +1487,8 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   }
   L.slots = c->loop_slots.p;
   void* args[] = {&L, &P, &FH};
-  PTB_CUDA(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(SPMV_THREADS), args, 0, c->stream));
+  PTB_CUDA(cudaLaunchCooperativeKernel(L.A.bal_begin != nullptr ? kernel_bal : kernel, dim3(grid),
+                                       dim3(SPMV_THREADS), args, 0, c->stream));
   c->launches += 1;
   return true;
 }

@@ -99,7 +99,7 @@ struct ptb_ctx
   std::string err;
   double stage_ms[PTB_STAGE_COUNT] = {0, 0, 0, 0};
   std::int64_t launches = 0;
-  int grid_cache[16] = {}; // one-wave grid sizes per kernel (0 = not queried yet)
+  int grid_cache[32] = {}; // one-wave grid sizes per kernel (0 = not queried yet)
   int num_sms = 148;
 
   // problem description
@@ -138,6 +138,14 @@ struct ptb_ctx
   // L2 plan of the operator kernels (abi.cu plan_l2): hints on/off, pinned prefix in mat_off units
   int l2_mode = 0;
   std::int64_t l2_pin_entries = 0;
+  // balanced work split of the operator kernels for small problems (cg.cu ensure_balance): one
+  // plan per kernel family (0 = spmv_sell, 1 = cg_loop), rebuilt when grid / roles / operator change
+  struct Balance
+  {
+    int grid = -1, npull = -2;
+    bool compact = false, ok = false;
+    ptb::DevBuf<std::int32_t> ounit, begin;
+  } balance[2];
   ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)
   std::int32_t n_interior_slices = 0;
   ptb::DevBuf<double> vals;            // SELL, bs2 planes per entry

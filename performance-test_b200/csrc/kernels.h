@@ -82,6 +82,12 @@ struct SpmvArgs
   // (mat_off units) are loaded evict_last, the rest evict_first
   int l2_mode;
   std::int64_t pin_entries;
+  // Balanced work split of small problems (cg.cu spmv_cta_balanced), nullptr = one slice per warp
+  // step: ounit [n_slices + 1] = stored entries per row (k-steps) before position i of the slice
+  // order; bal_begin = the CTAs' runs of positions (fused halo: npull + 1 entries for the pullers'
+  // ghost-reading slices, then the workers' entries; otherwise gridDim.x + 1 entries)
+  const std::int32_t* ounit;
+  const std::int32_t* bal_begin;
 };
 
 /// The operator view the SpMV kernels read: the compacted copy when one is current (compact.cu).
@@ -89,9 +95,11 @@ inline SpmvArgs spmv_args(const ptb_ctx* c)
 {
   if (c->have_compact)
     return SpmvArgs{c->n_owned, c->n_slices, c->mat_off_z.p, c->cols.p, c->vals_z.p,
-                    c->cdelta_z.p, c->colsx_z.p, c->xoff_z.p, c->l2_mode, c->l2_pin_entries};
+                    c->cdelta_z.p, c->colsx_z.p, c->xoff_z.p, c->l2_mode, c->l2_pin_entries,
+                    nullptr, nullptr};
   return SpmvArgs{c->n_owned, c->n_slices, c->mat_off.p, c->cols.p, c->vals.p,
-                  c->cdelta.p, c->colsx.p, c->xoff.p, c->l2_mode, c->l2_pin_entries};
+                  c->cdelta.p, c->colsx.p, c->xoff.p, c->l2_mode, c->l2_pin_entries,
+                  nullptr, nullptr};
 }
 /// Build the zero-column-compacted copy of the assembled scalar operator (no-op for bs = 3).
 void compact_operator(ptb_ctx* c);

@@ -104,11 +104,12 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
                       const int64_t* mat_off, const int32_t* cols, const double* vals,
                       const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                       const int32_t* order, const double* dinv, double* r, double* p, double* x,
-                      double* y, void* st, unsigned long long* slots, int n_it)
+                      double* y, void* st, unsigned long long* slots, int n_it,
+                      const int32_t* ounit, const int32_t* bal_begin)
 {
   using namespace ptb;
   LoopArgs L{};
-  L.A = SpmvArgs{n_rows, n_slices, mat_off, cols, vals, cdelta, colsx, xoff};
+  L.A = SpmvArgs{n_rows, n_slices, mat_off, cols, vals, cdelta, colsx, xoff, 0, 0, ounit, bal_begin};
   L.n = static_cast<std::int64_t>(n_rows) * bs;
   L.dinv = dinv, L.r = r, L.p = p, L.x = x, L.y = y;
   L.st = static_cast<CgState*>(st);
@@ -132,7 +133,9 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
   for (unsigned t = 0; t < T; ++t)
     th.emplace_back([=] {
       threadIdx.x = t, blockIdx.x = block;
-      if (bs == 1)
+      if (bal_begin != nullptr)
+        bs == 1 ? cg_loop<1, false, true>(L, P, FH) : cg_loop<3, false, true>(L, P, FH);
+      else if (bs == 1)
         cg_loop<1, false>(L, P, FH);
       else
         cg_loop<3, false>(L, P, FH);
@@ -152,11 +155,12 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
                            const int64_t* mat_off, const int32_t* cols, const double* vals,
                            const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                            const int32_t* order, const double* dinv, double* r, double* p,
-                           double* x, double* y, void* st, unsigned long long* slots, int n_it)
+                           double* x, double* y, void* st, unsigned long long* slots, int n_it,
+                           const int32_t* ounit, const int32_t* bal_begin)
 {
   using namespace ptb;
   LoopArgs L{};
-  L.A = SpmvArgs{n_rows, n_slices, mat_off, cols, vals, cdelta, colsx, xoff};
+  L.A = SpmvArgs{n_rows, n_slices, mat_off, cols, vals, cdelta, colsx, xoff, 0, 0, ounit, bal_begin};
   L.n = static_cast<std::int64_t>(n_rows) * bs;
   L.dinv = dinv, L.r = r, L.p = p, L.x = x, L.y = y;
   L.st = static_cast<CgState*>(st);
@@ -189,7 +193,9 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
   for (unsigned t = 0; t < T; ++t)
     th.emplace_back([=] {
       threadIdx.x = t, blockIdx.x = block;
-      if (bs == 1)
+      if (bal_begin != nullptr)
+        bs == 1 ? cg_loop<1, true, true>(L, P, FH) : cg_loop<3, true, true>(L, P, FH);
+      else if (bs == 1)
         cg_loop<1, true>(L, P, FH);
       else
         cg_loop<3, true>(L, P, FH);

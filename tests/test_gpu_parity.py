@@ -300,6 +300,33 @@ def test_config2_sampled_row_blocks_against_oracle(pt, oracle):
         assert np.abs(b[off:off + n] - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
 
 
+@pytest.mark.parametrize("ptype,dims", [("poisson", (55, 54, 53)), ("elasticity", (54, 54, 54))])
+def test_balanced_operator_split_matches_oracle(pt, oracle, ctx, ptype, dims):
+    """Problems with 1..8 slices per resident warp take the balanced instantiation of the operator
+    kernels (cg.cu spmv_cta_balanced: CTAs hold equal numbers of k-steps, slices are split between
+    the warps of a CTA): y against the oracle's SpMV to 1e-13, the CG solve as three kernels per
+    iteration and as the persistent loop against the oracle's iteration count."""
+    P = pt.host.Problem(ptype, 1, *dims)
+    assert 4736 <= (P.n_owned + 31) // 32 < 8 * 4736   # the range ensure_balance accepts on 148 SMs
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A, b = ctx.matrix_values(), ctx.rhs()
+    v = np.random.default_rng(9).standard_normal((P.n_owned + P.n_ghost) * P.bs)
+    y_ref = oracle.spmv(P.bs, P.n_owned, P["rowptr"], P["cols"], A, v, nthreads=oracle.max_threads())
+    assert np.abs(ctx.apply_operator(v) - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+    _, k_ref, rel_ref = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A, b, kmax=5000, rtol=1e-8,
+                                  precond="jacobi", nthreads=oracle.max_threads())
+    for mode in (0, 1):
+        ctx.set_cg_persistent(mode)
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond="jacobi")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8, (mode, k, k_ref, rel)
+        r = b - ctx.apply_operator(ctx.solution())
+        assert np.linalg.norm(r) <= 5e-8 * np.linalg.norm(b)
+    ctx.set_cg_persistent(-1)
+
+
 def test_large_properties_elasticity(pt, ctx):
     """Size-independent properties at a size the oracle would not finish quickly (3.2M DOFs):
     symmetry via <Au, v> = <u, Av>, rigid-body modes in the kernel away from the BC, and the CG

@@ -224,11 +224,40 @@ def emucg():
     return libs
 
 
+def _balance_plan(mat_off, order, groups):
+    """The host side of the balanced operator split (cg.cu ensure_balance) restated: unit prefix over
+    the slice order and, per (first position, last position, CTAs) group, the CTAs' runs with equal
+    units up to one slice. Returns (ounit, begin), begin = None where a run exceeds 64 slices."""
+    order = np.asarray(order)
+    w = (np.asarray(mat_off)[order + 1] - np.asarray(mat_off)[order]) // 32
+    ou = np.concatenate([[0], np.cumsum(w)]).astype(np.int32)
+    begin = []
+    for a, b, ctas in groups:
+        prev = a
+        for t in range(ctas + 1):
+            target = int(ou[a]) + (int(ou[b]) - int(ou[a])) * t // ctas
+            i = a + int(np.searchsorted(ou[a:b + 1], target, side="left"))
+            if i > a and target - ou[i - 1] < ou[i] - target:
+                i -= 1
+            i = max(i, prev)
+            if t == ctas:
+                i = b
+            if t > 0 and i - prev > 64:
+                return ou, None
+            begin.append(i)
+            prev = i
+    return ou, np.array(begin, dtype=np.int32)
+
+
+@pytest.mark.parametrize("balanced", [False, True])
 @pytest.mark.parametrize("ptype,dims,precond,grid", [("poisson", (6, 5, 7), "jacobi", 3),
                                                      ("poisson", (6, 5, 7), "none", 1),
                                                      ("poisson", (9, 2, 2), "jacobi", 4),
                                                      ("elasticity", (3, 4, 3), "jacobi", 2)])
-def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptype, dims, precond, grid):
+def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptype, dims, precond, grid,
+                                                         balanced):
+    """balanced = True runs the instantiation that cuts the CTA's slices into equal k-step ranges per
+    warp (spmv_cta_balanced): slices split between warps are summed through shared memory."""
     import threading
     P = pt.host.Problem(ptype, 1, *dims)
     bs, n, rtol = P.bs, P.n_owned * P.bs, 1e-8
@@ -258,6 +287,9 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     slots = np.zeros(4 * (grid + 1), np.uint64)   # LL arrival records of the CTAs + the release record
     args = [P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(vals), _p(cdelta), _p(colsx),
             _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(slots), 500]
+    ou, begin = _balance_plan(L["mat_off"], order, [(0, L["n_slices"], grid)]) if balanced else (None, None)
+    assert not balanced or begin is not None
+    args += [_p(ou) if balanced else None, _p(begin) if balanced else None]
     threads = [threading.Thread(target=emucg[g].emu_cg_loop_block, args=[bs, g, grid] + args)
                for g in range(grid)]
     for t in threads:
@@ -273,8 +305,9 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     assert np.all(slots >> np.uint64(32) == np.uint64(3 * int(fin["k"])))
 
 
+@pytest.mark.parametrize("balanced", [False, True])
 @pytest.mark.parametrize("ptype,dims", [("poisson", (4, 3, 9)), ("elasticity", (2, 3, 5))])
-def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
+def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, balanced):
     """Two ranks x two CTAs of cg_loop<BS, true>: CTA 0 of a rank is the puller (publishes 'p is
     ready', waits for the neighbour, pulls the ghost values out of the neighbour's vector, takes
     the ghost-reading slices), CTA 1 the worker; the dot products go through the LL windows. The
@@ -336,6 +369,14 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims):
                     P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(d["vals"]),
                     _p(d["cdelta"]), _p(d["colsx"]), _p(d["xoff"]), _p(d["order"]), _p(d["dinv"]),
                     _p(d["r"]), _p(d["p"]), _p(d["x"]), _p(d["y"]), _p(d["st"]), _p(d["slots"]), 500]
+            if balanced:   # one puller (ghost-reading slices), one worker (interior slices)
+                if "ou" not in d:
+                    d["ou"], d["begin"] = _balance_plan(L["mat_off"], d["order"],
+                                                        [(d["n_int"], L["n_slices"], 1), (0, d["n_int"], grid - 1)])
+                    assert d["begin"] is not None
+                args += [_p(d["ou"]), _p(d["begin"])]
+            else:
+                args += [None, None]
             threads.append(threading.Thread(target=emucg[q * grid + g].emu_cg_loop_block_peer, args=args))
     for t in threads:
         t.start()
