@@ -67,6 +67,8 @@ def parse():
     ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
                     help="one workload only (default: elasticity headline + poisson secondary)")
     ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-renumbered", action="store_true",
+                    help="skip the rcm / random dof-numbering measurements of the N = 1 run")
     ap.add_argument("--kmax", type=int, default=KMAX)
     ap.add_argument("--ndofs", type=int, default=None, help="override the workload's --ndofs")
     ap.add_argument("--cpu-kcap", type=int, default=200,
@@ -456,7 +458,47 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu):
     barrier()
     ctx.close()
     del ctx, P
+    if out is not None and world == 1 and not device_setup and not args.no_renumbered:
+        out["renumbered"] = renumbered_numbers(pt, wl_name, args, peak)
     return out
+
+
+def renumbered_numbers(pt, wl_name, args, peak):
+    """The same workload with the owned dofs renumbered the way a DOLFINx dofmap is (not lattice-
+    lexicographic): "rcm" = reverse Cuthill-McKee (banded, local, no translation invariance -- the
+    realistic case: every column index of the scalar operator goes explicit), "random" = seeded
+    shuffle (no locality: the worst case for the gather of p). One solve for rcm, kernel timings
+    for both; N = 1 only (the stand-in renumbers single-rank problems)."""
+    import torch
+    abi = pt.abi
+    res = {}
+    ptype, order, dims, base, scaling, ndofs_arg = sizing(pt, wl_name, 1, args.ndofs)
+    for kind in ("rcm", "random"):
+        t0 = time.perf_counter()
+        P = pt.host.Problem(ptype, order, *dims, renumber=kind, seed=1)
+        ctx = abi.Context(torch.cuda.current_device(), stream=torch.cuda.current_stream().cuda_stream)
+        ctx.set_problem(P)
+        t_setup = time.perf_counter() - t0
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        n, bs, nnz = P.n_owned, P.bs, P.nnz
+        r = {"setup_s": t_setup, "cols_explicit_fraction": ctx.cols_explicit_fraction(),
+             "stage_ms": {"assemble_matrix": ctx.stage_ms(abi.STAGE_ASSEMBLE_MATRIX),
+                          "assemble_vector": ctx.stage_ms(abi.STAGE_ASSEMBLE_VECTOR)}}
+        if kind == "rcm":
+            k, rel = ctx.cg_solve(kmax=args.kmax, rtol=1e-8, precond="jacobi")
+            sv = ctx.stage_ms(abi.STAGE_SOLVE)
+            r.update(cg_iterations=k, rel_residual=rel, value=k * n * bs / (sv * 1e-3),
+                     unit="DOF-iters/s", solve_ms=sv)
+        else:
+            ctx.cg_solve(kmax=5, rtol=1e-8, precond="jacobi")   # leaves p, r, x populated
+        t_spmv = ctx.time_kernel(abi.KERNEL_SPMV, 20)
+        spmv_b = 12 * nnz + 20 * n if bs == 1 else 76 * nnz + 52 * n
+        r.update(spmv_ms=t_spmv, spmv_GBps=spmv_b / t_spmv / 1e6, spmv_frac=spmv_b / t_spmv / 1e6 / peak)
+        res[kind] = r
+        ctx.close()
+        del ctx, P
+    return res
 
 
 def main():

@@ -39,6 +39,11 @@ int pth_problem_create(const char* problem_type, int order, int64_t nx, int64_t 
  * dof_x, rowptr/cols, bc_dofs, f, g stay empty; nnz and n_bc read 0. */
 int pth_problem_create_sizes_only(const char* problem_type, int order, int64_t nx, int64_t ny,
                                   int64_t nz, int rank, int nranks, pth_problem** out);
+/* Renumber the owned dofs of a single-rank problem the way a real DOLFINx dofmap is numbered: not
+ * lattice-lexicographically. kind = "rcm" (reverse Cuthill-McKee over the sparsity graph: banded,
+ * local, not translation invariant -- what fem::DofMap's graph reordering produces in kind) or
+ * "random" (seeded shuffle: no locality at all). dofmap, dof_x, f, g, bc_dofs, rowptr and cols follow. */
+int pth_problem_renumber(pth_problem* p, const char* kind, uint64_t seed);
 void pth_problem_destroy(pth_problem* p);
 
 /* Named scalar: n_cells, n_cells_owned, n_ghost_cells_front, cell_global_offset, n_cells_global,

@@ -983,7 +983,24 @@ struct LoopArgs
   int it0, n_it;             // iterations it0+1 .. it0+n_it
   unsigned int ebase;        // peer reduction epochs: ebase + 2 (j-1) for p.y, + 1 for (r.r, r.z)
   unsigned int lbase;        // grid barrier epochs: lbase + 3 (j-1) + {0, 1, 2}
+  // phase trace (PTB_LOOP_TRACE=iteration): [gridDim.x][8] globaltimer stamps of thread 0 of every
+  // CTA in iteration trace_iter: start, SpMV done, barrier 1 passed, update done, barrier 2 passed,
+  // direction done, barrier 3 passed. nullptr = no trace (one predictable branch per phase).
+  unsigned long long* trace;
+  int trace_iter;
 };
+
+__device__ __forceinline__ void loop_stamp(const LoopArgs& L, int j, int slot)
+{
+#ifndef PTB_HOST_EMU
+  if (L.trace != nullptr && j == L.trace_iter && threadIdx.x == 0)
+  {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    L.trace[static_cast<std::size_t>(blockIdx.x) * 8 + slot] = t;
+  }
+#endif
+}
 
 
 // Grid barrier fused with a deterministic reduction of NV values per CTA (NV = 0: barrier only).
@@ -1083,6 +1100,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     const int k_done = __ldcg(&cur->k);
 
     // ---- phase 1: y = A p, local p.y --------------------------------------------------------
+    loop_stamp(L, j, 0);
     double dotv = 0.0;
     constexpr bool balanced = BAL;
     if constexpr (FUSED)
@@ -1131,7 +1149,9 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     const unsigned int ea = L.ebase + 2u * static_cast<unsigned int>(j - 1), eb = ea + 1u;
     const unsigned int la = L.lbase + 3u * static_cast<unsigned int>(j - 1);
     double v1[1] = {dotv}, py[1];
+    loop_stamp(L, j, 1);
     grid_reduce_sync<1>(v1, L, P, la, ea, red, py);
+    loop_stamp(L, j, 2);
     const double alpha = rz_old / py[0]; // cg.h:65
 
     // ---- phase 2: r -= alpha y (cg.h:71), local r.r and r.z (cg.h:74) -----------------------
@@ -1161,7 +1181,9 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       }
     }
     double rs[2];
+    loop_stamp(L, j, 3);
     grid_reduce_sync<2>(v2, L, P, la + 1u, eb, red, rs);
+    loop_stamp(L, j, 4);
     const double rr = rs[0], rz = rs[1];
     const double beta = rz / rz_old;             // cg.h:75
     const bool converged = rr / rnorm0 < rtol2;  // cg.h:78
@@ -1202,7 +1224,9 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       }
     }
     double none[1] = {0.0}, none_out[1];
+    loop_stamp(L, j, 5);
     grid_reduce_sync<0>(none, L, P, la + 2u, 0u, red, none_out);
+    loop_stamp(L, j, 6);
   }
 }
 
@@ -1254,7 +1278,7 @@ int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, s
 // rows or P1 rows (one batch of column deltas), at most BAL_MAX_SLICES slices per CTA.
 void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
 {
-  static const bool enabled = env_flag("PTB_SPMV_BALANCE", true);
+  static const bool enabled = env_int("PTB_SPMV_BALANCE", 1) != 0;
   ptb_ctx::Balance& B = c->balance[which];
   const bool compact = c->have_compact;
   if (B.grid != grid || B.npull != npull || B.compact != compact)
@@ -1262,7 +1286,11 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
     B.grid = grid, B.npull = npull, B.compact = compact, B.ok = false;
     const std::int32_t S = A.n_slices;
     const std::int64_t warps = static_cast<std::int64_t>(grid) * (SPMV_THREADS / 32);
-    const bool shape_ok = c->bs == 3 || (c->bs == 1 && c->max_w <= 32 && A.cdelta != nullptr);
+    // block rows only: the scalar variant (spmv_slice_part<1>, kept for the tests) lost against the
+    // slice-per-warp kernel, whose delta-compressed column path it cannot use across a split
+    // (Poisson 500 k DOFs: 30.8 vs 18.3 us, profiles/r02/ab_call7_summary.txt); PTB_SPMV_BALANCE=2 forces it
+    static const bool scalar_too = env_int("PTB_SPMV_BALANCE", 1) == 2;
+    const bool shape_ok = c->bs == 3 || (scalar_too && c->bs == 1 && c->max_w <= 32 && A.cdelta != nullptr);
     if (enabled && shape_ok && S >= warps && S < 8 * warps && grid >= 1 && (npull < 0 || npull < grid))
     {
       std::vector<std::int64_t> mo(static_cast<std::size_t>(S) + 1);
@@ -1486,10 +1514,46 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     c->loop_slots.zero(c->stream); // epoch 0 = never written; the host counter starts at 1
   }
   L.slots = c->loop_slots.p;
+  static const int trace_iter = env_int("PTB_LOOP_TRACE", 0);
+  if (trace_iter > 0)
+  {
+    c->loop_trace.alloc(static_cast<std::size_t>(grid) * 8);
+    c->loop_trace.zero(c->stream);
+    L.trace = c->loop_trace.p, L.trace_iter = trace_iter;
+  }
   void* args[] = {&L, &P, &FH};
   PTB_CUDA(cudaLaunchCooperativeKernel(L.A.bal_begin != nullptr ? kernel_bal : kernel, dim3(grid),
                                        dim3(SPMV_THREADS), args, 0, c->stream));
   c->launches += 1;
+  if (trace_iter > 0)
+  {
+    // diagnostic: phase durations of iteration trace_iter over all CTAs (stderr)
+    std::vector<unsigned long long> t(static_cast<std::size_t>(grid) * 8);
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    PTB_CUDA(cudaMemcpy(t.data(), c->loop_trace.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int b = 0; b < grid; ++b)
+      if (t[b * 8] != 0)
+        t0 = std::min(t0, t[b * 8]);
+    const char* names[7] = {"start", "spmv done", "barrier1 out", "update done", "barrier2 out",
+                            "direction done", "barrier3 out"};
+    std::fprintf(stderr, "[ptb loop trace] iteration %d, %d CTAs, ns after the first CTA's start: min / mean / max\n",
+                 trace_iter, grid);
+    for (int s2 = 0; s2 < 7; ++s2)
+    {
+      double mn = 1e30, mx = 0, sum = 0;
+      int cnt = 0;
+      for (int b = 0; b < grid; ++b)
+      {
+        if (t[b * 8 + s2] == 0)
+          continue;
+        const double d = static_cast<double>(t[b * 8 + s2] - t0);
+        mn = std::min(mn, d), mx = std::max(mx, d), sum += d, ++cnt;
+      }
+      if (cnt)
+        std::fprintf(stderr, "[ptb loop trace]   %-15s %9.0f %9.0f %9.0f\n", names[s2], mn, sum / cnt, mx);
+    }
+  }
   return true;
 }
 

@@ -186,6 +186,7 @@ struct ptb_ctx
   ptb::DevBuf<unsigned int> tickets;     // [4]
   ptb::DevBuf<unsigned long long> loop_slots; // [grid + 1][4] LL records of the persistent loop's barrier
   unsigned int loop_epoch = 0;                // last barrier epoch used (monotone across solves)
+  ptb::DevBuf<unsigned long long> loop_trace; // PTB_LOOP_TRACE diagnostic (cg.cu launch_cg_loop)
   int cg_persistent = -1;                     // ptb_set_cg_persistent: -1 auto, 0 off, 1 on
   ptb::CgState* h_cg = nullptr;          // pinned [2]
   double* h_scalar = nullptr;            // pinned [4]

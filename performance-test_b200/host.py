@@ -32,6 +32,7 @@ def lib():
         L.pth_problem_create.argtypes = [C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
                                          C.c_int, C.c_int, C.POINTER(C.c_void_p)]
         L.pth_problem_create_sizes_only.argtypes = L.pth_problem_create.argtypes
+        L.pth_problem_renumber.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64]
         L.pth_problem_destroy.argtypes = [C.c_void_p]
         L.pth_problem_destroy.restype = None
         L.pth_problem_scalar.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64)]
@@ -70,12 +71,17 @@ class Problem:
     """Mesh slab + function space + BC + RHS + sparsity pattern for one rank (host memory)."""
 
     def __init__(self, problem_type: str, order: int, nx: int, ny: int, nz: int,
-                 rank: int = 0, nranks: int = 1, with_dofmap: bool = True):
+                 rank: int = 0, nranks: int = 1, with_dofmap: bool = True, renumber: str | None = None,
+                 seed: int = 0):
         """with_dofmap=False: sizes, halo lists and exterior facets only (the arrays are generated
-        on the device by Context.set_problem_on_device)."""
+        on the device by Context.set_problem_on_device). renumber = "rcm" | "random": owned dofs
+        renumbered like a DOLFINx dofmap is (single rank; include/ptb200_host.h)."""
         self._h = C.c_void_p()
         create = lib().pth_problem_create if with_dofmap else lib().pth_problem_create_sizes_only
         _check(create(problem_type.encode(), order, nx, ny, nz, rank, nranks, C.byref(self._h)))
+        if renumber:
+            _check(lib().pth_problem_renumber(self._h, renumber.encode(), seed))
+        self.renumber = renumber
         self.problem_type = problem_type
         for name in SCALARS:
             v = C.c_int64()

@@ -3,7 +3,9 @@
 #include "box_mesh.h"
 #include "fem.h"
 #include <cstring>
+#include <algorithm>
 #include <map>
+#include <random>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -105,6 +107,104 @@ int pth_problem_create_sizes_only(const char* problem_type, int order, int64_t n
     exterior_facets(p->mesh, p->facet_cells, p->facet_local);
     p->rowptr.assign(1, 0);
     *out = p.release();
+  });
+}
+
+// Renumber the owned dofs of a single-rank problem. DOLFINx does not number dofs lattice-
+// lexicographically: fem::DofMap reorders them (reverse Cuthill-McKee / Gibbs-Poole-Stockmeyer on
+// the dof graph), so a drop-in sees banded but NOT translation-invariant numberings. This
+// gives the stand-in the same property: "rcm" = reverse Cuthill-McKee over the sparsity graph
+// (breadth-first from a minimum-degree dof, neighbours by ascending degree, order reversed),
+// "random" = a seeded shuffle (the worst case for the gather of p). Everything that names a dof
+// follows: dofmap, dof coordinates, sources, Dirichlet dofs, pattern.
+int pth_problem_renumber(pth_problem* p, const char* kind, uint64_t seed)
+{
+  return guarded([&] {
+    if (p->mesh.nranks != 1)
+      throw std::runtime_error("pth_problem_renumber: single-rank problems only");
+    if (p->V.dofmap.empty() || p->rowptr.size() < 2)
+      throw std::runtime_error("pth_problem_renumber: needs the dofmap and the pattern");
+    const std::string k(kind);
+    const std::int32_t n = p->V.n_owned;
+    std::vector<std::int32_t> perm(n); // perm[old] = new
+    if (k == "random")
+    {
+      std::vector<std::int32_t> order(n);
+      for (std::int32_t i = 0; i < n; ++i)
+        order[i] = i;
+      std::mt19937_64 gen(seed);
+      for (std::int32_t i = n - 1; i > 0; --i)
+        std::swap(order[i], order[static_cast<std::int32_t>(gen() % static_cast<std::uint64_t>(i + 1))]);
+      for (std::int32_t i = 0; i < n; ++i)
+        perm[order[i]] = i;
+    }
+    else if (k == "rcm")
+    {
+      const std::vector<std::int64_t>& rp = p->rowptr;
+      const std::vector<std::int32_t>& cl = p->cols;
+      auto degree = [&](std::int32_t v) { return static_cast<std::int32_t>(rp[v + 1] - rp[v]); };
+      std::vector<std::int32_t> cm;
+      cm.reserve(n);
+      std::vector<char> seen(n, 0);
+      std::vector<std::int32_t> by_degree(n), nb;
+      for (std::int32_t i = 0; i < n; ++i)
+        by_degree[i] = i;
+      std::stable_sort(by_degree.begin(), by_degree.end(),
+                       [&](std::int32_t a, std::int32_t b) { return degree(a) < degree(b); });
+      for (std::int32_t start : by_degree) // one breadth-first sweep per connected component
+      {
+        if (seen[start])
+          continue;
+        seen[start] = 1;
+        std::size_t head = cm.size();
+        cm.push_back(start);
+        while (head < cm.size())
+        {
+          const std::int32_t v = cm[head++];
+          nb.clear();
+          for (std::int64_t q = rp[v]; q < rp[v + 1]; ++q)
+          {
+            const std::int32_t c = cl[q];
+            if (c < n && !seen[c])
+              seen[c] = 1, nb.push_back(c);
+          }
+          std::stable_sort(nb.begin(), nb.end(),
+                           [&](std::int32_t a, std::int32_t b) { return degree(a) < degree(b); });
+          cm.insert(cm.end(), nb.begin(), nb.end());
+        }
+      }
+      for (std::int32_t i = 0; i < n; ++i)
+        perm[cm[i]] = n - 1 - i; // reversed
+    }
+    else
+      throw std::runtime_error("pth_problem_renumber: kind must be rcm or random");
+
+    FunctionSpace& V = p->V;
+    const int bs = V.bs;
+#pragma omp parallel for schedule(static)
+    for (std::int64_t i = 0; i < static_cast<std::int64_t>(V.dofmap.size()); ++i)
+      if (V.dofmap[i] < n)
+        V.dofmap[i] = perm[V.dofmap[i]];
+    auto permute = [&](std::vector<double>& v, int width) {
+      if (v.empty())
+        return;
+      std::vector<double> out(v);
+#pragma omp parallel for schedule(static)
+      for (std::int32_t i = 0; i < n; ++i)
+        for (int a = 0; a < width; ++a)
+          out[static_cast<std::size_t>(perm[i]) * width + a] = v[static_cast<std::size_t>(i) * width + a];
+      v.swap(out);
+    };
+    permute(V.dof_x, 3);
+    permute(p->f, bs);
+    permute(p->g, 1);
+    for (std::int32_t& d : p->bc_dofs)
+      if (d < n)
+        d = perm[d];
+    std::sort(p->bc_dofs.begin(), p->bc_dofs.end());
+    ptb::RowAdjacency adj;
+    ptb::build_row_adjacency(V.dofmap.data(), p->mesh.n_cells_local(), V.nd, n, adj);
+    ptb::build_pattern(V.dofmap.data(), V.nd, n, adj, p->rowptr, p->cols);
   });
 }
 

@@ -18,7 +18,7 @@ for v in "$@"; do
   else
     launcher=(python bench.py)
   fi
-  env $envs timeout 600 "${launcher[@]}" "${args[@]}" --no-cpu-baseline > "$out/$name.json" 2> "$out/$name.err"
+  env $envs timeout 600 "${launcher[@]}" "${args[@]}" --no-cpu-baseline --no-renumbered > "$out/$name.json" 2> "$out/$name.err"
   python - "$out/$name.json" "$name" <<'PY'
 import json, sys
 try:

@@ -327,6 +327,39 @@ def test_balanced_operator_split_matches_oracle(pt, oracle, ctx, ptype, dims):
     ctx.set_cg_persistent(-1)
 
 
+RENUMBERED = [("poisson", 1, (16, 15, 17), "rcm"), ("poisson", 1, (9, 8, 10), "random"),
+              ("elasticity", 1, (12, 11, 13), "rcm"), ("elasticity", 1, (6, 5, 7), "random"),
+              ("poisson", 2, (5, 4, 6), "rcm"), ("poisson", 3, (4, 3, 4), "random"), ("poisson", 3, (5, 4, 3), "rcm")]
+
+
+@pytest.mark.parametrize("ptype,order,dims,kind", RENUMBERED)
+def test_hot_path_on_renumbered_dofs_matches_oracle(pt, oracle, ctx, ptype, order, dims, kind):
+    """The whole path on dof numberings that are not lattice-lexicographic (a DOLFINx dofmap is graph
+    reordered): reverse Cuthill-McKee and a random shuffle of the owned dofs (host stand-in,
+    pth_problem_renumber). No stencil is translation invariant there: every column index of the
+    scalar operator is stored explicitly, rows of different lengths share slices, the stars of the
+    P1 walk arrive in a different order. A, b, A p and the solve against the oracle as usual."""
+    P = pt.host.Problem(ptype, order, *dims, renumber=kind, seed=7)
+    ctx.set_problem(P)
+    ctx.assemble_matrix()
+    ctx.assemble_vector()
+    A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    _check_matrix(P, ctx.matrix_values(), A_ref)
+    assert np.abs(ctx.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    if P.bs == 1 and P.n_owned > 2000:
+        assert ctx.cols_explicit_fraction() > 0.5
+    v = np.random.default_rng(2).standard_normal((P.n_owned + P.n_ghost) * P.bs)
+    y_ref = oracle.spmv(P.bs, P.n_owned, P["rowptr"], P["cols"], ctx.matrix_values(), v)
+    assert np.abs(ctx.apply_operator(v) - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+    for precond in ("jacobi", "none"):
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=5000, rtol=1e-8, precond=precond)
+        x_ref, k_ref, _ = oracle.cg(P.bs, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=5000,
+                                    rtol=1e-8, precond=precond)
+        assert abs(k - k_ref) <= 1 and rel < 1e-8
+        assert np.linalg.norm(ctx.solution()[: P.n_owned * P.bs] - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
 def test_large_properties_elasticity(pt, ctx):
     """Size-independent properties at a size the oracle would not finish quickly (3.2M DOFs):
     symmetry via <Au, v> = <u, Av>, rigid-body modes in the kernel away from the BC, and the CG
