@@ -26,6 +26,13 @@ namespace
 {
 
 constexpr int SPMV_THREADS = 256;
+// The persistent loop runs ONE 1024-thread CTA per SM: its grid barrier costs one arrival record
+// per CTA (148 instead of 592), and the operator phase keeps the same 32 warps per SM.
+#ifdef PTB_HOST_EMU
+constexpr int LOOP_THREADS = 256; // the host harness plays a CTA with one std::thread per thread
+#else
+constexpr int LOOP_THREADS = 1024;
+#endif
 constexpr int VEC_THREADS = 256;
 
 // Gather of the input vector: read-only (non-coherent) path, except for slices that read ghost
@@ -196,7 +203,7 @@ __device__ __forceinline__ double spmv_slice(const SpmvArgs& A, const L2Plan& LP
 // Same arithmetic per stored entry, fixed order, no atomics; a split row is summed in (at most
 // eight) pieces instead of one, so y may differ from the slice-per-warp kernel in the last bit.
 // ------------------------------------------------------------------------------------------
-constexpr int BAL_MAX_SLICES = 64; // slices per CTA the shared-memory prefix can hold
+constexpr int BAL_SLICES_PER_WARP = 8; // the shared-memory prefix holds 8 slices per warp of the CTA
 
 // Partial row sums of one slice over its entries [kb, ke).
 template <int BS, Ld L>
@@ -264,19 +271,29 @@ __device__ __forceinline__ void spmv_slice_part(const SpmvArgs& A, const L2Plan&
   }
 }
 
+// Shared memory of spmv_cta_balanced, declared once per kernel (the roles call it from two places).
+template <int BS, int W>
+struct BalShared
+{
+  std::int32_t su[BAL_SLICES_PER_WARP * W + 1]; // unit prefix of the CTA's slices, from 0
+  double head[W][32 * BS];                      // partial sums of the slice a warp starts inside
+  std::int32_t head_pos[W];                     // its position in the CTA's run, -1 = none
+};
+
 // The slices at positions [i0, i1) of `order`, shared evenly by the warps of this CTA.
 // Every thread of the CTA must call this (it contains CTA barriers). Returns the thread's p.y share.
-template <int BS, Ld L>
+template <int BS, Ld L, int W>
 __device__ __forceinline__ double spmv_cta_balanced(const SpmvArgs& A, const L2Plan& LP,
                                                     const double* __restrict__ p,
                                                     double* __restrict__ y,
                                                     const std::int32_t* __restrict__ order,
-                                                    std::int32_t i0, std::int32_t i1)
+                                                    std::int32_t i0, std::int32_t i1,
+                                                    BalShared<BS, W>& sh)
 {
-  constexpr int W = SPMV_THREADS / 32;
-  __shared__ std::int32_t su[BAL_MAX_SLICES + 1]; // unit prefix of the CTA's slices, from 0
-  __shared__ double head[W][32 * BS];             // partial sums of the slice a warp starts inside
-  __shared__ std::int32_t head_pos[W];            // its position in the CTA's run, -1 = none
+  constexpr int MAXS = BAL_SLICES_PER_WARP * W;
+  std::int32_t* su = sh.su;
+  double(*head)[32 * BS] = sh.head;
+  std::int32_t* head_pos = sh.head_pos;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = i1 - i0;
   __syncthreads(); // the previous use of the shared arrays (persistent loop) is over
@@ -288,12 +305,11 @@ __device__ __forceinline__ double spmv_cta_balanced(const SpmvArgs& A, const L2P
   const std::int32_t total = su[n];
   const std::int32_t u0 = static_cast<std::int32_t>(static_cast<std::int64_t>(total) * warp / W);
   const std::int32_t u1 = static_cast<std::int32_t>(static_cast<std::int64_t>(total) * (warp + 1) / W);
-  // position j with su[j] <= u0 < su[j + 1] (n <= 64: two probes per lane)
+  // position j with su[j] <= u0 < su[j + 1]: the number of t in [1, n] with su[t] <= u0
   int j = 0;
-  {
-    const bool a = lane < n && su[lane + 1] <= u0, b = lane + 32 < n && su[lane + 33] <= u0;
-    j = __popc(__ballot_sync(0xffffffffu, a)) + __popc(__ballot_sync(0xffffffffu, b));
-  }
+#pragma unroll
+  for (int t0 = 0; t0 < MAXS; t0 += 32)
+    j += __popc(__ballot_sync(0xffffffffu, t0 + lane < n && su[t0 + lane + 1] <= u0));
   double dotv = 0.0;
   double pend[BS];
   int pend_j = -1;
@@ -456,6 +472,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   const L2Plan LP = l2_plan(A);
   double dotv = 0.0;
   constexpr bool balanced = BAL; // the host passes A.bal_begin / A.ounit with this instantiation
+  __shared__ BalShared<BS, BAL ? SPMV_THREADS / 32 : 1> bal_sh;
   if constexpr (FUSED)
   {
     if (blockIdx.x < FH.npull)
@@ -470,8 +487,8 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
         while (!__all_sync(0xffffffffu, f >= FH.epoch));
       }
       if constexpr (balanced)
-        dotv = spmv_cta_balanced<BS, Ld::CG>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
-                                             A.bal_begin[blockIdx.x + 1]);
+        dotv = spmv_cta_balanced<BS, Ld::CG, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
+                                             A.bal_begin[blockIdx.x + 1], bal_sh);
       else
         for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
              it += FH.npull * warps_per_cta)
@@ -480,7 +497,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
     else if constexpr (balanced)
     {
       const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
-      dotv = spmv_cta_balanced<BS, Ld::NC>(A, LP, p, y, FH.order, A.bal_begin[b], A.bal_begin[b + 1]);
+      dotv = spmv_cta_balanced<BS, Ld::NC, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh);
     }
     else
     {
@@ -491,8 +508,8 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
     }
   }
   else if constexpr (balanced)
-    dotv = spmv_cta_balanced<BS, Ld::NC>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
-                                         A.bal_begin[blockIdx.x + 1]);
+    dotv = spmv_cta_balanced<BS, Ld::NC, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
+                                         A.bal_begin[blockIdx.x + 1], bal_sh);
   else
   {
     const std::int32_t stride = gridDim.x * warps_per_cta;
@@ -1004,20 +1021,23 @@ __device__ __forceinline__ void loop_stamp(const LoopArgs& L, int j, int slot)
 
 
 // Grid barrier fused with a deterministic reduction of NV values per CTA (NV = 0: barrier only).
-// No atomics: every CTA stores one LL arrival record (its partial sums + the barrier epoch in the
-// same 8-byte words); CTA 0 collects the records in index order, adds them with the fixed block
-// tree, publishes the local sums to the peers (LL window) and stores the release record; every
-// CTA waits for the release (single GPU) or for all ranks' window slots (which contain this rank's
-// own, written after the collection) and holds the (peer-)global sums in out[] on return.
-// 592 same-address atomics cost ~27 cycles each when they arrive together (B300_MICROARCH.md,
-// "L2-atom multi-CTA"): ~8 us per barrier, three barriers per iteration -- the records do not queue.
+// No atomics and no leader: every CTA stores one LL arrival record (its partial sums + the barrier
+// epoch in the same 8-byte words) and then reads ALL records -- each thread polls its share with
+// the loads of all its records in flight at once -- and adds them in index order with the fixed
+// block tree, so every CTA of the grid computes the same bits without a second hop. Across GPUs
+// CTA 0 publishes the local sums to the peers' windows and every CTA collects the ranks' sums from
+// the local window (rank order). On return every thread holds the (peer-)global sums in out[].
+// History (profiles/r02/loop_trace_*.txt): 592 same-address atomics + last-CTA reduce + release
+// flag ~8 us per barrier; arrival records collected by CTA 0 + release record 5.2 us; this form
+// has one L2 round trip after the last arrival.
+constexpr int BAR_MAX_RECORDS = 1; // records per polling thread: grids up to blockDim.x CTAs
 template <int NV>
 __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], const LoopArgs& L,
                                                  const PeerView& P, unsigned int lepoch,
                                                  unsigned int pepoch, double* red,
                                                  double (&out)[NV > 0 ? NV : 1])
 {
-  __shared__ double bsum[2];
+  __shared__ double bsum[2][2]; // double-buffered by barrier parity: no trailing CTA barrier
   // Thread 0 may only arrive for the CTA once every thread of the CTA has finished the phase:
   // block_sum synchronises the CTA on its way; the plain barrier has to do it itself. (Found by
   // the host harness, tests/emu: without it a neighbour could pull p while it was being written.)
@@ -1028,56 +1048,67 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
   const bool peers = NV > 0 && P.nranks > 1;
   if (threadIdx.x == 0)
   {
-    __threadfence(); // the CTA's writes of this phase are ordered before its arrival record
+    fence_acq_rel_gpu(); // the CTA's writes of this phase are ordered before its arrival record
     ll_write(L.slots + 4 * static_cast<std::size_t>(blockIdx.x), lepoch, NV > 0 ? v[0] : 0.0,
              NV > 1 ? v[NV - 1] : 0.0);
   }
-  if (blockIdx.x == 0)
+  double a[BAR_MAX_RECORDS], b[BAR_MAX_RECORDS];
+  unsigned int todo = 0;
+#pragma unroll
+  for (int i = 0; i < BAR_MAX_RECORDS; ++i)
+    if (threadIdx.x + i * blockDim.x < gridDim.x)
+      todo |= 1u << i;
+  while (todo != 0u)
   {
-    double acc[2] = {0.0, 0.0};
-    for (unsigned int j = threadIdx.x; j < gridDim.x; j += blockDim.x)
-    {
-      double a, b;
-      ll_read(L.slots + 4 * static_cast<std::size_t>(j), lepoch, a, b);
-      acc[0] += a, acc[1] += b;
-    }
-    __syncthreads(); // red is reused
-    block_sum<2>(acc, red);
-    if (threadIdx.x == 0)
-    {
-      __threadfence(); // every arrival is ordered before the release
-      if (peers)
-        peer_publish(P, pepoch, acc[0], acc[1]);
-      ll_write(L.slots + 4 * static_cast<std::size_t>(gridDim.x), lepoch, acc[0], acc[1]);
-    }
+#pragma unroll
+    for (int i = 0; i < BAR_MAX_RECORDS; ++i)
+      if ((todo >> i) & 1u)
+      {
+        if (ll_try_read(L.slots + 4 * static_cast<std::size_t>(threadIdx.x + i * blockDim.x), lepoch, a[i], b[i]))
+          todo &= ~(1u << i);
+      }
   }
+  double acc[2] = {0.0, 0.0};
+  if constexpr (NV > 0)
+  {
+#pragma unroll
+    for (int i = 0; i < BAR_MAX_RECORDS; ++i)
+      if (threadIdx.x + i * blockDim.x < gridDim.x)
+        acc[0] += a[i], acc[1] += b[i];
+  }
+  __syncthreads(); // every record has been seen; red is free again
+  if constexpr (NV > 0)
+    block_sum<2>(acc, red);
+  const int par = lepoch & 1u;
   if (threadIdx.x == 0)
   {
-    double s0, s1;
+    double s0 = acc[0], s1 = acc[1];
     if (peers)
+    {
+      if (blockIdx.x == 0)
+        peer_publish(P, pepoch, s0, s1);
       peer_collect(P, pepoch, s0, s1); // rank order; contains this rank's own slot
-    else
-      ll_read(L.slots + 4 * static_cast<std::size_t>(gridDim.x), lepoch, s0, s1);
-    __threadfence(); // acquire: later loads (and the L1) must not see pre-barrier data
-    bsum[0] = s0, bsum[1] = s1;
+    }
+    fence_acq_rel_gpu(); // acquire: later loads (and the L1) must not see pre-barrier data
+    bsum[par][0] = s0, bsum[par][1] = s1;
   }
   __syncthreads();
   if constexpr (NV > 0)
   {
-    out[0] = bsum[0];
+    out[0] = bsum[par][0];
     if constexpr (NV > 1)
-      out[NV - 1] = bsum[1];
+      out[NV - 1] = bsum[par][1];
   }
-  __syncthreads(); // bsum is reused by the next call
 }
 
 template <int BS, bool FUSED, bool BAL = false>
-__global__ void __launch_bounds__(SPMV_THREADS, 4)
+__global__ void __launch_bounds__(LOOP_THREADS, LOOP_THREADS == 1024 ? 1 : 4)
 cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
 {
   __shared__ double red[64];
+  __shared__ BalShared<BS, BAL ? LOOP_THREADS / 32 : 1> bal_sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  constexpr int warps_per_cta = SPMV_THREADS / 32;
+  constexpr int warps_per_cta = LOOP_THREADS / 32;
   const SpmvArgs& A = L.A;
   const L2Plan LP = l2_plan(A);
   const bool first = blockIdx.x == 0 && threadIdx.x == 0;
@@ -1117,8 +1148,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
           while (!__all_sync(0xffffffffu, f >= hep));
         }
         if constexpr (balanced)
-          dotv = spmv_cta_balanced<BS, Ld::CG>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                               A.bal_begin[blockIdx.x + 1]);
+          dotv = spmv_cta_balanced<BS, Ld::CG, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                               A.bal_begin[blockIdx.x + 1], bal_sh);
         else
           for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
                s += FH.npull * warps_per_cta)
@@ -1127,7 +1158,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       else if constexpr (balanced)
       {
         const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
-        dotv = spmv_cta_balanced<BS, Ld::CA>(A, LP, L.p, L.y, FH.order, A.bal_begin[b], A.bal_begin[b + 1]);
+        dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh);
       }
       else
       {
@@ -1138,8 +1169,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       }
     }
     else if constexpr (balanced)
-      dotv = spmv_cta_balanced<BS, Ld::CA>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                           A.bal_begin[blockIdx.x + 1]);
+      dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                           A.bal_begin[blockIdx.x + 1], bal_sh);
     else
     {
       const std::int32_t stride = gridDim.x * warps_per_cta;
@@ -1276,7 +1307,7 @@ int cached_grid(ptb_ctx* c, int slot, K kernel, int threads, std::size_t smem, s
 // no roles. Sets A.ounit / A.bal_begin when the split applies: a problem small enough for slice
 // quantisation to matter (fewer than 8 slices per warp), big enough to give every warp work, block
 // rows or P1 rows (one batch of column deltas), at most BAL_MAX_SLICES slices per CTA.
-void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
+void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int warps_per_cta)
 {
   static const bool enabled = env_int("PTB_SPMV_BALANCE", 1) != 0;
   ptb_ctx::Balance& B = c->balance[which];
@@ -1285,7 +1316,8 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
   {
     B.grid = grid, B.npull = npull, B.compact = compact, B.ok = false;
     const std::int32_t S = A.n_slices;
-    const std::int64_t warps = static_cast<std::int64_t>(grid) * (SPMV_THREADS / 32);
+    const std::int64_t warps = static_cast<std::int64_t>(grid) * warps_per_cta;
+    const int max_run = BAL_SLICES_PER_WARP * warps_per_cta;
     // block rows only: the scalar variant (spmv_slice_part<1>, kept for the tests) lost against the
     // slice-per-warp kernel, whose delta-compressed column path it cannot use across a split
     // (Poisson 500 k DOFs: 30.8 vs 18.3 us, profiles/r02/ab_call7_summary.txt); PTB_SPMV_BALANCE=2 forces it
@@ -1317,7 +1349,7 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull)
           i = std::max(i, prev);
           if (t == ctas)
             i = b;
-          if (t > 0 && i - prev > BAL_MAX_SLICES)
+          if (t > 0 && i - prev > max_run)
             ok = false;
           begin.push_back(i);
           prev = i;
@@ -1389,7 +1421,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
     const int gbal = c->bs == 1 ? cached_grid(c, 16, spmv_sell<1, true, true>, SPMV_THREADS, 0, need)
                                 : cached_grid(c, 17, spmv_sell<3, true, true>, SPMV_THREADS, 0, need);
     FH.npull = pullers(gbal);
-    ensure_balance(c, A, 0, gbal, FH.npull);
+    ensure_balance(c, A, 0, gbal, FH.npull, SPMV_THREADS / 32);
     if (A.bal_begin != nullptr)
     {
       if (c->bs == 1)
@@ -1426,7 +1458,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   else if (c->bs == 1)
   {
     const int gbal = cached_grid(c, 18, spmv_sell<1, false, true>, SPMV_THREADS, 0, need);
-    ensure_balance(c, A, 0, gbal, -1);
+    ensure_balance(c, A, 0, gbal, -1, SPMV_THREADS / 32);
     if (A.bal_begin != nullptr)
       spmv_sell<1, false, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                       c->tickets.p, P, epoch, FH);
@@ -1437,7 +1469,7 @@ void launch_spmv(ptb_ctx* c, const double* p, double* y, CgState* st, unsigned i
   else
   {
     const int gbal = cached_grid(c, 19, spmv_sell<3, false, true>, SPMV_THREADS, 0, need);
-    ensure_balance(c, A, 0, gbal, -1);
+    ensure_balance(c, A, 0, gbal, -1, SPMV_THREADS / 32);
     if (A.bal_begin != nullptr)
       spmv_sell<3, false, true><<<gbal, SPMV_THREADS, 0, c->stream>>>(A, p, y, st, c->partials.p,
                                                                       c->tickets.p, P, epoch, FH);
@@ -1484,14 +1516,14 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   {
     // one grid for both instantiations: the smaller of their co-resident capacities
     int per_sm = 0, per_sm_bal = 0;
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, SPMV_THREADS, 0));
-    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bal, kernel_bal, SPMV_THREADS, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, LOOP_THREADS, 0));
+    PTB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_bal, kernel_bal, LOOP_THREADS, 0));
     c->grid_cache[slot] = c->num_sms * std::max(1, std::min(std::min(per_sm, per_sm_bal), 8));
     const int forced = env_int("PTB_LOOP_CTAS", 0); // A/B: must stay co-resident (cooperative launch)
     if (forced > 0)
       c->grid_cache[slot] = std::min(forced, c->grid_cache[slot]);
   }
-  const std::int64_t need = (c->n_slices + SPMV_THREADS / 32 - 1) / (SPMV_THREADS / 32);
+  const std::int64_t need = (c->n_slices + LOOP_THREADS / 32 - 1) / (LOOP_THREADS / 32);
   const int grid = static_cast<int>(std::max<std::int64_t>(1, std::min<std::int64_t>(need, c->grid_cache[slot])));
   if (fused_halo)
   {
@@ -1504,10 +1536,15 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     const double share = c->n_slices > 0
                              ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
                              : 0.0;
-    int npull = std::max(8, static_cast<int>(std::ceil(1.25 * share * grid)) + 4);
+    // 1024-thread CTAs: the ghost-reading share of the slices (+15 % for the pull itself), at least one
+    const int npull = std::max(LOOP_THREADS >= 1024 ? 1 : 8,
+                               static_cast<int>(std::ceil((LOOP_THREADS >= 1024 ? 1.15 : 1.25) * share * grid))
+                                   + (LOOP_THREADS >= 1024 ? 0 : 4));
     FH.npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
   }
-  ensure_balance(c, L.A, 1, grid, fused_halo ? FH.npull : -1);
+  ensure_balance(c, L.A, 1, grid, fused_halo ? FH.npull : -1, LOOP_THREADS / 32);
+  if (grid > BAR_MAX_RECORDS * LOOP_THREADS)
+    return false;
   if (c->loop_slots.n < static_cast<std::size_t>(grid + 1) * 4)
   {
     c->loop_slots.alloc(static_cast<std::size_t>(grid + 1) * 4);
@@ -1523,7 +1560,7 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   }
   void* args[] = {&L, &P, &FH};
   PTB_CUDA(cudaLaunchCooperativeKernel(L.A.bal_begin != nullptr ? kernel_bal : kernel, dim3(grid),
-                                       dim3(SPMV_THREADS), args, 0, c->stream));
+                                       dim3(LOOP_THREADS), args, 0, c->stream));
   c->launches += 1;
   if (trace_iter > 0)
   {

@@ -19,6 +19,21 @@ __device__ __forceinline__ void ll_write(unsigned long long* dst, unsigned int e
   st_relaxed_sys(dst + 2, (b1 & 0xffffffffull) | tag);
   st_relaxed_sys(dst + 3, (b1 >> 32) | tag);
 }
+/// One attempt: true (and the values) when all four words carry `epoch`.
+__device__ __forceinline__ bool ll_try_read(const unsigned long long* src, unsigned int epoch, double& v0, double& v1)
+{
+  unsigned long long w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    w[i] = ld_relaxed_sys(src + i);
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    ok = ok && static_cast<unsigned int>(w[i] >> 32) == epoch;
+  v0 = __longlong_as_double(static_cast<long long>((w[0] & 0xffffffffull) | (w[1] << 32)));
+  v1 = __longlong_as_double(static_cast<long long>((w[2] & 0xffffffffull) | (w[3] << 32)));
+  return ok;
+}
 /// Spin until all four words of the record carry `epoch`, then decode.
 __device__ __forceinline__ void ll_read(const unsigned long long* src, unsigned int epoch, double& v0, double& v1)
 {

@@ -34,6 +34,7 @@ __device__ __forceinline__ void st_release_gpu(unsigned long long* p, unsigned l
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) { return emu_ld(p, __ATOMIC_ACQUIRE); }
 __device__ __forceinline__ void st_release_gpu_u32(unsigned int* p, unsigned int v) { emu_st(p, v, __ATOMIC_RELEASE); }
 __device__ __forceinline__ double ld_ca_f64(const double* q) { return *reinterpret_cast<const volatile double*>(q); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 __device__ __forceinline__ unsigned long long l2_policy(int) { return 0ull; }
 __device__ __forceinline__ double ld_stream(const double* q, unsigned long long) { return *q; }
 __device__ __forceinline__ int ld_stream(const int* q, unsigned long long) { return *q; }
@@ -85,6 +86,11 @@ __device__ __forceinline__ double ld_ca_f64(const double* q)
   asm volatile("ld.global.ca.f64 %0, [%1];" : "=d"(v) : "l"(q));
   return v;
 }
+// fence.acq_rel.gpu: orders this thread's (and, through bar.sync, its CTA's) earlier accesses before
+// later ones at GPU scope and drops the L1 (CCTL.IVALL, B300_MICROARCH.md) -- what a grid barrier
+// needs, without the sequential-consistency round of __threadfence() (MEMBAR.SC).
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
 // L2 residency control for the operator stream ("L2 plan"). The matrix is read
 // once per CG iteration and never again before ~0.5-4 GB of other traffic has passed, while the
 // vectors (and a fixed prefix of the matrix, sized to what is left of the 126 MB L2) are re-read
