@@ -287,7 +287,7 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu):
     if world > 1 and comm_used == "peer":
         # the persistent CG loop pays below ~2 M DOFs per GPU; every rank must
         # take the same path, so the decision comes from the global size
-        ctx.set_cg_persistent(1 if ndofs_global / world <= 2_000_000 else 0)
+        ctx.set_cg_persistent(1 if P.bs == 3 and ndofs_global / world <= 3_000_000 else 0)
     nnz_local = ctx.nnz if device_setup else P.nnz
     nnz_global = allsum(float(nnz_local * P.bs * P.bs))
 

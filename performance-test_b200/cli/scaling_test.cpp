@@ -335,7 +335,8 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
   const std::int64_t nglob = ndofs_global;
   const int rank = boot.rank();
   const int world = boot.world();
-  SolverFunction solver_function = [gpu, kmax, rtol, pc, cgp, nglob, rank, world,
+  const bool block_rows = opt.problem_type == "elasticity"; // the loop pays for block rows
+  SolverFunction solver_function = [gpu, kmax, rtol, pc, cgp, nglob, rank, world, block_rows,
                                     &solve_seconds](Vector& u, const Vector& b) {
     ptb_ctx* c = gpu->c;
     int its = 0;
@@ -343,7 +344,7 @@ problem(const std::string& type, const BoxMesh& mesh, int order, const Options& 
     // across GPUs every rank must run the same form of the loop: decide from the global size
     // (include/ptb200.h ptb_set_cg_persistent); a single GPU decides by itself
     if (world > 1)
-      ok(c, ptb_set_cg_persistent(c, nglob / world <= 2000000 ? 1 : 0));
+      ok(c, ptb_set_cg_persistent(c, block_rows && nglob / world <= 3000000 ? 1 : 0));
     ok(c, ptb_set_rhs(c, b.array.data()));
     Timer tcg;
     ok(c, ptb_cg_solve(c, kmax, rtol, pc, &its, &rel));

@@ -883,14 +883,14 @@ int ptb_cg_solve(ptb_ctx* c, int kmax, double rtol, int precond, int* iterations
     // 2.5 M, 4 % slower at 10 M. PTB_CG_PERSISTENT=1 / 0 forces it on / off. Needs the assembled
     // operator and, across GPUs, the peer-memory path with the fused halo (no NCCL inside a kernel).
     static const int persistent_env = env_int("PTB_CG_PERSISTENT", -1);
-    const std::int64_t persistent_max = env_int("PTB_CG_PERSISTENT_MAX_DOFS", 2000000);
+    const std::int64_t persistent_max = env_int("PTB_CG_PERSISTENT_MAX_DOFS", 3000000);
     // Across GPUs every rank must take the same path (the two paths consume the peer epochs
     // differently), and the ranks' row counts differ: there the caller decides from the global size
     // (ptb_set_cg_persistent), here only a single GPU decides by itself.
     const bool persistent = persistent_env >= 0    ? persistent_env == 1
                             : c->cg_persistent >= 0 ? c->cg_persistent == 1
                             : c->nranks == 1 && !c->peer.enabled
-                                ? static_cast<std::int64_t>(c->n_owned) * c->bs <= persistent_max
+                                ? c->bs == 3 && static_cast<std::int64_t>(c->n_owned) * c->bs <= persistent_max
                                 : false;
     bool looped = false;
     if (persistent && !mf && kmax > 0 && (c->nranks == 1 || fused) && !c->nccl_comm)

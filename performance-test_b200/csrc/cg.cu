@@ -288,7 +288,8 @@ __device__ __forceinline__ double spmv_cta_balanced(const SpmvArgs& A, const L2P
                                                     double* __restrict__ y,
                                                     const std::int32_t* __restrict__ order,
                                                     std::int32_t i0, std::int32_t i1,
-                                                    BalShared<BS, W>& sh)
+                                                    BalShared<BS, W>& sh, std::int32_t& first_slice,
+                                                    int& first_kb)
 {
   constexpr int MAXS = BAL_SLICES_PER_WARP * W;
   std::int32_t* su = sh.su;
@@ -314,6 +315,9 @@ __device__ __forceinline__ double spmv_cta_balanced(const SpmvArgs& A, const L2P
   double pend[BS];
   int pend_j = -1;
   std::int32_t u = u0;
+  first_slice = -1, first_kb = 0; // where this warp's range starts (the loop's L2 prefetch uses it)
+  if (u0 < u1)
+    first_slice = order[i0 + j], first_kb = u0 - su[j];
   while (u < u1)
   {
     const int kb = u - su[j];
@@ -473,6 +477,8 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   double dotv = 0.0;
   constexpr bool balanced = BAL; // the host passes A.bal_begin / A.ounit with this instantiation
   __shared__ BalShared<BS, BAL ? SPMV_THREADS / 32 : 1> bal_sh;
+  [[maybe_unused]] std::int32_t pf_slice = -1;
+  [[maybe_unused]] int pf_kb = 0;
   if constexpr (FUSED)
   {
     if (blockIdx.x < FH.npull)
@@ -488,7 +494,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
       }
       if constexpr (balanced)
         dotv = spmv_cta_balanced<BS, Ld::CG, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
-                                             A.bal_begin[blockIdx.x + 1], bal_sh);
+                                             A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
       else
         for (std::int32_t it = FH.n_interior + blockIdx.x * warps_per_cta + warp; it < A.n_slices;
              it += FH.npull * warps_per_cta)
@@ -497,7 +503,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
     else if constexpr (balanced)
     {
       const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
-      dotv = spmv_cta_balanced<BS, Ld::NC, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh);
+      dotv = spmv_cta_balanced<BS, Ld::NC, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh, pf_slice, pf_kb);
     }
     else
     {
@@ -509,7 +515,7 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
   }
   else if constexpr (balanced)
     dotv = spmv_cta_balanced<BS, Ld::NC, SPMV_THREADS / 32>(A, LP, p, y, FH.order, A.bal_begin[blockIdx.x],
-                                         A.bal_begin[blockIdx.x + 1], bal_sh);
+                                         A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
   else
   {
     const std::int32_t stride = gridDim.x * warps_per_cta;
@@ -1005,7 +1011,39 @@ struct LoopArgs
   // direction done, barrier 3 passed. nullptr = no trace (one predictable branch per phase).
   unsigned long long* trace;
   int trace_iter;
+  int pf_bytes; // bytes of its matrix range every warp prefetches into L2 per iteration (0 = off)
 };
+
+// While the vectors are updated (L2-resident under strong scaling) and the CTAs wait in the grid
+// barriers, HBM idles: ~20 us of a ~105 us iteration at 1.25 M DOFs per GPU. Every warp uses that time
+// to pull the first pf_bytes of ITS range of the matrix (the same addresses every iteration) into L2
+// with prefetch.global.L2, one 128-byte line per lane and step; the next operator phase then starts on
+// L2 hits. [byte0, byte0 + nbytes) of the range that starts at entry kb of `slice`.
+template <int BS>
+__device__ __forceinline__ void prefetch_matrix_run(const SpmvArgs& A, std::int32_t slice, int kb, int lane,
+                                                    int byte0, int nbytes)
+{
+#ifndef PTB_HOST_EMU
+  if (slice < 0 || nbytes <= 0)
+    return;
+  const std::int64_t e0 = A.mat_off[slice] + static_cast<std::int64_t>(kb) * 32, e1 = A.mat_off[A.n_slices];
+  const char* v = reinterpret_cast<const char*>(A.vals + e0 * (BS * BS));
+  const char* vend = reinterpret_cast<const char*>(A.vals + e1 * (BS * BS));
+  for (int off = byte0 + lane * 128; off < byte0 + nbytes; off += 32 * 128)
+    if (v + off < vend)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(v + off));
+  if constexpr (BS == 3)
+  {
+    // the column indices of the same entries: 4 bytes per 72 bytes of values
+    const char* c = reinterpret_cast<const char*>(A.cols + e0);
+    const char* cend = reinterpret_cast<const char*>(A.cols + e1);
+    const int cb0 = byte0 / 18, cn = nbytes / 18;
+    for (int off = cb0 + lane * 128; off < cb0 + cn; off += 32 * 128)
+      if (c + off < cend)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(c + off));
+  }
+#endif
+}
 
 __device__ __forceinline__ void loop_stamp(const LoopArgs& L, int j, int slot)
 {
@@ -1116,6 +1154,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
   const std::int64_t tid = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
   const std::int64_t nthr = static_cast<std::int64_t>(gridDim.x) * blockDim.x;
   const unsigned long long halo0 = FH.epoch; // epoch of the launch that precedes this loop
+  [[maybe_unused]] std::int32_t pf_slice = -1; // start of this warp's matrix range (balanced split)
+  [[maybe_unused]] int pf_kb = 0;
 
   for (int j = 1; j <= L.n_it; ++j)
   {
@@ -1149,7 +1189,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
         }
         if constexpr (balanced)
           dotv = spmv_cta_balanced<BS, Ld::CG, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                               A.bal_begin[blockIdx.x + 1], bal_sh);
+                                               A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
         else
           for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
                s += FH.npull * warps_per_cta)
@@ -1158,7 +1198,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
       else if constexpr (balanced)
       {
         const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
-        dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh);
+        dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[b], A.bal_begin[b + 1], bal_sh, pf_slice, pf_kb);
       }
       else
       {
@@ -1170,7 +1210,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     }
     else if constexpr (balanced)
       dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                           A.bal_begin[blockIdx.x + 1], bal_sh);
+                                           A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
     else
     {
       const std::int32_t stride = gridDim.x * warps_per_cta;
@@ -1186,6 +1226,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     const double alpha = rz_old / py[0]; // cg.h:65
 
     // ---- phase 2: r -= alpha y (cg.h:71), local r.r and r.z (cg.h:74) -----------------------
+    if constexpr (BAL)
+      prefetch_matrix_run<BS>(A, pf_slice, pf_kb, lane, 0, L.pf_bytes / 2);
     double v2[2] = {0.0, 0.0};
     {
       const double2* y2 = reinterpret_cast<const double2*>(L.y);
@@ -1227,6 +1269,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     }
 
     // ---- phase 3: x += alpha p (cg.h:68), p = beta p + D^-1 r (cg.h:82) ------------------------
+    if constexpr (BAL)
+      prefetch_matrix_run<BS>(A, pf_slice, pf_kb, lane, L.pf_bytes / 2, L.pf_bytes - L.pf_bytes / 2);
     {
       const double2* r2 = reinterpret_cast<const double2*>(L.r);
       const double2* d2 = reinterpret_cast<const double2*>(L.dinv);
@@ -1551,6 +1595,9 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     c->loop_slots.zero(c->stream); // epoch 0 = never written; the host counter starts at 1
   }
   L.slots = c->loop_slots.p;
+  // L2 prefetch of the matrix during the vector phases (prefetch_matrix_run): KB per warp
+  static const int pf_kb_env = env_int("PTB_LOOP_PREFETCH_KB", 12);
+  L.pf_bytes = L.A.bal_begin != nullptr ? std::max(0, pf_kb_env) * 1024 : 0;
   static const int trace_iter = env_int("PTB_LOOP_TRACE", 0);
   if (trace_iter > 0)
   {
