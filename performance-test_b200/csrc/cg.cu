@@ -1084,11 +1084,12 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
   else
     __syncthreads();
   const bool peers = NV > 0 && P.nranks > 1;
+  constexpr int NW = NV == 0 ? 1 : NV == 1 ? 2 : 4; // words of the arrival record in use
   if (threadIdx.x == 0)
   {
     fence_acq_rel_gpu(); // the CTA's writes of this phase are ordered before its arrival record
-    ll_write(L.slots + 4 * static_cast<std::size_t>(blockIdx.x), lepoch, NV > 0 ? v[0] : 0.0,
-             NV > 1 ? v[NV - 1] : 0.0);
+    ll_write_n<NW>(L.slots + 4 * static_cast<std::size_t>(blockIdx.x), lepoch, NV > 0 ? v[0] : 0.0,
+                   NV > 1 ? v[NV - 1] : 0.0);
   }
   double a[BAR_MAX_RECORDS], b[BAR_MAX_RECORDS];
   unsigned int todo = 0;
@@ -1102,7 +1103,7 @@ __device__ __forceinline__ void grid_reduce_sync(double (&v)[NV > 0 ? NV : 1], c
     for (int i = 0; i < BAR_MAX_RECORDS; ++i)
       if ((todo >> i) & 1u)
       {
-        if (ll_try_read(L.slots + 4 * static_cast<std::size_t>(threadIdx.x + i * blockDim.x), lepoch, a[i], b[i]))
+        if (ll_try_read_n<NW>(L.slots + 4 * static_cast<std::size_t>(threadIdx.x + i * blockDim.x), lepoch, a[i], b[i]))
           todo &= ~(1u << i);
       }
   }
@@ -1595,8 +1596,11 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     c->loop_slots.zero(c->stream); // epoch 0 = never written; the host counter starts at 1
   }
   L.slots = c->loop_slots.p;
-  // L2 prefetch of the matrix during the vector phases (prefetch_matrix_run): KB per warp
-  static const int pf_kb_env = env_int("PTB_LOOP_PREFETCH_KB", 12);
+  // L2 prefetch of the matrix during the vector phases (prefetch_matrix_run): KB per warp. Measured
+  // and rejected (profiles/r02/ab_call11_summary.txt, elasticity 1.25 M DOFs, us per iteration:
+  // 0 KB 109.9, 6 KB 111.0, 12 KB 114.9, 20 KB 117.5, 32 KB 121.7): the operator phase does not get
+  // shorter and the vector phases, which run at the L2's bandwidth, get longer. Off by default.
+  static const int pf_kb_env = env_int("PTB_LOOP_PREFETCH_KB", 0);
   L.pf_bytes = L.A.bal_begin != nullptr ? std::max(0, pf_kb_env) * 1024 : 0;
   static const int trace_iter = env_int("PTB_LOOP_TRACE", 0);
   if (trace_iter > 0)

@@ -19,6 +19,38 @@ __device__ __forceinline__ void ll_write(unsigned long long* dst, unsigned int e
   st_relaxed_sys(dst + 2, (b1 & 0xffffffffull) | tag);
   st_relaxed_sys(dst + 3, (b1 >> 32) | tag);
 }
+/// The same record with only its first NW words in use (NW = 1: epoch only, a plain arrival;
+/// NW = 2: one double; NW = 4: two doubles) -- fewer L2 requests when 148 CTAs poll 148 records.
+template <int NW>
+__device__ __forceinline__ void ll_write_n(unsigned long long* dst, unsigned int epoch, double v0, double v1)
+{
+  const unsigned long long b0 = static_cast<unsigned long long>(__double_as_longlong(v0));
+  const unsigned long long b1 = static_cast<unsigned long long>(__double_as_longlong(v1));
+  const unsigned long long tag = static_cast<unsigned long long>(epoch) << 32;
+  st_relaxed_sys(dst + 0, (NW > 1 ? (b0 & 0xffffffffull) : 0ull) | tag);
+  if constexpr (NW > 1)
+    st_relaxed_sys(dst + 1, (b0 >> 32) | tag);
+  if constexpr (NW > 2)
+  {
+    st_relaxed_sys(dst + 2, (b1 & 0xffffffffull) | tag);
+    st_relaxed_sys(dst + 3, (b1 >> 32) | tag);
+  }
+}
+template <int NW>
+__device__ __forceinline__ bool ll_try_read_n(const unsigned long long* src, unsigned int epoch, double& v0, double& v1)
+{
+  unsigned long long w[4] = {0ull, 0ull, 0ull, 0ull};
+#pragma unroll
+  for (int i = 0; i < NW; ++i)
+    w[i] = ld_relaxed_sys(src + i);
+  bool ok = true;
+#pragma unroll
+  for (int i = 0; i < NW; ++i)
+    ok = ok && static_cast<unsigned int>(w[i] >> 32) == epoch;
+  v0 = __longlong_as_double(static_cast<long long>((w[0] & 0xffffffffull) | (w[1] << 32)));
+  v1 = __longlong_as_double(static_cast<long long>((w[2] & 0xffffffffull) | (w[3] << 32)));
+  return ok;
+}
 /// One attempt: true (and the values) when all four words carry `epoch`.
 __device__ __forceinline__ bool ll_try_read(const unsigned long long* src, unsigned int epoch, double& v0, double& v1)
 {
