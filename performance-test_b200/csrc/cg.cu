@@ -403,93 +403,52 @@ struct FusedHalo
 
 
 // The pull of one CTA's share of the receive list (generic Scatterer index lists) for halo epoch
-// `epoch` (the persistent loop advances the epoch per iteration), in two halves so that the NVLink
-// round trip (~2 us) can sit behind other work:
-//   begin   CTA 0 publishes "my p is complete"; every thread looks at the flag of the neighbour that
-//           owns its first PULL_EARLY entries ONCE and, where the neighbour is ready, issues the
-//           remote loads into registers -- nothing here waits;
-//   finish  entries whose neighbour was not ready yet (and any beyond PULL_EARLY per thread) are
-//           pulled now, waiting for the flag; the values are stored into the ghost part of p, the
-//           CTA's share is published in ready[blockIdx.x].
-constexpr int PULL_EARLY = 2;
-struct PullInFlight
-{
-  double val[PULL_EARLY];
-  unsigned int got;
-};
-
-__device__ __forceinline__ void halo_entry(const PeerHalo& H, std::int64_t i, int& nb, std::int64_t& dst,
-                                           const double*& src)
-{
-  const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
-  const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
-  nb = 0;
-  while (j >= H.recv_displ[nb + 1])
-    ++nb;
-  dst = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
-  src = H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c;
-}
-
-__device__ __forceinline__ PullInFlight halo_pull_begin(const PeerView& P, const FusedHalo& FH,
-                                                        unsigned long long epoch)
+// `epoch` (the persistent loop advances the epoch per iteration).
+__device__ __forceinline__ void halo_pull_share_at(const PeerView& P, const FusedHalo& FH,
+                                                   unsigned long long epoch)
 {
   const PeerHalo& H = FH.H;
   if (blockIdx.x == 0 && threadIdx.x < H.n_nbr)
   {
-    __threadfence_system(); // p was completed by the previous kernel / grid barrier: publish "ready"
+    __threadfence_system(); // p was completed by the previous kernel: publish "ready"
     st_release_sys(&P.win[H.nbr_rank[threadIdx.x]]->halo_flag[P.rank], epoch);
   }
-  PullInFlight F;
-  F.got = 0u;
-  const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
-  const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
-  const std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
-#pragma unroll
-  for (int u = 0; u < PULL_EARLY; ++u)
+  if (threadIdx.x < H.n_nbr)
   {
-    F.val[u] = 0.0;
-    const std::int64_t i = i0 + u * step;
-    if (i < n)
+    const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[threadIdx.x]];
+    while (ld_acquire_sys(flag) < epoch)
     {
-      int nb;
-      std::int64_t dst;
-      const double* src;
-      halo_entry(H, i, nb, dst, src);
-      if (ld_acquire_sys(&P.win[P.rank]->halo_flag[H.nbr_rank[nb]]) >= epoch)
-      {
-        F.val[u] = __ldcv(src);
-        F.got |= 1u << u;
-      }
     }
   }
-  return F;
-}
-
-__device__ __forceinline__ void halo_pull_finish(const PeerView& P, const FusedHalo& FH,
-                                                 unsigned long long epoch, const PullInFlight& F)
-{
-  const PeerHalo& H = FH.H;
+  __syncthreads();
+  constexpr int PULL_ILP = 4; // independent remote loads in flight per thread (NVLink ~2 us)
   const std::int64_t n = static_cast<std::int64_t>(H.recv_displ[H.n_nbr]) * H.bs;
   const std::int64_t step = static_cast<std::int64_t>(FH.npull) * blockDim.x;
-  const std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
-  for (std::int64_t i = i0, u = 0; i < n; i += step, ++u)
+  for (std::int64_t i0 = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x; i0 < n;
+       i0 += step * PULL_ILP)
   {
-    int nb;
-    std::int64_t dst;
-    const double* src;
-    halo_entry(H, i, nb, dst, src);
-    double v;
-    if (u < PULL_EARLY && ((F.got >> u) & 1u))
-      v = F.val[u];
-    else
+    double val[PULL_ILP];
+    std::int64_t dst[PULL_ILP];
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
     {
-      const unsigned long long* flag = &P.win[P.rank]->halo_flag[H.nbr_rank[nb]];
-      while (ld_acquire_sys(flag) < epoch)
+      const std::int64_t i = i0 + u * step;
+      dst[u] = -1;
+      if (i < n)
       {
+        const std::int32_t j = static_cast<std::int32_t>(i / H.bs);
+        const std::int32_t c = static_cast<std::int32_t>(i - static_cast<std::int64_t>(j) * H.bs);
+        int nb = 0;
+        while (j >= H.recv_displ[nb + 1])
+          ++nb;
+        dst[u] = static_cast<std::int64_t>(H.remote_indices[j]) * H.bs + c;
+        val[u] = __ldcv(H.peer_p[nb] + static_cast<std::int64_t>(H.src_index[j]) * H.bs + c);
       }
-      v = __ldcv(src);
     }
-    FH.pw[dst] = v;
+#pragma unroll
+    for (int u = 0; u < PULL_ILP; ++u)
+      if (dst[u] >= 0)
+        FH.pw[dst[u]] = val[u];
   }
   __syncthreads();
   if (threadIdx.x == 0)
@@ -497,14 +456,6 @@ __device__ __forceinline__ void halo_pull_finish(const PeerView& P, const FusedH
     __threadfence();
     st_release_gpu(&FH.ready[blockIdx.x], epoch);
   }
-}
-
-// Both halves back to back (the role-based kernels: the pullers have nothing else to do first).
-__device__ __forceinline__ void halo_pull_share_at(const PeerView& P, const FusedHalo& FH,
-                                                   unsigned long long epoch)
-{
-  const PullInFlight F = halo_pull_begin(P, FH, epoch);
-  halo_pull_finish(P, FH, epoch, F);
 }
 
 __device__ __forceinline__ void halo_pull_share(const PeerView& P, const FusedHalo& FH)
@@ -1226,16 +1177,16 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     constexpr bool balanced = BAL;
     if constexpr (FUSED && BAL)
     {
-      // No roles: every CTA issues the remote loads of its share of the ghost values (halo_pull_begin,
-      // nothing waits), works through its interior run with the NVLink round trip behind it, stores
-      // the values, waits for all shares and takes its run of ghost-reading slices. With puller CTAs the operator phase ended 15 us after its mean at 8 GPUs
+      // No roles: every CTA pulls its share of the ghost values first (the remote loads are in
+      // flight while it starts on its interior run), works through its interior run, and only then
+      // waits for all shares -- which landed ~80 us earlier -- and takes its run of ghost-reading
+      // slices. With puller CTAs the operator phase ended 15 us after its mean at 8 GPUs
       // (profiles/r02/multi_gpu/trace_8gpu_call12.txt): the pull and the L1-bypassing gathers of the
       // ghost-reading slices sat on the critical path of 19 of the 148 CTAs.
       const unsigned long long hep = halo0 + static_cast<unsigned long long>(j);
-      const PullInFlight pulled = halo_pull_begin(P, FH, hep); // FH.npull == gridDim.x
+      halo_pull_share_at(P, FH, hep); // FH.npull == gridDim.x
       dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
                                                            A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
-      halo_pull_finish(P, FH, hep, pulled);
       for (int base = 0; base < FH.npull; base += 32)
       {
         unsigned long long f;
