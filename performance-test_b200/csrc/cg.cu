@@ -1175,32 +1175,7 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     loop_stamp(L, j, 0);
     double dotv = 0.0;
     constexpr bool balanced = BAL;
-    if constexpr (FUSED && BAL)
-    {
-      // No roles: every CTA pulls its share of the ghost values first (the remote loads are in
-      // flight while it starts on its interior run), works through its interior run, and only then
-      // waits for all shares -- which landed ~80 us earlier -- and takes its run of ghost-reading
-      // slices. With puller CTAs the operator phase ended 15 us after its mean at 8 GPUs
-      // (profiles/r02/multi_gpu/trace_8gpu_call12.txt): the pull and the L1-bypassing gathers of the
-      // ghost-reading slices sat on the critical path of 19 of the 148 CTAs.
-      const unsigned long long hep = halo0 + static_cast<unsigned long long>(j);
-      halo_pull_share_at(P, FH, hep); // FH.npull == gridDim.x
-      dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                                           A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
-      for (int base = 0; base < FH.npull; base += 32)
-      {
-        unsigned long long f;
-        do
-          f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
-        while (!__all_sync(0xffffffffu, f >= hep));
-      }
-      std::int32_t s2 = -1;
-      int k2 = 0;
-      const int g0 = gridDim.x + 1 + blockIdx.x;
-      dotv += spmv_cta_balanced<BS, Ld::CG, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[g0],
-                                                            A.bal_begin[g0 + 1], bal_sh, s2, k2);
-    }
-    else if constexpr (FUSED)
+    if constexpr (FUSED)
     {
       const unsigned long long hep = halo0 + static_cast<unsigned long long>(j);
       if (blockIdx.x < FH.npull)
@@ -1213,9 +1188,19 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
             f = base + lane < FH.npull ? ld_acquire_gpu(&FH.ready[base + lane]) : ~0ull;
           while (!__all_sync(0xffffffffu, f >= hep));
         }
-        for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
-             s += FH.npull * warps_per_cta)
-          dotv += spmv_slice<BS, Ld::CG>(A, LP, L.p, L.y, FH.order[s], lane);
+        if constexpr (balanced)
+          dotv = spmv_cta_balanced<BS, Ld::CG, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                                               A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
+        else
+          for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
+               s += FH.npull * warps_per_cta)
+            dotv += spmv_slice<BS, Ld::CG>(A, LP, L.p, L.y, FH.order[s], lane);
+      }
+      else if constexpr (balanced)
+      {
+        const int b = FH.npull + 1 + (blockIdx.x - FH.npull);
+        dotv = spmv_cta_balanced<BS, Ld::CA, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[b],
+                                                             A.bal_begin[b + 1], bal_sh, pf_slice, pf_kb);
       }
       else
       {
@@ -1384,7 +1369,7 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
     // (Poisson 500 k DOFs: 30.8 vs 18.3 us, profiles/r02/ab_call7_summary.txt); PTB_SPMV_BALANCE=2 forces it
     static const bool scalar_too = env_int("PTB_SPMV_BALANCE", 1) == 2;
     const bool shape_ok = c->bs == 3 || (scalar_too && c->bs == 1 && c->max_w <= 32 && A.cdelta != nullptr);
-    if (enabled && shape_ok && S >= warps && S < 8 * warps && grid >= 1 && (npull < 0 || npull <= grid))
+    if (enabled && shape_ok && S >= warps && S < 8 * warps && grid >= 1 && (npull < 0 || npull < grid))
     {
       std::vector<std::int64_t> mo(static_cast<std::size_t>(S) + 1);
       std::vector<std::int32_t> order(S);
@@ -1416,14 +1401,7 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
           prev = i;
         }
       };
-      if (npull == grid)
-      {
-        // no roles (persistent loop): every CTA holds a run of interior slices, grid + 1 entries,
-        // and a run of ghost-reading slices, grid + 1 more
-        split(0, c->n_interior_slices, grid);
-        split(c->n_interior_slices, S, grid);
-      }
-      else if (npull >= 0)
+      if (npull >= 0)
       {
         split(c->n_interior_slices, S, std::max(npull, 1));
         split(0, c->n_interior_slices, grid - npull);
@@ -1604,22 +1582,17 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
     const double share = c->n_slices > 0
                              ? static_cast<double>(c->n_slices - c->n_interior_slices) / c->n_slices
                              : 0.0;
-    // 1024-thread CTAs: the ghost-reading share of the slices (+15 % for the pull itself), at least one
+    // 1024-thread CTAs: the ghost-reading share of the slices times PTB_PULL_FACTOR / 100 (default
+    // 1.40), at least one. The pullers start ~8 us late (neighbour flag + NVLink round trip) and
+    // gather p past L1, ~1.3 us per slice against 1.0 us for an interior slice: with 1.15 they ended
+    // the operator phase 15 us after the workers at 8 GPUs (profiles/r02/multi_gpu/trace_8gpu_call12.txt).
+    static const double pull_factor = env_int("PTB_PULL_FACTOR", 140) / 100.0;
     const int npull = std::max(LOOP_THREADS >= 1024 ? 1 : 8,
-                               static_cast<int>(std::ceil((LOOP_THREADS >= 1024 ? 1.15 : 1.25) * share * grid))
+                               static_cast<int>(std::ceil((LOOP_THREADS >= 1024 ? pull_factor : 1.25) * share * grid))
                                    + (LOOP_THREADS >= 1024 ? 0 : 4));
     FH.npull = std::max(1, std::min(std::min(npull, MAX_PULL), grid / 2));
   }
-  if (fused_halo && grid <= MAX_PULL)
-  {
-    // balanced instantiation: no roles, every CTA pulls a share (FH.npull = grid) and owns an interior
-    // run and a ghost run; when the split does not apply the role-based kernel above is launched
-    ensure_balance(c, L.A, 1, grid, grid, LOOP_THREADS / 32);
-    if (L.A.bal_begin != nullptr)
-      FH.npull = grid;
-  }
-  else if (!fused_halo)
-    ensure_balance(c, L.A, 1, grid, -1, LOOP_THREADS / 32);
+  ensure_balance(c, L.A, 1, grid, fused_halo ? FH.npull : -1, LOOP_THREADS / 32);
   if (grid > BAR_MAX_RECORDS * LOOP_THREADS)
     return false;
   if (c->loop_slots.n < static_cast<std::size_t>(grid + 1) * 4)

@@ -311,9 +311,7 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, 
     """Two ranks x two CTAs of cg_loop<BS, true>: CTA 0 of a rank is the puller (publishes 'p is
     ready', waits for the neighbour, pulls the ghost values out of the neighbour's vector, takes
     the ghost-reading slices), CTA 1 the worker; the dot products go through the LL windows. The
-    four CTAs are four copies of the harness running at once in one address space. balanced = True
-    is the instantiation without roles: both CTAs pull half of the ghost values, work through their
-    interior runs, wait for both shares and take their runs of ghost-reading slices."""
+    four CTAs are four copies of the harness running at once in one address space."""
     import threading
     rtol, grid, nranks = 1e-8, 2, 2
     G = pt.host.Problem(ptype, 1, *dims)
@@ -366,16 +364,15 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, 
     for q, d in enumerate(R):
         P, L = d["P"], d["L"]
         for g in range(grid):
-            # balanced instantiation: no roles, every CTA pulls a share (npull = grid); else CTA 0 pulls
             args = [P.bs, g, grid, q, nranks, win_ptrs, len(d["nbr"]), _p(d["nbr"]), _p(d["recv_displ"]),
-                    d["peer_p"], _p(d["remote"]), _p(d["src"]), d["n_int"], grid if balanced else 1, _p(d["ready"]),
+                    d["peer_p"], _p(d["remote"]), _p(d["src"]), d["n_int"], 1, _p(d["ready"]),
                     P.n_owned, L["n_slices"], _p(L["mat_off"]), _p(L["cols"]), _p(d["vals"]),
                     _p(d["cdelta"]), _p(d["colsx"]), _p(d["xoff"]), _p(d["order"]), _p(d["dinv"]),
                     _p(d["r"]), _p(d["p"]), _p(d["x"]), _p(d["y"]), _p(d["st"]), _p(d["slots"]), 500]
-            if balanced:   # every CTA: a run of interior slices, then a run of ghost-reading slices
+            if balanced:   # one puller (ghost-reading slices), one worker (interior slices)
                 if "ou" not in d:
                     d["ou"], d["begin"] = _balance_plan(L["mat_off"], d["order"],
-                                                        [(0, d["n_int"], grid), (d["n_int"], L["n_slices"], grid)])
+                                                        [(d["n_int"], L["n_slices"], 1), (0, d["n_int"], grid - 1)])
                     assert d["begin"] is not None
                 args += [_p(d["ou"]), _p(d["begin"])]
             else:
