@@ -207,7 +207,9 @@ def run_reference(args):
     pt = importlib.import_module("performance-test_b200")
     wl_name = args.workload or DEFAULT_HEADLINE
     wl = WORKLOADS[wl_name]
-    c = cpu_arm(pt, wl_name, args.gpus, args.steps, min(args.warmup, 1), args.cpu_kcap, args.ndofs)
+    # bounded: the whole --steps K run must end within minutes, so the iteration cap shrinks with K
+    kcap = max(10, min(args.cpu_kcap, 1000 // max(args.steps, 1)))
+    c = cpu_arm(pt, wl_name, args.gpus, args.steps, min(args.warmup, 1), kcap, args.ndofs)
     line = {
         "impl": "reference", "metric": "cg_dof_iters_per_s", "value": c["value"], "unit": "DOF-iters/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -222,7 +224,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
     }
     if args.workload is None and not args.no_secondary and args.gpus == 1:
-        s = cpu_arm(pt, DEFAULT_SECONDARY, 1, 1, 0, min(args.cpu_kcap, 100))
+        s = cpu_arm(pt, DEFAULT_SECONDARY, 1, 1, 0, min(kcap, 100))
         line["secondary"] = {"value": s["value"], "unit": "DOF-iters/s", "scaling": "weak",
                              "assembled_nnz_per_s": s["assembled_nnz_per_s"],
                              "cpu_baseline": {"value": s["value"], "unit": "DOF-iters/s",

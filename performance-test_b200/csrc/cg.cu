@@ -41,8 +41,11 @@ enum class Ld
 {
   NC,
   CG,
-  CA // coherent cached load (ld.global.ca): the vector changes inside a persistent kernel, L1
-     // lines are dropped by the acquire of the grid barrier, never served from the .nc path
+  CA, // coherent cached load (ld.global.ca): the vector changes inside a persistent kernel, L1
+      // lines are dropped by the acquire of the grid barrier, never served from the .nc path
+  MIX // ghost-reading slices of the persistent loop: owned entries through L1 (.ca), ghost entries
+      // (pulled by other CTAs of this very launch, index >= n_rows * BS) past it (.cg); a plain
+      // ldp<MIX> is the .ca load (used for the row's own entry, which is owned)
 };
 template <Ld L>
 __device__ __forceinline__ double ldp(const double* q)
@@ -53,6 +56,15 @@ __device__ __forceinline__ double ldp(const double* q)
     return __ldcg(q);
   else
     return ld_ca_f64(q);
+}
+// the same with the entry's index at hand (Ld::MIX needs it)
+template <Ld L>
+__device__ __forceinline__ double ldp_at(const double* base, std::int64_t i, std::int64_t ghost_from)
+{
+  if constexpr (L == Ld::MIX)
+    return i >= ghost_from ? __ldcg(base + i) : ld_ca_f64(base + i);
+  else
+    return ldp<L>(base + i);
 }
 
 // One SELL-32 slice: y[row] = sum_k vals * p[col]; returns this row's p.y contribution.
@@ -214,6 +226,7 @@ __device__ __forceinline__ void spmv_slice_part(const SpmvArgs& A, const L2Plan&
   const std::int64_t mo = A.mat_off[slice];
   const unsigned long long pol = mo < A.pin_entries ? LP.pinned : LP.stream;
   const std::int32_t row = slice * 32 + lane;
+  const std::int64_t ghost_from = static_cast<std::int64_t>(A.n_rows) * BS; // Ld::MIX
   if constexpr (BS == 1)
   {
     // rows of at most 32 stored entries (P1): one batch of column deltas
@@ -238,14 +251,14 @@ __device__ __forceinline__ void spmv_slice_part(const SpmvArgs& A, const L2Plan&
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u)
-        sum += vv[u] * ldp<L>(p + c[u]);
+        sum += vv[u] * ldp_at<L>(p, c[u], ghost_from);
     }
     for (; kk < ke; ++kk)
     {
       const std::int32_t d = __shfl_sync(0xffffffffu, dl, kk);
       const int rank = __popc(em & ((1u << kk) - 1u));
       const std::int32_t c = ((em >> kk) & 1u) ? ld_stream(xp + rank * 32, pol) : row + d;
-      sum += ld_stream(v + kk * 32, pol) * ldp<L>(p + c);
+      sum += ld_stream(v + kk * 32, pol) * ldp_at<L>(p, c, ghost_from);
     }
     s[0] = sum;
   }
@@ -262,7 +275,8 @@ __device__ __forceinline__ void spmv_slice_part(const SpmvArgs& A, const L2Plan&
 #pragma unroll
       for (int e = 0; e < 9; ++e)
         a[e] = ld_stream(v + e * 32, pol);
-      const double p0 = ldp<L>(p + 3 * c), p1 = ldp<L>(p + 3 * c + 1), p2 = ldp<L>(p + 3 * c + 2);
+      const double p0 = ldp_at<L>(p, 3 * c, ghost_from), p1 = ldp_at<L>(p, 3 * c + 1, ghost_from),
+                   p2 = ldp_at<L>(p, 3 * c + 2, ghost_from);
       s0 += a[0] * p0 + a[1] * p1 + a[2] * p2;
       s1 += a[3] * p0 + a[4] * p1 + a[5] * p2;
       s2 += a[6] * p0 + a[7] * p1 + a[8] * p2;
@@ -1189,8 +1203,8 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
           while (!__all_sync(0xffffffffu, f >= hep));
         }
         if constexpr (balanced)
-          dotv = spmv_cta_balanced<BS, Ld::CG, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
-                                                               A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
+          dotv = spmv_cta_balanced<BS, Ld::MIX, LOOP_THREADS / 32>(A, LP, L.p, L.y, FH.order, A.bal_begin[blockIdx.x],
+                                                                A.bal_begin[blockIdx.x + 1], bal_sh, pf_slice, pf_kb);
         else
           for (std::int32_t s = FH.n_interior + blockIdx.x * warps_per_cta + warp; s < A.n_slices;
                s += FH.npull * warps_per_cta)
