@@ -1026,6 +1026,11 @@ struct LoopArgs
   unsigned long long* trace;
   int trace_iter;
   int pf_bytes; // bytes of its matrix range every warp prefetches into L2 per iteration (0 = off)
+  // Resident vectors (balanced instantiation, runs of at most res_cap / (32 BS) slices): x and r of
+  // the CTA's own rows live in dynamic shared memory for the whole solve -- the vector phases run at
+  // the L2's bandwidth (120 MB per iteration in 9 us at 1.25 M DOFs), this takes 40 of their 96 B/DOF
+  // out of it. res_cap = entries per vector (0 = off); x is written back when the loop ends.
+  int res_cap;
 };
 
 // While the vectors are updated (L2-resident under strong scaling) and the CTAs wait in the grid
@@ -1160,6 +1165,11 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
 {
   __shared__ double red[64];
   __shared__ BalShared<BS, BAL ? LOOP_THREADS / 32 : 1> bal_sh;
+#ifdef PTB_HOST_EMU
+  static double loop_dsm[1 << 16];
+#else
+  extern __shared__ __align__(16) double loop_dsm[];
+#endif
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int warps_per_cta = LOOP_THREADS / 32;
   const SpmvArgs& A = L.A;
@@ -1171,6 +1181,31 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
   const unsigned long long halo0 = FH.epoch; // epoch of the launch that precedes this loop
   [[maybe_unused]] std::int32_t pf_slice = -1; // start of this warp's matrix range (balanced split)
   [[maybe_unused]] int pf_kb = 0;
+
+  // ---- resident x and r: this CTA's run of slices (the same every iteration) ------------------
+  constexpr int ROW = 32 * BS; // entries of one slice
+  [[maybe_unused]] double* x_sh = loop_dsm;
+  [[maybe_unused]] double* r_sh = loop_dsm + L.res_cap;
+  [[maybe_unused]] std::int32_t run0 = 0;
+  [[maybe_unused]] int run_entries = 0; // 0: vectors stay in global memory
+  if constexpr (BAL)
+  {
+    if (L.res_cap > 0)
+    {
+      int b = blockIdx.x;
+      if constexpr (FUSED)
+        b = blockIdx.x < FH.npull ? blockIdx.x : FH.npull + 1 + (blockIdx.x - FH.npull);
+      run0 = A.bal_begin[b];
+      run_entries = (A.bal_begin[b + 1] - run0) * ROW;
+      for (int idx = threadIdx.x; idx < run_entries; idx += blockDim.x)
+      {
+        const std::int64_t g = static_cast<std::int64_t>(FH.order[run0 + idx / ROW]) * ROW + idx % ROW;
+        x_sh[idx] = g < L.n ? __ldcg(L.x + g) : 0.0;
+        r_sh[idx] = g < L.n ? __ldcg(L.r + g) : 0.0;
+      }
+      __syncthreads();
+    }
+  }
 
   for (int j = 1; j <= L.n_it; ++j)
   {
@@ -1245,6 +1280,21 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     if constexpr (BAL)
       prefetch_matrix_run<BS>(A, pf_slice, pf_kb, lane, 0, L.pf_bytes / 2);
     double v2[2] = {0.0, 0.0};
+    if (BAL && run_entries > 0)
+    {
+      for (int idx = threadIdx.x; idx < run_entries; idx += blockDim.x)
+      {
+        const std::int64_t g = static_cast<std::int64_t>(FH.order[run0 + idx / ROW]) * ROW + idx % ROW;
+        if (g < L.n)
+        {
+          const double rr = -alpha * __ldcg(L.y + g) + r_sh[idx];
+          r_sh[idx] = rr;
+          v2[0] += rr * rr;
+          v2[1] += rr * (__ldg(L.dinv + g) * rr);
+        }
+      }
+    }
+    else
     {
       const double2* y2 = reinterpret_cast<const double2*>(L.y);
       const double2* d2 = reinterpret_cast<const double2*>(L.dinv);
@@ -1287,6 +1337,21 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     // ---- phase 3: x += alpha p (cg.h:68), p = beta p + D^-1 r (cg.h:82) ------------------------
     if constexpr (BAL)
       prefetch_matrix_run<BS>(A, pf_slice, pf_kb, lane, L.pf_bytes / 2, L.pf_bytes - L.pf_bytes / 2);
+    if (BAL && run_entries > 0)
+    {
+      for (int idx = threadIdx.x; idx < run_entries; idx += blockDim.x)
+      {
+        const std::int64_t g = static_cast<std::int64_t>(FH.order[run0 + idx / ROW]) * ROW + idx % ROW;
+        if (g < L.n)
+        {
+          const double pp = __ldcg(L.p + g);
+          x_sh[idx] = alpha * pp + x_sh[idx];
+          if (!converged)
+            L.p[g] = beta * pp + __ldg(L.dinv + g) * r_sh[idx];
+        }
+      }
+    }
+    else
     {
       const double2* r2 = reinterpret_cast<const double2*>(L.r);
       const double2* d2 = reinterpret_cast<const double2*>(L.dinv);
@@ -1318,6 +1383,17 @@ cg_loop(LoopArgs L, PeerView P, FusedHalo FH)
     loop_stamp(L, j, 5);
     grid_reduce_sync<0>(none, L, P, la + 2u, 0u, red, none_out);
     loop_stamp(L, j, 6);
+  }
+  if (BAL && run_entries > 0)
+  {
+    // the loop is over (converged or kmax): the solution and the residual go back to global memory
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < run_entries; idx += blockDim.x)
+    {
+      const std::int64_t g = static_cast<std::int64_t>(FH.order[run0 + idx / ROW]) * ROW + idx % ROW;
+      if (g < L.n)
+        L.x[g] = x_sh[idx], L.r[g] = r_sh[idx];
+    }
   }
 }
 
@@ -1396,6 +1472,7 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
         ou[i + 1] = ou[i] + static_cast<std::int32_t>((mo[order[i] + 1] - mo[order[i]]) >> 5);
       std::vector<std::int32_t> begin;
       bool ok = true;
+      int longest = 0;
       auto split = [&](std::int32_t a, std::int32_t b, int ctas) {
         // boundaries at the slice edges nearest to the equal-unit cuts
         const std::int64_t lo = ou[a], len = ou[b] - ou[a];
@@ -1411,6 +1488,8 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
             i = b;
           if (t > 0 && i - prev > max_run)
             ok = false;
+          if (t > 0)
+            longest = std::max(longest, i - prev);
           begin.push_back(i);
           prev = i;
         }
@@ -1428,6 +1507,7 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
         B.begin.upload(begin, c->stream);
         PTB_CUDA(cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
         B.ok = true;
+        B.longest_run = longest;
       }
     }
   }
@@ -1621,6 +1701,23 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   // shorter and the vector phases, which run at the L2's bandwidth, get longer. Off by default.
   static const int pf_kb_env = env_int("PTB_LOOP_PREFETCH_KB", 0);
   L.pf_bytes = L.A.bal_begin != nullptr ? std::max(0, pf_kb_env) * 1024 : 0;
+  // x and r resident in shared memory when every CTA's run fits (LoopArgs::res_cap)
+  static const bool resident_env = env_flag("PTB_LOOP_RESIDENT", true);
+  std::size_t dyn_smem = 0;
+  L.res_cap = 0;
+  if (L.A.bal_begin != nullptr && resident_env)
+  {
+    const std::size_t cap = static_cast<std::size_t>(c->balance[1].longest_run) * 32 * c->bs;
+    cudaFuncAttributes fa{};
+    PTB_CUDA(cudaFuncGetAttributes(&fa, kernel_bal));
+    if (cap > 0 && 2 * cap * sizeof(double) + fa.sharedSizeBytes + 1024 <= 227u * 1024u)
+    {
+      dyn_smem = 2 * cap * sizeof(double);
+      L.res_cap = static_cast<int>(cap);
+      PTB_CUDA(cudaFuncSetAttribute(kernel_bal, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(dyn_smem)));
+    }
+  }
   static const int trace_iter = env_int("PTB_LOOP_TRACE", 0);
   if (trace_iter > 0)
   {
@@ -1630,7 +1727,7 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   }
   void* args[] = {&L, &P, &FH};
   PTB_CUDA(cudaLaunchCooperativeKernel(L.A.bal_begin != nullptr ? kernel_bal : kernel, dim3(grid),
-                                       dim3(LOOP_THREADS), args, 0, c->stream));
+                                       dim3(LOOP_THREADS), args, dyn_smem, c->stream));
   c->launches += 1;
   if (trace_iter > 0)
   {

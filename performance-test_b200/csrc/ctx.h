@@ -144,6 +144,7 @@ struct ptb_ctx
   {
     int grid = -1, npull = -2;
     bool compact = false, ok = false;
+    int longest_run = 0; // slices of the longest CTA run
     ptb::DevBuf<std::int32_t> ounit, begin;
   } balance[2];
   ptb::DevBuf<std::int32_t> slice_order; // slices without ghost columns first (fused halo)

@@ -105,7 +105,7 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
                       const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                       const int32_t* order, const double* dinv, double* r, double* p, double* x,
                       double* y, void* st, unsigned long long* slots, int n_it,
-                      const int32_t* ounit, const int32_t* bal_begin)
+                      const int32_t* ounit, const int32_t* bal_begin, int res_cap)
 {
   using namespace ptb;
   LoopArgs L{};
@@ -115,6 +115,7 @@ int emu_cg_loop_block(int bs, int block, int grid, int32_t n_rows, int32_t n_sli
   L.st = static_cast<CgState*>(st);
   L.slots = slots;
   L.it0 = 0, L.n_it = n_it, L.ebase = 1, L.lbase = 1;
+  L.res_cap = bal_begin != nullptr ? res_cap : 0; // x and r of the CTA's run resident in "shared memory"
   PeerView P{};
   P.rank = 0, P.nranks = 1;
   FusedHalo FH{};
@@ -156,7 +157,7 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
                            const int32_t* cdelta, const int32_t* colsx, const int64_t* xoff,
                            const int32_t* order, const double* dinv, double* r, double* p,
                            double* x, double* y, void* st, unsigned long long* slots, int n_it,
-                           const int32_t* ounit, const int32_t* bal_begin)
+                           const int32_t* ounit, const int32_t* bal_begin, int res_cap)
 {
   using namespace ptb;
   LoopArgs L{};
@@ -166,6 +167,7 @@ int emu_cg_loop_block_peer(int bs, int block, int grid, int rank, int nranks, vo
   L.st = static_cast<CgState*>(st);
   L.slots = slots;
   L.it0 = 0, L.n_it = n_it, L.ebase = 1, L.lbase = 1;
+  L.res_cap = bal_begin != nullptr ? res_cap : 0; // x and r of the CTA's run resident in "shared memory"
   PeerView P{};
   P.rank = rank, P.nranks = nranks;
   for (int q = 0; q < nranks; ++q)

@@ -249,7 +249,7 @@ def _balance_plan(mat_off, order, groups):
     return ou, np.array(begin, dtype=np.int32)
 
 
-@pytest.mark.parametrize("balanced", [False, True])
+@pytest.mark.parametrize("balanced", [False, True, "resident"])
 @pytest.mark.parametrize("ptype,dims,precond,grid", [("poisson", (6, 5, 7), "jacobi", 3),
                                                      ("poisson", (6, 5, 7), "none", 1),
                                                      ("poisson", (9, 2, 2), "jacobi", 4),
@@ -257,7 +257,8 @@ def _balance_plan(mat_off, order, groups):
 def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptype, dims, precond, grid,
                                                          balanced):
     """balanced = True runs the instantiation that cuts the CTA's slices into equal k-step ranges per
-    warp (spmv_cta_balanced): slices split between warps are summed through shared memory."""
+    warp (spmv_cta_balanced): slices split between warps are summed through shared memory;
+    "resident" additionally keeps x and r of the CTA's own rows in shared memory for the whole solve."""
     import threading
     P = pt.host.Problem(ptype, 1, *dims)
     bs, n, rtol = P.bs, P.n_owned * P.bs, 1e-8
@@ -289,7 +290,10 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
             _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(slots), 500]
     ou, begin = _balance_plan(L["mat_off"], order, [(0, L["n_slices"], grid)]) if balanced else (None, None)
     assert not balanced or begin is not None
-    args += [_p(ou) if balanced else None, _p(begin) if balanced else None]
+    res_cap = 0
+    if balanced == "resident":
+        res_cap = int(np.diff(begin).max()) * 32 * bs
+    args += [_p(ou) if balanced else None, _p(begin) if balanced else None, res_cap]
     threads = [threading.Thread(target=emucg[g].emu_cg_loop_block, args=[bs, g, grid] + args)
                for g in range(grid)]
     for t in threads:
@@ -305,7 +309,7 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
     assert np.all(slots[: 4 * grid: 4] >> np.uint64(32) == np.uint64(3 * int(fin["k"])))
 
 
-@pytest.mark.parametrize("balanced", [False, True])
+@pytest.mark.parametrize("balanced", [False, True, "resident"])
 @pytest.mark.parametrize("ptype,dims", [("poisson", (4, 3, 9)), ("elasticity", (2, 3, 5))])
 def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, balanced):
     """Two ranks x two CTAs of cg_loop<BS, true>: CTA 0 of a rank is the puller (publishes 'p is
@@ -374,9 +378,10 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, 
                     d["ou"], d["begin"] = _balance_plan(L["mat_off"], d["order"],
                                                         [(d["n_int"], L["n_slices"], 1), (0, d["n_int"], grid - 1)])
                     assert d["begin"] is not None
-                args += [_p(d["ou"]), _p(d["begin"])]
+                runs = np.concatenate([np.diff(d["begin"][:2]), np.diff(d["begin"][2:])])
+                args += [_p(d["ou"]), _p(d["begin"]), int(runs.max()) * 32 * P.bs if balanced == "resident" else 0]
             else:
-                args += [None, None]
+                args += [None, None, 0]
             threads.append(threading.Thread(target=emucg[q * grid + g].emu_cg_loop_block_peer, args=args))
     for t in threads:
         t.start()
