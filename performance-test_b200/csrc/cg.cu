@@ -1026,10 +1026,10 @@ struct LoopArgs
   unsigned long long* trace;
   int trace_iter;
   int pf_bytes; // bytes of its matrix range every warp prefetches into L2 per iteration (0 = off)
-  // Resident vectors (balanced instantiation, runs of at most res_cap / (32 BS) slices): x and r of
-  // the CTA's own rows live in dynamic shared memory for the whole solve -- the vector phases run at
-  // the L2's bandwidth (120 MB per iteration in 9 us at 1.25 M DOFs), this takes 40 of their 96 B/DOF
-  // out of it. res_cap = entries per vector (0 = off); x is written back when the loop ends.
+  // Resident vectors (balanced instantiation, runs of at most res_cap / (32 BS) slices; opt-in,
+  // measured slower, see launch_cg_loop): x and r of the CTA's own rows live in dynamic shared memory
+  // for the whole solve, which takes 40 of the vector phases' 96 B/DOF out of the L2 traffic.
+  // res_cap = entries per vector (0 = off); x and r are written back when the loop ends.
   int res_cap;
 };
 
@@ -1701,8 +1701,12 @@ bool launch_cg_loop(ptb_ctx* c, const double* dinv, int it0, int n_it, unsigned 
   // shorter and the vector phases, which run at the L2's bandwidth, get longer. Off by default.
   static const int pf_kb_env = env_int("PTB_LOOP_PREFETCH_KB", 0);
   L.pf_bytes = L.A.bal_begin != nullptr ? std::max(0, pf_kb_env) * 1024 : 0;
-  // x and r resident in shared memory when every CTA's run fits (LoopArgs::res_cap)
-  static const bool resident_env = env_flag("PTB_LOOP_RESIDENT", true);
+  // x and r resident in shared memory when every CTA's run fits (LoopArgs::res_cap). Measured and
+  // rejected (profiles/r02/ab_call18_resident.txt, elasticity 1.25 M DOFs): 109.4 us per iteration
+  // without, 126.5 us with -- the 190 KB of dynamic shared memory leave ~30 KB of the SM's 256 KB for
+  // L1, and the operator phase, whose gathers of p live on L1 hits, grows from 84 to 101 us; the
+  // vector phases gain 1 us. Off by default (PTB_LOOP_RESIDENT=1 switches it on).
+  static const bool resident_env = env_flag("PTB_LOOP_RESIDENT", false);
   std::size_t dyn_smem = 0;
   L.res_cap = 0;
   if (L.A.bal_begin != nullptr && resident_env)
