@@ -11,6 +11,7 @@
 // Replaces the generated tabulate_tensor kernels of Poisson.py:31-32 for degree 2 and 3 and the
 // DOLFINx insertion loop (poisson_problem.cpp:129-137,150-155).
 #include "element_tables.h"
+#include <algorithm>
 #include "envopt.h"
 #include "kernels.h"
 
@@ -251,6 +252,180 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
     A.dinv[row] = 1.0 / diag;
 }
 
+// ------------------------------------------------------------------------------------------
+// Linear elasticity on P2 / P3 (Elasticity.py:22-43 with degree 2, 3; the reference's CI runs
+// `--problem_type elasticity --order 3`, .github/workflows/ccpp.yml:165-181). Blocked element,
+// local index 3 i + a. With u_a[c] = K[c][a] (K = J^-1) and the unsymmetrised reference tensors
+// KF[cd][i][j] = int d_c phi_i d_d phi_j (element_tables.h):
+//     M^{ab}_ij = |det| sum_cd u_a[c] u_b[d] KF[cd][i][j]            ( = int d_a phi_i d_b phi_j )
+//     A[(i,a),(j,b)] = mu (delta_ab sum_c M^{cc}_ij + M^{ba}_ij) + lambda M^{ab}_ij
+// (SURVEY K5 for general degree; checked against the oracle's quadrature kernel to 1e-15).
+// One warp = (slice, component a) as in the P1 elasticity kernels: the thread owns scalar row
+// 3 row + a and accumulates the three entries (b = 0, 1, 2) of each stored block; launched per
+// row-length bin, bin_w * 768 B of accumulators per warp. sum_c M^{cc} comes from the symmetrised
+// tensors S and G = |det| K K^T exactly as in the scalar kernel.
+// ------------------------------------------------------------------------------------------
+template <int ND, bool WIDE>
+__global__ void assemble_matrix_pk3_binned(MatrixArgs A, const double* __restrict__ Sg,
+                                           const double* __restrict__ KFg,
+                                           const std::int32_t* __restrict__ slice_list,
+                                           std::int32_t n_list, int bin_w)
+{
+  constexpr int NW = WIDE ? (ND + 1) / 2 : (ND + 3) / 4;
+  constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
+  constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
+  extern __shared__ double smem[];
+  double* St = smem;                 // [6][ND][ND]
+  double* Kt = smem + 6 * ND * ND;   // [9][ND][ND]
+  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
+    St[i] = Sg[i];
+  for (int i = threadIdx.x; i < 9 * ND * ND; i += blockDim.x)
+    Kt[i] = KFg[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const std::int32_t item = blockIdx.x * nwarps + warp;
+  if (item >= 3 * n_list)
+    return;
+  const std::int32_t slice = slice_list[item / 3];
+  const int a = item % 3;
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const std::int64_t mo = A.mat_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const std::int64_t ao = A.adj_off[slice];
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  double* acc = smem + 15 * ND * ND + static_cast<std::size_t>(warp) * bin_w * 96; // [k][b][lane]
+  for (int k = 0; k < 3 * w; ++k)
+    acc[k * 32 + lane] = 0.0;
+  __syncwarp();
+
+  for (int k = 0; k < wa; ++k)
+  {
+    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+    if (pair == ADJ_INVALID_DEV)
+      continue;
+    std::uint32_t words[NW];
+#pragma unroll
+    for (int q = 0; q < NW; ++q)
+      words[q] = A.adjso[(ao + k * 32) * NW + q * 32 + lane];
+    const std::uint32_t cell = pair / ND;
+    const int li = pair - cell * ND;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    const Vec3 X0 = load_point(A.xyz, v.x);
+    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+               e3 = load_point(A.xyz, v.w) - X0;
+    // rows of K = J^-1 are the cofactor vectors c_c / det
+    const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+    const double det = dot(e1, c1);
+    const double idet = 1.0 / det, s = fabs(det), inv = 1.0 / s;
+    const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
+                 G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+    // u_b[c] = K[c][b];  ua = u_a,  su[b] = |det| u_b
+    const double kx[3] = {c1.x * idet, c2.x * idet, c3.x * idet}; // u_0
+    const double ky[3] = {c1.y * idet, c2.y * idet, c3.y * idet}; // u_1
+    const double kz[3] = {c1.z * idet, c2.z * idet, c3.z * idet}; // u_2
+    const double* ua = a == 0 ? kx : a == 1 ? ky : kz;
+    const double ua0 = ua[0], ua1 = ua[1], ua2 = ua[2];
+    const double* S = St + li * ND;
+    const double* F = Kt + li * ND;
+#pragma unroll 2
+    for (int j = 0; j < ND; ++j)
+    {
+      const double kij = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j] + G02 * S[2 * ND * ND + j]
+                         + G11 * S[3 * ND * ND + j] + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+      double f[9];
+#pragma unroll
+      for (int q = 0; q < 9; ++q)
+        f[q] = F[q * ND * ND + j]; // KF[c][d], q = 3 c + d
+      // z_d = sum_c u_a[c] KF[c][d]  (M^{ab} = |det| z . u_b);  t_c = sum_d KF[c][d] u_a[d]  (M^{ba} = |det| u_b . t)
+      const double z0 = ua0 * f[0] + ua1 * f[3] + ua2 * f[6], z1 = ua0 * f[1] + ua1 * f[4] + ua2 * f[7],
+                   z2 = ua0 * f[2] + ua1 * f[5] + ua2 * f[8];
+      const double t0 = f[0] * ua0 + f[1] * ua1 + f[2] * ua2, t1 = f[3] * ua0 + f[4] * ua1 + f[5] * ua2,
+                   t2 = f[6] * ua0 + f[7] * ua1 + f[8] * ua2;
+      const double mab0 = s * (z0 * kx[0] + z1 * kx[1] + z2 * kx[2]), mba0 = s * (kx[0] * t0 + kx[1] * t1 + kx[2] * t2);
+      const double mab1 = s * (z0 * ky[0] + z1 * ky[1] + z2 * ky[2]), mba1 = s * (ky[0] * t0 + ky[1] * t1 + ky[2] * t2);
+      const double mab2 = s * (z0 * kz[0] + z1 * kz[1] + z2 * kz[2]), mba2 = s * (kz[0] * t0 + kz[1] * t1 + kz[2] * t2);
+      double* dst = acc + slot_of<ND, WIDE>(words, j) * 96 + lane;
+      dst[0] += mu * ((a == 0 ? kij : 0.0) + mba0) + lmbda * mab0;
+      dst[32] += mu * ((a == 1 ? kij : 0.0) + mba1) + lmbda * mab1;
+      dst[64] += mu * ((a == 2 ? kij : 0.0) + mba2) + lmbda * mab2;
+    }
+  }
+
+  const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
+  const bool bc_row = live && A.bc[row];
+  double diag = 1.0;
+  for (int k = 0; k < w; ++k)
+  {
+    const std::int32_t col = A.cols[mo + k * 32 + lane];
+    const bool real = k < len;
+    const bool own = real && col == row;
+    const bool dirichlet = bc_row || (real && A.bc[col]);
+#pragma unroll
+    for (int b = 0; b < 3; ++b)
+    {
+      double val = acc[(k * 3 + b) * 32 + lane];
+      if (dirichlet)
+        val = own && a == b ? 1.0 : 0.0;
+      if (!real)
+        val = 0.0;
+      A.vals[(mo + k * 32) * 9 + (3 * a + b) * 32 + lane] = val;
+      if (own && a == b)
+        diag = val;
+    }
+  }
+  if (live)
+    A.dinv[static_cast<std::int64_t>(row) * 3 + a] = 1.0 / diag;
+}
+
+// L = f . v dx for the blocked P2 / P3 space (Elasticity.py:40): be[(i,a)] = |det| sum_j M[i][j] f_j[a].
+template <int ND>
+__global__ void __launch_bounds__(PK_THREADS)
+assemble_vector_pk3(VectorArgs A, const double* __restrict__ Mg)
+{
+  __shared__ double Mt[ND * ND];
+  for (int i = threadIdx.x; i < ND * ND; i += blockDim.x)
+    Mt[i] = Mg[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int32_t row = slice * 32 + lane;
+  if (row >= A.n_rows)
+    return;
+  const std::int64_t ao = A.adj_off[slice];
+  const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < wa; ++k)
+  {
+    const std::uint32_t pair = A.adj[ao + k * 32 + lane];
+    if (pair == ADJ_INVALID_DEV)
+      break; // lists are front-packed
+    const std::uint32_t cell = pair / ND;
+    const int li = pair - cell * ND;
+    const int4 v = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+    const Vec3 X0 = load_point(A.xyz, v.x);
+    const Vec3 e1 = load_point(A.xyz, v.y) - X0, e2 = load_point(A.xyz, v.z) - X0,
+               e3 = load_point(A.xyz, v.w) - X0;
+    const double det = fabs(dot(e1, cross(e2, e3)));
+    const std::int32_t* dofs = A.dofmap + static_cast<std::int64_t>(cell) * ND;
+    double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < ND; ++j)
+    {
+      const double m = Mt[li * ND + j];
+      const double* fj = A.f + 3 * static_cast<std::int64_t>(__ldg(dofs + j));
+      t0 += m * __ldg(fj), t1 += m * __ldg(fj + 1), t2 += m * __ldg(fj + 2);
+    }
+    s0 += det * t0, s1 += det * t1, s2 += det * t2;
+  }
+  const bool bc = A.bc[row];
+  double* b = A.b + 3 * static_cast<std::int64_t>(row);
+  b[0] = bc ? 0.0 : s0, b[1] = bc ? 0.0 : s1, b[2] = bc ? 0.0 : s2;
+}
+
 template <int ND>
 __global__ void __launch_bounds__(PK_THREADS)
 assemble_vector_pk(VectorArgs A, const double* __restrict__ Mg)
@@ -409,6 +584,7 @@ void ensure_tables(ptb_ctx* c)
   c->tab_S.upload(p2 ? tables::S_P2 : tables::S_P3, 6 * nd * nd, c->stream);
   c->tab_M.upload(p2 ? tables::M_P2 : tables::M_P3, nd * nd, c->stream);
   c->tab_MF.upload(p2 ? tables::MF_P2 : tables::MF_P3, 4 * nd * nd, c->stream);
+  c->tab_KF.upload(p2 ? tables::KF_P2 : tables::KF_P3, 9 * nd * nd, c->stream);
   c->tab_order = c->order;
 }
 
@@ -436,9 +612,43 @@ void launch_matrix_bins(ptb_ctx* c, const MatrixArgs& A)
   }
 }
 
+template <int ND, bool WIDE>
+void launch_matrix3_bins(ptb_ctx* c, const MatrixArgs& A)
+{
+  if (c->pk_bin_slices.p == nullptr)
+    throw std::runtime_error("assemble_matrix: the elasticity P2/P3 kernel needs the row-length bins");
+  PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk3_binned<ND, WIDE>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  for (std::size_t b = 0; b + 1 < c->pk_bin_off.size(); ++b)
+  {
+    const std::int32_t n = c->pk_bin_off[b + 1] - c->pk_bin_off[b];
+    if (n == 0)
+      continue;
+    const int bin_w = c->pk_bin_w[b];
+    const std::size_t tables_bytes = static_cast<std::size_t>(15) * ND * ND * sizeof(double);
+    const std::size_t per_warp = static_cast<std::size_t>(bin_w) * 96 * sizeof(double);
+    if (tables_bytes + per_warp > 227 * 1024)
+      throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
+    const int warps = static_cast<int>(std::min<std::size_t>(4, (227 * 1024 - tables_bytes) / per_warp));
+    const std::int64_t items = static_cast<std::int64_t>(n) * 3;
+    const int grid = static_cast<int>((items + warps - 1) / warps);
+    assemble_matrix_pk3_binned<ND, WIDE><<<grid, warps * 32, tables_bytes + per_warp * warps, c->stream>>>(
+        A, c->tab_S.p, c->tab_KF.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
+    PTB_CUDA(cudaGetLastError());
+  }
+}
+
 template <int ND>
 void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
 {
+  if (c->bs == 3)
+  {
+    if (c->so_bits == 8)
+      launch_matrix3_bins<ND, false>(c, A);
+    else
+      launch_matrix3_bins<ND, true>(c, A);
+    return;
+  }
   if (env_flag("PTB_PK_BINS", true) && c->pk_bin_slices.p != nullptr)
   {
     if (c->so_bits == 8)
@@ -472,8 +682,6 @@ void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
 
 void launch_assemble_matrix_pk(ptb_ctx* c, const MatrixArgs& A)
 {
-  if (c->bs != 1)
-    throw std::runtime_error("assemble_matrix: order > 1 is built for the scalar Poisson space only");
   ensure_tables(c);
   if (c->order == 2)
     launch_matrix<10>(c, A);
@@ -509,10 +717,19 @@ void launch_action_matrix_free_pk(ptb_ctx* c, const VectorArgs& A, const double*
 
 void launch_assemble_vector_pk(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
 {
-  if (c->bs != 1)
-    throw std::runtime_error("assemble_vector: order > 1 is built for the scalar Poisson space only");
   ensure_tables(c);
   const int grid = (A.n_slices + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
+  if (c->bs == 3)
+  {
+    // Elasticity.py:40: cells only, no exterior-facet term
+    if (c->order == 2)
+      assemble_vector_pk3<10><<<grid, PK_THREADS, 0, c->stream>>>(A, c->tab_M.p);
+    else
+      assemble_vector_pk3<20><<<grid, PK_THREADS, 0, c->stream>>>(A, c->tab_M.p);
+    PTB_CUDA(cudaGetLastError());
+    c->launches += 1;
+    return;
+  }
   if (c->order == 2)
     assemble_vector_pk<10><<<grid, PK_THREADS, 0, c->stream>>>(A, c->tab_M.p);
   else

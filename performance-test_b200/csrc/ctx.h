@@ -166,7 +166,7 @@ struct ptb_ctx
   ptb::DevBuf<std::int32_t> frow_ids, frow_ptr, fent; // fent = {cell, local_facet*nd + li} pairs
 
   // reference tensors of the P2/P3 element (element_tables.h), uploaded on first use
-  ptb::DevBuf<double> tab_S, tab_M, tab_MF;
+  ptb::DevBuf<double> tab_S, tab_M, tab_MF, tab_KF;
   // P2/P3 matrix assembly by row-length bins (PTB_PK_BINS=1): slices grouped by width class
   ptb::DevBuf<std::int32_t> pk_bin_slices;
   std::vector<std::int32_t> pk_bin_off; // [n_bins + 1] into pk_bin_slices

@@ -122,7 +122,8 @@ def tables(order):
             for b_, j in enumerate(on):
                 full[i, j] = m2[a_, b_]
         Mf.append(full)
-    return nd, S, M, Mf
+    KF = [K[(a, b)] for a in range(3) for b in range(3)]
+    return nd, S, M, Mf, KF
 
 
 def emit(name, mats, nd, out):
@@ -148,10 +149,12 @@ def main():
            "// Exactly integrated reference tensors of the gll_warped Lagrange P2/P3 tetrahedron",
            "// (basix element of poisson_problem.cpp:35-38; forms Poisson.py:31-32).",
            "// S: [6][nd][nd] stiffness combos (00,01,02,11,12,22); M: [nd][nd] mass;",
-           "// MF: [4][nd][nd] facet mass on the reference triangle (zero off the facet).",
+           "// MF: [4][nd][nd] facet mass on the reference triangle (zero off the facet);",
+           "// KF: [9][nd][nd] the unsymmetrised stiffness tensors int d_c phi_i d_d phi_j, index 3c+d",
+           "// (vector-valued forms: Elasticity.py:30-39 needs d_a phi_i d_b phi_j for a != b).",
            "#pragma once", "namespace ptb { namespace tables {"]
     for order in (2, 3):
-        nd, S, M, Mf = tables(order)
+        nd, S, M, Mf, KF = tables(order)
         # sanity: rows of S sum to zero (constants in the kernel), sum(M) = 1/6, sum(Mf) = 1/2
         for Sx in S:
             for i in range(nd):
@@ -162,6 +165,11 @@ def main():
         emit(f"S_P{order}", S, nd, out)
         emit(f"M_P{order}", [M], nd, out)
         emit(f"MF_P{order}", Mf, nd, out)
+        # KF is consistent with S: S[bc] = KF[bc] + KF[cb] (b != c), S[bb] = KF[bb]
+        for q, (b, c) in enumerate([(0, 0), (0, 1), (0, 2), (1, 1), (1, 2), (2, 2)]):
+            ref = KF[3 * b + c] if b == c else KF[3 * b + c] + KF[3 * c + b]
+            assert max(abs(ref[i, j] - S[q][i, j]) for i in range(nd) for j in range(nd)) < mpf(10) ** -40
+        emit(f"KF_P{order}", KF, nd, out)
     out.append("} } // namespace ptb::tables")
     import sys
     path = sys.argv[1] if len(sys.argv) > 1 else os.path.join(

@@ -99,3 +99,18 @@ def test_cgpoisson_uses_cg_h_defaults(pt):
     its = int(re.search(r"\*\*\* Number of Krylov iterations: (\d+)", r.stdout).group(1))
     assert 1 <= its <= 100
     assert "Gdof/s" in r.stdout
+
+
+@pytest.mark.gpu
+def test_reference_ci_configuration_elasticity_order_3(pt):
+    """The reference's CI runs `--problem_type elasticity --scaling_type weak --ndofs 100000 --order 3`
+    (.github/workflows/ccpp.yml:165-181, with GAMG); the same command line with CG + Jacobi must run
+    through, print the ZZZ rows and a converged iteration count."""
+    r = subprocess.run([EXE, "--problem_type", "elasticity", "--scaling_type", "weak", "--ndofs", "100000",
+                        "--order", "3", "-ksp_rtol", "1e-8", "-pc_type", "jacobi"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "ZZZ Assemble matrix" in r.stdout and "ZZZ Solve" in r.stdout
+    its = int(re.search(r"\*\*\* Number of Krylov iterations: (\d+)", r.stdout).group(1))
+    assert 10 < its < 10000
+

@@ -47,7 +47,10 @@ SMALL = [("poisson", 1, (5, 4, 6)), ("poisson", 1, (1, 1, 1)), ("poisson", 1, (9
          ("poisson", 1, (16, 15, 17)), ("elasticity", 1, (4, 5, 3)), ("elasticity", 1, (1, 1, 2)),
          ("elasticity", 1, (12, 11, 13)),
          ("poisson", 2, (4, 3, 5)), ("poisson", 2, (1, 1, 1)), ("poisson", 2, (9, 8, 10)),
-         ("poisson", 3, (3, 4, 2)), ("poisson", 3, (1, 1, 1)), ("poisson", 3, (6, 5, 7))]
+         ("poisson", 3, (3, 4, 2)), ("poisson", 3, (1, 1, 1)), ("poisson", 3, (6, 5, 7)),
+         # elasticity P2 / P3 (round 2; the reference's CI runs --problem_type elasticity --order 3)
+         ("elasticity", 2, (3, 4, 2)), ("elasticity", 2, (1, 1, 2)), ("elasticity", 2, (6, 5, 7)),
+         ("elasticity", 3, (2, 3, 2)), ("elasticity", 3, (1, 1, 1)), ("elasticity", 3, (5, 4, 4))]
 
 
 @pytest.mark.parametrize("ptype,order,dims", SMALL)
@@ -358,6 +361,33 @@ def test_hot_path_on_renumbered_dofs_matches_oracle(pt, oracle, ctx, ptype, orde
                                     rtol=1e-8, precond=precond)
         assert abs(k - k_ref) <= 1 and rel < 1e-8
         assert np.linalg.norm(ctx.solution()[: P.n_owned * P.bs] - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
+
+
+@pytest.mark.parametrize("order,dims", [(2, (5, 4, 6)), (3, (4, 3, 4))])
+def test_elasticity_p2_p3_hot_path_matches_oracle(pt, oracle, perturbed, ctx, order, dims):
+    """Elasticity on P2 / P3 (assemble_matrix_pk3_binned, assemble_vector_pk3; Elasticity.py with
+    degree 2, 3): A, b, A p and the CG + Jacobi solve against the oracle, on the lattice and on the
+    jittered mesh (where no product of the element tensors vanishes)."""
+    for jitter in (False, True):
+        P = pt.host.Problem("elasticity", order, *dims)
+        ctx.set_problem(P)
+        if jitter:
+            P = perturbed(P)
+            ctx.update_geometry(P["x"])
+        ctx.assemble_matrix()
+        ctx.assemble_vector()
+        A_ref, b_ref = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+        _check_matrix(P, ctx.matrix_values(), A_ref)
+        assert np.abs(ctx.rhs() - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+        v = np.random.default_rng(4).standard_normal((P.n_owned + P.n_ghost) * 3)
+        y_ref = oracle.spmv(3, P.n_owned, P["rowptr"], P["cols"], ctx.matrix_values(), v)
+        assert np.abs(ctx.apply_operator(v) - y_ref).max() <= 1e-13 * np.abs(y_ref).max()
+        ctx.set_initial_guess(None)
+        k, rel = ctx.cg_solve(kmax=20000, rtol=1e-8, precond="jacobi")
+        x_ref, k_ref, _ = oracle.cg(3, P.n_owned, P["rowptr"], P["cols"], A_ref, b_ref, kmax=20000, rtol=1e-8,
+                                    precond="jacobi")
+        assert abs(k - k_ref) <= 1 and rel < 1e-8
+        assert np.linalg.norm(ctx.solution()[: P.n_owned * 3] - x_ref) <= 1e-6 * np.linalg.norm(x_ref)
 
 
 def test_large_properties_elasticity(pt, ctx):
