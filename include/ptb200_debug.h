@@ -58,6 +58,11 @@ int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* 
                                  const int32_t* cols, int32_t* cdelta, int64_t* xoff,
                                  int32_t* colsx);
 
+/* The balanced split of the operator kernels for small problems (layout.h build_balance_plan), host
+ * only: ounit [n_slices + 1]; begin holds at most grid + 2 entries, *n_begin receives the count. */
+int ptb_debug_balance_plan(int32_t n_slices, const int64_t* mat_off, const int32_t* order, int32_t n_interior,
+                           int grid, int npull, int32_t* ounit, int32_t* begin, int32_t* n_begin);
+
 /* The slice visiting order of the operator kernels (layout.h build_slice_order; slices without
  * ghost columns first), host only: order [ceil(n_rows/32)], *n_interior = number of leading
  * slices that read no ghost column. */

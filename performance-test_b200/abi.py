@@ -206,6 +206,19 @@ def slice_order(n_rows, rowptr, cols):
     return order, ni.value
 
 
+def balance_plan(mat_off, order, n_interior, grid, npull=-1):
+    """Host-only: (ounit, begin) of the balanced operator split (layout.h build_balance_plan)."""
+    mo, od = _a(mat_off, np.int64), _a(order, np.int32)
+    S = len(od)
+    ounit = np.zeros(S + 1, dtype=np.int32)
+    begin = np.zeros(grid + 2, dtype=np.int32)
+    nb = C.c_int32()
+    if lib().ptb_debug_balance_plan(S, _ptr(mo), _ptr(od), n_interior, grid, npull, _ptr(ounit), _ptr(begin),
+                                    C.byref(nb)) != 0:
+        raise RuntimeError(lib().ptb_last_error(None).decode())
+    return ounit, begin[: nb.value].copy()
+
+
 def pk_layout(dofmap, nd, n_owned, rowptr, cols):
     """Host-only: SELL-32 arrays of the P2/P3 assembly kernels + row-length bins, as a dict."""
     dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)

@@ -160,6 +160,20 @@ int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* 
   });
 }
 
+int ptb_debug_balance_plan(int32_t n_slices, const int64_t* mat_off, const int32_t* order, int32_t n_interior,
+                           int grid, int npull, int32_t* ounit, int32_t* begin, int32_t* n_begin)
+{
+  return guarded(nullptr, [&] {
+    need(mat_off && order && ounit && begin && n_begin, "ptb_debug_balance_plan: NULL argument");
+    std::vector<std::int32_t> ou, bg;
+    const int longest = build_balance_plan(mat_off, order, n_slices, n_interior, grid, npull, ou, bg);
+    std::copy(ou.begin(), ou.end(), ounit);
+    std::copy(bg.begin(), bg.end(), begin);
+    *n_begin = static_cast<std::int32_t>(bg.size());
+    (void)longest;
+  });
+}
+
 int ptb_debug_slice_order(int32_t n_rows, const int64_t* rowptr, const int32_t* cols,
                           int32_t* order, int32_t* n_interior)
 {

@@ -12,6 +12,7 @@
 #include "comm.h"
 #include "envopt.h"
 #include "kernels.h"
+#include "layout.h"
 #include "peer.cuh"
 #include "reduce.cuh"
 #include <algorithm>
@@ -1467,40 +1468,9 @@ void ensure_balance(ptb_ctx* c, SpmvArgs& A, int which, int grid, int npull, int
       PTB_CUDA(cudaMemcpy(mo.data(), A.mat_off, mo.size() * sizeof(std::int64_t), cudaMemcpyDeviceToHost));
       PTB_CUDA(cudaMemcpy(order.data(), c->slice_order.p, order.size() * sizeof(std::int32_t),
                           cudaMemcpyDeviceToHost));
-      std::vector<std::int32_t> ou(static_cast<std::size_t>(S) + 1, 0);
-      for (std::int32_t i = 0; i < S; ++i)
-        ou[i + 1] = ou[i] + static_cast<std::int32_t>((mo[order[i] + 1] - mo[order[i]]) >> 5);
-      std::vector<std::int32_t> begin;
-      bool ok = true;
-      int longest = 0;
-      auto split = [&](std::int32_t a, std::int32_t b, int ctas) {
-        // boundaries at the slice edges nearest to the equal-unit cuts
-        const std::int64_t lo = ou[a], len = ou[b] - ou[a];
-        std::int32_t prev = a;
-        for (int t = 0; t <= ctas; ++t)
-        {
-          const std::int64_t target = lo + len * t / ctas;
-          std::int32_t i = static_cast<std::int32_t>(std::lower_bound(ou.begin() + a, ou.begin() + b + 1, target) - ou.begin());
-          if (i > a && target - ou[i - 1] < ou[i] - target)
-            --i;
-          i = std::max(i, prev);
-          if (t == ctas)
-            i = b;
-          if (t > 0 && i - prev > max_run)
-            ok = false;
-          if (t > 0)
-            longest = std::max(longest, i - prev);
-          begin.push_back(i);
-          prev = i;
-        }
-      };
-      if (npull >= 0)
-      {
-        split(c->n_interior_slices, S, std::max(npull, 1));
-        split(0, c->n_interior_slices, grid - npull);
-      }
-      else
-        split(0, S, grid);
+      std::vector<std::int32_t> ou, begin;
+      const int longest = build_balance_plan(mo.data(), order.data(), S, c->n_interior_slices, grid, npull, ou, begin);
+      const bool ok = longest <= max_run;
       if (ok)
       {
         B.ounit.upload(ou, c->stream);

@@ -484,4 +484,44 @@ void build_facet_rows_gathered(std::int64_t n_facets, const std::int32_t* cells,
     ent[i] = cells[ent[i]];
 }
 
+int build_balance_plan(const std::int64_t* mat_off, const std::int32_t* order, std::int32_t n_slices,
+                       std::int32_t n_interior, int grid, int npull, std::vector<std::int32_t>& ounit,
+                       std::vector<std::int32_t>& begin)
+{
+  const std::int32_t S = n_slices;
+  ounit.assign(static_cast<std::size_t>(S) + 1, 0);
+  for (std::int32_t i = 0; i < S; ++i)
+    ounit[i + 1] = ounit[i] + static_cast<std::int32_t>((mat_off[order[i] + 1] - mat_off[order[i]]) >> 5);
+  begin.clear();
+  int longest = 0;
+  auto split = [&](std::int32_t a, std::int32_t b, int ctas) {
+    // boundaries at the slice edges nearest to the equal-unit cuts
+    const std::int64_t lo = ounit[a], len = ounit[b] - ounit[a];
+    std::int32_t prev = a;
+    for (int t = 0; t <= ctas; ++t)
+    {
+      const std::int64_t target = lo + len * t / ctas;
+      std::int32_t i = static_cast<std::int32_t>(
+          std::lower_bound(ounit.begin() + a, ounit.begin() + b + 1, target) - ounit.begin());
+      if (i > a && target - ounit[i - 1] < ounit[i] - target)
+        --i;
+      i = std::max(i, prev);
+      if (t == ctas)
+        i = b;
+      if (t > 0)
+        longest = std::max(longest, i - prev);
+      begin.push_back(i);
+      prev = i;
+    }
+  };
+  if (npull >= 0)
+  {
+    split(n_interior, S, std::max(npull, 1));
+    split(0, n_interior, grid - npull);
+  }
+  else
+    split(0, S, grid);
+  return longest;
+}
+
 } // namespace ptb

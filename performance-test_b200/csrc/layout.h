@@ -101,4 +101,13 @@ void build_facet_rows_gathered(std::int64_t n_facets, const std::int32_t* cells,
                                int order, std::int32_t n_rows, std::vector<std::int32_t>& row_ids,
                                std::vector<std::int32_t>& row_ptr, std::vector<std::int32_t>& ent);
 
+/// Balanced split of the operator kernels for small problems (cg.cu spmv_cta_balanced): ounit
+/// [S + 1] = k-steps (stored entries per row) before position i of the slice order; begin = the CTAs'
+/// runs of positions, equal in k-steps up to one slice: with puller roles (npull >= 0) npull + 1
+/// entries over the ghost-reading positions [n_interior, S) followed by grid - npull + 1 entries over
+/// [0, n_interior); without roles grid + 1 entries over [0, S). Returns the longest run in slices.
+int build_balance_plan(const std::int64_t* mat_off, const std::int32_t* order, std::int32_t n_slices,
+                       std::int32_t n_interior, int grid, int npull, std::vector<std::int32_t>& ounit,
+                       std::vector<std::int32_t>& begin);
+
 } // namespace ptb

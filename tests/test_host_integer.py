@@ -175,3 +175,31 @@ def test_host_sizes_only_modes_agree_with_the_full_build(tmp_path):
     for order, bs, dims, nranks in ((1, 1, (5, 4, 6), 1), (1, 3, (3, 3, 7), 3), (2, 1, (3, 2, 5), 2), (3, 1, (2, 2, 4), 4)):
         for rank in range(nranks):
             assert lib.header_modes_agree(order, bs, *dims, rank, nranks) == 0, (order, dims, rank, nranks)
+
+
+@pytest.mark.parametrize("ptype,dims,nranks,grid,npull", [("elasticity", (9, 8, 10), 1, 7, -1),
+                                                          ("elasticity", (6, 7, 12), 2, 9, 2),
+                                                          ("poisson", (16, 15, 17), 3, 12, 3)])
+def test_balance_plan_covers_every_slice_once_with_equal_work(pt, ptype, dims, nranks, grid, npull):
+    """Host plan of the balanced operator split (layout.cpp build_balance_plan): the CTAs' runs tile
+    the slice order without gap or overlap, puller runs cover exactly the ghost-reading positions,
+    and no run holds more k-steps than its equal share plus one slice."""
+    for rank in range(nranks):
+        P = pt.host.Problem(ptype, 1, *dims, rank, nranks)
+        L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+        order, n_int = pt.abi.slice_order(P.n_owned, P["rowptr"], P["cols"])
+        S = L["n_slices"]
+        use_pull = npull if nranks > 1 else -1
+        ou, begin = pt.abi.balance_plan(L["mat_off"], order, n_int, grid, use_pull)
+        w = (L["mat_off"][order + 1] - L["mat_off"][order]) // 32
+        assert np.array_equal(ou, np.concatenate([[0], np.cumsum(w)]))
+        groups = [(n_int, S, use_pull), (0, n_int, grid - use_pull)] if use_pull >= 0 else [(0, S, grid)]
+        pos = 0
+        for a, b, ctas in groups:
+            run = begin[pos:pos + ctas + 1]
+            pos += ctas + 1
+            assert run[0] == a and run[-1] == b and np.all(np.diff(run) >= 0)
+            units = ou[run[1:]] - ou[run[:-1]]
+            share = (ou[b] - ou[a]) / ctas
+            assert units.max() <= share + w.max() + 1
+        assert pos == len(begin)

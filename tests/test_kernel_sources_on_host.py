@@ -217,7 +217,7 @@ def emucg():
                         "-I", cuda_inc, "-o", base, CG_SRC], check=True)
     libs = []
     for g in range(4):  # one copy per CTA: `__shared__` variables are statics of the copy
-        path = base.replace(".so", f"_{g}.so")
+        path = base.replace(".so", f"_{os.environ.get('PYTEST_XDIST_WORKER', 'w')}_{g}.so")  # never rewrite a copy another worker has mapped
         shutil.copyfile(base, path)
         libs.append(C.CDLL(path))
     assert libs[0].emu_cgstate_size() == CGSTATE.itemsize
@@ -290,6 +290,9 @@ def test_persistent_cg_loop_source_reproduces_the_oracle(pt, oracle, emucg, ptyp
             _p(xoff), _p(order), _p(dinv), _p(r), _p(p), _p(x), _p(y), _p(st), _p(slots), 500]
     ou, begin = _balance_plan(L["mat_off"], order, [(0, L["n_slices"], grid)]) if balanced else (None, None)
     assert not balanced or begin is not None
+    if balanced:   # the product's host plan (layout.cpp build_balance_plan) is the same plan
+        ou_p, begin_p = pt.abi.balance_plan(L["mat_off"], order, L["n_slices"], grid)
+        assert np.array_equal(ou, ou_p) and np.array_equal(begin, begin_p)
     res_cap = 0
     if balanced == "resident":
         res_cap = int(np.diff(begin).max()) * 32 * bs
@@ -378,6 +381,8 @@ def test_persistent_cg_loop_peer_branch_on_host(pt, oracle, emucg, ptype, dims, 
                     d["ou"], d["begin"] = _balance_plan(L["mat_off"], d["order"],
                                                         [(d["n_int"], L["n_slices"], 1), (0, d["n_int"], grid - 1)])
                     assert d["begin"] is not None
+                    ou_p, begin_p = pt.abi.balance_plan(L["mat_off"], d["order"], d["n_int"], grid, 1)
+                    assert np.array_equal(d["ou"], ou_p) and np.array_equal(d["begin"], begin_p)
                 runs = np.concatenate([np.diff(d["begin"][:2]), np.diff(d["begin"][2:])])
                 args += [_p(d["ou"]), _p(d["begin"]), int(runs.max()) * 32 * P.bs if balanced == "resident" else 0]
             else:
