@@ -419,6 +419,8 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu, secondary=False):
     if rank == 0:
         wl = WORKLOADS[wl_name]
         walk3 = os.environ.get("PTB_ASM_WALK3", "1") != "0"
+        # edge-ring kernel: host-built maps only (device-generated problems keep the star walk)
+        ring = os.environ.get("PTB_ASM_RING", "1") != "0" and not device_setup
         walk = os.environ.get("PTB_ASM_WALK", "1") != "0"
         out = {
             "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",
@@ -444,7 +446,8 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu, secondary=False):
                                             "Plaza refinement (same entity counts)" if base[3] else None,
                        "switches": switches,
                        "matrix_kernel": ("assemble_matrix_pk_binned" if order > 1 else
-                                         ("assemble_matrix_p1_walk3 (star walk)" if walk3 else
+                                         ("assemble_matrix_p1_ring3 (edge rings)" if ring else
+                                          "assemble_matrix_p1_walk3 (star walk)" if walk3 else
                                           "assemble_matrix_p1<3> (cell order)") if ptype == "elasticity" else
                                          "assemble_matrix_p1_walk (star walk)" if walk else
                                          "assemble_matrix_p1<1> (cell order)")},

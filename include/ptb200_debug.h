@@ -52,6 +52,12 @@ int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
                         int64_t* adj_off, int64_t* walk1_off, int32_t* cols_sell, uint32_t* walk,
                         uint32_t* walk1, uint32_t* adjrot);
 
+/* The edge rings of the column-major elasticity P1 kernel (layout.h build_rings, csrc/assemble_ring.cu),
+ * host only: ring_off [ceil(n_owned/32) + 1] (in words), ring_ns [mat_off[S]/32] (chain bytes per
+ * lane of every (slice, column)); ring [ring_off[S]] may be NULL on the first call. */
+int ptb_debug_p1_rings(int64_t n_cells, const int32_t* dofmap, int32_t n_owned, const int64_t* rowptr,
+                       const int32_t* cols, int64_t* ring_off, uint8_t* ring_ns, uint32_t* ring);
+
 /* The compressed column indices of the scalar SpMV (layout.h: cdelta / xoff / colsx), host only:
  * cdelta [mat_off[S]/32], xoff [S + 1]; colsx [xoff[S]] may be NULL on the first call. */
 int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,

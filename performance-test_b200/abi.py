@@ -91,6 +91,7 @@ def lib():
         L.ptb_debug_pk_layout.argtypes = [i64, C.c_int, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
         L.ptb_debug_slice_order.argtypes = [i32, vp, vp, vp, C.POINTER(i32)]
         L.ptb_debug_compressed_columns.argtypes = [i32, i64, vp, vp, vp, vp, vp]
+        L.ptb_debug_p1_rings.argtypes = [i64, vp, i32, vp, vp, vp, vp, vp]
         L.ptb_debug_p1_layout.argtypes = [i64, vp, i32, vp, vp, C.POINTER(C.c_int), vp, vp, vp, vp, vp, vp, vp]
         L.ptb_time_kernel.argtypes = [vp, C.c_int, C.c_int, C.POINTER(dbl)]
         L.ptb_stage_ms.argtypes = [vp, C.c_int]
@@ -177,6 +178,23 @@ def p1_layout(dofmap, n_owned, rowptr, cols):
         if rc != 0:
             raise RuntimeError(lib().ptb_last_error(None).decode())
     return dict(off, **data, max_w=mw.value, n_slices=ns)
+
+
+def p1_rings(dofmap, n_owned, rowptr, cols, n_sell_entries):
+    """Host-only: (ring_off, ring_ns, ring) of the column-major elasticity kernel (layout.h build_rings)
+    for a pattern whose SELL-32 layout has n_sell_entries padded entries (mat_off[-1])."""
+    dm, rp, cl = _a(dofmap, np.int32), _a(rowptr, np.int64), _a(cols, np.int32)
+    ring_off = np.zeros((n_owned + 31) // 32 + 1, dtype=np.int64)
+    ring_ns = np.zeros(n_sell_entries // 32, dtype=np.uint8)
+    ring = None
+    for fill in (False, True):
+        if fill:
+            ring = np.zeros(max(int(ring_off[-1]), 1), dtype=np.uint32)
+        rc = lib().ptb_debug_p1_rings(len(dm) // 4, _ptr(dm), n_owned, _ptr(rp), _ptr(cl), _ptr(ring_off),
+                                      _ptr(ring_ns), _ptr(ring))
+        if rc != 0:
+            raise RuntimeError(lib().ptb_last_error(None).decode())
+    return ring_off, ring_ns, ring
 
 
 def compressed_columns(n_rows, n_cols, rowptr, cols, n_sell_entries):

@@ -20,6 +20,8 @@ bool walk_enabled() { return env_flag("PTB_ASM_WALK", true); }
 // Elasticity matrix along the star walk (assemble_matrix_p1_walk3): default since round 2
 // (1.40 -> 0.91 ms at 1.33 M nodes, profiles/r02/assembly_ab_4M.json); 0 = first-generation kernel.
 bool walk3_enabled() { return env_flag("PTB_ASM_WALK3", true); }
+// Elasticity matrix column-major along the edge rings (assemble_matrix_p1_ring3); 0 = walk3.
+bool ring_enabled() { return env_flag("PTB_ASM_RING", true); }
 // P1 cell vector by direct gather along the single-reload walk (assemble_gwalk.cu): default.
 bool gwalk_enabled() { return env_flag("PTB_VEC_GWALK", true); }
 // Assembly maps and column layout built by the setup kernels (setup.cu) instead of the host loops.
@@ -98,7 +100,7 @@ std::int64_t ptb_ctx::device_bytes() const
 {
   return xyz.bytes() + xyz3.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
-         + adjso.bytes() + adjrot.bytes() + walk.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + adjso.bytes() + adjrot.bytes() + walk.bytes() + ring.bytes() + ring_off.bytes() + ring_ns.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
          + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes() + zcnt_w.bytes() + zcnt_x.bytes() + mat_off_z.bytes() + xoff_z.bytes() + vals_z.bytes() + cdelta_z.bytes() + colsx_z.bytes()
@@ -414,6 +416,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       return (c->bs == 1 && walk_enabled() && L.max_w <= 32) || (c->bs == 3 && walk3_enabled());
     };
     c->walk.release();
+    c->ring.release(), c->ring_off.release(), c->ring_ns.release();
     c->walk_loads_per_step = 0.0;
     c->maps_on_device = false;
     if (dev_maps)
@@ -464,6 +467,18 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
         const WalkStats ws = build_walk(N, c->h_adj, c->h_so, L);
         c->walk_loads_per_step = ws.steps ? static_cast<double>(ws.loads) / ws.steps : 0.0;
         c->walk.upload(L.walk, c->stream);
+      }
+      if (!L.adjrot.empty() && c->bs == 3 && ring_enabled())
+      {
+        // edge rings of the column-major elasticity kernel (assemble_ring.cu)
+        const std::int64_t nb = build_rings(N, rowptr, c->h_adj, c->h_so, L);
+        if (!L.ring.empty())
+        {
+          c->ring.upload(L.ring, c->stream);
+          c->ring_off.upload(L.ring_off, c->stream);
+          c->ring_ns.upload(L.ring_ns, c->stream);
+          c->ring_bytes_per_row = N ? static_cast<double>(nb) / N : 0.0;
+        }
       }
     }
     c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
@@ -542,6 +557,7 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
         = (c->bs == 1 && walk_enabled() && c->max_w <= 32) || (c->bs == 3 && walk3_enabled());
     int max_wa = 0;
     c->walk.release();
+    c->ring.release(), c->ring_off.release(), c->ring_ns.release(); // host-built only: walk3 runs instead
     c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
     if (c->nd == 4)
     {

@@ -141,6 +141,27 @@ int ptb_debug_p1_layout(int64_t n_cells, const int32_t* dofmap, int32_t n_owned,
   });
 }
 
+int ptb_debug_p1_rings(int64_t n_cells, const int32_t* dofmap, int32_t n_owned, const int64_t* rowptr,
+                       const int32_t* cols, int64_t* ring_off, uint8_t* ring_ns, uint32_t* ring)
+{
+  return guarded(nullptr, [&] {
+    need(dofmap && rowptr && cols && ring_off && ring_ns, "ptb_debug_p1_rings: NULL argument");
+    RowAdjacency adj;
+    std::vector<std::uint16_t> so;
+    build_row_adjacency(dofmap, n_cells, 4, n_owned, adj);
+    const std::int64_t max_so = build_slot_offsets(dofmap, 4, n_owned, adj, rowptr, cols, so);
+    need(max_so >= 0 && max_so < 127, "ptb_debug_p1_rings: pattern does not cover the cells / row too long");
+    SellLayout L;
+    build_sell_layout(n_owned, 4, rowptr, cols, adj, so, max_so, L);
+    build_rings(n_owned, rowptr, adj, so, L);
+    need(!L.ring_off.empty(), "ptb_debug_p1_rings: no rings for this pattern");
+    std::copy(L.ring_off.begin(), L.ring_off.end(), ring_off);
+    std::copy(L.ring_ns.begin(), L.ring_ns.end(), ring_ns);
+    if (ring)
+      std::copy(L.ring.begin(), L.ring.end(), ring);
+  });
+}
+
 int ptb_debug_compressed_columns(int32_t n_rows, int64_t n_cols, const int64_t* rowptr,
                                  const int32_t* cols, int32_t* cdelta, int64_t* xoff,
                                  int32_t* colsx)

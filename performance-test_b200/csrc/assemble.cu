@@ -556,7 +556,7 @@ void launch_assemble_matrix(ptb_ctx* c, const MatrixArgs& A)
     return launch_assemble_matrix_pk(c, A);
   if (A.adjrot == nullptr)
     throw std::runtime_error("assemble_matrix: a P1 row has more than 254 columns");
-  if (launch_assemble_matrix_walk(c, A))
+  if (launch_assemble_matrix_ring(c, A) || launch_assemble_matrix_walk(c, A))
     return;
   if (c->bs == 1)
   {

@@ -1,0 +1,212 @@
+// Elasticity P1 matrix assembly, column-major along the *edge rings* (layout.h build_rings) -- third
+// generation of the row-owner gather for the 3x3-block operator, same results to rounding, same
+// reference region (fem::assemble_matrix + set_diagonal, elasticity_problem.cpp:203-211 with the
+// tabulate_tensor of Elasticity.py:30-40).
+//
+// Why: assemble_matrix_p1_walk3 (assemble_walk.cu) visits the 24 cells of a vertex star once, but it
+// needs three warps per slice (one per component row of the block, each repeating the geometry) and
+// read-modify-writes its accumulators in shared memory: ncu (profiles/r02/ncu_walk3_elasticity_10M.csv)
+// shows 4 700 issued instructions per warp for ~1 000 FP64 ones, 12 warps per SM, issue slots 56 %
+// busy. Here ONE thread owns the whole block row of a vertex and the loop runs over the row's
+// stored columns: for column k (neighbour j) the cells around the edge (i, j) are walked as a chain
+// v_0, v_1, ... (cell t = (i, j, v_{t-1}, v_t)), so that
+//   * the nine entries of T_j = sum_cells c_i (x) c_j / (6|det|) stay in registers until the block
+//     is written -- no accumulator in shared memory, nothing indexed dynamically;
+//   * consecutive cells share the face (i, j, v): one new edge vector (3 LDS.64) and two new
+//     cofactor vectors per cell, n_b of a cell is -n_a of its predecessor;
+//   * the material law is applied and the block stored (9 coalesced 256-byte lines) as soon as
+//     its ring is closed; the diagonal block follows from sum_j c_j = 0:  T_ii = -sum_{j != i} T_ij.
+// A cell is visited three times per row (once per non-owner vertex: 72 + 14 steps of ~39 FP64
+// instructions on the Kuhn box against 3 x 24 steps of ~40), but a step costs ~65 issue slots instead
+// of 3 x 150, and 16 warps per SM fit (13.4 KB of shared memory per slice: the star's edge vectors).
+// The chains follow the mesh topology and the ascending cell order only, so every off-diagonal block
+// is independent of the partition bit for bit; the diagonal block is summed in the row's local
+// column order (ghost columns last) and agrees across partitions to rounding (~4 ulp of |A_ii|).
+// PTB_ASM_RING=0 selects assemble_matrix_p1_walk3.
+#include "geom.cuh"
+#include "envopt.h"
+#include "kernels.h"
+#include <climits>
+
+namespace ptb
+{
+namespace
+{
+
+constexpr int RING_CHUNK = 8; // star columns staged per trip of the prologue
+constexpr std::uint32_t RING_PAD = 0x80808080u;
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
+                         const std::int64_t* __restrict__ ring_off, const std::uint8_t* __restrict__ ring_ns)
+{
+  extern __shared__ double smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const std::int32_t slice = blockIdx.x * WARPS + warp;
+  if (slice >= A.n_slices)
+    return;
+  const std::int64_t mo = A.mat_off[slice];
+  const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
+  const std::int32_t row = slice * 32 + lane;
+  const bool live = row < A.n_rows;
+  const int mw = A.max_w;
+
+  // private column `lane` of the slice's region: E[(k*3+d)*32] edge vectors owner -> column k,
+  // C[k*32] column index with the Dirichlet flag in the top bit. No barrier anywhere.
+  double* E = smem + warp * (mw * 112) + lane;
+  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem + warp * (mw * 112) + mw * 96) + lane;
+
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  const std::uint32_t* rp = ring + ring_off[slice] + lane;
+  const std::uint8_t* nsp = ring_ns + (mo >> 5);
+  int ns = w > 0 ? __ldg(nsp) : 0;
+  std::uint32_t w0 = ns > 0 ? __ldg(rp) : RING_PAD, w1 = ns > 4 ? __ldg(rp + 32) : RING_PAD;
+
+  // ---- star: edge vectors and flagged columns of the whole row --------------------------------
+  int own = -1;
+  for (int k0 = 0; k0 < w; k0 += RING_CHUNK)
+  {
+    std::int32_t c[RING_CHUNK];
+#pragma unroll
+    for (int j = 0; j < RING_CHUNK; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+    Vec3 x[RING_CHUNK];
+    std::uint8_t b[RING_CHUNK];
+#pragma unroll
+    for (int j = 0; j < RING_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        x[j] = load_point(A.xdof, c[j]);
+        b[j] = __ldg(A.bc + c[j]);
+      }
+#pragma unroll
+    for (int j = 0; j < RING_CHUNK; ++j)
+      if (c[j] >= 0)
+      {
+        const int k = k0 + j;
+        const Vec3 d = x[j] - X0;
+        E[(k * 3 + 0) * 32] = d.x;
+        E[(k * 3 + 1) * 32] = d.y;
+        E[(k * 3 + 2) * 32] = d.z;
+        C[k * 32] = c[j] | (b[j] ? INT32_MIN : 0);
+        own = c[j] == row && k < len ? k : own;
+      }
+  }
+  auto edge = [&](int o) { return Vec3{E[(o * 3 + 0) * 32], E[(o * 3 + 1) * 32], E[(o * 3 + 2) * 32]}; };
+
+  constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
+  constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
+  // block[a][b] = mu (delta_ab tr T + T[b][a]) + lambda T[a][b]   (Elasticity.py:33-39), T[a] = row a
+  auto store_block = [&](int k, Vec3 T0, Vec3 T1, Vec3 T2, bool zero, bool identity) {
+    const double tr = T0.x + T1.y + T2.z;
+    double v[9] = {mu * (tr + T0.x) + lmbda * T0.x, mu * T1.x + lmbda * T0.y, mu * T2.x + lmbda * T0.z,
+                   mu * T0.y + lmbda * T1.x, mu * (tr + T1.y) + lmbda * T1.y, mu * T2.y + lmbda * T1.z,
+                   mu * T0.z + lmbda * T2.x, mu * T1.z + lmbda * T2.y, mu * (tr + T2.z) + lmbda * T2.z};
+    double* out = A.vals + (mo + k * 32) * 9 + lane;
+#pragma unroll
+    for (int e = 0; e < 9; ++e)
+    {
+      double val = v[e];
+      if (identity)
+        val = (e == 0 || e == 4 || e == 8) ? 1.0 : 0.0;
+      else if (zero)
+        val = 0.0;
+      out[e * 32] = val;
+      v[e] = val;
+    }
+    return Vec3{v[0], v[4], v[8]};
+  };
+
+  // ---- columns ----------------------------------------------------------------------------------
+  Vec3 S0{0.0, 0.0, 0.0}, S1 = S0, S2 = S0; // sum of the off-diagonal raw tensors of the row
+  for (int k = 0; k < w; ++k)
+  {
+    // ring words of the next column in flight while this one is walked
+    const std::uint32_t* rpn = rp + ((ns + 3) >> 2) * 32;
+    const int ns_next = k + 1 < w ? __ldg(nsp + k + 1) : 0;
+    const std::uint32_t nx0 = ns_next > 0 ? __ldg(rpn) : RING_PAD, nx1 = ns_next > 4 ? __ldg(rpn + 32) : RING_PAD;
+
+    Vec3 T0{0.0, 0.0, 0.0}, T1 = T0, T2 = T0;
+    if (ns > 1)
+    {
+      const Vec3 ej = edge(k);
+      Vec3 ea = edge(w0 & 0x7Fu);
+      Vec3 nap = cross(ea, ej); // n_a of the step before: e_b x e_j with b = this step's a
+      for (int t = 1; t < ns; ++t)
+      {
+        const std::uint32_t word = t < 4 ? w0 : (t < 8 ? w1 : __ldg(rp + (t >> 2) * 32));
+        const std::uint32_t beta = (word >> (8 * (t & 3))) & 0xFFu;
+        const Vec3 eb = edge(beta & 0x7Fu);
+        // cell (i; j, a, b): n_j = e_a x e_b, n_a = e_b x e_j, n_b = e_j x e_a = -nap
+        const Vec3 nj = cross(ea, eb), na = cross(eb, ej);
+        const double det = dot(ej, nj);
+        const double r = (beta & 0x80u) ? 0.0 : rcp_nr(6.0 * fabs(det));
+        // c_i = -(n_j + n_a + n_b)
+        const double qx = r * (nap.x - nj.x - na.x), qy = r * (nap.y - nj.y - na.y), qz = r * (nap.z - nj.z - na.z);
+        T0 = Vec3{fma(qx, nj.x, T0.x), fma(qx, nj.y, T0.y), fma(qx, nj.z, T0.z)};
+        T1 = Vec3{fma(qy, nj.x, T1.x), fma(qy, nj.y, T1.y), fma(qy, nj.z, T1.z)};
+        T2 = Vec3{fma(qz, nj.x, T2.x), fma(qz, nj.y, T2.y), fma(qz, nj.z, T2.z)};
+        ea = eb;
+        nap = na;
+      }
+    }
+    S0 = Vec3{S0.x + T0.x, S0.y + T0.y, S0.z + T0.z};
+    S1 = Vec3{S1.x + T1.x, S1.y + T1.y, S1.z + T1.z};
+    S2 = Vec3{S2.x + T2.x, S2.y + T2.y, S2.z + T2.z};
+    const bool real = k < len;
+    store_block(k, T0, T1, T2, !real || bc_row || C[k * 32] < 0, false); // (the own column: zeros for now)
+    rp = rpn, ns = ns_next, w0 = nx0, w1 = nx1;
+  }
+
+  // ---- diagonal block: T_ii = -sum_j T_ij; Dirichlet rows -> identity ---------------------------
+  Vec3 diag{1.0, 1.0, 1.0};
+  if (own >= 0)
+    diag = store_block(own, Vec3{-S0.x, -S0.y, -S0.z}, Vec3{-S1.x, -S1.y, -S1.z}, Vec3{-S2.x, -S2.y, -S2.z},
+                       false, bc_row);
+  if (live)
+  {
+    double* di = A.dinv + static_cast<std::int64_t>(row) * 3;
+    di[0] = 1.0 / diag.x;
+    di[1] = 1.0 / diag.y;
+    di[2] = 1.0 / diag.z;
+  }
+}
+
+} // namespace
+
+#ifndef PTB_HOST_EMU // launcher: device build only
+namespace
+{
+template <int WARPS>
+bool launch_ring(ptb_ctx* c, const MatrixArgs& A)
+{
+  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 112 * WARPS * sizeof(double);
+  if (smem > 227 * 1024)
+    return false;
+  auto kernel = assemble_matrix_p1_ring3<WARPS>;
+  PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->ring.p, c->ring_off.p,
+                                                                          c->ring_ns.p);
+  PTB_CUDA(cudaGetLastError());
+  c->launches += 1;
+  return true;
+}
+} // namespace
+
+bool launch_assemble_matrix_ring(ptb_ctx* c, const MatrixArgs& A)
+{
+  if (c->order != 1 || c->bs != 3 || c->ring.p == nullptr)
+    return false;
+  switch (env_int("PTB_RING_WARPS", 4))
+  {
+  case 1: return launch_ring<1>(c, A);
+  case 2: return launch_ring<2>(c, A);
+  default: return launch_ring<4>(c, A);
+  }
+}
+#endif // PTB_HOST_EMU
+
+} // namespace ptb

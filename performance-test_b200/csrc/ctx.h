@@ -157,6 +157,11 @@ struct ptb_ctx
   bool maps_on_device = false;         // adj_off / adjrot / walk built by setup.cu (PTB_GPU_SETUP=1)
   ptb::DevBuf<std::uint32_t> walk1;    // one-vertex-per-step walk (layout.h), PTB_ASM_GWALK=1
   ptb::DevBuf<std::int64_t> walk1_off;
+  // P1 edge rings (layout.h build_rings) of the column-major elasticity kernel (assemble_ring.cu)
+  ptb::DevBuf<std::uint32_t> ring;
+  ptb::DevBuf<std::int64_t> ring_off;
+  ptb::DevBuf<std::uint8_t> ring_ns;
+  double ring_bytes_per_row = 0.0;
   // host copies of the compressed slot map (parity inspection)
   ptb::RowAdjacency h_adj;
   std::vector<std::uint16_t> h_so;

@@ -135,6 +135,9 @@ void launch_assemble_vector(ptb_ctx* c, const VectorArgs& A, const FacetArgs& F)
 /// Star-walk variant (assemble_walk.cu); returns false when it does not apply (no walk uploaded,
 /// not scalar P1, rows longer than 32 columns) and the caller falls through to the default kernel.
 bool launch_assemble_matrix_walk(ptb_ctx* c, const MatrixArgs& A);
+/// Column-major elasticity P1 kernel along the edge rings (assemble_ring.cu); false when the rings are
+/// not on the device (PTB_ASM_RING=0, device-built maps, rows longer than 127 columns).
+bool launch_assemble_matrix_ring(ptb_ctx* c, const MatrixArgs& A);
 /// Direct-gather walk kernel of the P1 cell vector (assemble_gwalk.cu); same convention: false
 /// when the single-reload walk is not on the device (PTB_VEC_GWALK=0, device-built maps).
 bool launch_assemble_vector_gwalk(ptb_ctx* c, const VectorArgs& A);

@@ -201,6 +201,164 @@ WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
   return {steps, loads};
 }
 
+namespace
+{
+// Chains of one row (SellLayout::ring): out[k] = bytes of column k. o = [c][3] in-row offsets of the
+// non-owner vertices of the row's cells (ascending cell order, rotation order inside a cell).
+void ring_chains(const std::vector<std::uint8_t>& o, int c, int len,
+                 std::vector<std::vector<std::uint8_t>>& out)
+{
+  out.resize(len);
+  std::vector<int> va, vb; // the two other vertices of every ring cell of the column
+  std::vector<char> used;
+  for (int k = 0; k < len; ++k)
+  {
+    std::vector<std::uint8_t>& bytes = out[k];
+    bytes.clear();
+    va.clear(), vb.clear();
+    for (int j = 0; j < c; ++j)
+      for (int t = 0; t < 3; ++t)
+        if (o[j * 3 + t] == k)
+        {
+          va.push_back(o[j * 3 + (t + 1) % 3]);
+          vb.push_back(o[j * 3 + (t + 2) % 3]);
+        }
+    const int n = static_cast<int>(va.size());
+    used.assign(n, 0);
+    auto degree = [&](int v) {
+      int d = 0;
+      for (int j = 0; j < n; ++j)
+        d += !used[j] && (va[j] == v || vb[j] == v);
+      return d;
+    };
+    auto next_with = [&](int v, int skip) {
+      for (int j = 0; j < n; ++j)
+        if (!used[j] && j != skip && (va[j] == v || vb[j] == v))
+          return j;
+      return -1;
+    };
+    int left = n;
+    while (left > 0)
+    {
+      int start = -1, v0 = 0, v1 = 0;
+      for (int j = 0; j < n && start < 0; ++j)
+      {
+        if (used[j])
+          continue;
+        if (degree(va[j]) == 1)
+          start = j, v0 = va[j], v1 = vb[j];
+        else if (degree(vb[j]) == 1)
+          start = j, v0 = vb[j], v1 = va[j];
+      }
+      if (start < 0)
+      {
+        for (int j = 0; j < n && start < 0; ++j)
+          if (!used[j])
+            start = j;
+        const int ja = next_with(va[start], start), jb = next_with(vb[start], start);
+        if (ja <= jb)
+          v1 = va[start], v0 = vb[start];
+        else
+          v1 = vb[start], v0 = va[start];
+      }
+      bytes.push_back(static_cast<std::uint8_t>(v0 | 0x80));
+      bytes.push_back(static_cast<std::uint8_t>(v1));
+      used[start] = 1, --left;
+      int cur = v1;
+      for (int j = next_with(cur, -1); j >= 0; j = next_with(cur, -1))
+      {
+        cur = va[j] == cur ? vb[j] : va[j];
+        bytes.push_back(static_cast<std::uint8_t>(cur));
+        used[j] = 1, --left;
+      }
+    }
+  }
+}
+} // namespace
+
+std::int64_t build_rings(std::int32_t n_rows, const std::int64_t* rowptr, const RowAdjacency& adj,
+                         const std::vector<std::uint16_t>& so, SellLayout& L)
+{
+  L.ring.clear(), L.ring_off.clear(), L.ring_ns.clear();
+  if (L.adjrot.empty() || L.max_w > 127)
+    return 0;
+  const std::int32_t S = L.n_slices;
+  const std::uint32_t* pairs = adj.pairs.data();
+  L.ring_ns.assign(static_cast<std::size_t>(L.mat_off[S] / 32), 0);
+  L.ring_off.assign(static_cast<std::size_t>(S) + 1, 0);
+  std::int64_t total = 0;
+  // pass 0: chain lengths -> ring_ns, ring_off; pass 1: the bytes. Rows with the same star (same
+  // offsets in the same cell order) have the same chains: the last result is kept per thread.
+  for (int pass = 0; pass < 2; ++pass)
+  {
+    if (pass == 1)
+    {
+      for (std::int32_t s = 0; s < S; ++s)
+      {
+        std::int64_t words = 0;
+        const std::int64_t k0 = L.mat_off[s] / 32, w = (L.mat_off[s + 1] - L.mat_off[s]) / 32;
+        for (std::int64_t k = 0; k < w; ++k)
+          words += (L.ring_ns[k0 + k] + 3) / 4;
+        L.ring_off[s + 1] = L.ring_off[s] + 32 * words;
+      }
+      L.ring.assign(static_cast<std::size_t>(L.ring_off[S]), 0x80808080u);
+    }
+#pragma omp parallel reduction(+ : total)
+    {
+      std::vector<std::uint8_t> o, last_o;
+      std::vector<std::vector<std::uint8_t>> chains;
+      int last_len = -1;
+#pragma omp for schedule(static)
+      for (std::int32_t s = 0; s < S; ++s)
+      {
+        const std::int64_t k0 = L.mat_off[s] / 32, w = (L.mat_off[s + 1] - L.mat_off[s]) / 32;
+        for (std::int32_t r = 32 * s; r < std::min(n_rows, 32 * s + 32); ++r)
+        {
+          const std::int64_t q0 = adj.ptr[r];
+          const int c = static_cast<int>(adj.ptr[r + 1] - q0);
+          const int len = static_cast<int>(rowptr[r + 1] - rowptr[r]);
+          o.resize(static_cast<std::size_t>(c) * 3);
+          for (int j = 0; j < c; ++j)
+          {
+            const int li = pairs[q0 + j] & 3;
+            for (int t = 1; t < 4; ++t)
+              o[j * 3 + t - 1] = static_cast<std::uint8_t>(so[(q0 + j) * 4 + ((li + t) & 3)]);
+          }
+          if (o != last_o || len != last_len)
+          {
+            ring_chains(o, c, len, chains);
+            last_o = o, last_len = len;
+          }
+          if (pass == 0)
+          {
+            for (int k = 0; k < len; ++k)
+            {
+              if (chains[k].size() > 255)
+                throw std::runtime_error("build_rings: more than 255 chain bytes around one edge");
+              L.ring_ns[k0 + k] = std::max<std::uint8_t>(L.ring_ns[k0 + k], static_cast<std::uint8_t>(chains[k].size()));
+              total += static_cast<std::int64_t>(chains[k].size());
+            }
+            continue;
+          }
+          std::int64_t base = L.ring_off[s] + (r & 31);
+          for (std::int64_t k = 0; k < w; ++k)
+          {
+            const int nw = (L.ring_ns[k0 + k] + 3) / 4;
+            if (k < len)
+              for (std::size_t t = 0; t < chains[k].size(); ++t)
+              {
+                std::uint32_t& word = L.ring[base + static_cast<std::int64_t>(t / 4) * 32];
+                word = (word & ~(0xFFu << (8 * (t % 4)))) | (static_cast<std::uint32_t>(chains[k][t]) << (8 * (t % 4)));
+              }
+            base += static_cast<std::int64_t>(nw) * 32;
+          }
+        }
+      }
+    }
+  }
+  return total;
+}
+
 void build_walk_single(std::int32_t n_rows, const RowAdjacency& adj, SellLayout& L)
 {
   if (L.walk.empty() && L.adj_off[L.n_slices] > 0)

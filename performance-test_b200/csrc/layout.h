@@ -41,6 +41,18 @@ struct SellLayout
   // and the 32 indices are stored in colsx at xoff[s] + j*32 + lane (j-th explicit k of the slice).
   std::vector<std::int32_t> cdelta, colsx;
   std::vector<std::int64_t> xoff; // [n_slices + 1]
+  // P1 only (row length <= 127): *edge rings* (build_rings). For row i and stored column k (a
+  // neighbour j != i) the cells that hold both i and j form a ring (interior edge) or fans
+  // (boundary edge) around the edge (i, j); they are stored as a chain of vertices
+  // v_0, v_1, ..., cell t = (i, j, v_{t-1}, v_t), one byte per vertex: bits 0-6 = in-row offset of
+  // the vertex, bit 7 = restart (the vertex opens a chain: no cell is formed with its predecessor;
+  // always set on byte 0). Padding = 0x80. ring_ns[mat_off[s]/32 + k] = bytes per lane of column k in
+  // slice s (longest chain of the 32 rows; 0 where no row has a ring, e.g. the diagonal); the bytes
+  // are packed four to a word, word q of column k of lane l at
+  // ring[ring_off[s] + (sum_{k' < k} ceil(ring_ns[k'] / 4) + q) * 32 + l].
+  std::vector<std::uint32_t> ring;
+  std::vector<std::int64_t> ring_off; // [n_slices + 1], in words
+  std::vector<std::uint8_t> ring_ns;  // [mat_off[n_slices] / 32]
 };
 constexpr std::int32_t CDELTA_EXPLICIT = INT32_MIN;
 
@@ -67,6 +79,16 @@ struct WalkStats
 };
 WalkStats build_walk(std::int32_t n_rows, const RowAdjacency& adj,
                      const std::vector<std::uint16_t>& so, SellLayout& L);
+
+/// Edge rings of every P1 row (see SellLayout::ring) for the column-major elasticity kernel
+/// (assemble_ring.cu). The chains depend on the mesh topology and the ascending cell order only:
+/// a chain starts at the lowest unvisited cell that has a vertex no other unvisited cell of the ring
+/// shares (the end of a fan; the end vertex comes first), else at the lowest unvisited cell,
+/// walking towards its lower face neighbour; it continues through the lowest unvisited cell that
+/// holds the current vertex. Leaves L.ring empty when a row is longer than 127 columns.
+/// Returns the number of chain bytes over all rows (cells + chains).
+std::int64_t build_rings(std::int32_t n_rows, const std::int64_t* rowptr, const RowAdjacency& adj,
+                         const std::vector<std::uint16_t>& so, SellLayout& L);
 
 /// Derive walk1 / walk1_off from L.walk (see SellLayout::walk1).
 void build_walk_single(std::int32_t n_rows, const RowAdjacency& adj, SellLayout& L);

@@ -58,6 +58,7 @@ alignas(16) double smem[232448 / 8]; // extern __shared__ double smem[] of the k
 
 #include "../../performance-test_b200/csrc/assemble_walk.cu"
 #include "../../performance-test_b200/csrc/assemble_gwalk.cu"
+#include "../../performance-test_b200/csrc/assemble_ring.cu"
 
 namespace
 {
@@ -114,6 +115,25 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
     break;
   default: return 1;
   }
+  return 0;
+}
+
+// assemble_matrix_p1_ring3<warps> (elasticity, column-major along the edge rings)
+int emu_assemble_matrix_ring(int warps, int32_t n_rows, int32_t n_slices, int max_w, const uint8_t* bc,
+                             const int64_t* rowptr, const int64_t* mat_off, const int32_t* cols,
+                             const double* xdof, const uint32_t* ring, const int64_t* ring_off,
+                             const uint8_t* ring_ns, double* vals, double* dinv)
+{
+  using namespace ptb;
+  MatrixArgs A{};
+  A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.rowptr = rowptr, A.mat_off = mat_off;
+  A.cols = cols, A.xdof = xdof, A.max_w = max_w, A.vals = vals, A.dinv = dinv;
+  if (warps == 1)
+    emu_launch(assemble_matrix_p1_ring3<1>, n_slices, 32, A, ring, ring_off, ring_ns);
+  else if (warps == 4)
+    emu_launch(assemble_matrix_p1_ring3<4>, (n_slices + 3) / 4, 128, A, ring, ring_off, ring_ns);
+  else
+    return 1;
   return 0;
 }
 

@@ -531,15 +531,20 @@ def _check_cg(k, rel, k_ref, rel_ref, rtol=1e-8):
 @pytest.mark.parametrize("env,ptype,dims", [
     ("PTB_ASM_WALK3", "elasticity", (4, 5, 3)), ("PTB_ASM_WALK3", "elasticity", (1, 1, 2)),
     ("PTB_ASM_WALK3", "elasticity", (12, 11, 13)),
+    ("PTB_ASM_RING", "elasticity", (4, 5, 3)), ("PTB_ASM_RING", "elasticity", (1, 1, 2)),
+    ("PTB_ASM_RING", "elasticity", (12, 11, 13)), ("PTB_ASM_RING", "elasticity", (33, 3, 2)),
     ("PTB_VEC_GWALK", "poisson", (5, 4, 6)), ("PTB_VEC_GWALK", "poisson", (1, 1, 1)),
     ("PTB_VEC_GWALK", "poisson", (16, 15, 17)), ("PTB_VEC_GWALK", "poisson", (33, 3, 2)),
     ("PTB_VEC_GWALK", "elasticity", (4, 5, 3)), ("PTB_VEC_GWALK", "elasticity", (12, 11, 13))])
 @pytest.mark.parametrize("on", ["1", "0"])
 def test_both_generations_of_the_p1_assembly_kernels_match_oracle(pt, oracle, monkeypatch, env, ptype, dims, on):
-    """The round-2 defaults (elasticity matrix along the star walk, cell vector by direct gather;
-    on = 1) and the kernels they replaced (on = 0), same oracle, same tolerances."""
+    """The round-2 defaults (elasticity matrix column-major along the edge rings, cell vector by direct
+    gather; on = 1) and the kernels they replaced (on = 0: PTB_ASM_RING=0 is the star-walk kernel,
+    PTB_ASM_WALK3=0 with it the first-generation one), same oracle, same tolerances."""
     P = pt.host.Problem(ptype, 1, *dims)
     monkeypatch.setenv(env, on)
+    if env == "PTB_ASM_WALK3":
+        monkeypatch.setenv("PTB_ASM_RING", "0")
     c = pt.abi.Context(0)
     try:
         c.set_problem(P)

@@ -26,7 +26,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "performance-test_b200", "csrc")
 @pytest.fixture(scope="module")
 def emu():
     deps = [SRC] + [os.path.join(CSRC, f) for f in
-                    ("assemble_walk.cu", "assemble_gwalk.cu", "geom.cuh", "kernels.h", "ctx.h")]
+                    ("assemble_walk.cu", "assemble_gwalk.cu", "assemble_ring.cu", "geom.cuh", "kernels.h", "ctx.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
         os.makedirs(os.path.dirname(OUT), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -45,7 +45,7 @@ def emu_fma():
     if "fma" not in open("/proc/cpuinfo").read().split():
         pytest.skip("host CPU without FMA")
     deps = [SRC] + [os.path.join(CSRC, f) for f in
-                    ("assemble_walk.cu", "assemble_gwalk.cu", "geom.cuh", "kernels.h", "ctx.h")]
+                    ("assemble_walk.cu", "assemble_gwalk.cu", "assemble_ring.cu", "geom.cuh", "kernels.h", "ctx.h")]
     if not os.path.exists(OUT_FMA) or any(os.path.getmtime(d) > os.path.getmtime(OUT_FMA) for d in deps):
         os.makedirs(os.path.dirname(OUT_FMA), exist_ok=True)
         cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
@@ -437,6 +437,78 @@ def test_kernel_sources_assemble_partition_independent_bits(pt, emu, variant, pt
         parts.update(assemble(q, 3))
     assert parts.keys() == whole.keys()
     assert all(parts[k] == whole[k] for k in whole)
+
+
+# ---- elasticity P1 along the edge rings (csrc/assemble_ring.cu) ---------------------------------------
+
+def _ring_assemble(pt, lib, P, warps):
+    L, xdof, bc = _inputs(pt, P)
+    ring_off, ring_ns, ring = pt.abi.p1_rings(P["dofmap"], P.n_owned, P["rowptr"], P["cols"], int(L["mat_off"][-1]))
+    vals = np.full(int(L["mat_off"][-1]) * 9, np.nan)
+    dinv = np.full(P.n_owned * 3, np.nan)
+    rp = np.ascontiguousarray(P["rowptr"])
+    assert lib.emu_assemble_matrix_ring(warps, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(rp),
+                                        _p(L["mat_off"]), _p(L["cols"]), _p(xdof), _p(ring), _p(ring_off),
+                                        _p(ring_ns), _p(vals), _p(dinv)) == 0
+    return L, vals, dinv
+
+
+@pytest.mark.parametrize("jitter", [False, True])
+@pytest.mark.parametrize("dims,rank,nranks,warps", [((4, 3, 3), 0, 1, 4), ((1, 1, 2), 0, 1, 1), ((3, 3, 4), 1, 2, 4),
+                                                    ((2, 5, 3), 2, 3, 1), ((9, 2, 2), 0, 1, 4)])
+def test_ring_kernel_source_reproduces_the_oracle(pt, oracle, emu, emu_fma, perturbed, dims, rank, nranks, warps,
+                                                  jitter):
+    """assemble_matrix_p1_ring3 on the host, plain and FMA-contracted build: every stored block within
+    1e-12 of its row's diagonal of the oracle's quadrature kernel (the diagonal block comes from
+    T_ii = -sum_j T_ij), 1/diag, exact zeros in the SELL padding."""
+    P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+    if jitter:
+        P = perturbed(P)
+    ref = oracle.assemble_matrix(P)
+    for lib in (emu, emu_fma):
+        L, vals, dinv = _ring_assemble(pt, lib, P, warps)
+        assert not np.isnan(vals).any(), "a stored value (padding included) was never written"
+        got = _sell_to_csr(P, L, vals, 9)
+        assert (np.abs(got - ref) / _row_diag(P, ref, 9)).max() <= 1e-12
+        A = ref.reshape(-1, 3, 3)
+        rows = np.repeat(np.arange(P.n_owned), np.diff(P["rowptr"]))
+        own = P["cols"] == rows
+        d = np.stack([A[own][:, i, i] for i in range(3)], axis=1).reshape(-1)
+        assert np.allclose(dinv, 1.0 / d, rtol=1e-12, atol=0)
+        mask = np.ones(len(vals), bool)
+        for r in range(P.n_owned):
+            mo = L["mat_off"][r >> 5]
+            for k in range(P["rowptr"][r + 1] - P["rowptr"][r]):
+                for e in range(9):
+                    mask[(mo + k * 32) * 9 + e * 32 + (r & 31)] = False
+        assert np.all(vals[mask] == 0.0)
+
+
+def test_ring_kernel_source_is_partition_independent_off_the_diagonal(pt, emu):
+    """The chains depend on the mesh topology and the ascending cell order only: every off-diagonal
+    block of an owned row has the same bits on 1 rank and on a 3-rank partition; the diagonal block
+    is summed in local column order (ghost columns last) and agrees to a few ulp."""
+    dims = (3, 2, 7)
+
+    def assemble(rank, nranks):
+        P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+        L, vals, _ = _ring_assemble(pt, emu, P, 4)
+        csr = _sell_to_csr(P, L, vals, 9).reshape(-1, 9)
+        glob = np.concatenate([P.global_offset + np.arange(P.n_owned), P["ghost_global"]])
+        rp = P["rowptr"]
+        return {(int(glob[r]), int(glob[P["cols"][k]])): csr[k].copy() for r in range(P.n_owned)
+                for k in range(rp[r], rp[r + 1])}
+
+    whole = assemble(0, 1)
+    parts = {}
+    for q in range(3):
+        parts.update(assemble(q, 3))
+    assert parts.keys() == whole.keys()
+    for (r, c), blk in whole.items():
+        if r != c:
+            assert parts[(r, c)].tobytes() == blk.tobytes()
+        else:
+            assert np.abs(parts[(r, c)] - blk).max() <= 1e-14 * np.abs(blk).max()
 
 
 # ---- P2 / P3 matrix kernels (csrc/assemble_pk.cu): all slices at once, and bin after bin -------------

@@ -386,3 +386,69 @@ def test_walks_on_random_boxes_and_partitions(pt, nx, ny, nz, nranks, rank_pick,
             if compute:
                 seen.append(tuple(pos))
         assert seen == [pos_ for pos_, _ in ref]
+
+
+def _ring_chains(pt, P):
+    """Decode pt.abi.p1_rings into {(row, k): [bytes]} (padding stripped)."""
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    ring_off, ring_ns, ring = pt.abi.p1_rings(P["dofmap"], P.n_owned, P["rowptr"], P["cols"], int(L["mat_off"][-1]))
+    rp = P["rowptr"]
+    out = {}
+    for r in range(P.n_owned):
+        s, lane = r >> 5, r & 31
+        k0 = int(L["mat_off"][s]) // 32
+        w = int(L["mat_off"][s + 1] - L["mat_off"][s]) // 32
+        base = int(ring_off[s]) + lane
+        for k in range(w):
+            ns = int(ring_ns[k0 + k])
+            nw = (ns + 3) // 4
+            by = [(int(ring[base + (t // 4) * 32]) >> (8 * (t % 4))) & 0xFF for t in range(ns)]
+            base += nw * 32
+            if k < rp[r + 1] - rp[r]:
+                while by and by[-1] == 0x80:
+                    by.pop()
+                out[(r, k)] = by
+            else:
+                assert all(b == 0x80 for b in by)
+        assert base == int(ring_off[s]) + lane + (int(ring_off[s + 1]) - int(ring_off[s]))
+    return out
+
+
+@pytest.mark.parametrize("dims,rank,nranks", [((3, 4, 2), 0, 1), ((1, 1, 1), 0, 1), ((4, 3, 5), 1, 2), ((2, 2, 6), 2, 3)])
+def test_edge_rings_cover_every_cell_of_every_edge_once(pt, dims, rank, nranks):
+    """layout.cpp build_rings: for row i and column k (neighbour j) the chain's cells
+    (i, j, v[t-1], v[t]) are exactly the mesh cells that hold i and j, each once; a restart byte opens
+    a chain and forms no cell; the diagonal column has no chain; interior stars of the Kuhn box take
+    72 cells + 14 chain heads."""
+    P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+    dm = np.array(P["dofmap"]).reshape(-1, 4)
+    rp, cols = P["rowptr"], P["cols"]
+    chains = _ring_chains(pt, P)
+    cells_of = {}
+    for c, vs in enumerate(dm):
+        for v in vs:
+            cells_of.setdefault(int(v), []).append(c)
+    full = 0
+    for r in range(P.n_owned):
+        row_cols = cols[rp[r]:rp[r + 1]]
+        total = 0
+        for k, j in enumerate(row_cols):
+            by = chains[(r, k)]
+            if j == r:
+                assert by == []
+                continue
+            want = sorted(tuple(sorted(int(v) for v in dm[c] if v != r and v != j))
+                          for c in cells_of[r] if j in dm[c])
+            assert by and by[0] & 0x80
+            got = []
+            for t in range(1, len(by)):
+                if by[t] & 0x80:
+                    continue
+                got.append(tuple(sorted((int(row_cols[by[t - 1] & 0x7F]), int(row_cols[by[t] & 0x7F])))))
+            assert sorted(got) == want
+            total += len(by)
+        if len(cells_of[r]) == 24:
+            assert total == 72 + 14
+            full += 1
+    if min(dims) >= 2 and nranks == 1:
+        assert full > 0
