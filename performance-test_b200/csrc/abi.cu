@@ -478,6 +478,10 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
           c->ring_off.upload(L.ring_off, c->stream);
           c->ring_ns.upload(L.ring_ns, c->stream);
           c->ring_bytes_per_row = N ? static_cast<double>(nb) / N : 0.0;
+          std::int64_t mrw = 0;
+          for (std::int32_t s = 0; s < L.n_slices; ++s)
+            mrw = std::max(mrw, (L.ring_off[s + 1] - L.ring_off[s]) / 32);
+          c->ring_max_words = static_cast<int>(mrw);
         }
       }
     }

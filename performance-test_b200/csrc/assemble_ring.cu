@@ -33,13 +33,52 @@ namespace ptb
 namespace
 {
 
-constexpr int RING_CHUNK = 8; // star columns staged per trip of the prologue
+constexpr int RING_CHUNK = 8; // star columns / ring words loaded per trip of the prologue
 constexpr std::uint32_t RING_PAD = 0x80808080u;
+// L2 prefetch distance in slices: one generation of resident warps (148 SMs x 14). Measured: with
+// 4096 and plain stores the 3 TB/s write stream evicted the prefetched lines before their use (ncu:
+// DRAM reads 0.71 -> 1.38 GB, L2 hit rate 16 %); the values are therefore stored evict-first (st.cs).
+#ifdef PTB_HOST_EMU
+constexpr int RING_PF_DIST = 3; // tests/emu: tiny meshes must reach the prefetch address arithmetic
+#else
+constexpr int RING_PF_DIST = 2048;
+#endif
+
+__device__ __forceinline__ void store_stream(double* p, double v)
+{
+#ifdef PTB_HOST_EMU
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+
+// 1/d for a normal, finite d: MUFU seed (~2^-21) + one cubic Newton step (-> 2^-63 before rounding).
+// The second step of geom.cuh's rcp_nr only tightens the last ulp; the row's blocks are sums of 4-8
+// such terms against a 1e-12 bound.
+__device__ __forceinline__ double rcp_nr1(double d)
+{
+#ifdef PTB_HOST_EMU
+  return 1.0 / d;
+#else
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  return fma(x, e, x);
+#endif
+}
+
+// Shared memory per slice (one warp), in doubles: E [3 mw][32] edge vectors owner -> column k,
+// RS [rw][32] ring words (uint32), NS [mw] chain bytes per column (uint8, padded to 8 bytes).
+// E and RS are private per lane (column `lane`); NS is the warp's (one __syncwarp after the prologue).
+__host__ __device__ inline int ring_smem_doubles(int mw, int rw) { return mw * 96 + rw * 16 + (mw + 7) / 8; }
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
-                         const std::int64_t* __restrict__ ring_off, const std::uint8_t* __restrict__ ring_ns)
+                         const std::int64_t* __restrict__ ring_off, const std::uint8_t* __restrict__ ring_ns,
+                         int max_rw)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -52,21 +91,53 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
   const bool live = row < A.n_rows;
   const int mw = A.max_w;
 
-  // private column `lane` of the slice's region: E[(k*3+d)*32] edge vectors owner -> column k,
-  // C[k*32] column index with the Dirichlet flag in the top bit. No barrier anywhere.
-  double* E = smem + warp * (mw * 112) + lane;
-  std::int32_t* C = reinterpret_cast<std::int32_t*>(smem + warp * (mw * 112) + mw * 96) + lane;
+  double* base = smem + warp * ring_smem_doubles(mw, max_rw);
+  double* E = base + lane;                                                      // E[(k*3+d)*32]
+  std::uint32_t* RS = reinterpret_cast<std::uint32_t*>(base + mw * 96) + lane;  // RS[q*32]
+  std::uint8_t* NS = reinterpret_cast<std::uint8_t*>(base + mw * 96 + max_rw * 16); // NS[k]
 
+  // ---- prologue: every global read of the slice is issued here ----------------------------------
+  const std::int64_t ro = ring_off[slice];
+  const int rw = static_cast<int>((ring_off[slice + 1] - ro) >> 5);
+  const std::uint32_t* rp = ring + ro + lane;
+  for (int q0 = 0; q0 < rw; q0 += RING_CHUNK)
+  {
+    std::uint32_t wd[RING_CHUNK];
+#pragma unroll
+    for (int j = 0; j < RING_CHUNK; ++j)
+      wd[j] = q0 + j < rw ? __ldg(rp + (q0 + j) * 32) : RING_PAD;
+#pragma unroll
+    for (int j = 0; j < RING_CHUNK; ++j)
+      if (q0 + j < rw)
+        RS[(q0 + j) * 32] = wd[j];
+  }
+  for (int k = lane; k < w; k += 32)
+    NS[k] = __ldg(ring_ns + (mo >> 5) + k);
+  {
+    // Pull the streams of a slice two warp generations ahead into L2: ring words, column indices
+    // (one 128-byte line per lane), row pointers, coordinates. Never past the end of an array.
+    const std::int32_t s2 = slice + RING_PF_DIST;
+    if (s2 < A.n_slices)
+    {
+      const std::int64_t mo2 = A.mat_off[s2], ro2 = ring_off[s2];
+      const int w2 = static_cast<int>((A.mat_off[s2 + 1] - mo2) >> 5);
+      const int rw2 = static_cast<int>((ring_off[s2 + 1] - ro2) >> 5);
+      const std::int64_t r2 = static_cast<std::int64_t>(s2) * 32;
+      for (int j = lane; j < rw2; j += 32)
+        prefetch_l2(ring + ro2 + j * 32);
+      for (int j = lane; j < w2; j += 32)
+        prefetch_l2(A.cols + mo2 + j * 32);
+      if (lane < 8 && r2 + lane * 4 < A.n_rows)
+        prefetch_l2(A.xdof + (r2 + lane * 4) * 4);
+      if (lane < 2 && r2 + lane * 16 < A.n_rows)
+        prefetch_l2(A.rowptr + r2 + lane * 16);
+    }
+  }
   const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
   const bool bc_row = live && A.bc[row];
   const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
-  const std::uint32_t* rp = ring + ring_off[slice] + lane;
-  const std::uint8_t* nsp = ring_ns + (mo >> 5);
-  int ns = w > 0 ? __ldg(nsp) : 0;
-  std::uint32_t w0 = ns > 0 ? __ldg(rp) : RING_PAD, w1 = ns > 4 ? __ldg(rp + 32) : RING_PAD;
-
-  // ---- star: edge vectors and flagged columns of the whole row --------------------------------
   int own = -1;
+  std::uint64_t bcm0 = 0, bcm1 = 0; // bit k: column k of the row is constrained
   for (int k0 = 0; k0 < w; k0 += RING_CHUNK)
   {
     std::int32_t c[RING_CHUNK];
@@ -91,59 +162,57 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
         E[(k * 3 + 0) * 32] = d.x;
         E[(k * 3 + 1) * 32] = d.y;
         E[(k * 3 + 2) * 32] = d.z;
-        C[k * 32] = c[j] | (b[j] ? INT32_MIN : 0);
+        const std::uint64_t bit = b[j] ? std::uint64_t(1) << (k & 63) : 0;
+        bcm0 |= k < 64 ? bit : 0;
+        bcm1 |= k < 64 ? 0 : bit;
         own = c[j] == row && k < len ? k : own;
       }
   }
+  __syncwarp();
   auto edge = [&](int o) { return Vec3{E[(o * 3 + 0) * 32], E[(o * 3 + 1) * 32], E[(o * 3 + 2) * 32]}; };
 
-  constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
-  constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
-  // block[a][b] = mu (delta_ab tr T + T[b][a]) + lambda T[a][b]   (Elasticity.py:33-39), T[a] = row a
-  auto store_block = [&](int k, Vec3 T0, Vec3 T1, Vec3 T2, bool zero, bool identity) {
+  // The walk accumulates 6 T (the 1/6 of the element volume is folded into the material constants):
+  // block[a][b] = mu (delta_ab tr T + T[b][a]) + lambda T[a][b]   (Elasticity.py:12-15, 33-39), T[a] = row a.
+  // A Dirichlet row / column or a padding entry is written as zeros by zeroing the two constants
+  // (every T of a valid mesh is finite).
+  constexpr double mu6 = 1.0e6 / (2.0 * (1.0 + 0.3)) / 6.0;
+  constexpr double lmbda6 = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3)) / 6.0;
+  auto store_block = [&](int k, Vec3 T0, Vec3 T1, Vec3 T2, bool zero) {
+    const double mu = zero ? 0.0 : mu6, lmbda = zero ? 0.0 : lmbda6;
     const double tr = T0.x + T1.y + T2.z;
-    double v[9] = {mu * (tr + T0.x) + lmbda * T0.x, mu * T1.x + lmbda * T0.y, mu * T2.x + lmbda * T0.z,
-                   mu * T0.y + lmbda * T1.x, mu * (tr + T1.y) + lmbda * T1.y, mu * T2.y + lmbda * T1.z,
-                   mu * T0.z + lmbda * T2.x, mu * T1.z + lmbda * T2.y, mu * (tr + T2.z) + lmbda * T2.z};
+    const double v[9] = {mu * (tr + T0.x) + lmbda * T0.x, mu * T1.x + lmbda * T0.y, mu * T2.x + lmbda * T0.z,
+                         mu * T0.y + lmbda * T1.x, mu * (tr + T1.y) + lmbda * T1.y, mu * T2.y + lmbda * T1.z,
+                         mu * T0.z + lmbda * T2.x, mu * T1.z + lmbda * T2.y, mu * (tr + T2.z) + lmbda * T2.z};
     double* out = A.vals + (mo + k * 32) * 9 + lane;
 #pragma unroll
     for (int e = 0; e < 9; ++e)
-    {
-      double val = v[e];
-      if (identity)
-        val = (e == 0 || e == 4 || e == 8) ? 1.0 : 0.0;
-      else if (zero)
-        val = 0.0;
-      out[e * 32] = val;
-      v[e] = val;
-    }
+      store_stream(out + e * 32, v[e]);
     return Vec3{v[0], v[4], v[8]};
   };
 
   // ---- columns ----------------------------------------------------------------------------------
   Vec3 S0{0.0, 0.0, 0.0}, S1 = S0, S2 = S0; // sum of the off-diagonal raw tensors of the row
+  int q = 0;                                // first ring word of the column
   for (int k = 0; k < w; ++k)
   {
-    // ring words of the next column in flight while this one is walked
-    const std::uint32_t* rpn = rp + ((ns + 3) >> 2) * 32;
-    const int ns_next = k + 1 < w ? __ldg(nsp + k + 1) : 0;
-    const std::uint32_t nx0 = ns_next > 0 ? __ldg(rpn) : RING_PAD, nx1 = ns_next > 4 ? __ldg(rpn + 32) : RING_PAD;
-
+    const int ns = NS[k];
     Vec3 T0{0.0, 0.0, 0.0}, T1 = T0, T2 = T0;
     if (ns > 1)
     {
       const Vec3 ej = edge(k);
-      Vec3 ea = edge(w0 & 0x7Fu);
+      std::uint32_t word = RS[q * 32];
+      Vec3 ea = edge(word & 0x7Fu);
       Vec3 nap = cross(ea, ej); // n_a of the step before: e_b x e_j with b = this step's a
       for (int t = 1; t < ns; ++t)
       {
-        const std::uint32_t word = t < 4 ? w0 : (t < 8 ? w1 : __ldg(rp + (t >> 2) * 32));
+        if ((t & 3) == 0)
+          word = RS[(q + (t >> 2)) * 32];
         const std::uint32_t beta = (word >> (8 * (t & 3))) & 0xFFu;
         const Vec3 eb = edge(beta & 0x7Fu);
         // cell (i; j, a, b): n_j = e_a x e_b, n_a = e_b x e_j, n_b = e_j x e_a = -nap
         const Vec3 nj = cross(ea, eb), na = cross(eb, ej);
         const double det = dot(ej, nj);
-        const double r = (beta & 0x80u) ? 0.0 : rcp_nr(6.0 * fabs(det));
+        const double r = (beta & 0x80u) ? 0.0 : rcp_nr1(fabs(det));
         // c_i = -(n_j + n_a + n_b)
         const double qx = r * (nap.x - nj.x - na.x), qy = r * (nap.y - nj.y - na.y), qz = r * (nap.z - nj.z - na.z);
         T0 = Vec3{fma(qx, nj.x, T0.x), fma(qx, nj.y, T0.y), fma(qx, nj.z, T0.z)};
@@ -153,19 +222,23 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
         nap = na;
       }
     }
+    q += (ns + 3) >> 2;
     S0 = Vec3{S0.x + T0.x, S0.y + T0.y, S0.z + T0.z};
     S1 = Vec3{S1.x + T1.x, S1.y + T1.y, S1.z + T1.z};
     S2 = Vec3{S2.x + T2.x, S2.y + T2.y, S2.z + T2.z};
-    const bool real = k < len;
-    store_block(k, T0, T1, T2, !real || bc_row || C[k * 32] < 0, false); // (the own column: zeros for now)
-    rp = rpn, ns = ns_next, w0 = nx0, w1 = nx1;
+    const bool bc_col = ((k < 64 ? bcm0 : bcm1) >> (k & 63)) & 1u;
+    store_block(k, T0, T1, T2, k >= len || bc_row || bc_col); // (the own column: zeros for now)
   }
 
   // ---- diagonal block: T_ii = -sum_j T_ij; Dirichlet rows -> identity ---------------------------
   Vec3 diag{1.0, 1.0, 1.0};
-  if (own >= 0)
-    diag = store_block(own, Vec3{-S0.x, -S0.y, -S0.z}, Vec3{-S1.x, -S1.y, -S1.z}, Vec3{-S2.x, -S2.y, -S2.z},
-                       false, bc_row);
+  if (own >= 0 && !bc_row)
+    diag = store_block(own, Vec3{-S0.x, -S0.y, -S0.z}, Vec3{-S1.x, -S1.y, -S1.z}, Vec3{-S2.x, -S2.y, -S2.z}, false);
+  else if (own >= 0)
+  {
+    double* out = A.vals + (mo + own * 32) * 9 + lane;
+    out[0] = out[4 * 32] = out[8 * 32] = 1.0; // the other six entries were written as zeros by the column loop
+  }
   if (live)
   {
     double* di = A.dinv + static_cast<std::int64_t>(row) * 3;
@@ -183,13 +256,13 @@ namespace
 template <int WARPS>
 bool launch_ring(ptb_ctx* c, const MatrixArgs& A)
 {
-  const std::size_t smem = static_cast<std::size_t>(c->max_w) * 112 * WARPS * sizeof(double);
+  const std::size_t smem = static_cast<std::size_t>(ring_smem_doubles(c->max_w, c->ring_max_words)) * WARPS * sizeof(double);
   if (smem > 227 * 1024)
     return false;
   auto kernel = assemble_matrix_p1_ring3<WARPS>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->ring.p, c->ring_off.p,
-                                                                          c->ring_ns.p);
+                                                                          c->ring_ns.p, c->ring_max_words);
   PTB_CUDA(cudaGetLastError());
   c->launches += 1;
   return true;
@@ -200,11 +273,12 @@ bool launch_assemble_matrix_ring(ptb_ctx* c, const MatrixArgs& A)
 {
   if (c->order != 1 || c->bs != 3 || c->ring.p == nullptr)
     return false;
-  switch (env_int("PTB_RING_WARPS", 4))
+  // one-warp CTAs measured fastest (profiles/r02/assembly_ring_ab_call57.json: 1.376 / 1.412 / 1.431 ms)
+  switch (env_int("PTB_RING_WARPS", 1))
   {
-  case 1: return launch_ring<1>(c, A);
+  case 4: return launch_ring<4>(c, A);
   case 2: return launch_ring<2>(c, A);
-  default: return launch_ring<4>(c, A);
+  default: return launch_ring<1>(c, A);
   }
 }
 #endif // PTB_HOST_EMU

@@ -162,6 +162,7 @@ struct ptb_ctx
   ptb::DevBuf<std::int64_t> ring_off;
   ptb::DevBuf<std::uint8_t> ring_ns;
   double ring_bytes_per_row = 0.0;
+  int ring_max_words = 0; // ring words per lane of the longest slice
   // host copies of the compressed slot map (parity inspection)
   ptb::RowAdjacency h_adj;
   std::vector<std::uint16_t> h_so;

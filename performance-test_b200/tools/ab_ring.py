@@ -34,8 +34,11 @@ def run(ndofs):
     tag = f"{P.n_owned * 3}"
     res[tag] = {"box": [nx * f, ny * f, nz * f], "nnz_blocks": int(P.nnz)}
     ref = None
+    only = os.environ.get("RING_AB_ONLY")  # e.g. "ring" under ncu
     for name, env in (("ring", {}), ("walk3", {"PTB_ASM_RING": "0"}),
                       ("cellorder", {"PTB_ASM_RING": "0", "PTB_ASM_WALK3": "0"})):
+        if only and name != only:
+            continue
         for k in ("PTB_ASM_RING", "PTB_ASM_WALK3", "PTB_RING_WARPS"):
             os.environ.pop(k, None)
         os.environ.update(env)
@@ -55,10 +58,12 @@ def run(ndofs):
         else:
             res[tag][f"{name}_vs_ring_max_rel_row_diag"] = float((np.abs(a - ref).reshape(-1, 9) / scale).max())
         if name == "ring":
-            for warps in (4, 2, 1):
+            for warps in ((4, 2, 1) if not only else ()):
                 os.environ["PTB_RING_WARPS"] = str(warps)
                 res[tag][f"ring_warps{warps}_ms"] = c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 5)
-            os.environ.pop("PTB_RING_WARPS")
+            os.environ.pop("PTB_RING_WARPS", None)
+            if only:
+                res[tag]["ring_ms"] = c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 2)
         else:
             res[tag][f"{name}_ms"] = c.time_kernel(pt.abi.KERNEL_ASSEMBLE_MATRIX, 5)
         res[tag][f"{name}_device_bytes"] = int(c.device_bytes())

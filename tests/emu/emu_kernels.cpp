@@ -48,6 +48,8 @@ static inline double __shfl_xor_sync(unsigned, double v, int o)
   return r;
 }
 
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp[threadIdx.x >> 5]->arrive_and_wait(); }
+
 namespace ptb
 {
 namespace
@@ -122,16 +124,16 @@ int emu_assemble_matrix(int variant, int32_t n_rows, int32_t n_slices, int max_w
 int emu_assemble_matrix_ring(int warps, int32_t n_rows, int32_t n_slices, int max_w, const uint8_t* bc,
                              const int64_t* rowptr, const int64_t* mat_off, const int32_t* cols,
                              const double* xdof, const uint32_t* ring, const int64_t* ring_off,
-                             const uint8_t* ring_ns, double* vals, double* dinv)
+                             const uint8_t* ring_ns, int max_rw, double* vals, double* dinv)
 {
   using namespace ptb;
   MatrixArgs A{};
   A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.rowptr = rowptr, A.mat_off = mat_off;
   A.cols = cols, A.xdof = xdof, A.max_w = max_w, A.vals = vals, A.dinv = dinv;
   if (warps == 1)
-    emu_launch(assemble_matrix_p1_ring3<1>, n_slices, 32, A, ring, ring_off, ring_ns);
+    emu_launch(assemble_matrix_p1_ring3<1>, n_slices, 32, A, ring, ring_off, ring_ns, max_rw);
   else if (warps == 4)
-    emu_launch(assemble_matrix_p1_ring3<4>, (n_slices + 3) / 4, 128, A, ring, ring_off, ring_ns);
+    emu_launch(assemble_matrix_p1_ring3<4>, (n_slices + 3) / 4, 128, A, ring, ring_off, ring_ns, max_rw);
   else
     return 1;
   return 0;

@@ -449,7 +449,7 @@ def _ring_assemble(pt, lib, P, warps):
     rp = np.ascontiguousarray(P["rowptr"])
     assert lib.emu_assemble_matrix_ring(warps, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(rp),
                                         _p(L["mat_off"]), _p(L["cols"]), _p(xdof), _p(ring), _p(ring_off),
-                                        _p(ring_ns), _p(vals), _p(dinv)) == 0
+                                        _p(ring_ns), int(np.diff(ring_off).max()) // 32, _p(vals), _p(dinv)) == 0
     return L, vals, dinv
 
 
