@@ -33,7 +33,9 @@ namespace ptb
 namespace
 {
 
-constexpr int RING_CHUNK = 8; // star columns / ring words loaded per trip of the prologue
+constexpr int RING_CHUNK = 8;   // star columns gathered (coordinates, Dirichlet flags) per trip of the prologue
+constexpr int RING_CCHUNK = 16; // column indices loaded per trip
+constexpr int RING_WCHUNK = 32; // ring words loaded per trip
 constexpr std::uint32_t RING_PAD = 0x80808080u;
 // L2 prefetch distance in slices: one generation of resident warps (148 SMs x 14). Measured: with
 // 4096 and plain stores the 3 TB/s write stream evicted the prefetched lines before their use (ncu:
@@ -75,7 +77,7 @@ __device__ __forceinline__ double rcp_nr1(double d)
 __host__ __device__ inline int ring_smem_doubles(int mw, int rw) { return mw * 96 + rw * 16 + (mw + 7) / 8; }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
+__global__ void __launch_bounds__(WARPS * 32, 14 / WARPS) // 14 slices per SM fit in shared memory on the Kuhn box
 assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
                          const std::int64_t* __restrict__ ring_off, const std::uint8_t* __restrict__ ring_ns,
                          int max_rw)
@@ -96,25 +98,38 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
   std::uint32_t* RS = reinterpret_cast<std::uint32_t*>(base + mw * 96) + lane;  // RS[q*32]
   std::uint8_t* NS = reinterpret_cast<std::uint8_t*>(base + mw * 96 + max_rw * 16); // NS[k]
 
-  // ---- prologue: every global read of the slice is issued here ----------------------------------
+  // ---- prologue: every global read of the slice is issued here, independent loads together -------
+  // (ncu of the first version: a fifth of the stall samples sat in eight serialised load -> store trips)
   const std::int64_t ro = ring_off[slice];
   const int rw = static_cast<int>((ring_off[slice + 1] - ro) >> 5);
   const std::uint32_t* rp = ring + ro + lane;
-  for (int q0 = 0; q0 < rw; q0 += RING_CHUNK)
-  {
-    std::uint32_t wd[RING_CHUNK];
+  std::uint32_t wd[RING_WCHUNK];
+  auto load_ring = [&](int q0) {
 #pragma unroll
-    for (int j = 0; j < RING_CHUNK; ++j)
+    for (int j = 0; j < RING_WCHUNK; ++j)
       wd[j] = q0 + j < rw ? __ldg(rp + (q0 + j) * 32) : RING_PAD;
+  };
+  auto store_ring = [&](int q0) {
 #pragma unroll
-    for (int j = 0; j < RING_CHUNK; ++j)
+    for (int j = 0; j < RING_WCHUNK; ++j)
       if (q0 + j < rw)
         RS[(q0 + j) * 32] = wd[j];
-  }
+  };
+  std::int32_t c[RING_CCHUNK];
+  auto load_cols = [&](int k0) {
+#pragma unroll
+    for (int j = 0; j < RING_CCHUNK; ++j)
+      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
+  };
+  load_ring(0);
+  load_cols(0);
   for (int k = lane; k < w; k += 32)
     NS[k] = __ldg(ring_ns + (mo >> 5) + k);
+  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
+  const bool bc_row = live && A.bc[row];
+  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
   {
-    // Pull the streams of a slice two warp generations ahead into L2: ring words, column indices
+    // Pull the streams of a slice one warp generation ahead into L2: ring words, column indices
     // (one 128-byte line per lane), row pointers, coordinates. Never past the end of an array.
     const std::int32_t s2 = slice + RING_PF_DIST;
     if (s2 < A.n_slices)
@@ -133,40 +148,45 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
         prefetch_l2(A.rowptr + r2 + lane * 16);
     }
   }
-  const int len = live ? static_cast<int>(A.rowptr[row + 1] - A.rowptr[row]) : 0;
-  const bool bc_row = live && A.bc[row];
-  const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
+  store_ring(0);
+  for (int q0 = RING_WCHUNK; q0 < rw; q0 += RING_WCHUNK)
+  {
+    load_ring(q0);
+    store_ring(q0);
+  }
   int own = -1;
   std::uint64_t bcm0 = 0, bcm1 = 0; // bit k: column k of the row is constrained
-  for (int k0 = 0; k0 < w; k0 += RING_CHUNK)
+  for (int k0 = 0; k0 < w; k0 += RING_CCHUNK)
   {
-    std::int32_t c[RING_CHUNK];
+    if (k0 > 0)
+      load_cols(k0);
 #pragma unroll
-    for (int j = 0; j < RING_CHUNK; ++j)
-      c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
-    Vec3 x[RING_CHUNK];
-    std::uint8_t b[RING_CHUNK];
+    for (int h = 0; h < RING_CCHUNK; h += RING_CHUNK)
+    {
+      Vec3 x[RING_CHUNK];
+      std::uint8_t b[RING_CHUNK];
 #pragma unroll
-    for (int j = 0; j < RING_CHUNK; ++j)
-      if (c[j] >= 0)
-      {
-        x[j] = load_point(A.xdof, c[j]);
-        b[j] = __ldg(A.bc + c[j]);
-      }
+      for (int j = 0; j < RING_CHUNK; ++j)
+        if (c[h + j] >= 0)
+        {
+          x[j] = load_point(A.xdof, c[h + j]);
+          b[j] = __ldg(A.bc + c[h + j]);
+        }
 #pragma unroll
-    for (int j = 0; j < RING_CHUNK; ++j)
-      if (c[j] >= 0)
-      {
-        const int k = k0 + j;
-        const Vec3 d = x[j] - X0;
-        E[(k * 3 + 0) * 32] = d.x;
-        E[(k * 3 + 1) * 32] = d.y;
-        E[(k * 3 + 2) * 32] = d.z;
-        const std::uint64_t bit = b[j] ? std::uint64_t(1) << (k & 63) : 0;
-        bcm0 |= k < 64 ? bit : 0;
-        bcm1 |= k < 64 ? 0 : bit;
-        own = c[j] == row && k < len ? k : own;
-      }
+      for (int j = 0; j < RING_CHUNK; ++j)
+        if (c[h + j] >= 0)
+        {
+          const int k = k0 + h + j;
+          const Vec3 d = x[j] - X0;
+          E[(k * 3 + 0) * 32] = d.x;
+          E[(k * 3 + 1) * 32] = d.y;
+          E[(k * 3 + 2) * 32] = d.z;
+          const std::uint64_t bit = b[j] ? std::uint64_t(1) << (k & 63) : 0;
+          bcm0 |= k < 64 ? bit : 0;
+          bcm1 |= k < 64 ? 0 : bit;
+          own = c[h + j] == row && k < len ? k : own;
+        }
+    }
   }
   __syncwarp();
   auto edge = [&](int o) { return Vec3{E[(o * 3 + 0) * 32], E[(o * 3 + 1) * 32], E[(o * 3 + 2) * 32]}; };
