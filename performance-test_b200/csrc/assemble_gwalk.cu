@@ -38,7 +38,7 @@ struct InFlight
 template <int NF>
 __device__ __forceinline__ InFlight<NF> gw_issue(std::uint32_t word, const std::int32_t* C,
                                                  const double* __restrict__ xdof,
-                                                 const double* __restrict__ f, int bs, int a)
+                                                 const double* __restrict__ f)
 {
   const bool loads = word != ADJ_INVALID_DEV && ((word >> 16) & 3u) != 3u;
   const int slot = loads ? static_cast<int>(word & 0xFFu) : 0;
@@ -49,8 +49,9 @@ __device__ __forceinline__ InFlight<NF> gw_issue(std::uint32_t word, const std::
   v.cw = cw;
   v.xy = __ldg(p);
   v.z_ = __ldg(p + 1);
-  if constexpr (NF > 0)
-    v.f[0] = __ldg(f + col * bs + a);
+#pragma unroll
+  for (int a = 0; a < NF; ++a)
+    v.f[a] = __ldg(f + col * NF + a);
   return v;
 }
 
@@ -69,8 +70,10 @@ __device__ __forceinline__ StepBits gw_decode(std::uint32_t word)
 
 // ------------------------------------------------------------------------------------------
 // Cell vector, P1, BS = 1 or 3: b[row*BS + a] = sum_cells |det|/120 (sum_j f_j + f_own).
-// One warp = (slice, component a); warps are independent (each keeps its own copy of the
-// column list: 1.9 KB), no barrier, no accumulators in shared memory.
+// One warp = one slice, one thread = one block row: the BS components share the walk, the gathered
+// coordinates and |det| (until round 2 every component had its own warp and repeated all three;
+// 1.06 ms at 10 M DOFs). Warps are independent (each keeps its own copy of the column list:
+// 1.9 KB), no barrier, no accumulators in shared memory.
 // ------------------------------------------------------------------------------------------
 template <int BS, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -79,9 +82,7 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const std::int32_t gw = blockIdx.x * WARPS + warp;
-  const std::int32_t slice = gw / BS;
-  const int a = gw - slice * BS;
+  const std::int32_t slice = blockIdx.x * WARPS + warp;
   if (slice >= A.n_slices)
     return;
   const std::int64_t mo = A.mat_off[slice], so = walk1_off[slice];
@@ -99,7 +100,10 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
   for (int j = 0; j < GW_CHUNK; ++j)
     wd[j] = j < nsteps ? __ldg(wp + j * 32) : ADJ_INVALID_DEV;
   const bool bc_row = live && A.bc[row];
-  const double f_own = live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
+  double f_own[BS];
+#pragma unroll
+  for (int a = 0; a < BS; ++a)
+    f_own[a] = live ? __ldg(A.f + static_cast<std::int64_t>(row) * BS + a) : 0.0;
   const Vec3 X0 = live ? load_point(A.xdof, row) : Vec3{0.0, 0.0, 0.0};
   for (int k0 = 0; k0 < w; k0 += 16)
   {
@@ -120,27 +124,41 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
   Vec3 e0 = load_point(A.xdof, c0) - X0;
   Vec3 e1 = load_point(A.xdof, c1) - X0;
   Vec3 e2 = load_point(A.xdof, c2) - X0;
-  double f0 = __ldg(A.f + c0 * BS + a), f1 = __ldg(A.f + c1 * BS + a), f2 = __ldg(A.f + c2 * BS + a);
-  InFlight<1> q[GW_AHEAD];
+  double f0[BS], f1[BS], f2[BS], sum[BS];
+#pragma unroll
+  for (int a = 0; a < BS; ++a)
+  {
+    f0[a] = __ldg(A.f + c0 * BS + a), f1[a] = __ldg(A.f + c1 * BS + a), f2[a] = __ldg(A.f + c2 * BS + a);
+    sum[a] = 0.0;
+  }
+  InFlight<BS> q[GW_AHEAD];
 #pragma unroll
   for (int j = 0; j < GW_AHEAD; ++j)
-    q[j] = gw_issue<1>(wd[j], C, A.xdof, A.f, BS, a);
-  double sum = 0.0;
+    q[j] = gw_issue<BS>(wd[j], C, A.xdof, A.f);
   auto cell = [&](bool compute) {
     const double det = dot(e0, cross(e1, e2));
     const double wgt = compute ? fabs(det) * (1.0 / 120.0) : 0.0;
-    sum = fma(wgt, ((f_own + f0) + (f1 + f2)) + f_own, sum);
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      sum[a] = fma(wgt, ((f_own[a] + f0[a]) + (f1[a] + f2[a])) + f_own[a], sum[a]);
   };
   cell(valid0);
-  auto step = [&](std::uint32_t word, const InFlight<1>& v) {
+  auto step = [&](std::uint32_t word, const InFlight<BS>& v) {
     const StepBits S = gw_decode(word);
     const Vec3 xn = {v.xy.x, v.xy.y, v.z_.x};
     if (S.p0)
-      e0 = xn - X0, f0 = v.f[0];
+      e0 = xn - X0;
     if (S.p1)
-      e1 = xn - X0, f1 = v.f[0];
+      e1 = xn - X0;
     if (S.p2)
-      e2 = xn - X0, f2 = v.f[0];
+      e2 = xn - X0;
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+    {
+      f0[a] = S.p0 ? v.f[a] : f0[a];
+      f1[a] = S.p1 ? v.f[a] : f1[a];
+      f2[a] = S.p2 ? v.f[a] : f2[a];
+    }
     cell(S.compute);
   };
   for (int k0 = 0; k0 < nsteps; k0 += GW_CHUNK)
@@ -152,10 +170,10 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
 #pragma unroll
     for (int j = 0; j < GW_CHUNK; ++j)
     {
-      const InFlight<1> cur = q[j % GW_AHEAD];
+      const InFlight<BS> cur = q[j % GW_AHEAD];
       const std::uint32_t ahead = j + GW_AHEAD < GW_CHUNK ? wd[(j + GW_AHEAD) % GW_CHUNK]
                                                           : nx[(j + GW_AHEAD) % GW_CHUNK];
-      q[j % GW_AHEAD] = gw_issue<1>(ahead, C, A.xdof, A.f, BS, a);
+      q[j % GW_AHEAD] = gw_issue<BS>(ahead, C, A.xdof, A.f);
       step(wd[j], cur);
     }
 #pragma unroll
@@ -163,7 +181,11 @@ assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
       wd[j] = nx[j];
   }
   if (live)
-    A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum;
+  {
+#pragma unroll
+    for (int a = 0; a < BS; ++a)
+      A.b[static_cast<std::int64_t>(row) * BS + a] = bc_row ? 0.0 : sum[a];
+  }
 }
 
 } // namespace
@@ -177,7 +199,7 @@ void launch_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t) * WARPS;
   auto kernel = assemble_vector_p1_gwalk<BS, WARPS>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const std::int64_t warps = static_cast<std::int64_t>(A.n_slices) * BS;
+  const std::int64_t warps = A.n_slices;
   kernel<<<static_cast<unsigned>((warps + WARPS - 1) / WARPS), WARPS * 32, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
 }
 

@@ -148,7 +148,8 @@ int emu_assemble_vector(int bs, int warps, int32_t n_rows, int32_t n_slices, int
   VectorArgs A{};
   A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.mat_off = mat_off, A.cols = cols;
   A.xdof = xdof, A.max_w = max_w, A.f = f, A.b = b;
-  const unsigned nw = static_cast<unsigned>(n_slices) * bs;
+  const unsigned nw = static_cast<unsigned>(n_slices); // one warp per slice, all components
+  (void)bs;
   if (bs == 1 && warps == 4)
     emu_launch(assemble_vector_p1_gwalk<1, 4>, (nw + 3) / 4, 128, A, walk1, walk1_off);
   else if (bs == 1 && warps == 1)
