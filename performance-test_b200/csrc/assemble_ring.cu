@@ -46,31 +46,6 @@ constexpr int RING_PF_DIST = 3; // tests/emu: tiny meshes must reach the prefetc
 constexpr int RING_PF_DIST = 2048;
 #endif
 
-__device__ __forceinline__ void store_stream(double* p, double v)
-{
-#ifdef PTB_HOST_EMU
-  *p = v;
-#else
-  __stcs(p, v);
-#endif
-}
-
-// 1/d for a normal, finite d: MUFU seed (~2^-21) + one cubic Newton step (-> 2^-63 before rounding).
-// The second step of geom.cuh's rcp_nr only tightens the last ulp; the row's blocks are sums of 4-8
-// such terms against a 1e-12 bound.
-__device__ __forceinline__ double rcp_nr1(double d)
-{
-#ifdef PTB_HOST_EMU
-  return 1.0 / d;
-#else
-  double x;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
-  double e = fma(-d, x, 1.0);
-  e = fma(e, e, e);
-  return fma(x, e, x);
-#endif
-}
-
 // Shared memory per slice (one warp), in doubles: E [3 mw][32] edge vectors owner -> column k,
 // RS [rw][32] ring words (uint32), NS [mw] chain bytes per column (uint8, padded to 8 bytes).
 // E and RS are private per lane (column `lane`); NS is the warp's (one __syncwarp after the prologue).

@@ -189,7 +189,7 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
         W.n2 = cross(W.e0, W.e1);
     }
     const double det = dot(W.e0, W.n0);
-    const double r = valid ? rcp_nr(6.0 * fabs(det)) : 0.0;
+    const double r = valid ? rcp_nr1(6.0 * fabs(det)) : 0.0;
     const Vec3 c0 = {-(W.n0.x + W.n1.x + W.n2.x), -(W.n0.y + W.n1.y + W.n2.y),
                      -(W.n0.z + W.n1.z + W.n2.z)};
     W.dg = fma(r, dot(c0, c0), W.dg);
@@ -225,7 +225,7 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
       val = is_own ? 1.0 : 0.0;
     if (!real)
       val = 0.0;
-    A.vals[mo + k * 32 + lane] = val;
+    store_stream(A.vals + mo + k * 32 + lane, val); // evict-first: the value stream must not push the stars out of L2
     diag = is_own ? val : diag;
   }
   if (live)

@@ -84,6 +84,32 @@ __device__ __forceinline__ double rcp_nr(double d)
 #endif
 }
 
+// 1/d for a normal, finite d: MUFU seed (~2^-21) + one cubic Newton step (-> 2^-63 before rounding).
+// The second step of rcp_nr only tightens the last ulp; the row's blocks are sums of 4-8
+// such terms against a 1e-12 bound.
+__device__ __forceinline__ double rcp_nr1(double d)
+{
+#ifdef PTB_HOST_EMU
+  return 1.0 / d;
+#else
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+  double e = fma(-d, x, 1.0);
+  e = fma(e, e, e);
+  return fma(x, e, x);
+#endif
+}
+
+// Evict-first store for streams that are written once and not read by the kernel.
+__device__ __forceinline__ void store_stream(double* p, double v)
+{
+#ifdef PTB_HOST_EMU
+  *p = v;
+#else
+  __stcs(p, v);
+#endif
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p)
 {
 #ifdef PTB_HOST_EMU
