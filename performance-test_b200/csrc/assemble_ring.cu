@@ -26,6 +26,7 @@
 #include "geom.cuh"
 #include "envopt.h"
 #include "kernels.h"
+#include "tma.cuh"
 #include <climits>
 
 namespace ptb
@@ -47,11 +48,19 @@ constexpr int RING_PF_DIST = 2048;
 #endif
 
 // Shared memory per slice (one warp), in doubles: E [3 mw][32] edge vectors owner -> column k,
-// RS [rw][32] ring words (uint32), NS [mw] chain bytes per column (uint8, padded to 8 bytes).
-// E and RS are private per lane (column `lane`); NS is the warp's (one __syncwarp after the prologue).
-__host__ __device__ inline int ring_smem_doubles(int mw, int rw) { return mw * 96 + rw * 16 + (mw + 7) / 8; }
+// RS [rw][32] ring words (uint32), NS [mw] chain bytes per column (uint8, padded to 8 bytes), one
+// mbarrier; rounded to 16 bytes. E and RS are private per lane (column `lane`); NS is the warp's
+// (one __syncwarp after the prologue).
+__host__ __device__ inline int ring_smem_doubles(int mw, int rw)
+{
+  return (mw * 96 + rw * 16 + (mw + 7) / 8 + 1 + 1) & ~1;
+}
 
-template <int WARPS>
+// TMA = true: the slice's ring words -- one contiguous block of rw x 128 bytes whose global layout
+// [word][lane] is the shared-memory layout -- are staged by ONE bulk copy through the TMA unit
+// (cp.async.bulk, SASS UBLKCP) issued by lane 0 and awaited on an mbarrier just before the column loop,
+// instead of rw LDG + STS per lane through registers.
+template <int WARPS, bool TMA>
 __global__ void __launch_bounds__(WARPS * 32, 14 / WARPS) // 14 slices per SM fit in shared memory on the Kuhn box
 assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
                          const std::int64_t* __restrict__ ring_off, const std::uint8_t* __restrict__ ring_ns,
@@ -72,6 +81,18 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
   double* E = base + lane;                                                      // E[(k*3+d)*32]
   std::uint32_t* RS = reinterpret_cast<std::uint32_t*>(base + mw * 96) + lane;  // RS[q*32]
   std::uint8_t* NS = reinterpret_cast<std::uint8_t*>(base + mw * 96 + max_rw * 16); // NS[k]
+#ifndef PTB_HOST_EMU
+  std::uint64_t* bar = reinterpret_cast<std::uint64_t*>(base + mw * 96 + max_rw * 16 + (mw + 7) / 8);
+  if constexpr (TMA)
+  {
+    if (lane == 0)
+    {
+      mbar_init(bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
+#endif
 
   // ---- prologue: every global read of the slice is issued here, independent loads together -------
   // (ncu of the first version: a fifth of the stall samples sat in eight serialised load -> store trips)
@@ -96,7 +117,19 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
     for (int j = 0; j < RING_CCHUNK; ++j)
       c[j] = k0 + j < w ? __ldg(A.cols + mo + (k0 + j) * 32 + lane) : -1;
   };
-  load_ring(0);
+#ifndef PTB_HOST_EMU
+  if constexpr (TMA)
+  {
+    if (lane == 0)
+    {
+      mbar_expect_tx(bar, static_cast<std::uint32_t>(rw) * 128u);
+      if (rw > 0)
+        tma_load_1d(base + mw * 96, ring + ro, static_cast<std::uint32_t>(rw) * 128u, bar);
+    }
+  }
+  else
+#endif
+    load_ring(0);
   load_cols(0);
   for (int k = lane; k < w; k += 32)
     NS[k] = __ldg(ring_ns + (mo >> 5) + k);
@@ -123,11 +156,16 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
         prefetch_l2(A.rowptr + r2 + lane * 16);
     }
   }
-  store_ring(0);
-  for (int q0 = RING_WCHUNK; q0 < rw; q0 += RING_WCHUNK)
+#ifndef PTB_HOST_EMU
+  if constexpr (!TMA)
+#endif
   {
-    load_ring(q0);
-    store_ring(q0);
+    store_ring(0);
+    for (int q0 = RING_WCHUNK; q0 < rw; q0 += RING_WCHUNK)
+    {
+      load_ring(q0);
+      store_ring(q0);
+    }
   }
   int own = -1;
   std::uint64_t bcm0 = 0, bcm1 = 0; // bit k: column k of the row is constrained
@@ -163,6 +201,10 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
         }
     }
   }
+#ifndef PTB_HOST_EMU
+  if constexpr (TMA)
+    mbar_wait(bar, 0);
+#endif
   __syncwarp();
   auto edge = [&](int o) { return Vec3{E[(o * 3 + 0) * 32], E[(o * 3 + 1) * 32], E[(o * 3 + 2) * 32]}; };
 
@@ -248,13 +290,13 @@ assemble_matrix_p1_ring3(MatrixArgs A, const std::uint32_t* __restrict__ ring,
 #ifndef PTB_HOST_EMU // launcher: device build only
 namespace
 {
-template <int WARPS>
+template <int WARPS, bool TMA>
 bool launch_ring(ptb_ctx* c, const MatrixArgs& A)
 {
   const std::size_t smem = static_cast<std::size_t>(ring_smem_doubles(c->max_w, c->ring_max_words)) * WARPS * sizeof(double);
   if (smem > 227 * 1024)
     return false;
-  auto kernel = assemble_matrix_p1_ring3<WARPS>;
+  auto kernel = assemble_matrix_p1_ring3<WARPS, TMA>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   kernel<<<(A.n_slices + WARPS - 1) / WARPS, WARPS * 32, smem, c->stream>>>(A, c->ring.p, c->ring_off.p,
                                                                           c->ring_ns.p, c->ring_max_words);
@@ -269,11 +311,12 @@ bool launch_assemble_matrix_ring(ptb_ctx* c, const MatrixArgs& A)
   if (c->order != 1 || c->bs != 3 || c->ring.p == nullptr)
     return false;
   // one-warp CTAs measured fastest (profiles/r02/assembly_ring_ab_call57.json: 1.376 / 1.412 / 1.431 ms)
+  const bool tma = env_flag("PTB_RING_TMA", true);
   switch (env_int("PTB_RING_WARPS", 1))
   {
-  case 4: return launch_ring<4>(c, A);
-  case 2: return launch_ring<2>(c, A);
-  default: return launch_ring<1>(c, A);
+  case 4: return tma ? launch_ring<4, true>(c, A) : launch_ring<4, false>(c, A);
+  case 2: return tma ? launch_ring<2, true>(c, A) : launch_ring<2, false>(c, A);
+  default: return tma ? launch_ring<1, true>(c, A) : launch_ring<1, false>(c, A);
   }
 }
 #endif // PTB_HOST_EMU

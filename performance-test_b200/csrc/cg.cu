@@ -15,6 +15,7 @@
 #include "layout.h"
 #include "peer.cuh"
 #include "reduce.cuh"
+#include "tma.cuh"
 #include <algorithm>
 #include <climits>
 #include <cmath>
@@ -562,41 +563,6 @@ spmv_sell(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgSt
 // ------------------------------------------------------------------------------------------
 constexpr int TMA_STAGES = 3;
 constexpr int TMA_THREADS = 256;
-
-__device__ __forceinline__ std::uint32_t smem_u32(const void* p)
-{
-  return static_cast<std::uint32_t>(__cvta_generic_to_shared(p));
-}
-__device__ __forceinline__ void mbar_init(std::uint64_t* bar, std::uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(std::uint64_t* bar, std::uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
-               "r"(bytes)
-               : "memory");
-}
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, std::uint32_t bytes,
-                                            std::uint64_t* bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void mbar_wait(std::uint64_t* bar, std::uint32_t parity)
-{
-  std::uint32_t ok = 0;
-  const std::uint32_t a = smem_u32(bar);
-  do
-  {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                 "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok)
-                 : "r"(a), "r"(parity)
-                 : "memory");
-  } while (!ok);
-}
 
 __global__ void __launch_bounds__(TMA_THREADS, 2)
 spmv_sell_tma(SpmvArgs A, const double* __restrict__ p, double* __restrict__ y, CgState* st,

@@ -131,9 +131,9 @@ int emu_assemble_matrix_ring(int warps, int32_t n_rows, int32_t n_slices, int ma
   A.n_rows = n_rows, A.n_slices = n_slices, A.bc = bc, A.rowptr = rowptr, A.mat_off = mat_off;
   A.cols = cols, A.xdof = xdof, A.max_w = max_w, A.vals = vals, A.dinv = dinv;
   if (warps == 1)
-    emu_launch(assemble_matrix_p1_ring3<1>, n_slices, 32, A, ring, ring_off, ring_ns, max_rw);
+    emu_launch(assemble_matrix_p1_ring3<1, false>, n_slices, 32, A, ring, ring_off, ring_ns, max_rw);
   else if (warps == 4)
-    emu_launch(assemble_matrix_p1_ring3<4>, (n_slices + 3) / 4, 128, A, ring, ring_off, ring_ns, max_rw);
+    emu_launch(assemble_matrix_p1_ring3<4, false>, (n_slices + 3) / 4, 128, A, ring, ring_off, ring_ns, max_rw);
   else
     return 1;
   return 0;
