@@ -190,6 +190,15 @@ void ptb_destroy(ptb_ctx* c)
     cudaEventDestroy(c->ev0);
   if (c->ev1)
     cudaEventDestroy(c->ev1);
+  for (int i = 0; i < ptb_ctx::N_BIN_STREAMS; ++i)
+  {
+    if (c->bin_streams[i])
+      cudaStreamDestroy(c->bin_streams[i]);
+    if (c->bin_join[i])
+      cudaEventDestroy(c->bin_join[i]);
+  }
+  if (c->bin_fork)
+    cudaEventDestroy(c->bin_fork);
   if (c->own_stream)
     cudaStreamDestroy(c->own_stream);
   delete c;

@@ -39,6 +39,23 @@ __device__ __forceinline__ Vec3 load_point(const double* __restrict__ xyz4, std:
 
 constexpr int PK_THREADS = 128;
 
+// Reference tensors in shared memory: [plane][li][LD] with an odd row stride LD = ND | 1. A lane reads
+// row li of a plane for ITS local index, so at a given (plane, j) the 32 lanes of a warp hit up to ND
+// different rows; with the natural stride ND = 20 (160 B) those rows fall into four bank groups
+// (five-way conflicts on every load of the P3 kernels' inner loop); with 21 doubles the first 16
+// rows are conflict free and rows 16..19 pair up with rows 0..3.
+template <int ND>
+struct PkTab
+{
+  static constexpr int LD = ND | 1;
+  static constexpr int PLANE = ND * LD;
+  __device__ static void stage(double* dst, const double* __restrict__ src, int planes)
+  {
+    for (int i = threadIdx.x; i < planes * ND * ND; i += blockDim.x)
+      dst[(i / ND) * LD + (i % ND)] = src[i];
+  }
+};
+
 // In-row slot offset of local column j from the packed words of a pair.
 template <int ND, bool WIDE>
 __device__ __forceinline__ int slot_of(const std::uint32_t* w, int j)
@@ -55,9 +72,8 @@ assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
 {
   constexpr int NW = WIDE ? (ND + 1) / 2 : (ND + 3) / 4;
   extern __shared__ double smem[];
-  double* St = smem; // [6][ND][ND]
-  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
-    St[i] = Sg[i];
+  double* St = smem; // [6][ND][LD]
+  PkTab<ND>::stage(St, Sg, 6);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -70,7 +86,7 @@ assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
   const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
   const std::int64_t ao = A.adj_off[slice];
   const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
-  double* acc = smem + 6 * ND * ND + warp * (A.max_w * 32);
+  double* acc = smem + 6 * PkTab<ND>::PLANE + warp * (A.max_w * 32);
   for (int k = 0; k < w; ++k)
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
@@ -95,13 +111,13 @@ assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
     const double inv = 1.0 / fabs(dot(e1, c1));
     const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
                  G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
-    const double* S = St + li * ND;
+    const double* S = St + li * PkTab<ND>::LD;
 #pragma unroll
     for (int j = 0; j < ND; ++j)
     {
-      const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
-                         + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
-                         + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+      const double val = G00 * S[0 * PkTab<ND>::PLANE + j] + G01 * S[1 * PkTab<ND>::PLANE + j]
+                         + G02 * S[2 * PkTab<ND>::PLANE + j] + G11 * S[3 * PkTab<ND>::PLANE + j]
+                         + G12 * S[4 * PkTab<ND>::PLANE + j] + G22 * S[5 * PkTab<ND>::PLANE + j];
       acc[slot_of<ND, WIDE>(words, j) * 32 + lane] += val;
     }
   }
@@ -139,9 +155,8 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
 {
   constexpr int NW = WIDE ? (ND + 1) / 2 : (ND + 3) / 4;
   extern __shared__ double smem[];
-  double* St = smem; // [6][ND][ND]
-  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
-    St[i] = Sg[i];
+  double* St = smem; // [6][ND][LD]
+  PkTab<ND>::stage(St, Sg, 6);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -155,7 +170,7 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
   const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
   const std::int64_t ao = A.adj_off[slice];
   const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
-  double* acc = smem + 6 * ND * ND + warp * (bin_w * 32);
+  double* acc = smem + 6 * PkTab<ND>::PLANE + warp * (bin_w * 32);
   for (int k = 0; k < w; ++k)
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
@@ -202,24 +217,25 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
       const double inv = 1.0 / fabs(dot(e1, c1));
       const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
                    G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
-      const double* S = St + li[u] * ND;
+      const double* S = St + li[u] * PkTab<ND>::LD;
 #pragma unroll
       for (int j = 0; j < ND; ++j)
       {
-        const double val = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j]
-                           + G02 * S[2 * ND * ND + j] + G11 * S[3 * ND * ND + j]
-                           + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+        const double val = G00 * S[0 * PkTab<ND>::PLANE + j] + G01 * S[1 * PkTab<ND>::PLANE + j]
+                           + G02 * S[2 * PkTab<ND>::PLANE + j] + G11 * S[3 * PkTab<ND>::PLANE + j]
+                           + G12 * S[4 * PkTab<ND>::PLANE + j] + G22 * S[5 * PkTab<ND>::PLANE + j];
         acc[slot_of<ND, WIDE>(words[u], j) * 32 + lane] += val;
       }
     }
   }
 
-  // Epilogue in chunks of eight entries: column indices, then their Dirichlet flags, then the
-  // stores -- two exposed load latencies per eight values instead of two per value.
+  // Epilogue in chunks of 32 entries: column indices, then their Dirichlet flags, then the stores --
+  // two exposed load latencies per chunk (ncu, P3 at 2 M DOFs: the kernel is bound by exposed load
+  // latency at 8-16 warps per SM, long-scoreboard 6-8 stall cycles per issued instruction).
   const std::int64_t len = live ? A.rowptr[row + 1] - A.rowptr[row] : 0;
   const bool bc_row = live && A.bc[row];
   double diag = 1.0;
-  constexpr int EB = 8;
+  constexpr int EB = 32;
   for (int k0 = 0; k0 < w; k0 += EB)
   {
     std::int32_t col[EB];
@@ -275,12 +291,10 @@ __global__ void assemble_matrix_pk3_binned(MatrixArgs A, const double* __restric
   constexpr double mu = 1.0e6 / (2.0 * (1.0 + 0.3));                       // Elasticity.py:12-15
   constexpr double lmbda = 1.0e6 * 0.3 / ((1.0 + 0.3) * (1.0 - 2.0 * 0.3));
   extern __shared__ double smem[];
-  double* St = smem;                 // [6][ND][ND]
-  double* Kt = smem + 6 * ND * ND;   // [9][ND][ND]
-  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
-    St[i] = Sg[i];
-  for (int i = threadIdx.x; i < 9 * ND * ND; i += blockDim.x)
-    Kt[i] = KFg[i];
+  double* St = smem;                          // [6][ND][LD]
+  double* Kt = smem + 6 * PkTab<ND>::PLANE;   // [9][ND][LD]
+  PkTab<ND>::stage(St, Sg, 6);
+  PkTab<ND>::stage(Kt, KFg, 9);
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
@@ -295,7 +309,7 @@ __global__ void assemble_matrix_pk3_binned(MatrixArgs A, const double* __restric
   const int w = static_cast<int>((A.mat_off[slice + 1] - mo) >> 5);
   const std::int64_t ao = A.adj_off[slice];
   const int wa = static_cast<int>((A.adj_off[slice + 1] - ao) >> 5);
-  double* acc = smem + 15 * ND * ND + static_cast<std::size_t>(warp) * bin_w * 96; // [k][b][lane]
+  double* acc = smem + 15 * PkTab<ND>::PLANE + static_cast<std::size_t>(warp) * bin_w * 96; // [k][b][lane]
   for (int k = 0; k < 3 * w; ++k)
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
@@ -327,17 +341,17 @@ __global__ void assemble_matrix_pk3_binned(MatrixArgs A, const double* __restric
     const double kz[3] = {c1.z * idet, c2.z * idet, c3.z * idet}; // u_2
     const double* ua = a == 0 ? kx : a == 1 ? ky : kz;
     const double ua0 = ua[0], ua1 = ua[1], ua2 = ua[2];
-    const double* S = St + li * ND;
-    const double* F = Kt + li * ND;
+    const double* S = St + li * PkTab<ND>::LD;
+    const double* F = Kt + li * PkTab<ND>::LD;
 #pragma unroll 2
     for (int j = 0; j < ND; ++j)
     {
-      const double kij = G00 * S[0 * ND * ND + j] + G01 * S[1 * ND * ND + j] + G02 * S[2 * ND * ND + j]
-                         + G11 * S[3 * ND * ND + j] + G12 * S[4 * ND * ND + j] + G22 * S[5 * ND * ND + j];
+      const double kij = G00 * S[0 * PkTab<ND>::PLANE + j] + G01 * S[1 * PkTab<ND>::PLANE + j] + G02 * S[2 * PkTab<ND>::PLANE + j]
+                         + G11 * S[3 * PkTab<ND>::PLANE + j] + G12 * S[4 * PkTab<ND>::PLANE + j] + G22 * S[5 * PkTab<ND>::PLANE + j];
       double f[9];
 #pragma unroll
       for (int q = 0; q < 9; ++q)
-        f[q] = F[q * ND * ND + j]; // KF[c][d], q = 3 c + d
+        f[q] = F[q * PkTab<ND>::PLANE + j]; // KF[c][d], q = 3 c + d
       // z_d = sum_c u_a[c] KF[c][d]  (M^{ab} = |det| z . u_b);  t_c = sum_d KF[c][d] u_a[d]  (M^{ba} = |det| u_b . t)
       const double z0 = ua0 * f[0] + ua1 * f[3] + ua2 * f[6], z1 = ua0 * f[1] + ua1 * f[4] + ua2 * f[7],
                    z2 = ua0 * f[2] + ua1 * f[5] + ua2 * f[8];
@@ -384,9 +398,8 @@ template <int ND>
 __global__ void __launch_bounds__(PK_THREADS)
 assemble_vector_pk3(VectorArgs A, const double* __restrict__ Mg)
 {
-  __shared__ double Mt[ND * ND];
-  for (int i = threadIdx.x; i < ND * ND; i += blockDim.x)
-    Mt[i] = Mg[i];
+  __shared__ double Mt[PkTab<ND>::PLANE];
+  PkTab<ND>::stage(Mt, Mg, 1);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
@@ -415,7 +428,7 @@ assemble_vector_pk3(VectorArgs A, const double* __restrict__ Mg)
 #pragma unroll
     for (int j = 0; j < ND; ++j)
     {
-      const double m = Mt[li * ND + j];
+      const double m = Mt[li * PkTab<ND>::LD + j];
       const double* fj = A.f + 3 * static_cast<std::int64_t>(__ldg(dofs + j));
       t0 += m * __ldg(fj), t1 += m * __ldg(fj + 1), t2 += m * __ldg(fj + 2);
     }
@@ -430,9 +443,8 @@ template <int ND>
 __global__ void __launch_bounds__(PK_THREADS)
 assemble_vector_pk(VectorArgs A, const double* __restrict__ Mg)
 {
-  __shared__ double Mt[ND * ND];
-  for (int i = threadIdx.x; i < ND * ND; i += blockDim.x)
-    Mt[i] = Mg[i];
+  __shared__ double Mt[PkTab<ND>::PLANE];
+  PkTab<ND>::stage(Mt, Mg, 1);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
@@ -460,7 +472,7 @@ assemble_vector_pk(VectorArgs A, const double* __restrict__ Mg)
     double s = 0.0;
 #pragma unroll
     for (int j = 0; j < ND; ++j)
-      s += Mt[li * ND + j] * __ldg(A.f + __ldg(dofs + j));
+      s += Mt[li * PkTab<ND>::LD + j] * __ldg(A.f + __ldg(dofs + j));
     sum += det * s;
   }
   A.b[row] = A.bc[row] ? 0.0 : sum;
@@ -507,10 +519,9 @@ __global__ void __launch_bounds__(PK_THREADS)
 action_pk(VectorArgs A, const double* __restrict__ Sg, const double* __restrict__ p,
           double* __restrict__ y, double* __restrict__ py_partials)
 {
-  extern __shared__ double St[]; // [6][ND][ND]
+  extern __shared__ double St[]; // [6][ND][LD]
   __shared__ double red[PK_THREADS / 32];
-  for (int i = threadIdx.x; i < 6 * ND * ND; i += blockDim.x)
-    St[i] = Sg[i];
+  PkTab<ND>::stage(St, Sg, 6);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const std::int32_t slice = blockIdx.x * (PK_THREADS / 32) + warp;
@@ -538,19 +549,19 @@ action_pk(VectorArgs A, const double* __restrict__ Sg, const double* __restrict_
       const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
                    G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
       const std::int32_t* dofs = A.dofmap + static_cast<std::int64_t>(cell) * ND;
-      const double* S = St + li * ND;
+      const double* S = St + li * PkTab<ND>::LD;
       double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, t5 = 0.0;
 #pragma unroll
       for (int j = 0; j < ND; ++j)
       {
         const std::int32_t dj = __ldg(dofs + j);
         const double pj = A.bc[dj] ? 0.0 : p[dj];
-        t0 += S[0 * ND * ND + j] * pj;
-        t1 += S[1 * ND * ND + j] * pj;
-        t2 += S[2 * ND * ND + j] * pj;
-        t3 += S[3 * ND * ND + j] * pj;
-        t4 += S[4 * ND * ND + j] * pj;
-        t5 += S[5 * ND * ND + j] * pj;
+        t0 += S[0 * PkTab<ND>::PLANE + j] * pj;
+        t1 += S[1 * PkTab<ND>::PLANE + j] * pj;
+        t2 += S[2 * PkTab<ND>::PLANE + j] * pj;
+        t3 += S[3 * PkTab<ND>::PLANE + j] * pj;
+        t4 += S[4 * PkTab<ND>::PLANE + j] * pj;
+        t5 += S[5 * PkTab<ND>::PLANE + j] * pj;
       }
       sum += ((G00 * t0 + G01 * t1) + (G02 * t2 + G11 * t3)) + (G12 * t4 + G22 * t5);
     }
@@ -588,28 +599,71 @@ void ensure_tables(ptb_ctx* c)
   c->tab_order = c->order;
 }
 
+// The launches of the row-length classes are independent (disjoint slices): launch(b, stream) of every
+// non-empty class goes to its own side stream between a fork and a join event on the context's
+// stream, so the classes with few, long rows (P3 vertex rows: 562 CTAs at one CTA per SM, 377 us at
+// 2 M DOFs, ncu profiles/r02/ncu_pk_binned_p3_2M.csv) run beside the large ones instead of after them.
+// PTB_PK_CONCURRENT=0 queues them on the context's stream one after the other.
+template <typename Launch>
+void run_bins(ptb_ctx* c, Launch launch)
+{
+  const std::size_t nb = c->pk_bin_off.empty() ? 0 : c->pk_bin_off.size() - 1;
+  if (!env_flag("PTB_PK_CONCURRENT", true))
+  {
+    for (std::size_t b = 0; b < nb; ++b)
+      if (c->pk_bin_off[b + 1] > c->pk_bin_off[b])
+        launch(b, c->stream);
+    return;
+  }
+  if (!c->bin_fork)
+  {
+    PTB_CUDA(cudaEventCreateWithFlags(&c->bin_fork, cudaEventDisableTiming));
+    for (int i = 0; i < ptb_ctx::N_BIN_STREAMS; ++i)
+    {
+      PTB_CUDA(cudaStreamCreateWithFlags(&c->bin_streams[i], cudaStreamNonBlocking));
+      PTB_CUDA(cudaEventCreateWithFlags(&c->bin_join[i], cudaEventDisableTiming));
+    }
+  }
+  PTB_CUDA(cudaEventRecord(c->bin_fork, c->stream));
+  bool used[ptb_ctx::N_BIN_STREAMS] = {};
+  // the classes with the longest rows first: they have the fewest CTAs and the longest tails
+  for (std::size_t b = nb; b-- > 0;)
+  {
+    if (c->pk_bin_off[b + 1] == c->pk_bin_off[b])
+      continue;
+    const int i = static_cast<int>(b % ptb_ctx::N_BIN_STREAMS);
+    if (!used[i])
+      PTB_CUDA(cudaStreamWaitEvent(c->bin_streams[i], c->bin_fork, 0));
+    used[i] = true;
+    launch(b, c->bin_streams[i]);
+  }
+  for (int i = 0; i < ptb_ctx::N_BIN_STREAMS; ++i)
+    if (used[i])
+    {
+      PTB_CUDA(cudaEventRecord(c->bin_join[i], c->bin_streams[i]));
+      PTB_CUDA(cudaStreamWaitEvent(c->stream, c->bin_join[i], 0));
+    }
+}
+
 template <int ND, bool WIDE>
 void launch_matrix_bins(ptb_ctx* c, const MatrixArgs& A)
 {
-  for (std::size_t b = 0; b + 1 < c->pk_bin_off.size(); ++b)
-  {
+  run_bins(c, [&](std::size_t b, cudaStream_t stream) {
     const std::int32_t n = c->pk_bin_off[b + 1] - c->pk_bin_off[b];
-    if (n == 0)
-      continue;
     const int bin_w = c->pk_bin_w[b];
     const std::size_t smem
-        = (static_cast<std::size_t>(6) * ND * ND + static_cast<std::size_t>(bin_w) * 32 * (PK_THREADS / 32))
+        = (static_cast<std::size_t>(6) * ND * (ND | 1) + static_cast<std::size_t>(bin_w) * 32 * (PK_THREADS / 32))
           * sizeof(double);
     if (smem > 227 * 1024)
       throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
     PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk_binned<ND, WIDE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = (n + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
-    assemble_matrix_pk_binned<ND, WIDE><<<grid, PK_THREADS, smem, c->stream>>>(
+    assemble_matrix_pk_binned<ND, WIDE><<<grid, PK_THREADS, smem, stream>>>(
         A, c->tab_S.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
     PTB_CUDA(cudaGetLastError());
     c->launches += 1;
-  }
+  });
 }
 
 template <int ND, bool WIDE>
@@ -619,23 +673,20 @@ void launch_matrix3_bins(ptb_ctx* c, const MatrixArgs& A)
     throw std::runtime_error("assemble_matrix: the elasticity P2/P3 kernel needs the row-length bins");
   PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk3_binned<ND, WIDE>,
                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  for (std::size_t b = 0; b + 1 < c->pk_bin_off.size(); ++b)
-  {
+  run_bins(c, [&](std::size_t b, cudaStream_t stream) {
     const std::int32_t n = c->pk_bin_off[b + 1] - c->pk_bin_off[b];
-    if (n == 0)
-      continue;
     const int bin_w = c->pk_bin_w[b];
-    const std::size_t tables_bytes = static_cast<std::size_t>(15) * ND * ND * sizeof(double);
+    const std::size_t tables_bytes = static_cast<std::size_t>(15) * ND * (ND | 1) * sizeof(double);
     const std::size_t per_warp = static_cast<std::size_t>(bin_w) * 96 * sizeof(double);
     if (tables_bytes + per_warp > 227 * 1024)
       throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
     const int warps = static_cast<int>(std::min<std::size_t>(4, (227 * 1024 - tables_bytes) / per_warp));
     const std::int64_t items = static_cast<std::int64_t>(n) * 3;
     const int grid = static_cast<int>((items + warps - 1) / warps);
-    assemble_matrix_pk3_binned<ND, WIDE><<<grid, warps * 32, tables_bytes + per_warp * warps, c->stream>>>(
+    assemble_matrix_pk3_binned<ND, WIDE><<<grid, warps * 32, tables_bytes + per_warp * warps, stream>>>(
         A, c->tab_S.p, c->tab_KF.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
     PTB_CUDA(cudaGetLastError());
-  }
+  });
 }
 
 template <int ND>
@@ -659,7 +710,7 @@ void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
     return;
   }
   const std::size_t smem
-      = (static_cast<std::size_t>(6) * ND * ND + static_cast<std::size_t>(c->max_w) * 32 * (PK_THREADS / 32))
+      = (static_cast<std::size_t>(6) * ND * (ND | 1) + static_cast<std::size_t>(c->max_w) * 32 * (PK_THREADS / 32))
         * sizeof(double);
   if (smem > 227 * 1024)
     throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
@@ -701,12 +752,12 @@ void launch_action_matrix_free_pk(ptb_ctx* c, const VectorArgs& A, const double*
   c->mf_partials.alloc(static_cast<std::size_t>(grid));
   if (c->order == 2)
   {
-    const std::size_t smem = 6 * 10 * 10 * sizeof(double);
+    const std::size_t smem = 6 * 10 * 11 * sizeof(double);
     action_pk<10><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p, p, y, c->mf_partials.p);
   }
   else
   {
-    const std::size_t smem = 6 * 20 * 20 * sizeof(double);
+    const std::size_t smem = 6 * 20 * 21 * sizeof(double);
     action_pk<20><<<grid, PK_THREADS, smem, c->stream>>>(A, c->tab_S.p, p, y, c->mf_partials.p);
   }
   PTB_CUDA(cudaGetLastError());

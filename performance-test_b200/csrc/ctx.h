@@ -178,6 +178,11 @@ struct ptb_ctx
   std::vector<std::int32_t> pk_bin_off; // [n_bins + 1] into pk_bin_slices
   std::vector<int> pk_bin_w;            // accumulator width of each bin
   int tab_order = 0;
+  // side streams of the binned launches (assemble_pk.cu run_bins): the row-length classes are
+  // independent kernels, the small ones run beside the large ones; created on first use
+  static constexpr int N_BIN_STREAMS = 6;
+  cudaStream_t bin_streams[N_BIN_STREAMS] = {};
+  cudaEvent_t bin_fork = nullptr, bin_join[N_BIN_STREAMS] = {};
 
   // matrix-free operator mode (ptb_set_operator_mode) and its per-CTA dot partials
   int operator_mode = 0;
