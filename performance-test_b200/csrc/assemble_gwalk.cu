@@ -21,8 +21,10 @@ namespace ptb
 namespace
 {
 
-constexpr int GW_CHUNK = 8; // step words in flight per thread
-constexpr int GW_AHEAD = 4; // gathers in flight per thread (steps of lookahead); divides GW_CHUNK
+// step words in flight per thread: GW_CHUNK = 2 * AHEAD (the next chunk is requested AHEAD steps before its first use)
+// gathers in flight per thread (steps of lookahead) = template parameter AHEAD of the kernel. Measured
+// (profiles/r02/vector_gwalk_lookahead_ab.txt, Poisson 20 M DOFs): AHEAD 4 2.38 ms, AHEAD 8 3.26 ms
+// (142 registers instead of 102) -> 4; PTB_GWALK_AHEAD=8 keeps the other instantiation reachable.
 
 // A vertex in flight: the two 16-byte halves of its padded coordinates (+ the source term).
 template <int NF>
@@ -75,13 +77,14 @@ __device__ __forceinline__ StepBits gw_decode(std::uint32_t word)
 // 1.06 ms at 10 M DOFs). Warps are independent (each keeps its own copy of the column list:
 // 1.9 KB), no barrier, no accumulators in shared memory.
 // ------------------------------------------------------------------------------------------
-template <int BS, int WARPS>
+template <int BS, int WARPS, int GW_AHEAD = 4>
 __global__ void __launch_bounds__(WARPS * 32)
 assemble_vector_p1_gwalk(VectorArgs A, const std::uint32_t* __restrict__ walk1,
                          const std::int64_t* __restrict__ walk1_off)
 {
   extern __shared__ double smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int GW_CHUNK = 2 * GW_AHEAD;
   const std::int32_t slice = blockIdx.x * WARPS + warp;
   if (slice >= A.n_slices)
     return;
@@ -197,7 +200,8 @@ template <int BS, int WARPS>
 void launch_vector_gwalk(ptb_ctx* c, const VectorArgs& A)
 {
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 32 * sizeof(std::int32_t) * WARPS;
-  auto kernel = assemble_vector_p1_gwalk<BS, WARPS>;
+  auto kernel = env_int("PTB_GWALK_AHEAD", 4) == 8 ? assemble_vector_p1_gwalk<BS, WARPS, 8>
+                                                   : assemble_vector_p1_gwalk<BS, WARPS, 4>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const std::int64_t warps = A.n_slices;
   kernel<<<static_cast<unsigned>((warps + WARPS - 1) / WARPS), WARPS * 32, smem, c->stream>>>(A, c->walk1.p, c->walk1_off.p);
