@@ -100,7 +100,7 @@ std::int64_t ptb_ctx::device_bytes() const
 {
   return xyz.bytes() + xyz3.bytes() + x_dofmap.bytes() + dofmap.bytes() + bc.bytes() + rowptr.bytes()
          + mat_off.bytes() + adj_off.bytes() + cols.bytes() + vals.bytes() + adj.bytes()
-         + adjso.bytes() + adjrot.bytes() + walk.bytes() + ring.bytes() + ring_off.bytes() + ring_ns.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
+         + cell_g.bytes() + adjso.bytes() + adjrot.bytes() + walk.bytes() + ring.bytes() + ring_off.bytes() + ring_ns.bytes() + walk1.bytes() + walk1_off.bytes() + xdof.bytes() + dof_vertex.bytes() + frow_ids.bytes() + frow_ptr.bytes() + fent.bytes() + f.bytes()
          + g.bytes() + b.bytes() + dinv.bytes() + ones.bytes() + x.bytes() + p.bytes() + r.bytes()
          + y.bytes() + cg.bytes() + partials.bytes() + tickets.bytes() + send_idx.bytes()
          + recv_idx.bytes() + send_buf.bytes() + recv_buf.bytes() + peer.window.bytes() + slice_order.bytes() + cdelta.bytes() + colsx.bytes() + xoff.bytes() + zcnt_w.bytes() + zcnt_x.bytes() + mat_off_z.bytes() + xoff_z.bytes() + vals_z.bytes() + cdelta_z.bytes() + colsx_z.bytes()

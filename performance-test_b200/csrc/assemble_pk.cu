@@ -143,12 +143,36 @@ assemble_matrix_pk(MatrixArgs A, const double* __restrict__ Sg)
     A.dinv[row] = 1.0 / diag;
 }
 
+// Geometry factors once per cell (the per-cell half of the element kernel): G = |det| K K^T and |det|
+// for every local cell, 64 bytes per cell, read by the (row, cell) pairs of the binned matrix kernel
+// instead of gathering four vertices and repeating ~60 FP64 instructions nd times per cell. Same
+// operations in the same order as the in-kernel geometry, so the assembled values do not change.
+__global__ void __launch_bounds__(256)
+cell_geometry_pk(std::int64_t n_cells, const std::int32_t* __restrict__ x_dofmap,
+                 const double* __restrict__ xyz, double* __restrict__ cell_g)
+{
+  const std::int64_t cell = static_cast<std::int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (cell >= n_cells)
+    return;
+  const int4 v = __ldg(reinterpret_cast<const int4*>(x_dofmap) + cell);
+  const Vec3 X0 = load_point(xyz, v.x);
+  const Vec3 e1 = load_point(xyz, v.y) - X0, e2 = load_point(xyz, v.z) - X0, e3 = load_point(xyz, v.w) - X0;
+  const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+  const double s = fabs(dot(e1, c1));
+  const double inv = 1.0 / s;
+  double2* out = reinterpret_cast<double2*>(cell_g + 8 * cell);
+  out[0] = double2{dot(c1, c1) * inv, dot(c1, c2) * inv};
+  out[1] = double2{dot(c1, c3) * inv, dot(c2, c2) * inv};
+  out[2] = double2{dot(c2, c3) * inv, dot(c3, c3) * inv};
+  out[3] = double2{s, 0.0};
+}
+
 // The same kernel over a list of slices whose rows are at most bin_w long: the accumulators are
 // sized by the bin, not by the longest row of the matrix. For P3 the vertex rows (175 columns)
 // pin the kernel above to ONE CTA of four warps per SM (198 KB of shared memory) although 26 of 27
 // rows are edge and face dofs with 20-60 columns; binned, those run at 8-16 warps per SM.
 // Opt-in (PTB_PK_BINS=1): written after the round's GPU budget was spent, host-executed only.
-template <int ND, bool WIDE>
+template <int ND, bool WIDE, bool CELLG = false>
 __global__ void __launch_bounds__(PK_THREADS)
 assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
                           const std::int32_t* __restrict__ slice_list, std::int32_t n_list, int bin_w)
@@ -175,9 +199,10 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
     acc[k * 32 + lane] = 0.0;
   __syncwarp();
 
-  // Cell loop, two cells per trip: the three dependent load levels of a cell (pair and slot words
-  // -> vertex ids -> coordinates) are issued for both cells before either is consumed.
-  constexpr int CB = 2;
+  // Cell loop, CB cells per trip: the dependent load levels of a cell (pair and slot words -> vertex
+  // ids -> coordinates; with CELLG pair and slot words -> the cell's geometry record) are issued for
+  // all CB cells before any is consumed.
+  constexpr int CB = CELLG ? 4 : 2;
   for (int k0 = 0; k0 < wa; k0 += CB)
   {
     std::uint32_t pair[CB], words[CB][NW];
@@ -190,33 +215,60 @@ assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,
       for (int q = 0; q < NW; ++q)
         words[u][q] = in ? A.adjso[(ao + (k0 + u) * 32) * NW + q * 32 + lane] : 0u;
     }
-    int4 v[CB];
     int li[CB];
-#pragma unroll
-    for (int u = 0; u < CB; ++u)
+    double G[CB][6];
+    if constexpr (CELLG)
     {
-      const std::uint32_t cell = pair[u] == ADJ_INVALID_DEV ? 0u : pair[u] / ND; // padding reads cell 0
-      li[u] = pair[u] == ADJ_INVALID_DEV ? 0 : static_cast<int>(pair[u] - cell * ND);
-      v[u] = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+      double2 g[CB][3];
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+      {
+        const std::uint32_t cell = pair[u] == ADJ_INVALID_DEV ? 0u : pair[u] / ND; // padding reads cell 0
+        li[u] = pair[u] == ADJ_INVALID_DEV ? 0 : static_cast<int>(pair[u] - cell * ND);
+        const double2* gp = reinterpret_cast<const double2*>(A.cell_g + 8 * static_cast<std::int64_t>(cell));
+        g[u][0] = __ldg(gp), g[u][1] = __ldg(gp + 1), g[u][2] = __ldg(gp + 2);
+      }
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+      {
+        G[u][0] = g[u][0].x, G[u][1] = g[u][0].y, G[u][2] = g[u][1].x;
+        G[u][3] = g[u][1].y, G[u][4] = g[u][2].x, G[u][5] = g[u][2].y;
+      }
     }
-    Vec3 X[CB][4];
-#pragma unroll
-    for (int u = 0; u < CB; ++u)
+    else
     {
-      X[u][0] = load_point(A.xyz, v[u].x), X[u][1] = load_point(A.xyz, v[u].y);
-      X[u][2] = load_point(A.xyz, v[u].z), X[u][3] = load_point(A.xyz, v[u].w);
+      int4 v[CB];
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+      {
+        const std::uint32_t cell = pair[u] == ADJ_INVALID_DEV ? 0u : pair[u] / ND; // padding reads cell 0
+        li[u] = pair[u] == ADJ_INVALID_DEV ? 0 : static_cast<int>(pair[u] - cell * ND);
+        v[u] = __ldg(reinterpret_cast<const int4*>(A.x_dofmap) + cell);
+      }
+      Vec3 X[CB][4];
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+      {
+        X[u][0] = load_point(A.xyz, v[u].x), X[u][1] = load_point(A.xyz, v[u].y);
+        X[u][2] = load_point(A.xyz, v[u].z), X[u][3] = load_point(A.xyz, v[u].w);
+      }
+#pragma unroll
+      for (int u = 0; u < CB; ++u)
+      {
+        const Vec3 e1 = X[u][1] - X[u][0], e2 = X[u][2] - X[u][0], e3 = X[u][3] - X[u][0];
+        // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
+        const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
+        const double inv = 1.0 / fabs(dot(e1, c1));
+        G[u][0] = dot(c1, c1) * inv, G[u][1] = dot(c1, c2) * inv, G[u][2] = dot(c1, c3) * inv;
+        G[u][3] = dot(c2, c2) * inv, G[u][4] = dot(c2, c3) * inv, G[u][5] = dot(c3, c3) * inv;
+      }
     }
 #pragma unroll
     for (int u = 0; u < CB; ++u)
     {
       if (pair[u] == ADJ_INVALID_DEV)
         continue;
-      const Vec3 e1 = X[u][1] - X[u][0], e2 = X[u][2] - X[u][0], e3 = X[u][3] - X[u][0];
-      // rows of K = J^-1 are c_b / det (c_b = cofactor vectors); G = |det| K K^T = c_b.c_c / |det|
-      const Vec3 c1 = cross(e2, e3), c2 = cross(e3, e1), c3 = cross(e1, e2);
-      const double inv = 1.0 / fabs(dot(e1, c1));
-      const double G00 = dot(c1, c1) * inv, G01 = dot(c1, c2) * inv, G02 = dot(c1, c3) * inv,
-                   G11 = dot(c2, c2) * inv, G12 = dot(c2, c3) * inv, G22 = dot(c3, c3) * inv;
+      const double G00 = G[u][0], G01 = G[u][1], G02 = G[u][2], G11 = G[u][3], G12 = G[u][4], G22 = G[u][5];
       const double* S = St + li[u] * PkTab<ND>::LD;
 #pragma unroll
       for (int j = 0; j < ND; ++j)
@@ -658,9 +710,15 @@ void launch_matrix_bins(ptb_ctx* c, const MatrixArgs& A)
       throw std::runtime_error("assemble_matrix: row too long for the shared-memory accumulators");
     PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk_binned<ND, WIDE>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PTB_CUDA(cudaFuncSetAttribute(assemble_matrix_pk_binned<ND, WIDE, true>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     const int grid = (n + PK_THREADS / 32 - 1) / (PK_THREADS / 32);
-    assemble_matrix_pk_binned<ND, WIDE><<<grid, PK_THREADS, smem, stream>>>(
-        A, c->tab_S.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
+    if (A.cell_g != nullptr)
+      assemble_matrix_pk_binned<ND, WIDE, true><<<grid, PK_THREADS, smem, stream>>>(
+          A, c->tab_S.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
+    else
+      assemble_matrix_pk_binned<ND, WIDE><<<grid, PK_THREADS, smem, stream>>>(
+          A, c->tab_S.p, c->pk_bin_slices.p + c->pk_bin_off[b], n, bin_w);
     PTB_CUDA(cudaGetLastError());
     c->launches += 1;
   });
@@ -702,10 +760,24 @@ void launch_matrix(ptb_ctx* c, const MatrixArgs& A)
   }
   if (env_flag("PTB_PK_BINS", true) && c->pk_bin_slices.p != nullptr)
   {
+    MatrixArgs B = A;
+    // Opt-in: measured on the B200 without gain (profiles/r02/assembly_pk_cellg_ab.txt: P3 1.246 vs
+    // 1.255 ms, P2 0.691 vs 0.676 ms at 2 M DOFs) -- the kernel waits on its index streams and its
+    // epilogue, not on the geometry chain.
+    if (env_flag("PTB_PK_CELLG", false))
+    {
+      // per-cell half of the element kernel first: geometry factors of every local cell
+      c->cell_g.alloc(static_cast<std::size_t>(c->n_cells) * 8);
+      cell_geometry_pk<<<static_cast<unsigned>((c->n_cells + 255) / 256), 256, 0, c->stream>>>(
+          c->n_cells, A.x_dofmap, A.xyz, c->cell_g.p);
+      PTB_CUDA(cudaGetLastError());
+      c->launches += 1;
+      B.cell_g = c->cell_g.p;
+    }
     if (c->so_bits == 8)
-      launch_matrix_bins<ND, false>(c, A);
+      launch_matrix_bins<ND, false>(c, B);
     else
-      launch_matrix_bins<ND, true>(c, A);
+      launch_matrix_bins<ND, true>(c, B);
     c->launches -= 1; // the caller counts one launch
     return;
   }

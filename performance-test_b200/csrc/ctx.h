@@ -178,6 +178,7 @@ struct ptb_ctx
   std::vector<std::int32_t> pk_bin_off; // [n_bins + 1] into pk_bin_slices
   std::vector<int> pk_bin_w;            // accumulator width of each bin
   int tab_order = 0;
+  ptb::DevBuf<double> cell_g;           // P2/P3 geometry factors per cell (assemble_pk.cu cell_geometry_pk)
   // side streams of the binned launches (assemble_pk.cu run_bins): the row-length classes are
   // independent kernels, the small ones run beside the large ones; created on first use
   static constexpr int N_BIN_STREAMS = 6;

@@ -34,6 +34,9 @@ struct MatrixArgs
   int max_w;
   double* vals;
   double* dinv;
+  // P2/P3: geometry factors per cell (assemble_pk.cu cell_geometry_pk), 8 doubles per cell:
+  // G00 G01 G02 G11 G12 G22 |det| 0; nullptr = the kernels compute them per (row, cell) pair
+  const double* cell_g = nullptr;
 };
 
 struct VectorArgs

@@ -66,13 +66,15 @@ void emu_launch(K kernel, unsigned grid, unsigned block, Args... args)
 
 extern "C" {
 
-// binned = 0: assemble_matrix_pk over all slices; 1: assemble_matrix_pk_binned, bin after bin
+// binned = 0: assemble_matrix_pk over all slices; 1: assemble_matrix_pk_binned, bin after bin;
+// 2: cell_geometry_pk over the n_cells cells, then assemble_matrix_pk_binned<.., CELLG> bin after bin
 int emu_assemble_matrix_pk(int binned, int nd, int so_bits, int32_t n_rows, int32_t n_slices,
                            int max_w, const double* xyz4, const int32_t* x_dofmap,
                            const uint8_t* bc, const int64_t* rowptr, const int64_t* mat_off,
                            const int64_t* adj_off, const int32_t* cols, const uint32_t* adj,
                            const uint32_t* adjso, int n_bins, const int32_t* bin_off,
-                           const int* bin_w, const int32_t* bin_slices, double* vals, double* dinv)
+                           const int* bin_w, const int32_t* bin_slices, double* vals, double* dinv,
+                           int64_t n_cells)
 {
   using namespace ptb;
   MatrixArgs A{};
@@ -83,8 +85,24 @@ int emu_assemble_matrix_pk(int binned, int nd, int so_bits, int32_t n_rows, int3
   auto run = [&](auto ND, auto WIDE) {
     constexpr int N = decltype(ND)::value;
     constexpr bool W = decltype(WIDE)::value;
+    std::vector<double> cell_g;
+    if (binned == 2)
+    {
+      cell_g.assign(static_cast<std::size_t>(n_cells) * 8, std::nan(""));
+      emu_launch(cell_geometry_pk, static_cast<unsigned>((n_cells + 255) / 256), 256, n_cells, x_dofmap, xyz4,
+                 cell_g.data());
+      A.cell_g = cell_g.data();
+    }
     if (!binned)
       emu_launch(assemble_matrix_pk<N, W>, (n_slices + 3) / 4, PK_THREADS, A, S);
+    else if (binned == 2)
+      for (int b = 0; b < n_bins; ++b)
+      {
+        const std::int32_t n = bin_off[b + 1] - bin_off[b];
+        if (n > 0)
+          emu_launch(assemble_matrix_pk_binned<N, W, true>, (n + 3) / 4, PK_THREADS, A, S,
+                     bin_slices + bin_off[b], n, bin_w[b]);
+      }
     else
       for (int b = 0; b < n_bins; ++b)
       {

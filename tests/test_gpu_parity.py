@@ -604,10 +604,15 @@ print("persistent ok")
     assert r.returncode == 0 and "persistent ok" in r.stdout, (r.stdout[-1000:], r.stderr[-2000:])
 
 
+@pytest.mark.parametrize("cellg,concurrent", [("0", "1"), ("1", "1"), ("0", "0")])
 @pytest.mark.parametrize("order,dims", [(2, (4, 3, 5)), (2, (9, 8, 10)), (3, (3, 4, 2)), (3, (6, 5, 7))])
-def test_binned_p2_p3_matrix_kernel_matches_oracle(pt, oracle, monkeypatch, order, dims):
+def test_binned_p2_p3_matrix_kernel_matches_oracle(pt, oracle, monkeypatch, order, dims, cellg, concurrent):
+    """Default (row-length classes on side streams, geometry per pair), with the geometry factors computed
+    once per cell (PTB_PK_CELLG=1), and with the classes queued one after the other."""
     P = pt.host.Problem("poisson", order, *dims)
     monkeypatch.setenv("PTB_PK_BINS", "1")
+    monkeypatch.setenv("PTB_PK_CELLG", cellg)
+    monkeypatch.setenv("PTB_PK_CONCURRENT", concurrent)
     c = pt.abi.Context(0)
     try:
         c.set_problem(P)

@@ -535,7 +535,7 @@ def emupk():
     return C.CDLL(out)
 
 
-@pytest.mark.parametrize("binned", [0, 1])
+@pytest.mark.parametrize("binned", [0, 1, 2])   # 2 = geometry factors once per cell (cell_geometry_pk) + binned
 @pytest.mark.parametrize("order,dims,rank,nranks", [(2, (3, 2, 4), 0, 1), (3, (2, 3, 2), 0, 1),
                                                     (3, (2, 2, 4), 1, 2)])
 def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, perturbed, order, dims, rank,
@@ -561,7 +561,8 @@ def test_p2_p3_matrix_kernel_sources_reproduce_the_oracle(pt, oracle, emupk, per
     rc = emupk.emu_assemble_matrix_pk(binned, P.nd, L["so_bits"], P.n_owned, L["n_slices"], L["max_w"],
                                       _p(xyz4), _p(xd), _p(bc), _p(rp), _p(L["mat_off"]), _p(L["adj_off"]),
                                       _p(L["cols"]), _p(L["adj"]), _p(L["adjso"]), L["n_bins"],
-                                      _p(L["bin_off"]), _p(L["bin_w"]), _p(L["bin_slices"]), _p(vals), _p(dinv))
+                                      _p(L["bin_off"]), _p(L["bin_w"]), _p(L["bin_slices"]), _p(vals), _p(dinv),
+                                      C.c_int64(len(xd) // 4))
     assert rc == 0 and not np.isnan(vals).any() and not np.isnan(dinv).any()
     got = _sell_to_csr(P, L, vals, 1)
     ref = oracle.assemble_matrix(P)
