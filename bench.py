@@ -419,8 +419,7 @@ def measure(pt, env, wl_name, args, steps, warmup, with_cpu, secondary=False):
     if rank == 0:
         wl = WORKLOADS[wl_name]
         walk3 = os.environ.get("PTB_ASM_WALK3", "1") != "0"
-        # edge-ring kernel: host-built maps only (device-generated problems keep the star walk)
-        ring = os.environ.get("PTB_ASM_RING", "1") != "0" and not device_setup
+        ring = os.environ.get("PTB_ASM_RING", "1") != "0"   # edge rings: host- or device-built maps
         walk = os.environ.get("PTB_ASM_WALK", "1") != "0"
         out = {
             "metric": "cg_dof_iters_per_s", "value": value, "unit": "DOF-iters/s",

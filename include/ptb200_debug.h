@@ -19,6 +19,13 @@ extern "C" {
 int ptb_get_p1_maps(ptb_ctx* ctx, int64_t* adj_off, uint32_t* adjrot, uint32_t* walk,
                     int* have_walk, int* built_on_device);
 
+/* The edge rings of the column-major elasticity P1 kernel as they sit on the device (needs the GPU):
+ * ring_off [n_slices + 1], ring_ns [mat_off[n_slices] / 32], ring [ring_off[n_slices]] (layout.h
+ * SellLayout::ring); any of the three may be NULL; *have_rings = 0 when the context holds none
+ * (scalar problem, PTB_ASM_RING=0, rows longer than 127 columns). Tests compare them with
+ * ptb_debug_p1_rings bit for bit for host-built and device-built (PTB_GPU_SETUP=1) maps. */
+int ptb_get_p1_rings(ptb_ctx* ctx, int64_t* ring_off, uint8_t* ring_ns, uint32_t* ring, int* have_rings);
+
 /* Round trip of the device matrix layout on the host (no GPU): builds the SELL-32 layout and the
  * compressed column indices from a CSR pattern, decodes them again into cols_out (CSR order) and
  * reports the fraction of indices that stayed explicit. Used by the CPU tests. */

@@ -83,6 +83,7 @@ def lib():
         L.ptb_debug_layout_roundtrip.argtypes = [i32, i64, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_get_slot_offsets.argtypes = [vp, C.POINTER(i64), vp, vp, vp]
         L.ptb_get_p1_maps.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ptb_get_p1_rings.argtypes = [vp, vp, vp, vp, C.POINTER(C.c_int)]
         L.ptb_debug_star_walk.argtypes = [i64, vp, i32, vp, vp, vp, C.POINTER(dbl)]
         L.ptb_debug_star_walk_single.argtypes = [i64, vp, i32, vp, vp, vp, vp]
         L.ptb_debug_facet_rows.argtypes = [i64, vp, vp, vp, C.c_int, C.c_int, i32, C.POINTER(i32),
@@ -540,6 +541,19 @@ class Context:
         self._check(lib().ptb_get_p1_maps(self._h, _ptr(adj_off), _ptr(adjrot), _ptr(walk), C.byref(hw),
                                           C.byref(dev)))
         return {"adj_off": adj_off, "adjrot": adjrot, "walk": walk, "built_on_device": bool(dev.value)}
+
+    def p1_rings(self, n_sell_entries):
+        """The edge rings downloaded from the device: (ring_off, ring_ns, ring) or None."""
+        ns = (self.n_owned + 31) // 32
+        ring_off = np.empty(ns + 1, dtype=np.int64)
+        ring_ns = np.empty(n_sell_entries // 32, dtype=np.uint8)
+        have = C.c_int()
+        self._check(lib().ptb_get_p1_rings(self._h, _ptr(ring_off), _ptr(ring_ns), None, C.byref(have)))
+        if not have.value:
+            return None
+        ring = np.empty(max(int(ring_off[-1]), 1), dtype=np.uint32)
+        self._check(lib().ptb_get_p1_rings(self._h, None, None, _ptr(ring), C.byref(have)))
+        return ring_off, ring_ns, ring
 
     # ---- instrumentation -------------------------------------------------------------------
     def stage_ms(self, stage):

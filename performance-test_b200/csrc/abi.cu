@@ -435,7 +435,7 @@ int ptb_set_pattern(ptb_ctx* c, const int64_t* rowptr, const int32_t* cols)
       // express (missing pair, offsets beyond a byte, a star of more than 64 cells) falls back to
       // the host build, which also owns the error messages.
       int max_wa = 0;
-      if (c->nd == 4 && L.max_w < 255 && gpu_setup_p1(c, want_walk(), &max_wa))
+      if (c->nd == 4 && L.max_w < 255 && gpu_setup_p1(c, want_walk(), c->bs == 3 && ring_enabled(), &max_wa))
       {
         c->max_wa = max_wa;
         c->adj.release(), c->adjso.release();
@@ -570,11 +570,10 @@ int ptb_build_pattern(ptb_ctx* c, int64_t* nnz)
         = (c->bs == 1 && walk_enabled() && c->max_w <= 32) || (c->bs == 3 && walk3_enabled());
     int max_wa = 0;
     c->walk.release();
-    c->ring.release(), c->ring_off.release(), c->ring_ns.release(); // host-built only: walk3 runs instead
     c->pk_bin_slices.release(), c->pk_bin_off.clear(), c->pk_bin_w.clear();
     if (c->nd == 4)
     {
-      if (c->max_w >= 255 || !gpu_setup_p1(c, want_walk, &max_wa))
+      if (c->max_w >= 255 || !gpu_setup_p1(c, want_walk, c->bs == 3 && ring_enabled(), &max_wa))
         return; // not expressible in one-byte offsets: ptb_set_pattern below rebuilds everything
       c->adj.release(), c->adjso.release();
     }
@@ -1173,6 +1172,24 @@ int ptb_get_p1_maps(ptb_ctx* c, int64_t* adj_off, uint32_t* adjrot, uint32_t* wa
       *have_walk = c->walk.p != nullptr;
     if (built_on_device)
       *built_on_device = c->maps_on_device;
+  });
+}
+
+int ptb_get_p1_rings(ptb_ctx* c, int64_t* ring_off, uint8_t* ring_ns, uint32_t* ring, int* have_rings)
+{
+  return guarded(c, [&] {
+    use_device(c);
+    need(c->have_pattern && have_rings != nullptr, "ptb_get_p1_rings: no pattern set / NULL have_rings");
+    *have_rings = c->ring.p != nullptr || (c->ring_off.p != nullptr && c->ring.n == 0);
+    if (!*have_rings)
+      return;
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    if (ring_off)
+      PTB_CUDA(cudaMemcpy(ring_off, c->ring_off.p, c->ring_off.bytes(), cudaMemcpyDeviceToHost));
+    if (ring_ns)
+      PTB_CUDA(cudaMemcpy(ring_ns, c->ring_ns.p, c->ring_ns.bytes(), cudaMemcpyDeviceToHost));
+    if (ring && c->ring.p)
+      PTB_CUDA(cudaMemcpy(ring, c->ring.p, c->ring.bytes(), cudaMemcpyDeviceToHost));
   });
 }
 

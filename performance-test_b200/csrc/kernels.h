@@ -110,7 +110,8 @@ void compact_operator(ptb_ctx* c);
 /// Device-side construction of the P1 assembly maps (setup.cu, opt-in PTB_GPU_SETUP=1): fills
 /// c->adj_off, c->adjrot and, if want_walk, c->walk from the uploaded dofmap, rowptr, mat_off and
 /// padded columns. Returns false when the pattern cannot be expressed (the caller builds on the host).
-bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa);
+/// want_rings: also c->ring, c->ring_off, c->ring_ns (edge rings of assemble_ring.cu; rows of at most 127 columns).
+bool gpu_setup_p1(ptb_ctx* c, bool want_walk, bool want_rings, int* max_wa);
 /// The same for P2/P3: c->adj_off, c->adj, c->adjso with 8-bit offsets (rows of at most 256 columns).
 bool gpu_setup_pk(ptb_ctx* c, int* max_wa);
 /// The sparsity pattern of the owned rows built on the device from the uploaded dofmap (setup.cu) and

@@ -556,6 +556,161 @@ __global__ void setup_walk(std::int32_t n_rows, std::int32_t n_slices,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Edge rings of layout.cpp build_rings (SellLayout::ring, the column-major elasticity kernel of
+// assemble_ring.cu) on the device, one thread per row, the same chains byte for byte: for column k
+// the cells that hold k as a chain of vertices; a chain starts at the lowest unvisited cell with a
+// vertex no other unvisited cell of the ring shares (that vertex first), else at the lowest
+// unvisited cell walking towards its lower face neighbour, and continues through the lowest
+// unvisited cell that holds the current vertex. Returns the number of bytes (<= 2 * cells).
+// ------------------------------------------------------------------------------------------
+__device__ inline int ring_chain(const std::uint32_t* o, int c, int k, std::uint8_t* bytes)
+{
+  std::uint8_t va[SU_MAX_CELLS], vb[SU_MAX_CELLS];
+  int n = 0;
+  for (int j = 0; j < c; ++j)
+    for (int t = 0; t < 3; ++t)
+      if (static_cast<int>((o[j] >> (8 * t)) & 0xFFu) == k)
+      {
+        va[n] = static_cast<std::uint8_t>((o[j] >> (8 * ((t + 1) % 3))) & 0xFFu);
+        vb[n] = static_cast<std::uint8_t>((o[j] >> (8 * ((t + 2) % 3))) & 0xFFu);
+        ++n;
+      }
+  unsigned long long used = 0ull;
+  auto degree = [&](int v) {
+    int d = 0;
+    for (int j = 0; j < n; ++j)
+      d += !((used >> j) & 1ull) && (va[j] == v || vb[j] == v) ? 1 : 0;
+    return d;
+  };
+  auto next_with = [&](int v, int skip) {
+    for (int j = 0; j < n; ++j)
+      if (!((used >> j) & 1ull) && j != skip && (va[j] == v || vb[j] == v))
+        return j;
+    return -1;
+  };
+  int left = n, nb = 0;
+  while (left > 0)
+  {
+    int start = -1, v0 = 0, v1 = 0;
+    for (int j = 0; j < n && start < 0; ++j)
+    {
+      if ((used >> j) & 1ull)
+        continue;
+      if (degree(va[j]) == 1)
+        start = j, v0 = va[j], v1 = vb[j];
+      else if (degree(vb[j]) == 1)
+        start = j, v0 = vb[j], v1 = va[j];
+    }
+    if (start < 0)
+    {
+      for (int j = 0; j < n && start < 0; ++j)
+        if (!((used >> j) & 1ull))
+          start = j;
+      const int ja = next_with(va[start], start), jb = next_with(vb[start], start);
+      if (ja <= jb)
+        v1 = va[start], v0 = vb[start];
+      else
+        v1 = vb[start], v0 = va[start];
+    }
+    bytes[nb++] = static_cast<std::uint8_t>(v0 | 0x80);
+    bytes[nb++] = static_cast<std::uint8_t>(v1);
+    used |= 1ull << start, --left;
+    int cur = v1;
+    for (int j = next_with(cur, -1); j >= 0; j = next_with(cur, -1))
+    {
+      cur = va[j] == cur ? vb[j] : va[j];
+      bytes[nb++] = static_cast<std::uint8_t>(cur);
+      used |= 1ull << j, --left;
+    }
+  }
+  return nb;
+}
+
+// PASS 0: ns32[mat_off[s]/32 + k] = longest chain of column k over the rows of slice s (atomicMax).
+// PASS 1: the chain bytes, four to a word, into ring at ring_off[s] + (words before column k + q)*32 + lane;
+// every word of the slice is written (padding 0x80). flags[1] is set when a row has more than
+// SU_MAX_CELLS cells or a chain of more than 255 bytes.
+template <int PASS>
+__global__ void setup_rings(std::int32_t n_rows, std::int32_t n_slices, const std::int64_t* __restrict__ ptr,
+                            const std::int64_t* __restrict__ rowptr, const std::int64_t* __restrict__ mat_off,
+                            const std::int64_t* __restrict__ adj_off, const std::uint32_t* __restrict__ adjrot,
+                            int* __restrict__ ns32, const std::uint8_t* __restrict__ ring_ns,
+                            const std::int64_t* __restrict__ ring_off, std::uint32_t* __restrict__ ring,
+                            int* __restrict__ flags)
+{
+  const std::int64_t t = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  const std::int32_t s = static_cast<std::int32_t>(t >> 5);
+  const int lane = static_cast<int>(t & 31);
+  if (s >= n_slices)
+    return;
+  const std::int32_t r = 32 * s + lane;
+  const bool live = r < n_rows;
+  const std::int64_t ao = adj_off[s];
+  int c = live ? static_cast<int>(ptr[r + 1] - ptr[r]) : 0;
+  const int len = live ? static_cast<int>(rowptr[r + 1] - rowptr[r]) : 0;
+  if (c > SU_MAX_CELLS)
+  {
+    flags[1] = 1;
+    c = 0;
+  }
+  std::uint32_t o[SU_MAX_CELLS]; // the three non-owner offsets of every cell (bytes 0..2)
+  for (int j = 0; j < c; ++j)
+    o[j] = adjrot[ao + static_cast<std::int64_t>(j) * 32 + lane] >> 8;
+  const std::int64_t k0 = mat_off[s] >> 5;
+  const int w = static_cast<int>((mat_off[s + 1] - mat_off[s]) >> 5);
+  std::uint8_t bytes[2 * SU_MAX_CELLS];
+  if constexpr (PASS == 0)
+  {
+    for (int k = 0; k < len; ++k)
+    {
+      const int nb = ring_chain(o, c, k, bytes);
+      if (nb > 255)
+        flags[1] = 1;
+      else if (nb > 0)
+        atomicMax(ns32 + k0 + k, nb);
+    }
+  }
+  else
+  {
+    std::int64_t base = ring_off[s] + lane;
+    for (int k = 0; k < w; ++k)
+    {
+      const int ns = ring_ns[k0 + k];
+      const int nw = (ns + 3) >> 2;
+      const int nb = (k < len && ns > 0) ? ring_chain(o, c, k, bytes) : 0;
+      for (int q = 0; q < nw; ++q)
+      {
+        std::uint32_t word = 0;
+        for (int u = 0; u < 4; ++u)
+          word |= static_cast<std::uint32_t>(4 * q + u < nb ? bytes[4 * q + u] : 0x80u) << (8 * u);
+        ring[base + static_cast<std::int64_t>(q) * 32] = word;
+      }
+      base += static_cast<std::int64_t>(nw) * 32;
+    }
+  }
+}
+
+// ring_ns (uint8) from the pass-0 maxima and the ring words per lane of every slice.
+__global__ void setup_ring_words(std::int32_t n_slices, const std::int64_t* __restrict__ mat_off,
+                                 const int* __restrict__ ns32, std::uint8_t* __restrict__ ring_ns,
+                                 unsigned long long* __restrict__ words)
+{
+  const std::int64_t s = blockIdx.x * static_cast<std::int64_t>(blockDim.x) + threadIdx.x;
+  if (s >= n_slices)
+    return;
+  const std::int64_t k0 = mat_off[s] >> 5;
+  const int w = static_cast<int>((mat_off[s + 1] - mat_off[s]) >> 5);
+  unsigned long long n = 0;
+  for (int k = 0; k < w; ++k)
+  {
+    const int ns = ns32[k0 + k];
+    ring_ns[k0 + k] = static_cast<std::uint8_t>(ns);
+    n += static_cast<unsigned long long>((ns + 3) >> 2);
+  }
+  words[s] = n;
+}
+
 } // namespace
 
 #ifndef PTB_HOST_EMU // host side: device build only
@@ -754,7 +909,7 @@ bool gpu_setup_pk(ptb_ctx* c, int* max_wa)
   return h_flags[0] == 0;
 }
 
-bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
+bool gpu_setup_p1(ptb_ctx* c, bool want_walk, bool want_rings, int* max_wa)
 {
   const std::int32_t N = c->n_owned, S = c->n_slices;
   DevBuf<unsigned long long> wa;
@@ -786,12 +941,50 @@ bool gpu_setup_p1(ptb_ctx* c, bool want_walk, int* max_wa)
     c->walk.alloc(static_cast<std::size_t>(n_adj));
     setup_walk<<<gl, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, c->adj_off.p, c->adjrot.p, c->walk.p, flags.p);
   }
+  c->ring.release(), c->ring_off.release(), c->ring_ns.release();
+  c->ring_max_words = 0;
+  if (want_rings && c->max_w <= 127)
+  {
+    // edge rings of the column-major elasticity kernel (assemble_ring.cu), as layout.cpp build_rings
+    const std::size_t n_cols = c->cols.n / 32;
+    DevBuf<int> ns32;
+    DevBuf<unsigned long long> words;
+    ns32.alloc(n_cols);
+    ns32.zero(c->stream);
+    words.alloc(static_cast<std::size_t>(S));
+    c->ring_ns.alloc(n_cols);
+    c->ring_off.alloc(static_cast<std::size_t>(S) + 1);
+    setup_rings<0><<<gl, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, c->rowptr.p, c->mat_off.p, c->adj_off.p,
+                                                     c->adjrot.p, ns32.p, nullptr, nullptr, nullptr, flags.p);
+    setup_ring_words<<<(S + SU_THREADS - 1) / SU_THREADS, SU_THREADS, 0, c->stream>>>(S, c->mat_off.p, ns32.p,
+                                                                                     c->ring_ns.p, words.p);
+    device_scan(c, S, words.p, c->ring_off.p, 32);
+    std::int64_t n_ring = 0;
+    std::vector<unsigned long long> h_words(static_cast<std::size_t>(S));
+    PTB_CUDA(cudaMemcpyAsync(&n_ring, c->ring_off.p + S, sizeof(n_ring), cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaMemcpyAsync(h_words.data(), words.p, h_words.size() * sizeof(unsigned long long),
+                             cudaMemcpyDeviceToHost, c->stream));
+    PTB_CUDA(cudaStreamSynchronize(c->stream));
+    for (unsigned long long v : h_words)
+      c->ring_max_words = std::max(c->ring_max_words, static_cast<int>(v));
+    c->ring.alloc(static_cast<std::size_t>(n_ring));
+    setup_rings<1><<<gl, SU_THREADS, 0, c->stream>>>(N, S, ptr.p, c->rowptr.p, c->mat_off.p, c->adj_off.p,
+                                                     c->adjrot.p, nullptr, c->ring_ns.p, c->ring_off.p, c->ring.p,
+                                                     flags.p);
+    c->ring_bytes_per_row = N ? 4.0 * static_cast<double>(n_ring) / N : 0.0; // padded words, not chain bytes
+    c->launches += 3;
+  }
   PTB_CUDA(cudaGetLastError());
   int h_flags[2] = {0, 0};
   PTB_CUDA(cudaMemcpyAsync(h_flags, flags.p, sizeof(h_flags), cudaMemcpyDeviceToHost, c->stream));
   PTB_CUDA(cudaStreamSynchronize(c->stream));
   c->launches += want_walk ? 3 : 2;
-  return h_flags[0] == 0 && h_flags[1] == 0;
+  if (h_flags[0] != 0 || h_flags[1] != 0)
+  {
+    c->ring.release(), c->ring_off.release(), c->ring_ns.release();
+    return false;
+  }
+  return true;
 }
 #endif // PTB_HOST_EMU
 

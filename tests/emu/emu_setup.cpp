@@ -29,6 +29,14 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
 {
   return __atomic_fetch_add(p, v, __ATOMIC_RELAXED);
 }
+static inline int atomicMax(int* p, int v)
+{
+  int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED))
+  {
+  }
+  return old;
+}
 using std::max;
 using std::min;
 
@@ -215,6 +223,44 @@ int emu_setup_p1(int64_t n_cells, const int32_t* dofmap, int32_t n_rows, int32_t
              flags);
   emu_launch(setup_walk, gl, SU_THREADS, n_rows, n_slices, (const std::int64_t*)ptr.data(),
              (const std::int64_t*)adj_off, (const std::uint32_t*)adjrot, walk, flags);
+  return 0;
+}
+
+// The ring part of gpu_setup_p1 (setup.cu): pairs -> adj_off / adjrot -> setup_rings<0> -> setup_ring_words
+// -> scan -> setup_rings<1>. ring_off [n_slices + 1] and ring_ns [mat_off[n_slices] / 32] are always
+// written; ring (capacity cap words) when the total fits (returns -1 otherwise). flags[0..1] as in setup.cu.
+int emu_setup_p1_rings(int64_t n_cells, const int32_t* dofmap, int32_t n_rows, int32_t n_slices,
+                       const int64_t* rowptr, const int64_t* mat_off, const int32_t* cols_sell, int shuffle,
+                       int64_t cap, int64_t* ring_off, uint8_t* ring_ns, uint32_t* ring, int* flags)
+{
+  using namespace ptb;
+  std::vector<unsigned long long> wa(static_cast<std::size_t>(n_slices), 0);
+  std::vector<std::int64_t> ptr, adj_off(static_cast<std::size_t>(n_slices) + 1, -1);
+  std::vector<std::uint32_t> pairs;
+  emu_pairs(n_cells * 4, dofmap, n_rows, shuffle, ptr, pairs);
+  emu_launch(setup_widths, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_rows, n_slices,
+             (const std::int64_t*)ptr.data(), wa.data());
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)wa.data(), adj_off.data(), static_cast<std::int64_t>(32));
+  std::vector<std::uint32_t> adjrot(static_cast<std::size_t>(adj_off[n_slices]), 0xDEADBEEFu);
+  flags[0] = flags[1] = 0;
+  const unsigned gl = static_cast<unsigned>((static_cast<std::int64_t>(n_slices) * 32 + SU_THREADS - 1) / SU_THREADS);
+  emu_launch(setup_adjrot, gl, SU_THREADS, n_rows, n_slices, dofmap, rowptr, mat_off, cols_sell,
+             (const std::int64_t*)ptr.data(), (const std::uint32_t*)pairs.data(), (const std::int64_t*)adj_off.data(),
+             adjrot.data(), flags);
+  const std::size_t n_cols = static_cast<std::size_t>(mat_off[n_slices] / 32);
+  std::vector<int> ns32(n_cols, 0);
+  std::vector<unsigned long long> words(static_cast<std::size_t>(n_slices), 0);
+  emu_launch(setup_rings<0>, gl, SU_THREADS, n_rows, n_slices, (const std::int64_t*)ptr.data(), rowptr, mat_off,
+             (const std::int64_t*)adj_off.data(), (const std::uint32_t*)adjrot.data(), ns32.data(),
+             (const std::uint8_t*)nullptr, (const std::int64_t*)nullptr, (std::uint32_t*)nullptr, flags);
+  emu_launch(setup_ring_words, (n_slices + SU_THREADS - 1) / SU_THREADS, SU_THREADS, n_slices, mat_off,
+             (const int*)ns32.data(), ring_ns, words.data());
+  emu_scan(static_cast<std::int64_t>(n_slices), (const unsigned long long*)words.data(), ring_off, static_cast<std::int64_t>(32));
+  if (ring_off[n_slices] > cap)
+    return -1;
+  emu_launch(setup_rings<1>, gl, SU_THREADS, n_rows, n_slices, (const std::int64_t*)ptr.data(), rowptr, mat_off,
+             (const std::int64_t*)adj_off.data(), (const std::uint32_t*)adjrot.data(), (int*)nullptr,
+             (const std::uint8_t*)ring_ns, (const std::int64_t*)ring_off, ring, flags);
   return 0;
 }
 }

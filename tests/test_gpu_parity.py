@@ -736,8 +736,13 @@ def test_device_setup_builds_the_host_maps(pt, oracle, monkeypatch, ptype, dims)
         assert np.array_equal(M["adjrot"], L["adjrot"])
         if M["walk"] is not None:
             assert np.array_equal(M["walk"], L["walk"])
+        if ptype == "elasticity":             # the edge rings of the default matrix kernel, device-built
+            ro, rn, rg = pt.abi.p1_rings(P["dofmap"], P.n_owned, P["rowptr"], P["cols"], int(L["mat_off"][-1]))
+            d_ro, d_rn, d_rg = c.p1_rings(int(L["mat_off"][-1]))
+            assert np.array_equal(d_ro, ro) and np.array_equal(d_rn, rn)
+            assert np.array_equal(d_rg[:int(ro[-1])], rg[:int(ro[-1])])
         else:
-            assert ptype == "elasticity"      # its walk kernel is a separate opt-in (PTB_ASM_WALK3)
+            assert c.p1_rings(int(L["mat_off"][-1])) is None
         c.assemble_matrix()
         c.assemble_vector()
         _check_matrix(P, c.matrix_values(), oracle.assemble_matrix(P))

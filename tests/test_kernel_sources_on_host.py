@@ -787,6 +787,29 @@ def test_device_setup_source_builds_the_host_maps_bit_for_bit(pt, emusu, ptype, 
     assert np.array_equal(walk, L["walk"])
 
 
+@pytest.mark.parametrize("shuffle", [0, 1])
+@pytest.mark.parametrize("dims,rank,nranks", [((3, 4, 3), 0, 1), ((1, 1, 1), 0, 1), ((2, 2, 5), 1, 2), ((33, 2, 1), 0, 1),
+                                              ((3, 3, 7), 2, 3), ((12, 11, 13), 0, 1)])
+def test_device_setup_source_builds_the_host_edge_rings_bit_for_bit(pt, emusu, dims, rank, nranks, shuffle):
+    """ring_off, ring_ns and the ring words of the column-major elasticity kernel built by the setup
+    kernels (setup.cu setup_rings<0/1>, setup_ring_words) equal layout.cpp build_rings word for word."""
+    P = pt.host.Problem("elasticity", 1, *dims, rank, nranks)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    ring_off, ring_ns, ring = pt.abi.p1_rings(P["dofmap"], P.n_owned, P["rowptr"], P["cols"], int(L["mat_off"][-1]))
+    S, cap = L["n_slices"], int(ring_off[-1])
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rp = np.ascontiguousarray(P["rowptr"], np.int64)
+    d_off = np.full(S + 1, -1, np.int64)
+    d_ns = np.full(len(ring_ns), 0xEE, np.uint8)
+    d_ring = np.full(max(cap, 1), 0xDEADBEEF, np.uint32)
+    flags = np.full(2, -1, np.int32)
+    rc = emusu.emu_setup_p1_rings(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]),
+                                  _p(L["cols"]), shuffle, C.c_int64(cap), _p(d_off), _p(d_ns), _p(d_ring), _p(flags))
+    assert rc == 0 and flags.tolist() == [0, 0]
+    assert np.array_equal(d_off, ring_off) and np.array_equal(d_ns, ring_ns)
+    assert np.array_equal(d_ring[:cap], ring[:cap])
+
+
 def test_device_setup_source_flags_a_pattern_that_misses_a_cell_pair(pt, emusu):
     """A (row, column) pair of a cell that is absent from the caller's pattern must raise flag 0
     (the host build refuses the pattern: ptb_set_pattern 'pair is missing')."""
