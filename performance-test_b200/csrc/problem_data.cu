@@ -13,8 +13,8 @@
 //                        are spelled with the non-contracting intrinsics, so the arguments of
 //                        exp / sin / sqrt are the host's bit for bit and the results differ from a
 //                        host libm by the functions' own rounding only (<= 2 ulp).
-// NOT YET RUN ON A GPU (written after the round's GPU budget was spent); tests/emu runs these
-// sources on the host against the stand-in's bc_dofs / f / g.
+// Run on the B200 since round 2 (GPU tests against the stand-in's bc_dofs / f / g); tests/emu also runs
+// these sources on the host.
 #include "kernels.h"
 
 namespace ptb

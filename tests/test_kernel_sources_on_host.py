@@ -1,9 +1,9 @@
 """The P1 walk kernels' *sources* executed on the host (tests/emu/emu_kernels.cpp): one std::thread
 per CUDA thread, a barrier for __syncthreads, a plain array for shared memory. This checks what the
 numpy restatements cannot: the kernels' own indexing, shared-memory layouts, register-position
-logic and epilogues -- for the default star-walk kernel (which has also run on the B200: if the
-harness and the GPU disagree the harness is wrong) and for the opt-in kernels that have not yet
-seen a GPU. CPU only; nothing here is part of the product path.
+logic and epilogues. Every kernel executed here has also run on the B200 (if the harness and the GPU
+disagree the harness is wrong); the harness is where new kernels are debugged before GPU time is
+spent on them. CPU only; nothing here is part of the product path.
 """
 import ctypes as C
 import os
