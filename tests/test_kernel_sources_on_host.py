@@ -607,6 +607,144 @@ def test_ring_kernel_source_is_partition_independent_off_the_diagonal(pt, emu):
             assert np.abs(parts[(r, c)] - blk).max() <= 1e-14 * np.abs(blk).max()
 
 
+# ---- an unstructured mesh: nothing of the Kuhn box's regularity --------------------------------------
+
+class _Unstructured:
+    """Delaunay tetrahedralisation of random points in the unit cube (scipy), vertices in random order:
+    stars of 8-40 cells, edge rings of 3-9 cells, fans on the hull, both orientations of the cells,
+    mixed ring lengths inside every slice. Slivers are dropped, which also leaves a few edges whose
+    cells form more than one fan (chain restarts). Duck-typed like pt.host.Problem for the oracle."""
+
+    def __init__(self, ptype, n_points, seed):
+        from scipy.spatial import Delaunay
+        rng = np.random.default_rng(seed)
+        corners = np.array([[i, j, k] for i in (0.0, 1.0) for j in (0.0, 1.0) for k in (0.0, 1.0)])
+        X = np.concatenate([corners, rng.uniform(0.0, 1.0, size=(n_points, 3))])
+        X = X[rng.permutation(len(X))]
+        tets = Delaunay(X).simplices.astype(np.int32)
+        E = X[tets[:, 1:]] - X[tets[:, :1]]
+        vol = np.abs(np.linalg.det(E)) / 6.0
+        h = np.linalg.norm(E, axis=2).max(axis=1)
+        tets = tets[vol > 0.02 * h ** 3]                     # no slivers
+        used = np.unique(tets)
+        assert len(used) == len(X)                           # every vertex keeps a cell
+        self.problem_type, self.order, self.bs = ptype, 1, (3 if ptype == "elasticity" else 1)
+        self.n_cells, self.n_owned, self.n_ghost, self.nd = len(tets), len(X), 0, 4
+        rows = [set() for _ in range(len(X))]
+        for t in tets:
+            for v in t:
+                rows[v].update(int(u) for u in t)
+        cols = [np.array(sorted(r), np.int32) for r in rows]
+        self._d = {"x": np.ascontiguousarray(X.reshape(-1)), "dof_x": np.ascontiguousarray(X.reshape(-1)),
+                   "x_dofmap": np.ascontiguousarray(tets.reshape(-1)), "dofmap": np.ascontiguousarray(tets.reshape(-1)),
+                   "rowptr": np.concatenate([[0], np.cumsum([len(c) for c in cols])]).astype(np.int64),
+                   "cols": np.concatenate(cols),
+                   "bc_dofs": np.flatnonzero(X[:, 0] < 0.15).astype(np.int32),
+                   "f": np.ascontiguousarray(rng.standard_normal(len(X) * self.bs)), "g": np.zeros(0),
+                   "facet_cells": np.zeros(0, np.int32), "facet_local": np.zeros(0, np.int32)}
+
+    def __getitem__(self, k):
+        return self._d[k]
+
+
+@pytest.mark.parametrize("seed,n_points", [(1, 60), (2, 150)])
+def test_ring_and_walk_kernel_sources_on_an_unstructured_mesh(pt, oracle, emu, seed, n_points):
+    """The elasticity matrix kernels (edge rings and star walk) and their host-built maps on a Delaunay
+    mesh: same oracle, same 1e-12 bound, and the two kernels agree with each other."""
+    P = _Unstructured("elasticity", n_points, seed)
+    ref = oracle.assemble_matrix(P)
+    scale = _row_diag(P, ref, 9)
+    # chains: for row i and column k the chain's cells are exactly the mesh cells that hold both
+    dm = P["dofmap"].reshape(-1, 4)
+    rp, cols = P["rowptr"], P["cols"]
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, rp, cols)
+    ring_off, ring_ns, ring = pt.abi.p1_rings(P["dofmap"], P.n_owned, rp, cols, int(L["mat_off"][-1]))
+    lens, restarts = [], 0
+    for r in range(P.n_owned):
+        s, lane = r >> 5, r & 31
+        k0, base = int(L["mat_off"][s]) // 32, int(ring_off[s]) + lane
+        row_cols = cols[rp[r]:rp[r + 1]]
+        mine = dm[(dm == r).any(axis=1)]
+        for k in range(int(L["mat_off"][s + 1] - L["mat_off"][s]) // 32):
+            ns = int(ring_ns[k0 + k])
+            by = [(int(ring[base + (t // 4) * 32]) >> (8 * (t % 4))) & 0xFF for t in range(ns)]
+            base += ((ns + 3) // 4) * 32
+            if k >= len(row_cols) or row_cols[k] == r:
+                assert all(b == 0x80 for b in by)
+                continue
+            while by and by[-1] == 0x80:
+                by.pop()
+            j = row_cols[k]
+            want = sorted(tuple(sorted(int(v) for v in c if v != r and v != j)) for c in mine if j in c)
+            got = [tuple(sorted((int(row_cols[by[t - 1] & 0x7F]), int(row_cols[by[t] & 0x7F]))))
+                   for t in range(1, len(by)) if not by[t] & 0x80]
+            assert sorted(got) == want
+            lens.append(len(want))
+            restarts += sum(1 for t in range(1, len(by)) if by[t] & 0x80)
+    assert min(lens) <= 2 and max(lens) >= 7            # nothing like the 4- and 6-rings of the Kuhn box
+    for warps in (1, 4):
+        Lr, vals, dinv = _ring_assemble(pt, emu, P, warps)
+        assert not np.isnan(vals).any()
+        ring_csr = _sell_to_csr(P, Lr, vals, 9)
+        assert (np.abs(ring_csr - ref) / scale).max() <= 1e-12
+    _, xdof, bc = _inputs(pt, P)
+    vals = np.full(int(L["mat_off"][-1]) * 9, np.nan)
+    dinv3 = np.full(P.n_owned * 3, np.nan)
+    rp64 = np.ascontiguousarray(rp)
+    assert emu.emu_assemble_matrix(2, P.n_owned, L["n_slices"], L["max_w"], 3, _p(bc), _p(rp64), _p(L["mat_off"]),
+                                   _p(L["adj_off"]), _p(L["cols"]), _p(xdof), _p(L["walk"]), _p(L["walk1"]),
+                                   _p(L["walk1_off"]), _p(vals), _p(dinv3)) == 0
+    walk_csr = _sell_to_csr(P, L, vals, 9)
+    assert (np.abs(walk_csr - ref) / scale).max() <= 1e-12
+    assert (np.abs(walk_csr - ring_csr) / scale).max() <= 1e-13
+    assert np.allclose(dinv, dinv3, rtol=1e-12, atol=0)
+
+
+@pytest.mark.parametrize("ptype,seed,n_points", [("poisson", 1, 60), ("poisson", 2, 150), ("elasticity", 3, 100)])
+def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emu, ptype, seed, n_points):
+    """The scalar star-walk matrix kernel (rows of at most 32 columns) and the P1 cell-vector kernel
+    (one thread per block row) on the Delaunay mesh, against the oracle."""
+    P = _Unstructured(ptype, n_points, seed)
+    L, xdof, bc = _inputs(pt, P)
+    assert L["max_w"] <= 32
+    rp64 = np.ascontiguousarray(P["rowptr"])
+    if ptype == "poisson":
+        ref = oracle.assemble_matrix(P)
+        vals, dinv = np.full(int(L["mat_off"][-1]), np.nan), np.full(P.n_owned, np.nan)
+        assert emu.emu_assemble_matrix(0, P.n_owned, L["n_slices"], L["max_w"], 1, _p(bc), _p(rp64), _p(L["mat_off"]),
+                                       _p(L["adj_off"]), _p(L["cols"]), _p(xdof), _p(L["walk"]), _p(L["walk1"]),
+                                       _p(L["walk1_off"]), _p(vals), _p(dinv)) == 0
+        assert (np.abs(_sell_to_csr(P, L, vals, 1) - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
+    b = np.full(P.n_owned * P.bs, np.nan)
+    f = np.ascontiguousarray(P["f"])
+    assert emu.emu_assemble_vector(P.bs, 4, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(L["mat_off"]),
+                                   _p(L["cols"]), _p(xdof), _p(f), _p(L["walk1"]), _p(L["walk1_off"]), _p(b)) == 0
+    b_ref = oracle.assemble_vector(P)
+    assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
+@pytest.mark.parametrize("seed,n_points", [(1, 60), (2, 150)])
+def test_device_ring_builder_source_on_an_unstructured_mesh(pt, emusu, seed, n_points):
+    """setup.cu setup_rings against layout.cpp build_rings on the Delaunay mesh (fans, restarts, rings of
+    3-9 cells): the same words, unless a star exceeds the device kernel's 64 cells -- then flag 1."""
+    P = _Unstructured("elasticity", n_points, seed)
+    L = pt.abi.p1_layout(P["dofmap"], P.n_owned, P["rowptr"], P["cols"])
+    ring_off, ring_ns, ring = pt.abi.p1_rings(P["dofmap"], P.n_owned, P["rowptr"], P["cols"], int(L["mat_off"][-1]))
+    S, cap = L["n_slices"], int(ring_off[-1])
+    dm, rp = np.ascontiguousarray(P["dofmap"], np.int32), np.ascontiguousarray(P["rowptr"], np.int64)
+    d_off, d_ns = np.full(S + 1, -1, np.int64), np.full(len(ring_ns), 0xEE, np.uint8)
+    d_ring, flags = np.full(max(cap, 1), 0xDEADBEEF, np.uint32), np.full(2, -1, np.int32)
+    rc = emusu.emu_setup_p1_rings(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]),
+                                  _p(L["cols"]), 1, C.c_int64(cap), _p(d_off), _p(d_ns), _p(d_ring), _p(flags))
+    star = np.bincount(dm, minlength=P.n_owned).max()
+    if star > 64:
+        assert flags[1] == 1
+        return
+    assert rc == 0 and flags.tolist() == [0, 0]
+    assert np.array_equal(d_off, ring_off) and np.array_equal(d_ns, ring_ns)
+    assert np.array_equal(d_ring[:cap], ring[:cap])
+
+
 # ---- P2 / P3 matrix kernels (csrc/assemble_pk.cu): all slices at once, and bin after bin -------------
 
 PK_SRC = os.path.join(HERE, "emu", "emu_pk.cpp")
@@ -904,6 +1042,14 @@ def test_device_setup_source_builds_the_host_edge_rings_bit_for_bit(pt, emusu, d
     assert rc == 0 and flags.tolist() == [0, 0]
     assert np.array_equal(d_off, ring_off) and np.array_equal(d_ns, ring_ns)
     assert np.array_equal(d_ring[:cap], ring[:cap])
+    # and the rotated slot words + star walk of setup_adjrot / setup_walk
+    capw = int(L["adj_off"][-1])
+    adj_off, adjrot, walk = np.full(S + 1, -1, np.int64), np.full(capw, 0xDEADBEEF, np.uint32), np.full(capw, 0xDEADBEEF, np.uint32)
+    flags[:] = -1
+    assert emusu.emu_setup_p1(C.c_int64(len(dm) // 4), _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]), _p(L["cols"]), 1,
+                              C.c_int64(capw), _p(adj_off), _p(adjrot), _p(walk), _p(flags)) == 0
+    assert flags.tolist() == [0, 0] and np.array_equal(adj_off, L["adj_off"])
+    assert np.array_equal(adjrot, L["adjrot"]) and np.array_equal(walk, L["walk"])
 
 
 def test_device_setup_source_flags_a_pattern_that_misses_a_cell_pair(pt, emusu):
