@@ -16,9 +16,11 @@
 //     cofactor vectors per cell, n_b of a cell is -n_a of its predecessor;
 //   * the material law is applied and the block stored (9 coalesced 256-byte lines) as soon as
 //     its ring is closed; the diagonal block follows from sum_j c_j = 0:  T_ii = -sum_{j != i} T_ij.
-// A cell is visited three times per row (once per non-owner vertex: 72 + 14 steps of ~39 FP64
-// instructions on the Kuhn box against 3 x 24 steps of ~40), but a step costs ~65 issue slots instead
-// of 3 x 150, and 16 warps per SM fit (13.4 KB of shared memory per slice: the star's edge vectors).
+// A cell is visited three times per row (once per non-owner vertex: 72 cell steps + 14 chain heads of
+// 36 FP64 instructions on the Kuhn box against 3 x 24 steps of ~40), but a step costs ~53 issue slots
+// instead of 3 x 150, and 14 one-warp CTAs per SM fit (15.1 KB of shared memory per slice: the star's
+// edge vectors 11.5 KB + the slice's ring words 3.6 KB, the latter staged by one TMA bulk copy).
+// Measured at 10 M DOFs: 1.02 ms against 2.26 ms (profiles/r02/assembly_ring_tma_ab.txt).
 // The chains follow the mesh topology and the ascending cell order only, so every off-diagonal block
 // is independent of the partition bit for bit; the diagonal block is summed in the row's local
 // column order (ghost columns last) and agrees across partitions to rounding (~4 ulp of |A_ii|).
