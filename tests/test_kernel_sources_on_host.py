@@ -615,7 +615,7 @@ class _Unstructured:
     mixed ring lengths inside every slice. Slivers are dropped, which also leaves a few edges whose
     cells form more than one fan (chain restarts). Duck-typed like pt.host.Problem for the oracle."""
 
-    def __init__(self, ptype, n_points, seed):
+    def __init__(self, ptype, n_points, seed, order=1):
         from scipy.spatial import Delaunay
         rng = np.random.default_rng(seed)
         corners = np.array([[i, j, k] for i in (0.0, 1.0) for j in (0.0, 1.0) for k in (0.0, 1.0)])
@@ -628,15 +628,32 @@ class _Unstructured:
         tets = tets[vol > 0.02 * h ** 3]                     # no slivers
         used = np.unique(tets)
         assert len(used) == len(X)                           # every vertex keeps a cell
-        self.problem_type, self.order, self.bs = ptype, 1, (3 if ptype == "elasticity" else 1)
-        self.n_cells, self.n_owned, self.n_ghost, self.nd = len(tets), len(X), 0, 4
-        rows = [set() for _ in range(len(X))]
-        for t in tets:
+        self.problem_type, self.order, self.bs = ptype, order, (3 if ptype == "elasticity" else 1)
+        dofmap, DX = tets, X
+        if order == 2:   # one dof per edge (midpoint), local dof 4 + e on edge e of the reference tetrahedron
+            tet_edges = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]
+            edge_id, mids, rowsd = {}, [], []
+            for t in tets:
+                loc = list(t)
+                for a, b in tet_edges:
+                    key = (min(t[a], t[b]), max(t[a], t[b]))
+                    if key not in edge_id:
+                        edge_id[key] = len(X) + len(edge_id)
+                        mids.append(0.5 * (X[key[0]] + X[key[1]]))
+                    loc.append(edge_id[key])
+                rowsd.append(loc)
+            dofmap, DX = np.array(rowsd, np.int32), np.concatenate([X, np.array(mids)])
+        else:
+            assert order == 1
+        self.n_cells, self.n_owned, self.n_ghost, self.nd = len(tets), len(DX), 0, dofmap.shape[1]
+        rows = [set() for _ in range(len(DX))]
+        for t in dofmap:
             for v in t:
                 rows[v].update(int(u) for u in t)
         cols = [np.array(sorted(r), np.int32) for r in rows]
-        self._d = {"x": np.ascontiguousarray(X.reshape(-1)), "dof_x": np.ascontiguousarray(X.reshape(-1)),
-                   "x_dofmap": np.ascontiguousarray(tets.reshape(-1)), "dofmap": np.ascontiguousarray(tets.reshape(-1)),
+        X_geo, X = X, DX
+        self._d = {"x": np.ascontiguousarray(X_geo.reshape(-1)), "dof_x": np.ascontiguousarray(DX.reshape(-1)),
+                   "x_dofmap": np.ascontiguousarray(tets.reshape(-1)), "dofmap": np.ascontiguousarray(dofmap.reshape(-1)),
                    "rowptr": np.concatenate([[0], np.cumsum([len(c) for c in cols])]).astype(np.int64),
                    "cols": np.concatenate(cols),
                    "bc_dofs": np.flatnonzero(X[:, 0] < 0.15).astype(np.int32),
@@ -721,6 +738,38 @@ def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracl
                                    _p(L["cols"]), _p(xdof), _p(f), _p(L["walk1"]), _p(L["walk1_off"]), _p(b)) == 0
     b_ref = oracle.assemble_vector(P)
     assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+
+
+@pytest.mark.parametrize("binned", [0, 1, 2])
+def test_p2_matrix_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emupk, binned):
+    """The P2 kernels (csrc/assemble_pk.cu: all slices, row-length classes, per-cell geometry pre-pass; cell
+    vector) and their host-built maps on the Delaunay mesh with one dof per edge."""
+    P = _Unstructured("poisson", 60, 5, order=2)
+    L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
+    nv = len(P["x"]) // 3
+    xyz4 = np.zeros((nv, 4))
+    xyz4[:, :3] = P["x"].reshape(-1, 3)
+    xyz4 = np.ascontiguousarray(xyz4.reshape(-1))
+    bc = np.zeros(P.n_owned, np.uint8)
+    bc[P["bc_dofs"]] = 1
+    vals, dinv = np.full(int(L["mat_off"][-1]), np.nan), np.full(P.n_owned, np.nan)
+    rp, xd, dm = np.ascontiguousarray(P["rowptr"]), np.ascontiguousarray(P["x_dofmap"]), np.ascontiguousarray(P["dofmap"])
+    rc = emupk.emu_assemble_matrix_pk(binned, P.nd, L["so_bits"], P.n_owned, L["n_slices"], L["max_w"], _p(xyz4), _p(xd),
+                                      _p(bc), _p(rp), _p(L["mat_off"]), _p(L["adj_off"]), _p(L["cols"]), _p(L["adj"]),
+                                      _p(L["adjso"]), L["n_bins"], _p(L["bin_off"]), _p(L["bin_w"]),
+                                      _p(L["bin_slices"]), _p(vals), _p(dinv), C.c_int64(P.n_cells))
+    assert rc == 0 and not np.isnan(vals).any() and not np.isnan(dinv).any()
+    ref = oracle.assemble_matrix(P)
+    assert (np.abs(_sell_to_csr(P, L, vals, 1) - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
+    if binned == 0:
+        b = np.full(P.n_owned, np.nan)
+        f = np.ascontiguousarray(P["f"])
+        empty = np.zeros(1, np.int32)
+        assert emupk.emu_assemble_vector_pk(P.nd, P.n_owned, L["n_slices"], _p(xyz4), _p(xd), _p(dm), _p(bc),
+                                            _p(L["adj_off"]), _p(L["adj"]), _p(f), 0, _p(empty), _p(empty), _p(empty),
+                                            None, _p(b)) == 0
+        b_ref = oracle.assemble_vector(P)
+        assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
 
 
 @pytest.mark.parametrize("seed,n_points", [(1, 60), (2, 150)])
