@@ -1348,6 +1348,48 @@ def test_device_setup_source_builds_the_p2_p3_slot_words(pt, emusu, order, dims,
     assert np.array_equal(adjso, L["adjso"])
 
 
+@pytest.mark.parametrize("order", [1, 2])
+def test_device_pattern_column_and_map_builders_on_an_unstructured_mesh(pt, emusu, order):
+    """ptb_build_pattern, gpu_setup_columns and gpu_setup_pk (setup.cu, emulated) on the Delaunay mesh:
+    the pattern equals the sorted union of the cells' dofs, the column side and the P2 pair / slot
+    words equal the host build word for word. (Nothing here is translation invariant: every column
+    index of the scalar operator goes explicit.)"""
+    P = _Unstructured("poisson", 90, 7, order=order)
+    dm = np.ascontiguousarray(P["dofmap"], np.int32)
+    rp, cl = np.ascontiguousarray(P["rowptr"], np.int64), np.ascontiguousarray(P["cols"], np.int32)
+    nnz = int(rp[-1])
+    rowptr, cols, flags3 = np.full(P.n_owned + 1, -1, np.int64), np.full(nnz, -1, np.int32), np.full(3, -1, np.int32)
+    rc = emusu.emu_build_pattern(C.c_int64(P.n_cells), P.nd, _p(dm), P.n_owned, C.c_int64(nnz), _p(rowptr), _p(cols),
+                                 _p(flags3))
+    if flags3[2] != 0:
+        pytest.skip("a row beyond the device pattern kernel's capacity: the product falls back to the host build")
+    assert rc == 0 and np.array_equal(rowptr, rp) and np.array_equal(cols, cl)
+    L = (pt.abi.p1_layout if order == 1 else lambda d, n, r, c: pt.abi.pk_layout(d, P.nd, n, r, c))(dm, P.n_owned, rp, cl)
+    S, cap = L["n_slices"], int(L["mat_off"][-1])
+    cd_ref, xoff_ref, cx_ref = pt.abi.compressed_columns(P.n_owned, P.n_owned, rp, cl, cap)
+    order_ref, ni_ref = pt.abi.slice_order(P.n_owned, rp, cl)
+    mat_off, xoff = np.full(S + 1, -1, np.int64), np.full(S + 1, -1, np.int64)
+    cols_sell, cdelta = np.full(cap, -7, np.int32), np.full(cap // 32, -7, np.int32)
+    capx = int(xoff_ref[-1])
+    colsx, so = np.full(max(capx, 1), -7, np.int32), np.full(S, -7, np.int32)
+    ni = C.c_int32(-1)
+    assert emusu.emu_setup_columns(P.n_owned, C.c_int64(P.n_owned), S, _p(rp), _p(cl), C.c_int64(cap), C.c_int64(capx),
+                                   _p(mat_off), _p(cols_sell), _p(cdelta), _p(xoff), _p(colsx), _p(so), C.byref(ni)) == 0
+    assert np.array_equal(mat_off, L["mat_off"]) and np.array_equal(cols_sell, L["cols"])
+    assert np.array_equal(cdelta, cd_ref) and np.array_equal(xoff, xoff_ref) and np.array_equal(colsx[:capx], cx_ref[:capx])
+    assert ni.value == ni_ref and np.array_equal(so, order_ref)
+    assert capx > 0.9 * cap                       # (almost) no translation-invariant column on this mesh
+    if order == 2:
+        capa = int(L["adj_off"][-1])
+        adj_off, adj = np.full(S + 1, -1, np.int64), np.full(capa, 0xDEADBEEF, np.uint32)
+        adjso, flags = np.full(capa * L["so_words"], 0xDEADBEEF, np.uint32), np.full(2, -1, np.int32)
+        assert L["so_bits"] == 8
+        assert emusu.emu_setup_pk(C.c_int64(P.n_cells), P.nd, _p(dm), P.n_owned, S, _p(rp), _p(L["mat_off"]), _p(L["cols"]),
+                                  C.c_int64(capa), _p(adj_off), _p(adj), _p(adjso), _p(flags)) == 0
+        assert flags.tolist() == [0, 0] and np.array_equal(adj_off, L["adj_off"])
+        assert np.array_equal(adj, L["adj"]) and np.array_equal(adjso, L["adjso"])
+
+
 @pytest.mark.parametrize("n,scale", [(1, 1), (1000, 32), (8192, 1), (8193, 1), (16384, 32), (20001, 1)])
 def test_device_scan_source_both_routes(emusu, n, scale):
     """The prefix sum of the setup kernels: one CTA up to a tile (8192 elements), three tile passes
