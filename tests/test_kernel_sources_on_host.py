@@ -643,6 +643,35 @@ class _Unstructured:
                     loc.append(edge_id[key])
                 rowsd.append(loc)
             dofmap, DX = np.array(rowsd, np.int32), np.concatenate([X, np.array(mids)])
+        elif order == 3:   # two dofs per edge (ordered from the lower global vertex), one per face
+            tets = np.sort(tets, axis=1)      # ascending vertices: every local edge runs low -> high, as in the Kuhn box
+            tet_edges = [(2, 3), (1, 3), (1, 2), (0, 3), (0, 2), (0, 1)]
+            tet_faces = [(1, 2, 3), (0, 2, 3), (0, 1, 3), (0, 1, 2)]
+            edge_id, face_id, rowsd = {}, {}, []
+            for t in tets:
+                loc = list(t)
+                for a, b in tet_edges:
+                    key = (t[a], t[b])
+                    if key not in edge_id:
+                        edge_id[key] = len(edge_id)
+                    loc += [len(X) + 2 * edge_id[key], len(X) + 2 * edge_id[key] + 1]
+                rowsd.append(loc)
+            ne = len(edge_id)
+            for t, loc in zip(tets, rowsd):
+                for fv in tet_faces:
+                    key = tuple(t[list(fv)])
+                    if key not in face_id:
+                        face_id[key] = len(face_id)
+                    loc.append(len(X) + 2 * ne + face_id[key])
+            # (the points only place the Dirichlet marker here: f is given per dof)
+            dofmap = np.array(rowsd, np.int32)
+            epts = np.zeros((2 * ne + len(face_id), 3))
+            for key, e in edge_id.items():
+                epts[2 * e] = (2 * X[key[0]] + X[key[1]]) / 3
+                epts[2 * e + 1] = (X[key[0]] + 2 * X[key[1]]) / 3
+            for key, f_ in face_id.items():
+                epts[2 * ne + f_] = X[list(key)].mean(axis=0)
+            DX = np.concatenate([X, epts])
         else:
             assert order == 1
         self.n_cells, self.n_owned, self.n_ghost, self.nd = len(tets), len(DX), 0, dofmap.shape[1]
@@ -740,11 +769,13 @@ def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracl
     assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
 
 
+@pytest.mark.parametrize("order", [2, 3])
 @pytest.mark.parametrize("binned", [0, 1, 2])
-def test_p2_matrix_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emupk, binned):
-    """The P2 kernels (csrc/assemble_pk.cu: all slices, row-length classes, per-cell geometry pre-pass; cell
-    vector) and their host-built maps on the Delaunay mesh with one dof per edge."""
-    P = _Unstructured("poisson", 60, 5, order=2)
+def test_p2_p3_matrix_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emupk, binned, order):
+    """The P2 / P3 kernels (csrc/assemble_pk.cu: all slices, row-length classes, per-cell geometry pre-pass;
+    cell vector) and their host-built maps on the Delaunay mesh: one dof per edge (P2); two per edge,
+    ordered from the lower global vertex, and one per face (P3)."""
+    P = _Unstructured("poisson", 60 if order == 2 else 40, 5 if order == 2 else 3, order=order)
     L = pt.abi.pk_layout(P["dofmap"], P.nd, P.n_owned, P["rowptr"], P["cols"])
     nv = len(P["x"]) // 3
     xyz4 = np.zeros((nv, 4))
