@@ -300,3 +300,28 @@ def test_patch_test_on_a_jittered_mesh(pt, oracle, nobc, perturbed, ptype, order
     rows = np.repeat(interior[:P0.n_owned], P0.bs)
     assert rows.any()
     assert np.abs(r[rows]).max() <= 1e-10 * np.abs(r).max()
+
+
+@pytest.mark.parametrize("ptype,dims", [("poisson", (7, 6, 8)), ("elasticity", (4, 5, 3))])
+def test_jacobi_cg_iterates_equal_scipys_preconditioned_cg(pt, oracle, ptype, dims):
+    """cg.h has no preconditioner; the Jacobi extension of the oracle (z = D^-1 r, alpha = r.z / p.Ap,
+    beta = r'.z' / r.z) is the textbook preconditioned CG. Pin it to an independent, widely
+    used implementation: after k iterations the oracle's x equals the k-th iterate of
+    scipy.sparse.linalg.cg with M = D^-1 (same recurrences, different code) to 1e-10, for several k,
+    and the converged solutions agree with a sparse direct solve."""
+    import scipy.sparse.linalg as spla
+    P = pt.host.Problem(ptype, 1, *dims)
+    bs, n = P.bs, P.n_owned * P.bs
+    vals, b = oracle.assemble_matrix(P), oracle.assemble_vector(P)
+    A = sp.csr_matrix(_csr(P, vals))[:, :n]
+    dinv = 1.0 / A.diagonal()
+    M = spla.LinearOperator((n, n), matvec=lambda r: dinv * r)
+    for k in (1, 2, 5, 17):
+        x_o, k_o, _ = oracle.cg(bs, P.n_owned, P["rowptr"], P["cols"], vals, b, kmax=k, rtol=1e-30, precond="jacobi")
+        iterates = []
+        spla.cg(A, b, x0=np.zeros(n), rtol=0.0, atol=0.0, maxiter=k, M=M, callback=lambda xk: iterates.append(xk.copy()))
+        assert k_o == k and len(iterates) == k
+        assert np.abs(x_o - iterates[-1]).max() <= 1e-10 * np.abs(iterates[-1]).max()
+    x_o, k_o, rel = oracle.cg(bs, P.n_owned, P["rowptr"], P["cols"], vals, b, kmax=5000, rtol=1e-10, precond="jacobi")
+    x_d = spla.spsolve(sp.csc_matrix(A), b)
+    assert rel < 1e-10 and np.abs(x_o - x_d).max() <= 1e-7 * np.abs(x_d).max()
