@@ -688,6 +688,15 @@ class _Unstructured:
                    "bc_dofs": np.flatnonzero(X[:, 0] < 0.15).astype(np.int32),
                    "f": np.ascontiguousarray(rng.standard_normal(len(X) * self.bs)), "g": np.zeros(0),
                    "facet_cells": np.zeros(0, np.int32), "facet_local": np.zeros(0, np.int32)}
+        if ptype == "poisson":   # g v ds over the exterior facets: the faces that belong to one cell only
+            faces = {}
+            for c, t in enumerate(tets):
+                for lf in range(4):   # local facet lf is opposite to local vertex lf
+                    faces.setdefault(tuple(sorted(int(v) for i, v in enumerate(t) if i != lf)), []).append((c, lf))
+            ext = sorted(v[0] for v in faces.values() if len(v) == 1)
+            self._d["facet_cells"] = np.array([c for c, _ in ext], np.int32)
+            self._d["facet_local"] = np.array([lf for _, lf in ext], np.int32)
+            self._d["g"] = np.ascontiguousarray(rng.standard_normal(len(X)))
 
     def __getitem__(self, k):
         return self._d[k]
@@ -747,7 +756,7 @@ def test_ring_and_walk_kernel_sources_on_an_unstructured_mesh(pt, oracle, emu, s
 
 
 @pytest.mark.parametrize("ptype,seed,n_points", [("poisson", 1, 60), ("poisson", 2, 150), ("elasticity", 3, 100)])
-def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emu, ptype, seed, n_points):
+def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracle, emu, emup1, ptype, seed, n_points):
     """The scalar star-walk matrix kernel (rows of at most 32 columns) and the P1 cell-vector kernel
     (one thread per block row) on the Delaunay mesh, against the oracle."""
     P = _Unstructured(ptype, n_points, seed)
@@ -765,8 +774,17 @@ def test_scalar_walk_and_vector_kernel_sources_on_an_unstructured_mesh(pt, oracl
     f = np.ascontiguousarray(P["f"])
     assert emu.emu_assemble_vector(P.bs, 4, P.n_owned, L["n_slices"], L["max_w"], _p(bc), _p(L["mat_off"]),
                                    _p(L["cols"]), _p(xdof), _p(f), _p(L["walk1"]), _p(L["walk1_off"]), _p(b)) == 0
+    assert not np.isnan(b).any()
+    if ptype == "poisson":   # + g v ds over the hull (assemble_facets_p1 through the facet-row lists)
+        assert len(P["facet_cells"]) > 20
+        ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], 4, 1, P.n_owned)
+        xyz4 = np.zeros((P.n_owned, 4))
+        xyz4[:, :3] = P["x"].reshape(-1, 3)
+        xyz4 = np.ascontiguousarray(xyz4.reshape(-1))
+        xd, dm, g = np.ascontiguousarray(P["x_dofmap"]), np.ascontiguousarray(P["dofmap"]), np.ascontiguousarray(P["g"])
+        assert emup1.emu_p1_facets(len(ids), _p(xyz4), _p(xd), _p(dm), _p(bc), _p(ids), _p(ptr), _p(ent), _p(g), _p(b)) == 0
     b_ref = oracle.assemble_vector(P)
-    assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
+    assert np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
 
 
 @pytest.mark.parametrize("order", [2, 3])
@@ -792,13 +810,14 @@ def test_p2_p3_matrix_and_vector_kernel_sources_on_an_unstructured_mesh(pt, orac
     assert rc == 0 and not np.isnan(vals).any() and not np.isnan(dinv).any()
     ref = oracle.assemble_matrix(P)
     assert (np.abs(_sell_to_csr(P, L, vals, 1) - ref) / _row_diag(P, ref, 1)).max() <= 1e-12
-    if binned == 0:
+    if binned == 0:   # cell vector + g v ds over the hull (assemble_vector_pk, assemble_facets_pk)
         b = np.full(P.n_owned, np.nan)
-        f = np.ascontiguousarray(P["f"])
-        empty = np.zeros(1, np.int32)
+        f, g = np.ascontiguousarray(P["f"]), np.ascontiguousarray(P["g"])
+        ids, ptr, ent = pt.abi.facet_rows(P["facet_cells"], P["facet_local"], P["dofmap"], P.nd, order, P.n_owned)
+        assert len(ids) > 20
         assert emupk.emu_assemble_vector_pk(P.nd, P.n_owned, L["n_slices"], _p(xyz4), _p(xd), _p(dm), _p(bc),
-                                            _p(L["adj_off"]), _p(L["adj"]), _p(f), 0, _p(empty), _p(empty), _p(empty),
-                                            None, _p(b)) == 0
+                                            _p(L["adj_off"]), _p(L["adj"]), _p(f), len(ids), _p(ids), _p(ptr), _p(ent),
+                                            _p(g), _p(b)) == 0
         b_ref = oracle.assemble_vector(P)
         assert not np.isnan(b).any() and np.abs(b - b_ref).max() <= 1e-12 * np.abs(b_ref).max()
 
